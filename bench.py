@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py -- SpMM GFLOP/s (2*nnz*N) and achieved HBM GB/s against the roofline.
+
+A "step" is one SpMM  C = alpha*A*B + beta*C  over the named workload.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+Workloads (BASELINE.json configs):
+  nasa4704   nasa4704.mtx  N=16 fp64   (configs[1]; the default)
+  pcrystk02  pcrystk02.mtx N=16 fp32   (configs[2]; --ncols 8|16|32|64)
+  uniform    synthetic M=K=1e6, 20 nnz/row, N=128 fp32      (configs[3])
+  powerlaw   synthetic power-law M=K=1e6, nnz~1e8, N=16 fp64 (configs[4])
+
+Own arm, per rank (one process per GPU): A's row block resident on the device; at N>1
+the matrix is N row blocks of the workload stacked (weak scaling), every rank owns one,
+and each step starts with the NCCL broadcast of B from rank 0 over NVLink.
+  value : steps timed with CUDA events on the launching stream, inputs resident in
+          HBM, L2 flushed (a 512 MB buffer is overwritten) before every step
+  e2e   : the same step through the host-facing C-ABI call sx_spmm_* with pinned host
+          B and C (column-major, as the host program holds them): H2D copies, layout
+          change, kernel, layout change, D2H copy -- all inside the timed region
+Reference arm (--impl reference): the CPU path (the reference's cpu_spmm_CSR when the
+run is fp32 and oracle/_ref is built, else the oracle port) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    #            kind         dtype        N
+    "nasa4704": ("suitesparse", np.float64, 16),
+    "pcrystk02": ("suitesparse", np.float32, 16),
+    "uniform": ("uniform", np.float32, 128),
+    "powerlaw": ("powerlaw", np.float64, 16),
+}
+ALPHA, BETA = float(np.float32(0.85)), float(np.float32(-2.06))   # host.cpp:29-30
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=50)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="native", choices=["native", "reference"])
+    p.add_argument("--workload", default="nasa4704", choices=sorted(WORKLOADS))
+    p.add_argument("--ncols", type=int, default=0, help="override the workload's N")
+    p.add_argument("--dtype", default="", choices=["", "f32", "f64"])
+    p.add_argument("--scale", type=float, default=1.0, help="shrink the synthetic workloads (testing)")
+    p.add_argument("--arith", default="strict", choices=["strict", "fast"])
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-flush", action="store_true", help="leave L2 warm between steps")
+    return p.parse_args()
+
+
+def build_workload(args):
+    """-> dict(name, M, K, nnz, N, dtype, rowptr, colidx, val, B, Cin) for ONE row block."""
+    import sextans_b200 as sx
+    from sextans_b200 import workloads as wl
+    kind, dtype, N = WORKLOADS[args.workload]
+    if args.dtype:
+        dtype = np.float32 if args.dtype == "f32" else np.float64
+    if args.ncols:
+        N = args.ncols
+    if kind == "suitesparse":
+        M, K, nnz, rp, ci, v = sx.load_mtx(wl.suitesparse_path(args.workload), dtype)
+        B, Cin = wl.host_dense(M, K, N, dtype)
+        desc = f"{args.workload}.mtx M=K={M} nnz={nnz} N={N} {np.dtype(dtype).name}, B=1, C_in=(m+1)(n+1)/M/N (host.cpp:100-111)"
+    elif kind == "uniform":
+        M = K = max(1000, int(1_000_000 * args.scale))
+        rp, ci, v = wl.uniform_csr(M, K, 20, 12345, dtype)
+        nnz = int(ci.size)
+        B, Cin = wl.random_dense(M, K, N, 12345, dtype)
+        desc = f"synthetic uniform CSR M=K={M} nnz={nnz} (20/row) N={N} {np.dtype(dtype).name}, seed 12345"
+    else:
+        M = K = max(1000, int(1_000_000 * args.scale))
+        rp, ci, v = wl.powerlaw_csr(M, K, int(100_000_000 * args.scale), 12345, dtype)
+        nnz = int(ci.size)
+        B, Cin = wl.random_dense(M, K, N, 12345, dtype)
+        desc = f"synthetic power-law CSR M=K={M} nnz={nnz} N={N} {np.dtype(dtype).name}, seed 12345"
+    return dict(name=args.workload, desc=desc, M=M, K=K, nnz=nnz, N=N, dtype=np.dtype(dtype),
+                rowptr=rp, colidx=ci, val=v, B=B, Cin=Cin)
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(name, N, dtype):
+    """dram bytes per launch of the SpMM kernel from the committed ncu capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return t.get(f"{name}_n{N}_{dtype}")
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi-equivalent clock / throttle-reason samples (NVML) during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        if self.is_alive():
+            self.join(timeout=1)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_baseline(w, threads, budget_s=12.0, min_runs=3):
+    """Time the CPU path on this workload (checker code, timed as a reported baseline).
+    fp32 + oracle/_ref present -> the reference's own cpu_spmm_CSR (1 thread, as written);
+    otherwise the oracle port, `threads` OpenMP threads over rows."""
+    import oracle
+    M, K, N, nnz = w["M"], w["K"], w["N"], w["nnz"]
+    rows_sample = None
+    # bound the work: if one full SpMM would take more than the budget (~2 GFLOP/s per
+    # thread), time a contiguous prefix of the rows with the same B
+    est = 2.0 * nnz * N / (1.5e9 * max(1, threads))
+    rp, ci, v = w["rowptr"], w["colidx"], w["val"]
+    Cin = w["Cin"]
+    if est > budget_s:
+        frac = budget_s / est
+        Ms = max(1, int(M * frac))
+        rows_sample = Ms
+        rp = np.ascontiguousarray(rp[:Ms + 1])
+        ci, v = ci[:rp[-1]], v[:rp[-1]]
+        Cin = np.ascontiguousarray(Cin.reshape(N, M)[:, :Ms]).ravel()
+        M = Ms
+        nnz = int(rp[-1])
+    use_ref = (w["dtype"] == np.float32 and threads == 1 and oracle.ref() is not None)
+    times = []
+    t_all = time.perf_counter()
+    while len(times) < min_runs or (time.perf_counter() - t_all < budget_s / 2 and len(times) < 20):
+        C = Cin.copy()
+        t0 = time.perf_counter()
+        if use_ref:
+            oracle.ref_spmm_csr(M, N, K, rp, ci, v, ALPHA, w["B"], BETA, C)
+        else:
+            oracle.spmm_csr(M, N, K, rp, ci, v, w["dtype"].type(ALPHA), w["B"], w["dtype"].type(BETA), C, threads=threads)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_all > budget_s * 2:
+            break
+    best = min(times)
+    sample = "the whole workload" if rows_sample is None else f"first {rows_sample} rows ({nnz} nnz) of the workload, full B"
+    return {"value": 2.0 * nnz * N / best / 1e9, "unit": "GFLOP/s", "cores": threads,
+            "kind": "reference" if use_ref else "port",
+            "sample": f"{sample}; best of {len(times)} runs, {best * 1e3:.3f} ms",
+            "ms": best * 1e3, "mean_ms": float(np.mean(times)) * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    w = build_workload(args)
+    threads = max(1, oracle.lib().sx_oracle_max_threads())
+    M, K, N, nnz = w["M"], w["K"], w["N"], w["nnz"]
+    est = 2.0 * nnz * N / (1.5e9 * threads)
+    rp, ci, v, Cin = w["rowptr"], w["colidx"], w["val"], w["Cin"]
+    sample = "the whole workload per step"
+    if est > 2.0:   # bounded sample: a row prefix sized to ~2 s per step
+        Ms = max(1, int(M * 2.0 / est))
+        rp = np.ascontiguousarray(rp[:Ms + 1])
+        ci, v = ci[:rp[-1]], v[:rp[-1]]
+        Cin = np.ascontiguousarray(Cin.reshape(N, M)[:, :Ms]).ravel()
+        M, nnz = Ms, int(rp[-1])
+        sample = f"first {Ms} rows ({nnz} nnz) of the workload per step, full B"
+    a, b = w["dtype"].type(ALPHA), w["dtype"].type(BETA)
+    for _ in range(args.warmup):
+        oracle.spmm_csr(M, N, K, rp, ci, v, a, w["B"], b, Cin.copy(), threads=threads)
+    total = 0.0
+    for _ in range(args.steps):
+        C = Cin.copy()
+        t0 = time.perf_counter()
+        oracle.spmm_csr(M, N, K, rp, ci, v, a, w["B"], b, C, threads=threads)
+        total += time.perf_counter() - t0
+    val = 2.0 * nnz * N * args.steps / total / 1e9
+    single = cpu_baseline(w, 1, budget_s=6.0)
+    line = {
+        "impl": "reference", "metric": "SpMM GFLOP/s (2*nnz*N)", "value": val, "unit": "GFLOP/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64" if w["dtype"] == np.float64 else "f32", "data": "synthetic" if w["name"] in ("uniform", "powerlaw") else "SuiteSparse fixture shipped with the reference, host program's B/C",
+        "config": {"workload": w["desc"], "alpha": ALPHA, "beta": BETA},
+        "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": threads, "kind": "port", "sample": sample,
+                         "note": "row-parallel OpenMP over the oracle port of cpu_spmm_CSR (bitwise the same result); "
+                                 "the reference function itself is single-threaded",
+                         "single_thread": single},
+        "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    import sextans_b200 as sx
+    from sextans_b200 import workloads as wl
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = build_workload(args)
+    M, K, N, nnz, dtype = w["M"], w["K"], w["N"], w["nnz"], w["dtype"]
+    tdtype = torch.float64 if dtype == np.float64 else torch.float32
+    s = dtype.itemsize
+
+    eng = sx.Engine(local, arith=sx.STRICT if args.arith == "strict" else sx.FAST)
+    stream = torch.cuda.Stream(device=dev)
+    eng.set_stream(stream.cuda_stream)
+    eng.upload_csr(M, K, w["rowptr"], w["colidx"], w["val"])
+
+    # ---- device-resident operands (row-major images, ld = N rounded up to 8) ----------
+    ld = (N + 7) // 8 * 8
+    with torch.cuda.stream(stream):
+        dB_cm = torch.from_numpy(w["B"]).to(dev)
+        dC_cm = torch.from_numpy(w["Cin"]).to(dev)
+        dB = torch.zeros(K * ld, dtype=tdtype, device=dev)
+        dCin = torch.zeros(M * ld, dtype=tdtype, device=dev)
+        dCout = torch.zeros(M * ld, dtype=tdtype, device=dev)
+        eng.colmajor_to_rowmajor(K, N, dB_cm, dB, ld)
+        eng.colmajor_to_rowmajor(M, N, dC_cm, dCin, ld)
+        if world > 1 and rank != 0:
+            dB.zero_()          # non-root ranks receive B through the broadcast
+        flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)
+    stream.synchronize()
+
+    def step_device():
+        if world > 1:
+            dist.broadcast(dB, src=0)
+        eng.spmm_device(N, ALPHA, dB, ld, BETA, dCin, dCout, ld)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(max(3, args.warmup)):
+            step_device()
+    barrier()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    # ---- timed: K steps, each bracketed by events on the launching stream ------------
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = eng.launches
+    barrier()
+    with torch.cuda.stream(stream):
+        for a, b in ev:
+            if not args.no_flush:
+                flush.zero_()
+            a.record(stream)
+            step_device()
+            b.record(stream)
+    barrier()
+    launches_dev = eng.launches - l0
+    dev_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(dev_ms))
+
+    # ---- steady state (L2 warm, back to back), for the launch-latency picture ---------
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            eng.spmm_device(N, ALPHA, dB, ld, BETA, dCin, dCout, ld)
+        e1.record(stream)
+    barrier()
+    warm_ms = e0.elapsed_time(e1) / args.steps
+
+    # ---- e2e: host-facing call, pinned host buffers -----------------------------------
+    hB = sx.pinned_empty(K * N, dtype)
+    hC = sx.pinned_empty(M * N, dtype)
+    hB[:] = w["B"]
+    for _ in range(3):
+        hC[:] = w["Cin"]
+        eng.spmm(N, ALPHA, hB, BETA, hC)
+    checksum = float(np.asarray(hC, dtype=np.float64).sum())
+    barrier()
+    l1 = eng.launches
+    e2e_s = 0.0
+    for _ in range(args.steps):
+        hC[:] = w["Cin"]                       # restore the in/out operand (untimed)
+        t0 = time.perf_counter()
+        eng.spmm(N, ALPHA, hB, BETA, hC)      # H2D B, H2D C, kernels, D2H C; returns synchronised
+        e2e_s += time.perf_counter() - t0
+    launches_e2e = eng.launches - l1
+    barrier()
+    clocks = sampler.result()
+
+    # ---- reduce over ranks: max time ---------------------------------------------------
+    t = torch.tensor([total_ms, e2e_s, warm_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_s, warm_ms = t.tolist()
+
+    flops_step = 2.0 * nnz * N * world
+    value = flops_step * args.steps / (total_ms * 1e-3) / 1e9
+    e2e = flops_step * args.steps / e2e_s / 1e9
+    alg_bytes = wl.algorithmic_bytes(M, K, nnz, N, s)
+    kern_ms = total_ms / args.steps       # N=1: the step is exactly one SpMM kernel launch
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+
+    if rank == 0:
+        line = {
+            "metric": "SpMM GFLOP/s (2*nnz*N)", "value": value, "unit": "GFLOP/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": kern_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64" if dtype == np.float64 else "f32",
+            "data": "synthetic" if w["name"] in ("uniform", "powerlaw") else "SuiteSparse fixture shipped with the reference, host program's B/C",
+            "config": {"workload": w["desc"], "alpha": ALPHA, "beta": BETA, "arith": args.arith,
+                       "l2": "warm (--no-flush)" if args.no_flush else "flushed: a 512 MB buffer is overwritten before every timed step",
+                       "partition": "1 row block" if world == 1 else f"{world} stacked row blocks, one per GPU; NCCL broadcast of B from rank 0 inside every step"},
+            "gflops_ref_formula": 2.0 * (nnz + M) * N * world * args.steps / (total_ms * 1e-3) / 1e9,
+            "steady_state_l2_warm": {"ms_per_step": warm_ms, "value": flops_step / (warm_ms * 1e-3) / 1e9,
+                                     "gbs": alg_bytes / (warm_ms * 1e-3) / 1e9},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": ncu_traffic(w["name"], N, "f64" if s == 8 else "f32"),
+                         "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
+                         "kernel": f"spmm_rows_kernel (variant {eng.info(sx.INFO_LAST_KERNEL)})"},
+            "e2e": {"value": e2e, "unit": "GFLOP/s", "ms_per_step": e2e_s / args.steps * 1e3,
+                    "h2d_bytes_per_step": (K * N + M * N) * s, "d2h_bytes_per_step": M * N * s,
+                    "timer": "host wall clock around the blocking sx_spmm_* call"},
+            "gpu_launches": int(launches_dev + launches_e2e),
+            "gpu_launches_detail": {"device_steps": int(launches_dev), "e2e_steps": int(launches_e2e)},
+            "clocks": clocks, "checksum_C": checksum,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(w, 1)
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)

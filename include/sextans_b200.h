@@ -1,0 +1,179 @@
+/*
+ * sextans_b200.h -- C ABI of the B200-native SpMM engine (libsextans_b200.so).
+ *
+ *   C = alpha * A * B + beta * C      A sparse M x K (CSR), B dense K x N, C dense M x N
+ *
+ * This is the drop-in boundary for the one device call of the Sextans host
+ * program.  Citations are relative to the reference tree (linghaosong/Sextans):
+ *
+ *   reference interface                                        replaced by
+ *   ---------------------------------------------------------  --------------------------
+ *   tapa::invoke(Sextans, bitstream, ptr, A[8], B[4], Cin[8],  sx_spmm_f32 / sx_spmm_f64
+ *     Cout[8], NUM_ITE, NUM_A_LEN, M, K, P_N, alpha_u, beta_u)
+ *     src/sextans-host.cpp:237-251, proto src/sextans.h:20-26
+ *   its return value (elapsed ns for all rp_time repeats)      *kernel_ns
+ *     src/sextans-host.cpp:237,252
+ *   P_N = (rp_time << 16) | N      src/sextans-host.cpp:223    int N, int rp_time
+ *   alpha_u / beta_u bit-casts     src/sextans-host.cpp:225-229 float/double alpha, beta
+ *   generate_edge_list_for_all_PEs + edge_list_64bit           sx_upload_csr_f32/_f64
+ *     (A -> device image) src/sextans-host.cpp:119-146           (CSR goes up as is)
+ *   B / C channel-image repacking  src/sextans-host.cpp:152-202 done on the device inside
+ *     and read-back un-interleave  src/sextans-host.cpp:264-270   sx_spmm_* (col-major in/out)
+ *   tapa::aligned_allocator<T>     src/sextans-host.cpp:23-24  sx_host_alloc / sx_host_free
+ *   env TAPAB (backend select)     src/sextans-host.cpp:231-234 int device of sx_create
+ *   read_suitsparse_matrix + CSC_2_CSR                         sx_load_mtx_f32/_f64
+ *     src/sparse_helper.h:169-259,475-509
+ *
+ * Dense operands at this boundary are exactly the host program's: column-major,
+ * B[k + K*n], C[m + M*n] (src/sextans-host.cpp:102,109; src/sparse_helper.h:283,287).
+ *
+ * Conventions: every function returns SX_OK (0) or a non-zero sx_status and never
+ * throws; sx_last_error() returns the text of the calling thread's last failure.
+ * Host pointers stay caller-owned.  One context drives one GPU; calls on one
+ * context must be serialised by the caller (the reference makes one blocking call
+ * from main).  There is NO CPU fallback: without a usable CUDA device sx_create
+ * fails with SX_ERR_NO_DEVICE.
+ */
+#ifndef SEXTANS_B200_H
+#define SEXTANS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SX_ABI_VERSION 1
+
+typedef struct sx_ctx sx_ctx;
+
+enum sx_status {
+    SX_OK = 0,
+    SX_ERR_INVALID = 1,   /* bad argument */
+    SX_ERR_CUDA = 2,      /* a CUDA runtime call failed; text in sx_last_error() */
+    SX_ERR_NO_DEVICE = 3, /* no CUDA device / ordinal out of range */
+    SX_ERR_STATE = 4,     /* call order: e.g. SpMM before sx_upload_csr_* */
+    SX_ERR_NOMEM = 5,
+    SX_ERR_IO = 6,        /* loader: cannot open / premature end */
+    SX_ERR_FORMAT = 7     /* loader: unsupported Matrix Market content */
+};
+
+enum sx_dtype { SX_F32 = 0, SX_F64 = 1 };
+
+enum sx_option {
+    /* 0 (default) "strict": every product and every sum separately rounded, each
+     * row's nonzeros accumulated in stored order -- bit-identical to cpu_spmm_CSR
+     * (src/sparse_helper.h:283,287) for rows up to SX_OPT_SPLIT_ROW_NNZ.
+     * 1 "fast": fused multiply-add. */
+    SX_OPT_ARITH = 0,
+    /* rows with more nonzeros than this are split across a whole thread block and
+     * tree-reduced (summation order differs from the oracle; error ~ 1e-7 fp32 /
+     * 1e-16 fp64 relative to the row's |a||b| sum).  0 disables splitting. */
+    SX_OPT_SPLIT_ROW_NNZ = 1,
+    /* 0 auto; otherwise force a kernel variant */
+    SX_OPT_KERNEL = 2
+};
+
+enum sx_info {
+    SX_INFO_LAUNCHES = 0,    /* kernels launched by this context so far */
+    SX_INFO_M = 1,
+    SX_INFO_K = 2,
+    SX_INFO_NNZ = 3,
+    SX_INFO_DTYPE = 4,
+    SX_INFO_SPLIT_ROWS = 5,  /* rows that take the split path */
+    SX_INFO_LAST_KERNEL = 6, /* variant id of the last SpMM launch */
+    SX_INFO_LD = 7           /* leading dimension (elements) of the context's row-major B/C */
+};
+
+/* ---- library ------------------------------------------------------------- */
+int sx_abi_version(void);
+const char *sx_last_error(void);
+const char *sx_status_name(int status);
+int sx_device_count(int *count);
+
+/* ---- context ------------------------------------------------------------- */
+int sx_create(int device, sx_ctx **out);
+int sx_destroy(sx_ctx *ctx);
+/* Run this context's work on an existing cudaStream_t (pass it as void*); NULL
+ * returns to the context's own stream. */
+int sx_set_stream(sx_ctx *ctx, void *cuda_stream);
+int sx_set_option(sx_ctx *ctx, int option, int64_t value);
+int sx_get_info(sx_ctx *ctx, int what, int64_t *value);
+int sx_synchronize(sx_ctx *ctx);
+
+/* ---- A: CSR upload (replaces the FPGA edge-list preprocessing) ------------ */
+/* rowptr has M+1 entries with rowptr[0] == 0 and rowptr[M] == nnz; column indices
+ * must lie in [0, K).  Rows keep their stored nonzero order (the loader's order is
+ * ascending column).  Re-uploading replaces the previous matrix. */
+int sx_upload_csr_f32(sx_ctx *ctx, int M, int K, int64_t nnz, const int32_t *rowptr,
+                      const int32_t *colidx, const float *val);
+int sx_upload_csr_f64(sx_ctx *ctx, int M, int K, int64_t nnz, const int32_t *rowptr,
+                      const int32_t *colidx, const double *val);
+
+/* ---- the SpMM call (replaces tapa::invoke(Sextans, ...)) ------------------ */
+/* B: K x N column-major (ld K), read only.  C: M x N column-major (ld M), in/out.
+ * The kernel is run rp_time times (rp_time < 1 is treated as 1, like
+ * src/sextans.cpp:52-54), every repeat starting from the ORIGINAL C (the FPGA
+ * re-reads mat_C_ch_in each repeat, src/sextans.cpp:143), so the result does not
+ * depend on rp_time.  *kernel_ns (may be NULL) receives the device time of all
+ * repeats together, measured with CUDA events on the context's stream; host<->
+ * device copies and layout changes are outside it, as the FPGA's DMA is outside
+ * the reference's figure. */
+int sx_spmm_f32(sx_ctx *ctx, int N, float alpha, const float *B, float beta, float *C,
+                int rp_time, double *kernel_ns);
+int sx_spmm_f64(sx_ctx *ctx, int N, double alpha, const double *B, double beta, double *C,
+                int rp_time, double *kernel_ns);
+
+/* ---- the same call in stages (what sx_spmm_* does internally) ------------- */
+int sx_stage_B_f32(sx_ctx *ctx, int N, const float *B_colmajor);
+int sx_stage_B_f64(sx_ctx *ctx, int N, const double *B_colmajor);
+int sx_stage_C_f32(sx_ctx *ctx, int N, const float *C_colmajor);
+int sx_stage_C_f64(sx_ctx *ctx, int N, const double *C_colmajor);
+int sx_launch_f32(sx_ctx *ctx, float alpha, float beta, int rp_time, double *kernel_ns);
+int sx_launch_f64(sx_ctx *ctx, double alpha, double beta, int rp_time, double *kernel_ns);
+int sx_fetch_C_f32(sx_ctx *ctx, float *C_colmajor);
+int sx_fetch_C_f64(sx_ctx *ctx, double *C_colmajor);
+/* Device address of the context's staged row-major B (K x ld, ld from SX_INFO_LD):
+ * the buffer a collective (NCCL broadcast over NVLink) fills on the non-root
+ * ranks.  Allocates it for N columns if needed. */
+int sx_device_B(sx_ctx *ctx, int N, void **dptr, size_t *bytes);
+
+/* ---- device-resident operands (stream-ordered, no copies, no sync) -------- */
+/* dB: K rows of ldb elements, dCin/dCout: M rows of ldc elements, all ROW-major
+ * device memory, 16-byte aligned, ldb/ldc multiples of 16/sizeof(T) elements and
+ * >= N.  dCin == dCout is allowed (in place).  Enqueues on the context's stream
+ * and returns. */
+int sx_spmm_device_f32(sx_ctx *ctx, int N, float alpha, const float *dB, int64_t ldb,
+                       float beta, const float *dCin, float *dCout, int64_t ldc);
+int sx_spmm_device_f64(sx_ctx *ctx, int N, double alpha, const double *dB, int64_t ldb,
+                       double beta, const double *dCin, double *dCout, int64_t ldc);
+/* Layout changes between the host program's column-major operands and the
+ * engine's row-major ones, on device memory, enqueued on the context's stream:
+ * src is rows x cols column-major (ld rows); dst is row-major with leading
+ * dimension ld_dst (columns cols..ld_dst-1 are zero-filled), and the reverse. */
+int sx_colmajor_to_rowmajor(sx_ctx *ctx, int dtype, int64_t rows, int cols, const void *d_src,
+                            void *d_dst, int64_t ld_dst);
+int sx_rowmajor_to_colmajor(sx_ctx *ctx, int dtype, int64_t rows, int cols, const void *d_src,
+                            int64_t ld_src, void *d_dst);
+
+/* ---- host-side helpers of the drop-in surface ----------------------------- */
+/* Page-locked host memory for B and C (stands in for tapa::aligned_allocator). */
+int sx_host_alloc(size_t bytes, void **ptr);
+int sx_host_free(void *ptr);
+/* Contiguous row blocks with ~equal nonzeros: bounds[0]=0 <= ... <= bounds[parts]=M.
+ * The GPU-count analogue of the reference's row -> PE map (src/sparse_helper.h:370). */
+int sx_partition_rows(int M, const int32_t *rowptr, int parts, int32_t *bounds);
+/* Matrix Market -> CSR with the reference loader's semantics (symmetric expansion,
+ * +0.0 entries dropped, 1-based -> 0-based, columns ascending within a row,
+ * duplicates kept).  Arrays are malloc'ed; release each with sx_free. */
+int sx_load_mtx_f32(const char *path, int *M, int *K, int64_t *nnz, int32_t **rowptr,
+                    int32_t **colidx, float **val);
+int sx_load_mtx_f64(const char *path, int *M, int *K, int64_t *nnz, int32_t **rowptr,
+                    int32_t **colidx, double **val);
+void sx_free(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEXTANS_B200_H */

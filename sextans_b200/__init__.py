@@ -1,0 +1,315 @@
+"""sextans_b200 -- B200-native SpMM engine behind the Sextans host call surface.
+
+``C = alpha * A @ B + beta * C`` for a CSR / Matrix-Market sparse ``A`` and a tall
+dense ``B``.  The product is ``libsextans_b200.so`` (hand-written sm_100a CUDA kernels
+behind the C ABI of ``include/sextans_b200.h``) and the ``sextans`` host program;
+this package is the thin Python mirror of that ABI used by the tests and the bench.
+
+There is no CPU path here: importing works anywhere (so that the ABI can be
+inspected), but creating an :class:`Engine` without the built library or without a
+CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+__all__ = ["Engine", "SextansError", "lib", "library_path", "load_mtx", "partition_rows",
+           "pinned_empty", "STRICT", "FAST"]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+SX_F32, SX_F64 = 0, 1
+STRICT, FAST = 0, 1
+OPT_ARITH, OPT_SPLIT_ROW_NNZ, OPT_KERNEL = 0, 1, 2
+INFO_LAUNCHES, INFO_M, INFO_K, INFO_NNZ, INFO_DTYPE, INFO_SPLIT_ROWS, INFO_LAST_KERNEL, INFO_LD = range(8)
+
+_PI32 = C.POINTER(C.c_int32)
+_PF = C.POINTER(C.c_float)
+_PD = C.POINTER(C.c_double)
+
+
+class SextansError(RuntimeError):
+    def __init__(self, status, text):
+        super().__init__(f"{text} [{status}]")
+        self.status = status
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libsextans_b200.so")
+
+
+def lib():
+    """The C ABI.  Raises if the CUDA library has not been built -- never falls back."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build it with `make -C sextans_b200/csrc` "
+                          "(or __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(path)
+    vp, i, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+    sig = {
+        "sx_abi_version": ([], i),
+        "sx_last_error": ([], C.c_char_p),
+        "sx_status_name": ([i], C.c_char_p),
+        "sx_device_count": ([C.POINTER(i)], i),
+        "sx_create": ([i, C.POINTER(vp)], i),
+        "sx_destroy": ([vp], i),
+        "sx_set_stream": ([vp, vp], i),
+        "sx_set_option": ([vp, i, i64], i),
+        "sx_get_info": ([vp, i, C.POINTER(i64)], i),
+        "sx_synchronize": ([vp], i),
+        "sx_upload_csr_f32": ([vp, i, i, i64, _PI32, _PI32, _PF], i),
+        "sx_upload_csr_f64": ([vp, i, i, i64, _PI32, _PI32, _PD], i),
+        "sx_spmm_f32": ([vp, i, C.c_float, vp, C.c_float, vp, i, _PD], i),
+        "sx_spmm_f64": ([vp, i, C.c_double, vp, C.c_double, vp, i, _PD], i),
+        "sx_stage_B_f32": ([vp, i, vp], i), "sx_stage_B_f64": ([vp, i, vp], i),
+        "sx_stage_C_f32": ([vp, i, vp], i), "sx_stage_C_f64": ([vp, i, vp], i),
+        "sx_launch_f32": ([vp, C.c_float, C.c_float, i, _PD], i),
+        "sx_launch_f64": ([vp, C.c_double, C.c_double, i, _PD], i),
+        "sx_fetch_C_f32": ([vp, vp], i), "sx_fetch_C_f64": ([vp, vp], i),
+        "sx_device_B": ([vp, i, C.POINTER(vp), C.POINTER(sz)], i),
+        "sx_spmm_device_f32": ([vp, i, C.c_float, vp, i64, C.c_float, vp, vp, i64], i),
+        "sx_spmm_device_f64": ([vp, i, C.c_double, vp, i64, C.c_double, vp, vp, i64], i),
+        "sx_colmajor_to_rowmajor": ([vp, i, i64, i, vp, vp, i64], i),
+        "sx_rowmajor_to_colmajor": ([vp, i, i64, i, vp, i64, vp], i),
+        "sx_host_alloc": ([sz, C.POINTER(vp)], i),
+        "sx_host_free": ([vp], i),
+        "sx_partition_rows": ([i, _PI32, i, _PI32], i),
+        "sx_load_mtx_f32": ([C.c_char_p, C.POINTER(i), C.POINTER(i), C.POINTER(i64),
+                             C.POINTER(_PI32), C.POINTER(_PI32), C.POINTER(_PF)], i),
+        "sx_load_mtx_f64": ([C.c_char_p, C.POINTER(i), C.POINTER(i), C.POINTER(i64),
+                             C.POINTER(_PI32), C.POINTER(_PI32), C.POINTER(_PD)], i),
+        "sx_free": ([vp], None),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = res
+    _LIB = L
+    return L
+
+
+def _check(status):
+    if status != 0:
+        L = lib()
+        raise SextansError(L.sx_status_name(status).decode(), L.sx_last_error().decode())
+
+
+def _suffix(dtype):
+    dtype = np.dtype(dtype)
+    if dtype == np.float32:
+        return "f32", C.c_float, SX_F32
+    if dtype == np.float64:
+        return "f64", C.c_double, SX_F64
+    raise TypeError(f"float32 or float64 expected, got {dtype}")
+
+
+def _host_ptr(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def _dev_ptr(t):
+    # torch tensor / anything with data_ptr(), or a raw integer address
+    return C.c_void_p(t.data_ptr() if hasattr(t, "data_ptr") else int(t))
+
+
+def load_mtx(path, dtype=np.float32):
+    """Matrix Market -> (M, K, nnz, rowptr, colidx, val) with the reference loader's
+    semantics (sx_load_mtx_*; src/sparse_helper.h:169-259 + 475-509)."""
+    suf, ct, _ = _suffix(dtype)
+    M, K, nnz = C.c_int(), C.c_int(), C.c_int64()
+    rp, ci, v = _PI32(), _PI32(), C.POINTER(ct)()
+    L = lib()
+    _check(getattr(L, f"sx_load_mtx_{suf}")(os.fsencode(path), C.byref(M), C.byref(K),
+                                             C.byref(nnz), C.byref(rp), C.byref(ci), C.byref(v)))
+    try:
+        n = nnz.value
+        rowptr = np.ctypeslib.as_array(rp, shape=(M.value + 1,)).copy()
+        colidx = np.ctypeslib.as_array(ci, shape=(max(n, 1),))[:n].copy()
+        val = np.ctypeslib.as_array(v, shape=(max(n, 1),))[:n].copy()
+    finally:
+        L.sx_free(rp), L.sx_free(ci), L.sx_free(v)
+    return M.value, K.value, n, rowptr, colidx, val
+
+
+def partition_rows(rowptr, parts):
+    """nnz-balanced contiguous row blocks -> bounds[parts+1] (sx_partition_rows)."""
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+    bounds = np.empty(parts + 1, dtype=np.int32)
+    _check(lib().sx_partition_rows(rowptr.size - 1, rowptr.ctypes.data_as(_PI32), parts,
+                                   bounds.ctypes.data_as(_PI32)))
+    return bounds
+
+
+class _Pinned:
+    def __init__(self, nbytes):
+        self.ptr = C.c_void_p()
+        _check(lib().sx_host_alloc(nbytes, C.byref(self.ptr)))
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().sx_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(n, dtype):
+    """1-D page-locked host array (sx_host_alloc), for B and C at the boundary."""
+    dtype = np.dtype(dtype)
+    nbytes = max(1, n * dtype.itemsize)
+    owner = _Pinned(nbytes)
+    buf = (C.c_char * nbytes).from_address(owner.ptr.value)
+    return _PinnedArray(np.frombuffer(buf, dtype=dtype, count=n), owner)
+
+
+class _PinnedArray(np.ndarray):
+    """ndarray view that keeps its page-locked allocation alive."""
+
+    def __new__(cls, arr, owner):
+        obj = arr.view(cls)
+        obj._owner = owner
+        return obj
+
+    def __array_finalize__(self, obj):
+        self._owner = getattr(obj, "_owner", None)
+
+
+class Engine:
+    """One GPU's SpMM context (``sx_ctx``).
+
+    Mirrors the reference host's single device call: upload A once, then
+    ``spmm(N, alpha, B, beta, C)`` with column-major host operands, exactly the
+    arguments ``cpu_spmm_CSR`` takes (src/sparse_helper.h:262-272).
+    """
+
+    def __init__(self, device: int = 0, arith: int = STRICT):
+        self._ctx = C.c_void_p()
+        self._L = lib()
+        _check(self._L.sx_create(device, C.byref(self._ctx)))
+        self.device = device
+        self.dtype = None
+        self.M = self.K = self.nnz = 0
+        if arith != STRICT:
+            self.set_option(OPT_ARITH, arith)
+
+    # -- lifecycle -----------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._L.sx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_stream(self, cuda_stream):
+        """Run on an existing CUDA stream (integer handle, e.g. torch's .cuda_stream)."""
+        _check(self._L.sx_set_stream(self._ctx, C.c_void_p(cuda_stream or None)))
+
+    def set_option(self, option, value):
+        _check(self._L.sx_set_option(self._ctx, option, int(value)))
+
+    def info(self, what) -> int:
+        v = C.c_int64()
+        _check(self._L.sx_get_info(self._ctx, what, C.byref(v)))
+        return v.value
+
+    @property
+    def launches(self) -> int:
+        return self.info(INFO_LAUNCHES)
+
+    def synchronize(self):
+        _check(self._L.sx_synchronize(self._ctx))
+
+    # -- A ---------------------------------------------------------------------------
+    def upload_csr(self, M, K, rowptr, colidx, val):
+        suf, ct, _ = _suffix(val.dtype)
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+        colidx = np.ascontiguousarray(colidx, dtype=np.int32)
+        val = np.ascontiguousarray(val)
+        if rowptr.size != M + 1:
+            raise ValueError("rowptr must have M+1 entries")
+        _check(getattr(self._L, f"sx_upload_csr_{suf}")(
+            self._ctx, M, K, int(colidx.size), rowptr.ctypes.data_as(_PI32),
+            colidx.ctypes.data_as(_PI32), val.ctypes.data_as(C.POINTER(ct))))
+        self.dtype, self.M, self.K, self.nnz = val.dtype, M, K, int(colidx.size)
+        return self
+
+    # -- the call ----------------------------------------------------------------------
+    def spmm(self, N, alpha, B, beta, C_inout, rp_time=1):
+        """In place on ``C_inout`` (column-major 1-D, like the host program's vectors).
+        Returns the kernel time in ns summed over the ``rp_time`` repeats, the value
+        ``tapa::invoke`` returns in the reference (src/sextans-host.cpp:237)."""
+        suf, ct, _ = _suffix(self.dtype)
+        B = np.ascontiguousarray(B, dtype=self.dtype)
+        if C_inout.dtype != self.dtype or not C_inout.flags.c_contiguous:
+            raise ValueError("C must be a contiguous array of the matrix dtype")
+        if B.size != self.K * N or C_inout.size != self.M * N:
+            raise ValueError("B must hold K*N and C must hold M*N elements")
+        ns = C.c_double()
+        _check(getattr(self._L, f"sx_spmm_{suf}")(self._ctx, N, ct(alpha), _host_ptr(B), ct(beta),
+                                                  _host_ptr(C_inout), rp_time, C.byref(ns)))
+        return ns.value
+
+    # -- staged ------------------------------------------------------------------------
+    def stage_B(self, N, B):
+        suf = _suffix(self.dtype)[0]
+        B = np.ascontiguousarray(B, dtype=self.dtype)
+        assert B.size == self.K * N
+        _check(getattr(self._L, f"sx_stage_B_{suf}")(self._ctx, N, _host_ptr(B)))
+
+    def stage_C(self, N, Cin):
+        suf = _suffix(self.dtype)[0]
+        Cin = np.ascontiguousarray(Cin, dtype=self.dtype)
+        assert Cin.size == self.M * N
+        _check(getattr(self._L, f"sx_stage_C_{suf}")(self._ctx, N, _host_ptr(Cin)))
+
+    def launch(self, alpha, beta, rp_time=1):
+        suf, ct, _ = _suffix(self.dtype)
+        ns = C.c_double()
+        _check(getattr(self._L, f"sx_launch_{suf}")(self._ctx, ct(alpha), ct(beta), rp_time, C.byref(ns)))
+        return ns.value
+
+    def fetch_C(self, out):
+        suf = _suffix(self.dtype)[0]
+        assert out.dtype == self.dtype and out.flags.c_contiguous
+        _check(getattr(self._L, f"sx_fetch_C_{suf}")(self._ctx, _host_ptr(out)))
+        return out
+
+    def device_B(self, N):
+        """(device address, bytes) of the context's row-major B image."""
+        p, n = C.c_void_p(), C.c_size_t()
+        _check(self._L.sx_device_B(self._ctx, N, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    # -- device-resident -----------------------------------------------------------------
+    def spmm_device(self, N, alpha, dB, ldb, beta, dCin, dCout, ldc):
+        """Enqueue one SpMM on row-major device operands (torch tensors or addresses)."""
+        suf, ct, _ = _suffix(self.dtype)
+        _check(getattr(self._L, f"sx_spmm_device_{suf}")(
+            self._ctx, N, ct(alpha), _dev_ptr(dB), ldb, ct(beta), _dev_ptr(dCin), _dev_ptr(dCout), ldc))
+
+    def colmajor_to_rowmajor(self, rows, cols, d_src, d_dst, ld_dst, dtype=None):
+        code = _suffix(dtype or self.dtype)[2]
+        _check(self._L.sx_colmajor_to_rowmajor(self._ctx, code, rows, cols, _dev_ptr(d_src),
+                                               _dev_ptr(d_dst), ld_dst))
+
+    def rowmajor_to_colmajor(self, rows, cols, d_src, ld_src, d_dst, dtype=None):
+        code = _suffix(dtype or self.dtype)[2]
+        _check(self._L.sx_rowmajor_to_colmajor(self._ctx, code, rows, cols, _dev_ptr(d_src),
+                                               ld_src, _dev_ptr(d_dst)))

@@ -1,0 +1,285 @@
+// spmm_kernels.cuh -- sm_100a kernels of the SpMM hot path.
+//
+// What of the reference these stand in for (citations relative to the reference
+// tree): the whole accelerator dataflow of src/sextans.cpp:836-984 --
+//   read_A / read_B / read_C / write_C           (:75-194)  -> global loads/stores here
+//   PEG_Bmtx: val * B[col][0..7]                 (:285-423) -> the B-row gather + multiply
+//   PEG_Cmtx: local_C[row] += abvec              (:425-570) -> register accumulators per row
+//   FloatvMultConst / FloatvAddFloatv epilogue   (:196-233) -> fused alpha/beta epilogue
+// and they compute exactly what cpu_spmm_CSR (src/sparse_helper.h:262-290) computes.
+//
+// Device data layout: A in CSR (int32 rowptr/colidx, T values); B, C ROW-major with
+// a leading dimension that is a multiple of 16 bytes, so that one nonzero's B row is
+// read with 16-byte vector loads by a sub-warp "row group" of G lanes.  Each lane
+// owns 16 bytes (4 fp32 / 2 fp64 columns) of VPL interleaved vectors of its row's
+// accumulator; the group walks the row's nonzeros IN STORED ORDER, so in strict mode
+// (separately rounded multiply and add, sparse_helper.h:283) the result is
+// bit-identical to the reference loop.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sx {
+
+template <typename T> struct VecOf;
+template <> struct VecOf<float> { using type = float4; static constexpr int E = 4; };
+template <> struct VecOf<double> { using type = double2; static constexpr int E = 2; };
+
+// ---- scalar arithmetic with an explicit rounding contract -------------------
+template <bool STRICT> __device__ __forceinline__ float mac(float acc, float a, float b) {
+    if (STRICT) return __fadd_rn(acc, __fmul_rn(a, b));  // never contracted to FMA
+    return fmaf(a, b, acc);
+}
+template <bool STRICT> __device__ __forceinline__ double mac(double acc, double a, double b) {
+    if (STRICT) return __dadd_rn(acc, __dmul_rn(a, b));
+    return fma(a, b, acc);
+}
+// alpha*acc + beta*c: two rounded products and a rounded sum (sparse_helper.h:287,
+// sextans.cpp:211,229)
+template <bool STRICT> __device__ __forceinline__ float axpby(float alpha, float acc, float beta, float c) {
+    if (STRICT) return __fadd_rn(__fmul_rn(alpha, acc), __fmul_rn(beta, c));
+    return fmaf(alpha, acc, beta * c);
+}
+template <bool STRICT> __device__ __forceinline__ double axpby(double alpha, double acc, double beta, double c) {
+    if (STRICT) return __dadd_rn(__dmul_rn(alpha, acc), __dmul_rn(beta, c));
+    return fma(alpha, acc, beta * c);
+}
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+
+// ---- 16-byte vector helpers ---------------------------------------------------
+__device__ __forceinline__ void vzero(float4 &v) { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void vzero(double2 &v) { v = make_double2(0.0, 0.0); }
+
+template <bool STRICT> __device__ __forceinline__ void vmac(float4 &acc, float a, const float4 &b) {
+    acc.x = mac<STRICT>(acc.x, a, b.x); acc.y = mac<STRICT>(acc.y, a, b.y);
+    acc.z = mac<STRICT>(acc.z, a, b.z); acc.w = mac<STRICT>(acc.w, a, b.w);
+}
+template <bool STRICT> __device__ __forceinline__ void vmac(double2 &acc, double a, const double2 &b) {
+    acc.x = mac<STRICT>(acc.x, a, b.x); acc.y = mac<STRICT>(acc.y, a, b.y);
+}
+template <bool STRICT> __device__ __forceinline__ float4 vaxpby(float alpha, const float4 &acc, float beta, const float4 &c) {
+    return make_float4(axpby<STRICT>(alpha, acc.x, beta, c.x), axpby<STRICT>(alpha, acc.y, beta, c.y),
+                       axpby<STRICT>(alpha, acc.z, beta, c.z), axpby<STRICT>(alpha, acc.w, beta, c.w));
+}
+template <bool STRICT> __device__ __forceinline__ double2 vaxpby(double alpha, const double2 &acc, double beta, const double2 &c) {
+    return make_double2(axpby<STRICT>(alpha, acc.x, beta, c.x), axpby<STRICT>(alpha, acc.y, beta, c.y));
+}
+__device__ __forceinline__ void vadd(float4 &a, const float4 &b) {
+    a.x = add_rn(a.x, b.x); a.y = add_rn(a.y, b.y); a.z = add_rn(a.z, b.z); a.w = add_rn(a.w, b.w);
+}
+__device__ __forceinline__ void vadd(double2 &a, const double2 &b) {
+    a.x = add_rn(a.x, b.x); a.y = add_rn(a.y, b.y);
+}
+__device__ __forceinline__ float4 vshfl_xor(unsigned m, const float4 &v, int off) {
+    return make_float4(__shfl_xor_sync(m, v.x, off), __shfl_xor_sync(m, v.y, off),
+                       __shfl_xor_sync(m, v.z, off), __shfl_xor_sync(m, v.w, off));
+}
+__device__ __forceinline__ double2 vshfl_xor(unsigned m, const double2 &v, int off) {
+    return make_double2(__shfl_xor_sync(m, v.x, off), __shfl_xor_sync(m, v.y, off));
+}
+// read-only 16-byte gather of a B-row piece (ld.global.nc)
+__device__ __forceinline__ float4 ldg_vec(const float4 *p) { return __ldg(p); }
+__device__ __forceinline__ double2 ldg_vec(const double2 *p) { return __ldg(p); }
+
+// Accumulate nonzeros [begin, end) of one row, visiting chunks of G nonzeros at
+// positions begin + first*G, begin + (first+stride)*G, ...  The G lanes of the group
+// fetch a chunk's (col, val) pairs with one coalesced load each and hand them round
+// by shuffle; the next chunk's pair is fetched before the current one is consumed.
+template <typename T, int G, int VPL, bool STRICT>
+__device__ __forceinline__ void accumulate_range(
+    typename VecOf<T>::type (&acc)[VPL], const int begin, const int end, const int first,
+    const int stride, const int lg, const unsigned gmask, const int nvec,
+    const int *__restrict__ colidx, const T *__restrict__ val, const T *__restrict__ B,
+    const int64_t ldb) {
+    using V = typename VecOf<T>::type;
+    constexpr int U = G < 8 ? G : 8;  // B-row gathers kept in flight per lane
+    int base = begin + first * G;
+    int c = 0;
+    T a = T(0);
+    if (base + lg < end) { c = __ldg(colidx + base + lg); a = __ldg(val + base + lg); }
+    for (; base < end; base += stride * G) {
+        const int nbase = base + stride * G;
+        int cn = 0;
+        T an = T(0);
+        if (nbase + lg < end) { cn = __ldg(colidx + nbase + lg); an = __ldg(val + nbase + lg); }
+        const int cnt = end - base;  // >= 1; entries t >= cnt of this chunk do not exist
+#pragma unroll
+        for (int t0 = 0; t0 < G; t0 += U) {
+            if (t0 < cnt) {  // group-uniform
+                V b[U][VPL];
+                T av[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int cc = __shfl_sync(gmask, c, t0 + u, G);
+                    av[u] = __shfl_sync(gmask, a, t0 + u, G);
+                    const V *brow = reinterpret_cast<const V *>(B + (int64_t)cc * ldb);
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) {
+                        const int vi = lg + v * G;
+                        if (t0 + u < cnt && vi < nvec) b[u][v] = ldg_vec(brow + vi);
+                        else vzero(b[u][v]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (t0 + u < cnt) {
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v) vmac<STRICT>(acc[v], av[u], b[u][v]);
+                    }
+                }
+            }
+        }
+        c = cn;
+        a = an;
+    }
+}
+
+// ---- main kernel: one row group per row ---------------------------------------
+// Rows longer than split_nnz (when > 0) are left to the segment kernels below.
+template <typename T, int G, int VPL, bool STRICT>
+__global__ void __launch_bounds__(256)
+spmm_rows_kernel(const int M, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                 const T *__restrict__ val, const T *__restrict__ B, const int64_t ldb,
+                 const T *Cin, T *Cout, const int64_t ldc, const T alpha, const T beta,
+                 const int nvec, const int split_nnz) {
+    using V = typename VecOf<T>::type;
+    const int lane = threadIdx.x & 31;
+    const int lg = lane & (G - 1);
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - lg));
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    if (row >= M) return;
+    const int begin = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+    if (split_nnz > 0 && end - begin > split_nnz) return;
+
+    V acc[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) vzero(acc[v]);
+    accumulate_range<T, G, VPL, STRICT>(acc, begin, end, 0, 1, lg, gmask, nvec, colidx, val, B, ldb);
+
+    const V *cin = reinterpret_cast<const V *>(Cin + row * ldc);
+    V *cout = reinterpret_cast<V *>(Cout + row * ldc);
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        const int vi = lg + v * G;
+        if (vi < nvec) cout[vi] = vaxpby<STRICT>(alpha, acc[v], beta, cin[vi]);
+    }
+}
+
+// ---- long rows: one warp per segment of <= split_nnz nonzeros -------------------
+// The 32/G groups of the warp take interleaved chunks of the segment and their
+// partial vectors are combined by a fixed xor-shuffle tree, so the result is
+// deterministic but NOT in the oracle's summation order.
+template <typename T, int G, int VPL, bool STRICT>
+__global__ void __launch_bounds__(256)
+spmm_segments_kernel(const int nseg, const int *__restrict__ seg_begin,
+                     const int *__restrict__ seg_end, const int *__restrict__ colidx,
+                     const T *__restrict__ val, const T *__restrict__ B, const int64_t ldb,
+                     T *__restrict__ partial, const int64_t ldp, const int nvec) {
+    using V = typename VecOf<T>::type;
+    const int lane = threadIdx.x & 31;
+    const int lg = lane & (G - 1);
+    const int gi = lane / G;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - lg));
+    const int seg = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (seg >= nseg) return;  // warp-uniform
+    V acc[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) vzero(acc[v]);
+    accumulate_range<T, G, VPL, STRICT>(acc, __ldg(seg_begin + seg), __ldg(seg_end + seg), gi,
+                                        32 / G, lg, gmask, nvec, colidx, val, B, ldb);
+#pragma unroll
+    for (int off = G; off < 32; off <<= 1) {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            V o = vshfl_xor(0xffffffffu, acc[v], off);
+            vadd(acc[v], o);
+        }
+    }
+    if (gi == 0) {
+        V *out = reinterpret_cast<V *>(partial + (int64_t)seg * ldp);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const int vi = lg + v * G;
+            if (vi < nvec) out[vi] = acc[v];
+        }
+    }
+}
+
+// Sum a split row's segment partials in segment order and apply the epilogue.
+template <typename T, int G, int VPL, bool STRICT>
+__global__ void __launch_bounds__(256)
+spmm_finalize_kernel(const int nsplit, const int *__restrict__ split_row,
+                     const int *__restrict__ split_seg_ptr, const T *__restrict__ partial,
+                     const int64_t ldp, const T *Cin, T *Cout, const int64_t ldc, const T alpha,
+                     const T beta, const int nvec) {
+    using V = typename VecOf<T>::type;
+    const int lg = threadIdx.x & (G - 1);
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    if (i >= nsplit) return;
+    const int64_t row = __ldg(split_row + i);
+    const int s0 = __ldg(split_seg_ptr + i), s1 = __ldg(split_seg_ptr + i + 1);
+    const V *cin = reinterpret_cast<const V *>(Cin + row * ldc);
+    V *cout = reinterpret_cast<V *>(Cout + row * ldc);
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        const int vi = lg + v * G;
+        if (vi >= nvec) continue;
+        V acc;
+        vzero(acc);
+        for (int s = s0; s < s1; ++s) {
+            const V p = reinterpret_cast<const V *>(partial + (int64_t)s * ldp)[vi];
+            vadd(acc, p);
+        }
+        cout[vi] = vaxpby<STRICT>(alpha, acc, beta, cin[vi]);
+    }
+}
+
+// ---- layout changes at the host boundary ---------------------------------------
+// column-major (ld = rows) -> row-major (ld = ld_dst, pad columns zero-filled); the
+// device-side stand-in for the reference's B/C channel repacking
+// (src/sextans-host.cpp:152-195).
+template <typename T>
+__global__ void __launch_bounds__(256)
+colmajor_to_rowmajor_kernel(const int64_t rows, const int cols, const T *__restrict__ src,
+                            T *__restrict__ dst, const int64_t ld_dst) {
+    __shared__ T tile[32][33];
+    const int64_t r0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int c = c0 + j;
+        const int64_t r = r0 + threadIdx.x;
+        tile[j][threadIdx.x] = (r < rows && c < cols) ? src[r + rows * (int64_t)c] : T(0);
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int64_t r = r0 + j;
+        const int c = c0 + threadIdx.x;
+        if (r < rows && c < ld_dst) dst[r * ld_dst + c] = tile[threadIdx.x][j];
+    }
+}
+
+// row-major (ld = ld_src) -> column-major (ld = rows); the read-back un-interleave
+// (src/sextans-host.cpp:264-270).
+template <typename T>
+__global__ void __launch_bounds__(256)
+rowmajor_to_colmajor_kernel(const int64_t rows, const int cols, const T *__restrict__ src,
+                            const int64_t ld_src, T *__restrict__ dst) {
+    __shared__ T tile[32][33];
+    const int64_t r0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int64_t r = r0 + j;
+        const int c = c0 + threadIdx.x;
+        tile[j][threadIdx.x] = (r < rows && c < cols) ? src[r * ld_src + c] : T(0);
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int c = c0 + j;
+        const int64_t r = r0 + threadIdx.x;
+        if (r < rows && c < cols) dst[r + rows * (int64_t)c] = tile[threadIdx.x][j];
+    }
+}
+
+}  // namespace sx

@@ -1,0 +1,602 @@
+// sx_api.cu -- the C ABI of include/sextans_b200.h on top of spmm_kernels.cuh.
+//
+// A context owns one GPU's copy of A (CSR), the row-major device images of B,
+// C_in and C_out, and a staging area for the host program's column-major operands.
+// The call sequence of sx_spmm_* mirrors what tapa::invoke does for the reference
+// (src/sextans-host.cpp:237-251): copy inputs to the device, run the kernel rp_time
+// times, copy the result back, return the kernel time.
+#include "../../include/sextans_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "spmm_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int status, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return status;
+}
+
+#define SX_CUDA(call)                                                                   \
+    do {                                                                                \
+        cudaError_t e_ = (call);                                                        \
+        if (e_ != cudaSuccess)                                                          \
+            return fail(SX_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                            \
+    } while (0)
+
+template <typename T> struct DtypeOf;
+template <> struct DtypeOf<float> { static constexpr int value = SX_F32; };
+template <> struct DtypeOf<double> { static constexpr int value = SX_F64; };
+
+size_t dtype_size(int dtype) { return dtype == SX_F64 ? 8 : 4; }
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return SX_OK;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        SX_CUDA(cudaMalloc(&p, bytes));
+        cap = bytes;
+        return SX_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct sx_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 0;
+
+    // A
+    bool has_A = false;
+    int dtype = SX_F32;
+    int M = 0, K = 0;
+    int64_t nnz = 0;
+    DevBuf rowptr, colidx, val;
+    // long-row segments
+    int nsplit = 0, nseg = 0;
+    DevBuf split_row, split_seg_ptr, seg_begin, seg_end, partial;
+    std::vector<int32_t> h_rowptr;  // kept to re-derive segments when the option changes
+
+    // dense operands (row-major, ld elements per row)
+    int N = 0;
+    int64_t ld = 0;
+    bool has_B = false, has_C = false;
+    DevBuf B, Cin, Cout, stage;
+
+    // options
+    int arith = 0;
+    int split_nnz = 512;
+    int kernel = 0;
+    bool segments_dirty = false;
+
+    int64_t launches = 0;
+    int last_kernel = 0;
+};
+
+namespace {
+
+int64_t padded_ld(int N, int dtype) {
+    // 8 elements: 32 B (fp32) / 64 B (fp64) -- whole sectors per row, and the host
+    // program's own granularity (N is rounded up to 8, src/sextans-host.cpp:51)
+    (void)dtype;
+    return ((int64_t)N + 7) / 8 * 8;
+}
+
+int bind(sx_ctx *c) {
+    if (!c) return fail(SX_ERR_INVALID, "null context");
+    SX_CUDA(cudaSetDevice(c->device));
+    return SX_OK;
+}
+
+// ---- kernel dispatch ------------------------------------------------------------
+// nvec = 16-byte vectors per dense row; G lanes per row group, VPL vectors per lane.
+struct Shape { int G, VPL; };
+
+bool pick_shape(int nvec, Shape *s) {
+    int G = 2;
+    while (G < 32 && G < nvec) G <<= 1;
+    int vpl = (nvec + G - 1) / G;
+    if (vpl > 4) return false;
+    if (vpl == 3) vpl = 4;
+    *s = {G, vpl};
+    return true;
+}
+
+template <typename T, int G, int VPL, bool STRICT>
+int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, const T *dCin,
+                 T *dCout, int64_t ldc) {
+    const int nvec = (N * (int)sizeof(T) + 15) / 16;
+    const int threads = 256;
+    const int rows_per_block = threads / G;
+    const int split = c->nseg > 0 ? c->split_nnz : 0;
+    if (c->M > 0) {
+        const unsigned grid = (unsigned)(((int64_t)c->M + rows_per_block - 1) / rows_per_block);
+        sx::spmm_rows_kernel<T, G, VPL, STRICT><<<grid, threads, 0, c->stream>>>(
+            c->M, (const int *)c->rowptr.p, (const int *)c->colidx.p, (const T *)c->val.p, dB, ldb,
+            dCin, dCout, ldc, alpha, beta, nvec, split);
+        c->launches++;
+    }
+    if (c->nseg > 0) {
+        const int64_t ldp = ((int64_t)N + 7) / 8 * 8;
+        int rc = c->partial.ensure((size_t)c->nseg * ldp * sizeof(T));
+        if (rc) return rc;
+        const unsigned gseg = (unsigned)(((int64_t)c->nseg * 32 + threads - 1) / threads);
+        sx::spmm_segments_kernel<T, G, VPL, STRICT><<<gseg, threads, 0, c->stream>>>(
+            c->nseg, (const int *)c->seg_begin.p, (const int *)c->seg_end.p,
+            (const int *)c->colidx.p, (const T *)c->val.p, dB, ldb, (T *)c->partial.p, ldp, nvec);
+        const unsigned gfin = (unsigned)(((int64_t)c->nsplit + rows_per_block - 1) / rows_per_block);
+        sx::spmm_finalize_kernel<T, G, VPL, STRICT><<<gfin, threads, 0, c->stream>>>(
+            c->nsplit, (const int *)c->split_row.p, (const int *)c->split_seg_ptr.p,
+            (const T *)c->partial.p, ldp, dCin, dCout, ldc, alpha, beta, nvec);
+        c->launches += 2;
+    }
+    c->last_kernel = G * 100 + VPL * 10 + (STRICT ? 0 : 1);
+    SX_CUDA(cudaGetLastError());
+    return SX_OK;
+}
+
+template <typename T, int G, bool STRICT>
+int launch_vpl(sx_ctx *c, int vpl, int N, T alpha, const T *dB, int64_t ldb, T beta,
+               const T *dCin, T *dCout, int64_t ldc) {
+    switch (vpl) {
+        case 1: return launch_shape<T, G, 1, STRICT>(c, N, alpha, dB, ldb, beta, dCin, dCout, ldc);
+        case 2: return launch_shape<T, G, 2, STRICT>(c, N, alpha, dB, ldb, beta, dCin, dCout, ldc);
+        default: return launch_shape<T, G, 4, STRICT>(c, N, alpha, dB, ldb, beta, dCin, dCout, ldc);
+    }
+}
+
+template <typename T, bool STRICT>
+int launch_group(sx_ctx *c, Shape s, int N, T alpha, const T *dB, int64_t ldb, T beta,
+                 const T *dCin, T *dCout, int64_t ldc) {
+    switch (s.G) {
+        case 2: return launch_shape<T, 2, 1, STRICT>(c, N, alpha, dB, ldb, beta, dCin, dCout, ldc);
+        case 4: return launch_shape<T, 4, 1, STRICT>(c, N, alpha, dB, ldb, beta, dCin, dCout, ldc);
+        case 8: return launch_shape<T, 8, 1, STRICT>(c, N, alpha, dB, ldb, beta, dCin, dCout, ldc);
+        case 16: return launch_shape<T, 16, 1, STRICT>(c, N, alpha, dB, ldb, beta, dCin, dCout, ldc);
+        default: return launch_vpl<T, 32, STRICT>(c, s.VPL, N, alpha, dB, ldb, beta, dCin, dCout, ldc);
+    }
+}
+
+int refresh_segments(sx_ctx *c);
+
+// One SpMM over device-resident row-major operands.  Column counts beyond what one
+// row group covers (4 vectors x 32 lanes) are processed in column panels.
+template <typename T>
+int spmm_device(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, const T *dCin,
+                T *dCout, int64_t ldc) {
+    int rc = bind(c);
+    if (rc) return rc;
+    if (!c->has_A) return fail(SX_ERR_STATE, "no matrix uploaded (call sx_upload_csr_* first)");
+    if (c->dtype != DtypeOf<T>::value)
+        return fail(SX_ERR_INVALID, "matrix was uploaded as %s", c->dtype == SX_F64 ? "f64" : "f32");
+    constexpr int E = sx::VecOf<T>::E;
+    if (N < 1) return fail(SX_ERR_INVALID, "N must be >= 1 (got %d)", N);
+    if (ldb < N || ldc < N || ldb % E || ldc % E)
+        return fail(SX_ERR_INVALID, "ldb/ldc must be >= N and multiples of %d elements", E);
+    if (((uintptr_t)dB | (uintptr_t)dCin | (uintptr_t)dCout) & 15)
+        return fail(SX_ERR_INVALID, "device operands must be 16-byte aligned");
+    if (c->segments_dirty && (rc = refresh_segments(c))) return rc;
+
+    const int panel_cols = 4 * 32 * E;  // widest shape: G = 32, VPL = 4
+    for (int n0 = 0; n0 < N; n0 += panel_cols) {
+        const int n = std::min(panel_cols, N - n0);
+        const int nvec = (n * (int)sizeof(T) + 15) / 16;
+        Shape s;
+        if (!pick_shape(nvec, &s)) return fail(SX_ERR_INVALID, "internal: no shape for %d", nvec);
+        if (c->arith == 0)
+            rc = launch_group<T, true>(c, s, n, alpha, dB + n0, ldb, beta, dCin + n0, dCout + n0, ldc);
+        else
+            rc = launch_group<T, false>(c, s, n, alpha, dB + n0, ldb, beta, dCin + n0, dCout + n0, ldc);
+        if (rc) return rc;
+    }
+    return SX_OK;
+}
+
+// ---- A upload ---------------------------------------------------------------------
+int refresh_segments(sx_ctx *c) {
+    c->segments_dirty = false;
+    c->nsplit = c->nseg = 0;
+    const int S = c->split_nnz;
+    if (S <= 0 || c->M == 0) return SX_OK;
+    std::vector<int32_t> rows, segptr(1, 0), sb, se;
+    for (int i = 0; i < c->M; ++i) {
+        const int b = c->h_rowptr[i], e = c->h_rowptr[i + 1];
+        if (e - b <= S) continue;
+        rows.push_back(i);
+        for (int s = b; s < e; s += S) {
+            sb.push_back(s);
+            se.push_back(std::min(e, s + S));
+        }
+        segptr.push_back((int32_t)sb.size());
+    }
+    if (rows.empty()) return SX_OK;
+    int rc;
+    if ((rc = c->split_row.ensure(rows.size() * 4))) return rc;
+    if ((rc = c->split_seg_ptr.ensure(segptr.size() * 4))) return rc;
+    if ((rc = c->seg_begin.ensure(sb.size() * 4))) return rc;
+    if ((rc = c->seg_end.ensure(se.size() * 4))) return rc;
+    SX_CUDA(cudaMemcpyAsync(c->split_row.p, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    SX_CUDA(cudaMemcpyAsync(c->split_seg_ptr.p, segptr.data(), segptr.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    SX_CUDA(cudaMemcpyAsync(c->seg_begin.p, sb.data(), sb.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    SX_CUDA(cudaMemcpyAsync(c->seg_end.p, se.data(), se.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    SX_CUDA(cudaStreamSynchronize(c->stream));  // the host vectors die at return
+    c->nsplit = (int)rows.size();
+    c->nseg = (int)sb.size();
+    return SX_OK;
+}
+
+template <typename T>
+int upload_csr(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rowptr, const int32_t *colidx,
+               const T *val) {
+    int rc = bind(c);
+    if (rc) return rc;
+    if (M < 0 || K < 0 || nnz < 0 || nnz > INT32_MAX)
+        return fail(SX_ERR_INVALID, "bad sizes M=%d K=%d nnz=%lld (32-bit row pointers)", M, K, (long long)nnz);
+    if (!rowptr || (nnz > 0 && (!colidx || !val))) return fail(SX_ERR_INVALID, "null CSR array");
+    if (rowptr[0] != 0 || rowptr[M] != nnz)
+        return fail(SX_ERR_INVALID, "rowptr[0] must be 0 and rowptr[M] must equal nnz");
+    for (int i = 0; i < M; ++i)
+        if (rowptr[i + 1] < rowptr[i]) return fail(SX_ERR_INVALID, "rowptr decreases at row %d", i);
+    for (int64_t j = 0; j < nnz; ++j)
+        if ((uint32_t)colidx[j] >= (uint32_t)K)
+            return fail(SX_ERR_INVALID, "column index %d out of range at nonzero %lld", colidx[j], (long long)j);
+    c->has_A = false;
+    if ((rc = c->rowptr.ensure(((size_t)M + 1) * 4))) return rc;
+    if ((rc = c->colidx.ensure(std::max<size_t>(16, (size_t)nnz * 4)))) return rc;
+    if ((rc = c->val.ensure(std::max<size_t>(16, (size_t)nnz * sizeof(T))))) return rc;
+    SX_CUDA(cudaMemcpyAsync(c->rowptr.p, rowptr, ((size_t)M + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    if (nnz > 0) {
+        SX_CUDA(cudaMemcpyAsync(c->colidx.p, colidx, (size_t)nnz * 4, cudaMemcpyHostToDevice, c->stream));
+        SX_CUDA(cudaMemcpyAsync(c->val.p, val, (size_t)nnz * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    }
+    SX_CUDA(cudaStreamSynchronize(c->stream));
+    c->h_rowptr.assign(rowptr, rowptr + M + 1);
+    c->M = M; c->K = K; c->nnz = nnz;
+    c->dtype = DtypeOf<T>::value;
+    c->has_B = c->has_C = false;
+    c->N = 0; c->ld = 0;
+    if ((rc = refresh_segments(c))) return rc;
+    c->has_A = true;
+    return SX_OK;
+}
+
+// ---- dense staging ----------------------------------------------------------------
+int set_columns(sx_ctx *c, int N) {
+    if (N < 1) return fail(SX_ERR_INVALID, "N must be >= 1 (got %d)", N);
+    if (c->N != N) {
+        c->N = N;
+        c->ld = padded_ld(N, c->dtype);
+        c->has_B = c->has_C = false;
+    }
+    return SX_OK;
+}
+
+int transpose_in(sx_ctx *c, int dtype, int64_t rows, int cols, const void *src, void *dst, int64_t ld) {
+    if (rows == 0) return SX_OK;
+    dim3 block(32, 8), grid((unsigned)((rows + 31) / 32), (unsigned)((ld + 31) / 32));
+    if (dtype == SX_F64)
+        sx::colmajor_to_rowmajor_kernel<double><<<grid, block, 0, c->stream>>>(rows, cols, (const double *)src, (double *)dst, ld);
+    else
+        sx::colmajor_to_rowmajor_kernel<float><<<grid, block, 0, c->stream>>>(rows, cols, (const float *)src, (float *)dst, ld);
+    c->launches++;
+    SX_CUDA(cudaGetLastError());
+    return SX_OK;
+}
+
+int transpose_out(sx_ctx *c, int dtype, int64_t rows, int cols, const void *src, int64_t ld, void *dst) {
+    if (rows == 0) return SX_OK;
+    dim3 block(32, 8), grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
+    if (dtype == SX_F64)
+        sx::rowmajor_to_colmajor_kernel<double><<<grid, block, 0, c->stream>>>(rows, cols, (const double *)src, ld, (double *)dst);
+    else
+        sx::rowmajor_to_colmajor_kernel<float><<<grid, block, 0, c->stream>>>(rows, cols, (const float *)src, ld, (float *)dst);
+    c->launches++;
+    SX_CUDA(cudaGetLastError());
+    return SX_OK;
+}
+
+template <typename T>
+int stage_dense(sx_ctx *c, int N, const T *host, bool is_B) {
+    int rc = bind(c);
+    if (rc) return rc;
+    if (!c->has_A) return fail(SX_ERR_STATE, "no matrix uploaded (call sx_upload_csr_* first)");
+    if (c->dtype != DtypeOf<T>::value) return fail(SX_ERR_INVALID, "dtype differs from the uploaded matrix");
+    if (!host) return fail(SX_ERR_INVALID, "null host operand");
+    if ((rc = set_columns(c, N))) return rc;
+    const int64_t rows = is_B ? c->K : c->M;
+    const size_t bytes = (size_t)rows * N * sizeof(T);
+    DevBuf &dst = is_B ? c->B : c->Cin;
+    if ((rc = c->stage.ensure(std::max<size_t>(bytes, 16)))) return rc;
+    if ((rc = dst.ensure(std::max<size_t>((size_t)rows * c->ld * sizeof(T), 16)))) return rc;
+    if (!is_B && (rc = c->Cout.ensure(std::max<size_t>((size_t)rows * c->ld * sizeof(T), 16)))) return rc;
+    if (bytes) SX_CUDA(cudaMemcpyAsync(c->stage.p, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = transpose_in(c, c->dtype, rows, N, c->stage.p, dst.p, c->ld))) return rc;
+    (is_B ? c->has_B : c->has_C) = true;
+    return SX_OK;
+}
+
+template <typename T>
+int launch(sx_ctx *c, T alpha, T beta, int rp_time, double *kernel_ns) {
+    int rc = bind(c);
+    if (rc) return rc;
+    if (!c->has_A || !c->has_B || !c->has_C)
+        return fail(SX_ERR_STATE, "stage A, B and C before launching (A=%d B=%d C=%d)", c->has_A, c->has_B, c->has_C);
+    if (rp_time < 1) rp_time = 1;
+    SX_CUDA(cudaEventRecord(c->ev0, c->stream));
+    for (int r = 0; r < rp_time; ++r) {
+        rc = spmm_device<T>(c, c->N, alpha, (const T *)c->B.p, c->ld, beta, (const T *)c->Cin.p,
+                            (T *)c->Cout.p, c->ld);
+        if (rc) return rc;
+    }
+    SX_CUDA(cudaEventRecord(c->ev1, c->stream));
+    SX_CUDA(cudaEventSynchronize(c->ev1));
+    if (kernel_ns) {
+        float ms = 0.f;
+        SX_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        *kernel_ns = (double)ms * 1e6;
+    }
+    return SX_OK;
+}
+
+template <typename T>
+int fetch_C(sx_ctx *c, T *host) {
+    int rc = bind(c);
+    if (rc) return rc;
+    if (!c->has_C) return fail(SX_ERR_STATE, "no C staged");
+    if (c->dtype != DtypeOf<T>::value) return fail(SX_ERR_INVALID, "dtype differs from the uploaded matrix");
+    if (!host) return fail(SX_ERR_INVALID, "null host operand");
+    const size_t bytes = (size_t)c->M * c->N * sizeof(T);
+    if ((rc = c->stage.ensure(std::max<size_t>(bytes, 16)))) return rc;
+    if ((rc = transpose_out(c, c->dtype, c->M, c->N, c->Cout.p, c->ld, c->stage.p))) return rc;
+    if (bytes) SX_CUDA(cudaMemcpyAsync(host, c->stage.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    SX_CUDA(cudaStreamSynchronize(c->stream));
+    return SX_OK;
+}
+
+template <typename T>
+int spmm_host(sx_ctx *c, int N, T alpha, const T *B, T beta, T *C, int rp_time, double *kernel_ns) {
+    int rc;
+    if ((rc = stage_dense<T>(c, N, B, true))) return rc;
+    if ((rc = stage_dense<T>(c, N, C, false))) return rc;
+    if ((rc = launch<T>(c, alpha, beta, rp_time, kernel_ns))) return rc;
+    return fetch_C<T>(c, C);
+}
+
+}  // namespace
+
+// =====================================================================================
+extern "C" {
+
+// lets the host-only translation unit (sx_host.cpp) report through sx_last_error()
+void sx_internal_set_error(const char *msg) { g_err = msg ? msg : ""; }
+
+int sx_abi_version(void) { return SX_ABI_VERSION; }
+
+const char *sx_last_error(void) { return g_err.c_str(); }
+
+const char *sx_status_name(int status) {
+    switch (status) {
+        case SX_OK: return "SX_OK";
+        case SX_ERR_INVALID: return "SX_ERR_INVALID";
+        case SX_ERR_CUDA: return "SX_ERR_CUDA";
+        case SX_ERR_NO_DEVICE: return "SX_ERR_NO_DEVICE";
+        case SX_ERR_STATE: return "SX_ERR_STATE";
+        case SX_ERR_NOMEM: return "SX_ERR_NOMEM";
+        case SX_ERR_IO: return "SX_ERR_IO";
+        case SX_ERR_FORMAT: return "SX_ERR_FORMAT";
+        default: return "SX_ERR_UNKNOWN";
+    }
+}
+
+int sx_device_count(int *count) {
+    if (!count) return fail(SX_ERR_INVALID, "null count");
+    *count = 0;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        cudaGetLastError();
+        return fail(SX_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    return SX_OK;
+}
+
+int sx_create(int device, sx_ctx **out) {
+    if (!out) return fail(SX_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    int n = 0;
+    int rc = sx_device_count(&n);
+    if (rc) return rc;
+    if (n == 0) return fail(SX_ERR_NO_DEVICE, "no CUDA device present (this engine has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(SX_ERR_NO_DEVICE, "device %d out of range (0..%d)", device, n - 1);
+    SX_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SX_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(SX_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    sx_ctx *c = new (std::nothrow) sx_ctx();
+    if (!c) return fail(SX_ERR_NOMEM, "out of host memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e != cudaSuccess) {
+        sx_destroy(c);
+        return fail(SX_ERR_CUDA, "context setup: %s", cudaGetErrorString(e));
+    }
+    c->stream = c->own_stream;
+    *out = c;
+    return SX_OK;
+}
+
+int sx_destroy(sx_ctx *c) {
+    if (!c) return SX_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (DevBuf *b : {&c->rowptr, &c->colidx, &c->val, &c->split_row, &c->split_seg_ptr, &c->seg_begin,
+                      &c->seg_end, &c->partial, &c->B, &c->Cin, &c->Cout, &c->stage})
+        b->release();
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return SX_OK;
+}
+
+int sx_set_stream(sx_ctx *c, void *cuda_stream) {
+    if (!c) return fail(SX_ERR_INVALID, "null context");
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return SX_OK;
+}
+
+int sx_set_option(sx_ctx *c, int option, int64_t value) {
+    if (!c) return fail(SX_ERR_INVALID, "null context");
+    switch (option) {
+        case SX_OPT_ARITH:
+            if (value != 0 && value != 1) return fail(SX_ERR_INVALID, "SX_OPT_ARITH is 0 (strict) or 1 (fast)");
+            c->arith = (int)value;
+            return SX_OK;
+        case SX_OPT_SPLIT_ROW_NNZ:
+            if (value < 0 || value > INT32_MAX) return fail(SX_ERR_INVALID, "SX_OPT_SPLIT_ROW_NNZ must be >= 0");
+            if (value != 0 && value < 32) return fail(SX_ERR_INVALID, "SX_OPT_SPLIT_ROW_NNZ must be 0 or >= 32");
+            c->split_nnz = (int)value;
+            c->segments_dirty = c->has_A;
+            return SX_OK;
+        case SX_OPT_KERNEL:
+            c->kernel = (int)value;
+            return SX_OK;
+        default:
+            return fail(SX_ERR_INVALID, "unknown option %d", option);
+    }
+}
+
+int sx_get_info(sx_ctx *c, int what, int64_t *value) {
+    if (!c || !value) return fail(SX_ERR_INVALID, "null argument");
+    if (c->segments_dirty) {
+        int rc = bind(c);
+        if (rc || (rc = refresh_segments(c))) return rc;
+    }
+    switch (what) {
+        case SX_INFO_LAUNCHES: *value = c->launches; return SX_OK;
+        case SX_INFO_M: *value = c->M; return SX_OK;
+        case SX_INFO_K: *value = c->K; return SX_OK;
+        case SX_INFO_NNZ: *value = c->nnz; return SX_OK;
+        case SX_INFO_DTYPE: *value = c->dtype; return SX_OK;
+        case SX_INFO_SPLIT_ROWS: *value = c->nsplit; return SX_OK;
+        case SX_INFO_LAST_KERNEL: *value = c->last_kernel; return SX_OK;
+        case SX_INFO_LD: *value = c->ld; return SX_OK;
+        default: return fail(SX_ERR_INVALID, "unknown info id %d", what);
+    }
+}
+
+int sx_synchronize(sx_ctx *c) {
+    int rc = bind(c);
+    if (rc) return rc;
+    SX_CUDA(cudaStreamSynchronize(c->stream));
+    return SX_OK;
+}
+
+int sx_upload_csr_f32(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rowptr, const int32_t *colidx, const float *val) {
+    return upload_csr<float>(c, M, K, nnz, rowptr, colidx, val);
+}
+int sx_upload_csr_f64(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rowptr, const int32_t *colidx, const double *val) {
+    return upload_csr<double>(c, M, K, nnz, rowptr, colidx, val);
+}
+
+int sx_spmm_f32(sx_ctx *c, int N, float alpha, const float *B, float beta, float *C, int rp_time, double *kernel_ns) {
+    return spmm_host<float>(c, N, alpha, B, beta, C, rp_time, kernel_ns);
+}
+int sx_spmm_f64(sx_ctx *c, int N, double alpha, const double *B, double beta, double *C, int rp_time, double *kernel_ns) {
+    return spmm_host<double>(c, N, alpha, B, beta, C, rp_time, kernel_ns);
+}
+
+int sx_stage_B_f32(sx_ctx *c, int N, const float *B) { return stage_dense<float>(c, N, B, true); }
+int sx_stage_B_f64(sx_ctx *c, int N, const double *B) { return stage_dense<double>(c, N, B, true); }
+int sx_stage_C_f32(sx_ctx *c, int N, const float *C) { return stage_dense<float>(c, N, C, false); }
+int sx_stage_C_f64(sx_ctx *c, int N, const double *C) { return stage_dense<double>(c, N, C, false); }
+int sx_launch_f32(sx_ctx *c, float alpha, float beta, int rp_time, double *ns) { return launch<float>(c, alpha, beta, rp_time, ns); }
+int sx_launch_f64(sx_ctx *c, double alpha, double beta, int rp_time, double *ns) { return launch<double>(c, alpha, beta, rp_time, ns); }
+int sx_fetch_C_f32(sx_ctx *c, float *C) { return fetch_C<float>(c, C); }
+int sx_fetch_C_f64(sx_ctx *c, double *C) { return fetch_C<double>(c, C); }
+
+int sx_device_B(sx_ctx *c, int N, void **dptr, size_t *bytes) {
+    int rc = bind(c);
+    if (rc) return rc;
+    if (!c->has_A) return fail(SX_ERR_STATE, "no matrix uploaded (call sx_upload_csr_* first)");
+    if (!dptr) return fail(SX_ERR_INVALID, "null dptr");
+    if ((rc = set_columns(c, N))) return rc;
+    const size_t need = std::max<size_t>((size_t)c->K * c->ld * dtype_size(c->dtype), 16);
+    const bool fresh = need > c->B.cap;
+    if ((rc = c->B.ensure(need))) return rc;
+    if (fresh) SX_CUDA(cudaMemsetAsync(c->B.p, 0, need, c->stream));
+    c->has_B = true;  // the caller fills it (e.g. a broadcast) before launching
+    *dptr = c->B.p;
+    if (bytes) *bytes = (size_t)c->K * c->ld * dtype_size(c->dtype);
+    return SX_OK;
+}
+
+int sx_spmm_device_f32(sx_ctx *c, int N, float alpha, const float *dB, int64_t ldb, float beta, const float *dCin, float *dCout, int64_t ldc) {
+    return spmm_device<float>(c, N, alpha, dB, ldb, beta, dCin, dCout, ldc);
+}
+int sx_spmm_device_f64(sx_ctx *c, int N, double alpha, const double *dB, int64_t ldb, double beta, const double *dCin, double *dCout, int64_t ldc) {
+    return spmm_device<double>(c, N, alpha, dB, ldb, beta, dCin, dCout, ldc);
+}
+
+int sx_colmajor_to_rowmajor(sx_ctx *c, int dtype, int64_t rows, int cols, const void *d_src, void *d_dst, int64_t ld_dst) {
+    int rc = bind(c);
+    if (rc) return rc;
+    if ((dtype != SX_F32 && dtype != SX_F64) || rows < 0 || cols < 1 || ld_dst < cols || !d_src || !d_dst)
+        return fail(SX_ERR_INVALID, "bad layout-change arguments");
+    return transpose_in(c, dtype, rows, cols, d_src, d_dst, ld_dst);
+}
+
+int sx_rowmajor_to_colmajor(sx_ctx *c, int dtype, int64_t rows, int cols, const void *d_src, int64_t ld_src, void *d_dst) {
+    int rc = bind(c);
+    if (rc) return rc;
+    if ((dtype != SX_F32 && dtype != SX_F64) || rows < 0 || cols < 1 || ld_src < cols || !d_src || !d_dst)
+        return fail(SX_ERR_INVALID, "bad layout-change arguments");
+    return transpose_out(c, dtype, rows, cols, d_src, ld_src, d_dst);
+}
+
+int sx_host_alloc(size_t bytes, void **ptr) {
+    if (!ptr) return fail(SX_ERR_INVALID, "null ptr");
+    *ptr = nullptr;
+    SX_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return SX_OK;
+}
+
+int sx_host_free(void *ptr) {
+    if (!ptr) return SX_OK;
+    SX_CUDA(cudaFreeHost(ptr));
+    return SX_OK;
+}
+
+}  // extern "C"
