@@ -299,7 +299,7 @@ def test_error_paths(eng):
             e.upload_csr(2, 2, np.array([0, 2, 1]), np.array([0]), np.ones(1, np.float32))
         e.upload_csr(2, 2, np.array([0, 1, 2]), np.array([0, 1]), np.ones(2, np.float32))
         with pytest.raises(sx.SextansError, match="INVALID"):
-            e._L.sx_spmm_f64(e._ctx, 8, 1.0, None, 0.0, None, 1, None)   # f64 call on an f32 matrix
+            sx._check(e._L.sx_spmm_f64(e._ctx, 8, 1.0, None, 0.0, None, 1, None))   # f64 call on an f32 matrix
         with pytest.raises(sx.SextansError, match="NO_DEVICE"):
             sx.Engine(1000)
     # an empty matrix and a matrix with only empty rows are fine
