@@ -57,6 +57,9 @@ def parse():
     p.add_argument("--dtype", default="", choices=["", "f32", "f64"])
     p.add_argument("--scale", type=float, default=1.0, help="shrink the synthetic workloads (testing)")
     p.add_argument("--arith", default="strict", choices=["strict", "fast"])
+    p.add_argument("--kernel", type=int, default=0, help="SX_OPT_KERNEL (0 work items, 1 row per group)")
+    p.add_argument("--item-nnz", type=int, default=0, help="SX_OPT_ITEM_NNZ (0 auto)")
+    p.add_argument("--split", type=int, default=-1, help="SX_OPT_SPLIT_ROW_NNZ (-1 default)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-flush", action="store_true", help="leave L2 warm between steps")
     return p.parse_args()
@@ -271,6 +274,10 @@ def run_native(args):
     eng = sx.Engine(local, arith=sx.STRICT if args.arith == "strict" else sx.FAST)
     stream = torch.cuda.Stream(device=dev)
     eng.set_stream(stream.cuda_stream)
+    eng.set_option(sx.OPT_KERNEL, args.kernel)
+    eng.set_option(sx.OPT_ITEM_NNZ, args.item_nnz)
+    if args.split >= 0:
+        eng.set_option(sx.OPT_SPLIT_ROW_NNZ, args.split)
     eng.upload_csr(M, K, w["rowptr"], w["colidx"], w["val"])
 
     # ---- device-resident operands (row-major images, ld = N rounded up to 8) ----------
@@ -382,7 +389,8 @@ def run_native(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(w["name"], N, "f64" if s == 8 else "f32"),
                          "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
-                         "kernel": f"spmm_rows_kernel (variant {eng.info(sx.INFO_LAST_KERNEL)})"},
+                         "kernel": f"{'spmm_rows_kernel' if args.kernel == 1 else 'spmm_items_kernel'} (variant {eng.info(sx.INFO_LAST_KERNEL)}, "
+                                   f"{eng.info(sx.INFO_ITEMS)} items of <= {eng.info(sx.INFO_ITEM_NNZ)} nnz, {eng.info(sx.INFO_SPLIT_ROWS)} split rows)"},
             "e2e": {"value": e2e, "unit": "GFLOP/s", "ms_per_step": e2e_s / args.steps * 1e3,
                     "h2d_bytes_per_step": (K * N + M * N) * s, "d2h_bytes_per_step": M * N * s,
                     "timer": "host wall clock around the blocking sx_spmm_* call"},

@@ -71,8 +71,11 @@ enum sx_option {
      * tree-reduced (summation order differs from the oracle; error ~ 1e-7 fp32 /
      * 1e-16 fp64 relative to the row's |a||b| sum).  0 disables splitting. */
     SX_OPT_SPLIT_ROW_NNZ = 1,
-    /* 0 auto; otherwise force a kernel variant */
-    SX_OPT_KERNEL = 2
+    /* 0 (default): work-item kernel (nnz-balanced runs of rows per lane group);
+     * 1: one lane group per row */
+    SX_OPT_KERNEL = 2,
+    /* nonzeros per work item; 0 = auto (<= 256, smaller for small matrices) */
+    SX_OPT_ITEM_NNZ = 3
 };
 
 enum sx_info {
@@ -83,7 +86,9 @@ enum sx_info {
     SX_INFO_DTYPE = 4,
     SX_INFO_SPLIT_ROWS = 5,  /* rows that take the split path */
     SX_INFO_LAST_KERNEL = 6, /* variant id of the last SpMM launch */
-    SX_INFO_LD = 7           /* leading dimension (elements) of the context's row-major B/C */
+    SX_INFO_LD = 7,          /* leading dimension (elements) of the context's row-major B/C */
+    SX_INFO_ITEMS = 8,       /* work items of the main kernel */
+    SX_INFO_ITEM_NNZ = 9     /* nonzero budget per work item in use */
 };
 
 /* ---- library ------------------------------------------------------------- */

@@ -83,6 +83,9 @@ struct sx_ctx {
     // long-row segments
     int nsplit = 0, nseg = 0;
     DevBuf split_row, split_seg_ptr, seg_begin, seg_end, partial;
+    // work items of the main kernel: runs of consecutive rows with ~item_nnz nonzeros
+    int nitems = 0, item_nnz_used = 0;
+    DevBuf items;
     std::vector<int32_t> h_rowptr;  // kept to re-derive segments when the option changes
 
     // dense operands (row-major, ld elements per row)
@@ -95,6 +98,7 @@ struct sx_ctx {
     int arith = 0;
     int split_nnz = 512;
     int kernel = 0;
+    int item_nnz = 0;  // 0 = auto
     bool segments_dirty = false;
 
     int64_t launches = 0;
@@ -137,11 +141,17 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
     const int threads = 256;
     const int rows_per_block = threads / G;
     const int split = c->nseg > 0 ? c->split_nnz : 0;
-    if (c->M > 0) {
+    if (c->M > 0 && c->kernel == 1) {
         const unsigned grid = (unsigned)(((int64_t)c->M + rows_per_block - 1) / rows_per_block);
         sx::spmm_rows_kernel<T, G, VPL, STRICT><<<grid, threads, 0, c->stream>>>(
             c->M, (const int *)c->rowptr.p, (const int *)c->colidx.p, (const T *)c->val.p, dB, ldb,
             dCin, dCout, ldc, alpha, beta, nvec, split);
+        c->launches++;
+    } else if (c->nitems > 0) {
+        const unsigned grid = (unsigned)(((int64_t)c->nitems + rows_per_block - 1) / rows_per_block);
+        sx::spmm_items_kernel<T, G, VPL, STRICT><<<grid, threads, 0, c->stream>>>(
+            c->nitems, (const int2 *)c->items.p, (const int *)c->rowptr.p, (const int *)c->colidx.p,
+            (const T *)c->val.p, dB, ldb, dCin, dCout, ldc, alpha, beta, nvec);
         c->launches++;
     }
     if (c->nseg > 0) {
@@ -158,7 +168,7 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
             (const T *)c->partial.p, ldp, dCin, dCout, ldc, alpha, beta, nvec);
         c->launches += 2;
     }
-    c->last_kernel = G * 100 + VPL * 10 + (STRICT ? 0 : 1);
+    c->last_kernel = (c->kernel == 1 ? 10000 : 0) + G * 100 + VPL * 10 + (STRICT ? 0 : 1);
     SX_CUDA(cudaGetLastError());
     return SX_OK;
 }
@@ -186,6 +196,7 @@ int launch_group(sx_ctx *c, Shape s, int N, T alpha, const T *dB, int64_t ldb, T
 }
 
 int refresh_segments(sx_ctx *c);
+int build_items(sx_ctx *c);
 
 // One SpMM over device-resident row-major operands.  Column counts beyond what one
 // row group covers (4 vectors x 32 lanes) are processed in column panels.
@@ -221,10 +232,58 @@ int spmm_device(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, con
 }
 
 // ---- A upload ---------------------------------------------------------------------
+// Work items of spmm_items_kernel: maximal runs of consecutive rows (none of them a
+// split row) whose nonzeros sum to <= budget; a single row above the budget is an item
+// of its own.  The budget shrinks for small matrices so that the grid still fills the
+// machine (one item never holds less than one row).
+int build_items(sx_ctx *c) {
+    c->nitems = 0;
+    if (c->M == 0) return SX_OK;
+    int budget = c->item_nnz;
+    if (budget <= 0) {
+        // aim at >= 8 resident warps' worth of items per SM before growing items
+        const int64_t want_items = (int64_t)c->sm_count * 64 * 8;
+        budget = (int)std::min<int64_t>(256, std::max<int64_t>(16, c->nnz / want_items));
+    }
+    c->item_nnz_used = budget;
+    const int split = c->split_nnz;
+    const int max_rows = 256;
+    std::vector<int32_t> items;
+    items.reserve((size_t)(c->nnz / budget + 16) * 2);
+    const int32_t *rp = c->h_rowptr.data();
+    int i = 0;
+    while (i < c->M) {
+        if (split > 0 && rp[i + 1] - rp[i] > split) { ++i; continue; }
+        const int start = i;
+        int total = 0;
+        while (i < c->M && i - start < max_rows) {
+            const int len = rp[i + 1] - rp[i];
+            if (split > 0 && len > split) break;
+            if (i > start && total + len > budget) break;
+            total += len;
+            ++i;
+        }
+        items.push_back(start);
+        items.push_back(i);
+    }
+    const size_t n = items.size() / 2;
+    if (n == 0) return SX_OK;
+    int rc = c->items.ensure(n * 8);
+    if (rc) return rc;
+    SX_CUDA(cudaMemcpyAsync(c->items.p, items.data(), n * 8, cudaMemcpyHostToDevice, c->stream));
+    SX_CUDA(cudaStreamSynchronize(c->stream));
+    c->nitems = (int)n;
+    return SX_OK;
+}
+
 int refresh_segments(sx_ctx *c) {
     c->segments_dirty = false;
     c->nsplit = c->nseg = 0;
     const int S = c->split_nnz;
+    {
+        int rc = build_items(c);
+        if (rc) return rc;
+    }
     if (S <= 0 || c->M == 0) return SX_OK;
     std::vector<int32_t> rows, segptr(1, 0), sb, se;
     for (int i = 0; i < c->M; ++i) {
@@ -462,7 +521,7 @@ int sx_destroy(sx_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (DevBuf *b : {&c->rowptr, &c->colidx, &c->val, &c->split_row, &c->split_seg_ptr, &c->seg_begin,
-                      &c->seg_end, &c->partial, &c->B, &c->Cin, &c->Cout, &c->stage})
+                      &c->seg_end, &c->partial, &c->items, &c->B, &c->Cin, &c->Cout, &c->stage})
         b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -491,7 +550,13 @@ int sx_set_option(sx_ctx *c, int option, int64_t value) {
             c->segments_dirty = c->has_A;
             return SX_OK;
         case SX_OPT_KERNEL:
+            if (value != 0 && value != 1) return fail(SX_ERR_INVALID, "SX_OPT_KERNEL is 0 (work items) or 1 (row per group)");
             c->kernel = (int)value;
+            return SX_OK;
+        case SX_OPT_ITEM_NNZ:
+            if (value < 0 || value > (1 << 20)) return fail(SX_ERR_INVALID, "SX_OPT_ITEM_NNZ must be in [0, 2^20]");
+            c->item_nnz = (int)value;
+            c->segments_dirty = c->has_A;
             return SX_OK;
         default:
             return fail(SX_ERR_INVALID, "unknown option %d", option);
@@ -513,6 +578,8 @@ int sx_get_info(sx_ctx *c, int what, int64_t *value) {
         case SX_INFO_SPLIT_ROWS: *value = c->nsplit; return SX_OK;
         case SX_INFO_LAST_KERNEL: *value = c->last_kernel; return SX_OK;
         case SX_INFO_LD: *value = c->ld; return SX_OK;
+        case SX_INFO_ITEMS: *value = c->nitems; return SX_OK;
+        case SX_INFO_ITEM_NNZ: *value = c->item_nnz_used; return SX_OK;
         default: return fail(SX_ERR_INVALID, "unknown info id %d", what);
     }
 }
