@@ -13,6 +13,7 @@ dev = torch.device("cuda:0")
 eng = sx.Engine(0)
 st = torch.cuda.Stream()
 eng.set_stream(st.cuda_stream)
+eng.set_option(sx.OPT_KERNEL, int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 eng.upload_csr(M, K, rp, ci, v)
 with torch.cuda.stream(st):
     B = torch.rand(K, N, device=dev) * 2 - 1

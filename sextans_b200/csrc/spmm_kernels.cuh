@@ -182,45 +182,113 @@ __device__ __forceinline__ void st_once(double2 *p, const double2 &v, uint64_t p
                  :: "l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
 }
 
-// ---- main kernel: one row group per work item --------------------------------------
-// A work item is a run of consecutive whole rows holding about the same number of
-// nonzeros as every other item (built at upload, sx_api.cu: build_items), the GPU
-// analogue of the reference's row -> PE assignment with padded, equal-length PE lists
-// (src/sparse_helper.h:345-403).  The G lanes of a group walk the item's nonzeros as
-// ONE stream -- (col, val) chunks are fetched G at a time with coalesced loads, one
-// chunk ahead, regardless of row boundaries -- and close a row (fused alpha/beta
-// epilogue, src/sextans.cpp:196-233) whenever the stream position reaches the next row
-// pointer.  Each row is still accumulated in stored order by a single accumulator per
-// output column, so strict mode stays bit-identical to cpu_spmm_CSR.
+// ---- mbarrier + TMA bulk copy (cp.async.bulk, SASS UBLKCP) ------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared, completion signalled on the mbarrier; 16-byte aligned, size % 16 == 0
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+
+// ---- main kernel, staged: A streams through shared memory by TMA -------------------
+// A work item is a run of consecutive whole rows, or a piece of one long row, holding
+// about the same number of nonzeros as every other item (built at upload, sx_api.cu:
+// build_plan) -- the GPU analogue of the reference's row -> PE assignment with equal-
+// length PE lists (src/sparse_helper.h:345-403).  One lane group (G lanes = one B/C
+// row of 16-byte vectors) owns one item:
+//   * its slice of colidx[] and val[] streams through a double-buffered shared-memory
+//     tile, filled by TMA bulk copies that complete on the group's own mbarriers (the
+//     TAPA stream channels read_A -> Scatter -> PEG of src/sextans.cpp:75-100,785-800
+//     become TMA + smem staging);
+//   * B rows are gathered with 16-byte LDGs through a register ring: the gathers of
+//     batch q+1 are issued before batch q is accumulated, so a lane keeps up to 2*U
+//     vectors in flight (scripts/micro/gather_bench.cu: plain LDG reaches 16-19 TB/s
+//     from L2, per-row TMA bulk copies 6.5-11 TB/s -- so B rows do not go through TMA);
+//   * a row is closed (fused alpha/beta epilogue, src/sextans.cpp:196-233) when the
+//     stream position reaches the next row pointer.  Every row is accumulated in stored
+//     order by one accumulator per output column, so strict mode is bit-identical to
+//     cpu_spmm_CSR for every row that is not split into pieces.
+//
+// item = {row_begin, row_end | ~partial_slot, nnz_begin, nnz_end}.  row_end >= 0: whole
+// rows [row_begin, row_end).  row_end < 0: a piece of long row row_begin whose raw sum
+// goes to partial[~row_end] for spmm_finalize_kernel.
+// ts = tile size in entries (power of two, >= 2*U); dynamic smem per block:
+//   GPB * (16 + 2*ts*(sizeof(T)+4)) bytes.
 template <typename T, int G, int VPL, bool STRICT>
 __global__ void __launch_bounds__(256)
-spmm_items_kernel(const int nitems, const int2 *__restrict__ items, const int *__restrict__ rowptr,
-                  const int *__restrict__ colidx, const T *__restrict__ val, const T *__restrict__ B,
-                  const int64_t ldb, const T *Cin, T *Cout, const int64_t ldc, const T alpha,
-                  const T beta, const int nvec) {
+spmm_staged_kernel(const int nitems, const int4 *__restrict__ items, const int ts,
+                   const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                   const T *__restrict__ val, const T *__restrict__ B, const int64_t ldb, const T *Cin,
+                   T *Cout, const int64_t ldc, T *__restrict__ partial, const int64_t ldp,
+                   const T alpha, const T beta, const int nvec) {
     using V = typename VecOf<T>::type;
-    constexpr int U = (G < 8 ? G : 8) / (VPL > 2 ? 2 : 1);  // B-row gathers in flight per lane
+    constexpr int U = (G < 8 ? G : 8) / (VPL > 2 ? 4 : VPL);  // gathers per batch per lane
+    constexpr int GPB = 256 / G;                               // lane groups per block
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // layout: [GPB][2] mbarriers | [GPB][2*ts] T values | [GPB][2*ts] int columns
     const int lane = threadIdx.x & 31;
     const int lg = lane & (G - 1);
+    const int gi = threadIdx.x / G;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - lg));
-    const int item = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G);
-    if (item >= nitems) return;  // whole groups leave together
-    const uint64_t pol = policy_evict_first();
-    const int2 it = __ldg(items + item);
-    int r = it.x;
-    const int re = it.y;
-    const int j0 = __ldg(rowptr + r), jend = __ldg(rowptr + re);
-    int rend = __ldg(rowptr + r + 1);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw) + 2 * gi;
+    T *sval = reinterpret_cast<T *>(smem_raw + GPB * 16) + (size_t)gi * 2 * ts;
+    int *scol = reinterpret_cast<int *>(smem_raw + GPB * 16 + (size_t)GPB * 2 * ts * sizeof(T)) + (size_t)gi * 2 * ts;
 
+    const int item = blockIdx.x * GPB + gi;
+    if (item >= nitems) return;  // whole groups leave together; no block-wide barrier below
+    const uint64_t pol = policy_evict_first();
+    const int4 it = __ldg(items + item);
+    const int jb = it.z, je = it.w;
+    const int jal = jb & ~3;      // 16-byte aligned start of both streams
+    const int off = jb - jal;     // entries of the first tile that belong to the previous item
+    const int len = je - jal;     // stream length counted from the aligned start
+    const int ring = 2 * ts - 1;  // entry e lives at smem index e & ring
+    const int bpt = ts / U;       // batches per tile (even)
+
+    auto load_tile = [&](const int k) {  // lane 0 of the group only
+        const int e0 = k * ts;
+        const uint32_t cnt = (uint32_t)min(ts, (len - e0 + 3) & ~3);
+        uint64_t *bk = bar + (k & 1);
+        mbar_expect_tx(bk, cnt * (uint32_t)(sizeof(T) + 4));
+        tma_bulk_g2s(scol + (e0 & ring), colidx + jal + e0, cnt * 4u, bk, pol);
+        tma_bulk_g2s(sval + (e0 & ring), val + jal + e0, cnt * (uint32_t)sizeof(T), bk, pol);
+    };
+    const int nt = (len + ts - 1) / ts;
+    if (je > jb) {
+        if (lg == 0) {
+            mbar_init(bar, 1);
+            mbar_init(bar + 1, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            load_tile(0);
+            if (nt > 1) load_tile(1);
+        }
+        __syncwarp(gmask);
+    }
+
+    int r = it.x;
+    const bool piece = it.y < 0;
+    const int re = piece ? r + 1 : it.y;
+    int rend = piece ? -1 : __ldg(rowptr + r + 1);
     V acc[VPL], cin[VPL];
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
         vzero(acc[v]);
+        vzero(cin[v]);
         const int vi = lg + v * G;
-        if (vi < nvec) cin[v] = ld_once(reinterpret_cast<const V *>(Cin + (int64_t)r * ldc) + vi, pol);
-        else vzero(cin[v]);
+        if (!piece && vi < nvec) cin[v] = ld_once(reinterpret_cast<const V *>(Cin + (int64_t)r * ldc) + vi, pol);
     }
-    // close row r: C[r] = alpha*acc + beta*C_in[r]; then open row r+1
     auto close_row = [&]() {
         V *cout = reinterpret_cast<V *>(Cout + (int64_t)r * ldc);
 #pragma unroll
@@ -238,52 +306,74 @@ spmm_items_kernel(const int nitems, const int2 *__restrict__ items, const int *_
                 if (vi < nvec) cin[v] = ld_once(reinterpret_cast<const V *>(Cin + (int64_t)r * ldc) + vi, pol);
             }
         } else {
-            rend = -1;  // no stream position equals it
+            rend = -1;
         }
     };
 
-    int base = j0 & ~(G - 1);  // chunks aligned to G entries: whole sectors per load
-    int c = 0;
-    T a = T(0);
-    if (base + lg >= j0 && base + lg < jend) { c = ld_stream(colidx + base + lg, pol); a = ld_stream(val + base + lg, pol); }
-    for (; base < jend; base += G) {
-        const int nbase = base + G;
-        int cn = 0;
-        T an = T(0);
-        if (nbase + lg < jend) { cn = ld_stream(colidx + nbase + lg, pol); an = ld_stream(val + nbase + lg, pol); }
+    if (je > jb) {
+        V b0[U][VPL], b1[U][VPL];
+        auto wait_tile = [&](const int k) { mbar_wait(bar + (k & 1), (uint32_t)((k >> 1) & 1)); };
+        // every lane of the group has finished with tile k: refill its buffer with tile k+2
+        auto release_tile = [&](const int k) {
+            __syncwarp(gmask);
+            if (lg == 0 && k + 2 < nt) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                load_tile(k + 2);
+            }
+        };
+        auto issue = [&](V (&b)[U][VPL], const int q) {
 #pragma unroll
-        for (int t0 = 0; t0 < G; t0 += U) {
-            if (base + t0 < jend && base + t0 + U > j0) {  // group-uniform
-                V b[U][VPL];
-                T av[U];
+            for (int u = 0; u < U; ++u) {
+                const int e = q * U + u;
+                const bool live = e >= off && e < len;
+                const int cc = live ? scol[e & ring] : 0;
+                const V *brow = reinterpret_cast<const V *>(B + (int64_t)cc * ldb);
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int p = base + t0 + u;
-                    const int cc = __shfl_sync(gmask, c, t0 + u, G);
-                    av[u] = __shfl_sync(gmask, a, t0 + u, G);
-                    const V *brow = reinterpret_cast<const V *>(B + (int64_t)cc * ldb);
-#pragma unroll
-                    for (int v = 0; v < VPL; ++v) {
-                        const int vi = lg + v * G;
-                        if (p >= j0 && p < jend && vi < nvec) b[u][v] = ldg_vec(brow + vi);
-                        else vzero(b[u][v]);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int p = base + t0 + u;
-                    if (p >= j0 && p < jend) {
-                        while (p == rend) close_row();  // also steps over empty rows
-#pragma unroll
-                        for (int v = 0; v < VPL; ++v) vmac<STRICT>(acc[v], av[u], b[u][v]);
-                    }
+                for (int v = 0; v < VPL; ++v) {
+                    const int vi = lg + v * G;
+                    if (live && vi < nvec) b[u][v] = ldg_vec(brow + vi);
+                    else vzero(b[u][v]);
                 }
             }
+        };
+        auto consume = [&](V (&b)[U][VPL], const int q) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = q * U + u;
+                if (e >= off && e < len) {
+                    while (jal + e == rend) close_row();  // also steps over empty rows
+                    const T a = sval[e & ring];
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) vmac<STRICT>(acc[v], a, b[u][v]);
+                }
+            }
+        };
+        const int nb = (len + U - 1) / U;
+        wait_tile(0);
+        issue(b0, 0);
+        for (int q = 0; q < nb; q += 2) {  // q even; tiles start at even q
+            if (q + 1 < nb) issue(b1, q + 1);
+            consume(b0, q);
+            if (q + 2 < nb) {
+                if ((q + 2) % bpt == 0) wait_tile((q + 2) / bpt);
+                issue(b0, q + 2);
+            }
+            if (q + 1 < nb) {
+                consume(b1, q + 1);
+                if ((q + 2) % bpt == 0) release_tile((q + 1) / bpt);
+            }
         }
-        c = cn;
-        a = an;
     }
-    while (r < re) close_row();  // the last row and any trailing empty rows
+    if (piece) {
+        V *out = reinterpret_cast<V *>(partial + (int64_t)(~it.y) * ldp);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const int vi = lg + v * G;
+            if (vi < nvec) out[vi] = acc[v];
+        }
+    } else {
+        while (r < re) close_row();  // the last row and any trailing empty rows
+    }
 }
 
 // ---- one row group per row (kept as variant 1) -------------------------------------

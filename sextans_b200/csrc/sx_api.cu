@@ -67,6 +67,16 @@ struct DevBuf {
 
 }  // namespace
 
+// Work items of spmm_staged_kernel for one nonzero budget per item.
+struct Plan {
+    int budget = 0;
+    int nitems = 0;   // whole-row runs + pieces
+    int npieces = 0;  // pieces of split rows (= rows of the partial buffer)
+    int nsplit = 0;   // split rows
+    DevBuf items, split_row, split_ptr;
+    void release() { items.release(); split_row.release(); split_ptr.release(); }
+};
+
 struct sx_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
@@ -83,9 +93,10 @@ struct sx_ctx {
     // long-row segments
     int nsplit = 0, nseg = 0;
     DevBuf split_row, split_seg_ptr, seg_begin, seg_end, partial;
-    // work items of the main kernel: runs of consecutive rows with ~item_nnz nonzeros
-    int nitems = 0, item_nnz_used = 0;
-    DevBuf items;
+    // work-item plans of the staged kernel, one per item budget in use (the budget
+    // depends on the lane-group width, i.e. on N)
+    std::vector<Plan *> plans;
+    Plan *last_plan = nullptr;
     std::vector<int32_t> h_rowptr;  // kept to re-derive segments when the option changes
 
     // dense operands (row-major, ld elements per row)
@@ -120,6 +131,11 @@ int bind(sx_ctx *c) {
     return SX_OK;
 }
 
+int refresh_segments(sx_ctx *c);
+int get_plan(sx_ctx *c, int budget, Plan **out);
+int pick_budget(const sx_ctx *c, int G);
+template <typename T, int G> int pick_tile(int U);
+
 // ---- kernel dispatch ------------------------------------------------------------
 // nvec = 16-byte vectors per dense row; G lanes per row group, VPL vectors per lane.
 struct Shape { int G, VPL; };
@@ -140,33 +156,57 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
     const int nvec = (N * (int)sizeof(T) + 15) / 16;
     const int threads = 256;
     const int rows_per_block = threads / G;
-    const int split = c->nseg > 0 ? c->split_nnz : 0;
-    if (c->M > 0 && c->kernel == 1) {
-        const unsigned grid = (unsigned)(((int64_t)c->M + rows_per_block - 1) / rows_per_block);
-        sx::spmm_rows_kernel<T, G, VPL, STRICT><<<grid, threads, 0, c->stream>>>(
-            c->M, (const int *)c->rowptr.p, (const int *)c->colidx.p, (const T *)c->val.p, dB, ldb,
-            dCin, dCout, ldc, alpha, beta, nvec, split);
+    const int64_t ldp = ((int64_t)N + 7) / 8 * 8;
+    int rc;
+    if (c->kernel == 1) {
+        // variant 1: one lane group per row + one warp per long-row segment
+        const int split = c->nseg > 0 ? c->split_nnz : 0;
+        if (c->M > 0) {
+            const unsigned grid = (unsigned)(((int64_t)c->M + rows_per_block - 1) / rows_per_block);
+            sx::spmm_rows_kernel<T, G, VPL, STRICT><<<grid, threads, 0, c->stream>>>(
+                c->M, (const int *)c->rowptr.p, (const int *)c->colidx.p, (const T *)c->val.p, dB, ldb,
+                dCin, dCout, ldc, alpha, beta, nvec, split);
+            c->launches++;
+        }
+        if (c->nseg > 0) {
+            if ((rc = c->partial.ensure((size_t)c->nseg * ldp * sizeof(T)))) return rc;
+            const unsigned gseg = (unsigned)(((int64_t)c->nseg * 32 + threads - 1) / threads);
+            sx::spmm_segments_kernel<T, G, VPL, STRICT><<<gseg, threads, 0, c->stream>>>(
+                c->nseg, (const int *)c->seg_begin.p, (const int *)c->seg_end.p,
+                (const int *)c->colidx.p, (const T *)c->val.p, dB, ldb, (T *)c->partial.p, ldp, nvec);
+            const unsigned gfin = (unsigned)(((int64_t)c->nsplit + rows_per_block - 1) / rows_per_block);
+            sx::spmm_finalize_kernel<T, G, VPL, STRICT><<<gfin, threads, 0, c->stream>>>(
+                c->nsplit, (const int *)c->split_row.p, (const int *)c->split_seg_ptr.p,
+                (const T *)c->partial.p, ldp, dCin, dCout, ldc, alpha, beta, nvec);
+            c->launches += 2;
+        }
+    } else if (c->M > 0) {
+        // variant 0: TMA-staged work items (+ finalize for rows split into pieces)
+        constexpr int U = (G < 8 ? G : 8) / (VPL > 2 ? 4 : VPL);
+        Plan *p = nullptr;
+        if ((rc = get_plan(c, pick_budget(c, G), &p))) return rc;
+        c->last_plan = p;
+        if (p->npieces > 0 && (rc = c->partial.ensure((size_t)p->npieces * ldp * sizeof(T)))) return rc;
+        const int ts = pick_tile<T, G>(U);
+        const size_t smem = (size_t)rows_per_block * (16 + 2 * (size_t)ts * (sizeof(T) + 4));
+        auto kern = sx::spmm_staged_kernel<T, G, VPL, STRICT>;
+        static thread_local const void *configured = nullptr;  // per instantiation
+        if (configured != (const void *)kern) {
+            SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            configured = (const void *)kern;
+        }
+        const unsigned grid = (unsigned)(((int64_t)p->nitems + rows_per_block - 1) / rows_per_block);
+        kern<<<grid, threads, smem, c->stream>>>(
+            p->nitems, (const int4 *)p->items.p, ts, (const int *)c->rowptr.p, (const int *)c->colidx.p,
+            (const T *)c->val.p, dB, ldb, dCin, dCout, ldc, (T *)c->partial.p, ldp, alpha, beta, nvec);
         c->launches++;
-    } else if (c->nitems > 0) {
-        const unsigned grid = (unsigned)(((int64_t)c->nitems + rows_per_block - 1) / rows_per_block);
-        sx::spmm_items_kernel<T, G, VPL, STRICT><<<grid, threads, 0, c->stream>>>(
-            c->nitems, (const int2 *)c->items.p, (const int *)c->rowptr.p, (const int *)c->colidx.p,
-            (const T *)c->val.p, dB, ldb, dCin, dCout, ldc, alpha, beta, nvec);
-        c->launches++;
-    }
-    if (c->nseg > 0) {
-        const int64_t ldp = ((int64_t)N + 7) / 8 * 8;
-        int rc = c->partial.ensure((size_t)c->nseg * ldp * sizeof(T));
-        if (rc) return rc;
-        const unsigned gseg = (unsigned)(((int64_t)c->nseg * 32 + threads - 1) / threads);
-        sx::spmm_segments_kernel<T, G, VPL, STRICT><<<gseg, threads, 0, c->stream>>>(
-            c->nseg, (const int *)c->seg_begin.p, (const int *)c->seg_end.p,
-            (const int *)c->colidx.p, (const T *)c->val.p, dB, ldb, (T *)c->partial.p, ldp, nvec);
-        const unsigned gfin = (unsigned)(((int64_t)c->nsplit + rows_per_block - 1) / rows_per_block);
-        sx::spmm_finalize_kernel<T, G, VPL, STRICT><<<gfin, threads, 0, c->stream>>>(
-            c->nsplit, (const int *)c->split_row.p, (const int *)c->split_seg_ptr.p,
-            (const T *)c->partial.p, ldp, dCin, dCout, ldc, alpha, beta, nvec);
-        c->launches += 2;
+        if (p->nsplit > 0) {
+            const unsigned gfin = (unsigned)(((int64_t)p->nsplit + rows_per_block - 1) / rows_per_block);
+            sx::spmm_finalize_kernel<T, G, VPL, STRICT><<<gfin, threads, 0, c->stream>>>(
+                p->nsplit, (const int *)p->split_row.p, (const int *)p->split_ptr.p,
+                (const T *)c->partial.p, ldp, dCin, dCout, ldc, alpha, beta, nvec);
+            c->launches++;
+        }
     }
     c->last_kernel = (c->kernel == 1 ? 10000 : 0) + G * 100 + VPL * 10 + (STRICT ? 0 : 1);
     SX_CUDA(cudaGetLastError());
@@ -195,8 +235,6 @@ int launch_group(sx_ctx *c, Shape s, int N, T alpha, const T *dB, int64_t ldb, T
     }
 }
 
-int refresh_segments(sx_ctx *c);
-int build_items(sx_ctx *c);
 
 // One SpMM over device-resident row-major operands.  Column counts beyond what one
 // row group covers (4 vectors x 32 lanes) are processed in column panels.
@@ -232,28 +270,41 @@ int spmm_device(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, con
 }
 
 // ---- A upload ---------------------------------------------------------------------
-// Work items of spmm_items_kernel: maximal runs of consecutive rows (none of them a
-// split row) whose nonzeros sum to <= budget; a single row above the budget is an item
-// of its own.  The budget shrinks for small matrices so that the grid still fills the
-// machine (one item never holds less than one row).
-int build_items(sx_ctx *c) {
-    c->nitems = 0;
-    if (c->M == 0) return SX_OK;
-    int budget = c->item_nnz;
-    if (budget <= 0) {
-        // aim at >= 8 resident warps' worth of items per SM before growing items
-        const int64_t want_items = (int64_t)c->sm_count * 64 * 8;
-        budget = (int)std::min<int64_t>(256, std::max<int64_t>(16, c->nnz / want_items));
-    }
-    c->item_nnz_used = budget;
+void drop_plans(sx_ctx *c) {
+    for (Plan *p : c->plans) { p->release(); delete p; }
+    c->plans.clear();
+    c->last_plan = nullptr;
+}
+
+// Work items for a nonzero budget: rows longer than the split threshold become pieces
+// of <= budget nonzeros (summed later by spmm_finalize_kernel, in piece order); all
+// other rows are grouped into maximal runs of consecutive rows with <= budget nonzeros
+// (a single row above the budget is an item of its own and stays bit-exact).
+int get_plan(sx_ctx *c, int budget, Plan **out) {
+    for (Plan *p : c->plans)
+        if (p->budget == budget) { *out = p; return SX_OK; }
+    Plan *p = new (std::nothrow) Plan();
+    if (!p) return fail(SX_ERR_NOMEM, "out of host memory");
+    p->budget = budget;
     const int split = c->split_nnz;
     const int max_rows = 256;
-    std::vector<int32_t> items;
-    items.reserve((size_t)(c->nnz / budget + 16) * 2);
+    std::vector<int32_t> items, srow, sptr(1, 0);
+    items.reserve((size_t)(c->nnz / budget + 16) * 4);
     const int32_t *rp = c->h_rowptr.data();
+    int npieces = 0;
     int i = 0;
     while (i < c->M) {
-        if (split > 0 && rp[i + 1] - rp[i] > split) { ++i; continue; }
+        const int len0 = rp[i + 1] - rp[i];
+        if (split > 0 && len0 > split) {
+            srow.push_back(i);
+            for (int j = rp[i]; j < rp[i + 1]; j += budget) {
+                items.insert(items.end(), {i, ~npieces, j, std::min(rp[i + 1], j + budget)});
+                ++npieces;
+            }
+            sptr.push_back(npieces);
+            ++i;
+            continue;
+        }
         const int start = i;
         int total = 0;
         while (i < c->M && i - start < max_rows) {
@@ -263,27 +314,53 @@ int build_items(sx_ctx *c) {
             total += len;
             ++i;
         }
-        items.push_back(start);
-        items.push_back(i);
+        items.insert(items.end(), {start, i, rp[start], rp[i]});
     }
-    const size_t n = items.size() / 2;
-    if (n == 0) return SX_OK;
-    int rc = c->items.ensure(n * 8);
-    if (rc) return rc;
-    SX_CUDA(cudaMemcpyAsync(c->items.p, items.data(), n * 8, cudaMemcpyHostToDevice, c->stream));
-    SX_CUDA(cudaStreamSynchronize(c->stream));
-    c->nitems = (int)n;
+    p->nitems = (int)(items.size() / 4);
+    p->npieces = npieces;
+    p->nsplit = (int)srow.size();
+    int rc = SX_OK;
+    if (p->nitems > 0) {
+        if (!(rc = p->items.ensure(items.size() * 4)))
+            if (cudaMemcpyAsync(p->items.p, items.data(), items.size() * 4, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+                rc = fail(SX_ERR_CUDA, "plan upload failed");
+    }
+    if (!rc && p->nsplit > 0) {
+        if (!(rc = p->split_row.ensure(srow.size() * 4)) && !(rc = p->split_ptr.ensure(sptr.size() * 4))) {
+            if (cudaMemcpyAsync(p->split_row.p, srow.data(), srow.size() * 4, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+                cudaMemcpyAsync(p->split_ptr.p, sptr.data(), sptr.size() * 4, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+                rc = fail(SX_ERR_CUDA, "plan upload failed");
+        }
+    }
+    if (!rc && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(SX_ERR_CUDA, "plan upload failed");
+    if (rc) { p->release(); delete p; return rc; }
+    c->plans.push_back(p);
+    *out = p;
     return SX_OK;
+}
+
+// Nonzeros per work item for lane groups of G lanes: 256, less when the matrix is so
+// small that 256 would leave SMs without work (an item never holds less than one row).
+int pick_budget(const sx_ctx *c, int G) {
+    if (c->item_nnz > 0) return c->item_nnz;
+    const int64_t want_items = (int64_t)c->sm_count * (256 / G) * 4;
+    return (int)std::min<int64_t>(256, std::max<int64_t>(16, c->nnz / want_items));
+}
+
+// tile size (entries, power of two) of the staged kernel: ~48 KB of staging per block
+template <typename T, int G>
+int pick_tile(int U) {
+    const int gpb = 256 / G;
+    int ts = 16;
+    while (ts < 128 && (size_t)gpb * (16 + 4 * ts * (sizeof(T) + 4)) <= 48 * 1024) ts *= 2;  // test is for 2*ts
+    return std::max(ts, 2 * U);
 }
 
 int refresh_segments(sx_ctx *c) {
     c->segments_dirty = false;
     c->nsplit = c->nseg = 0;
     const int S = c->split_nnz;
-    {
-        int rc = build_items(c);
-        if (rc) return rc;
-    }
+    drop_plans(c);
     if (S <= 0 || c->M == 0) return SX_OK;
     std::vector<int32_t> rows, segptr(1, 0), sb, se;
     for (int i = 0; i < c->M; ++i) {
@@ -329,8 +406,8 @@ int upload_csr(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rowptr, cons
             return fail(SX_ERR_INVALID, "column index %d out of range at nonzero %lld", colidx[j], (long long)j);
     c->has_A = false;
     if ((rc = c->rowptr.ensure(((size_t)M + 1) * 4))) return rc;
-    if ((rc = c->colidx.ensure(std::max<size_t>(16, (size_t)nnz * 4)))) return rc;
-    if ((rc = c->val.ensure(std::max<size_t>(16, (size_t)nnz * sizeof(T))))) return rc;
+    if ((rc = c->colidx.ensure((size_t)nnz * 4 + 16))) return rc;  // +16: TMA reads whole 16-byte units
+    if ((rc = c->val.ensure((size_t)nnz * sizeof(T) + 32))) return rc;
     SX_CUDA(cudaMemcpyAsync(c->rowptr.p, rowptr, ((size_t)M + 1) * 4, cudaMemcpyHostToDevice, c->stream));
     if (nnz > 0) {
         SX_CUDA(cudaMemcpyAsync(c->colidx.p, colidx, (size_t)nnz * 4, cudaMemcpyHostToDevice, c->stream));
@@ -521,8 +598,9 @@ int sx_destroy(sx_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (DevBuf *b : {&c->rowptr, &c->colidx, &c->val, &c->split_row, &c->split_seg_ptr, &c->seg_begin,
-                      &c->seg_end, &c->partial, &c->items, &c->B, &c->Cin, &c->Cout, &c->stage})
+                      &c->seg_end, &c->partial, &c->B, &c->Cin, &c->Cout, &c->stage})
         b->release();
+    drop_plans(c);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -550,11 +628,11 @@ int sx_set_option(sx_ctx *c, int option, int64_t value) {
             c->segments_dirty = c->has_A;
             return SX_OK;
         case SX_OPT_KERNEL:
-            if (value != 0 && value != 1) return fail(SX_ERR_INVALID, "SX_OPT_KERNEL is 0 (work items) or 1 (row per group)");
+            if (value != 0 && value != 1) return fail(SX_ERR_INVALID, "SX_OPT_KERNEL is 0 (TMA-staged work items) or 1 (row per group)");
             c->kernel = (int)value;
             return SX_OK;
         case SX_OPT_ITEM_NNZ:
-            if (value < 0 || value > (1 << 20)) return fail(SX_ERR_INVALID, "SX_OPT_ITEM_NNZ must be in [0, 2^20]");
+            if (value < 0 || value > (1 << 20) || (value != 0 && value < 4)) return fail(SX_ERR_INVALID, "SX_OPT_ITEM_NNZ must be 0 or in [4, 2^20]");
             c->item_nnz = (int)value;
             c->segments_dirty = c->has_A;
             return SX_OK;
@@ -575,11 +653,11 @@ int sx_get_info(sx_ctx *c, int what, int64_t *value) {
         case SX_INFO_K: *value = c->K; return SX_OK;
         case SX_INFO_NNZ: *value = c->nnz; return SX_OK;
         case SX_INFO_DTYPE: *value = c->dtype; return SX_OK;
-        case SX_INFO_SPLIT_ROWS: *value = c->nsplit; return SX_OK;
+        case SX_INFO_SPLIT_ROWS: *value = (c->kernel == 1 || !c->last_plan) ? c->nsplit : c->last_plan->nsplit; return SX_OK;
         case SX_INFO_LAST_KERNEL: *value = c->last_kernel; return SX_OK;
         case SX_INFO_LD: *value = c->ld; return SX_OK;
-        case SX_INFO_ITEMS: *value = c->nitems; return SX_OK;
-        case SX_INFO_ITEM_NNZ: *value = c->item_nnz_used; return SX_OK;
+        case SX_INFO_ITEMS: *value = c->last_plan ? c->last_plan->nitems : 0; return SX_OK;
+        case SX_INFO_ITEM_NNZ: *value = c->last_plan ? c->last_plan->budget : 0; return SX_OK;
         default: return fail(SX_ERR_INVALID, "unknown info id %d", what);
     }
 }
