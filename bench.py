@@ -57,7 +57,7 @@ def parse():
     p.add_argument("--dtype", default="", choices=["", "f32", "f64"])
     p.add_argument("--scale", type=float, default=1.0, help="shrink the synthetic workloads (testing)")
     p.add_argument("--arith", default="strict", choices=["strict", "fast"])
-    p.add_argument("--kernel", type=int, default=0, help="SX_OPT_KERNEL (0 work items, 1 row per group)")
+    p.add_argument("--kernel", type=int, default=0, help="SX_OPT_KERNEL (0 auto, 1 row per group, 2 TMA-staged items, 3 warp per row)")
     p.add_argument("--item-nnz", type=int, default=0, help="SX_OPT_ITEM_NNZ (0 auto)")
     p.add_argument("--split", type=int, default=-1, help="SX_OPT_SPLIT_ROW_NNZ (-1 default)")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -373,6 +373,11 @@ def run_native(args):
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
 
+    lk = eng.info(sx.INFO_LAST_KERNEL)
+    kernel_name = ({1: "spmm_rows_kernel (+segments/finalize)", 2: "spmm_staged_kernel", 3: "spmm_warprow_kernel"}.get(lk // 10000, "?")
+                   + f" <G={lk % 10000 // 100}, VPL={lk % 100 // 10}, {'fast' if lk % 10 else 'strict'}>"
+                   + (f", {eng.info(sx.INFO_ITEMS)} items of <= {eng.info(sx.INFO_ITEM_NNZ)} nnz, {eng.info(sx.INFO_SPLIT_ROWS)} split rows" if lk // 10000 == 2 else ""))
+    host_path = "zero-copy kernels over PCIe (no memcpy)" if eng.info(sx.INFO_HOST_PATH) == 1 else "cudaMemcpyAsync + layout kernels"
     if rank == 0:
         line = {
             "metric": "SpMM GFLOP/s (2*nnz*N)", "value": value, "unit": "GFLOP/s",
@@ -389,11 +394,10 @@ def run_native(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(w["name"], N, "f64" if s == 8 else "f32"),
                          "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
-                         "kernel": f"{'spmm_rows_kernel' if args.kernel == 1 else 'spmm_items_kernel'} (variant {eng.info(sx.INFO_LAST_KERNEL)}, "
-                                   f"{eng.info(sx.INFO_ITEMS)} items of <= {eng.info(sx.INFO_ITEM_NNZ)} nnz, {eng.info(sx.INFO_SPLIT_ROWS)} split rows)"},
+                         "kernel": kernel_name},
             "e2e": {"value": e2e, "unit": "GFLOP/s", "ms_per_step": e2e_s / args.steps * 1e3,
                     "h2d_bytes_per_step": (K * N + M * N) * s, "d2h_bytes_per_step": M * N * s,
-                    "timer": "host wall clock around the blocking sx_spmm_* call"},
+                    "timer": "host wall clock around the blocking sx_spmm_* call", "path": host_path},
             "gpu_launches": int(launches_dev + launches_e2e),
             "gpu_launches_detail": {"device_steps": int(launches_dev), "e2e_steps": int(launches_e2e)},
             "clocks": clocks, "checksum_C": checksum,

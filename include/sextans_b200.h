@@ -64,18 +64,25 @@ enum sx_dtype { SX_F32 = 0, SX_F64 = 1 };
 enum sx_option {
     /* 0 (default) "strict": every product and every sum separately rounded, each
      * row's nonzeros accumulated in stored order -- bit-identical to cpu_spmm_CSR
-     * (src/sparse_helper.h:283,287) for rows up to SX_OPT_SPLIT_ROW_NNZ.
+     * (src/sparse_helper.h:283,287) for rows up to SX_OPT_SPLIT_ROW_NNZ nonzeros.
      * 1 "fast": fused multiply-add. */
     SX_OPT_ARITH = 0,
     /* rows with more nonzeros than this are split across a whole thread block and
      * tree-reduced (summation order differs from the oracle; error ~ 1e-7 fp32 /
      * 1e-16 fp64 relative to the row's |a||b| sum).  0 disables splitting. */
     SX_OPT_SPLIT_ROW_NNZ = 1,
-    /* 0 (default): work-item kernel (nnz-balanced runs of rows per lane group);
-     * 1: one lane group per row */
+    /* kernel variant: 0 auto (3 for matrices with fewer rows than the GPU
+     * has warp slots, else 2); 1 one lane group per row (+ one warp per long-row
+     * segment); 2 TMA-staged nnz-balanced work items; 3 one warp per row with
+     * parallel gathers and in-order summation (N*sizeof(T) <= 256 bytes only) */
     SX_OPT_KERNEL = 2,
     /* nonzeros per work item; 0 = auto (<= 256, smaller for small matrices) */
-    SX_OPT_ITEM_NNZ = 3
+    SX_OPT_ITEM_NNZ = 3,
+    /* sx_spmm_*: page-locked host B and C of up to this many bytes together are read
+     * and written by the kernels directly over PCIe (no copy-engine transfers);
+     * larger or pageable operands go through cudaMemcpyAsync.  Default 16 MiB; 0
+     * disables. */
+    SX_OPT_ZEROCOPY_BYTES = 4
 };
 
 enum sx_info {
@@ -88,7 +95,8 @@ enum sx_info {
     SX_INFO_LAST_KERNEL = 6, /* variant id of the last SpMM launch */
     SX_INFO_LD = 7,          /* leading dimension (elements) of the context's row-major B/C */
     SX_INFO_ITEMS = 8,       /* work items of the main kernel */
-    SX_INFO_ITEM_NNZ = 9     /* nonzero budget per work item in use */
+    SX_INFO_ITEM_NNZ = 9,    /* nonzero budget per work item in use */
+    SX_INFO_HOST_PATH = 10   /* 1 if the last sx_spmm_* call took the zero-copy path */
 };
 
 /* ---- library ------------------------------------------------------------- */

@@ -224,14 +224,58 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 // item = {row_begin, row_end | ~partial_slot, nnz_begin, nnz_end}.  row_end >= 0: whole
 // rows [row_begin, row_end).  row_end < 0: a piece of long row row_begin whose raw sum
 // goes to partial[~row_end] for spmm_finalize_kernel.
-// ts = tile size in entries (power of two, >= 2*U); dynamic smem per block:
+// ts = tile size in entries (power of two, a multiple of U); dynamic smem per block:
 //   GPB * (16 + 2*ts*(sizeof(T)+4)) bytes.
+//
+// The hot loop is kept lean on purpose (the first version of this kernel spent ~58
+// instructions per nonzero on liveness tests, 64-bit index arithmetic and divergence
+// bookkeeping and was issue-bound): a batch of U entries takes the CLEAN path -- vector
+// LDS of U columns and values, U x (IMAD.WIDE + LDG.128), U multiply-adds -- unless the
+// item starts/ends inside it or a row ends inside it.
+template <int U> __device__ __forceinline__ void lds_vec(const int *p, int (&c)[U]) {
+    if constexpr (U % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < U; i += 4) {
+            const int4 t = *reinterpret_cast<const int4 *>(p + i);
+            c[i] = t.x; c[i + 1] = t.y; c[i + 2] = t.z; c[i + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < U; i += 2) {
+            const int2 t = *reinterpret_cast<const int2 *>(p + i);
+            c[i] = t.x; c[i + 1] = t.y;
+        }
+    }
+}
+template <int U> __device__ __forceinline__ void lds_vec(const float *p, float (&a)[U]) {
+    if constexpr (U % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < U; i += 4) {
+            const float4 t = *reinterpret_cast<const float4 *>(p + i);
+            a[i] = t.x; a[i + 1] = t.y; a[i + 2] = t.z; a[i + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < U; i += 2) {
+            const float2 t = *reinterpret_cast<const float2 *>(p + i);
+            a[i] = t.x; a[i + 1] = t.y;
+        }
+    }
+}
+template <int U> __device__ __forceinline__ void lds_vec(const double *p, double (&a)[U]) {
+#pragma unroll
+    for (int i = 0; i < U; i += 2) {
+        const double2 t = *reinterpret_cast<const double2 *>(p + i);
+        a[i] = t.x; a[i + 1] = t.y;
+    }
+}
+
 template <typename T, int G, int VPL, bool STRICT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (VPL > 1 ? 2 : (sizeof(T) == 8 ? 3 : 4)))
 spmm_staged_kernel(const int nitems, const int4 *__restrict__ items, const int ts,
                    const int *__restrict__ rowptr, const int *__restrict__ colidx,
-                   const T *__restrict__ val, const T *__restrict__ B, const int64_t ldb, const T *Cin,
-                   T *Cout, const int64_t ldc, T *__restrict__ partial, const int64_t ldp,
+                   const T *__restrict__ val, const T *__restrict__ B, const uint32_t ldbv, const T *Cin,
+                   T *Cout, const uint32_t ldcv, T *__restrict__ partial, const uint32_t ldpv,
                    const T alpha, const T beta, const int nvec) {
     using V = typename VecOf<T>::type;
     constexpr int U = (G < 8 ? G : 8) / (VPL > 2 ? 4 : VPL);  // gathers per batch per lane
@@ -243,27 +287,26 @@ spmm_staged_kernel(const int nitems, const int4 *__restrict__ items, const int t
     const int gi = threadIdx.x / G;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - lg));
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw) + 2 * gi;
-    T *sval = reinterpret_cast<T *>(smem_raw + GPB * 16) + (size_t)gi * 2 * ts;
-    int *scol = reinterpret_cast<int *>(smem_raw + GPB * 16 + (size_t)GPB * 2 * ts * sizeof(T)) + (size_t)gi * 2 * ts;
+    const T *sval = reinterpret_cast<const T *>(smem_raw + GPB * 16) + (size_t)gi * 2 * ts;
+    const int *scol = reinterpret_cast<const int *>(smem_raw + GPB * 16 + (size_t)GPB * 2 * ts * sizeof(T)) + (size_t)gi * 2 * ts;
 
     const int item = blockIdx.x * GPB + gi;
     if (item >= nitems) return;  // whole groups leave together; no block-wide barrier below
     const uint64_t pol = policy_evict_first();
     const int4 it = __ldg(items + item);
     const int jb = it.z, je = it.w;
-    const int jal = jb & ~3;      // 16-byte aligned start of both streams
-    const int off = jb - jal;     // entries of the first tile that belong to the previous item
+    const int jal = jb & ~(U < 4 ? 3 : U - 1);  // batch- and 16-byte-aligned start of both streams
+    const int off = jb - jal;     // leading entries that belong to the previous item
     const int len = je - jal;     // stream length counted from the aligned start
     const int ring = 2 * ts - 1;  // entry e lives at smem index e & ring
-    const int bpt = ts / U;       // batches per tile (even)
 
     auto load_tile = [&](const int k) {  // lane 0 of the group only
         const int e0 = k * ts;
         const uint32_t cnt = (uint32_t)min(ts, (len - e0 + 3) & ~3);
         uint64_t *bk = bar + (k & 1);
         mbar_expect_tx(bk, cnt * (uint32_t)(sizeof(T) + 4));
-        tma_bulk_g2s(scol + (e0 & ring), colidx + jal + e0, cnt * 4u, bk, pol);
-        tma_bulk_g2s(sval + (e0 & ring), val + jal + e0, cnt * (uint32_t)sizeof(T), bk, pol);
+        tma_bulk_g2s(const_cast<int *>(scol) + (e0 & ring), colidx + jal + e0, cnt * 4u, bk, pol);
+        tma_bulk_g2s(const_cast<T *>(sval) + (e0 & ring), val + jal + e0, cnt * (uint32_t)sizeof(T), bk, pol);
     };
     const int nt = (len + ts - 1) / ts;
     if (je > jb) {
@@ -280,100 +323,191 @@ spmm_staged_kernel(const int nitems, const int4 *__restrict__ items, const int t
     int r = it.x;
     const bool piece = it.y < 0;
     const int re = piece ? r + 1 : it.y;
-    int rend = piece ? -1 : __ldg(rowptr + r + 1);
+    int rend = piece ? -1 : __ldg(rowptr + r + 1) - jal;  // in stream coordinates
+    const V *Bv = reinterpret_cast<const V *>(B) + lg;
+    const V *Cv = reinterpret_cast<const V *>(Cin) + lg;
     V acc[VPL], cin[VPL];
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
         vzero(acc[v]);
         vzero(cin[v]);
-        const int vi = lg + v * G;
-        if (!piece && vi < nvec) cin[v] = ld_once(reinterpret_cast<const V *>(Cin + (int64_t)r * ldc) + vi, pol);
+        if (!piece && lg + v * G < nvec) cin[v] = ld_once(Cv + (size_t)r * ldcv + v * G, pol);
     }
     auto close_row = [&]() {
-        V *cout = reinterpret_cast<V *>(Cout + (int64_t)r * ldc);
+        V *cout = reinterpret_cast<V *>(Cout) + (size_t)r * ldcv + lg;
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
-            const int vi = lg + v * G;
-            if (vi < nvec) st_once(cout + vi, vaxpby<STRICT>(alpha, acc[v], beta, cin[v]), pol);
+            if (lg + v * G < nvec) st_once(cout + v * G, vaxpby<STRICT>(alpha, acc[v], beta, cin[v]), pol);
             vzero(acc[v]);
         }
         ++r;
         if (r < re) {
-            rend = __ldg(rowptr + r + 1);
+            rend = __ldg(rowptr + r + 1) - jal;
 #pragma unroll
-            for (int v = 0; v < VPL; ++v) {
-                const int vi = lg + v * G;
-                if (vi < nvec) cin[v] = ld_once(reinterpret_cast<const V *>(Cin + (int64_t)r * ldc) + vi, pol);
-            }
+            for (int v = 0; v < VPL; ++v)
+                if (lg + v * G < nvec) cin[v] = ld_once(Cv + (size_t)r * ldcv + v * G, pol);
         } else {
             rend = -1;
         }
     };
 
     if (je > jb) {
-        V b0[U][VPL], b1[U][VPL];
-        auto wait_tile = [&](const int k) { mbar_wait(bar + (k & 1), (uint32_t)((k >> 1) & 1)); };
-        // every lane of the group has finished with tile k: refill its buffer with tile k+2
-        auto release_tile = [&](const int k) {
-            __syncwarp(gmask);
-            if (lg == 0 && k + 2 < nt) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                load_tile(k + 2);
-            }
-        };
-        auto issue = [&](V (&b)[U][VPL], const int q) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int e = q * U + u;
-                const bool live = e >= off && e < len;
-                const int cc = live ? scol[e & ring] : 0;
-                const V *brow = reinterpret_cast<const V *>(B + (int64_t)cc * ldb);
-#pragma unroll
-                for (int v = 0; v < VPL; ++v) {
-                    const int vi = lg + v * G;
-                    if (live && vi < nvec) b[u][v] = ldg_vec(brow + vi);
-                    else vzero(b[u][v]);
-                }
-            }
-        };
-        auto consume = [&](V (&b)[U][VPL], const int q) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int e = q * U + u;
-                if (e >= off && e < len) {
-                    while (jal + e == rend) close_row();  // also steps over empty rows
-                    const T a = sval[e & ring];
-#pragma unroll
-                    for (int v = 0; v < VPL; ++v) vmac<STRICT>(acc[v], a, b[u][v]);
-                }
-            }
-        };
+        const int bpt = ts / U;  // batches per tile
         const int nb = (len + U - 1) / U;
-        wait_tile(0);
-        issue(b0, 0);
-        for (int q = 0; q < nb; q += 2) {  // q even; tiles start at even q
-            if (q + 1 < nb) issue(b1, q + 1);
-            consume(b0, q);
-            if (q + 2 < nb) {
-                if ((q + 2) % bpt == 0) wait_tile((q + 2) / bpt);
-                issue(b0, q + 2);
+        for (int q = 0; q < nb; ++q) {
+            const int e0 = q * U;
+            if (q % bpt == 0) mbar_wait(bar + ((q / bpt) & 1), (uint32_t)(((q / bpt) >> 1) & 1));
+            const int idx = e0 & ring;
+            int cc[U];
+            T av[U];
+            V b[U][VPL];
+            lds_vec<U>(scol + idx, cc);
+            if (e0 >= off && e0 + U <= len) {
+                // every entry of the batch belongs to the item
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const V *brow = Bv + (size_t)(uint32_t)cc[u] * ldbv;
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) {
+                        if (VPL == 1 || lg + v * G < nvec) b[u][v] = ldg_vec(brow + v * G);
+                        else vzero(b[u][v]);
+                    }
+                }
+                lds_vec<U>(sval + idx, av);
+                if ((unsigned)(rend - e0) >= (unsigned)U) {
+                    // clean: no row ends inside the batch
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v) vmac<STRICT>(acc[v], av[u], b[u][v]);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        while (e0 + u == rend) close_row();  // also steps over empty rows
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v) vmac<STRICT>(acc[v], av[u], b[u][v]);
+                    }
+                }
+            } else {
+                // first / last batch of the item: per-entry liveness
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool live = e0 + u >= off && e0 + u < len;
+                    const V *brow = Bv + (size_t)(uint32_t)(live ? cc[u] : 0) * ldbv;
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) {
+                        if (live && lg + v * G < nvec) b[u][v] = ldg_vec(brow + v * G);
+                        else vzero(b[u][v]);
+                    }
+                }
+                lds_vec<U>(sval + idx, av);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (e0 + u >= off && e0 + u < len) {
+                        while (e0 + u == rend) close_row();
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v) vmac<STRICT>(acc[v], av[u], b[u][v]);
+                    }
+                }
             }
-            if (q + 1 < nb) {
-                consume(b1, q + 1);
-                if ((q + 2) % bpt == 0) release_tile((q + 1) / bpt);
+            if ((q + 1) % bpt == 0) {
+                // the whole group is done with this tile: refill its buffer with tile +2
+                const int k = q / bpt;
+                __syncwarp(gmask);
+                if (lg == 0 && k + 2 < nt) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    load_tile(k + 2);
+                }
             }
         }
     }
     if (piece) {
-        V *out = reinterpret_cast<V *>(partial + (int64_t)(~it.y) * ldp);
+        V *out = reinterpret_cast<V *>(partial) + (size_t)(~it.y) * ldpv + lg;
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-            const int vi = lg + v * G;
-            if (vi < nvec) out[vi] = acc[v];
-        }
+        for (int v = 0; v < VPL; ++v)
+            if (lg + v * G < nvec) out[v * G] = acc[v];
     } else {
         while (r < re) close_row();  // the last row and any trailing empty rows
     }
+}
+
+// ---- small matrices: one warp per row, gathers in parallel, sum in order ------------
+// The shipped SuiteSparse inputs (nasa4704: 4 704 rows, pcrystk02: 13 965) give a B200
+// fewer rows than it has warp slots, so what matters is the length of the dependent
+// memory chain, not bandwidth.  Here a whole warp takes one row: 32 (col, val) entries
+// arrive with one coalesced load, the 32/G lane groups gather their B rows side by
+// side, every product is rounded where it was gathered, and the products are then
+// handed to lane group 0 by shuffle and added IN STORED ORDER -- so the result is still
+// bit-identical to cpu_spmm_CSR, while the chain is rowptr -> entries -> B rows.
+template <typename T> __device__ __forceinline__ T mul_rn(T a, T b);
+template <> __device__ __forceinline__ float mul_rn<float>(float a, float b) { return __fmul_rn(a, b); }
+template <> __device__ __forceinline__ double mul_rn<double>(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float4 vmul(float a, const float4 &b) {
+    return make_float4(__fmul_rn(a, b.x), __fmul_rn(a, b.y), __fmul_rn(a, b.z), __fmul_rn(a, b.w));
+}
+__device__ __forceinline__ double2 vmul(double a, const double2 &b) {
+    return make_double2(__dmul_rn(a, b.x), __dmul_rn(a, b.y));
+}
+__device__ __forceinline__ float4 vshfl_idx(const float4 &v, int src) {
+    return make_float4(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src),
+                       __shfl_sync(0xffffffffu, v.z, src), __shfl_sync(0xffffffffu, v.w, src));
+}
+__device__ __forceinline__ double2 vshfl_idx(const double2 &v, int src) {
+    return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+
+template <typename T, int G>
+__global__ void __launch_bounds__(256)
+spmm_warprow_kernel(const int M, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                    const T *__restrict__ val, const T *__restrict__ B, const uint32_t ldbv, const T *Cin,
+                    T *Cout, const uint32_t ldcv, const T alpha, const T beta, const int nvec) {
+    using V = typename VecOf<T>::type;
+    constexpr int NG = 32 / G;  // lane groups per warp
+    constexpr int PER = G;      // entries of a 32-entry chunk that one group gathers
+    const int lane = threadIdx.x & 31;
+    const int lg = lane & (G - 1);
+    const int g = lane / G;
+    const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (row >= M) return;  // warp-uniform
+    const int begin = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+    const bool owner = g == 0 && lg < nvec;
+    V cin, acc;
+    vzero(cin);
+    vzero(acc);
+    if (owner) cin = reinterpret_cast<const V *>(Cin)[(size_t)row * ldcv + lg];
+    const V *Bv = reinterpret_cast<const V *>(B) + lg;
+    int c = 0;
+    T a = T(0);
+    if (begin + lane < end) { c = __ldg(colidx + begin + lane); a = __ldg(val + begin + lane); }
+    for (int base = begin; base < end; base += 32) {
+        int cn = 0;
+        T an = T(0);
+        if (base + 32 + lane < end) { cn = __ldg(colidx + base + 32 + lane); an = __ldg(val + base + 32 + lane); }
+        const int cnt = min(32, end - base);
+        V p[PER];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {  // group g gathers entries g, g+NG, g+2NG, ...
+            const int t = g + NG * k;
+            const int cc = __shfl_sync(0xffffffffu, c, t);
+            if (t < cnt && lg < nvec) p[k] = ldg_vec(Bv + (size_t)(uint32_t)cc * ldbv);
+            else vzero(p[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const T av = __shfl_sync(0xffffffffu, a, g + NG * k);
+            p[k] = vmul(av, p[k]);
+        }
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {  // stored order; group 0 holds the running sum
+            if (t < cnt) {              // warp-uniform
+                const V q = vshfl_idx(p[t / NG], (t % NG) * G + lg);
+                vadd(acc, q);
+            }
+        }
+        c = cn;
+        a = an;
+    }
+    if (owner) reinterpret_cast<V *>(Cout)[(size_t)row * ldcv + lg] = vaxpby<true>(alpha, acc, beta, cin);
 }
 
 // ---- one row group per row (kept as variant 1) -------------------------------------
@@ -497,6 +631,37 @@ colmajor_to_rowmajor_kernel(const int64_t rows, const int cols, const T *__restr
         const int64_t r = r0 + j;
         const int c = c0 + threadIdx.x;
         if (r < rows && c < ld_dst) dst[r * ld_dst + c] = tile[threadIdx.x][j];
+    }
+}
+
+// B (rowsB x cols) and C_in (rowsC x cols) in one launch: blocks [0, tilesB) take B,
+// the rest take C.  Used with the sources in page-locked HOST memory: threadIdx.x runs
+// along a column, so every warp reads 128/256 contiguous bytes over PCIe.
+template <typename T>
+__global__ void __launch_bounds__(256)
+colmajor_to_rowmajor_pair_kernel(const int64_t rowsB, const int64_t rowsC, const int cols,
+                                 const T *__restrict__ srcB, const T *__restrict__ srcC,
+                                 T *__restrict__ dstB, T *__restrict__ dstC, const int64_t ld,
+                                 const int tcol, const int64_t tilesB) {
+    __shared__ T tile[32][33];
+    int64_t t = blockIdx.x;
+    const bool isC = t >= tilesB;
+    if (isC) t -= tilesB;
+    const int64_t rows = isC ? rowsC : rowsB;
+    const T *src = isC ? srcC : srcB;
+    T *dst = isC ? dstC : dstB;
+    const int64_t r0 = (t / tcol) * 32;
+    const int c0 = (int)(t % tcol) * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int c = c0 + j;
+        const int64_t r = r0 + threadIdx.x;
+        tile[j][threadIdx.x] = (r < rows && c < cols) ? src[r + rows * (int64_t)c] : T(0);
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int64_t r = r0 + j;
+        const int c = c0 + threadIdx.x;
+        if (r < rows && c < ld) dst[r * ld + c] = tile[threadIdx.x][j];
     }
 }
 

@@ -89,6 +89,7 @@ struct sx_ctx {
     int dtype = SX_F32;
     int M = 0, K = 0;
     int64_t nnz = 0;
+    int max_row_nnz = 0;
     DevBuf rowptr, colidx, val;
     // long-row segments
     int nsplit = 0, nseg = 0;
@@ -110,6 +111,8 @@ struct sx_ctx {
     int split_nnz = 512;
     int kernel = 0;
     int item_nnz = 0;  // 0 = auto
+    int64_t zerocopy_bytes = 16 << 20;
+    int last_path = 0;  // 1: the last host-facing call took the zero-copy path
     bool segments_dirty = false;
 
     int64_t launches = 0;
@@ -158,6 +161,24 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
     const int rows_per_block = threads / G;
     const int64_t ldp = ((int64_t)N + 7) / 8 * 8;
     int rc;
+    // kernel 0 (auto): tiny matrices -- fewer rows than a couple of warps per scheduler
+    // slot -- take the warp-per-row latency kernel, everything else the staged kernel
+    const bool small = (int64_t)c->M * 32 <= (int64_t)c->sm_count * 2048 * 4 && c->max_row_nnz <= 4096;
+    if constexpr (G < 32 && VPL == 1) {
+        if (c->kernel == 3 || (c->kernel == 0 && small && c->arith == 0)) {
+            constexpr int E = sx::VecOf<T>::E;
+            if (c->M > 0) {
+                const unsigned grid = (unsigned)(((int64_t)c->M * 32 + threads - 1) / threads);
+                sx::spmm_warprow_kernel<T, G><<<grid, threads, 0, c->stream>>>(
+                    c->M, (const int *)c->rowptr.p, (const int *)c->colidx.p, (const T *)c->val.p, dB,
+                    (uint32_t)(ldb / E), dCin, dCout, (uint32_t)(ldc / E), alpha, beta, nvec);
+                c->launches++;
+            }
+            c->last_kernel = 30000 + G * 100 + VPL * 10;
+            SX_CUDA(cudaGetLastError());
+            return SX_OK;
+        }
+    }
     if (c->kernel == 1) {
         // variant 1: one lane group per row + one warp per long-row segment
         const int split = c->nseg > 0 ? c->split_nnz : 0;
@@ -183,6 +204,7 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
     } else if (c->M > 0) {
         // variant 0: TMA-staged work items (+ finalize for rows split into pieces)
         constexpr int U = (G < 8 ? G : 8) / (VPL > 2 ? 4 : VPL);
+        constexpr int E = sx::VecOf<T>::E;
         Plan *p = nullptr;
         if ((rc = get_plan(c, pick_budget(c, G), &p))) return rc;
         c->last_plan = p;
@@ -198,7 +220,8 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
         const unsigned grid = (unsigned)(((int64_t)p->nitems + rows_per_block - 1) / rows_per_block);
         kern<<<grid, threads, smem, c->stream>>>(
             p->nitems, (const int4 *)p->items.p, ts, (const int *)c->rowptr.p, (const int *)c->colidx.p,
-            (const T *)c->val.p, dB, ldb, dCin, dCout, ldc, (T *)c->partial.p, ldp, alpha, beta, nvec);
+            (const T *)c->val.p, dB, (uint32_t)(ldb / E), dCin, dCout, (uint32_t)(ldc / E), (T *)c->partial.p,
+            (uint32_t)(ldp / E), alpha, beta, nvec);
         c->launches++;
         if (p->nsplit > 0) {
             const unsigned gfin = (unsigned)(((int64_t)p->nsplit + rows_per_block - 1) / rows_per_block);
@@ -208,7 +231,7 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
             c->launches++;
         }
     }
-    c->last_kernel = (c->kernel == 1 ? 10000 : 0) + G * 100 + VPL * 10 + (STRICT ? 0 : 1);
+    c->last_kernel = (c->kernel == 1 ? 10000 : 20000) + G * 100 + VPL * 10 + (STRICT ? 0 : 1);
     SX_CUDA(cudaGetLastError());
     return SX_OK;
 }
@@ -347,12 +370,12 @@ int pick_budget(const sx_ctx *c, int G) {
     return (int)std::min<int64_t>(256, std::max<int64_t>(16, c->nnz / want_items));
 }
 
-// tile size (entries, power of two) of the staged kernel: ~48 KB of staging per block
+// tile size (entries, power of two) of the staged kernel: <= 28 KB of staging per block
 template <typename T, int G>
 int pick_tile(int U) {
     const int gpb = 256 / G;
     int ts = 16;
-    while (ts < 128 && (size_t)gpb * (16 + 4 * ts * (sizeof(T) + 4)) <= 48 * 1024) ts *= 2;  // test is for 2*ts
+    while (ts < 128 && (size_t)gpb * (16 + 4 * ts * (sizeof(T) + 4)) <= 28 * 1024) ts *= 2;  // test is for 2*ts
     return std::max(ts, 2 * U);
 }
 
@@ -415,6 +438,8 @@ int upload_csr(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rowptr, cons
     }
     SX_CUDA(cudaStreamSynchronize(c->stream));
     c->h_rowptr.assign(rowptr, rowptr + M + 1);
+    c->max_row_nnz = 0;
+    for (int i = 0; i < M; ++i) c->max_row_nnz = std::max(c->max_row_nnz, rowptr[i + 1] - rowptr[i]);
     c->M = M; c->K = K; c->nnz = nnz;
     c->dtype = DtypeOf<T>::value;
     c->has_B = c->has_C = false;
@@ -479,8 +504,9 @@ int stage_dense(sx_ctx *c, int N, const T *host, bool is_B) {
     return SX_OK;
 }
 
+// enqueue the rp_time kernel repeats between the two timing events; no host sync
 template <typename T>
-int launch(sx_ctx *c, T alpha, T beta, int rp_time, double *kernel_ns) {
+int enqueue_launch(sx_ctx *c, T alpha, T beta, int rp_time) {
     int rc = bind(c);
     if (rc) return rc;
     if (!c->has_A || !c->has_B || !c->has_C)
@@ -493,6 +519,21 @@ int launch(sx_ctx *c, T alpha, T beta, int rp_time, double *kernel_ns) {
         if (rc) return rc;
     }
     SX_CUDA(cudaEventRecord(c->ev1, c->stream));
+    return SX_OK;
+}
+
+// wait for everything enqueued so far, then read the kernel time
+int finish_stream(sx_ctx *c, double *kernel_ns) {
+    SX_CUDA(cudaStreamSynchronize(c->stream));
+    if (kernel_ns) {
+        float ms = 0.f;
+        SX_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        *kernel_ns = (double)ms * 1e6;
+    }
+    return SX_OK;
+}
+
+int finish_timing(sx_ctx *c, double *kernel_ns) {
     SX_CUDA(cudaEventSynchronize(c->ev1));
     if (kernel_ns) {
         float ms = 0.f;
@@ -500,6 +541,13 @@ int launch(sx_ctx *c, T alpha, T beta, int rp_time, double *kernel_ns) {
         *kernel_ns = (double)ms * 1e6;
     }
     return SX_OK;
+}
+
+template <typename T>
+int launch(sx_ctx *c, T alpha, T beta, int rp_time, double *kernel_ns) {
+    int rc = enqueue_launch<T>(c, alpha, beta, rp_time);
+    if (rc) return rc;
+    return finish_timing(c, kernel_ns);
 }
 
 template <typename T>
@@ -517,13 +565,63 @@ int fetch_C(sx_ctx *c, T *host) {
     return SX_OK;
 }
 
+// Device-visible alias of a page-locked host pointer (cudaHostAlloc / cudaHostRegister /
+// sx_host_alloc), or nullptr for pageable memory.
+void *mapped_alias(const void *host) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
+// The host-facing call.  Two ways in and out of the device:
+//   * page-locked B and C up to SX_OPT_ZEROCOPY_BYTES together: no copy-engine
+//     transfers at all -- one kernel reads both column-major host operands over PCIe and
+//     writes the row-major device images, the SpMM kernel(s) run, one kernel writes the
+//     column-major result straight back into the caller's C; a single host sync at the
+//     end.  Three launches instead of 3 memcpys + 4 launches + 2 syncs, which is what
+//     matters for the SuiteSparse-sized configs where the whole call is ~50 us.
+//   * otherwise: cudaMemcpyAsync through a device staging buffer + layout kernels.
 template <typename T>
 int spmm_host(sx_ctx *c, int N, T alpha, const T *B, T beta, T *C, int rp_time, double *kernel_ns) {
-    int rc;
+    int rc = bind(c);
+    if (rc) return rc;
+    if (!c->has_A) return fail(SX_ERR_STATE, "no matrix uploaded (call sx_upload_csr_* first)");
+    if (c->dtype != DtypeOf<T>::value) return fail(SX_ERR_INVALID, "dtype differs from the uploaded matrix");
+    if (!B || !C) return fail(SX_ERR_INVALID, "null host operand");
+    const size_t bytes = ((size_t)c->K + (size_t)c->M) * (size_t)(N > 0 ? N : 0) * sizeof(T);
+    const void *dB = nullptr;
+    void *dC = nullptr;
+    if (N >= 1 && bytes <= (size_t)c->zerocopy_bytes && (dB = mapped_alias(B)) && (dC = mapped_alias(C))) {
+        if ((rc = set_columns(c, N))) return rc;
+        const size_t szB = std::max<size_t>((size_t)c->K * c->ld * sizeof(T), 16);
+        const size_t szC = std::max<size_t>((size_t)c->M * c->ld * sizeof(T), 16);
+        if ((rc = c->B.ensure(szB)) || (rc = c->Cin.ensure(szC)) || (rc = c->Cout.ensure(szC))) return rc;
+        const int64_t tB = ((int64_t)c->K + 31) / 32, tC = ((int64_t)c->M + 31) / 32, tcol = (c->ld + 31) / 32;
+        if ((tB + tC) * tcol > 0) {
+            dim3 block(32, 8), grid((unsigned)((tB + tC) * tcol));
+            sx::colmajor_to_rowmajor_pair_kernel<T><<<grid, block, 0, c->stream>>>(
+                c->K, c->M, N, (const T *)dB, (const T *)dC, (T *)c->B.p, (T *)c->Cin.p, c->ld, (int)tcol, tB * tcol);
+            c->launches++;
+            SX_CUDA(cudaGetLastError());
+        }
+        c->has_B = c->has_C = true;
+        if ((rc = enqueue_launch<T>(c, alpha, beta, rp_time))) return rc;
+        if ((rc = transpose_out(c, c->dtype, c->M, N, c->Cout.p, c->ld, dC))) return rc;
+        c->last_path = 1;
+        return finish_stream(c, kernel_ns);
+    }
     if ((rc = stage_dense<T>(c, N, B, true))) return rc;
     if ((rc = stage_dense<T>(c, N, C, false))) return rc;
-    if ((rc = launch<T>(c, alpha, beta, rp_time, kernel_ns))) return rc;
-    return fetch_C<T>(c, C);
+    if ((rc = enqueue_launch<T>(c, alpha, beta, rp_time))) return rc;
+    const size_t out_bytes = (size_t)c->M * c->N * sizeof(T);
+    if ((rc = c->stage.ensure(std::max<size_t>(out_bytes, 16)))) return rc;
+    if ((rc = transpose_out(c, c->dtype, c->M, c->N, c->Cout.p, c->ld, c->stage.p))) return rc;
+    if (out_bytes) SX_CUDA(cudaMemcpyAsync(C, c->stage.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    c->last_path = 0;
+    return finish_stream(c, kernel_ns);
 }
 
 }  // namespace
@@ -628,8 +726,12 @@ int sx_set_option(sx_ctx *c, int option, int64_t value) {
             c->segments_dirty = c->has_A;
             return SX_OK;
         case SX_OPT_KERNEL:
-            if (value != 0 && value != 1) return fail(SX_ERR_INVALID, "SX_OPT_KERNEL is 0 (TMA-staged work items) or 1 (row per group)");
+            if (value < 0 || value > 3) return fail(SX_ERR_INVALID, "SX_OPT_KERNEL is 0 (auto), 1 (row per group), 2 (TMA-staged work items) or 3 (warp per row)");
             c->kernel = (int)value;
+            return SX_OK;
+        case SX_OPT_ZEROCOPY_BYTES:
+            if (value < 0) return fail(SX_ERR_INVALID, "SX_OPT_ZEROCOPY_BYTES must be >= 0");
+            c->zerocopy_bytes = value;
             return SX_OK;
         case SX_OPT_ITEM_NNZ:
             if (value < 0 || value > (1 << 20) || (value != 0 && value < 4)) return fail(SX_ERR_INVALID, "SX_OPT_ITEM_NNZ must be 0 or in [4, 2^20]");
@@ -656,6 +758,7 @@ int sx_get_info(sx_ctx *c, int what, int64_t *value) {
         case SX_INFO_SPLIT_ROWS: *value = (c->kernel == 1 || !c->last_plan) ? c->nsplit : c->last_plan->nsplit; return SX_OK;
         case SX_INFO_LAST_KERNEL: *value = c->last_kernel; return SX_OK;
         case SX_INFO_LD: *value = c->ld; return SX_OK;
+        case SX_INFO_HOST_PATH: *value = c->last_path; return SX_OK;
         case SX_INFO_ITEMS: *value = c->last_plan ? c->last_plan->nitems : 0; return SX_OK;
         case SX_INFO_ITEM_NNZ: *value = c->last_plan ? c->last_plan->budget : 0; return SX_OK;
         default: return fail(SX_ERR_INVALID, "unknown info id %d", what);

@@ -165,30 +165,103 @@ def test_beta_zero_still_propagates_nan_like_the_reference(eng):
     assert np.array_equal(np.isnan(C), np.isnan(ref))
 
 
+@pytest.mark.parametrize("kernel", [1, 2])
 @pytest.mark.parametrize("dtype,tol", [(np.float32, 1e-5), (np.float64, 1e-12)])
 @pytest.mark.parametrize("N", [8, 16, 128])
-def test_long_rows_take_the_split_path(eng, dtype, tol, N):
+def test_long_rows_take_the_split_path(eng, dtype, tol, N, kernel):
     M, K = 300, 5000
     rp, ci, v = random_csr(M, K, 20, 77, dtype, long_row=4000)
     B, Cin = random_dense(M, K, N, 77, dtype)
     a, b = dtype(0.85), dtype(-2.06)
-    eng.set_option(sx.OPT_SPLIT_ROW_NNZ, 512)
-    C, _ = run(eng, M, K, N, rp, ci, v, a, B, b, Cin)
-    assert eng.info(sx.INFO_SPLIT_ROWS) == 1
-    ref = oracle.spmm_csr(M, N, K, rp, ci, v, a, B, b, Cin.copy())
-    assert scaled_err(C, ref) <= tol
-    long_row = int(np.argmax(np.diff(rp)))
-    keep = np.ones(M, dtype=bool)
-    keep[long_row] = False
-    Cm, Rm = C.reshape(N, M)[:, keep], ref.reshape(N, M)[:, keep]
-    assert np.array_equal(bits(np.ascontiguousarray(Cm)), bits(np.ascontiguousarray(Rm)))
-    # with splitting disabled the long row is walked in order as well: bit-exact everywhere
-    eng.set_option(sx.OPT_SPLIT_ROW_NNZ, 0)
-    C2 = Cin.copy()
-    eng.spmm(N, a, B, b, C2)
-    assert eng.info(sx.INFO_SPLIT_ROWS) == 0
-    assert np.array_equal(bits(C2), bits(ref))
-    eng.set_option(sx.OPT_SPLIT_ROW_NNZ, 512)
+    eng.set_option(sx.OPT_KERNEL, kernel)
+    try:
+        eng.set_option(sx.OPT_SPLIT_ROW_NNZ, 512)
+        C, _ = run(eng, M, K, N, rp, ci, v, a, B, b, Cin)
+        assert eng.info(sx.INFO_SPLIT_ROWS) == 1
+        ref = oracle.spmm_csr(M, N, K, rp, ci, v, a, B, b, Cin.copy())
+        assert scaled_err(C, ref) <= tol
+        long_row = int(np.argmax(np.diff(rp)))
+        keep = np.ones(M, dtype=bool)
+        keep[long_row] = False
+        Cm, Rm = C.reshape(N, M)[:, keep], ref.reshape(N, M)[:, keep]
+        assert np.array_equal(bits(np.ascontiguousarray(Cm)), bits(np.ascontiguousarray(Rm)))
+        # with splitting disabled the long row is walked in order as well: bit-exact everywhere
+        eng.set_option(sx.OPT_SPLIT_ROW_NNZ, 0)
+        C2 = Cin.copy()
+        eng.spmm(N, a, B, b, C2)
+        assert eng.info(sx.INFO_SPLIT_ROWS) == 0
+        assert np.array_equal(bits(C2), bits(ref))
+    finally:
+        eng.set_option(sx.OPT_SPLIT_ROW_NNZ, 512)
+        eng.set_option(sx.OPT_KERNEL, 0)
+
+
+KERNEL_SHAPES = [(7, 5, 2, 8), (257, 300, 17, 32), (64, 1000, 40, 40), (500, 200, 8, 64),
+                 (300, 300, 30, 128), (130, 77, 9, 256), (1000, 1000, 3, 1), (2000, 3000, 70, 16)]
+
+
+@pytest.mark.parametrize("kernel", [1, 2, 3])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("M,K,avg,N", KERNEL_SHAPES)
+def test_every_kernel_variant_bit_exact(eng, kernel, dtype, M, K, avg, N):
+    """Variants 1 (row per lane group), 2 (TMA-staged work items) and 3 (warp per row,
+    ordered sum) all reproduce the oracle bit for bit; 3 silently defers to 2 when a dense
+    row is wider than one warp covers."""
+    rp, ci, v = random_csr(M, K, avg, M * 17 + N + kernel, dtype, long_row=min(K, 300))
+    B, Cin = random_dense(M, K, N, M * 17 + N, dtype)
+    eng.set_option(sx.OPT_KERNEL, kernel)
+    try:
+        for item_nnz in ((0, 8, 64) if kernel == 2 else (0,)):
+            eng.set_option(sx.OPT_ITEM_NNZ, item_nnz)
+            C, _ = run(eng, M, K, N, rp, ci, v, dtype(0.85), B, dtype(-2.06), Cin)
+            ref = oracle.spmm_csr(M, N, K, rp, ci, v, dtype(0.85), B, dtype(-2.06), Cin.copy())
+            assert np.array_equal(bits(C), bits(ref)), (kernel, item_nnz)
+            assert eng.info(sx.INFO_LAST_KERNEL) // 10000 in ((kernel,) if kernel != 3 else (3, 2))
+    finally:
+        eng.set_option(sx.OPT_KERNEL, 0)
+        eng.set_option(sx.OPT_ITEM_NNZ, 0)
+
+
+def test_auto_kernel_choice(eng):
+    # a few thousand rows: latency kernel; a matrix with more rows than warp slots: staged
+    rp, ci, v = random_csr(3000, 500, 10, 1, np.float32)
+    B, Cin = random_dense(3000, 500, 16, 1, np.float32)
+    run(eng, 3000, 500, 16, rp, ci, v, A32, B, B32, Cin)
+    assert eng.info(sx.INFO_LAST_KERNEL) // 10000 == 3
+    M = 60000
+    rp = (np.arange(M + 1) * 2).astype(np.int32)
+    ci = np.tile(np.array([1, 7], dtype=np.int32), M)
+    v = np.ones(2 * M, np.float32)
+    B, Cin = random_dense(M, 16, 16, 2, np.float32)
+    C, _ = run(eng, M, 16, 16, rp, ci, v, A32, B, B32, Cin)
+    assert eng.info(sx.INFO_LAST_KERNEL) // 10000 == 2
+    ref = oracle.spmm_csr(M, 16, 16, rp, ci, v, A32, B, B32, Cin.copy())
+    assert np.array_equal(bits(C), bits(ref))
+
+
+def test_host_paths_zero_copy_and_copy_engine(eng):
+    """Page-locked operands are read/written by the kernels directly (no memcpy);
+    pageable ones, or anything above SX_OPT_ZEROCOPY_BYTES, take cudaMemcpyAsync.  Same bits."""
+    M, K, N = 900, 700, 24
+    rp, ci, v = random_csr(M, K, 11, 3, np.float64)
+    B, Cin = random_dense(M, K, N, 3, np.float64)
+    ref = oracle.spmm_csr(M, N, K, rp, ci, v, 0.85, B, -2.06, Cin.copy())
+    eng.upload_csr(M, K, rp, ci, v)
+    C = Cin.copy()
+    eng.spmm(N, 0.85, B, -2.06, C)
+    assert eng.info(sx.INFO_HOST_PATH) == 0 and np.array_equal(bits(C), bits(ref))
+    pB, pC = sx.pinned_empty(B.size, np.float64), sx.pinned_empty(Cin.size, np.float64)
+    pB[:] = B
+    pC[:] = Cin
+    eng.spmm(N, 0.85, pB, -2.06, pC, rp_time=3)
+    assert eng.info(sx.INFO_HOST_PATH) == 1 and np.array_equal(bits(np.asarray(pC)), bits(ref))
+    eng.set_option(sx.OPT_ZEROCOPY_BYTES, 0)
+    try:
+        pC[:] = Cin
+        eng.spmm(N, 0.85, pB, -2.06, pC)
+        assert eng.info(sx.INFO_HOST_PATH) == 0 and np.array_equal(bits(np.asarray(pC)), bits(ref))
+    finally:
+        eng.set_option(sx.OPT_ZEROCOPY_BYTES, 16 << 20)
 
 
 @pytest.mark.parametrize("dtype,tol", [(np.float32, 1e-5), (np.float64, 1e-12)])
