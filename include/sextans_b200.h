@@ -71,10 +71,9 @@ enum sx_option {
      * tree-reduced (summation order differs from the oracle; error ~ 1e-7 fp32 /
      * 1e-16 fp64 relative to the row's |a||b| sum).  0 disables splitting. */
     SX_OPT_SPLIT_ROW_NNZ = 1,
-    /* kernel variant: 0 auto (3 for matrices with fewer rows than the GPU
-     * has warp slots, else 2); 1 one lane group per row (+ one warp per long-row
-     * segment); 2 TMA-staged nnz-balanced work items; 3 one warp per row with
-     * parallel gathers and in-order summation (N*sizeof(T) <= 256 bytes only) */
+    /* kernel variant: 0 auto (1 for matrices whose rows fill less than one
+     * wave of lane groups, else 2); 1 one lane group per row (+ one warp per long-row
+     * segment); 2 TMA-staged nnz-balanced work items */
     SX_OPT_KERNEL = 2,
     /* nonzeros per work item; 0 = auto (<= 256, smaller for small matrices) */
     SX_OPT_ITEM_NNZ = 3,

@@ -2,7 +2,7 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_gpu.log
 show() { python -c "
-import json,sys;d=json.load(open(sys.argv[1]));print('  ms',round(d['ms_per_step'],4),'warm',round(d['steady_state_l2_warm']['ms_per_step'],4),'GF',round(d['value'],1),'frac',round(d['roofline']['frac'],4),'e2e_ms',round(d['e2e']['ms_per_step'],4),d['e2e']['path'][:10],d['roofline']['kernel'])" $1; }
+import json,sys;d=json.load(open(sys.argv[1]));print('  ms',round(d['ms_per_step'],4),'warm',round(d['single_copy_back_to_back']['ms_per_step'],4),'GF',round(d['value'],1),'frac',round(d['roofline']['frac'],4),'e2e_ms',round(d['e2e']['ms_per_step'],4),d['e2e']['path'][:10],d['roofline']['kernel'])" $1; }
 for wlk in nasa4704 pcrystk02; do
  for k in 0 1 2; do
   timeout 300 python bench.py --workload $wlk --steps 30 --kernel $k --no-cpu-baseline > gpurun_out/p6_${wlk}_k$k.json 2> gpurun_out/p6_${wlk}_k$k.err; echo "$wlk k=$k rc=$?"; tail -2 gpurun_out/p6_${wlk}_k$k.err; show gpurun_out/p6_${wlk}_k$k.json

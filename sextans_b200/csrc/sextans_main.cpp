@@ -33,6 +33,9 @@
 #include <thread>
 #include <vector>
 
+#include <cuda_runtime_api.h>
+#include <nccl.h>
+
 #include "../../include/sextans_b200.h"
 
 using std::cout;
@@ -76,11 +79,21 @@ template <> struct Api<float> {
     static int load(const char *p, int *M, int *K, int64_t *nnz, int32_t **rp, int32_t **ci, float **v) { return sx_load_mtx_f32(p, M, K, nnz, rp, ci, v); }
     static int upload(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rp, const int32_t *ci, const float *v) { return sx_upload_csr_f32(c, M, K, nnz, rp, ci, v); }
     static int spmm(sx_ctx *c, int N, float a, const float *B, float b, float *C, int rp, double *ns) { return sx_spmm_f32(c, N, a, B, b, C, rp, ns); }
+    static int stage_B(sx_ctx *c, int N, const float *B) { return sx_stage_B_f32(c, N, B); }
+    static int stage_C(sx_ctx *c, int N, const float *C) { return sx_stage_C_f32(c, N, C); }
+    static int launch(sx_ctx *c, float a, float b, int rp, double *ns) { return sx_launch_f32(c, a, b, rp, ns); }
+    static int fetch_C(sx_ctx *c, float *C) { return sx_fetch_C_f32(c, C); }
+    static constexpr ncclDataType_t nccl_type = ncclFloat;
 };
 template <> struct Api<double> {
     static int load(const char *p, int *M, int *K, int64_t *nnz, int32_t **rp, int32_t **ci, double **v) { return sx_load_mtx_f64(p, M, K, nnz, rp, ci, v); }
     static int upload(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rp, const int32_t *ci, const double *v) { return sx_upload_csr_f64(c, M, K, nnz, rp, ci, v); }
     static int spmm(sx_ctx *c, int N, double a, const double *B, double b, double *C, int rp, double *ns) { return sx_spmm_f64(c, N, a, B, b, C, rp, ns); }
+    static int stage_B(sx_ctx *c, int N, const double *B) { return sx_stage_B_f64(c, N, B); }
+    static int stage_C(sx_ctx *c, int N, const double *C) { return sx_stage_C_f64(c, N, C); }
+    static int launch(sx_ctx *c, double a, double b, int rp, double *ns) { return sx_launch_f64(c, a, b, rp, ns); }
+    static int fetch_C(sx_ctx *c, double *C) { return sx_fetch_C_f64(c, C); }
+    static constexpr ncclDataType_t nccl_type = ncclDouble;
 };
 
 template <typename T>
@@ -152,29 +165,64 @@ int run(const Options &opt, const char *filename_A, int N, int rp_time, float AL
     cout << "CPU GFLOPS: " << 2.0f * (nnz + M) * N / 1000000000 / time_cpu << "\n";
 
     cout << "launch kernel\n";
-    // one host thread per GPU; each row block's C is a strided slice of the column-major
-    // C, so every block is packed into its own column-major buffer around the call
+    // G == 1: the one host-facing call.  G > 1: B goes to GPU 0 once and reaches the other
+    // GPUs by ONE ncclBroadcast over NVLink (the daisy chain of src/sextans.cpp:909-941);
+    // then one host thread per GPU runs its row block.  A row block of the column-major C
+    // is a strided slice, so it is packed into its own column-major buffer around the call.
     std::vector<double> ns((size_t)G, 0.0);
     std::vector<int> status((size_t)G, 0);
     std::vector<std::string> errtext((size_t)G);
     std::vector<std::vector<T>> blockC((size_t)G);
-    auto worker = [&](int g) {
-        const int r0 = bounds[g], r1 = bounds[g + 1], mb = r1 - r0;
-        T *Cb = mat_C_dev;
-        if (G > 1) {
+    double bcast_ms = 0.0;
+    if (G == 1) {
+        status[0] = Api<T>::spmm(ctx[0], N, (T)ALPHA, mat_B, (T)BETA, mat_C_dev, rp_time, &ns[0]);
+        if (status[0]) errtext[0] = sx_last_error();
+    } else {
+        std::vector<ncclComm_t> comm((size_t)G);
+        std::vector<int> devs((size_t)G);
+        std::vector<cudaStream_t> streams((size_t)G);
+        std::vector<void *> dB((size_t)G);
+        size_t bytesB = 0;
+        for (int g = 0; g < G; ++g) devs[g] = g;
+        if (ncclCommInitAll(comm.data(), G, devs.data()) != ncclSuccess) {
+            std::fprintf(stderr, "sextans: ncclCommInitAll failed\n");
+            return EXIT_FAILURE;
+        }
+        for (int g = 0; g < G; ++g) {
+            cudaSetDevice(g);
+            cudaStreamCreateWithFlags(&streams[g], cudaStreamNonBlocking);
+            if ((rc = sx_set_stream(ctx[g], streams[g]))) return die("sx_set_stream", rc);
+            if (g == 0 && (rc = Api<T>::stage_B(ctx[0], N, mat_B))) return die("sx_stage_B", rc);
+            if ((rc = sx_device_B(ctx[g], N, &dB[g], &bytesB))) return die("sx_device_B", rc);
+        }
+        auto t0 = std::chrono::steady_clock::now();
+        ncclGroupStart();
+        for (int g = 0; g < G; ++g)
+            ncclBroadcast(dB[0], dB[g], bytesB / sizeof(T), Api<T>::nccl_type, 0, comm[g], streams[g]);
+        ncclGroupEnd();
+        for (int g = 0; g < G; ++g) { cudaSetDevice(g); cudaStreamSynchronize(streams[g]); }
+        bcast_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        auto worker = [&](int g) {
+            const int r0 = bounds[g], r1 = bounds[g + 1], mb = r1 - r0;
             blockC[g].resize((size_t)mb * N);
             for (int nn = 0; nn < N; ++nn)
                 std::memcpy(blockC[g].data() + (size_t)mb * nn, mat_C_dev + r0 + (size_t)M * nn, (size_t)mb * sizeof(T));
-            Cb = blockC[g].data();
-        }
-        status[g] = Api<T>::spmm(ctx[g], N, (T)ALPHA, mat_B, (T)BETA, Cb, rp_time, &ns[g]);
-        if (status[g]) errtext[g] = sx_last_error();
-    };
-    if (G == 1) worker(0);
-    else {
+            int st = Api<T>::stage_C(ctx[g], N, blockC[g].data());
+            if (!st) st = Api<T>::launch(ctx[g], (T)ALPHA, (T)BETA, rp_time, &ns[g]);
+            if (!st) st = Api<T>::fetch_C(ctx[g], blockC[g].data());
+            status[g] = st;
+            if (st) errtext[g] = sx_last_error();
+        };
         std::vector<std::thread> th;
         for (int g = 0; g < G; ++g) th.emplace_back(worker, g);
         for (auto &t : th) t.join();
+        for (int g = 0; g < G; ++g) {
+            sx_set_stream(ctx[g], nullptr);
+            cudaSetDevice(g);
+            cudaStreamDestroy(streams[g]);
+            ncclCommDestroy(comm[g]);
+        }
+        std::printf("B broadcast over NCCL: %.3f ms (%zu bytes to %d GPUs)\n", bcast_ms, bytesB, G - 1);
     }
     for (int g = 0; g < G; ++g)
         if (status[g]) {

@@ -431,86 +431,7 @@ spmm_staged_kernel(const int nitems, const int4 *__restrict__ items, const int t
     }
 }
 
-// ---- small matrices: one warp per row, gathers in parallel, sum in order ------------
-// The shipped SuiteSparse inputs (nasa4704: 4 704 rows, pcrystk02: 13 965) give a B200
-// fewer rows than it has warp slots, so what matters is the length of the dependent
-// memory chain, not bandwidth.  Here a whole warp takes one row: 32 (col, val) entries
-// arrive with one coalesced load, the 32/G lane groups gather their B rows side by
-// side, every product is rounded where it was gathered, and the products are then
-// handed to lane group 0 by shuffle and added IN STORED ORDER -- so the result is still
-// bit-identical to cpu_spmm_CSR, while the chain is rowptr -> entries -> B rows.
-template <typename T> __device__ __forceinline__ T mul_rn(T a, T b);
-template <> __device__ __forceinline__ float mul_rn<float>(float a, float b) { return __fmul_rn(a, b); }
-template <> __device__ __forceinline__ double mul_rn<double>(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ float4 vmul(float a, const float4 &b) {
-    return make_float4(__fmul_rn(a, b.x), __fmul_rn(a, b.y), __fmul_rn(a, b.z), __fmul_rn(a, b.w));
-}
-__device__ __forceinline__ double2 vmul(double a, const double2 &b) {
-    return make_double2(__dmul_rn(a, b.x), __dmul_rn(a, b.y));
-}
-__device__ __forceinline__ float4 vshfl_idx(const float4 &v, int src) {
-    return make_float4(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src),
-                       __shfl_sync(0xffffffffu, v.z, src), __shfl_sync(0xffffffffu, v.w, src));
-}
-__device__ __forceinline__ double2 vshfl_idx(const double2 &v, int src) {
-    return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
-}
-
-template <typename T, int G>
-__global__ void __launch_bounds__(256)
-spmm_warprow_kernel(const int M, const int *__restrict__ rowptr, const int *__restrict__ colidx,
-                    const T *__restrict__ val, const T *__restrict__ B, const uint32_t ldbv, const T *Cin,
-                    T *Cout, const uint32_t ldcv, const T alpha, const T beta, const int nvec) {
-    using V = typename VecOf<T>::type;
-    constexpr int NG = 32 / G;  // lane groups per warp
-    constexpr int PER = G;      // entries of a 32-entry chunk that one group gathers
-    const int lane = threadIdx.x & 31;
-    const int lg = lane & (G - 1);
-    const int g = lane / G;
-    const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (row >= M) return;  // warp-uniform
-    const int begin = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
-    const bool owner = g == 0 && lg < nvec;
-    V cin, acc;
-    vzero(cin);
-    vzero(acc);
-    if (owner) cin = reinterpret_cast<const V *>(Cin)[(size_t)row * ldcv + lg];
-    const V *Bv = reinterpret_cast<const V *>(B) + lg;
-    int c = 0;
-    T a = T(0);
-    if (begin + lane < end) { c = __ldg(colidx + begin + lane); a = __ldg(val + begin + lane); }
-    for (int base = begin; base < end; base += 32) {
-        int cn = 0;
-        T an = T(0);
-        if (base + 32 + lane < end) { cn = __ldg(colidx + base + 32 + lane); an = __ldg(val + base + 32 + lane); }
-        const int cnt = min(32, end - base);
-        V p[PER];
-#pragma unroll
-        for (int k = 0; k < PER; ++k) {  // group g gathers entries g, g+NG, g+2NG, ...
-            const int t = g + NG * k;
-            const int cc = __shfl_sync(0xffffffffu, c, t);
-            if (t < cnt && lg < nvec) p[k] = ldg_vec(Bv + (size_t)(uint32_t)cc * ldbv);
-            else vzero(p[k]);
-        }
-#pragma unroll
-        for (int k = 0; k < PER; ++k) {
-            const T av = __shfl_sync(0xffffffffu, a, g + NG * k);
-            p[k] = vmul(av, p[k]);
-        }
-#pragma unroll
-        for (int t = 0; t < 32; ++t) {  // stored order; group 0 holds the running sum
-            if (t < cnt) {              // warp-uniform
-                const V q = vshfl_idx(p[t / NG], (t % NG) * G + lg);
-                vadd(acc, q);
-            }
-        }
-        c = cn;
-        a = an;
-    }
-    if (owner) reinterpret_cast<V *>(Cout)[(size_t)row * ldcv + lg] = vaxpby<true>(alpha, acc, beta, cin);
-}
-
-// ---- one row group per row (kept as variant 1) -------------------------------------
+// ---- one row group per row (variant 1: matrices that fill less than one wave) -------------------------------------
 // Rows longer than split_nnz (when > 0) are left to the segment kernels below.
 template <typename T, int G, int VPL, bool STRICT>
 __global__ void __launch_bounds__(256)

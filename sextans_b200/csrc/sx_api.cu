@@ -161,25 +161,13 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
     const int rows_per_block = threads / G;
     const int64_t ldp = ((int64_t)N + 7) / 8 * 8;
     int rc;
-    // kernel 0 (auto): tiny matrices -- fewer rows than a couple of warps per scheduler
-    // slot -- take the warp-per-row latency kernel, everything else the staged kernel
-    const bool small = (int64_t)c->M * 32 <= (int64_t)c->sm_count * 2048 * 4 && c->max_row_nnz <= 4096;
-    if constexpr (G < 32 && VPL == 1) {
-        if (c->kernel == 3 || (c->kernel == 0 && small && c->arith == 0)) {
-            constexpr int E = sx::VecOf<T>::E;
-            if (c->M > 0) {
-                const unsigned grid = (unsigned)(((int64_t)c->M * 32 + threads - 1) / threads);
-                sx::spmm_warprow_kernel<T, G><<<grid, threads, 0, c->stream>>>(
-                    c->M, (const int *)c->rowptr.p, (const int *)c->colidx.p, (const T *)c->val.p, dB,
-                    (uint32_t)(ldb / E), dCin, dCout, (uint32_t)(ldc / E), alpha, beta, nvec);
-                c->launches++;
-            }
-            c->last_kernel = 30000 + G * 100 + VPL * 10;
-            SX_CUDA(cudaGetLastError());
-            return SX_OK;
-        }
-    }
-    if (c->kernel == 1) {
+    // kernel 0 (auto): a matrix whose rows, one lane group each, fill less than one wave
+    // of the machine is latency-bound -- it takes variant 1 (most parallelism, shortest
+    // dependent chain; measured 10.4 us against 14.7 us per nasa4704 SpMM); anything
+    // larger takes the nnz-balanced TMA-staged variant 2.
+    const bool sub_wave = (int64_t)c->M * G <= (int64_t)c->sm_count * 2048;
+    const int variant = c->kernel != 0 ? c->kernel : (sub_wave ? 1 : 2);
+    if (variant == 1) {
         // variant 1: one lane group per row + one warp per long-row segment
         const int split = c->nseg > 0 ? c->split_nnz : 0;
         if (c->M > 0) {
@@ -231,7 +219,7 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
             c->launches++;
         }
     }
-    c->last_kernel = (c->kernel == 1 ? 10000 : 20000) + G * 100 + VPL * 10 + (STRICT ? 0 : 1);
+    c->last_kernel = variant * 10000 + G * 100 + VPL * 10 + (STRICT ? 0 : 1);
     SX_CUDA(cudaGetLastError());
     return SX_OK;
 }
@@ -726,7 +714,7 @@ int sx_set_option(sx_ctx *c, int option, int64_t value) {
             c->segments_dirty = c->has_A;
             return SX_OK;
         case SX_OPT_KERNEL:
-            if (value < 0 || value > 3) return fail(SX_ERR_INVALID, "SX_OPT_KERNEL is 0 (auto), 1 (row per group), 2 (TMA-staged work items) or 3 (warp per row)");
+            if (value < 0 || value > 2) return fail(SX_ERR_INVALID, "SX_OPT_KERNEL is 0 (auto), 1 (row per lane group) or 2 (TMA-staged work items)");
             c->kernel = (int)value;
             return SX_OK;
         case SX_OPT_ZEROCOPY_BYTES:
@@ -755,7 +743,7 @@ int sx_get_info(sx_ctx *c, int what, int64_t *value) {
         case SX_INFO_K: *value = c->K; return SX_OK;
         case SX_INFO_NNZ: *value = c->nnz; return SX_OK;
         case SX_INFO_DTYPE: *value = c->dtype; return SX_OK;
-        case SX_INFO_SPLIT_ROWS: *value = (c->kernel == 1 || !c->last_plan) ? c->nsplit : c->last_plan->nsplit; return SX_OK;
+        case SX_INFO_SPLIT_ROWS: *value = (c->last_kernel / 10000 != 2 || !c->last_plan) ? c->nsplit : c->last_plan->nsplit; return SX_OK;
         case SX_INFO_LAST_KERNEL: *value = c->last_kernel; return SX_OK;
         case SX_INFO_LD: *value = c->ld; return SX_OK;
         case SX_INFO_HOST_PATH: *value = c->last_path; return SX_OK;

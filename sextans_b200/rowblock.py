@@ -1,0 +1,109 @@
+"""Row-block partition of one SpMM across the GPUs of a box.
+
+Rows of A and C are independent (the reference itself deals rows to its 64 PEs,
+src/sparse_helper.h:370), so every rank owns a contiguous block of rows holding about
+nnz/world nonzeros, ALL of B, and the matching block of C.  The only exchange step is
+the broadcast of B from the rank that has it -- the multi-GPU form of the reference's
+daisy chain that hands the B window from PEG to PEG (src/sextans.cpp:909-941).  There
+are no reductions, and a row's arithmetic does not depend on the partition, so the
+result is bitwise the single-GPU result.
+
+``RowBlock`` is pure host logic (no GPU, no torch); ``ShardedSpMM`` drives one
+``Engine`` per process with ``torch.distributed`` (NCCL over NVLink on the GPUs).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import Engine, partition_rows
+
+
+class RowBlock:
+    """This rank's rows [r0, r1) of a CSR matrix, with the row pointers rebased to 0."""
+
+    def __init__(self, M, K, rowptr, colidx, val, world, rank):
+        if not 0 <= rank < world:
+            raise ValueError("rank out of range")
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+        self.M, self.K, self.world, self.rank = int(M), int(K), int(world), int(rank)
+        self.bounds = partition_rows(rowptr, world)
+        self.r0, self.r1 = int(self.bounds[rank]), int(self.bounds[rank + 1])
+        j0, j1 = int(rowptr[self.r0]), int(rowptr[self.r1])
+        self.rows = self.r1 - self.r0
+        self.rowptr = (rowptr[self.r0:self.r1 + 1] - rowptr[self.r0]).astype(np.int32)
+        self.colidx = np.ascontiguousarray(colidx[j0:j1], dtype=np.int32)
+        self.val = np.ascontiguousarray(val[j0:j1])
+        self.nnz = j1 - j0
+
+    def take_C(self, C_colmajor, N):
+        """This rank's block of a column-major M x N operand, as its own column-major array."""
+        return np.ascontiguousarray(C_colmajor.reshape(N, self.M)[:, self.r0:self.r1]).ravel()
+
+    def put_C(self, C_colmajor, block, N, rank=None):
+        """Write a rank's block back into the full column-major M x N array."""
+        r = self.rank if rank is None else rank
+        r0, r1 = int(self.bounds[r]), int(self.bounds[r + 1])
+        C_colmajor.reshape(N, self.M)[:, r0:r1] = np.asarray(block).reshape(N, r1 - r0)
+        return C_colmajor
+
+
+class ShardedSpMM:
+    """One process per GPU.  ``spmm`` broadcasts B (device to device, NCCL) and runs the
+    local row block; C stays sharded unless ``gather`` is asked for."""
+
+    def __init__(self, M, K, rowptr, colidx, val, device, group=None, arith=0):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.block = RowBlock(M, K, rowptr, colidx, val, self.world, self.rank)
+        import torch
+        self.engine = Engine(device, arith=arith)
+        # one stream for the engine's kernels AND the collective, so that they are ordered
+        self.stream = torch.cuda.Stream(device=device)
+        self.engine.set_stream(self.stream.cuda_stream)
+        self.engine.upload_csr(self.block.rows, K, self.block.rowptr, self.block.colidx, self.block.val)
+        self.dtype = self.block.val.dtype
+        self.device = device
+
+    def close(self):
+        self.engine.close()
+
+    def device_B(self, N):
+        """torch view of the engine's row-major B image [K, ld] (the broadcast target)."""
+        import torch
+        ptr, nbytes = self.engine.device_B(N)
+        ld = self.engine.info(7)
+        tdtype = torch.float64 if self.dtype == np.float64 else torch.float32
+        n = nbytes // self.dtype.itemsize
+
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8" if self.dtype == np.float64 else "<f4",
+                                        "data": (ptr, False), "version": 3}
+        return torch.as_tensor(_Arr(), device=f"cuda:{self.device}").view(self.block.K, ld), tdtype
+
+    def spmm(self, N, alpha, B_colmajor_root, beta, C_block_colmajor, src=0, rp_time=1):
+        """B_colmajor_root: the K x N column-major host B on rank ``src`` (ignored elsewhere).
+        C_block_colmajor: this rank's block (in/out).  Returns the local kernel ns."""
+        if self.rank == src:
+            self.engine.stage_B(N, B_colmajor_root)        # H2D + layout change on the root only
+        import torch
+        dB, _ = self.device_B(N)
+        with torch.cuda.stream(self.stream):
+            self.dist.broadcast(dB, src=src, group=self.group)  # NCCL over NVLink / NVSwitch
+        self.engine.stage_C(N, C_block_colmajor)
+        ns = self.engine.launch(alpha, beta, rp_time)
+        self.engine.fetch_C(C_block_colmajor)
+        return ns
+
+    def gather(self, C_block_colmajor, N, dst=0):
+        """Collect the blocks on rank ``dst`` -> full column-major C there, None elsewhere."""
+        blocks = [None] * self.world if self.rank == dst else None
+        self.dist.gather_object(C_block_colmajor, blocks, dst=dst, group=self.group)
+        if self.rank != dst:
+            return None
+        out = np.empty(self.block.M * N, dtype=self.dtype)
+        for r, b in enumerate(blocks):
+            self.block.put_C(out, b, N, rank=r)
+        return out
