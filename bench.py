@@ -62,6 +62,7 @@ def parse():
     p.add_argument("--split", type=int, default=-1, help="SX_OPT_SPLIT_ROW_NNZ (-1 default)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-flush", action="store_true", help="leave L2 warm between steps")
+    p.add_argument("--no-graph", action="store_true", help="launch the timed steps one by one instead of replaying a CUDA graph")
     return p.parse_args()
 
 
@@ -329,16 +330,33 @@ def run_native(args):
     sampler = ClockSampler(local)
     sampler.start()
     # ---- timed: exactly K steps between two events on the launching stream ------------
+    # The K steps are captured once into a CUDA graph (launch-bound loop: a nasa4704 SpMM
+    # is ~10 us of device work) and the graph is replayed inside the timed region;
+    # --no-graph launches them one by one instead.
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = launches()
+    graph = None
+    use_graph = not args.no_graph and world == 1   # NCCL collectives are launched eagerly
+    if use_graph:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            for i in range(args.steps):
+                step_device(nwarm + i)
+        launches_dev = launches() - l0       # kernels recorded into the graph = launched per replay
+        with torch.cuda.stream(stream):
+            graph.replay()                   # one untimed replay
     barrier()
     with torch.cuda.stream(stream):
         e0.record(stream)
-        for i in range(args.steps):
-            step_device(nwarm + i)
+        if graph is not None:
+            graph.replay()
+        else:
+            for i in range(args.steps):
+                step_device(nwarm + i)
         e1.record(stream)
     barrier()
-    launches_dev = launches() - l0
+    if graph is None:
+        launches_dev = launches() - l0
     total_ms = float(e0.elapsed_time(e1))
 
     # ---- the same on ONE copy (L2 warm when the working set fits), for comparison ------
@@ -413,6 +431,7 @@ def run_native(args):
             "data": "synthetic" if w["name"] in ("uniform", "powerlaw") else "SuiteSparse fixture shipped with the reference, host program's B/C",
             "config": {"workload": w["desc"], "alpha": ALPHA, "beta": BETA, "arith": args.arith,
                        "l2": "warm (--no-flush)" if args.no_flush else (f"inputs larger than L2: {R} independent device copies of A/B/C ({R * alg_bytes / 1e6:.0f} MB > 2 x 126 MB L2), step i uses copy i mod {R}; no flush kernel in the timed region" if R > 1 else f"inputs larger than L2: one copy is {alg_bytes / 1e6:.0f} MB; steps run back to back"),
+                       "launch": f"the {args.steps} steps are one CUDA graph replay" if use_graph else "one by one",
                        "partition": "1 row block" if world == 1 else f"{world} stacked row blocks, one per GPU; NCCL broadcast of B from rank 0 inside every step"},
             "gflops_ref_formula": 2.0 * (nnz + M) * N * world * args.steps / (total_ms * 1e-3) / 1e9,
             "single_copy_back_to_back": {"ms_per_step": warm_ms, "value": flops_step / (warm_ms * 1e-3) / 1e9,
