@@ -79,8 +79,9 @@ enum sx_option {
     SX_OPT_ITEM_NNZ = 3,
     /* sx_spmm_*: page-locked host B and C of up to this many bytes together are read
      * and written by the kernels directly over PCIe (no copy-engine transfers);
-     * larger or pageable operands go through cudaMemcpyAsync.  Default 16 MiB; 0
-     * disables. */
+     * larger or pageable operands go through cudaMemcpyAsync.  Default 1.5 MiB
+     * (measured cross-over on PCIe Gen5: SM-driven transfers reach ~43 GB/s in and
+     * ~31 GB/s out, the copy engines more, but each memcpy costs a launch); 0 disables. */
     SX_OPT_ZEROCOPY_BYTES = 4
 };
 

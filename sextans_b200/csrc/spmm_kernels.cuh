@@ -431,7 +431,75 @@ spmm_staged_kernel(const int nitems, const int4 *__restrict__ items, const int t
     }
 }
 
-// ---- one row group per row (variant 1: matrices that fill less than one wave) -------------------------------------
+// ---- one row group per row (variant 1: matrices that fill less than one wave) ---
+// Latency-oriented walk of one row for G <= 8.  Entries travel in chunks of 8 (each
+// lane holds 8/G (col,val) pairs of a chunk), one chunk is one batch of 8 B-row gathers;
+// the gathers of chunk k+1 are issued before chunk k is accumulated and chunks are
+// fetched two ahead, so a short row costs rowptr -> entries -> B rows instead of one
+// B-row latency per chunk.
+template <typename T, int G, int VPL, bool STRICT>
+__device__ __forceinline__ void accumulate_row_pipelined(
+    typename VecOf<T>::type (&acc)[VPL], const int begin, const int end, const int lg,
+    const unsigned gmask, const int nvec, const int *__restrict__ colidx, const T *__restrict__ val,
+    const T *__restrict__ B, const int64_t ldb) {
+    using V = typename VecOf<T>::type;
+    constexpr int CH = 8;      // entries per chunk
+    constexpr int R = CH / G;  // (col,val) pairs per lane per chunk
+    struct Chunk { int c[R]; T a[R]; };
+    auto fetch = [&](const int b, Chunk &k) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int p = b + r * G + lg;
+            k.c[r] = 0;
+            k.a[r] = T(0);
+            if (p < end) { k.c[r] = __ldg(colidx + p); k.a[r] = __ldg(val + p); }
+        }
+    };
+    auto gather = [&](V (&b)[CH][VPL], const Chunk &k, const int base) {
+#pragma unroll
+        for (int t = 0; t < CH; ++t) {
+            const int cc = __shfl_sync(gmask, k.c[t / G], t % G, G);
+            const V *brow = reinterpret_cast<const V *>(B + (int64_t)cc * ldb);
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const int vi = lg + v * G;
+                if (base + t < end && vi < nvec) b[t][v] = ldg_vec(brow + vi);
+                else vzero(b[t][v]);
+            }
+        }
+    };
+    auto mac_chunk = [&](V (&b)[CH][VPL], const Chunk &k, const int base) {
+#pragma unroll
+        for (int t = 0; t < CH; ++t) {
+            const T av = __shfl_sync(gmask, k.a[t / G], t % G, G);
+            if (base + t < end) {
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) vmac<STRICT>(acc[v], av, b[t][v]);
+            }
+        }
+    };
+    if (begin >= end) return;
+    Chunk k0, k1, k2;
+    fetch(begin, k0);
+    fetch(begin + CH, k1);
+    fetch(begin + 2 * CH, k2);
+    V bA[CH][VPL], bB[CH][VPL];
+    gather(bA, k0, begin);
+    for (int base = begin; base < end; base += 2 * CH) {
+        Chunk k3, k4;
+        if (base + CH < end) gather(bB, k1, base + CH);
+        fetch(base + 3 * CH, k3);
+        mac_chunk(bA, k0, base);
+        if (base + CH >= end) break;
+        if (base + 2 * CH < end) gather(bA, k2, base + 2 * CH);
+        fetch(base + 4 * CH, k4);
+        mac_chunk(bB, k1, base + CH);
+        k0 = k2;
+        k1 = k3;
+        k2 = k4;
+    }
+}
+
 // Rows longer than split_nnz (when > 0) are left to the segment kernels below.
 template <typename T, int G, int VPL, bool STRICT>
 __global__ void __launch_bounds__(256)
@@ -448,17 +516,25 @@ spmm_rows_kernel(const int M, const int *__restrict__ rowptr, const int *__restr
     const int begin = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
     if (split_nnz > 0 && end - begin > split_nnz) return;
 
-    V acc[VPL];
-#pragma unroll
-    for (int v = 0; v < VPL; ++v) vzero(acc[v]);
-    accumulate_range<T, G, VPL, STRICT>(acc, begin, end, 0, 1, lg, gmask, nvec, colidx, val, B, ldb);
-
+    // C_in does not depend on A: fetch it now, use it in the epilogue
     const V *cin = reinterpret_cast<const V *>(Cin + row * ldc);
+    V acc[VPL], cv[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        vzero(acc[v]);
+        vzero(cv[v]);
+        if (lg + v * G < nvec) cv[v] = cin[lg + v * G];
+    }
+    if constexpr (G <= 8 && VPL == 1)
+        accumulate_row_pipelined<T, G, VPL, STRICT>(acc, begin, end, lg, gmask, nvec, colidx, val, B, ldb);
+    else
+        accumulate_range<T, G, VPL, STRICT>(acc, begin, end, 0, 1, lg, gmask, nvec, colidx, val, B, ldb);
+
     V *cout = reinterpret_cast<V *>(Cout + row * ldc);
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
         const int vi = lg + v * G;
-        if (vi < nvec) cout[vi] = vaxpby<STRICT>(alpha, acc[v], beta, cin[vi]);
+        if (vi < nvec) cout[vi] = vaxpby<STRICT>(alpha, acc[v], beta, cv[v]);
     }
 }
 
@@ -556,33 +632,79 @@ colmajor_to_rowmajor_kernel(const int64_t rows, const int cols, const T *__restr
 }
 
 // B (rowsB x cols) and C_in (rowsC x cols) in one launch: blocks [0, tilesB) take B,
-// the rest take C.  Used with the sources in page-locked HOST memory: threadIdx.x runs
-// along a column, so every warp reads 128/256 contiguous bytes over PCIe.
-template <typename T>
+// the rest take C.  Used with the sources in page-locked HOST memory.  threadIdx.x runs
+// along a column and every thread moves VEC consecutive rows with one 16-byte access
+// when VEC > 1 (the host passes VEC = 16/sizeof(T) only if both row counts are multiples
+// of it, which keeps every column start 16-byte aligned), so a warp reads 512 contiguous
+// bytes over PCIe per instruction.
+template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
 colmajor_to_rowmajor_pair_kernel(const int64_t rowsB, const int64_t rowsC, const int cols,
                                  const T *__restrict__ srcB, const T *__restrict__ srcC,
                                  T *__restrict__ dstB, T *__restrict__ dstC, const int64_t ld,
                                  const int tcol, const int64_t tilesB) {
-    __shared__ T tile[32][33];
+    constexpr int TR = 32 * VEC;  // rows per tile
+    __shared__ T tile[32][TR + 1];
     int64_t t = blockIdx.x;
     const bool isC = t >= tilesB;
     if (isC) t -= tilesB;
     const int64_t rows = isC ? rowsC : rowsB;
     const T *src = isC ? srcC : srcB;
     T *dst = isC ? dstC : dstB;
-    const int64_t r0 = (t / tcol) * 32;
+    const int64_t r0 = (t / tcol) * TR;
     const int c0 = (int)(t % tcol) * 32;
     for (int j = threadIdx.y; j < 32; j += 8) {
         const int c = c0 + j;
-        const int64_t r = r0 + threadIdx.x;
-        tile[j][threadIdx.x] = (r < rows && c < cols) ? src[r + rows * (int64_t)c] : T(0);
+        const int64_t r = r0 + (int64_t)threadIdx.x * VEC;
+        if (VEC > 1 && c < cols && r + VEC <= rows) {
+            struct alignas(16) Pack { T v[VEC]; };
+            const Pack p = *reinterpret_cast<const Pack *>(src + r + rows * (int64_t)c);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) tile[j][threadIdx.x * VEC + e] = p.v[e];
+        } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e)
+                tile[j][threadIdx.x * VEC + e] = (r + e < rows && c < cols) ? src[r + e + rows * (int64_t)c] : T(0);
+        }
     }
     __syncthreads();
-    for (int j = threadIdx.y; j < 32; j += 8) {
+    for (int j = threadIdx.y; j < TR; j += 8) {
         const int64_t r = r0 + j;
         const int c = c0 + threadIdx.x;
         if (r < rows && c < ld) dst[r * ld + c] = tile[threadIdx.x][j];
+    }
+}
+
+// row-major device image -> column-major HOST memory, 16 bytes per thread (see above)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+rowmajor_to_colmajor_vec_kernel(const int64_t rows, const int cols, const T *__restrict__ src,
+                                const int64_t ld_src, T *__restrict__ dst) {
+    constexpr int TR = 32 * VEC;
+    __shared__ T tile[32][TR + 1];
+    const int64_t r0 = (int64_t)blockIdx.x * TR;
+    const int c0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < TR; j += 8) {
+        const int64_t r = r0 + j;
+        const int c = c0 + threadIdx.x;
+        tile[threadIdx.x][j] = (r < rows && c < cols) ? src[r * ld_src + c] : T(0);
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int c = c0 + j;
+        const int64_t r = r0 + (int64_t)threadIdx.x * VEC;
+        if (c >= cols) continue;
+        if (VEC > 1 && r + VEC <= rows) {
+            struct alignas(16) Pack { T v[VEC]; };
+            Pack p;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) p.v[e] = tile[j][threadIdx.x * VEC + e];
+            *reinterpret_cast<Pack *>(dst + r + rows * (int64_t)c) = p;
+        } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e)
+                if (r + e < rows) dst[r + e + rows * (int64_t)c] = tile[j][threadIdx.x * VEC + e];
+        }
     }
 }
 

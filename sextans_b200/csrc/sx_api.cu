@@ -111,7 +111,7 @@ struct sx_ctx {
     int split_nnz = 512;
     int kernel = 0;
     int item_nnz = 0;  // 0 = auto
-    int64_t zerocopy_bytes = 16 << 20;
+    int64_t zerocopy_bytes = 3 << 19;  // 1.5 MiB: above that the copy engines win
     int last_path = 0;  // 1: the last host-facing call took the zero-copy path
     bool segments_dirty = false;
 
@@ -161,11 +161,13 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
     const int rows_per_block = threads / G;
     const int64_t ldp = ((int64_t)N + 7) / 8 * 8;
     int rc;
-    // kernel 0 (auto): a matrix whose rows, one lane group each, fill less than one wave
-    // of the machine is latency-bound -- it takes variant 1 (most parallelism, shortest
-    // dependent chain; measured 10.4 us against 14.7 us per nasa4704 SpMM); anything
-    // larger takes the nnz-balanced TMA-staged variant 2.
-    const bool sub_wave = (int64_t)c->M * G <= (int64_t)c->sm_count * 2048;
+    // kernel 0 (auto): a matrix whose rows, one lane group each, fit in ONE wave of
+    // variant 1 (which keeps 16 B-row gathers in flight per lane and therefore runs at
+    // ~512 threads per SM) is latency-bound and takes variant 1 -- most parallelism,
+    // shortest dependent chain (nasa4704: 7.2 us per SpMM against 14.7 us staged;
+    // pcrystk02 N=16: 14.4 against 20.4).  Anything larger takes the nnz-balanced
+    // TMA-staged variant 2 (pcrystk02 N=32: 18.8 us against 24.8 us).
+    const bool sub_wave = (int64_t)c->M * G <= (int64_t)c->sm_count * 512;
     const int variant = c->kernel != 0 ? c->kernel : (sub_wave ? 1 : 2);
     if (variant == 1) {
         // variant 1: one lane group per row + one warp per long-row segment
@@ -556,6 +558,7 @@ int fetch_C(sx_ctx *c, T *host) {
 // Device-visible alias of a page-locked host pointer (cudaHostAlloc / cudaHostRegister /
 // sx_host_alloc), or nullptr for pageable memory.
 void *mapped_alias(const void *host) {
+    // asked on every call (no cache: a freed pinned buffer's address may come back pageable)
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
         cudaGetLastError();
@@ -587,17 +590,33 @@ int spmm_host(sx_ctx *c, int N, T alpha, const T *B, T beta, T *C, int rp_time, 
         const size_t szB = std::max<size_t>((size_t)c->K * c->ld * sizeof(T), 16);
         const size_t szC = std::max<size_t>((size_t)c->M * c->ld * sizeof(T), 16);
         if ((rc = c->B.ensure(szB)) || (rc = c->Cin.ensure(szC)) || (rc = c->Cout.ensure(szC))) return rc;
-        const int64_t tB = ((int64_t)c->K + 31) / 32, tC = ((int64_t)c->M + 31) / 32, tcol = (c->ld + 31) / 32;
+        // 16-byte accesses to host memory when every column start stays 16-byte aligned
+        constexpr int VEC = 16 / (int)sizeof(T);
+        const bool vec = c->K % VEC == 0 && c->M % VEC == 0 && (((uintptr_t)dB | (uintptr_t)dC) & 15) == 0;
+        const int tr = vec ? 32 * VEC : 32;
+        const int64_t tB = ((int64_t)c->K + tr - 1) / tr, tC = ((int64_t)c->M + tr - 1) / tr, tcol = (c->ld + 31) / 32;
         if ((tB + tC) * tcol > 0) {
             dim3 block(32, 8), grid((unsigned)((tB + tC) * tcol));
-            sx::colmajor_to_rowmajor_pair_kernel<T><<<grid, block, 0, c->stream>>>(
-                c->K, c->M, N, (const T *)dB, (const T *)dC, (T *)c->B.p, (T *)c->Cin.p, c->ld, (int)tcol, tB * tcol);
+            if (vec)
+                sx::colmajor_to_rowmajor_pair_kernel<T, VEC><<<grid, block, 0, c->stream>>>(
+                    c->K, c->M, N, (const T *)dB, (const T *)dC, (T *)c->B.p, (T *)c->Cin.p, c->ld, (int)tcol, tB * tcol);
+            else
+                sx::colmajor_to_rowmajor_pair_kernel<T, 1><<<grid, block, 0, c->stream>>>(
+                    c->K, c->M, N, (const T *)dB, (const T *)dC, (T *)c->B.p, (T *)c->Cin.p, c->ld, (int)tcol, tB * tcol);
             c->launches++;
             SX_CUDA(cudaGetLastError());
         }
         c->has_B = c->has_C = true;
         if ((rc = enqueue_launch<T>(c, alpha, beta, rp_time))) return rc;
-        if ((rc = transpose_out(c, c->dtype, c->M, N, c->Cout.p, c->ld, dC))) return rc;
+        if (c->M > 0) {
+            dim3 block(32, 8), grid((unsigned)tC, (unsigned)((N + 31) / 32));
+            if (vec)
+                sx::rowmajor_to_colmajor_vec_kernel<T, VEC><<<grid, block, 0, c->stream>>>(c->M, N, (const T *)c->Cout.p, c->ld, (T *)dC);
+            else
+                sx::rowmajor_to_colmajor_vec_kernel<T, 1><<<grid, block, 0, c->stream>>>(c->M, N, (const T *)c->Cout.p, c->ld, (T *)dC);
+            c->launches++;
+            SX_CUDA(cudaGetLastError());
+        }
         c->last_path = 1;
         return finish_stream(c, kernel_ns);
     }

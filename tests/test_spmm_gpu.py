@@ -260,7 +260,7 @@ def test_host_paths_zero_copy_and_copy_engine(eng):
         eng.spmm(N, 0.85, pB, -2.06, pC)
         assert eng.info(sx.INFO_HOST_PATH) == 0 and np.array_equal(bits(np.asarray(pC)), bits(ref))
     finally:
-        eng.set_option(sx.OPT_ZEROCOPY_BYTES, 16 << 20)
+        eng.set_option(sx.OPT_ZEROCOPY_BYTES, 3 << 19)
 
 
 @pytest.mark.parametrize("dtype,tol", [(np.float32, 1e-5), (np.float64, 1e-12)])
