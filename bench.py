@@ -60,6 +60,7 @@ def parse():
     p.add_argument("--kernel", type=int, default=0, help="SX_OPT_KERNEL (0 auto, 1 row per lane group, 2 TMA-staged items)")
     p.add_argument("--item-nnz", type=int, default=0, help="SX_OPT_ITEM_NNZ (0 auto)")
     p.add_argument("--split", type=int, default=-1, help="SX_OPT_SPLIT_ROW_NNZ (-1 default)")
+    p.add_argument("--ref-threads", type=int, default=1, help="--impl reference: threads of the CPU path (1 = as the reference runs it; -1 = all cores, OpenMP port)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-flush", action="store_true", help="leave L2 warm between steps")
     p.add_argument("--no-graph", action="store_true", help="launch the timed steps one by one instead of replaying a CUDA graph")
@@ -206,12 +207,18 @@ def cpu_baseline(w, threads, budget_s=12.0, min_runs=3):
 
 
 def run_reference(args):
+    """The reference arm: cpu_spmm_CSR as the reference runs it -- ONE thread, the function
+    has no threading (src/sparse_helper.h:262-290) -- through oracle/_ref (the reference's
+    own header, compiled unmodified) for fp32 and the line-for-line double port for fp64.
+    --ref-threads N times the port's row-parallel OpenMP variant instead; the default line
+    carries that all-core figure as extra information."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle
     w = build_workload(args)
-    threads = max(1, oracle.lib().sx_oracle_max_threads())
+    all_threads = max(1, oracle.lib().sx_oracle_max_threads())
+    threads = all_threads if args.ref_threads < 0 else max(1, args.ref_threads)
     M, K, N, nnz = w["M"], w["K"], w["N"], w["nnz"]
     est = 2.0 * nnz * N / (1.5e9 * threads)
     rp, ci, v, Cin = w["rowptr"], w["colidx"], w["val"], w["Cin"]
@@ -224,26 +231,42 @@ def run_reference(args):
         M, nnz = Ms, int(rp[-1])
         sample = f"first {Ms} rows ({nnz} nnz) of the workload per step, full B"
     a, b = w["dtype"].type(ALPHA), w["dtype"].type(BETA)
-    for _ in range(args.warmup):
-        oracle.spmm_csr(M, N, K, rp, ci, v, a, w["B"], b, Cin.copy(), threads=threads)
+    use_ref = w["dtype"] == np.float32 and threads == 1 and oracle.ref() is not None
+
+    def one(C):
+        if use_ref:
+            oracle.ref_spmm_csr(M, N, K, rp, ci, v, ALPHA, w["B"], BETA, C)
+        else:
+            oracle.spmm_csr(M, N, K, rp, ci, v, a, w["B"], b, C, threads=threads)
+
+    steps = args.steps
+    if est * steps > 120:   # keep the whole run within a few minutes
+        steps = max(3, int(120 / est))
+    for _ in range(min(args.warmup, 3)):
+        one(Cin.copy())
     total = 0.0
-    for _ in range(args.steps):
+    for _ in range(steps):
         C = Cin.copy()
         t0 = time.perf_counter()
-        oracle.spmm_csr(M, N, K, rp, ci, v, a, w["B"], b, C, threads=threads)
+        one(C)
         total += time.perf_counter() - t0
-    val = 2.0 * nnz * N * args.steps / total / 1e9
-    single = cpu_baseline(w, 1, budget_s=6.0)
+    val = 2.0 * nnz * N * steps / total / 1e9
+    extra = None
+    if threads == 1 and all_threads > 1:
+        extra = cpu_baseline(dict(w, M=M, nnz=nnz, rowptr=rp, colidx=ci, val=v, Cin=Cin), all_threads, budget_s=6.0)
+        extra["note"] = "row-parallel OpenMP over the oracle port (bitwise the same result); NOT the reference, which is single-threaded"
     line = {
         "impl": "reference", "metric": "SpMM GFLOP/s (2*nnz*N)", "value": val, "unit": "GFLOP/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64" if w["dtype"] == np.float64 else "f32", "data": "synthetic" if w["name"] in ("uniform", "powerlaw") else "SuiteSparse fixture shipped with the reference, host program's B/C",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3),
+        "ms_per_step": total / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64" if w["dtype"] == np.float64 else "f32",
+        "data": "synthetic" if w["name"] in ("uniform", "powerlaw") else "SuiteSparse fixture shipped with the reference, host program's B/C",
         "config": {"workload": w["desc"], "alpha": ALPHA, "beta": BETA},
-        "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": threads, "kind": "port", "sample": sample,
-                         "note": "row-parallel OpenMP over the oracle port of cpu_spmm_CSR (bitwise the same result); "
-                                 "the reference function itself is single-threaded",
-                         "single_thread": single},
+        "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": threads, "kind": "reference" if use_ref else "port",
+                         "sample": sample,
+                         "note": "cpu_spmm_CSR as the reference runs it: one thread (src/sparse_helper.h:262-290 has no threading)"
+                                 if threads == 1 else "row-parallel OpenMP over the oracle port of cpu_spmm_CSR",
+                         "all_cores_openmp_port": extra},
         "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
