@@ -10,6 +10,8 @@ Workloads (BASELINE.json configs):
   pcrystk02  pcrystk02.mtx N=16 fp32   (configs[2]; --ncols 8|16|32|64)
   uniform    synthetic M=K=1e6, 20 nnz/row, N=128 fp32      (configs[3])
   powerlaw   synthetic power-law M=K=1e6, nnz~1e8, N=16 fp64 (configs[4])
+  fem        synthetic block-structured (4 dof/node) M=K=1e6, nnz~9.5e7, N=16 fp64: the
+             input of the dense-tile tensor-core variant (configs[4] tail; --tiles 4)
 
 Own arm, per rank (one process per GPU): A's row block resident on the device; at N>1
 the matrix is N row blocks of the workload stacked (weak scaling), every rank owns one,
@@ -42,6 +44,7 @@ WORKLOADS = {
     "pcrystk02": ("suitesparse", np.float32, 16),
     "uniform": ("uniform", np.float32, 128),
     "powerlaw": ("powerlaw", np.float64, 16),
+    "fem": ("fem", np.float64, 16),
 }
 ALPHA, BETA = float(np.float32(0.85)), float(np.float32(-2.06))   # host.cpp:29-30
 
@@ -60,6 +63,7 @@ def parse():
     p.add_argument("--kernel", type=int, default=0, help="SX_OPT_KERNEL (0 auto, 1 row per lane group, 2 TMA-staged items)")
     p.add_argument("--item-nnz", type=int, default=0, help="SX_OPT_ITEM_NNZ (0 auto)")
     p.add_argument("--split", type=int, default=-1, help="SX_OPT_SPLIT_ROW_NNZ (-1 default)")
+    p.add_argument("--tiles", type=int, default=0, help="SX_OPT_TILE_MIN_ROWS (fp64 dense-tile tensor-core variant; 0 off)")
     p.add_argument("--ref-threads", type=int, default=1, help="--impl reference: threads of the CPU path (1 = as the reference runs it; -1 = all cores, OpenMP port)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-flush", action="store_true", help="leave L2 warm between steps")
@@ -86,6 +90,13 @@ def build_workload(args):
         nnz = int(ci.size)
         B, Cin = wl.random_dense(M, K, N, 12345, dtype)
         desc = f"synthetic uniform CSR M=K={M} nnz={nnz} (20/row) N={N} {np.dtype(dtype).name}, seed 12345"
+    elif kind == "fem":
+        nodes = max(250, int(250_000 * args.scale))
+        M = K = nodes * 4
+        rp, ci, v = wl.fem_like_csr(nodes, 4, 23, 12345, dtype)
+        nnz = int(ci.size)
+        B, Cin = wl.random_dense(M, K, N, 12345, dtype)
+        desc = f"synthetic FEM-like CSR (4 dof/node, dense 4x4 couplings) M=K={M} nnz={nnz} N={N} {np.dtype(dtype).name}, seed 12345"
     else:
         M = K = max(1000, int(1_000_000 * args.scale))
         rp, ci, v = wl.powerlaw_csr(M, K, int(100_000_000 * args.scale), 12345, dtype)
@@ -314,6 +325,7 @@ def run_native(args):
         e.set_stream(stream.cuda_stream)
         e.set_option(sx.OPT_KERNEL, args.kernel)
         e.set_option(sx.OPT_ITEM_NNZ, args.item_nnz)
+        e.set_option(sx.OPT_TILE_MIN_ROWS, args.tiles)
         if args.split >= 0:
             e.set_option(sx.OPT_SPLIT_ROW_NNZ, args.split)
         e.upload_csr(M, K, w["rowptr"], w["colidx"], w["val"])
@@ -441,9 +453,15 @@ def run_native(args):
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
 
     lk = eng.info(sx.INFO_LAST_KERNEL)
-    kernel_name = ({1: "spmm_rows_kernel (+segments/finalize)", 2: "spmm_staged_kernel"}.get(lk // 10000, "?")
+    if eng.info(sx.INFO_TILE_NNZ) > 0:
+        tiles_note = (f"; dense tiles: {eng.info(sx.INFO_TILE_NNZ)} nnz in {eng.info(sx.INFO_TILE_SLOTS)} slots "
+                      f"(fill {eng.info(sx.INFO_TILE_NNZ) / max(1, eng.info(sx.INFO_TILE_SLOTS)):.2f}) on spmm_panels_dmma_kernel, "
+                      f"{eng.info(sx.INFO_REST_NNZ)} nnz left to CSR")
+    else:
+        tiles_note = ""
+    kernel_name = ({1: "spmm_rows_kernel (+segments/finalize)", 2: "spmm_staged_kernel", 4: "spmm_panels_dmma_kernel"}.get(lk // 10000, "?")
                    + f" <G={lk % 10000 // 100}, VPL={lk % 100 // 10}, {'fast' if lk % 10 else 'strict'}>"
-                   + (f", {eng.info(sx.INFO_ITEMS)} items of <= {eng.info(sx.INFO_ITEM_NNZ)} nnz, {eng.info(sx.INFO_SPLIT_ROWS)} split rows" if lk // 10000 == 2 else ""))
+                   + (f", {eng.info(sx.INFO_ITEMS)} items of <= {eng.info(sx.INFO_ITEM_NNZ)} nnz, {eng.info(sx.INFO_SPLIT_ROWS)} split rows" if lk // 10000 == 2 else "") + tiles_note)
     host_path = "zero-copy kernels over PCIe (no memcpy)" if eng.info(sx.INFO_HOST_PATH) == 1 else "cudaMemcpyAsync + layout kernels"
     if rank == 0:
         line = {

@@ -82,7 +82,14 @@ enum sx_option {
      * larger or pageable operands go through cudaMemcpyAsync.  Default 1.5 MiB
      * (measured cross-over on PCIe Gen5: SM-driven transfers reach ~43 GB/s in and
      * ~31 GB/s out, the copy engines more, but each memcpy costs a launch); 0 disables. */
-    SX_OPT_ZEROCOPY_BYTES = 4
+    SX_OPT_ZEROCOPY_BYTES = 4,
+    /* dense-tile (blocked) variant on the FP64 tensor cores, fp64 only; read by the NEXT
+     * sx_upload_csr_f64.  0 (default) off.  t in 1..8: in every panel of 8 consecutive
+     * rows a column used by >= t rows goes into the panel's dense tile (DMMA m8n8k4),
+     * the rest of A stays CSR and is added afterwards.  Summation order then differs from
+     * cpu_spmm_CSR (fp64 rounding-level differences), and an explicit zero of a tile
+     * times a non-finite B entry yields NaN. */
+    SX_OPT_TILE_MIN_ROWS = 5
 };
 
 enum sx_info {
@@ -96,7 +103,10 @@ enum sx_info {
     SX_INFO_LD = 7,          /* leading dimension (elements) of the context's row-major B/C */
     SX_INFO_ITEMS = 8,       /* work items of the main kernel */
     SX_INFO_ITEM_NNZ = 9,    /* nonzero budget per work item in use */
-    SX_INFO_HOST_PATH = 10   /* 1 if the last sx_spmm_* call took the zero-copy path */
+    SX_INFO_HOST_PATH = 10,  /* 1 if the last sx_spmm_* call took the zero-copy path */
+    SX_INFO_TILE_NNZ = 11,   /* nonzeros held in dense tiles */
+    SX_INFO_TILE_SLOTS = 12, /* tile slots incl. explicit zeros (fill = TILE_NNZ / TILE_SLOTS) */
+    SX_INFO_REST_NNZ = 13    /* nonzeros left to the CSR kernels */
 };
 
 /* ---- library ------------------------------------------------------------- */

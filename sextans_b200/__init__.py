@@ -24,9 +24,9 @@ _LIB = None
 
 SX_F32, SX_F64 = 0, 1
 STRICT, FAST = 0, 1
-OPT_ARITH, OPT_SPLIT_ROW_NNZ, OPT_KERNEL, OPT_ITEM_NNZ, OPT_ZEROCOPY_BYTES = 0, 1, 2, 3, 4
+OPT_ARITH, OPT_SPLIT_ROW_NNZ, OPT_KERNEL, OPT_ITEM_NNZ, OPT_ZEROCOPY_BYTES, OPT_TILE_MIN_ROWS = 0, 1, 2, 3, 4, 5
 (INFO_LAUNCHES, INFO_M, INFO_K, INFO_NNZ, INFO_DTYPE, INFO_SPLIT_ROWS, INFO_LAST_KERNEL, INFO_LD,
- INFO_ITEMS, INFO_ITEM_NNZ, INFO_HOST_PATH) = range(11)
+ INFO_ITEMS, INFO_ITEM_NNZ, INFO_HOST_PATH, INFO_TILE_NNZ, INFO_TILE_SLOTS, INFO_REST_NNZ) = range(14)
 
 _PI32 = C.POINTER(C.c_int32)
 _PF = C.POINTER(C.c_float)

@@ -607,6 +607,77 @@ spmm_finalize_kernel(const int nsplit, const int *__restrict__ split_row,
     }
 }
 
+// ---- dense-tile variant: 8-row panels on the FP64 tensor cores (DMMA) ---------------
+// Where A admits dense sub-blocks (FEM-type matrices: the rows of a node share their
+// columns) the upload splits A into  A = A_tiles + A_rest  (sx_api.cu: build_panels):
+// in every panel of 8 consecutive rows, a column used by at least `tau` of the 8 rows
+// becomes a column of the panel's dense 8 x w tile (missing entries are explicit zeros),
+// everything else stays in a CSR remainder that the staged kernel adds afterwards.
+// One warp owns one panel and walks its tile four columns at a time with
+//     mma.sync.aligned.m8n8k4.row.col.f64  (SASS DMMA.884)
+// -- tcgen05.mma has no fp64 kind, so the legacy warp-level path IS the fp64 tensor path
+// on sm_100a.  The point of the format is not the flops but the gathers: one B row is
+// fetched once per panel column instead of once per nonzero, i.e. up to 8x fewer bytes
+// through L2, which is what bounds SpMM on this machine.
+// Storage per k-step (4 tile columns): 4 column indices + 32 values in A-fragment order
+// (lane l holds A[l/4][l%4]), so a step is one coalesced 256-byte load.
+// Output: C_out = alpha * A_tiles * B + beta * C_in for EVERY row (panels without tile
+// columns just run the epilogue); the remainder is added in place afterwards.
+// Summation order differs from cpu_spmm_CSR (tolerance-level parity, not bit parity),
+// and a padded zero times a non-finite B entry gives NaN where the reference has none.
+__device__ __forceinline__ void dmma884(double &c0, double &c1, const double a, const double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int NT, bool STRICT>
+__global__ void __launch_bounds__(256)
+spmm_panels_dmma_kernel(const int npanels, const int M, const int *__restrict__ step_ptr,
+                        const int *__restrict__ tcols, const double *__restrict__ tvals,
+                        const double *__restrict__ B, const int64_t ldb, const double *Cin, double *Cout,
+                        const int64_t ldc, const double alpha, const double beta, const int N) {
+    constexpr int UNR = 4;  // k-steps in flight
+    const int lane = threadIdx.x & 31;
+    const int panel = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (panel >= npanels) return;  // warp-uniform
+    const int kq = lane & 3, rq = lane >> 2;
+    const int s0 = __ldg(step_ptr + panel), s1 = __ldg(step_ptr + panel + 1);
+    double acc[NT][2];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = 0.0;
+    const double *Bq = B + rq;  // this lane's column inside an 8-wide n-tile
+    for (int s = s0; s < s1; s += UNR) {
+        double a[UNR], b[UNR][NT];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const bool live = s + u < s1;
+            const int col = live ? __ldg(tcols + (size_t)(s + u) * 4 + kq) : 0;
+            a[u] = live ? __ldg(tvals + (size_t)(s + u) * 32 + lane) : 0.0;
+            const double *brow = Bq + (int64_t)col * ldb;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) b[u][t] = (live && 8 * t + rq < N) ? __ldg(brow + 8 * t) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+#pragma unroll
+            for (int t = 0; t < NT; ++t) dmma884(acc[t][0], acc[t][1], a[u], b[u][t]);
+    }
+    const int row = panel * 8 + rq;
+    if (row < M) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const int n = 8 * t + 2 * kq;
+            if (n + 1 < N) {
+                const double2 cin = *reinterpret_cast<const double2 *>(Cin + (int64_t)row * ldc + n);
+                *reinterpret_cast<double2 *>(Cout + (int64_t)row * ldc + n) =
+                    vaxpby<STRICT>(alpha, make_double2(acc[t][0], acc[t][1]), beta, cin);
+            } else if (n < N) {
+                Cout[(int64_t)row * ldc + n] = axpby<STRICT>(alpha, acc[t][0], beta, Cin[(int64_t)row * ldc + n]);
+            }
+        }
+    }
+}
+
 // ---- layout changes at the host boundary ---------------------------------------
 // column-major (ld = rows) -> row-major (ld = ld_dst, pad columns zero-filled); the
 // device-side stand-in for the reference's B/C channel repacking

@@ -99,6 +99,12 @@ struct sx_ctx {
     std::vector<Plan *> plans;
     Plan *last_plan = nullptr;
     std::vector<int32_t> h_rowptr;  // kept to re-derive segments when the option changes
+    // dense-tile split A = A_tiles + A_rest (fp64, SX_OPT_TILE_MIN_ROWS > 0 at upload)
+    int tile_min_rows = 0;
+    int npanels = 0;
+    int64_t tile_steps = 0, tile_nnz = 0, rest_nnz = 0;
+    DevBuf step_ptr, tcols, tvals;
+    sx_ctx *rest = nullptr;  // child context holding A_rest; shares this context's stream
 
     // dense operands (row-major, ld elements per row)
     int N = 0;
@@ -249,6 +255,56 @@ int launch_group(sx_ctx *c, Shape s, int N, T alpha, const T *dB, int64_t ldb, T
 }
 
 
+template <typename T>
+int spmm_device(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, const T *dCin, T *dCout, int64_t ldc);
+
+// A = A_tiles + A_rest:  C_out = alpha*A_tiles*B + beta*C_in on the FP64 tensor cores,
+// then C_out += alpha*A_rest*B with the CSR kernels, in place.
+template <typename T>
+int spmm_tiles(sx_ctx *, int, T, const T *, int64_t, T, const T *, T *, int64_t) {
+    return fail(SX_ERR_INVALID, "internal: the dense-tile variant is fp64 only");
+}
+template <>
+int spmm_tiles<double>(sx_ctx *c, int N, double alpha, const double *dB, int64_t ldb, double beta,
+                       const double *dCin, double *dCout, int64_t ldc) {
+    const unsigned grid = (unsigned)(((int64_t)c->npanels * 32 + 255) / 256);
+    for (int n0 = 0; n0 < N; n0 += 64) {
+        const int n = std::min(64, N - n0);
+        const int nt = (n + 7) / 8;
+#define SX_PANELS(NT)                                                                              \
+    do {                                                                                           \
+        if (c->arith == 0)                                                                         \
+            sx::spmm_panels_dmma_kernel<NT, true><<<grid, 256, 0, c->stream>>>(                    \
+                c->npanels, c->M, (const int *)c->step_ptr.p, (const int *)c->tcols.p,             \
+                (const double *)c->tvals.p, dB + n0, ldb, dCin + n0, dCout + n0, ldc, alpha, beta, n); \
+        else                                                                                       \
+            sx::spmm_panels_dmma_kernel<NT, false><<<grid, 256, 0, c->stream>>>(                   \
+                c->npanels, c->M, (const int *)c->step_ptr.p, (const int *)c->tcols.p,             \
+                (const double *)c->tvals.p, dB + n0, ldb, dCin + n0, dCout + n0, ldc, alpha, beta, n); \
+    } while (0)
+        if (nt <= 1) SX_PANELS(1);
+        else if (nt <= 2) SX_PANELS(2);
+        else if (nt <= 4) SX_PANELS(4);
+        else SX_PANELS(8);
+#undef SX_PANELS
+        c->launches++;
+    }
+    SX_CUDA(cudaGetLastError());
+    c->last_kernel = 40000 + (c->arith ? 1 : 0);
+    if (c->rest && c->rest_nnz > 0) {
+        sx_ctx *r = c->rest;
+        r->stream = c->stream;
+        r->arith = c->arith;
+        r->kernel = c->kernel;
+        r->item_nnz = c->item_nnz;
+        const int64_t before = r->launches;
+        int rc = spmm_device<double>(r, N, alpha, dB, ldb, 1.0, dCout, dCout, ldc);
+        c->launches += r->launches - before;
+        if (rc) return rc;
+    }
+    return SX_OK;
+}
+
 // One SpMM over device-resident row-major operands.  Column counts beyond what one
 // row group covers (4 vectors x 32 lanes) are processed in column panels.
 template <typename T>
@@ -266,6 +322,8 @@ int spmm_device(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, con
     if (((uintptr_t)dB | (uintptr_t)dCin | (uintptr_t)dCout) & 15)
         return fail(SX_ERR_INVALID, "device operands must be 16-byte aligned");
     if (c->segments_dirty && (rc = refresh_segments(c))) return rc;
+
+    if (c->tile_steps > 0) return spmm_tiles<T>(c, N, alpha, dB, ldb, beta, dCin, dCout, ldc);
 
     const int panel_cols = 4 * 32 * E;  // widest shape: G = 32, VPL = 4
     for (int n0 = 0; n0 < N; n0 += panel_cols) {
@@ -403,6 +461,127 @@ int refresh_segments(sx_ctx *c) {
 }
 
 template <typename T>
+int upload_csr(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rowptr, const int32_t *colidx, const T *val);
+
+void drop_tiles(sx_ctx *c) {
+    c->npanels = 0;
+    c->tile_steps = c->tile_nnz = c->rest_nnz = 0;
+    if (c->rest) {
+        sx_ctx *r = c->rest;
+        c->rest = nullptr;
+        r->stream = c->stream;
+        drop_plans(r);
+        for (DevBuf *b : {&r->rowptr, &r->colidx, &r->val, &r->split_row, &r->split_seg_ptr, &r->seg_begin,
+                          &r->seg_end, &r->partial})
+            b->release();
+        delete r;
+    }
+}
+
+// Split A into 8-row panel tiles and a CSR remainder (see spmm_panels_dmma_kernel).
+int build_panels(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rowptr, const int32_t *colidx,
+                 const double *val) {
+    const int tau = c->tile_min_rows;
+    const int P = (M + 7) / 8;
+    struct Ent { int32_t col, r, j; };
+    std::vector<int32_t> step_ptr((size_t)P + 1, 0), tcols, rrp((size_t)M + 1, 0), rci;
+    std::vector<double> tvals, rv;
+    std::vector<char> used((size_t)nnz, 0);
+    std::vector<Ent> ents;
+    std::vector<int32_t> dcols;
+    int64_t steps = 0, tile_nnz = 0;
+    for (int p = 0; p < P; ++p) {
+        const int r0 = p * 8, r1 = std::min(M, r0 + 8);
+        ents.clear();
+        for (int r = r0; r < r1; ++r)
+            for (int32_t j = rowptr[r]; j < rowptr[r + 1]; ++j) ents.push_back({colidx[j], r - r0, j});
+        std::sort(ents.begin(), ents.end(), [](const Ent &a, const Ent &b) {
+            return a.col != b.col ? a.col < b.col : (a.r != b.r ? a.r < b.r : a.j < b.j);
+        });
+        dcols.clear();
+        const size_t first_val = tvals.size();
+        // pass 1: which columns are dense enough
+        for (size_t i = 0; i < ents.size();) {
+            size_t e = i;
+            int rows_here = 0, last_r = -1;
+            while (e < ents.size() && ents[e].col == ents[i].col) {
+                if (ents[e].r != last_r) { ++rows_here; last_r = ents[e].r; }
+                ++e;
+            }
+            if (rows_here >= tau) dcols.push_back(ents[i].col);
+            i = e;
+        }
+        const int w = (int)dcols.size();
+        const int nsteps = (w + 3) / 4;
+        if (w > 0) {
+            tcols.resize(tcols.size() + (size_t)nsteps * 4, dcols.back());  // pad slots reuse a real column
+            std::copy(dcols.begin(), dcols.end(), tcols.end() - (size_t)nsteps * 4);
+            tvals.resize(first_val + (size_t)nsteps * 32, 0.0);
+            // pass 2: first entry of every (row, dense column) goes into the tile
+            size_t di = 0;
+            for (size_t i = 0; i < ents.size();) {
+                size_t e = i;
+                while (e < ents.size() && ents[e].col == ents[i].col) ++e;
+                while (di < dcols.size() && dcols[di] < ents[i].col) ++di;
+                if (di < dcols.size() && dcols[di] == ents[i].col) {
+                    int last_r = -1;
+                    for (size_t q = i; q < e; ++q) {
+                        if (ents[q].r == last_r) continue;  // duplicate (row, col): stays in the remainder
+                        last_r = ents[q].r;
+                        const size_t step = di / 4, kk = di % 4;
+                        tvals[first_val + step * 32 + (size_t)ents[q].r * 4 + kk] = val[ents[q].j];
+                        used[ents[q].j] = 1;
+                        ++tile_nnz;
+                    }
+                }
+                i = e;
+            }
+        }
+        steps += nsteps;
+        step_ptr[p + 1] = (int32_t)steps;
+        for (int r = r0; r < r1; ++r) {
+            for (int32_t j = rowptr[r]; j < rowptr[r + 1]; ++j)
+                if (!used[j]) { rci.push_back(colidx[j]); rv.push_back(val[j]); }
+            rrp[r + 1] = (int32_t)rci.size();
+        }
+    }
+    if (steps > INT32_MAX / 32) return fail(SX_ERR_INVALID, "dense-tile structure too large for 32-bit offsets");
+    drop_tiles(c);
+    if (tile_nnz == 0) return SX_OK;  // nothing dense: plain CSR path
+    int rc;
+    if ((rc = c->step_ptr.ensure(step_ptr.size() * 4)) || (rc = c->tcols.ensure(tcols.size() * 4 + 16)) ||
+        (rc = c->tvals.ensure(tvals.size() * 8 + 16)))
+        return rc;
+    SX_CUDA(cudaMemcpyAsync(c->step_ptr.p, step_ptr.data(), step_ptr.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    SX_CUDA(cudaMemcpyAsync(c->tcols.p, tcols.data(), tcols.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    SX_CUDA(cudaMemcpyAsync(c->tvals.p, tvals.data(), tvals.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    SX_CUDA(cudaStreamSynchronize(c->stream));
+    sx_ctx *r = new (std::nothrow) sx_ctx();
+    if (!r) return fail(SX_ERR_NOMEM, "out of host memory");
+    r->device = c->device;
+    r->sm_count = c->sm_count;
+    r->stream = c->stream;
+    r->split_nnz = c->split_nnz;
+    rc = upload_csr<double>(r, M, K, (int64_t)rci.size(), rrp.data(), rci.empty() ? rrp.data() : rci.data(),
+                            rv.empty() ? val : rv.data());
+    if (rc) { delete r; return rc; }
+    c->rest = r;
+    c->npanels = P;
+    c->tile_steps = steps;
+    c->tile_nnz = tile_nnz;
+    c->rest_nnz = (int64_t)rci.size();
+    return SX_OK;
+}
+
+template <typename T>
+int maybe_build_panels(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rp, const int32_t *ci, const T *v) {
+    drop_tiles(c);
+    if (c->tile_min_rows <= 0) return SX_OK;
+    if constexpr (sizeof(T) == 8) return build_panels(c, M, K, nnz, rp, ci, v);
+    else return fail(SX_ERR_INVALID, "SX_OPT_TILE_MIN_ROWS: the dense-tile variant is fp64 only (no exact fp32 tensor-core kind)");
+}
+
+template <typename T>
 int upload_csr(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rowptr, const int32_t *colidx,
                const T *val) {
     int rc = bind(c);
@@ -435,6 +614,7 @@ int upload_csr(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rowptr, cons
     c->has_B = c->has_C = false;
     c->N = 0; c->ld = 0;
     if ((rc = refresh_segments(c))) return rc;
+    if ((rc = maybe_build_panels<T>(c, M, K, nnz, rowptr, colidx, val))) return rc;
     c->has_A = true;
     return SX_OK;
 }
@@ -706,6 +886,8 @@ int sx_destroy(sx_ctx *c) {
                       &c->seg_end, &c->partial, &c->B, &c->Cin, &c->Cout, &c->stage})
         b->release();
     drop_plans(c);
+    drop_tiles(c);
+    for (DevBuf *b : {&c->step_ptr, &c->tcols, &c->tvals}) b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -731,10 +913,15 @@ int sx_set_option(sx_ctx *c, int option, int64_t value) {
             if (value != 0 && value < 32) return fail(SX_ERR_INVALID, "SX_OPT_SPLIT_ROW_NNZ must be 0 or >= 32");
             c->split_nnz = (int)value;
             c->segments_dirty = c->has_A;
+            if (c->rest) { c->rest->split_nnz = (int)value; c->rest->segments_dirty = true; }
             return SX_OK;
         case SX_OPT_KERNEL:
             if (value < 0 || value > 2) return fail(SX_ERR_INVALID, "SX_OPT_KERNEL is 0 (auto), 1 (row per lane group) or 2 (TMA-staged work items)");
             c->kernel = (int)value;
+            return SX_OK;
+        case SX_OPT_TILE_MIN_ROWS:
+            if (value < 0 || value > 8) return fail(SX_ERR_INVALID, "SX_OPT_TILE_MIN_ROWS must be in [0, 8]");
+            c->tile_min_rows = (int)value;  // takes effect at the next sx_upload_csr_f64
             return SX_OK;
         case SX_OPT_ZEROCOPY_BYTES:
             if (value < 0) return fail(SX_ERR_INVALID, "SX_OPT_ZEROCOPY_BYTES must be >= 0");
@@ -744,6 +931,7 @@ int sx_set_option(sx_ctx *c, int option, int64_t value) {
             if (value < 0 || value > (1 << 20) || (value != 0 && value < 4)) return fail(SX_ERR_INVALID, "SX_OPT_ITEM_NNZ must be 0 or in [4, 2^20]");
             c->item_nnz = (int)value;
             c->segments_dirty = c->has_A;
+            if (c->rest) c->rest->segments_dirty = true;
             return SX_OK;
         default:
             return fail(SX_ERR_INVALID, "unknown option %d", option);
@@ -765,6 +953,9 @@ int sx_get_info(sx_ctx *c, int what, int64_t *value) {
         case SX_INFO_SPLIT_ROWS: *value = (c->last_kernel / 10000 != 2 || !c->last_plan) ? c->nsplit : c->last_plan->nsplit; return SX_OK;
         case SX_INFO_LAST_KERNEL: *value = c->last_kernel; return SX_OK;
         case SX_INFO_LD: *value = c->ld; return SX_OK;
+        case SX_INFO_TILE_NNZ: *value = c->tile_nnz; return SX_OK;
+        case SX_INFO_TILE_SLOTS: *value = c->tile_steps * 32; return SX_OK;
+        case SX_INFO_REST_NNZ: *value = c->tile_steps > 0 ? c->rest_nnz : c->nnz; return SX_OK;
         case SX_INFO_HOST_PATH: *value = c->last_path; return SX_OK;
         case SX_INFO_ITEMS: *value = c->last_plan ? c->last_plan->nitems : 0; return SX_OK;
         case SX_INFO_ITEM_NNZ: *value = c->last_plan ? c->last_plan->budget : 0; return SX_OK;

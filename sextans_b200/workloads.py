@@ -110,6 +110,52 @@ def powerlaw_csr(M, K, nnz, seed=12345, dtype=np.float64, exponent=2.0, col_skew
     return rowptr.astype(np.int32), colidx, val
 
 
+def fem_like_csr(nodes, dof, nbrs, seed=12345, dtype=np.float64, band=2000, noise_per_row=0):
+    """Block-structured CSR of the kind finite-element codes produce (what the shipped
+    nasa4704 / pcrystk02 are): `nodes` mesh nodes with `dof` unknowns each; a node is
+    coupled to itself and to ~`nbrs` other nodes within `band` node numbers, and every
+    coupling is a dense dof x dof block.  M = K = nodes*dof, nnz ~ nodes*(1+nbrs)*dof^2.
+    `noise_per_row` extra uniformly random entries per row break the pure block structure.
+    Rows keep ascending, duplicate-free columns."""
+    rng = np.random.default_rng(seed)
+    off = rng.integers(-band, band + 1, size=(nodes, nbrs), dtype=np.int64)
+    nb = np.clip(np.arange(nodes, dtype=np.int64)[:, None] + off, 0, nodes - 1)
+    nb = np.concatenate([nb, np.arange(nodes, dtype=np.int64)[:, None]], axis=1)
+    nb.sort(axis=1)
+    keep = np.ones_like(nb, dtype=bool)
+    keep[:, 1:] = nb[:, 1:] != nb[:, :-1]
+    lens_n = keep.sum(axis=1)                         # couplings per node
+    bcol = nb[keep]                                   # block columns, node-major, ascending
+    bptr = np.zeros(nodes + 1, dtype=np.int64)
+    np.cumsum(lens_n, out=bptr[1:])
+    # element columns of one node's rows: every block column expanded to dof columns
+    pat = (bcol[:, None] * dof + np.arange(dof, dtype=np.int64)[None, :]).ravel()
+    L = lens_n * dof                                  # row length of each of the node's dof rows
+    row_node = np.repeat(np.arange(nodes, dtype=np.int64), dof)
+    row_len = L[row_node]
+    rowptr = np.zeros(nodes * dof + 1, dtype=np.int64)
+    np.cumsum(row_len, out=rowptr[1:])
+    total = int(rowptr[-1])
+    start = (bptr[:-1] * dof)[row_node]               # where the node's pattern starts in `pat`
+    idx = np.repeat(start - rowptr[:-1], row_len) + np.arange(total, dtype=np.int64)
+    colidx = pat[idx].astype(np.int32)
+    del idx, pat
+    M = K = nodes * dof
+    if noise_per_row > 0:
+        extra = rng.integers(0, K, size=(M, noise_per_row), dtype=np.int64)
+        rows = np.concatenate([np.repeat(np.arange(M, dtype=np.int64), row_len),
+                               np.repeat(np.arange(M, dtype=np.int64), noise_per_row)])
+        cols = np.concatenate([colidx.astype(np.int64), extra.ravel()])
+        key = np.unique(rows * K + cols)
+        rows = key // K
+        colidx = (key - rows * K).astype(np.int32)
+        rowptr = np.zeros(M + 1, dtype=np.int64)
+        np.cumsum(np.bincount(rows, minlength=M), out=rowptr[1:])
+    val = rng.random(colidx.size).astype(dtype)
+    val *= 2; val -= 1
+    return rowptr.astype(np.int32), colidx, val
+
+
 def algorithmic_bytes(M, K, nnz, N, itemsize, beta_nonzero=True):
     """CSR A once (32-bit indices), B once, C read once and written once."""
     c_passes = 2 if beta_nonzero else 1

@@ -404,3 +404,78 @@ def test_medium_matrix_sampled_rows_and_linearity(eng):
     y1 = z.copy(); eng.spmm(N, 1.0, B1, 0.0, y1)
     y2 = z.copy(); eng.spmm(N, 1.0, 2 * B1, 0.0, y2)
     assert np.array_equal(y2, 2 * y1)
+
+
+# ---- dense-tile (blocked) variant on the FP64 tensor cores -------------------------------
+def _tiles_case(eng, M, K, N, rp, ci, v, tau, expect_tiles=True, alpha=0.85, beta=-2.06):
+    B, Cin = random_dense(M, K, N, M + N, np.float64)
+    ref = oracle.spmm_csr(M, N, K, rp, ci, v, alpha, B, beta, Cin.copy())
+    eng.set_option(sx.OPT_TILE_MIN_ROWS, tau)
+    try:
+        eng.upload_csr(M, K, rp, ci, v)
+        C = Cin.copy()
+        eng.spmm(N, alpha, B, beta, C, rp_time=2)
+        tile_nnz, slots, rest = eng.info(sx.INFO_TILE_NNZ), eng.info(sx.INFO_TILE_SLOTS), eng.info(sx.INFO_REST_NNZ)
+        assert tile_nnz + rest == ci.size
+        if expect_tiles:
+            assert tile_nnz > 0 and slots >= tile_nnz and eng.info(sx.INFO_LAST_KERNEL) // 10000 in (1, 2, 4)
+        # tolerance-level parity (summation order differs): 1e-12 of the largest entry, and
+        # the BASELINE contract of 1e-6 relative with room to spare
+        assert scaled_err(C, ref) <= 1e-12, scaled_err(C, ref)
+        n_bad, pct, ok = oracle.verify_f32(ref.astype(np.float32), C.astype(np.float32), M, N)
+        assert ok and n_bad == 0
+        return tile_nnz, slots, rest
+    finally:
+        eng.set_option(sx.OPT_TILE_MIN_ROWS, 0)
+
+
+@pytest.mark.parametrize("N", [8, 16, 24, 64, 72, 5])
+def test_tiles_fem_like_matrix(eng, N):
+    from sextans_b200.workloads import fem_like_csr
+    rp, ci, v = fem_like_csr(500, 4, 6, seed=3, band=40, noise_per_row=2)
+    M = K = 2000
+    tile_nnz, slots, rest = _tiles_case(eng, M, K, N, rp, ci, v, tau=4)
+    assert tile_nnz > 0.7 * ci.size and rest > 0          # blocks in tiles, noise in the remainder
+    assert tile_nnz / slots > 0.45
+
+
+@pytest.mark.parametrize("name", SUITESPARSE)
+def test_tiles_on_the_shipped_matrices(eng, name):
+    M, K, nnz, rp, ci, v = sx.load_mtx(mtx_path(name), np.float64)
+    val, _, _ = perturbed_inputs(M, K, 16, nnz, np.float64)
+    tile_nnz, slots, rest = _tiles_case(eng, M, K, 16, rp, ci, val, tau=4)
+    assert tile_nnz > 0.5 * nnz      # both are FEM matrices: most of A sits in dense panel columns
+
+
+def test_tiles_edge_cases(eng):
+    # M not a multiple of 8, empty rows, duplicates, an all-dense panel, tau extremes, no tiles at all
+    rng = np.random.default_rng(8)
+    M, K, N = 27, 40, 16
+    dense = (rng.random((M, K)) < 0.5)
+    dense[8:16] = True                      # a fully dense panel
+    dense[16:19] = False                    # empty rows
+    rows, cols = np.nonzero(dense)
+    rp = np.zeros(M + 1, dtype=np.int32)
+    np.cumsum(np.bincount(rows, minlength=M), out=rp[1:])
+    ci = cols.astype(np.int32)
+    v = rng.uniform(-1, 1, ci.size)
+    for tau in (1, 4, 8):
+        _tiles_case(eng, M, K, N, rp, ci, v, tau)
+    # duplicates of one (row, col): the first goes to the tile, the others stay in the remainder
+    rp2 = np.array([0, 3, 5, 6, 7, 8, 9, 10, 11], dtype=np.int32)
+    ci2 = np.array([2, 2, 2, 2, 5, 2, 2, 2, 2, 2, 2], dtype=np.int32)
+    v2 = rng.uniform(-1, 1, ci2.size)
+    t, s_, r = _tiles_case(eng, 8, 6, 8, rp2, ci2, v2, tau=4)
+    assert t == 8 and r == 3
+    # a matrix without any shared column: nothing goes to tiles, plain CSR path, bit-exact
+    rp3 = np.arange(9, dtype=np.int32)
+    ci3 = np.arange(8, dtype=np.int32)
+    t, s_, r = _tiles_case(eng, 8, 8, 8, rp3, ci3, np.ones(8), tau=2, expect_tiles=False)
+    assert t == 0 and r == 8
+    # fp32 has no exact tensor-core kind: refused loudly
+    eng.set_option(sx.OPT_TILE_MIN_ROWS, 4)
+    try:
+        with pytest.raises(sx.SextansError, match="fp64 only"):
+            eng.upload_csr(8, 8, rp3, ci3, np.ones(8, np.float32))
+    finally:
+        eng.set_option(sx.OPT_TILE_MIN_ROWS, 0)
