@@ -620,7 +620,15 @@ spmm_finalize_kernel(const int nsplit, const int *__restrict__ split_row,
 // fetched once per panel column instead of once per nonzero, i.e. up to 8x fewer bytes
 // through L2, which is what bounds SpMM on this machine.
 // Storage per k-step (4 tile columns): 4 column indices + 32 values in A-fragment order
-// (lane l holds A[l/4][l%4]), so a step is one coalesced 256-byte load.
+// (lane l holds A[l/4][l%4], explicit zeros included), so a step is one coalesced
+// 256-byte load with no index arithmetic.  (A packed variant -- occupancy mask + only the
+// stored values, found by popc -- halves the bytes of A at fill 0.5 but doubles the
+// instructions per step and ran 1.9x SLOWER: the kernel is latency/issue-bound, not
+// DRAM-bound; profiles/r01_pass16_tiles.md.)
+// Output columns are dealt to the 8-wide DMMA n-tiles in even/odd pairs (tile 2p takes
+// columns 16p + {0,2,..,14}, tile 2p+1 the odd ones), so that a lane's two B operands of
+// a pair are adjacent in memory (one 16-byte gather instead of two 8-byte ones) and its
+// four C values are 32 contiguous bytes.
 // Output: C_out = alpha * A_tiles * B + beta * C_in for EVERY row (panels without tile
 // columns just run the epilogue); the remainder is added in place afterwards.
 // Summation order differs from cpu_spmm_CSR (tolerance-level parity, not bit parity),
@@ -630,49 +638,95 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, const double a, 
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-template <int NT, bool STRICT>
+// volatile loads: the compiler must not sink them towards their uses (it did, to save
+// registers, and with that serialised the gathers the unrolling was meant to overlap)
+__device__ __forceinline__ int ldv_s32(const int *p) {
+    int v;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ldv_f64(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 ldv_v2f64(const double *p) {
+    double2 v;
+    asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+// NP = number of 16-column pairs handled by one launch (N <= 16*NP)
+template <int NP, bool STRICT>
 __global__ void __launch_bounds__(256)
 spmm_panels_dmma_kernel(const int npanels, const int M, const int *__restrict__ step_ptr,
                         const int *__restrict__ tcols, const double *__restrict__ tvals,
-                        const double *__restrict__ B, const int64_t ldb, const double *Cin, double *Cout,
+                        const double *__restrict__ B, const uint32_t ldb, const double *Cin, double *Cout,
                         const int64_t ldc, const double alpha, const double beta, const int N) {
-    constexpr int UNR = 4;  // k-steps in flight
+    constexpr int UNR = 4;  // k-steps per batch
     const int lane = threadIdx.x & 31;
     const int panel = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (panel >= npanels) return;  // warp-uniform
     const int kq = lane & 3, rq = lane >> 2;
     const int s0 = __ldg(step_ptr + panel), s1 = __ldg(step_ptr + panel + 1);
-    double acc[NT][2];
+    double acc[2 * NP][2];
 #pragma unroll
-    for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = 0.0;
-    const double *Bq = B + rq;  // this lane's column inside an 8-wide n-tile
-    for (int s = s0; s < s1; s += UNR) {
-        double a[UNR], b[UNR][NT];
+    for (int t = 0; t < 2 * NP; ++t) acc[t][0] = acc[t][1] = 0.0;
+    const double *Bq = B + 2 * rq;  // this lane's even/odd column pair inside a 16-wide pair of tiles
+    const bool colok[4] = {2 * rq < N, 16 + 2 * rq < N, 32 + 2 * rq < N, 48 + 2 * rq < N};
+    // column index and A value of a batch of steps (steps past the panel's end: value 0,
+    // column of the last real step, so that every load stays unconditional)
+    auto load_meta = [&](const int s, int (&col)[UNR], double (&a)[UNR]) {
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-            const bool live = s + u < s1;
-            const int col = live ? __ldg(tcols + (size_t)(s + u) * 4 + kq) : 0;
-            a[u] = live ? __ldg(tvals + (size_t)(s + u) * 32 + lane) : 0.0;
-            const double *brow = Bq + (int64_t)col * ldb;
-#pragma unroll
-            for (int t = 0; t < NT; ++t) b[u][t] = (live && 8 * t + rq < N) ? __ldg(brow + 8 * t) : 0.0;
+            const int su = min(s + u, s1 - 1);
+            col[u] = ldv_s32(tcols + (size_t)su * 4 + kq);
+            a[u] = ldv_f64(tvals + (size_t)su * 32 + lane);
+            if (s + u >= s1) a[u] = 0.0;
         }
+    };
+    if (s0 < s1) {
+        int col[UNR], coln[UNR];
+        double a[UNR], an[UNR];
+        load_meta(s0, col, a);
+        for (int s = s0; s < s1; s += UNR) {
+            double2 b[UNR][NP];
 #pragma unroll
-        for (int u = 0; u < UNR; ++u)
+            for (int u = 0; u < UNR; ++u) {
+                const double *brow = Bq + (size_t)(uint32_t)col[u] * ldb;
 #pragma unroll
-            for (int t = 0; t < NT; ++t) dmma884(acc[t][0], acc[t][1], a[u], b[u][t]);
+                for (int p = 0; p < NP; ++p) b[u][p] = colok[p] ? ldv_v2f64(brow + 16 * p) : make_double2(0.0, 0.0);
+            }
+            if (s + UNR < s1) load_meta(s + UNR, coln, an);  // next batch's indices fly with this batch's gathers
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    dmma884(acc[2 * p][0], acc[2 * p][1], a[u], b[u][p].x);
+                    dmma884(acc[2 * p + 1][0], acc[2 * p + 1][1], a[u], b[u][p].y);
+                }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) { col[u] = coln[u]; a[u] = an[u]; }
+        }
     }
     const int row = panel * 8 + rq;
     if (row < M) {
 #pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            const int n = 8 * t + 2 * kq;
-            if (n + 1 < N) {
-                const double2 cin = *reinterpret_cast<const double2 *>(Cin + (int64_t)row * ldc + n);
-                *reinterpret_cast<double2 *>(Cout + (int64_t)row * ldc + n) =
-                    vaxpby<STRICT>(alpha, make_double2(acc[t][0], acc[t][1]), beta, cin);
-            } else if (n < N) {
-                Cout[(int64_t)row * ldc + n] = axpby<STRICT>(alpha, acc[t][0], beta, Cin[(int64_t)row * ldc + n]);
+        for (int p = 0; p < NP; ++p) {
+            // this lane's four consecutive output columns of pair p
+            const int n = 16 * p + 4 * kq;
+            const double v[4] = {acc[2 * p][0], acc[2 * p + 1][0], acc[2 * p][1], acc[2 * p + 1][1]};
+            const double *ci = Cin + (int64_t)row * ldc + n;
+            double *co = Cout + (int64_t)row * ldc + n;
+            if (n + 3 < N) {
+                const double2 c01 = *reinterpret_cast<const double2 *>(ci);
+                const double2 c23 = *reinterpret_cast<const double2 *>(ci + 2);
+                *reinterpret_cast<double2 *>(co) = vaxpby<STRICT>(alpha, make_double2(v[0], v[1]), beta, c01);
+                *reinterpret_cast<double2 *>(co + 2) = vaxpby<STRICT>(alpha, make_double2(v[2], v[3]), beta, c23);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (n + i < N) co[i] = axpby<STRICT>(alpha, v[i], beta, ci[i]);
             }
         }
     }

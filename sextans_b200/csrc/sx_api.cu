@@ -270,22 +270,21 @@ int spmm_tiles<double>(sx_ctx *c, int N, double alpha, const double *dB, int64_t
     const unsigned grid = (unsigned)(((int64_t)c->npanels * 32 + 255) / 256);
     for (int n0 = 0; n0 < N; n0 += 64) {
         const int n = std::min(64, N - n0);
-        const int nt = (n + 7) / 8;
-#define SX_PANELS(NT)                                                                              \
+        const int np = (n + 15) / 16;
+#define SX_PANELS(NP)                                                                              \
     do {                                                                                           \
         if (c->arith == 0)                                                                         \
-            sx::spmm_panels_dmma_kernel<NT, true><<<grid, 256, 0, c->stream>>>(                    \
+            sx::spmm_panels_dmma_kernel<NP, true><<<grid, 256, 0, c->stream>>>(                    \
                 c->npanels, c->M, (const int *)c->step_ptr.p, (const int *)c->tcols.p,             \
-                (const double *)c->tvals.p, dB + n0, ldb, dCin + n0, dCout + n0, ldc, alpha, beta, n); \
+                (const double *)c->tvals.p, dB + n0, (uint32_t)ldb, dCin + n0, dCout + n0, ldc, alpha, beta, n); \
         else                                                                                       \
-            sx::spmm_panels_dmma_kernel<NT, false><<<grid, 256, 0, c->stream>>>(                   \
+            sx::spmm_panels_dmma_kernel<NP, false><<<grid, 256, 0, c->stream>>>(                   \
                 c->npanels, c->M, (const int *)c->step_ptr.p, (const int *)c->tcols.p,             \
-                (const double *)c->tvals.p, dB + n0, ldb, dCin + n0, dCout + n0, ldc, alpha, beta, n); \
+                (const double *)c->tvals.p, dB + n0, (uint32_t)ldb, dCin + n0, dCout + n0, ldc, alpha, beta, n); \
     } while (0)
-        if (nt <= 1) SX_PANELS(1);
-        else if (nt <= 2) SX_PANELS(2);
-        else if (nt <= 4) SX_PANELS(4);
-        else SX_PANELS(8);
+        if (np <= 1) SX_PANELS(1);
+        else if (np <= 2) SX_PANELS(2);
+        else SX_PANELS(4);
 #undef SX_PANELS
         c->launches++;
     }
@@ -499,7 +498,6 @@ int build_panels(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rowptr, co
             return a.col != b.col ? a.col < b.col : (a.r != b.r ? a.r < b.r : a.j < b.j);
         });
         dcols.clear();
-        const size_t first_val = tvals.size();
         // pass 1: which columns are dense enough
         for (size_t i = 0; i < ents.size();) {
             size_t e = i;
@@ -516,6 +514,7 @@ int build_panels(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rowptr, co
         if (w > 0) {
             tcols.resize(tcols.size() + (size_t)nsteps * 4, dcols.back());  // pad slots reuse a real column
             std::copy(dcols.begin(), dcols.end(), tcols.end() - (size_t)nsteps * 4);
+            const size_t first_val = tvals.size();
             tvals.resize(first_val + (size_t)nsteps * 32, 0.0);
             // pass 2: first entry of every (row, dense column) goes into the tile
             size_t di = 0;
@@ -528,8 +527,7 @@ int build_panels(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rowptr, co
                     for (size_t q = i; q < e; ++q) {
                         if (ents[q].r == last_r) continue;  // duplicate (row, col): stays in the remainder
                         last_r = ents[q].r;
-                        const size_t step = di / 4, kk = di % 4;
-                        tvals[first_val + step * 32 + (size_t)ents[q].r * 4 + kk] = val[ents[q].j];
+                        tvals[first_val + (di / 4) * 32 + (size_t)ents[q].r * 4 + di % 4] = val[ents[q].j];
                         used[ents[q].j] = 1;
                         ++tile_nnz;
                     }

@@ -444,7 +444,7 @@ def test_tiles_on_the_shipped_matrices(eng, name):
     M, K, nnz, rp, ci, v = sx.load_mtx(mtx_path(name), np.float64)
     val, _, _ = perturbed_inputs(M, K, 16, nnz, np.float64)
     tile_nnz, slots, rest = _tiles_case(eng, M, K, 16, rp, ci, val, tau=4)
-    assert tile_nnz > 0.5 * nnz      # both are FEM matrices: most of A sits in dense panel columns
+    assert tile_nnz > (0.3 if name == "nasa4704" else 0.75) * nnz      # FEM matrices: a third / four fifths of A sits in dense panel columns
 
 
 def test_tiles_edge_cases(eng):
