@@ -65,6 +65,7 @@ def parse():
     p.add_argument("--split", type=int, default=-1, help="SX_OPT_SPLIT_ROW_NNZ (-1 default)")
     p.add_argument("--tiles", type=int, default=0, help="SX_OPT_TILE_MIN_ROWS (fp64 dense-tile tensor-core variant; 0 off)")
     p.add_argument("--ref-threads", type=int, default=1, help="--impl reference: threads of the CPU path (1 = as the reference runs it; -1 = all cores, OpenMP port)")
+    p.add_argument("--peer-bytes", type=int, default=8 << 20, help="N>1: B images up to this size travel by peer copy instead of NCCL")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-flush", action="store_true", help="leave L2 warm between steps")
     p.add_argument("--no-graph", action="store_true", help="launch the timed steps one by one instead of replaying a CUDA graph")
@@ -281,7 +282,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_native(args):
@@ -341,9 +342,46 @@ def run_native(args):
     eng = engines[0]
     stream.synchronize()
 
+    # N > 1: how B reaches the other ranks.  Small B: every rank pulls the root's image with a
+    # peer copy over NVLink ordered by device-side step counters (PeerBroadcast); large B
+    # (or if CUDA IPC is not available): one NCCL broadcast.
+    peer = None
+    exchange = "none"
+    if world > 1:
+        exchange = "one NCCL broadcast of B from rank 0 inside every step"
+        if K * ld * s <= args.peer_bytes:
+            try:
+                from sextans_b200.rowblock import PeerBroadcast
+                for j in range(R):                      # the engines' own B images are the operands here
+                    ptr, _ = engines[j].device_B(N)          # zero-filled; only the root holds B
+                    if rank == 0:
+                        engines[j].colmajor_to_rowmajor(K, N, dB_cm, ptr, ld)
+                    dBs[j] = ptr
+                stream.synchronize()
+                peer = PeerBroadcast(engines, N)
+                exchange = "peer copy of B from rank 0 over NVLink (copy engine) ordered by device-side step counters, inside every step"
+            except Exception as ex:                     # no IPC in this sandbox: keep NCCL
+                peer = None
+                exchange += f" (peer path unavailable: {type(ex).__name__})"
+    step_no = [0]
+    copy_stream = torch.cuda.Stream(device=dev) if peer is not None else None
+
     def step_device(i):
         j = i % R
-        if world > 1:
+        if peer is not None:
+            # the pull of step k runs on its own stream, so it overlaps the SpMM of step k-1
+            step_no[0] += 1
+            assert (step_no[0] - 1) % R == j
+            if rank == 0:
+                peer.publish(step_no[0])
+            else:
+                engines[j].set_stream(copy_stream.cuda_stream)
+                peer.pull(step_no[0])
+                engines[j].set_stream(stream.cuda_stream)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                stream.wait_event(ev)
+        elif world > 1:
             dist.broadcast(dBs[j], src=0)
         engines[j].spmm_device(N, ALPHA, dBs[j], ld, BETA, dCins[j], dCouts[j], ld)
 
@@ -371,15 +409,26 @@ def run_native(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = launches()
     graph = None
-    use_graph = not args.no_graph and world == 1   # NCCL collectives are launched eagerly
+    use_graph = not args.no_graph and (world == 1 or peer is not None)   # NCCL collectives are launched eagerly
     if use_graph:
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=stream):
-            for i in range(args.steps):
-                step_device(nwarm + i)
-        launches_dev = launches() - l0       # kernels recorded into the graph = launched per replay
+        def capture():
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                if copy_stream is not None:
+                    copy_stream.wait_stream(stream)          # fork
+                for i in range(args.steps):
+                    step_device(next_i[0])
+                    next_i[0] += 1
+                if copy_stream is not None:
+                    stream.wait_stream(copy_stream)          # join
+            return g
+        next_i = [nwarm]
+        warm_graph = capture()
+        launches_dev = launches() - l0       # kernels recorded into one graph = launched per replay
+        # step counters only move forward: the timed replay is a second graph over the NEXT K steps
+        graph = capture() if peer is not None else warm_graph
         with torch.cuda.stream(stream):
-            graph.replay()                   # one untimed replay
+            warm_graph.replay()              # one untimed replay
     barrier()
     with torch.cuda.stream(stream):
         e0.record(stream)
@@ -473,7 +522,7 @@ def run_native(args):
             "config": {"workload": w["desc"], "alpha": ALPHA, "beta": BETA, "arith": args.arith,
                        "l2": "warm (--no-flush)" if args.no_flush else (f"inputs larger than L2: {R} independent device copies of A/B/C ({R * alg_bytes / 1e6:.0f} MB > 2 x 126 MB L2), step i uses copy i mod {R}; no flush kernel in the timed region" if R > 1 else f"inputs larger than L2: one copy is {alg_bytes / 1e6:.0f} MB; steps run back to back"),
                        "launch": f"the {args.steps} steps are one CUDA graph replay" if use_graph else "one by one",
-                       "partition": "1 row block" if world == 1 else f"{world} stacked row blocks, one per GPU; NCCL broadcast of B from rank 0 inside every step"},
+                       "partition": "1 row block" if world == 1 else f"{world} stacked row blocks, one per GPU; {exchange}"},
             "gflops_ref_formula": 2.0 * (nnz + M) * N * world * args.steps / (total_ms * 1e-3) / 1e9,
             "single_copy_back_to_back": {"ms_per_step": warm_ms, "value": flops_step / (warm_ms * 1e-3) / 1e9,
                                          "gbs": alg_bytes / (warm_ms * 1e-3) / 1e9, "note": "L2-warm when one copy fits in L2"},
@@ -491,14 +540,23 @@ def run_native(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(w, 1)
-        print(json.dumps(line))
+        emit(line)
     for e in engines:
         e.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else any library writes to
+    file descriptor 1 (NCCL prints its version banner there) has been sent to stderr."""
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 if __name__ == "__main__":
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         run_reference(a)

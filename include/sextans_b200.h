@@ -180,6 +180,28 @@ int sx_colmajor_to_rowmajor(sx_ctx *ctx, int dtype, int64_t rows, int cols, cons
 int sx_rowmajor_to_colmajor(sx_ctx *ctx, int dtype, int64_t rows, int cols, const void *d_src,
                             int64_t ld_src, void *d_dst);
 
+/* ---- peer memory: B from another GPU's context over NVLink, no collective ---- */
+/* One process per GPU.  For a small B the launch latency of a collective dwarfs the
+ * transfer (600 KB: ~60 us through NCCL against ~10 us of SpMM), so the row-block path
+ * can instead let every rank PULL the root's B image with a copy-engine peer copy,
+ * ordered by 32-bit flags in peer-mapped device memory (stream memory operations: no
+ * kernel, no host round trip).  Handles are CUDA IPC handles (64 bytes) to be exchanged
+ * by whatever transport the host program has (torch.distributed object gather in
+ * sextans_b200/rowblock.py). */
+#define SX_IPC_HANDLE_BYTES 64
+int sx_device_alloc(sx_ctx *ctx, size_t bytes, void **dptr);  /* zero-filled */
+int sx_device_free(sx_ctx *ctx, void *dptr);
+int sx_ipc_export(sx_ctx *ctx, const void *dptr, unsigned char handle[SX_IPC_HANDLE_BYTES]);
+int sx_ipc_import(sx_ctx *ctx, const unsigned char handle[SX_IPC_HANDLE_BYTES], void **dptr);
+int sx_ipc_close(sx_ctx *ctx, void *dptr);
+/* enqueue on the context's stream: *flag = value once everything before it has finished */
+int sx_flag_write(sx_ctx *ctx, void *flag_dptr, uint32_t value);
+/* enqueue on the context's stream: work after it starts when (int32)(*flag - value) >= 0 */
+int sx_flag_wait(sx_ctx *ctx, void *flag_dptr, uint32_t value);
+/* enqueue a copy of a peer's row-major B image (same K, same N, same dtype: the bytes
+ * sx_device_B reports) into this context's image; marks B as staged. */
+int sx_pull_B(sx_ctx *ctx, int N, const void *peer_B_image);
+
 /* ---- host-side helpers of the drop-in surface ----------------------------- */
 /* Page-locked host memory for B and C (stands in for tapa::aligned_allocator). */
 int sx_host_alloc(size_t bytes, void **ptr);

@@ -79,6 +79,14 @@ def lib():
         "sx_spmm_device_f64": ([vp, i, C.c_double, vp, i64, C.c_double, vp, vp, i64], i),
         "sx_colmajor_to_rowmajor": ([vp, i, i64, i, vp, vp, i64], i),
         "sx_rowmajor_to_colmajor": ([vp, i, i64, i, vp, i64, vp], i),
+        "sx_device_alloc": ([vp, sz, C.POINTER(vp)], i),
+        "sx_device_free": ([vp, vp], i),
+        "sx_ipc_export": ([vp, vp, C.c_char_p], i),
+        "sx_ipc_import": ([vp, C.c_char_p, C.POINTER(vp)], i),
+        "sx_ipc_close": ([vp, vp], i),
+        "sx_flag_write": ([vp, vp, C.c_uint32], i),
+        "sx_flag_wait": ([vp, vp, C.c_uint32], i),
+        "sx_pull_B": ([vp, i, vp], i),
         "sx_host_alloc": ([sz, C.POINTER(vp)], i),
         "sx_host_free": ([vp], i),
         "sx_partition_rows": ([i, _PI32, i, _PI32], i),
@@ -297,6 +305,37 @@ class Engine:
         p, n = C.c_void_p(), C.c_size_t()
         _check(self._L.sx_device_B(self._ctx, N, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    # -- peer memory -----------------------------------------------------------------------
+    def device_alloc(self, nbytes) -> int:
+        p = C.c_void_p()
+        _check(self._L.sx_device_alloc(self._ctx, nbytes, C.byref(p)))
+        return p.value
+
+    def device_free(self, ptr):
+        _check(self._L.sx_device_free(self._ctx, C.c_void_p(ptr)))
+
+    def ipc_export(self, ptr) -> bytes:
+        buf = C.create_string_buffer(64)
+        _check(self._L.sx_ipc_export(self._ctx, C.c_void_p(ptr), buf))
+        return buf.raw
+
+    def ipc_import(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        _check(self._L.sx_ipc_import(self._ctx, C.create_string_buffer(handle, 64), C.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr):
+        _check(self._L.sx_ipc_close(self._ctx, C.c_void_p(ptr)))
+
+    def flag_write(self, flag_ptr, value):
+        _check(self._L.sx_flag_write(self._ctx, C.c_void_p(flag_ptr), value & 0xFFFFFFFF))
+
+    def flag_wait(self, flag_ptr, value):
+        _check(self._L.sx_flag_wait(self._ctx, C.c_void_p(flag_ptr), value & 0xFFFFFFFF))
+
+    def pull_B(self, N, peer_image_ptr):
+        _check(self._L.sx_pull_B(self._ctx, N, C.c_void_p(peer_image_ptr)))
 
     # -- device-resident -----------------------------------------------------------------
     def spmm_device(self, N, alpha, dB, ldb, beta, dCin, dCout, ldc):

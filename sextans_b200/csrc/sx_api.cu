@@ -7,6 +7,7 @@
 // times, copy the result back, return the kernel time.
 #include "../../include/sextans_b200.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -1028,6 +1029,91 @@ int sx_rowmajor_to_colmajor(sx_ctx *c, int dtype, int64_t rows, int cols, const 
     if ((dtype != SX_F32 && dtype != SX_F64) || rows < 0 || cols < 1 || ld_src < cols || !d_src || !d_dst)
         return fail(SX_ERR_INVALID, "bad layout-change arguments");
     return transpose_out(c, dtype, rows, cols, d_src, ld_src, d_dst);
+}
+
+int sx_device_alloc(sx_ctx *c, size_t bytes, void **dptr) {
+    int rc = bind(c);
+    if (rc) return rc;
+    if (!dptr) return fail(SX_ERR_INVALID, "null dptr");
+    *dptr = nullptr;
+    SX_CUDA(cudaMalloc(dptr, bytes ? bytes : 4));
+    SX_CUDA(cudaMemsetAsync(*dptr, 0, bytes ? bytes : 4, c->stream));
+    SX_CUDA(cudaStreamSynchronize(c->stream));
+    return SX_OK;
+}
+
+int sx_device_free(sx_ctx *c, void *dptr) {
+    int rc = bind(c);
+    if (rc) return rc;
+    if (dptr) SX_CUDA(cudaFree(dptr));
+    return SX_OK;
+}
+
+int sx_ipc_export(sx_ctx *c, const void *dptr, unsigned char handle[SX_IPC_HANDLE_BYTES]) {
+    int rc = bind(c);
+    if (rc) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == SX_IPC_HANDLE_BYTES, "IPC handle size");
+    if (!dptr || !handle) return fail(SX_ERR_INVALID, "null argument");
+    cudaIpcMemHandle_t h;
+    SX_CUDA(cudaIpcGetMemHandle(&h, const_cast<void *>(dptr)));
+    std::memcpy(handle, &h, sizeof h);
+    return SX_OK;
+}
+
+int sx_ipc_import(sx_ctx *c, const unsigned char handle[SX_IPC_HANDLE_BYTES], void **dptr) {
+    int rc = bind(c);
+    if (rc) return rc;
+    if (!dptr || !handle) return fail(SX_ERR_INVALID, "null argument");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    SX_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SX_OK;
+}
+
+int sx_ipc_close(sx_ctx *c, void *dptr) {
+    int rc = bind(c);
+    if (rc) return rc;
+    if (dptr) SX_CUDA(cudaIpcCloseMemHandle(dptr));
+    return SX_OK;
+}
+
+namespace {
+// the two stream memory operations come from the driver; resolved through the runtime so
+// that the library does not link libcuda (it must still load on a machine without a GPU)
+typedef CUresult (*StreamValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+int stream_value32(const char *name, sx_ctx *c, void *flag, uint32_t value, unsigned flags) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    SX_CUDA(cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) return fail(SX_ERR_CUDA, "%s is not available in this driver", name);
+    const CUresult r = ((StreamValue32Fn)fn)((CUstream)c->stream, (CUdeviceptr)(uintptr_t)flag, value, flags);
+    if (r != CUDA_SUCCESS) return fail(SX_ERR_CUDA, "%s failed with CUresult %d", name, (int)r);
+    return SX_OK;
+}
+}  // namespace
+
+int sx_flag_write(sx_ctx *c, void *flag, uint32_t value) {
+    int rc = bind(c);
+    if (rc) return rc;
+    if (!flag) return fail(SX_ERR_INVALID, "null flag");
+    return stream_value32("cuStreamWriteValue32", c, flag, value, CU_STREAM_WRITE_VALUE_DEFAULT);
+}
+
+int sx_flag_wait(sx_ctx *c, void *flag, uint32_t value) {
+    int rc = bind(c);
+    if (rc) return rc;
+    if (!flag) return fail(SX_ERR_INVALID, "null flag");
+    return stream_value32("cuStreamWaitValue32", c, flag, value, CU_STREAM_WAIT_VALUE_GEQ);
+}
+
+int sx_pull_B(sx_ctx *c, int N, const void *peer_B_image) {
+    void *mine = nullptr;
+    size_t bytes = 0;
+    int rc = sx_device_B(c, N, &mine, &bytes);
+    if (rc) return rc;
+    if (!peer_B_image) return fail(SX_ERR_INVALID, "null peer image");
+    if (bytes) SX_CUDA(cudaMemcpyAsync(mine, peer_B_image, bytes, cudaMemcpyDefault, c->stream));
+    return SX_OK;
 }
 
 int sx_host_alloc(size_t bytes, void **ptr) {

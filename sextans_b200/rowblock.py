@@ -47,6 +47,75 @@ class RowBlock:
         return C_colmajor
 
 
+class PeerBroadcast:
+    """B from the root rank's engine(s) to every other rank WITHOUT a collective: each
+    rank pulls the root's row-major B image with a copy-engine peer copy over NVLink, and
+    the ordering is carried by 32-bit step counters in peer-mapped device memory, written
+    and waited on by stream memory operations (sx_flag_write / sx_flag_wait) -- no kernel,
+    no host round trip.  For the SuiteSparse-sized configs this replaces ~60 us of NCCL
+    launch latency per broadcast by a ~10 us peer copy.
+
+    ``engines``: this rank's Engine objects (one, or several replicas used round-robin),
+    each with A uploaded.  Step numbers start at 1 and must increase by one per call.
+      root : publish(k)      after B of replica (k-1) % R is staged
+             reclaim(k)      before that replica's B is overwritten again (waits until every
+                             peer has finished pulling step k)
+      peers: pull(k)         waits for publish(k), copies, acknowledges
+    """
+
+    def __init__(self, engines, N, group=None, root=0):
+        import torch.distributed as dist
+        self.engines, self.N, self.root = list(engines), N, root
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.R = len(self.engines)
+        e0 = self.engines[0]
+        self._imported = []
+        if self.rank == root:
+            self.done = e0.device_alloc(4 * self.world)                 # done[r]: last step rank r pulled
+            mine = {"images": [e0_.ipc_export(e0_.device_B(N)[0]) for e0_ in self.engines],
+                    "done": e0.ipc_export(self.done)}
+        else:
+            self.ready = e0.device_alloc(4)                              # last step the root published
+            mine = {"ready": e0.ipc_export(self.ready)}
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)
+        if self.rank == root:
+            self.peer_ready = {}
+            for r, obj in enumerate(everyone):
+                if r != root:
+                    self.peer_ready[r] = e0.ipc_import(obj["ready"])
+                    self._imported.append(self.peer_ready[r])
+        else:
+            self.root_images = [e0.ipc_import(h) for h in everyone[root]["images"]]
+            self.root_done = e0.ipc_import(everyone[root]["done"])
+            self._imported += self.root_images + [self.root_done]
+        dist.barrier(group=group)
+
+    def publish(self, k):
+        e = self.engines[(k - 1) % self.R]
+        for ptr in self.peer_ready.values():
+            e.flag_write(ptr, k)
+
+    def reclaim(self, k):
+        e = self.engines[(k - 1) % self.R]
+        for r in self.peer_ready:
+            e.flag_wait(self.done + 4 * r, k)
+
+    def pull(self, k):
+        j = (k - 1) % self.R
+        e = self.engines[j]
+        e.flag_wait(self.ready, k)
+        e.pull_B(self.N, self.root_images[j])
+        e.flag_write(self.root_done + 4 * self.rank, k)
+
+    def close(self):
+        e0 = self.engines[0]
+        e0.synchronize()
+        for ptr in self._imported:
+            e0.ipc_close(ptr)
+        self._imported = []
+
+
 class ShardedSpMM:
     """One process per GPU.  ``spmm`` broadcasts B (device to device, NCCL) and runs the
     local row block; C stays sharded unless ``gather`` is asked for."""

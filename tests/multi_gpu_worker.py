@@ -39,6 +39,39 @@ def main():
             assert full.tobytes() == ref.tobytes(), name
             print(f"OK {name}: {world} row blocks == oracle bitwise; rank-0 kernel {ns / 2e3:.1f} us", flush=True)
         sh.close()
+    # the same exchange without a collective: peers pull the root's B over NVLink, ordered by
+    # device-side step counters (PeerBroadcast); several steps with a B that changes each time
+    from sextans_b200.rowblock import PeerBroadcast, RowBlock
+    M, K, N = 4000, 3000, 16
+    rp, ci, v = random_csr(M, K, 10, 5, np.float64)
+    blk = RowBlock(M, K, rp, ci, v, world, rank)
+    eng = sx.Engine(local)
+    eng.upload_csr(blk.rows, K, blk.rowptr, blk.colidx, blk.val)
+    eng.device_B(N)
+    pb = PeerBroadcast([eng], N)
+    for k in range(1, 6):
+        B, Cin = random_dense(M, K, N, 100 + k, np.float64)          # every rank can rebuild the root's B to check
+        Cb = blk.take_C(Cin, N)
+        if rank == 0:
+            if k > 1:
+                pb.reclaim(k - 1)                                      # peers are done with the previous B
+            eng.stage_B(N, B)
+            pb.publish(k)
+        else:
+            pb.pull(k)
+        eng.stage_C(N, Cb)
+        eng.launch(0.85, -2.06)
+        eng.fetch_C(Cb)
+        ref = oracle.spmm_csr(blk.rows, N, K, blk.rowptr, blk.colidx, blk.val, 0.85, B, -2.06, blk.take_C(Cin, N))
+        assert Cb.tobytes() == ref.tobytes(), (rank, k)
+    if rank == 0:
+        pb.reclaim(5)
+    eng.synchronize()
+    dist.barrier()
+    pb.close()
+    if rank == 0:
+        print("OK peer pull of B over NVLink: 5 steps bitwise on every rank", flush=True)
+    eng.close()
     dist.barrier()
     dist.destroy_process_group()
 
