@@ -117,17 +117,19 @@ class PeerBroadcast:
 
 
 class ShardedSpMM:
-    """One process per GPU.  ``spmm`` broadcasts B (device to device, NCCL) and runs the
-    local row block; C stays sharded unless ``gather`` is asked for."""
+    """One process per GPU.  ``spmm`` moves B from the rank that has it to the others --
+    by peer copy (PeerBroadcast) when the B image is at most ``peer_bytes``, by one NCCL
+    broadcast otherwise -- and runs the local row block; C stays sharded unless ``gather``
+    is asked for."""
 
-    def __init__(self, M, K, rowptr, colidx, val, device, group=None, arith=0):
+    def __init__(self, M, K, rowptr, colidx, val, device, group=None, arith=0, peer_bytes=8 << 20):
+        import torch
         import torch.distributed as dist
         self.dist = dist
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.block = RowBlock(M, K, rowptr, colidx, val, self.world, self.rank)
-        import torch
         self.engine = Engine(device, arith=arith)
         # one stream for the engine's kernels AND the collective, so that they are ordered
         self.stream = torch.cuda.Stream(device=device)
@@ -135,8 +137,16 @@ class ShardedSpMM:
         self.engine.upload_csr(self.block.rows, K, self.block.rowptr, self.block.colidx, self.block.val)
         self.dtype = self.block.val.dtype
         self.device = device
+        self.peer_bytes = peer_bytes
+        self._peer = None        # (N, src, PeerBroadcast) once set up
+        self._peer_failed = False
+        self._step = 0
+        self.last_exchange = None
 
     def close(self):
+        if self._peer is not None:
+            self._peer[2].close()
+            self._peer = None
         self.engine.close()
 
     def device_B(self, N):
@@ -144,23 +154,54 @@ class ShardedSpMM:
         import torch
         ptr, nbytes = self.engine.device_B(N)
         ld = self.engine.info(7)
-        tdtype = torch.float64 if self.dtype == np.float64 else torch.float32
         n = nbytes // self.dtype.itemsize
 
         class _Arr:
             __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8" if self.dtype == np.float64 else "<f4",
                                         "data": (ptr, False), "version": 3}
-        return torch.as_tensor(_Arr(), device=f"cuda:{self.device}").view(self.block.K, ld), tdtype
+        return torch.as_tensor(_Arr(), device=f"cuda:{self.device}").view(self.block.K, ld)
+
+    def _peer_for(self, N, src):
+        if self._peer is not None and self._peer[:2] == (N, src):
+            return self._peer[2]
+        if self._peer is not None or self._peer_failed or self.world == 1:
+            return None              # a different N / root than the one the handles were made for
+        _, nbytes = self.engine.device_B(N)
+        ok = nbytes <= self.peer_bytes
+        flags = [None] * self.world
+        self.dist.all_gather_object(flags, bool(ok), group=self.group)
+        if not all(flags):
+            self._peer_failed = True
+            return None
+        try:
+            self._peer = (N, src, PeerBroadcast([self.engine], N, self.group, root=src))
+        except Exception:
+            self._peer_failed = True
+            return None
+        return self._peer[2]
 
     def spmm(self, N, alpha, B_colmajor_root, beta, C_block_colmajor, src=0, rp_time=1):
         """B_colmajor_root: the K x N column-major host B on rank ``src`` (ignored elsewhere).
         C_block_colmajor: this rank's block (in/out).  Returns the local kernel ns."""
-        if self.rank == src:
-            self.engine.stage_B(N, B_colmajor_root)        # H2D + layout change on the root only
         import torch
-        dB, _ = self.device_B(N)
-        with torch.cuda.stream(self.stream):
-            self.dist.broadcast(dB, src=src, group=self.group)  # NCCL over NVLink / NVSwitch
+        pb = self._peer_for(N, src)
+        if pb is not None:
+            self._step += 1
+            if self.rank == src:
+                if self._step > 1:
+                    pb.reclaim(self._step - 1)             # every peer has finished with the previous B
+                self.engine.stage_B(N, B_colmajor_root)    # H2D + layout change on the root only
+                pb.publish(self._step)
+            else:
+                pb.pull(self._step)
+            self.last_exchange = "peer"
+        else:
+            if self.rank == src:
+                self.engine.stage_B(N, B_colmajor_root)
+            dB = self.device_B(N)
+            with torch.cuda.stream(self.stream):
+                self.dist.broadcast(dB, src=src, group=self.group)  # NCCL over NVLink / NVSwitch
+            self.last_exchange = "nccl"
         self.engine.stage_C(N, C_block_colmajor)
         ns = self.engine.launch(alpha, beta, rp_time)
         self.engine.fetch_C(C_block_colmajor)

@@ -29,16 +29,20 @@ def main():
     cases.append(("random f64 N=32 with a long row", M, K, N, rp, ci, v, B, Cin))
     for name, M, K, N, rp, ci, v, B, Cin in cases:
         dtype = v.dtype.type
-        sh = ShardedSpMM(M, K, rp, ci, v, local)
-        sh.engine.set_option(sx.OPT_SPLIT_ROW_NNZ, 0)          # everything in stored order: bitwise
-        Cb = sh.block.take_C(Cin, N)
-        ns = sh.spmm(N, dtype(0.85), B if rank == 0 else None, dtype(-2.06), Cb, src=0, rp_time=2)
-        full = sh.gather(Cb, N, dst=0)
-        if rank == 0:
-            ref = oracle.spmm_csr(M, N, K, rp, ci, v, dtype(0.85), B, dtype(-2.06), Cin.copy())
-            assert full.tobytes() == ref.tobytes(), name
-            print(f"OK {name}: {world} row blocks == oracle bitwise; rank-0 kernel {ns / 2e3:.1f} us", flush=True)
-        sh.close()
+        for peer_bytes, want in ((8 << 20, "peer"), (0, "nccl")):      # both ways of moving B
+            sh = ShardedSpMM(M, K, rp, ci, v, local, peer_bytes=peer_bytes)
+            sh.engine.set_option(sx.OPT_SPLIT_ROW_NNZ, 0)          # everything in stored order: bitwise
+            for rep in range(2):                                       # twice: B is re-staged and re-sent
+                Cb = sh.block.take_C(Cin, N)
+                ns = sh.spmm(N, dtype(0.85), B if rank == 0 else None, dtype(-2.06), Cb, src=0, rp_time=2)
+                assert sh.last_exchange == want, (sh.last_exchange, want)
+                full = sh.gather(Cb, N, dst=0)
+                if rank == 0:
+                    ref = oracle.spmm_csr(M, N, K, rp, ci, v, dtype(0.85), B, dtype(-2.06), Cin.copy())
+                    assert full.tobytes() == ref.tobytes(), (name, want)
+            if rank == 0:
+                print(f"OK {name} via {want}: {world} row blocks == oracle bitwise; rank-0 kernel {ns / 2e3:.1f} us", flush=True)
+            sh.close()
     # the same exchange without a collective: peers pull the root's B over NVLink, ordered by
     # device-side step counters (PeerBroadcast); several steps with a B that changes each time
     from sextans_b200.rowblock import PeerBroadcast, RowBlock
