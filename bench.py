@@ -66,6 +66,7 @@ def parse():
     p.add_argument("--tiles", type=int, default=0, help="SX_OPT_TILE_MIN_ROWS (fp64 dense-tile tensor-core variant; 0 off)")
     p.add_argument("--ref-threads", type=int, default=1, help="--impl reference: threads of the CPU path (1 = as the reference runs it; -1 = all cores, OpenMP port)")
     p.add_argument("--peer-bytes", type=int, default=8 << 20, help="N>1: B images up to this size travel by peer copy instead of NCCL")
+    p.add_argument("--peer-mode", default="fused", choices=["fused", "memops"])
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-flush", action="store_true", help="leave L2 warm between steps")
     p.add_argument("--no-graph", action="store_true", help="launch the timed steps one by one instead of replaying a CUDA graph")
@@ -358,8 +359,8 @@ def run_native(args):
                         engines[j].colmajor_to_rowmajor(K, N, dB_cm, ptr, ld)
                     dBs[j] = ptr
                 stream.synchronize()
-                peer = PeerBroadcast(engines, N)
-                exchange = "peer copy of B from rank 0 over NVLink (copy engine) ordered by device-side step counters, inside every step"
+                peer = PeerBroadcast(engines, N, fused=(args.peer_mode == "fused"))
+                exchange = ("B pulled from rank 0 over NVLink by one fused kernel per step (spin on the step flag, copy, acknowledge)" if args.peer_mode == "fused" else "peer copy of B from rank 0 over NVLink (copy engine) ordered by stream memory operations") + ", inside every step"
             except Exception as ex:                     # no IPC in this sandbox: keep NCCL
                 peer = None
                 exchange += f" (peer path unavailable: {type(ex).__name__})"
@@ -373,7 +374,11 @@ def run_native(args):
             step_no[0] += 1
             assert (step_no[0] - 1) % R == j
             if rank == 0:
+                # B is resident and constant here, so publishing step k does not depend on the
+                # SpMM stream: it runs beside it (in a pipeline it would follow B's producer)
+                engines[j].set_stream(copy_stream.cuda_stream)
                 peer.publish(step_no[0])
+                engines[j].set_stream(stream.cuda_stream)
             else:
                 engines[j].set_stream(copy_stream.cuda_stream)
                 peer.pull(step_no[0])

@@ -196,11 +196,20 @@ int sx_ipc_import(sx_ctx *ctx, const unsigned char handle[SX_IPC_HANDLE_BYTES], 
 int sx_ipc_close(sx_ctx *ctx, void *dptr);
 /* enqueue on the context's stream: *flag = value once everything before it has finished */
 int sx_flag_write(sx_ctx *ctx, void *flag_dptr, uint32_t value);
+/* the same for up to 16 flags with ONE small kernel (the root publishing a step to all
+ * its peers: a chain of stream memory operations costs ~3 us each) */
+int sx_flag_write_many(sx_ctx *ctx, void *const *flag_dptrs, int n, uint32_t value);
 /* enqueue on the context's stream: work after it starts when (int32)(*flag - value) >= 0 */
 int sx_flag_wait(sx_ctx *ctx, void *flag_dptr, uint32_t value);
 /* enqueue a copy of a peer's row-major B image (same K, same N, same dtype: the bytes
  * sx_device_B reports) into this context's image; marks B as staged. */
 int sx_pull_B(sx_ctx *ctx, int N, const void *peer_B_image);
+/* the three steps of a pull in ONE kernel: spin until (int32)(*ready_flag - step) >= 0
+ * (ready_flag in this GPU's memory), copy the peer's image over NVLink, then store step
+ * into done_flag (the root's, peer-mapped).  ~5 us for 600 KB against ~13 us for
+ * sx_flag_wait + sx_pull_B + sx_flag_write. */
+int sx_pull_B_fused(sx_ctx *ctx, int N, const void *peer_B_image, const void *ready_flag,
+                    void *done_flag, uint32_t step);
 
 /* ---- host-side helpers of the drop-in surface ----------------------------- */
 /* Page-locked host memory for B and C (stands in for tapa::aligned_allocator). */

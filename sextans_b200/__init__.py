@@ -85,8 +85,10 @@ def lib():
         "sx_ipc_import": ([vp, C.c_char_p, C.POINTER(vp)], i),
         "sx_ipc_close": ([vp, vp], i),
         "sx_flag_write": ([vp, vp, C.c_uint32], i),
+        "sx_flag_write_many": ([vp, C.POINTER(vp), i, C.c_uint32], i),
         "sx_flag_wait": ([vp, vp, C.c_uint32], i),
         "sx_pull_B": ([vp, i, vp], i),
+        "sx_pull_B_fused": ([vp, i, vp, vp, vp, C.c_uint32], i),
         "sx_host_alloc": ([sz, C.POINTER(vp)], i),
         "sx_host_free": ([vp], i),
         "sx_partition_rows": ([i, _PI32, i, _PI32], i),
@@ -331,8 +333,16 @@ class Engine:
     def flag_write(self, flag_ptr, value):
         _check(self._L.sx_flag_write(self._ctx, C.c_void_p(flag_ptr), value & 0xFFFFFFFF))
 
+    def flag_write_many(self, flag_ptrs, value):
+        arr = (C.c_void_p * len(flag_ptrs))(*flag_ptrs)
+        _check(self._L.sx_flag_write_many(self._ctx, arr, len(flag_ptrs), value & 0xFFFFFFFF))
+
     def flag_wait(self, flag_ptr, value):
         _check(self._L.sx_flag_wait(self._ctx, C.c_void_p(flag_ptr), value & 0xFFFFFFFF))
+
+    def pull_B_fused(self, N, peer_image_ptr, ready_flag, done_flag, step):
+        _check(self._L.sx_pull_B_fused(self._ctx, N, C.c_void_p(peer_image_ptr), C.c_void_p(ready_flag),
+                                       C.c_void_p(done_flag), step & 0xFFFFFFFF))
 
     def pull_B(self, N, peer_image_ptr):
         _check(self._L.sx_pull_B(self._ctx, N, C.c_void_p(peer_image_ptr)))

@@ -732,6 +732,56 @@ spmm_panels_dmma_kernel(const int npanels, const int M, const int *__restrict__ 
     }
 }
 
+// ---- peer flags -------------------------------------------------------------------
+// One launch publishes a step number to up to 16 peer-mapped flags (one per rank that
+// pulls B): 16 stream memory operations in a row cost ~3 us EACH on the root's stream,
+// one kernel with 16 stores costs ~3 us in total.
+struct FlagList { uint32_t *p[16]; };
+__global__ void flag_store_kernel(const FlagList flags, const int n, const uint32_t value) {
+    const int i = threadIdx.x;
+    if (i < n) {
+        __threadfence_system();  // everything this stream did before is visible to the peers first
+        *reinterpret_cast<volatile uint32_t *>(flags.p[i]) = value;
+    }
+}
+
+// ---- pull of the root's B image, fused: wait for the step, copy over NVLink, acknowledge --
+// One launch on the pulling rank replaces [stream wait-value, copy-engine peer copy, stream
+// write-value] (~13 us for the 600 KB B of nasa4704) by ~5 us: every block spins on the
+// LOCAL ready flag (the root stores the step number into it through its peer mapping),
+// all threads then copy 16-byte units from the root's memory with cache-volatile loads
+// (peer data may sit in L1 only, and L1 is clean at launch), and the last block to finish
+// stores the step number into the root's done flag.  The spin gives up after ~2 s and
+// raises *error instead of hanging the GPU if the root never publishes.
+__global__ void __launch_bounds__(256)
+pull_image_kernel(int4 *__restrict__ dst, const int4 *src, const int64_t n16, const uint32_t *ready,
+                  const uint32_t step, uint32_t *done_remote, unsigned int *counter, int *error) {
+    __shared__ int ok;
+    if (threadIdx.x == 0) {
+        ok = 1;
+        const long long t0 = clock64();
+        while ((int)(*reinterpret_cast<const volatile uint32_t *>(ready) - step) < 0) {
+            __nanosleep(64);
+            if (clock64() - t0 > 4000000000ll) { ok = 0; break; }
+        }
+    }
+    __syncthreads();
+    if (ok) {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x)
+            dst[i] = __ldcv(src + i);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (!ok) *error = 1;
+        __threadfence();
+        if (atomicAdd(counter, 1u) == gridDim.x - 1) {
+            *counter = 0;
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t *>(done_remote) = step;
+        }
+    }
+}
+
 // ---- layout changes at the host boundary ---------------------------------------
 // column-major (ld = rows) -> row-major (ld = ld_dst, pad columns zero-filled); the
 // device-side stand-in for the reference's B/C channel repacking

@@ -112,6 +112,8 @@ struct sx_ctx {
     int64_t ld = 0;
     bool has_B = false, has_C = false;
     DevBuf B, Cin, Cout, stage;
+    DevBuf sync_words;  // [0] block counter of pull_image_kernel, [1] its time-out flag
+    bool sync_words_zeroed = false;
 
     // options
     int arith = 0;
@@ -882,7 +884,7 @@ int sx_destroy(sx_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (DevBuf *b : {&c->rowptr, &c->colidx, &c->val, &c->split_row, &c->split_seg_ptr, &c->seg_begin,
-                      &c->seg_end, &c->partial, &c->B, &c->Cin, &c->Cout, &c->stage})
+                      &c->seg_end, &c->partial, &c->sync_words, &c->B, &c->Cin, &c->Cout, &c->stage})
         b->release();
     drop_plans(c);
     drop_tiles(c);
@@ -1099,11 +1101,49 @@ int sx_flag_write(sx_ctx *c, void *flag, uint32_t value) {
     return stream_value32("cuStreamWriteValue32", c, flag, value, CU_STREAM_WRITE_VALUE_DEFAULT);
 }
 
+int sx_flag_write_many(sx_ctx *c, void *const *flags, int n, uint32_t value) {
+    int rc = bind(c);
+    if (rc) return rc;
+    if (n < 0 || n > 16 || (n > 0 && !flags)) return fail(SX_ERR_INVALID, "0..16 flags expected (got %d)", n);
+    if (n == 0) return SX_OK;
+    sx::FlagList fl = {};
+    for (int i = 0; i < n; ++i) {
+        if (!flags[i]) return fail(SX_ERR_INVALID, "null flag");
+        fl.p[i] = (uint32_t *)flags[i];
+    }
+    sx::flag_store_kernel<<<1, 32, 0, c->stream>>>(fl, n, value);
+    c->launches++;
+    SX_CUDA(cudaGetLastError());
+    return SX_OK;
+}
+
 int sx_flag_wait(sx_ctx *c, void *flag, uint32_t value) {
     int rc = bind(c);
     if (rc) return rc;
     if (!flag) return fail(SX_ERR_INVALID, "null flag");
     return stream_value32("cuStreamWaitValue32", c, flag, value, CU_STREAM_WAIT_VALUE_GEQ);
+}
+
+int sx_pull_B_fused(sx_ctx *c, int N, const void *peer_B_image, const void *ready_flag, void *done_flag,
+                    uint32_t step) {
+    void *mine = nullptr;
+    size_t bytes = 0;
+    int rc = sx_device_B(c, N, &mine, &bytes);
+    if (rc) return rc;
+    if (!peer_B_image || !ready_flag || !done_flag) return fail(SX_ERR_INVALID, "null argument");
+    if ((rc = c->sync_words.ensure(16))) return rc;
+    if (!c->sync_words_zeroed) {
+        SX_CUDA(cudaMemsetAsync(c->sync_words.p, 0, 16, c->stream));
+        c->sync_words_zeroed = true;
+    }
+    const int64_t n16 = (int64_t)((bytes + 15) / 16);  // images are allocated in whole 16-byte units
+    const int grid = (int)std::min<int64_t>(c->sm_count, std::max<int64_t>(1, (n16 + 255) / 256));
+    sx::pull_image_kernel<<<grid, 256, 0, c->stream>>>((int4 *)mine, (const int4 *)peer_B_image, n16,
+                                                       (const uint32_t *)ready_flag, step, (uint32_t *)done_flag,
+                                                       (unsigned int *)c->sync_words.p, (int *)c->sync_words.p + 1);
+    c->launches++;
+    SX_CUDA(cudaGetLastError());
+    return SX_OK;
 }
 
 int sx_pull_B(sx_ctx *c, int N, const void *peer_B_image) {

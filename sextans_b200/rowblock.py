@@ -63,9 +63,9 @@ class PeerBroadcast:
       peers: pull(k)         waits for publish(k), copies, acknowledges
     """
 
-    def __init__(self, engines, N, group=None, root=0):
+    def __init__(self, engines, N, group=None, root=0, fused=True):
         import torch.distributed as dist
-        self.engines, self.N, self.root = list(engines), N, root
+        self.engines, self.N, self.root, self.fused, self.group = list(engines), N, root, fused, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.R = len(self.engines)
         e0 = self.engines[0]
@@ -93,8 +93,9 @@ class PeerBroadcast:
 
     def publish(self, k):
         e = self.engines[(k - 1) % self.R]
-        for ptr in self.peer_ready.values():
-            e.flag_write(ptr, k)
+        ptrs = list(self.peer_ready.values())
+        for i in range(0, len(ptrs), 16):              # one small kernel per 16 peers
+            e.flag_write_many(ptrs[i:i + 16], k)
 
     def reclaim(self, k):
         e = self.engines[(k - 1) % self.R]
@@ -104,16 +105,27 @@ class PeerBroadcast:
     def pull(self, k):
         j = (k - 1) % self.R
         e = self.engines[j]
-        e.flag_wait(self.ready, k)
-        e.pull_B(self.N, self.root_images[j])
-        e.flag_write(self.root_done + 4 * self.rank, k)
+        if self.fused:      # one kernel: spin on the local flag, copy over NVLink, acknowledge
+            e.pull_B_fused(self.N, self.root_images[j], self.ready, self.root_done + 4 * self.rank, k)
+        else:               # stream memory operations around a copy-engine peer copy
+            e.flag_wait(self.ready, k)
+            e.pull_B(self.N, self.root_images[j])
+            e.flag_write(self.root_done + 4 * self.rank, k)
 
     def close(self):
+        """Collective: every rank unmaps what it imported, then the owners free their flags."""
+        import torch.distributed as dist
         e0 = self.engines[0]
         e0.synchronize()
         for ptr in self._imported:
             e0.ipc_close(ptr)
         self._imported = []
+        dist.barrier(group=self.group)
+        for name in ("done", "ready"):
+            ptr = getattr(self, name, None)
+            if ptr:
+                e0.device_free(ptr)
+                setattr(self, name, None)
 
 
 class ShardedSpMM:

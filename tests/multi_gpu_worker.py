@@ -52,29 +52,30 @@ def main():
     eng = sx.Engine(local)
     eng.upload_csr(blk.rows, K, blk.rowptr, blk.colidx, blk.val)
     eng.device_B(N)
-    pb = PeerBroadcast([eng], N)
-    for k in range(1, 6):
-        B, Cin = random_dense(M, K, N, 100 + k, np.float64)          # every rank can rebuild the root's B to check
-        Cb = blk.take_C(Cin, N)
+    for fused in (True, False):      # one fused kernel per pull / stream memory ops around a peer copy
+        pb = PeerBroadcast([eng], N, fused=fused)
+        for k in range(1, 6):
+            B, Cin = random_dense(M, K, N, 100 + k + 10 * fused, np.float64)   # every rank can rebuild the root's B to check
+            Cb = blk.take_C(Cin, N)
+            if rank == 0:
+                if k > 1:
+                    pb.reclaim(k - 1)                                  # peers are done with the previous B
+                eng.stage_B(N, B)
+                pb.publish(k)
+            else:
+                pb.pull(k)
+            eng.stage_C(N, Cb)
+            eng.launch(0.85, -2.06)
+            eng.fetch_C(Cb)
+            ref = oracle.spmm_csr(blk.rows, N, K, blk.rowptr, blk.colidx, blk.val, 0.85, B, -2.06, blk.take_C(Cin, N))
+            assert Cb.tobytes() == ref.tobytes(), (rank, k, fused)
         if rank == 0:
-            if k > 1:
-                pb.reclaim(k - 1)                                      # peers are done with the previous B
-            eng.stage_B(N, B)
-            pb.publish(k)
-        else:
-            pb.pull(k)
-        eng.stage_C(N, Cb)
-        eng.launch(0.85, -2.06)
-        eng.fetch_C(Cb)
-        ref = oracle.spmm_csr(blk.rows, N, K, blk.rowptr, blk.colidx, blk.val, 0.85, B, -2.06, blk.take_C(Cin, N))
-        assert Cb.tobytes() == ref.tobytes(), (rank, k)
+            pb.reclaim(5)
+        eng.synchronize()
+        dist.barrier()
+        pb.close()
     if rank == 0:
-        pb.reclaim(5)
-    eng.synchronize()
-    dist.barrier()
-    pb.close()
-    if rank == 0:
-        print("OK peer pull of B over NVLink: 5 steps bitwise on every rank", flush=True)
+        print("OK peer pull of B over NVLink (fused kernel and memory-op variants): 5 steps each, bitwise on every rank", flush=True)
     eng.close()
     dist.barrier()
     dist.destroy_process_group()
