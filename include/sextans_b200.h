@@ -75,7 +75,8 @@ enum sx_option {
      * wave of lane groups, else 2); 1 one lane group per row (+ one warp per long-row
      * segment); 2 TMA-staged nnz-balanced work items */
     SX_OPT_KERNEL = 2,
-    /* nonzeros per work item; 0 = auto (<= 256, smaller for small matrices) */
+    /* nonzeros per work item; 0 = auto (512 for N*sizeof(T) <= 128 bytes, else 256;
+     * smaller for small matrices) */
     SX_OPT_ITEM_NNZ = 3,
     /* sx_spmm_*: page-locked host B and C of up to this many bytes together are read
      * and written by the kernels directly over PCIe (no copy-engine transfers);

@@ -201,7 +201,7 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
             c->launches += 2;
         }
     } else if (c->M > 0) {
-        // variant 0: TMA-staged work items (+ finalize for rows split into pieces)
+        // variant 2: TMA-staged work items (+ finalize for rows split into pieces)
         constexpr int U = (G < 8 ? G : 8) / (VPL > 2 ? 4 : VPL);
         constexpr int E = sx::VecOf<T>::E;
         Plan *p = nullptr;
@@ -211,11 +211,8 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
         const int ts = pick_tile<T, G>(U);
         const size_t smem = (size_t)rows_per_block * (16 + 2 * (size_t)ts * (sizeof(T) + 4));
         auto kern = sx::spmm_staged_kernel<T, G, VPL, STRICT>;
-        static thread_local const void *configured = nullptr;  // per instantiation
-        if (configured != (const void *)kern) {
-            SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-            configured = (const void *)kern;
-        }
+        if (smem > 48 * 1024)  // only the narrowest fp64 shape (128 lane groups per block) gets there
+            SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (unsigned)(((int64_t)p->nitems + rows_per_block - 1) / rows_per_block);
         kern<<<grid, threads, smem, c->stream>>>(
             p->nitems, (const int4 *)p->items.p, ts, (const int *)c->rowptr.p, (const int *)c->colidx.p,
@@ -412,12 +409,16 @@ int get_plan(sx_ctx *c, int budget, Plan **out) {
     return SX_OK;
 }
 
-// Nonzeros per work item for lane groups of G lanes: 256, less when the matrix is so
-// small that 256 would leave SMs without work (an item never holds less than one row).
+// Nonzeros per work item for lane groups of G lanes: 512 for narrow groups (several
+// items share a warp, and longer items even out their lengths: C5 at G=8 runs 1.76 ms
+// with 512 against 1.93 ms with 256), 256 for wide ones (C4 at G=32: 1.47 ms with 256,
+// 1.50 ms with 512); less when the matrix is so small that this would leave SMs without
+// work (an item never holds less than one row).
 int pick_budget(const sx_ctx *c, int G) {
     if (c->item_nnz > 0) return c->item_nnz;
+    const int base = G <= 8 ? 512 : 256;
     const int64_t want_items = (int64_t)c->sm_count * (256 / G) * 4;
-    return (int)std::min<int64_t>(256, std::max<int64_t>(16, c->nnz / want_items));
+    return (int)std::min<int64_t>(base, std::max<int64_t>(16, c->nnz / want_items));
 }
 
 // tile size (entries, power of two) of the staged kernel: <= 28 KB of staging per block

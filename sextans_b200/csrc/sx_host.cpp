@@ -4,11 +4,14 @@
 // The loader reproduces the OBSERVABLE behaviour of the reference's
 // read_suitsparse_matrix(..., CSC) + CSC_2_CSR pair (src/sparse_helper.h:112-259,
 // 475-509; banner/size rules of src/mmio.h:254-367) with a different mechanism: the
-// file is read once into memory and tokenised by hand (the reference calls fscanf per
-// entry), and the (column,row) qsort + CSC->CSR sweep is replaced by two stable
-// counting sorts, which give the same CSR: rows in order, columns ascending within a
-// row.  Entries with equal (row,col) keep file order here; the reference's qsort
-// leaves their order unspecified.
+// file is mapped into memory, the entry region is parsed by one thread per host core
+// (the reference calls fscanf per entry), and the (column,row) qsort + CSC->CSR sweep is
+// replaced by a bucket-by-row-owner build with a stable per-row sort, which gives the
+// same CSR: rows in order, columns ascending within a row.  Entries with equal (row,col)
+// keep file order here; the reference's qsort leaves their order unspecified
+// (SURVEY.md appendix B).  Measured on 5e6 entries / 132 MB, 8 vCPU: 0.29 s against
+// 4.8 s for the reference's loader, same CSR (scripts/bench_loader.py,
+// profiles/r01_loader_bench.txt).
 //
 // Deliberate differences, all on malformed input where the reference has undefined
 // or silent behaviour: truncated files, unparsable tokens and indices beyond the
@@ -19,10 +22,18 @@
 #include <algorithm>
 #include <cctype>
 #include <cerrno>
+#include <charconv>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <utility>
 #include <vector>
 
 namespace sxhost {
@@ -47,6 +58,7 @@ class Cursor {
   public:
     Cursor(const char *b, const char *e) : p_(b), e_(e) {}
     bool eof() const { return p_ >= e_; }
+    const char *pos() const { return p_; }
     // one text line without its terminator; false at end of data
     bool line(std::string *out) {
         if (p_ >= e_) return false;
@@ -124,63 +136,108 @@ template <typename T> static bool is_plus_zero(T v) {
     return std::memcmp(&v, z, sizeof(T)) == 0;
 }
 
+// ---- parallel parsing -------------------------------------------------------------
+// for SuiteSparse-sized files the fscanf + qsort loader of the
+// reference dwarfs the SpMM.  The entry region is cut at line ends into one chunk per
+// host thread; a chunk is accepted only if EVERY non-blank line holds exactly one entry
+// (2 tokens for pattern files, 3 otherwise) -- the layout every real .mtx has.  Anything
+// else (entries that share or straddle lines, which fscanf tolerates) makes the whole
+// file fall back to the serial token parser, so the result never depends on the route.
+// Numbers go through std::from_chars, which rounds exactly like strtof/strtod (%f / %lg).
+struct Raw { int64_t r, c; };  // 1-based as in the file
+
 template <typename T>
-static int load(const char *path, int *M_out, int *K_out, int64_t *nnz_out, int32_t **rowptr_out,
-                int32_t **colidx_out, T **val_out) {
-    if (!path || !M_out || !K_out || !nnz_out || !rowptr_out || !colidx_out || !val_out)
-        return fail(SX_ERR_INVALID, "null argument");
-    *rowptr_out = nullptr; *colidx_out = nullptr; *val_out = nullptr;
-    FILE *f = std::fopen(path, "rb");
-    if (!f) return fail(SX_ERR_IO, std::string("Could not open ") + path);
-    std::vector<char> text;
-    {
-        char buf[1 << 16];
-        size_t got;
-        while ((got = std::fread(buf, 1, sizeof buf, f)) > 0) text.insert(text.end(), buf, buf + got);
-        std::fclose(f);
-    }
-    text.push_back('\0');  // strtof/strtod need a terminator
-    Cursor cur(text.data(), text.data() + text.size() - 1);
+struct ChunkOut {
+    std::vector<Raw> idx;
+    std::vector<T> val;
+    bool regular = true;
+    std::string err;
+};
 
-    Banner b;
-    int rc = parse_banner(cur, &b);
-    if (rc) return rc;
-    long M = 0, K = 0, nz = 0;
-    if ((rc = parse_size(cur, &M, &K, &nz))) return rc;
-    if (!b.coordinate) return fail(SX_ERR_FORMAT, std::string("The input matrix file ") + path + " is not a coordinate file!");
-    if (b.complex_) return fail(SX_ERR_FORMAT, "complex matrices are not supported");
-    if (M < 0 || K < 0 || nz < 0 || M > INT32_MAX || K > INT32_MAX) return fail(SX_ERR_FORMAT, "bad matrix size");
+static inline const char *skip_blank(const char *p, const char *e) {
+    while (p < e && (*p == ' ' || *p == '\t' || *p == '\r')) ++p;
+    return p;
+}
 
-    struct Entry { int32_t r, c; T v; };
-    std::vector<Entry> coo;
-    coo.reserve((size_t)nz * (b.symmetric ? 2 : 1));
-    for (long e = 0; e < nz; ++e) {
-        long r, c;
-        T v = T(1);
-        if (!cur.integer(&r) || !cur.integer(&c)) return fail(SX_ERR_IO, "entry " + std::to_string(e) + ": missing or malformed indices");
-        if (!b.pattern && !cur.real(&v)) return fail(SX_ERR_IO, "entry " + std::to_string(e) + ": missing or malformed value");
-        if (is_plus_zero(v)) continue;  // explicit +0 entries are not nonzeros; -0 is kept
-        if (r < 1 || c < 1) return fail(SX_ERR_FORMAT, "entry " + std::to_string(e) + ": index below 1");
-        if (r > M || c > K) return fail(SX_ERR_FORMAT, "entry " + std::to_string(e) + ": index beyond the declared size");
-        coo.push_back({(int32_t)(r - 1), (int32_t)(c - 1), v});
-        if (b.symmetric && r != c) {
-            if (c > M || r > K) return fail(SX_ERR_FORMAT, "entry " + std::to_string(e) + ": mirrored index beyond the declared size");
-            coo.push_back({(int32_t)(c - 1), (int32_t)(r - 1), v});
+template <typename T>
+static void parse_chunk(const char *p, const char *e, bool pattern, ChunkOut<T> *out) {
+    while (p < e) {
+        const char *nl = (const char *)memchr(p, '\n', (size_t)(e - p));
+        const char *le = nl ? nl : e;
+        const char *q = skip_blank(p, le);
+        if (q < le) {
+            long long r = 0, c = 0;
+            auto r1 = std::from_chars(q, le, r);
+            if (r1.ec != std::errc()) { out->regular = false; return; }
+            q = skip_blank(r1.ptr, le);
+            auto r2 = std::from_chars(q, le, c);
+            if (r2.ec != std::errc() || r2.ptr == q) { out->regular = false; return; }
+            q = skip_blank(r2.ptr, le);
+            T v = T(1);
+            if (!pattern) {
+                if (q < le && *q == '+') ++q;  // from_chars takes no leading plus; strtod does
+                auto r3 = std::from_chars(q, le, v);
+                if (r3.ec == std::errc::result_out_of_range) { out->regular = false; return; }  // let strtod decide
+                if (r3.ec != std::errc() || r3.ptr == q) { out->regular = false; return; }
+                q = skip_blank(r3.ptr, le);
+            }
+            if (q != le) { out->regular = false; return; }  // more tokens on the line
+            out->idx.push_back({r, c});
+            out->val.push_back(v);
         }
+        p = nl ? nl + 1 : e;
     }
-    const size_t n = coo.size();
-    if (n > (size_t)INT32_MAX) return fail(SX_ERR_FORMAT, "more than 2^31-1 nonzeros");
+}
 
-    // stable counting sort by column, then by row  ==  rows ascending, columns
-    // ascending inside a row, file order among duplicates
-    std::vector<Entry> bycol(n);
-    {
-        std::vector<size_t> start((size_t)K + 1, 0);
-        for (const Entry &en : coo) start[(size_t)en.c + 1]++;
-        for (long k = 0; k < K; ++k) start[k + 1] += start[k];
-        for (const Entry &en : coo) bycol[start[en.c]++] = en;
+static unsigned host_threads() {
+    if (const char *env = std::getenv("SX_LOADER_THREADS")) {
+        const int n = std::atoi(env);
+        if (n >= 1) return (unsigned)std::min(n, 256);
     }
-    std::vector<Entry>().swap(coo);
+    const unsigned hc = std::thread::hardware_concurrency();
+    return std::max(1u, std::min(hc ? hc : 1u, 64u));
+}
+
+template <typename F>
+static void parallel_for(unsigned nthreads, F f) {
+    if (nthreads <= 1) { f(0u); return; }
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nthreads; ++t) th.emplace_back(f, t);
+    f(0u);
+    for (auto &x : th) x.join();
+}
+
+template <typename T> struct Entry { int32_t r, c; T v; };
+
+// One entry of the file -> 0, 1 or 2 CSR entries (zero drop, 1-based -> 0-based, symmetric
+// mirror), bucketed by the thread that owns the row.  Returns 0 or an sx_status with *err.
+template <typename T>
+static inline int emit_entry(long e, long r, long c, T v, long M, long K, bool symmetric, long rows_per_owner,
+                             std::vector<std::vector<Entry<T>>> &bucket, std::string *err) {
+    if (is_plus_zero(v)) return SX_OK;  // explicit +0 entries are not nonzeros; -0 is kept
+    if (r < 1 || c < 1) { *err = "entry " + std::to_string(e) + ": index below 1"; return SX_ERR_FORMAT; }
+    if (r > M || c > K) { *err = "entry " + std::to_string(e) + ": index beyond the declared size"; return SX_ERR_FORMAT; }
+    bucket[(size_t)((r - 1) / rows_per_owner)].push_back({(int32_t)(r - 1), (int32_t)(c - 1), v});
+    if (symmetric && r != c) {
+        if (c > M || r > K) { *err = "entry " + std::to_string(e) + ": mirrored index beyond the declared size"; return SX_ERR_FORMAT; }
+        bucket[(size_t)((c - 1) / rows_per_owner)].push_back({(int32_t)(c - 1), (int32_t)(r - 1), v});
+    }
+    return SX_OK;
+}
+
+// buckets[chunk][owner], chunks in file order, owners = contiguous row ranges -> CSR with
+// rows ascending, columns ascending inside a row, file order among equal (row, col).
+// Every phase runs one thread per owner: row counts, (serial prefix sum), a scatter that
+// walks the owner's buckets in chunk order (so it is stable), a stable sort of every row
+// that is not already ascending.
+template <typename T>
+static int buckets_to_csr(const std::vector<std::vector<std::vector<Entry<T>>>> &buckets, long M, unsigned owners,
+                          long rows_per_owner, int64_t *nnz_out, int32_t **rowptr_out, int32_t **colidx_out,
+                          T **val_out) {
+    size_t n = 0;
+    for (const auto &ch : buckets)
+        for (const auto &bk : ch) n += bk.size();
+    if (n > (size_t)INT32_MAX) return fail(SX_ERR_FORMAT, "more than 2^31-1 nonzeros");
     int32_t *rowptr = (int32_t *)std::calloc((size_t)M + 1, sizeof(int32_t));
     int32_t *colidx = (int32_t *)std::malloc(sizeof(int32_t) * std::max<size_t>(n, 1));
     T *val = (T *)std::malloc(sizeof(T) * std::max<size_t>(n, 1));
@@ -188,18 +245,160 @@ static int load(const char *path, int *M_out, int *K_out, int64_t *nnz_out, int3
         std::free(rowptr); std::free(colidx); std::free(val);
         return fail(SX_ERR_NOMEM, "out of host memory");
     }
-    for (const Entry &en : bycol) rowptr[en.r + 1]++;
+    parallel_for(owners, [&](unsigned o) {
+        for (const auto &ch : buckets)
+            for (const Entry<T> &en : ch[o]) rowptr[en.r + 1]++;
+    });
     for (long i = 0; i < M; ++i) rowptr[i + 1] += rowptr[i];
+    parallel_for(owners, [&](unsigned o) {
+        const long r0 = std::min(M, rows_per_owner * (long)o), r1 = std::min(M, rows_per_owner * (long)(o + 1));
+        if (r0 >= r1) return;
+        std::vector<int32_t> next(rowptr + r0, rowptr + r1);
+        for (const auto &ch : buckets)
+            for (const Entry<T> &en : ch[o]) {
+                const int32_t pos = next[en.r - r0]++;
+                colidx[pos] = en.c;
+                val[pos] = en.v;
+            }
+        std::vector<std::pair<int32_t, T>> tmp;
+        for (long r = r0; r < r1; ++r) {
+            const int32_t b = rowptr[r], e = rowptr[r + 1];
+            bool sorted = true;
+            for (int32_t j = b + 1; j < e; ++j)
+                if (colidx[j] < colidx[j - 1]) { sorted = false; break; }
+            if (sorted) continue;
+            tmp.resize((size_t)(e - b));
+            for (int32_t j = b; j < e; ++j) tmp[(size_t)(j - b)] = {colidx[j], val[j]};
+            std::stable_sort(tmp.begin(), tmp.end(),
+                             [](const std::pair<int32_t, T> &x, const std::pair<int32_t, T> &y) { return x.first < y.first; });
+            for (int32_t j = b; j < e; ++j) { colidx[j] = tmp[(size_t)(j - b)].first; val[j] = tmp[(size_t)(j - b)].second; }
+        }
+    });
+    *nnz_out = (int64_t)n;
+    *rowptr_out = rowptr; *colidx_out = colidx; *val_out = val;
+    return SX_OK;
+}
+
+// The whole file in memory without a copy; the bytes after the end of the file in its
+// last page read as zeros, which is the terminator strtod needs -- unless the size is an
+// exact multiple of the page size, in which case the file is copied.
+struct FileText {
+    const char *data = nullptr;
+    size_t size = 0;
+    void *map = nullptr;
+    size_t map_len = 0;
+    std::vector<char> copy;
+    ~FileText() { if (map) munmap(map, map_len); }
+    int open(const char *path) {
+        const int fd = ::open(path, O_RDONLY);
+        if (fd < 0) return fail(SX_ERR_IO, std::string("Could not open ") + path);
+        struct stat st;
+        const long page = sysconf(_SC_PAGESIZE);
+        if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0 && st.st_size % page != 0) {
+            void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m != MAP_FAILED) {
+                map = m; map_len = (size_t)st.st_size;
+                data = (const char *)m; size = (size_t)st.st_size;
+                ::close(fd);
+                return SX_OK;
+            }
+        }
+        char buf[1 << 16];
+        ssize_t got;
+        while ((got = ::read(fd, buf, sizeof buf)) > 0) copy.insert(copy.end(), buf, buf + got);
+        ::close(fd);
+        size = copy.size();
+        copy.push_back('\0');
+        data = copy.data();
+        return SX_OK;
+    }
+};
+
+template <typename T>
+static int load(const char *path, int *M_out, int *K_out, int64_t *nnz_out, int32_t **rowptr_out,
+                int32_t **colidx_out, T **val_out) {
+    if (!path || !M_out || !K_out || !nnz_out || !rowptr_out || !colidx_out || !val_out)
+        return fail(SX_ERR_INVALID, "null argument");
+    *rowptr_out = nullptr; *colidx_out = nullptr; *val_out = nullptr;
+    const bool trace = std::getenv("SX_LOADER_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t_start = now();
+    FileText text;
+    int rc = text.open(path);
+    if (rc) return rc;
+    Cursor cur(text.data, text.data + text.size);
+
+    Banner b;
+    if ((rc = parse_banner(cur, &b))) return rc;
+    long M = 0, K = 0, nz = 0;
+    if ((rc = parse_size(cur, &M, &K, &nz))) return rc;
+    if (!b.coordinate) return fail(SX_ERR_FORMAT, std::string("The input matrix file ") + path + " is not a coordinate file!");
+    if (b.complex_) return fail(SX_ERR_FORMAT, "complex matrices are not supported");
+    if (M < 0 || K < 0 || nz < 0 || M > INT32_MAX || K > INT32_MAX) return fail(SX_ERR_FORMAT, "bad matrix size");
+    const auto t_read = now();
+
+    // ---- entries: parallel when the file is line-regular, serial token parser otherwise ----
+    const char *dbeg = cur.pos(), *dend = text.data + text.size;
+    const unsigned nthreads = (size_t)(dend - dbeg) < (1u << 20) ? 1u : host_threads();
+    const unsigned owners = nthreads;
+    const long rows_per_owner = std::max(1L, (M + (long)owners - 1) / (long)owners);
+    std::vector<ChunkOut<T>> chunks(nthreads);
     {
-        std::vector<int32_t> next(rowptr, rowptr + M);
-        for (const Entry &en : bycol) {
-            const int32_t pos = next[en.r]++;
-            colidx[pos] = en.c;
-            val[pos] = en.v;
+        std::vector<const char *> cut(nthreads + 1, dend);
+        cut[0] = dbeg;
+        for (unsigned t = 1; t < nthreads; ++t) {
+            const char *p = dbeg + (size_t)(dend - dbeg) * t / nthreads;
+            const char *nl = (const char *)memchr(p, '\n', (size_t)(dend - p));
+            cut[t] = nl ? nl + 1 : dend;
+        }
+        for (unsigned t = 1; t <= nthreads; ++t) cut[t] = std::max(cut[t], cut[t - 1]);
+        parallel_for(nthreads, [&](unsigned t) { parse_chunk<T>(cut[t], cut[t + 1], b.pattern, &chunks[t]); });
+    }
+    const auto t_parse = now();
+    bool regular = true;
+    size_t found = 0;
+    for (const auto &c : chunks) { regular = regular && c.regular; found += c.idx.size(); }
+
+    std::vector<std::vector<std::vector<Entry<T>>>> buckets;
+    if (regular && found >= (size_t)nz) {
+        // the reference reads exactly nz entries and ignores what follows
+        std::vector<long> first(nthreads + 1, 0);
+        for (unsigned t = 0; t < nthreads; ++t) first[t + 1] = first[t] + (long)chunks[t].idx.size();
+        buckets.assign(nthreads, std::vector<std::vector<Entry<T>>>(owners));
+        std::vector<int> status(nthreads, SX_OK);
+        std::vector<std::string> errs(nthreads);
+        parallel_for(nthreads, [&](unsigned t) {
+            const ChunkOut<T> &c = chunks[t];
+            const long take = std::max(0L, std::min((long)c.idx.size(), nz - first[t]));
+            for (auto &bk : buckets[t]) bk.reserve((size_t)take * (b.symmetric ? 2 : 1) / owners + 16);
+            for (long i = 0; i < take; ++i)
+                if ((status[t] = emit_entry<T>(first[t] + i, (long)c.idx[(size_t)i].r, (long)c.idx[(size_t)i].c, c.val[(size_t)i], M,
+                                               K, b.symmetric, rows_per_owner, buckets[t], &errs[t])))
+                    return;
+        });
+        for (unsigned t = 0; t < nthreads; ++t)  // the first bad entry in file order, as the serial walk would report
+            if (status[t]) return fail(status[t], errs[t]);
+    } else {
+        regular = false;
+        buckets.assign(1, std::vector<std::vector<Entry<T>>>(owners));
+        std::string err;
+        for (long e = 0; e < nz; ++e) {
+            long r, c;
+            T v = T(1);
+            if (!cur.integer(&r) || !cur.integer(&c)) return fail(SX_ERR_IO, "entry " + std::to_string(e) + ": missing or malformed indices");
+            if (!b.pattern && !cur.real(&v)) return fail(SX_ERR_IO, "entry " + std::to_string(e) + ": missing or malformed value");
+            if ((rc = emit_entry<T>(e, r, c, v, M, K, b.symmetric, rows_per_owner, buckets[0], &err))) return fail(rc, err);
         }
     }
-    *M_out = (int)M; *K_out = (int)K; *nnz_out = (int64_t)n;
-    *rowptr_out = rowptr; *colidx_out = colidx; *val_out = val;
+    std::vector<ChunkOut<T>>().swap(chunks);
+    const auto t_coo = now();
+    if ((rc = buckets_to_csr<T>(buckets, M, owners, rows_per_owner, nnz_out, rowptr_out, colidx_out, val_out))) return rc;
+    if (trace)
+        std::fprintf(stderr, "sx loader: open+header %.0f ms, parse %.0f ms (%u threads, %s), entries %.0f ms, csr %.0f ms\n",
+                     ms(t_start, t_read), ms(t_read, t_parse), nthreads, regular ? "regular" : "serial fallback",
+                     ms(t_parse, t_coo), ms(t_coo, now()));
+    *M_out = (int)M; *K_out = (int)K;
     return SX_OK;
 }
 

@@ -115,3 +115,56 @@ def test_partition_rows():
     # more parts than rows, and an empty matrix
     assert sx.partition_rows(np.array([0, 5], dtype=np.int32), 4)[-1] == 1
     assert sx.partition_rows(np.zeros(5, dtype=np.int32), 2).tolist() == [0, 2, 4]
+
+
+def _write_big_mtx(path, M, K, nz, seed, field="real", symmetry="general", irregular=False):
+    rng = np.random.default_rng(seed)
+    r = rng.integers(1, M + 1, size=nz)
+    c = rng.integers(1, K + 1, size=nz)
+    if symmetry == "symmetric":
+        r, c = np.maximum(r, c), np.minimum(r, c)
+    v = rng.uniform(-1, 1, size=nz)
+    v[::97] = 0.0            # explicit +0 entries are dropped
+    v[1::97] = -0.0          # -0 is kept
+    r[5::211], c[5::211] = r[4::211][:r[5::211].size], c[4::211][:c[5::211].size]   # duplicates
+    with open(path, "w") as f:
+        f.write(f"%%MatrixMarket matrix coordinate {field} {symmetry}\n% generated\n{M} {K} {nz}\n")
+        if field == "pattern":
+            lines = [f"{a} {b}" for a, b in zip(r, c)]
+        else:
+            lines = [f"{a} {b} {float(x)!r}" for a, b, x in zip(r, c, v)]
+        if irregular:         # two entries on one line here and there: legal for fscanf
+            lines[10] = lines[10] + " " + lines.pop(11)
+        f.write("\n".join(lines) + "\n")
+
+
+@pytest.mark.parametrize("field,symmetry", [("real", "general"), ("real", "symmetric"), ("pattern", "symmetric")])
+def test_parallel_loader_equals_oracle_for_any_thread_count(tmp_path, monkeypatch, field, symmetry):
+    p = str(tmp_path / "big.mtx")
+    K = 3000 if symmetry == "symmetric" else 2500                      # symmetric files are square
+    _write_big_mtx(p, 3000, K, 160_000 if field == "pattern" else 120_000, 5, field, symmetry)   # > 1 MB: the parallel route
+    assert os.path.getsize(p) > (1 << 20)
+    ref = oracle.load_mtx(p, np.float64)
+    for threads in ("1", "3", "8"):
+        monkeypatch.setenv("SX_LOADER_THREADS", threads)
+        mine = sx.load_mtx(p, np.float64)
+        assert mine[:3] == ref[:3]
+        for a, b in zip(mine[3:], ref[3:6]):
+            assert np.array_equal(a, b)
+        assert np.array_equal(mine[5].view(np.uint64), ref[5].view(np.uint64))
+    mine32, ref32 = sx.load_mtx(p, np.float32), oracle.load_mtx(p, np.float32)
+    assert all(np.array_equal(a, b) for a, b in zip(mine32[3:], ref32[3:6]))
+
+
+def test_parallel_loader_falls_back_on_irregular_lines(tmp_path):
+    p = str(tmp_path / "irr.mtx")
+    _write_big_mtx(p, 3000, 2500, 120_000, 6, irregular=True)
+    mine, ref = sx.load_mtx(p, np.float64), oracle.load_mtx(p, np.float64)
+    assert mine[:3] == ref[:3] and all(np.array_equal(a, b) for a, b in zip(mine[3:], ref[3:6]))
+    # fewer entries than declared: still an error, whatever the route
+    with open(p) as f:
+        text = f.read().splitlines()
+    with open(p, "w") as f:
+        f.write("\n".join(text[:-50]) + "\n")
+    with pytest.raises(sx.SextansError, match="missing"):
+        sx.load_mtx(p, np.float64)
