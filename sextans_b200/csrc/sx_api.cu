@@ -1160,6 +1160,10 @@ int sx_pull_B(sx_ctx *c, int N, const void *peer_B_image) {
 int sx_host_alloc(size_t bytes, void **ptr) {
     if (!ptr) return fail(SX_ERR_INVALID, "null ptr");
     *ptr = nullptr;
+    int n = 0;
+    int rc = sx_device_count(&n);
+    if (rc) return rc;
+    if (n == 0) return fail(SX_ERR_NO_DEVICE, "no CUDA device present (this engine has no CPU fallback)");
     SX_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
     return SX_OK;
 }

@@ -168,3 +168,22 @@ def test_parallel_loader_falls_back_on_irregular_lines(tmp_path):
         f.write("\n".join(text[:-50]) + "\n")
     with pytest.raises(sx.SextansError, match="missing"):
         sx.load_mtx(p, np.float64)
+
+
+def test_host_program_call_surface_without_gpu():
+    """The argv contract of src/sextans-host.cpp:33-48 needs no device; without a GPU the
+    program must stop with an error after loading A -- never compute on the CPU instead."""
+    import subprocess
+    import torch
+    exe = os.path.join(ROOT, "sextans_b200", "sextans")
+    assert os.path.exists(exe), "build with make -C sextans_b200/csrc"
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode != 0 and r.stdout.startswith("start host\n")
+    assert "Usage: " in r.stdout and "[matrix A file] [N] [rp_time] [alpha] [beta]" in r.stdout
+    r = subprocess.run([exe, "/nonexistent.mtx", "8"], capture_output=True, text=True)
+    assert r.returncode == 1 and "N = 8" in r.stdout and "Could not open" in r.stdout
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, mtx_path("nasa4704"), "13"], capture_output=True, text=True)
+        assert r.returncode != 0
+        assert "N = 16" in r.stdout and "A: sparse matrix, 4704 x 4704. NNZ = 104756" in r.stdout
+        assert "NO_DEVICE" in r.stderr and "Success!" not in r.stdout
