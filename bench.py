@@ -60,9 +60,10 @@ def parse():
     p.add_argument("--dtype", default="", choices=["", "f32", "f64"])
     p.add_argument("--scale", type=float, default=1.0, help="shrink the synthetic workloads (testing)")
     p.add_argument("--arith", default="strict", choices=["strict", "fast"])
-    p.add_argument("--kernel", type=int, default=0, help="SX_OPT_KERNEL (0 auto, 1 row per lane group, 2 TMA-staged items)")
+    p.add_argument("--kernel", type=int, default=0, help="SX_OPT_KERNEL (0 auto, 1 row per lane group, 2 TMA-staged items, 3 TMA-staged B window)")
     p.add_argument("--item-nnz", type=int, default=0, help="SX_OPT_ITEM_NNZ (0 auto)")
     p.add_argument("--split", type=int, default=-1, help="SX_OPT_SPLIT_ROW_NNZ (-1 default)")
+    p.add_argument("--band", type=int, default=2000, help="fem workload: couplings reach +-band nodes")
     p.add_argument("--tiles", type=int, default=0, help="SX_OPT_TILE_MIN_ROWS (fp64 dense-tile tensor-core variant; 0 off)")
     p.add_argument("--ref-threads", type=int, default=1, help="--impl reference: threads of the CPU path (1 = as the reference runs it; -1 = all cores, OpenMP port)")
     p.add_argument("--peer-bytes", type=int, default=8 << 20, help="N>1: B images up to this size travel by peer copy instead of NCCL")
@@ -95,10 +96,10 @@ def build_workload(args):
     elif kind == "fem":
         nodes = max(250, int(250_000 * args.scale))
         M = K = nodes * 4
-        rp, ci, v = wl.fem_like_csr(nodes, 4, 23, 12345, dtype)
+        rp, ci, v = wl.fem_like_csr(nodes, 4, 23, 12345, dtype, band=args.band)
         nnz = int(ci.size)
         B, Cin = wl.random_dense(M, K, N, 12345, dtype)
-        desc = f"synthetic FEM-like CSR (4 dof/node, dense 4x4 couplings) M=K={M} nnz={nnz} N={N} {np.dtype(dtype).name}, seed 12345"
+        desc = f"synthetic FEM-like CSR (4 dof/node, dense 4x4 couplings within +-{args.band} nodes) M=K={M} nnz={nnz} N={N} {np.dtype(dtype).name}, seed 12345"
     else:
         M = K = max(1000, int(1_000_000 * args.scale))
         rp, ci, v = wl.powerlaw_csr(M, K, int(100_000_000 * args.scale), 12345, dtype)
@@ -513,7 +514,7 @@ def run_native(args):
                       f"{eng.info(sx.INFO_REST_NNZ)} nnz left to CSR")
     else:
         tiles_note = ""
-    kernel_name = ({1: "spmm_rows_kernel (+segments/finalize)", 2: "spmm_staged_kernel", 4: "spmm_panels_dmma_kernel"}.get(lk // 10000, "?")
+    kernel_name = ({1: "spmm_rows_kernel (+segments/finalize)", 2: "spmm_staged_kernel", 3: "spmm_window_kernel", 4: "spmm_panels_dmma_kernel"}.get(lk // 10000, "?")
                    + f" <G={lk % 10000 // 100}, VPL={lk % 100 // 10}, {'fast' if lk % 10 else 'strict'}>"
                    + (f", {eng.info(sx.INFO_ITEMS)} items of <= {eng.info(sx.INFO_ITEM_NNZ)} nnz, {eng.info(sx.INFO_SPLIT_ROWS)} split rows" if lk // 10000 == 2 else "") + tiles_note)
     host_path = "zero-copy kernels over PCIe (no memcpy)" if eng.info(sx.INFO_HOST_PATH) == 1 else "cudaMemcpyAsync + layout kernels"

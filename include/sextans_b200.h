@@ -71,9 +71,11 @@ enum sx_option {
      * tree-reduced (summation order differs from the oracle; error ~ 1e-7 fp32 /
      * 1e-16 fp64 relative to the row's |a||b| sum).  0 disables splitting. */
     SX_OPT_SPLIT_ROW_NNZ = 1,
-    /* kernel variant: 0 auto (1 for matrices whose rows fill less than one
-     * wave of lane groups, else 2); 1 one lane group per row (+ one warp per long-row
-     * segment); 2 TMA-staged nnz-balanced work items */
+    /* kernel variant: 0 auto; 1 one lane group per row (+ one warp per
+     * long-row segment); 2 TMA-staged nnz-balanced work items; 3 B window of each
+     * 32-row block staged into shared memory by TMA (banded matrices whose windows fit;
+     * falls back to 1 otherwise).  Auto: matrices below one wave of lane groups take 3 if
+     * they qualify, else 1; everything larger takes 2. */
     SX_OPT_KERNEL = 2,
     /* nonzeros per work item; 0 = auto (512 for N*sizeof(T) <= 128 bytes, else 256;
      * smaller for small matrices) */

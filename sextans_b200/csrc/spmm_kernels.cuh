@@ -431,6 +431,80 @@ spmm_staged_kernel(const int nitems, const int4 *__restrict__ items, const int t
     }
 }
 
+// ---- variant 3: banded matrices, the B window of a row block staged by TMA ----------
+// The reference keeps a 4096-row window of B on chip and streams the nonzeros whose
+// column falls inside it (src/sextans.h:11, src/sextans.cpp:337-381).  Where a block of 32
+// consecutive rows of A only touches a narrow, CONTIGUOUS range of columns -- banded
+// matrices: both shipped FEM matrices, span <= 822 / 954 columns -- the same idea fits a
+// B200 SM exactly: one thread block owns the 32 rows, thread 0 issues TMA bulk copies of
+// (i) rows [cmin, cmin+span) of B, which are one contiguous piece of the row-major image,
+// (ii) the block's slice of colidx[] and (iii) of val[], all completing on one mbarrier,
+// and the lane groups then walk their rows entirely out of shared memory: no global
+// gather, no shuffles, one row per group in stored order (bit-exact in strict mode).
+// The dependent chain is block record -> TMA -> shared-memory arithmetic.
+// block record = {cmin, span, nnz_begin, nnz_end}; dynamic smem = window + A slice + 16.
+template <typename T, int G, bool STRICT>
+__global__ void __launch_bounds__(32 * G)
+spmm_window_kernel(const int M, const int4 *__restrict__ blocks, const int *__restrict__ rowptr,
+                   const int *__restrict__ colidx, const T *__restrict__ val, const T *__restrict__ B,
+                   const uint32_t ldbv, const T *Cin, T *Cout, const uint32_t ldcv, const T alpha,
+                   const T beta, const int nvec) {
+    using V = typename VecOf<T>::type;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    const int lg = threadIdx.x & (G - 1);
+    const int row = blockIdx.x * 32 + threadIdx.x / G;
+    const int4 blk = __ldg(blocks + blockIdx.x);
+    const int jal = blk.z & ~3;  // 16-byte aligned start of the A slice
+    const uint32_t cnt = (uint32_t)((blk.w - jal + 3) & ~3);
+    const uint32_t wbytes = (uint32_t)blk.y * ldbv * 16u;  // the window: span whole rows of B
+    const V *win = reinterpret_cast<const V *>(smem_raw);
+    const T *sval = reinterpret_cast<const T *>(smem_raw + wbytes);
+    const int *scol = reinterpret_cast<const int *>(smem_raw + wbytes + (size_t)cnt * sizeof(T));
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && blk.w > blk.z) {
+        const uint64_t pol_a = policy_evict_first();
+        mbar_expect_tx(&bar, wbytes + cnt * (uint32_t)(sizeof(T) + 4));
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(B) + (size_t)blk.x * ldbv * 16u;
+        uint64_t pol_b;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_b));
+        for (uint32_t o = 0; o < wbytes; o += 32768u)  // several copies in flight
+            tma_bulk_g2s(smem_raw + o, src + o, min(32768u, wbytes - o), &bar, pol_b);
+        tma_bulk_g2s(const_cast<T *>(sval), val + jal, cnt * (uint32_t)sizeof(T), &bar, pol_a);
+        tma_bulk_g2s(const_cast<int *>(scol), colidx + jal, cnt * 4u, &bar, pol_a);
+    }
+    if (row >= M) return;  // after the barrier above; no block-wide barrier below
+    const int begin = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+    const bool mine = lg < nvec;
+    V acc, cin;
+    vzero(acc);
+    vzero(cin);
+    if (mine) cin = reinterpret_cast<const V *>(Cin)[(size_t)row * ldcv + lg];
+    if (blk.w > blk.z) mbar_wait(&bar, 0);
+    if (mine) {
+        const V *w = win + lg;                 // w[(col - cmin) * ldbv] = this lane's piece of B row col
+        const int cmin = blk.x;
+        int j = begin;
+        for (; j + 4 <= end; j += 4) {
+            int c[4];
+            T a[4];
+            V b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { c[u] = scol[j + u - jal]; a[u] = sval[j + u - jal]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) b[u] = w[(uint32_t)(c[u] - cmin) * ldbv];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) vmac<STRICT>(acc, a[u], b[u]);
+        }
+        for (; j < end; ++j) vmac<STRICT>(acc, sval[j - jal], w[(uint32_t)(scol[j - jal] - cmin) * ldbv]);
+        reinterpret_cast<V *>(Cout)[(size_t)row * ldcv + lg] = vaxpby<STRICT>(alpha, acc, beta, cin);
+    }
+}
+
 // ---- one row group per row (variant 1: matrices that fill less than one wave) ---
 // Latency-oriented walk of one row for G <= 8.  Entries travel in chunks of 8 (each
 // lane holds 8/G (col,val) pairs of a chunk), one chunk is one batch of 8 B-row gathers;

@@ -100,6 +100,10 @@ struct sx_ctx {
     std::vector<Plan *> plans;
     Plan *last_plan = nullptr;
     std::vector<int32_t> h_rowptr;  // kept to re-derive segments when the option changes
+    // variant 3: per block of 32 rows {first column, column span, nnz begin, nnz end}
+    DevBuf wblocks;
+    int nwblocks = 0, max_span = 0, max_block_nnz = 0;
+    std::vector<const void *> big_smem_ok;  // kernels already allowed > 48 KB of dynamic smem
     // dense-tile split A = A_tiles + A_rest (fp64, SX_OPT_TILE_MIN_ROWS > 0 at upload)
     int tile_min_rows = 0;
     int npanels = 0;
@@ -177,7 +181,34 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
     // pcrystk02 N=16: 14.4 against 20.4).  Anything larger takes the nnz-balanced
     // TMA-staged variant 2 (pcrystk02 N=32: 18.8 us against 24.8 us).
     const bool sub_wave = (int64_t)c->M * G <= (int64_t)c->sm_count * 512;
-    const int variant = c->kernel != 0 ? c->kernel : (sub_wave ? 1 : 2);
+    // variant 3 (B window of a 32-row block staged by TMA) needs every block's window and
+    // A slice to fit in shared memory: banded matrices only
+    size_t wsmem = 0;
+    bool window_ok = false;
+    if constexpr (G <= 16 && VPL == 1) {
+        wsmem = (size_t)c->max_span * (size_t)(ldb / sx::VecOf<T>::E) * 16 + ((size_t)c->max_block_nnz + 8) * (sizeof(T) + 4) + 16;
+        window_ok = c->nwblocks > 0 && wsmem <= 200 * 1024;
+    }
+    int variant = c->kernel != 0 ? c->kernel : (window_ok ? 3 : (sub_wave ? 1 : 2));
+    if (variant == 3 && !window_ok) variant = sub_wave ? 1 : 2;
+    if constexpr (G <= 16 && VPL == 1) {
+        if (variant == 3) {
+            constexpr int E = sx::VecOf<T>::E;
+            auto kern = sx::spmm_window_kernel<T, G, STRICT>;
+            if (wsmem > 48 * 1024 &&
+                std::find(c->big_smem_ok.begin(), c->big_smem_ok.end(), (const void *)kern) == c->big_smem_ok.end()) {
+                SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                c->big_smem_ok.push_back((const void *)kern);
+            }
+            kern<<<(unsigned)c->nwblocks, 32 * G, wsmem, c->stream>>>(
+                c->M, (const int4 *)c->wblocks.p, (const int *)c->rowptr.p, (const int *)c->colidx.p,
+                (const T *)c->val.p, dB, (uint32_t)(ldb / E), dCin, dCout, (uint32_t)(ldc / E), alpha, beta, nvec);
+            c->launches++;
+            c->last_kernel = 30000 + G * 100 + VPL * 10 + (STRICT ? 0 : 1);
+            SX_CUDA(cudaGetLastError());
+            return SX_OK;
+        }
+    }
     if (variant == 1) {
         // variant 1: one lane group per row + one warp per long-row segment
         const int split = c->nseg > 0 ? c->split_nnz : 0;
@@ -466,6 +497,45 @@ int refresh_segments(sx_ctx *c) {
 template <typename T>
 int upload_csr(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rowptr, const int32_t *colidx, const T *val);
 
+// Column window of every block of 32 consecutive rows (variant 3).  The scan stops at
+// the first block whose window could not fit in shared memory even at the narrowest B
+// row (32 bytes), and the matrix only qualifies if the windows together are at most
+// twice as many B rows as there are nonzeros (otherwise staging them costs more than
+// gathering).
+int build_window_blocks(sx_ctx *c, int M, const int32_t *rowptr, const int32_t *colidx) {
+    c->nwblocks = c->max_span = c->max_block_nnz = 0;
+    if (M == 0) return SX_OK;
+    const int nb = (M + 31) / 32;
+    std::vector<int32_t> blk((size_t)nb * 4);
+    int64_t span_sum = 0;
+    int max_span = 0, max_block_nnz = 0;
+    for (int b = 0; b < nb; ++b) {
+        const int r0 = b * 32, r1 = std::min(M, r0 + 32);
+        const int32_t jb = rowptr[r0], je = rowptr[r1];
+        int32_t lo = INT32_MAX, hi = -1;
+        for (int32_t j = jb; j < je; ++j) { lo = std::min(lo, colidx[j]); hi = std::max(hi, colidx[j]); }
+        if (je == jb) { lo = 0; hi = -1; }
+        const int span = hi - lo + 1;
+        if ((int64_t)span * 32 > 200 * 1024 || (int64_t)(je - jb) * 8 > 200 * 1024) return SX_OK;  // can never fit
+        blk[(size_t)b * 4 + 0] = lo;
+        blk[(size_t)b * 4 + 1] = span;
+        blk[(size_t)b * 4 + 2] = jb;
+        blk[(size_t)b * 4 + 3] = je;
+        span_sum += span;
+        max_span = std::max(max_span, span);
+        max_block_nnz = std::max(max_block_nnz, je - (jb & ~3));
+    }
+    if (span_sum > 2 * (int64_t)rowptr[M]) return SX_OK;
+    c->max_span = max_span;
+    c->max_block_nnz = max_block_nnz;
+    int rc = c->wblocks.ensure(blk.size() * 4);
+    if (rc) return rc;
+    SX_CUDA(cudaMemcpyAsync(c->wblocks.p, blk.data(), blk.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    SX_CUDA(cudaStreamSynchronize(c->stream));
+    c->nwblocks = nb;
+    return SX_OK;
+}
+
 void drop_tiles(sx_ctx *c) {
     c->npanels = 0;
     c->tile_steps = c->tile_nnz = c->rest_nnz = 0;
@@ -616,6 +686,7 @@ int upload_csr(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rowptr, cons
     c->has_B = c->has_C = false;
     c->N = 0; c->ld = 0;
     if ((rc = refresh_segments(c))) return rc;
+    if ((rc = build_window_blocks(c, M, rowptr, colidx))) return rc;
     if ((rc = maybe_build_panels<T>(c, M, K, nnz, rowptr, colidx, val))) return rc;
     c->has_A = true;
     return SX_OK;
@@ -885,7 +956,7 @@ int sx_destroy(sx_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (DevBuf *b : {&c->rowptr, &c->colidx, &c->val, &c->split_row, &c->split_seg_ptr, &c->seg_begin,
-                      &c->seg_end, &c->partial, &c->sync_words, &c->B, &c->Cin, &c->Cout, &c->stage})
+                      &c->seg_end, &c->partial, &c->sync_words, &c->wblocks, &c->B, &c->Cin, &c->Cout, &c->stage})
         b->release();
     drop_plans(c);
     drop_tiles(c);
@@ -918,7 +989,7 @@ int sx_set_option(sx_ctx *c, int option, int64_t value) {
             if (c->rest) { c->rest->split_nnz = (int)value; c->rest->segments_dirty = true; }
             return SX_OK;
         case SX_OPT_KERNEL:
-            if (value < 0 || value > 2) return fail(SX_ERR_INVALID, "SX_OPT_KERNEL is 0 (auto), 1 (row per lane group) or 2 (TMA-staged work items)");
+            if (value < 0 || value > 3) return fail(SX_ERR_INVALID, "SX_OPT_KERNEL is 0 (auto), 1 (row per lane group), 2 (TMA-staged work items) or 3 (TMA-staged B window)");
             c->kernel = (int)value;
             return SX_OK;
         case SX_OPT_TILE_MIN_ROWS:
