@@ -189,7 +189,13 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
         wsmem = (size_t)c->max_span * (size_t)(ldb / sx::VecOf<T>::E) * 16 + ((size_t)c->max_block_nnz + 8) * (sizeof(T) + 4) + 16;
         window_ok = c->nwblocks > 0 && wsmem <= 200 * 1024;
     }
-    int variant = c->kernel != 0 ? c->kernel : (window_ok ? 3 : (sub_wave ? 1 : 2));
+    // ... and it is chosen automatically when two blocks fit on an SM, or when the whole
+    // matrix is a few waves of one block per SM (the latency regime, where it is 1.3-2.7x
+    // faster than variant 1); a long banded matrix with fat windows is left to variant 2
+    // (fem band=100 fp64, 143 KB windows: 1.11 ms against 1.04 ms; fp32, 78 KB: 0.58 against 0.84)
+    const int window_cap = wsmem ? (int)std::max<size_t>(1, (220 * 1024) / wsmem) : 1;
+    const bool window_auto = window_ok && (window_cap >= 2 || (int64_t)c->nwblocks <= (int64_t)4 * c->sm_count * window_cap);
+    int variant = c->kernel != 0 ? c->kernel : (window_auto ? 3 : (sub_wave ? 1 : 2));
     if (variant == 3 && !window_ok) variant = sub_wave ? 1 : 2;
     if constexpr (G <= 16 && VPL == 1) {
         if (variant == 3) {
