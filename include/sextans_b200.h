@@ -109,7 +109,9 @@ enum sx_info {
     SX_INFO_HOST_PATH = 10,  /* 1 if the last sx_spmm_* call took the zero-copy path */
     SX_INFO_TILE_NNZ = 11,   /* nonzeros held in dense tiles */
     SX_INFO_TILE_SLOTS = 12, /* tile slots incl. explicit zeros (fill = TILE_NNZ / TILE_SLOTS) */
-    SX_INFO_REST_NNZ = 13    /* nonzeros left to the CSR kernels */
+    SX_INFO_REST_NNZ = 13,   /* nonzeros left to the CSR kernels */
+    SX_INFO_UPLOAD_SERIAL = 14 /* process-wide serial number of the matrix this context holds
+                                * (every successful sx_upload_csr_* draws a new one; 0: none) */
 };
 
 /* ---- library ------------------------------------------------------------- */
@@ -229,6 +231,75 @@ int sx_load_mtx_f32(const char *path, int *M, int *K, int64_t *nnz, int32_t **ro
 int sx_load_mtx_f64(const char *path, int *M, int *K, int64_t *nnz, int32_t **rowptr,
                     int32_t **colidx, double **val);
 void sx_free(void *ptr);
+
+/* ---- the literal Sextans(...) argument list: FPGA channel images -------------- */
+/* For a host program that keeps the reference's OWN preprocessing
+ * (generate_edge_list_for_all_PEs + edge_list_64bit, src/sparse_helper.h:345-473, and
+ * the B/C channel repacking of src/sextans-host.cpp:152-202) and wants to change
+ * nothing but the device call: sx_sextans_invoke takes exactly the arguments of
+ *     void Sextans(mmap<int> edge_list_ptr, mmaps<ap_uint<512>,8> edge_list_ch,
+ *                  mmaps<float_v16,4> mat_B_ch, mmaps<float_v16,8> mat_C_ch_in,
+ *                  mmaps<float_v16,8> mat_C_ch, int NUM_ITE, int NUM_A_LEN, int M, int K,
+ *                  int P_N, int alpha_u, int beta_u)              src/sextans.h:20-26
+ * as plain pointers, and *kernel_ns is what tapa::invoke returns
+ * (src/sextans-host.cpp:237).  integration/sextans_kernel_b200.cpp defines Sextans()
+ * itself on top of it, and include/tapa_compat/ supplies the few TAPA names the
+ * unmodified host source uses.  fp32 only, like the images.
+ *
+ * Image layouts:
+ *   edge word  [63:50] column inside its 4096-column window, [49:32] row/64 (bit 17 set
+ *              = bubble), [31:0] fp32 bits                 src/sparse_helper.h:419-443
+ *   A          slot i of channel ch is the 8 words [8i, 8i+8); word bitrev3(q) belongs to
+ *              PE ch + 8q, which owns the rows r with r % 64 == PE
+ *                                                          src/sparse_helper.h:451-464
+ *   ptr        ptr[w]..ptr[w+1] = slots of column window w, NUM_ITE windows, ptr[NUM_ITE]
+ *              == NUM_A_LEN                                 src/sparse_helper.h:359,400
+ *   B          channel (n/2)%4, element (k/8)*16 + (n%2)*8 + k%8 + 2*roundup(K,8)*(n/8)
+ *                                                          src/sextans-host.cpp:158-171
+ *   C in/out   channel m%8, element roundup(M,16)*(n/8) + (m/8)*8 + n%8
+ *                                                          src/sextans-host.cpp:181-195,269
+ *   P_N        (rp_time << 16) | N, rp_time 0 read as 1; N is processed in whole blocks
+ *              of 8 columns                src/sextans-host.cpp:223, src/sextans.cpp:52-54
+ *   alpha_u, beta_u   fp32 bit patterns                    src/sextans-host.cpp:225-229
+ *
+ * A images are decoded to CSR on the host (row order inside a PE stream is the order
+ * the FPGA accumulates in, so the CSR rows come out in ascending column order) and
+ * uploaded; a second call with the same images (same contents) reuses the uploaded A.
+ * Rows M..roundup(M,16)-1 of mat_C_ch receive alpha*0 + beta*C_in like the FPGA's
+ * whole-word writes; nothing beyond is touched. */
+#define SX_IMAGES_A_CHANNELS 8
+#define SX_IMAGES_B_CHANNELS 4
+#define SX_IMAGES_C_CHANNELS 8
+#define SX_IMAGES_WINDOW 4096
+#define SX_IMAGES_PES 64
+int sx_sextans_invoke(sx_ctx *ctx, const int32_t *edge_list_ptr,
+                      const uint64_t *const edge_list_ch[SX_IMAGES_A_CHANNELS],
+                      const float *const mat_B_ch[SX_IMAGES_B_CHANNELS],
+                      const float *const mat_C_ch_in[SX_IMAGES_C_CHANNELS],
+                      float *const mat_C_ch[SX_IMAGES_C_CHANNELS], int NUM_ITE, int NUM_A_LEN,
+                      int M, int K, int P_N, int alpha_u, int beta_u, double *kernel_ns);
+/* kernel time of the calling thread's last successful sx_sextans_invoke (what the
+ * tapa::invoke of include/tapa_compat/tapa.h returns) */
+double sx_sextans_last_kernel_ns(void);
+/* elements every channel buffer must at least hold: 64-bit words of an A channel, floats
+ * of a B channel, floats of a C channel (the host pads them further to 512/1024) */
+int64_t sx_images_A_words(int NUM_A_LEN);
+int64_t sx_images_B_floats(int K, int N);
+int64_t sx_images_C_floats(int M, int N);
+/* the pieces, usable on their own (host only, no GPU needed): */
+int sx_images_decode_A(const int32_t *edge_list_ptr,
+                       const uint64_t *const edge_list_ch[SX_IMAGES_A_CHANNELS], int NUM_ITE,
+                       int NUM_A_LEN, int M, int K, int64_t *nnz, int32_t **rowptr,
+                       int32_t **colidx, float **val); /* arrays malloc'ed: sx_free */
+int sx_images_decode_B(const float *const mat_B_ch[SX_IMAGES_B_CHANNELS], int K, int N,
+                       float *B_colmajor /* K x roundup(N,8) */);
+int sx_images_decode_C(const float *const mat_C_ch[SX_IMAGES_C_CHANNELS], int M, int N,
+                       float *C_colmajor /* M x roundup(N,8) */);
+/* writes rows 0..M-1 from C_colmajor and rows M..roundup(M,16)-1 as alpha*0 + beta*pad
+ * of mat_C_ch_in (NULL: those rows are left alone) */
+int sx_images_encode_C(const float *C_colmajor, int M, int N, float alpha, float beta,
+                       const float *const mat_C_ch_in[SX_IMAGES_C_CHANNELS],
+                       float *const mat_C_ch[SX_IMAGES_C_CHANNELS]);
 
 #ifdef __cplusplus
 }

@@ -88,6 +88,10 @@ def ref():
         R.sxref_edge_list_slots.argtypes = [_I, _I, _I, _PI, _PI, _PF, _I, _I, _I]
         R.sxref_edge_list_slots.restype = _I
         R.sxref_free.argtypes = [C.c_void_p]
+        if hasattr(R, "sxref_build_images"):
+            R.sxref_build_images.argtypes = [_I, _I, _I, _PI, _PI, _PF, C.POINTER(_PI), _PI,
+                                             C.POINTER(C.POINTER(C.c_ulong)), C.POINTER(C.c_long)]
+            R.sxref_build_images.restype = _I
         _REF = R
     return _REF
 
@@ -213,3 +217,87 @@ def ref_spmm_csr(M, N, K, rowptr, colidx, val, alpha, B, beta, C_inout):
                               _ptr(val, C.c_float), _ptr(B, C.c_float), float(beta),
                               _ptr(C_inout, C.c_float))
     return ns * 1e-9
+
+
+# ---- FPGA channel images (checker side of sx_sextans_invoke) -------------------------
+def ref_build_images(M, K, rowptr, colidx, val):
+    """The reference's own A preprocessing (generate_edge_list_for_all_PEs +
+    edge_list_64bit, src/sparse_helper.h:345-473, constants of src/sextans.h:7-12) on a
+    CSR with ascending columns -> (ptr int32[NUM_ITE+1], [8 x uint64 image], NUM_A_LEN)."""
+    R = ref()
+    if R is None or not hasattr(R, "sxref_build_images"):
+        raise RuntimeError("oracle/_ref/libsextans_ref.so (with sxref_build_images) not built")
+    rowptr, colidx, val = _csr_args(rowptr, colidx, val, np.float32)
+    ptr, ptr_len, image_len = _PI(), _I(), C.c_long()
+    imgs = (C.POINTER(C.c_ulong) * 8)()
+    num_a_len = R.sxref_build_images(M, K, int(colidx.size), _ptr(rowptr, C.c_int),
+                                     _ptr(colidx, C.c_int), _ptr(val, C.c_float), C.byref(ptr),
+                                     C.byref(ptr_len), imgs, C.byref(image_len))
+    p = _take(ptr, ptr_len.value, np.int32, R.sxref_free)
+    images = []
+    for c in range(8):
+        a = np.ctypeslib.as_array(imgs[c], shape=(max(image_len.value, 1),))[:image_len.value]
+        images.append(a.astype(np.uint64, copy=True))
+        R.sxref_free(imgs[c])
+    return p, images, int(num_a_len)
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def pack_B_images(B, K, N):
+    """Column-major B (K x N, N % 8 == 0) -> the 4 channel images the host program builds
+    (src/sextans-host.cpp:148-171, NUM_CH_B == 4 branch), chunk-padded like there."""
+    assert N % 8 == 0
+    B = np.asarray(B, dtype=np.float32).reshape(N, K)         # [n, k]
+    colsz = _round_up(K, 8) * 2
+    chunk = _round_up(colsz * (N // 8), 1024)
+    imgs = [np.zeros(chunk, dtype=np.float32) for _ in range(4)]
+    k = np.arange(K, dtype=np.int64)
+    for n in range(N):
+        pos = (k // 8) * 16 + (n % 2) * 8 + k % 8 + colsz * (n // 8)
+        imgs[(n // 2) % 4][pos] = B[n]
+    return imgs
+
+
+def pack_C_images(Cm, M, N, fill_pad=None):
+    """Column-major C (M x N) -> the 8 channel images (src/sextans-host.cpp:173-195).
+    fill_pad: value for the rows that pad M to a multiple of 16 (the host leaves 0)."""
+    assert N % 8 == 0
+    Cm = np.asarray(Cm, dtype=np.float32).reshape(N, M)
+    colsz = _round_up(M, 16)
+    chunk = _round_up(colsz * (N // 8), 1024)
+    imgs = [np.zeros(chunk, dtype=np.float32) for _ in range(8)]
+    m = np.arange(M, dtype=np.int64)
+    mp = np.arange(M, colsz, dtype=np.int64)
+    for n in range(N):
+        pos = colsz * (n // 8) + (m // 8) * 8 + n % 8
+        for c in range(8):
+            sel = m % 8 == c
+            imgs[c][pos[sel]] = Cm[n][sel]
+        if fill_pad is not None:
+            ppos = colsz * (n // 8) + (mp // 8) * 8 + n % 8
+            for c in range(8):
+                imgs[c][ppos[mp % 8 == c]] = fill_pad
+    return imgs
+
+
+def unpack_C_images(imgs, M, N):
+    """The read-back un-interleave of the verification loop (src/sextans-host.cpp:264-270)
+    -> column-major C (M x N)."""
+    colsz = _round_up(M, 16)
+    out = np.empty((N, M), dtype=np.float32)
+    m = np.arange(M, dtype=np.int64)
+    for n in range(N):
+        pos = colsz * (n // 8) + (m // 8) * 8 + n % 8
+        for c in range(8):
+            sel = m % 8 == c
+            out[n][sel] = imgs[c][pos[sel]]
+    return out.ravel()
+
+
+def pack_scalars(N, rp_time, alpha, beta):
+    """P_N, alpha_u, beta_u as the host packs them (src/sextans-host.cpp:223-229)."""
+    f = np.array([alpha, beta], dtype=np.float32).view(np.int32)
+    return (int(rp_time) << 16) | int(N), int(f[0]), int(f[1])

@@ -87,6 +87,38 @@ int sxref_edge_list_slots(int M, int K, int nnz, const int *rowptr_csr, const in
     return ptr.empty() ? 0 : ptr.back();
 }
 
+// The complete A side of "Preparing sparse A for FPGA" (src/sextans-host.cpp:117-146):
+// generate_edge_list_for_all_PEs + edge_list_64bit with the shipped constants
+// (src/sextans.h:7-12), from a CSR whose rows hold ascending columns.  Outputs are
+// malloc'ed: ptr (ptr_len ints, unpadded), 8 channel images of image_len 64-bit words.
+// Lets the tests feed the engine's image path (sx_sextans_invoke) the reference's own images.
+int sxref_build_images(int M, int K, int nnz, const int *rowptr_csr, const int *colidx_csr,
+                       const float *val_csr, int **ptr, int *ptr_len, unsigned long **images /*[8]*/,
+                       long *image_len) {
+    std::vector<int> cptr(K + 1, 0), ridx(nnz);
+    std::vector<float> cval(nnz);
+    for (int j = 0; j < nnz; ++j) cptr[colidx_csr[j] + 1]++;
+    for (int k = 0; k < K; ++k) cptr[k + 1] += cptr[k];
+    std::vector<int> fill(K, 0);
+    for (int i = 0; i < M; ++i)
+        for (int j = rowptr_csr[i]; j < rowptr_csr[i + 1]; ++j) {
+            int k = colidx_csr[j];
+            int pos = cptr[k] + fill[k]++;
+            ridx[pos] = i;
+            cval[pos] = val_csr[j];
+        }
+    std::vector<std::vector<edge>> pes;
+    std::vector<int> eptr;
+    generate_edge_list_for_all_PEs(cptr, ridx, cval, 8 * 8, M, K, 4096, pes, eptr, 10);
+    std::vector<std::vector<unsigned long, tapa::aligned_allocator<unsigned long>>> img(8);
+    edge_list_64bit(pes, eptr, img, 8);
+    *ptr = dup(eptr);
+    *ptr_len = (int)eptr.size();
+    *image_len = (long)img[0].size();
+    for (int c = 0; c < 8; ++c) images[c] = dup(img[c]);
+    return eptr.empty() ? 0 : eptr.back();
+}
+
 void sxref_free(void *p) { std::free(p); }
 
 }  // extern "C"

@@ -17,7 +17,8 @@ import os
 import numpy as np
 
 __all__ = ["Engine", "SextansError", "lib", "library_path", "load_mtx", "partition_rows",
-           "pinned_empty", "STRICT", "FAST"]
+           "pinned_empty", "STRICT", "FAST", "images_decode_A", "images_decode_B",
+           "images_decode_C", "images_encode_C"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -26,11 +27,16 @@ SX_F32, SX_F64 = 0, 1
 STRICT, FAST = 0, 1
 OPT_ARITH, OPT_SPLIT_ROW_NNZ, OPT_KERNEL, OPT_ITEM_NNZ, OPT_ZEROCOPY_BYTES, OPT_TILE_MIN_ROWS = 0, 1, 2, 3, 4, 5
 (INFO_LAUNCHES, INFO_M, INFO_K, INFO_NNZ, INFO_DTYPE, INFO_SPLIT_ROWS, INFO_LAST_KERNEL, INFO_LD,
- INFO_ITEMS, INFO_ITEM_NNZ, INFO_HOST_PATH, INFO_TILE_NNZ, INFO_TILE_SLOTS, INFO_REST_NNZ) = range(14)
+ INFO_ITEMS, INFO_ITEM_NNZ, INFO_HOST_PATH, INFO_TILE_NNZ, INFO_TILE_SLOTS, INFO_REST_NNZ,
+ INFO_UPLOAD_SERIAL) = range(15)
 
 _PI32 = C.POINTER(C.c_int32)
 _PF = C.POINTER(C.c_float)
 _PD = C.POINTER(C.c_double)
+_PU64 = C.POINTER(C.c_uint64)
+_A8 = _PU64 * 8   # const uint64_t *const edge_list_ch[8]
+_F4 = _PF * 4     # const float *const mat_B_ch[4]
+_F8 = _PF * 8     # (const) float *const mat_C_ch[8]
 
 
 class SextansError(RuntimeError):
@@ -97,6 +103,16 @@ def lib():
         "sx_load_mtx_f64": ([C.c_char_p, C.POINTER(i), C.POINTER(i), C.POINTER(i64),
                              C.POINTER(_PI32), C.POINTER(_PI32), C.POINTER(_PD)], i),
         "sx_free": ([vp], None),
+        "sx_sextans_invoke": ([vp, _PI32, _A8, _F4, _F8, _F8, i, i, i, i, i, i, i, _PD], i),
+        "sx_sextans_last_kernel_ns": ([], C.c_double),
+        "sx_images_A_words": ([i], i64),
+        "sx_images_B_floats": ([i, i], i64),
+        "sx_images_C_floats": ([i, i], i64),
+        "sx_images_decode_A": ([_PI32, _A8, i, i, i, i, C.POINTER(i64), C.POINTER(_PI32),
+                                C.POINTER(_PI32), C.POINTER(_PF)], i),
+        "sx_images_decode_B": ([_F4, i, i, _PF], i),
+        "sx_images_decode_C": ([_F8, i, i, _PF], i),
+        "sx_images_encode_C": ([_PF, i, i, C.c_float, C.c_float, _F8, _F8], i),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)
@@ -156,6 +172,79 @@ def partition_rows(rowptr, parts):
     _check(lib().sx_partition_rows(rowptr.size - 1, rowptr.ctypes.data_as(_PI32), parts,
                                    bounds.ctypes.data_as(_PI32)))
     return bounds
+
+
+# ---- FPGA channel images (the literal Sextans(...) argument list) ----------------------
+def _chan(arrs, n, ctype, dtype):
+    """n contiguous channel arrays -> (ctypes pointer array, keep-alive list)."""
+    if len(arrs) != n:
+        raise ValueError(f"{n} channel images expected, got {len(arrs)}")
+    keep = []
+    for a in arrs:
+        if not (isinstance(a, np.ndarray) and a.dtype == dtype and a.flags.c_contiguous):
+            raise ValueError(f"channel images must be contiguous {np.dtype(dtype).name} arrays")
+        keep.append(a)
+    return (C.POINTER(ctype) * n)(*[a.ctypes.data_as(C.POINTER(ctype)) for a in keep]), keep
+
+
+def images_decode_A(ptr, images, M, K):
+    """Edge-list images (src/sparse_helper.h:345-473) -> CSR (rowptr, colidx, val)."""
+    ptr = np.ascontiguousarray(ptr, dtype=np.int32)
+    num_ite, num_a_len = ptr.size - 1, int(ptr[-1])
+    a, keep = _chan(images, 8, C.c_uint64, np.uint64)
+    for im in keep:
+        if im.size < 8 * num_a_len:
+            raise ValueError("A channel image shorter than 8 * NUM_A_LEN words")
+    nnz = C.c_int64()
+    rp, ci, v = _PI32(), _PI32(), _PF()
+    L = lib()
+    _check(L.sx_images_decode_A(ptr.ctypes.data_as(_PI32), a, num_ite, num_a_len, M, K, C.byref(nnz),
+                                C.byref(rp), C.byref(ci), C.byref(v)))
+    try:
+        n = nnz.value
+        rowptr = np.ctypeslib.as_array(rp, shape=(M + 1,)).copy()
+        colidx = np.ctypeslib.as_array(ci, shape=(max(n, 1),))[:n].copy()
+        val = np.ctypeslib.as_array(v, shape=(max(n, 1),))[:n].copy()
+    finally:
+        L.sx_free(rp), L.sx_free(ci), L.sx_free(v)
+    return rowptr, colidx, val
+
+
+def _need(images, elems, what):
+    for im in images:
+        if im.size < elems:
+            raise ValueError(f"{what} channel image shorter than {elems} floats")
+
+
+def images_decode_B(images, K, N):
+    """4 B channel images (src/sextans-host.cpp:158-171) -> column-major K x roundup(N,8)."""
+    L = lib()
+    b, keep = _chan(images, 4, C.c_float, np.float32)
+    _need(keep, L.sx_images_B_floats(K, N), "B")
+    out = np.empty(K * ((N + 7) // 8 * 8), dtype=np.float32)
+    _check(L.sx_images_decode_B(b, K, N, out.ctypes.data_as(_PF)))
+    return out
+
+
+def images_decode_C(images, M, N):
+    """8 C channel images (src/sextans-host.cpp:181-195) -> column-major M x roundup(N,8)."""
+    L = lib()
+    c, keep = _chan(images, 8, C.c_float, np.float32)
+    _need(keep, L.sx_images_C_floats(M, N), "C")
+    out = np.empty(M * ((N + 7) // 8 * 8), dtype=np.float32)
+    _check(L.sx_images_decode_C(c, M, N, out.ctypes.data_as(_PF)))
+    return out
+
+
+def images_encode_C(Cm, M, N, alpha, beta, images_in, images_out):
+    """Column-major C -> the 8 output images, pad rows as the FPGA writes them."""
+    L = lib()
+    Cm = np.ascontiguousarray(Cm, dtype=np.float32)
+    assert Cm.size == M * ((N + 7) // 8 * 8)
+    ci, keep_i = _chan(images_in, 8, C.c_float, np.float32)
+    co, keep_o = _chan(images_out, 8, C.c_float, np.float32)
+    _need(keep_i + keep_o, L.sx_images_C_floats(M, N), "C")
+    _check(L.sx_images_encode_C(Cm.ctypes.data_as(_PF), M, N, alpha, beta, ci, co))
 
 
 class _Pinned:
@@ -275,6 +364,31 @@ class Engine:
         ns = C.c_double()
         _check(getattr(self._L, f"sx_spmm_{suf}")(self._ctx, N, ct(alpha), _host_ptr(B), ct(beta),
                                                   _host_ptr(C_inout), rp_time, C.byref(ns)))
+        return ns.value
+
+    def sextans_invoke(self, ptr, A_images, B_images, Cin_images, Cout_images, M, K, P_N,
+                       alpha_u, beta_u):
+        """The reference's device call with its own arguments (src/sextans.h:20-26):
+        FPGA channel images in, C images out (written in place into ``Cout_images``).
+        Returns the kernel time in ns like ``tapa::invoke``."""
+        L = self._L
+        ptr = np.ascontiguousarray(ptr, dtype=np.int32)
+        num_ite, num_a_len = ptr.size - 1, int(ptr[-1])
+        N = P_N & 0xFFFF
+        a, ka = _chan(A_images, 8, C.c_uint64, np.uint64)
+        b, kb = _chan(B_images, 4, C.c_float, np.float32)
+        ci, kci = _chan(Cin_images, 8, C.c_float, np.float32)
+        co, kco = _chan(Cout_images, 8, C.c_float, np.float32)
+        for im in ka:
+            if im.size < L.sx_images_A_words(num_a_len):
+                raise ValueError("A channel image shorter than 8 * NUM_A_LEN words")
+        _need(kb, L.sx_images_B_floats(K, N), "B")
+        _need(kci + kco, L.sx_images_C_floats(M, N), "C")
+        ns = C.c_double()
+        _check(L.sx_sextans_invoke(self._ctx, ptr.ctypes.data_as(_PI32), a, b, ci, co, num_ite,
+                                   num_a_len, M, K, P_N, alpha_u, beta_u, C.byref(ns)))
+        self.dtype, self.M, self.K = np.dtype(np.float32), M, K
+        self.nnz = self.info(INFO_NNZ)
         return ns.value
 
     # -- staged ------------------------------------------------------------------------

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -24,6 +25,7 @@
 namespace {
 
 thread_local std::string g_err;
+std::atomic<int64_t> g_upload_serial{0};  // process-wide: every successful upload gets a new number
 
 int fail(int status, const char *fmt, ...) {
     char buf[512];
@@ -130,6 +132,7 @@ struct sx_ctx {
 
     int64_t launches = 0;
     int last_kernel = 0;
+    int64_t upload_serial = 0;  // g_upload_serial value of the matrix held (0: none)
 };
 
 namespace {
@@ -675,6 +678,7 @@ int upload_csr(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rowptr, cons
         if ((uint32_t)colidx[j] >= (uint32_t)K)
             return fail(SX_ERR_INVALID, "column index %d out of range at nonzero %lld", colidx[j], (long long)j);
     c->has_A = false;
+    c->upload_serial = 0;
     if ((rc = c->rowptr.ensure(((size_t)M + 1) * 4))) return rc;
     if ((rc = c->colidx.ensure((size_t)nnz * 4 + 16))) return rc;  // +16: TMA reads whole 16-byte units
     if ((rc = c->val.ensure((size_t)nnz * sizeof(T) + 32))) return rc;
@@ -695,6 +699,7 @@ int upload_csr(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rowptr, cons
     if ((rc = build_window_blocks(c, M, rowptr, colidx))) return rc;
     if ((rc = maybe_build_panels<T>(c, M, K, nnz, rowptr, colidx, val))) return rc;
     c->has_A = true;
+    c->upload_serial = ++g_upload_serial;
     return SX_OK;
 }
 
@@ -895,8 +900,9 @@ int spmm_host(sx_ctx *c, int N, T alpha, const T *B, T beta, T *C, int rp_time, 
 // =====================================================================================
 extern "C" {
 
-// lets the host-only translation unit (sx_host.cpp) report through sx_last_error()
+// lets the host-only translation units (sx_host.cpp, sx_images.cpp) report through sx_last_error()
 void sx_internal_set_error(const char *msg) { g_err = msg ? msg : ""; }
+void sx_internal_images_forget(sx_ctx *ctx);  // sx_images.cpp: per-context state of the image path
 
 int sx_abi_version(void) { return SX_ABI_VERSION; }
 
@@ -960,6 +966,7 @@ int sx_create(int device, sx_ctx **out) {
 int sx_destroy(sx_ctx *c) {
     if (!c) return SX_OK;
     cudaSetDevice(c->device);
+    sx_internal_images_forget(c);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (DevBuf *b : {&c->rowptr, &c->colidx, &c->val, &c->split_row, &c->split_seg_ptr, &c->seg_begin,
                       &c->seg_end, &c->partial, &c->sync_words, &c->wblocks, &c->B, &c->Cin, &c->Cout, &c->stage})
@@ -1038,6 +1045,7 @@ int sx_get_info(sx_ctx *c, int what, int64_t *value) {
         case SX_INFO_HOST_PATH: *value = c->last_path; return SX_OK;
         case SX_INFO_ITEMS: *value = c->last_plan ? c->last_plan->nitems : 0; return SX_OK;
         case SX_INFO_ITEM_NNZ: *value = c->last_plan ? c->last_plan->budget : 0; return SX_OK;
+        case SX_INFO_UPLOAD_SERIAL: *value = c->has_A ? c->upload_serial : 0; return SX_OK;
         default: return fail(SX_ERR_INVALID, "unknown info id %d", what);
     }
 }

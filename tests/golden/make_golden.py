@@ -14,6 +14,10 @@ Outputs (committed):
   golden.json              sizes, row-length stats, sha256 of the reference CSR and of
                            the reference C for the SuiteSparse runs, known answers
   spmm_small.npz           full reference C for small seeded cases, with their inputs
+  images_small.npz         the reference's FPGA channel images (generate_edge_list_for_all_PEs
+                           + edge_list_64bit, src/sparse_helper.h:345-473) of small seeded
+                           matrices, with the CSR they were made from
+                           (`make_golden.py --images-only` rewrites just this file)
 """
 import json
 import lzma
@@ -33,8 +37,33 @@ from helpers import SMALL_MTX, SUITESPARSE, perturbed_inputs, random_csr, random
 REF = "/root/reference"
 
 
+IMAGE_SPECS = [  # (tag, M, K, avg nnz/row, long_row)
+    ("p", 70, 5000, 4, None),     # two column windows
+    ("q", 130, 64, 7, 60),        # more rows than PEs, one dense row
+    ("r", 3, 9000, 2, None),      # fewer rows than PEs, three windows
+    ("s", 65, 4096, 0, None),     # no nonzeros at all
+]
+
+
+def write_images():
+    out = {}
+    for i, (tag, M, K, avg, long_row) in enumerate(IMAGE_SPECS):
+        rp, ci, v = random_csr(M, K, avg, 200 + i, np.float32, long_row=long_row)
+        ptr, imgs, num_a_len = oracle.ref_build_images(M, K, rp, ci, v)
+        out[tag + "_dims"] = np.array([M, K, num_a_len], dtype=np.int64)
+        out[tag + "_ptr"] = ptr
+        for c in range(8):
+            out[f"{tag}_A{c}"] = imgs[c]
+        for k, a in (("rowptr", rp), ("colidx", ci), ("val", v)):
+            out[f"{tag}_{k}"] = a
+    np.savez_compressed(os.path.join(HERE, "images_small.npz"), **out)
+
+
 def main():
     assert oracle.ref() is not None, "build oracle/_ref first (make -C oracle)"
+    if "--images-only" in sys.argv:
+        write_images()
+        return
     gold = {"generator": "tests/golden/make_golden.py", "source": "reference cpu_spmm_CSR "
             "(src/sparse_helper.h:262-290) via oracle/_ref/libsextans_ref.so", "suitesparse": {}}
 
@@ -103,6 +132,8 @@ def main():
             cases[f"{tag}_{k}"] = a
     np.savez_compressed(os.path.join(HERE, "spmm_small.npz"), **cases)
     gold["small_cases"] = [s[0] for s in specs]
+    write_images()
+    gold["image_cases"] = [s[0] for s in IMAGE_SPECS]
 
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(gold, f, indent=1, sort_keys=True)
