@@ -65,6 +65,7 @@ def parse():
     p.add_argument("--split", type=int, default=-1, help="SX_OPT_SPLIT_ROW_NNZ (-1 default)")
     p.add_argument("--band", type=int, default=2000, help="fem workload: couplings reach +-band nodes")
     p.add_argument("--tiles", type=int, default=0, help="SX_OPT_TILE_MIN_ROWS (fp64 dense-tile tensor-core variant; 0 off)")
+    p.add_argument("--col-window-rows", type=int, default=0, help="SX_OPT_COL_WINDOW_ROWS (column-window passes keeping a window of B in L2; 0 off, -1 = 32 MiB of B per window)")
     p.add_argument("--ref-threads", type=int, default=1, help="--impl reference: threads of the CPU path (1 = as the reference runs it; -1 = all cores, OpenMP port)")
     p.add_argument("--peer-bytes", type=int, default=8 << 20, help="N>1: B images up to this size travel by peer copy instead of NCCL")
     p.add_argument("--peer-mode", default="fused", choices=["fused", "memops"])
@@ -329,6 +330,10 @@ def run_native(args):
         e.set_option(sx.OPT_KERNEL, args.kernel)
         e.set_option(sx.OPT_ITEM_NNZ, args.item_nnz)
         e.set_option(sx.OPT_TILE_MIN_ROWS, args.tiles)
+        cw = args.col_window_rows
+        if cw < 0:  # a window of B of ~32 MiB: well inside one L2 partition
+            cw = max(1, (32 << 20) // (ld * s))
+        e.set_option(sx.OPT_COL_WINDOW_ROWS, cw)
         if args.split >= 0:
             e.set_option(sx.OPT_SPLIT_ROW_NNZ, args.split)
         e.upload_csr(M, K, w["rowptr"], w["colidx"], w["val"])
@@ -516,7 +521,8 @@ def run_native(args):
         tiles_note = ""
     kernel_name = ({1: "spmm_rows_kernel (+segments/finalize)", 2: "spmm_staged_kernel", 3: "spmm_window_kernel", 4: "spmm_panels_dmma_kernel"}.get(lk // 10000, "?")
                    + f" <G={lk % 10000 // 100}, VPL={lk % 100 // 10}, {'fast' if lk % 10 else 'strict'}>"
-                   + (f", {eng.info(sx.INFO_ITEMS)} items of <= {eng.info(sx.INFO_ITEM_NNZ)} nnz, {eng.info(sx.INFO_SPLIT_ROWS)} split rows" if lk // 10000 == 2 else "") + tiles_note)
+                   if lk // 10000 != 5 else f"spmm_staged_kernel<WIN>, {lk % 10000} column-window passes of {cw} columns each") + (
+                   (f", {eng.info(sx.INFO_ITEMS)} items of <= {eng.info(sx.INFO_ITEM_NNZ)} nnz, {eng.info(sx.INFO_SPLIT_ROWS)} split rows" if lk // 10000 == 2 else "") + tiles_note)
     host_path = "zero-copy kernels over PCIe (no memcpy)" if eng.info(sx.INFO_HOST_PATH) == 1 else "cudaMemcpyAsync + layout kernels"
     if rank == 0:
         line = {

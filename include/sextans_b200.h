@@ -92,7 +92,20 @@ enum sx_option {
      * the rest of A stays CSR and is added afterwards.  Summation order then differs from
      * cpu_spmm_CSR (fp64 rounding-level differences), and an explicit zero of a tile
      * times a non-finite B entry yields NaN. */
-    SX_OPT_TILE_MIN_ROWS = 5
+    SX_OPT_TILE_MIN_ROWS = 5,
+    /* column windows (the reference's K windows, src/sextans.h:11, src/sextans.cpp:57,337-381,
+     * with L2 in the role of the on-chip B buffer); read by the NEXT sx_upload_csr_*.
+     * 0 (default) off.  W >= 1: A is cut into windows of W consecutive columns and one SpMM
+     * becomes ceil(K/W) passes of the TMA-staged kernel, window by window, a row's running
+     * sum travelling through a device buffer, so that the B rows a pass gathers -- W rows,
+     * W * ld * sizeof(T) bytes -- stay resident in the 126 MB L2 instead of coming from HBM
+     * once per nonzero.  Worth it when B is much larger than L2's reach and rows hold many
+     * nonzeros per window (power-law / wide-band matrices); pick W so that a window of B is
+     * ~32 MiB.  Strict mode stays bit-identical to cpu_spmm_CSR for rows stored in ascending
+     * column order (the loader's order); rows stored otherwise are summed window by window
+     * (rounding-level differences).  Ignored when SX_OPT_TILE_MIN_ROWS is in effect or when
+     * K <= W. */
+    SX_OPT_COL_WINDOW_ROWS = 6
 };
 
 enum sx_info {
@@ -110,8 +123,9 @@ enum sx_info {
     SX_INFO_TILE_NNZ = 11,   /* nonzeros held in dense tiles */
     SX_INFO_TILE_SLOTS = 12, /* tile slots incl. explicit zeros (fill = TILE_NNZ / TILE_SLOTS) */
     SX_INFO_REST_NNZ = 13,   /* nonzeros left to the CSR kernels */
-    SX_INFO_UPLOAD_SERIAL = 14 /* process-wide serial number of the matrix this context holds
-                                * (every successful sx_upload_csr_* draws a new one; 0: none) */
+    SX_INFO_UPLOAD_SERIAL = 14, /* process-wide serial number of the matrix this context holds
+                                 * (every successful sx_upload_csr_* draws a new one; 0: none) */
+    SX_INFO_COL_WINDOWS = 15    /* column windows in use (0: the matrix is not windowed) */
 };
 
 /* ---- library ------------------------------------------------------------- */
@@ -223,6 +237,17 @@ int sx_host_free(void *ptr);
 /* Contiguous row blocks with ~equal nonzeros: bounds[0]=0 <= ... <= bounds[parts]=M.
  * The GPU-count analogue of the reference's row -> PE map (src/sparse_helper.h:370). */
 int sx_partition_rows(int M, const int32_t *rowptr, int parts, int32_t *bounds);
+/* Column windows of W = window_rows columns (what SX_OPT_COL_WINDOW_ROWS makes of A; host
+ * only): *nwin = ceil(K/W) windows, each a CSR of its own over all M rows.
+ *   win_rowptr  nwin x (M+1): row pointers of window w at [w*(M+1), (w+1)*(M+1)), from 0
+ *   win_base    nwin + 1: window w's entries are order[win_base[w] .. win_base[w+1])
+ *   order       nnz: position in the caller's colidx/val of every entry, window-major;
+ *               inside (window, row) the stored order is kept
+ *   ascending   (may be NULL) 1 if every row is stored in non-decreasing column order
+ * Arrays are malloc'ed; release each with sx_free. */
+int sx_split_col_windows(int M, int K, const int32_t *rowptr, const int32_t *colidx, int window_rows,
+                         int *nwin, int32_t **win_rowptr, int64_t **win_base, int32_t **order,
+                         int *ascending);
 /* Matrix Market -> CSR with the reference loader's semantics (symmetric expansion,
  * +0.0 entries dropped, 1-based -> 0-based, columns ascending within a row,
  * duplicates kept).  Arrays are malloc'ed; release each with sx_free. */

@@ -17,6 +17,7 @@ import os
 import numpy as np
 
 __all__ = ["Engine", "SextansError", "lib", "library_path", "load_mtx", "partition_rows",
+           "split_col_windows",
            "pinned_empty", "STRICT", "FAST", "images_decode_A", "images_decode_B",
            "images_decode_C", "images_encode_C"]
 
@@ -25,10 +26,11 @@ _LIB = None
 
 SX_F32, SX_F64 = 0, 1
 STRICT, FAST = 0, 1
-OPT_ARITH, OPT_SPLIT_ROW_NNZ, OPT_KERNEL, OPT_ITEM_NNZ, OPT_ZEROCOPY_BYTES, OPT_TILE_MIN_ROWS = 0, 1, 2, 3, 4, 5
+(OPT_ARITH, OPT_SPLIT_ROW_NNZ, OPT_KERNEL, OPT_ITEM_NNZ, OPT_ZEROCOPY_BYTES, OPT_TILE_MIN_ROWS,
+ OPT_COL_WINDOW_ROWS) = range(7)
 (INFO_LAUNCHES, INFO_M, INFO_K, INFO_NNZ, INFO_DTYPE, INFO_SPLIT_ROWS, INFO_LAST_KERNEL, INFO_LD,
  INFO_ITEMS, INFO_ITEM_NNZ, INFO_HOST_PATH, INFO_TILE_NNZ, INFO_TILE_SLOTS, INFO_REST_NNZ,
- INFO_UPLOAD_SERIAL) = range(15)
+ INFO_UPLOAD_SERIAL, INFO_COL_WINDOWS) = range(16)
 
 _PI32 = C.POINTER(C.c_int32)
 _PF = C.POINTER(C.c_float)
@@ -102,6 +104,8 @@ def lib():
                              C.POINTER(_PI32), C.POINTER(_PI32), C.POINTER(_PF)], i),
         "sx_load_mtx_f64": ([C.c_char_p, C.POINTER(i), C.POINTER(i), C.POINTER(i64),
                              C.POINTER(_PI32), C.POINTER(_PI32), C.POINTER(_PD)], i),
+        "sx_split_col_windows": ([i, i, _PI32, _PI32, i, C.POINTER(i), C.POINTER(_PI32),
+                                  C.POINTER(C.POINTER(i64)), C.POINTER(_PI32), C.POINTER(i)], i),
         "sx_free": ([vp], None),
         "sx_sextans_invoke": ([vp, _PI32, _A8, _F4, _F8, _F8, i, i, i, i, i, i, i, _PD], i),
         "sx_sextans_last_kernel_ns": ([], C.c_double),
@@ -172,6 +176,28 @@ def partition_rows(rowptr, parts):
     _check(lib().sx_partition_rows(rowptr.size - 1, rowptr.ctypes.data_as(_PI32), parts,
                                    bounds.ctypes.data_as(_PI32)))
     return bounds
+
+
+def split_col_windows(M, K, rowptr, colidx, window_rows):
+    """Column windows of ``window_rows`` columns (sx_split_col_windows) ->
+    (win_rowptr [nwin, M+1], win_base [nwin+1], order [nnz], ascending)."""
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+    colidx = np.ascontiguousarray(colidx, dtype=np.int32)
+    nwin, asc = C.c_int(), C.c_int()
+    wrp, order, base = _PI32(), _PI32(), C.POINTER(C.c_int64)()
+    L = lib()
+    _check(L.sx_split_col_windows(M, K, rowptr.ctypes.data_as(_PI32), colidx.ctypes.data_as(_PI32),
+                                  window_rows, C.byref(nwin), C.byref(wrp), C.byref(base),
+                                  C.byref(order), C.byref(asc)))
+    try:
+        n = int(rowptr[M])
+        w = nwin.value
+        win_rowptr = np.ctypeslib.as_array(wrp, shape=(w * (M + 1),)).reshape(w, M + 1).copy()
+        win_base = np.ctypeslib.as_array(base, shape=(w + 1,)).copy()
+        ordr = np.ctypeslib.as_array(order, shape=(max(n, 1),))[:n].copy()
+    finally:
+        L.sx_free(wrp), L.sx_free(base), L.sx_free(order)
+    return win_rowptr, win_base, ordr, bool(asc.value)
 
 
 # ---- FPGA channel images (the literal Sextans(...) argument list) ----------------------

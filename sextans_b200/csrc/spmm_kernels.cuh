@@ -270,14 +270,29 @@ template <int U> __device__ __forceinline__ void lds_vec(const double *p, double
     }
 }
 
-template <typename T, int G, int VPL, bool STRICT>
+//
+// WIN = true is the column-window pass (sx_api.cu: spmm_windows; the reference's K windows,
+// src/sextans.cpp:57,337-381, with L2 in the role of the on-chip B buffer): A has been cut
+// into windows of W consecutive columns so that the B rows one pass gathers (W * N * s
+// bytes) stay L2-resident, and a row's running sum travels from pass to pass through the
+// row-major buffer P (leading dimension = C's).  wflags bit 0 (SX_WIN_INIT): the
+// accumulator of a row starts from P[row] instead of 0; bit 1 (SX_WIN_RAW): the row's raw
+// sum is stored to P[row] instead of the epilogue to C_out.  First window: RAW; middle:
+// INIT|RAW; last: INIT.  The chain of additions of a row is the same as in one pass
+// (windows ascend, columns ascend inside a window), so strict mode stays bit-identical.
+// P[row + 1] is fetched when row opens, like C_in, so its latency hides behind the row.
+constexpr int SX_WIN_INIT = 1, SX_WIN_RAW = 2;
+
+template <typename T, int G, int VPL, bool STRICT, bool WIN = false>
 __global__ void __launch_bounds__(256, (VPL > 1 ? 2 : (sizeof(T) == 8 ? 3 : 4)))
 spmm_staged_kernel(const int nitems, const int4 *__restrict__ items, const int ts,
                    const int *__restrict__ rowptr, const int *__restrict__ colidx,
                    const T *__restrict__ val, const T *__restrict__ B, const uint32_t ldbv, const T *Cin,
                    T *Cout, const uint32_t ldcv, T *__restrict__ partial, const uint32_t ldpv,
-                   const T alpha, const T beta, const int nvec) {
+                   const T alpha, const T beta, const int nvec, T *P, const int wflags) {
     using V = typename VecOf<T>::type;
+    const bool w_init = WIN && (wflags & SX_WIN_INIT);
+    const bool w_raw = WIN && (wflags & SX_WIN_RAW);
     constexpr int U = (G < 8 ? G : 8) / (VPL > 2 ? 4 : VPL);  // gathers per batch per lane
     constexpr int GPB = 256 / G;                               // lane groups per block
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -326,18 +341,29 @@ spmm_staged_kernel(const int nitems, const int4 *__restrict__ items, const int t
     int rend = piece ? -1 : __ldg(rowptr + r + 1) - jal;  // in stream coordinates
     const V *Bv = reinterpret_cast<const V *>(B) + lg;
     const V *Cv = reinterpret_cast<const V *>(Cin) + lg;
-    V acc[VPL], cin[VPL];
+    V *Pv = reinterpret_cast<V *>(P) + lg;  // dereferenced in window passes only
+    V acc[VPL], cin[VPL], pin[VPL];          // pin: next row's running sum (window passes)
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
         vzero(acc[v]);
         vzero(cin[v]);
-        if (!piece && lg + v * G < nvec) cin[v] = ld_once(Cv + (size_t)r * ldcv + v * G, pol);
+        vzero(pin[v]);
+        if (!piece && lg + v * G < nvec) {
+            if (!w_raw) cin[v] = ld_once(Cv + (size_t)r * ldcv + v * G, pol);
+            if (w_init) {
+                acc[v] = ld_once(Pv + (size_t)r * ldcv + v * G, pol);
+                if (r + 1 < re) pin[v] = ld_once(Pv + (size_t)(r + 1) * ldcv + v * G, pol);
+            }
+        }
     }
     auto close_row = [&]() {
         V *cout = reinterpret_cast<V *>(Cout) + (size_t)r * ldcv + lg;
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
-            if (lg + v * G < nvec) st_once(cout + v * G, vaxpby<STRICT>(alpha, acc[v], beta, cin[v]), pol);
+            if (lg + v * G < nvec) {
+                if (w_raw) st_once(Pv + (size_t)r * ldcv + v * G, acc[v], pol);
+                else st_once(cout + v * G, vaxpby<STRICT>(alpha, acc[v], beta, cin[v]), pol);
+            }
             vzero(acc[v]);
         }
         ++r;
@@ -345,7 +371,13 @@ spmm_staged_kernel(const int nitems, const int4 *__restrict__ items, const int t
             rend = __ldg(rowptr + r + 1) - jal;
 #pragma unroll
             for (int v = 0; v < VPL; ++v)
-                if (lg + v * G < nvec) cin[v] = ld_once(Cv + (size_t)r * ldcv + v * G, pol);
+                if (lg + v * G < nvec) {
+                    if (!w_raw) cin[v] = ld_once(Cv + (size_t)r * ldcv + v * G, pol);
+                    if (w_init) {
+                        acc[v] = pin[v];
+                        if (r + 1 < re) pin[v] = ld_once(Pv + (size_t)(r + 1) * ldcv + v * G, pol);
+                    }
+                }
         } else {
             rend = -1;
         }
@@ -653,12 +685,14 @@ spmm_segments_kernel(const int nseg, const int *__restrict__ seg_begin,
 }
 
 // Sum a split row's segment partials in segment order and apply the epilogue.
-template <typename T, int G, int VPL, bool STRICT>
+// WIN: the column-window pass of a split row -- the pieces are added to the running sum
+// in P (SX_WIN_INIT) and the result goes back to P (SX_WIN_RAW) or through the epilogue.
+template <typename T, int G, int VPL, bool STRICT, bool WIN = false>
 __global__ void __launch_bounds__(256)
 spmm_finalize_kernel(const int nsplit, const int *__restrict__ split_row,
                      const int *__restrict__ split_seg_ptr, const T *__restrict__ partial,
                      const int64_t ldp, const T *Cin, T *Cout, const int64_t ldc, const T alpha,
-                     const T beta, const int nvec) {
+                     const T beta, const int nvec, T *P, const int wflags) {
     using V = typename VecOf<T>::type;
     const int lg = threadIdx.x & (G - 1);
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
@@ -667,17 +701,20 @@ spmm_finalize_kernel(const int nsplit, const int *__restrict__ split_row,
     const int s0 = __ldg(split_seg_ptr + i), s1 = __ldg(split_seg_ptr + i + 1);
     const V *cin = reinterpret_cast<const V *>(Cin + row * ldc);
     V *cout = reinterpret_cast<V *>(Cout + row * ldc);
+    V *prow = reinterpret_cast<V *>(P + row * ldc);  // dereferenced in window passes only
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
         const int vi = lg + v * G;
         if (vi >= nvec) continue;
         V acc;
         vzero(acc);
+        if (WIN && (wflags & SX_WIN_INIT)) acc = prow[vi];
         for (int s = s0; s < s1; ++s) {
             const V p = reinterpret_cast<const V *>(partial + (int64_t)s * ldp)[vi];
             vadd(acc, p);
         }
-        cout[vi] = vaxpby<STRICT>(alpha, acc, beta, cin[vi]);
+        if (WIN && (wflags & SX_WIN_RAW)) prow[vi] = acc;
+        else cout[vi] = vaxpby<STRICT>(alpha, acc, beta, cin[vi]);
     }
 }
 

@@ -112,6 +112,17 @@ struct sx_ctx {
     int64_t tile_steps = 0, tile_nnz = 0, rest_nnz = 0;
     DevBuf step_ptr, tcols, tvals;
     sx_ctx *rest = nullptr;  // child context holding A_rest; shares this context's stream
+    // column windows (SX_OPT_COL_WINDOW_ROWS > 0 at upload): one child context per window,
+    // each holding that window's CSR; psum carries a row's running sum from pass to pass
+    int col_window_rows = 0;
+    std::vector<sx_ctx *> wins;
+    bool wins_ascending = true;
+    DevBuf psum;
+    // set on a window child by spmm_windows for the duration of one pass
+    bool win_mode = false;
+    int win_flags = 0;
+    void *win_P = nullptr;  // parent's psum, same leading dimension as C
+    int win_col0 = 0;       // first column of the column panel being launched
 
     // dense operands (row-major, ld elements per row)
     int N = 0;
@@ -200,6 +211,7 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
     const bool window_auto = window_ok && (window_cap >= 2 || (int64_t)c->nwblocks <= (int64_t)4 * c->sm_count * window_cap);
     int variant = c->kernel != 0 ? c->kernel : (window_auto ? 3 : (sub_wave ? 1 : 2));
     if (variant == 3 && !window_ok) variant = sub_wave ? 1 : 2;
+    if (c->win_mode) variant = 2;  // a column-window pass: only the staged kernel carries running sums
     if constexpr (G <= 16 && VPL == 1) {
         if (variant == 3) {
             constexpr int E = sx::VecOf<T>::E;
@@ -237,7 +249,7 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
             const unsigned gfin = (unsigned)(((int64_t)c->nsplit + rows_per_block - 1) / rows_per_block);
             sx::spmm_finalize_kernel<T, G, VPL, STRICT><<<gfin, threads, 0, c->stream>>>(
                 c->nsplit, (const int *)c->split_row.p, (const int *)c->split_seg_ptr.p,
-                (const T *)c->partial.p, ldp, dCin, dCout, ldc, alpha, beta, nvec);
+                (const T *)c->partial.p, ldp, dCin, dCout, ldc, alpha, beta, nvec, (T *)nullptr, 0);
             c->launches += 2;
         }
     } else if (c->M > 0) {
@@ -250,20 +262,24 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
         if (p->npieces > 0 && (rc = c->partial.ensure((size_t)p->npieces * ldp * sizeof(T)))) return rc;
         const int ts = pick_tile<T, G>(U);
         const size_t smem = (size_t)rows_per_block * (16 + 2 * (size_t)ts * (sizeof(T) + 4));
-        auto kern = sx::spmm_staged_kernel<T, G, VPL, STRICT>;
+        // a column-window pass runs the WIN instantiation with the parent's running sums
+        auto kern = c->win_mode ? sx::spmm_staged_kernel<T, G, VPL, STRICT, true> : sx::spmm_staged_kernel<T, G, VPL, STRICT, false>;
+        T *P = c->win_mode ? (T *)c->win_P + c->win_col0 : (T *)nullptr;
+        const int wflags = c->win_mode ? c->win_flags : 0;
         if (smem > 48 * 1024)  // only the narrowest fp64 shape (128 lane groups per block) gets there
             SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (unsigned)(((int64_t)p->nitems + rows_per_block - 1) / rows_per_block);
         kern<<<grid, threads, smem, c->stream>>>(
             p->nitems, (const int4 *)p->items.p, ts, (const int *)c->rowptr.p, (const int *)c->colidx.p,
             (const T *)c->val.p, dB, (uint32_t)(ldb / E), dCin, dCout, (uint32_t)(ldc / E), (T *)c->partial.p,
-            (uint32_t)(ldp / E), alpha, beta, nvec);
+            (uint32_t)(ldp / E), alpha, beta, nvec, P, wflags);
         c->launches++;
         if (p->nsplit > 0) {
             const unsigned gfin = (unsigned)(((int64_t)p->nsplit + rows_per_block - 1) / rows_per_block);
-            sx::spmm_finalize_kernel<T, G, VPL, STRICT><<<gfin, threads, 0, c->stream>>>(
+            auto fin = c->win_mode ? sx::spmm_finalize_kernel<T, G, VPL, STRICT, true> : sx::spmm_finalize_kernel<T, G, VPL, STRICT, false>;
+            fin<<<gfin, threads, 0, c->stream>>>(
                 p->nsplit, (const int *)p->split_row.p, (const int *)p->split_ptr.p,
-                (const T *)c->partial.p, ldp, dCin, dCout, ldc, alpha, beta, nvec);
+                (const T *)c->partial.p, ldp, dCin, dCout, ldc, alpha, beta, nvec, P, wflags);
             c->launches++;
         }
     }
@@ -344,6 +360,33 @@ int spmm_tiles<double>(sx_ctx *c, int N, double alpha, const double *dB, int64_t
     return SX_OK;
 }
 
+// Column windows: one pass of the staged kernel per window of W columns, in ascending
+// window order; pass w starts every row from the running sum pass w-1 left in psum and
+// the last pass applies the epilogue.  Stream-ordered like everything else; psum has C's
+// leading dimension so that a column panel of C and its running sums share offsets.
+template <typename T>
+int spmm_windows(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, const T *dCin, T *dCout, int64_t ldc) {
+    int rc = c->psum.ensure(std::max<size_t>((size_t)c->M * (size_t)ldc * sizeof(T), 16));
+    if (rc) return rc;
+    const int nwin = (int)c->wins.size();
+    for (int w = 0; w < nwin; ++w) {
+        sx_ctx *k = c->wins[w];
+        k->stream = c->stream;
+        k->arith = c->arith;
+        k->item_nnz = c->item_nnz;
+        k->win_mode = true;
+        k->win_flags = (w > 0 ? sx::SX_WIN_INIT : 0) | (w + 1 < nwin ? sx::SX_WIN_RAW : 0);
+        k->win_P = c->psum.p;
+        const int64_t before = k->launches;
+        rc = spmm_device<T>(k, N, alpha, dB, ldb, beta, dCin, dCout, ldc);
+        c->launches += k->launches - before;
+        if (rc) return rc;
+    }
+    c->last_plan = nullptr;  // the plans in use belong to the window children
+    c->last_kernel = 50000 + nwin;
+    return SX_OK;
+}
+
 // One SpMM over device-resident row-major operands.  Column counts beyond what one
 // row group covers (4 vectors x 32 lanes) are processed in column panels.
 template <typename T>
@@ -363,6 +406,7 @@ int spmm_device(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, con
     if (c->segments_dirty && (rc = refresh_segments(c))) return rc;
 
     if (c->tile_steps > 0) return spmm_tiles<T>(c, N, alpha, dB, ldb, beta, dCin, dCout, ldc);
+    if (!c->wins.empty()) return spmm_windows<T>(c, N, alpha, dB, ldb, beta, dCin, dCout, ldc);
 
     const int panel_cols = 4 * 32 * E;  // widest shape: G = 32, VPL = 4
     for (int n0 = 0; n0 < N; n0 += panel_cols) {
@@ -370,6 +414,7 @@ int spmm_device(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, con
         const int nvec = (n * (int)sizeof(T) + 15) / 16;
         Shape s;
         if (!pick_shape(nvec, &s)) return fail(SX_ERR_INVALID, "internal: no shape for %d", nvec);
+        c->win_col0 = n0;
         if (c->arith == 0)
             rc = launch_group<T, true>(c, s, n, alpha, dB + n0, ldb, beta, dCin + n0, dCout + n0, ldc);
         else
@@ -545,6 +590,20 @@ int build_window_blocks(sx_ctx *c, int M, const int32_t *rowptr, const int32_t *
     return SX_OK;
 }
 
+void release_child(sx_ctx *r, cudaStream_t stream) {
+    r->stream = stream;
+    drop_plans(r);
+    for (DevBuf *b : {&r->rowptr, &r->colidx, &r->val, &r->split_row, &r->split_seg_ptr, &r->seg_begin,
+                      &r->seg_end, &r->partial, &r->wblocks})
+        b->release();
+    delete r;
+}
+
+void drop_windows(sx_ctx *c) {
+    for (sx_ctx *k : c->wins) release_child(k, c->stream);
+    c->wins.clear();
+}
+
 void drop_tiles(sx_ctx *c) {
     c->npanels = 0;
     c->tile_steps = c->tile_nnz = c->rest_nnz = 0;
@@ -654,6 +713,45 @@ int build_panels(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rowptr, co
     return SX_OK;
 }
 
+// Cut A into column windows of c->col_window_rows columns: one child context per window
+// (sx_split_col_windows does the index work on the host; values and columns are gathered
+// into window-major order here and uploaded window by window).
+template <typename T>
+int maybe_build_windows(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rp, const int32_t *ci, const T *v) {
+    drop_windows(c);
+    const int W = c->col_window_rows;
+    if (W <= 0 || c->tile_steps > 0 || K <= W || M == 0 || nnz == 0) return SX_OK;
+    int nwin = 0, asc = 1;
+    int32_t *wrp = nullptr, *order = nullptr;
+    int64_t *base = nullptr;
+    int rc = sx_split_col_windows(M, K, rp, ci, W, &nwin, &wrp, &base, &order, &asc);
+    if (rc) return rc;
+    std::vector<int32_t> wci;
+    std::vector<T> wv;
+    for (int w = 0; w < nwin && !rc; ++w) {
+        const int64_t n = base[w + 1] - base[w];
+        wci.resize((size_t)std::max<int64_t>(n, 1));
+        wv.resize((size_t)std::max<int64_t>(n, 1));
+        const int32_t *o = order + base[w];
+        for (int64_t j = 0; j < n; ++j) { wci[(size_t)j] = ci[o[j]]; wv[(size_t)j] = v[o[j]]; }
+        sx_ctx *k = new (std::nothrow) sx_ctx();
+        if (!k) { rc = fail(SX_ERR_NOMEM, "out of host memory"); break; }
+        k->device = c->device;
+        k->sm_count = c->sm_count;
+        k->stream = c->stream;
+        k->split_nnz = c->split_nnz;
+        rc = upload_csr<T>(k, M, K, n, wrp + (size_t)w * ((size_t)M + 1), wci.data(), wv.data());
+        if (rc) { release_child(k, c->stream); break; }
+        c->wins.push_back(k);
+    }
+    sx_free(wrp);
+    sx_free(base);
+    sx_free(order);
+    if (rc) { drop_windows(c); return rc; }
+    c->wins_ascending = asc != 0;
+    return SX_OK;
+}
+
 template <typename T>
 int maybe_build_panels(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rp, const int32_t *ci, const T *v) {
     drop_tiles(c);
@@ -698,6 +796,7 @@ int upload_csr(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rowptr, cons
     if ((rc = refresh_segments(c))) return rc;
     if ((rc = build_window_blocks(c, M, rowptr, colidx))) return rc;
     if ((rc = maybe_build_panels<T>(c, M, K, nnz, rowptr, colidx, val))) return rc;
+    if ((rc = maybe_build_windows<T>(c, M, K, nnz, rowptr, colidx, val))) return rc;
     c->has_A = true;
     c->upload_serial = ++g_upload_serial;
     return SX_OK;
@@ -973,7 +1072,8 @@ int sx_destroy(sx_ctx *c) {
         b->release();
     drop_plans(c);
     drop_tiles(c);
-    for (DevBuf *b : {&c->step_ptr, &c->tcols, &c->tvals}) b->release();
+    drop_windows(c);
+    for (DevBuf *b : {&c->step_ptr, &c->tcols, &c->tvals, &c->psum}) b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -1000,6 +1100,7 @@ int sx_set_option(sx_ctx *c, int option, int64_t value) {
             c->split_nnz = (int)value;
             c->segments_dirty = c->has_A;
             if (c->rest) { c->rest->split_nnz = (int)value; c->rest->segments_dirty = true; }
+            for (sx_ctx *k : c->wins) { k->split_nnz = (int)value; k->segments_dirty = true; }
             return SX_OK;
         case SX_OPT_KERNEL:
             if (value < 0 || value > 3) return fail(SX_ERR_INVALID, "SX_OPT_KERNEL is 0 (auto), 1 (row per lane group), 2 (TMA-staged work items) or 3 (TMA-staged B window)");
@@ -1018,6 +1119,11 @@ int sx_set_option(sx_ctx *c, int option, int64_t value) {
             c->item_nnz = (int)value;
             c->segments_dirty = c->has_A;
             if (c->rest) c->rest->segments_dirty = true;
+            for (sx_ctx *k : c->wins) k->segments_dirty = true;
+            return SX_OK;
+        case SX_OPT_COL_WINDOW_ROWS:
+            if (value < 0 || value > INT32_MAX) return fail(SX_ERR_INVALID, "SX_OPT_COL_WINDOW_ROWS must be >= 0");
+            c->col_window_rows = (int)value;  // takes effect at the next sx_upload_csr_*
             return SX_OK;
         default:
             return fail(SX_ERR_INVALID, "unknown option %d", option);
@@ -1045,6 +1151,7 @@ int sx_get_info(sx_ctx *c, int what, int64_t *value) {
         case SX_INFO_HOST_PATH: *value = c->last_path; return SX_OK;
         case SX_INFO_ITEMS: *value = c->last_plan ? c->last_plan->nitems : 0; return SX_OK;
         case SX_INFO_ITEM_NNZ: *value = c->last_plan ? c->last_plan->budget : 0; return SX_OK;
+        case SX_INFO_COL_WINDOWS: *value = (int64_t)c->wins.size(); return SX_OK;
         case SX_INFO_UPLOAD_SERIAL: *value = c->has_A ? c->upload_serial : 0; return SX_OK;
         default: return fail(SX_ERR_INVALID, "unknown info id %d", what);
     }

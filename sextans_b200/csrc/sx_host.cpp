@@ -446,4 +446,100 @@ int sx_partition_rows(int M, const int32_t *rowptr, int parts, int32_t *bounds) 
     return SX_OK;
 }
 
+// Column windows (the reference's WINDOW_SIZE partition of A, src/sparse_helper.h:359-371,
+// with a window sized for the GPU's L2 instead of the FPGA's on-chip B buffer): window w
+// holds the nonzeros with w*W <= col < (w+1)*W as a CSR of its own.  Rows are walked by
+// one host thread per contiguous row range; positions follow from prefix sums, so the
+// result does not depend on the thread count.  Inside (window, row) the stored order is
+// kept, and for rows stored in ascending column order (what the loader produces) walking
+// the windows in order visits a row's nonzeros in exactly the stored order.
+int sx_split_col_windows(int M, int K, const int32_t *rowptr, const int32_t *colidx, int window_rows, int *nwin_out,
+                         int32_t **win_rowptr_out, int64_t **win_base_out, int32_t **order_out, int *ascending_out) {
+    if (!nwin_out || !win_rowptr_out || !win_base_out || !order_out) {
+        sx_internal_set_error("sx_split_col_windows: null output pointer");
+        return SX_ERR_INVALID;
+    }
+    *nwin_out = 0;
+    *win_rowptr_out = nullptr;
+    *win_base_out = nullptr;
+    *order_out = nullptr;
+    if (M < 0 || K < 0 || window_rows < 1 || !rowptr || (rowptr[M] > 0 && !colidx)) {
+        sx_internal_set_error("sx_split_col_windows: bad argument");
+        return SX_ERR_INVALID;
+    }
+    const int W = window_rows;
+    if (((int64_t)K + W - 1) / W > 4096) {
+        sx_internal_set_error("sx_split_col_windows: more than 4096 windows (window_rows too small for K)");
+        return SX_ERR_INVALID;
+    }
+    const int nwin = std::max(1, (int)(((int64_t)K + W - 1) / W));
+    const int64_t nnz = rowptr[M];
+    const size_t stride = (size_t)M + 1;
+    int32_t *wrp = (int32_t *)std::calloc((size_t)nwin * stride, sizeof(int32_t));
+    int64_t *base = (int64_t *)std::calloc((size_t)nwin + 1, sizeof(int64_t));
+    int32_t *order = (int32_t *)std::malloc(std::max<size_t>((size_t)nnz, 1) * sizeof(int32_t));
+    if (!wrp || !base || !order) {
+        std::free(wrp); std::free(base); std::free(order);
+        sx_internal_set_error("sx_split_col_windows: out of host memory");
+        return SX_ERR_NOMEM;
+    }
+    const unsigned nt = nnz < (1 << 18) ? 1u : sxhost::host_threads();
+    auto row_range = [&](unsigned t, int *r0, int *r1) {
+        *r0 = (int)((int64_t)M * t / nt);
+        *r1 = (int)((int64_t)M * (t + 1) / nt);
+    };
+    std::vector<int> bad(nt, 0), unsorted(nt, 0);
+    // pass 1: wrp[w][r + 1] = nonzeros of row r in window w
+    sxhost::parallel_for(nt, [&](unsigned t) {
+        int r0, r1;
+        row_range(t, &r0, &r1);
+        for (int r = r0; r < r1; ++r) {
+            int32_t prev = -1;
+            for (int32_t j = rowptr[r]; j < rowptr[r + 1]; ++j) {
+                const int32_t c = colidx[j];
+                if ((uint32_t)c >= (uint32_t)K) { bad[t] = 1; continue; }
+                if (c < prev) unsorted[t] = 1;
+                prev = c;
+                ++wrp[(size_t)(c / W) * stride + r + 1];
+            }
+        }
+    });
+    for (unsigned t = 0; t < nt; ++t)
+        if (bad[t]) {
+            std::free(wrp); std::free(base); std::free(order);
+            sx_internal_set_error("sx_split_col_windows: column index out of range");
+            return SX_ERR_INVALID;
+        }
+    // per-window prefix sums (windows are independent)
+    sxhost::parallel_for(std::min<unsigned>(nt, (unsigned)nwin), [&](unsigned t) {
+        const unsigned step = std::min<unsigned>(nt, (unsigned)nwin);
+        for (int w = (int)t; w < nwin; w += (int)step) {
+            int32_t *p = wrp + (size_t)w * stride;
+            for (int r = 0; r < M; ++r) p[r + 1] += p[r];
+        }
+    });
+    for (int w = 0; w < nwin; ++w) base[w + 1] = base[w] + wrp[(size_t)w * stride + M];
+    // pass 2: source position of every entry, window-major
+    sxhost::parallel_for(nt, [&](unsigned t) {
+        int r0, r1;
+        row_range(t, &r0, &r1);
+        std::vector<int32_t> fill((size_t)nwin);
+        for (int r = r0; r < r1; ++r) {
+            for (int w = 0; w < nwin; ++w) fill[w] = wrp[(size_t)w * stride + r];
+            for (int32_t j = rowptr[r]; j < rowptr[r + 1]; ++j) {
+                const int w = colidx[j] / W;
+                order[base[w] + fill[w]++] = j;
+            }
+        }
+    });
+    int asc = 1;
+    for (unsigned t = 0; t < nt; ++t) asc &= !unsorted[t];
+    if (ascending_out) *ascending_out = asc;
+    *nwin_out = nwin;
+    *win_rowptr_out = wrp;
+    *win_base_out = base;
+    *order_out = order;
+    return SX_OK;
+}
+
 }  // extern "C"
