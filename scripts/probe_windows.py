@@ -16,7 +16,7 @@ from sextans_b200 import workloads as wl  # noqa: E402
 M = K = int(float(os.environ.get("PROBE_M", 1e6)))
 NNZ = int(float(os.environ.get("PROBE_NNZ", 1e8)))
 N = int(os.environ.get("PROBE_N", 16))
-WINDOWS = [int(x) for x in os.environ.get("PROBE_W", "0,262144,131072").split(",")]
+WINDOWS = [int(x) for x in os.environ.get("PROBE_W", "0,524288,262144,131072").split(",")]
 REPS = int(os.environ.get("PROBE_REPS", 5))
 
 t0 = time.time()
