@@ -105,7 +105,12 @@ enum sx_option {
      * column order (the loader's order); rows stored otherwise are summed window by window
      * (rounding-level differences).  Ignored when SX_OPT_TILE_MIN_ROWS is in effect or when
      * K <= W. */
-    SX_OPT_COL_WINDOW_ROWS = 6
+    SX_OPT_COL_WINDOW_ROWS = 6,
+    /* TMA-staged kernel: 1 = while a batch's B-row gathers are in flight, prefetch the next
+     * batch's B rows into L2 (prefetch.global.L2; their column indices are already in the
+     * shared-memory tile), taking the DRAM latency of the gathers off the lane group's
+     * critical path.  Results are unaffected.  0 = off. */
+    SX_OPT_PREFETCH = 7
 };
 
 enum sx_info {

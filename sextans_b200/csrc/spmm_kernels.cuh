@@ -282,6 +282,14 @@ template <int U> __device__ __forceinline__ void lds_vec(const double *p, double
 // (windows ascend, columns ascend inside a window), so strict mode stays bit-identical.
 // P[row + 1] is fetched when row opens, like C_in, so its latency hides behind the row.
 constexpr int SX_WIN_INIT = 1, SX_WIN_RAW = 2;
+// wflags bit 2 (any instantiation): while a batch's gathers are in flight, ask L2 for the
+// B rows of the NEXT batch (its columns already sit in the shared-memory tile), so that
+// the next batch's gathers find them in L2 instead of paying the DRAM latency on the
+// group's critical path.  No registers are held across the prefetch.
+constexpr int SX_FLAG_PREFETCH = 4;
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 template <typename T, int G, int VPL, bool STRICT, bool WIN = false>
 __global__ void __launch_bounds__(256, (VPL > 1 ? 2 : (sizeof(T) == 8 ? 3 : 4)))
@@ -293,6 +301,7 @@ spmm_staged_kernel(const int nitems, const int4 *__restrict__ items, const int t
     using V = typename VecOf<T>::type;
     const bool w_init = WIN && (wflags & SX_WIN_INIT);
     const bool w_raw = WIN && (wflags & SX_WIN_RAW);
+    const bool pf = (wflags & SX_FLAG_PREFETCH) != 0;
     constexpr int U = (G < 8 ? G : 8) / (VPL > 2 ? 4 : VPL);  // gathers per batch per lane
     constexpr int GPB = 256 / G;                               // lane groups per block
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -323,7 +332,10 @@ spmm_staged_kernel(const int nitems, const int4 *__restrict__ items, const int t
         tma_bulk_g2s(const_cast<int *>(scol) + (e0 & ring), colidx + jal + e0, cnt * 4u, bk, pol);
         tma_bulk_g2s(const_cast<T *>(sval) + (e0 & ring), val + jal + e0, cnt * (uint32_t)sizeof(T), bk, pol);
     };
-    const int nt = (len + ts - 1) / ts;
+    // ts and U are powers of two: tile/batch bookkeeping by shift and mask (as runtime
+    // divisions these cost ~70 of the ~250 instructions a batch executed; profiles/r01_colwindow.md)
+    const int tsh = 31 - __clz(ts);
+    const int nt = (len + ts - 1) >> tsh;
     if (je > jb) {
         if (lg == 0) {
             mbar_init(bar, 1);
@@ -340,6 +352,9 @@ spmm_staged_kernel(const int nitems, const int4 *__restrict__ items, const int t
     const int re = piece ? r + 1 : it.y;
     int rend = piece ? -1 : __ldg(rowptr + r + 1) - jal;  // in stream coordinates
     const V *Bv = reinterpret_cast<const V *>(B) + lg;
+    // a B row's address is base + column * (row bytes): one IMAD.WIDE.U32 per gather
+    const unsigned char *Bb = reinterpret_cast<const unsigned char *>(Bv);
+    const uint32_t ldbb = ldbv * 16u;
     const V *Cv = reinterpret_cast<const V *>(Cin) + lg;
     V *Pv = reinterpret_cast<V *>(P) + lg;  // dereferenced in window passes only
     V acc[VPL], cin[VPL], pin[VPL];          // pin: next row's running sum (window passes)
@@ -384,11 +399,14 @@ spmm_staged_kernel(const int nitems, const int4 *__restrict__ items, const int t
     };
 
     if (je > jb) {
-        const int bpt = ts / U;  // batches per tile
+        constexpr int USH = U == 8 ? 3 : (U == 4 ? 2 : 1);
+        static_assert((1 << USH) == U, "U is 2, 4 or 8");
+        const int bsh = tsh - USH;           // log2(batches per tile)
+        const int bmask = (1 << bsh) - 1;
         const int nb = (len + U - 1) / U;
         for (int q = 0; q < nb; ++q) {
             const int e0 = q * U;
-            if (q % bpt == 0) mbar_wait(bar + ((q / bpt) & 1), (uint32_t)(((q / bpt) >> 1) & 1));
+            if ((q & bmask) == 0) mbar_wait(bar + ((q >> bsh) & 1), (uint32_t)(((q >> bsh) >> 1) & 1));
             const int idx = e0 & ring;
             int cc[U];
             T av[U];
@@ -398,11 +416,23 @@ spmm_staged_kernel(const int nitems, const int4 *__restrict__ items, const int t
                 // every entry of the batch belongs to the item
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const V *brow = Bv + (size_t)(uint32_t)cc[u] * ldbv;
+                    const V *brow = reinterpret_cast<const V *>(Bb + (uint64_t)(uint32_t)cc[u] * ldbb);
 #pragma unroll
                     for (int v = 0; v < VPL; ++v) {
                         if (VPL == 1 || lg + v * G < nvec) b[u][v] = ldg_vec(brow + v * G);
                         else vzero(b[u][v]);
+                    }
+                }
+                // next batch fully inside the item and inside this tile: its columns are here
+                if (pf && ((q + 1) & bmask) != 0 && e0 + 2 * U <= len) {
+                    int cn[U];
+                    lds_vec<U>(scol + idx + U, cn);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const unsigned char *nrow = Bb + (uint64_t)(uint32_t)cn[u] * ldbb;
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v)
+                            if (VPL == 1 || lg + v * G < nvec) prefetch_l2(nrow + v * G * 16);
                     }
                 }
                 lds_vec<U>(sval + idx, av);
@@ -425,7 +455,7 @@ spmm_staged_kernel(const int nitems, const int4 *__restrict__ items, const int t
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const bool live = e0 + u >= off && e0 + u < len;
-                    const V *brow = Bv + (size_t)(uint32_t)(live ? cc[u] : 0) * ldbv;
+                    const V *brow = reinterpret_cast<const V *>(Bb + (uint64_t)(uint32_t)(live ? cc[u] : 0) * ldbb);
 #pragma unroll
                     for (int v = 0; v < VPL; ++v) {
                         if (live && lg + v * G < nvec) b[u][v] = ldg_vec(brow + v * G);
@@ -442,9 +472,9 @@ spmm_staged_kernel(const int nitems, const int4 *__restrict__ items, const int t
                     }
                 }
             }
-            if ((q + 1) % bpt == 0) {
+            if (((q + 1) & bmask) == 0) {
                 // the whole group is done with this tile: refill its buffer with tile +2
-                const int k = q / bpt;
+                const int k = q >> bsh;
                 __syncwarp(gmask);
                 if (lg == 0 && k + 2 < nt) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -137,6 +137,7 @@ struct sx_ctx {
     int split_nnz = 512;
     int kernel = 0;
     int item_nnz = 0;  // 0 = auto
+    int prefetch = 0;  // SX_OPT_PREFETCH
     int64_t zerocopy_bytes = 3 << 19;  // 1.5 MiB: above that the copy engines win
     int last_path = 0;  // 1: the last host-facing call took the zero-copy path
     bool segments_dirty = false;
@@ -265,7 +266,7 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
         // a column-window pass runs the WIN instantiation with the parent's running sums
         auto kern = c->win_mode ? sx::spmm_staged_kernel<T, G, VPL, STRICT, true> : sx::spmm_staged_kernel<T, G, VPL, STRICT, false>;
         T *P = c->win_mode ? (T *)c->win_P + c->win_col0 : (T *)nullptr;
-        const int wflags = c->win_mode ? c->win_flags : 0;
+        const int wflags = (c->win_mode ? c->win_flags : 0) | (c->prefetch ? sx::SX_FLAG_PREFETCH : 0);
         if (smem > 48 * 1024)  // only the narrowest fp64 shape (128 lane groups per block) gets there
             SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (unsigned)(((int64_t)p->nitems + rows_per_block - 1) / rows_per_block);
@@ -352,6 +353,7 @@ int spmm_tiles<double>(sx_ctx *c, int N, double alpha, const double *dB, int64_t
         r->arith = c->arith;
         r->kernel = c->kernel;
         r->item_nnz = c->item_nnz;
+        r->prefetch = c->prefetch;
         const int64_t before = r->launches;
         int rc = spmm_device<double>(r, N, alpha, dB, ldb, 1.0, dCout, dCout, ldc);
         c->launches += r->launches - before;
@@ -374,6 +376,7 @@ int spmm_windows(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
         k->stream = c->stream;
         k->arith = c->arith;
         k->item_nnz = c->item_nnz;
+        k->prefetch = c->prefetch;
         k->win_mode = true;
         k->win_flags = (w > 0 ? sx::SX_WIN_INIT : 0) | (w + 1 < nwin ? sx::SX_WIN_RAW : 0);
         k->win_P = c->psum.p;
@@ -507,11 +510,21 @@ int pick_budget(const sx_ctx *c, int G) {
 }
 
 // tile size (entries, power of two) of the staged kernel: <= 28 KB of staging per block
+// (tuning knob, not an interface: SX_STAGE_KB in the environment overrides the 28 KB)
+size_t stage_limit_bytes() {
+    static const size_t v = [] {
+        const char *e = getenv("SX_STAGE_KB");
+        const int kb = e ? atoi(e) : 0;
+        return (size_t)(kb >= 8 && kb <= 200 ? kb : 28) * 1024;
+    }();
+    return v;
+}
+
 template <typename T, int G>
 int pick_tile(int U) {
     const int gpb = 256 / G;
     int ts = 16;
-    while (ts < 128 && (size_t)gpb * (16 + 4 * ts * (sizeof(T) + 4)) <= 28 * 1024) ts *= 2;  // test is for 2*ts
+    while (ts < 128 && (size_t)gpb * (16 + 4 * ts * (sizeof(T) + 4)) <= stage_limit_bytes()) ts *= 2;  // test is for 2*ts
     return std::max(ts, 2 * U);
 }
 
@@ -1120,6 +1133,10 @@ int sx_set_option(sx_ctx *c, int option, int64_t value) {
             c->segments_dirty = c->has_A;
             if (c->rest) c->rest->segments_dirty = true;
             for (sx_ctx *k : c->wins) k->segments_dirty = true;
+            return SX_OK;
+        case SX_OPT_PREFETCH:
+            if (value != 0 && value != 1) return fail(SX_ERR_INVALID, "SX_OPT_PREFETCH is 0 or 1");
+            c->prefetch = (int)value;
             return SX_OK;
         case SX_OPT_COL_WINDOW_ROWS:
             if (value < 0 || value > INT32_MAX) return fail(SX_ERR_INVALID, "SX_OPT_COL_WINDOW_ROWS must be >= 0");

@@ -222,6 +222,28 @@ def test_every_kernel_variant_bit_exact(eng, kernel, dtype, M, K, avg, N):
         eng.set_option(sx.OPT_ITEM_NNZ, 0)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("M,K,avg,N", KERNEL_SHAPES + [(3000, 50000, 90, 16), (800, 20000, 120, 128)])
+def test_l2_prefetch_of_the_next_batch_changes_nothing(eng, dtype, M, K, avg, N):
+    """SX_OPT_PREFETCH only moves data towards L2 earlier: the staged kernel's results stay
+    bit-identical to the oracle (long rows included, at several item budgets)."""
+    rp, ci, v = random_csr(M, K, avg, M * 19 + N, dtype, long_row=min(K, 300))
+    B, Cin = random_dense(M, K, N, M * 19 + N, dtype)
+    ref = oracle.spmm_csr(M, N, K, rp, ci, v, dtype(0.85), B, dtype(-2.06), Cin.copy())
+    eng.set_option(sx.OPT_KERNEL, 2)
+    eng.set_option(sx.OPT_PREFETCH, 1)
+    try:
+        for item_nnz in (0, 64, 2048):
+            eng.set_option(sx.OPT_ITEM_NNZ, item_nnz)
+            C, _ = run(eng, M, K, N, rp, ci, v, dtype(0.85), B, dtype(-2.06), Cin)
+            assert np.array_equal(bits(C), bits(ref)), item_nnz
+            assert eng.info(sx.INFO_LAST_KERNEL) // 10000 == 2
+    finally:
+        eng.set_option(sx.OPT_KERNEL, 0)
+        eng.set_option(sx.OPT_ITEM_NNZ, 0)
+        eng.set_option(sx.OPT_PREFETCH, 0)
+
+
 def test_auto_kernel_choice(eng):
     # less than one wave of row groups and narrow column windows: variant 3 (else 1);
     # more rows than that: the staged variant 2
