@@ -109,7 +109,10 @@ enum sx_option {
     /* TMA-staged kernel: 1 = while a batch's B-row gathers are in flight, prefetch the next
      * batch's B rows into L2 (prefetch.global.L2; their column indices are already in the
      * shared-memory tile), taking the DRAM latency of the gathers off the lane group's
-     * critical path.  Results are unaffected.  0 = off. */
+     * critical path.  Results are unaffected.  0 = off.  -1 (default) = auto: on when B is
+     * larger than 32 MiB and a dense row is at most 256 bytes (measured: power-law
+     * M=K=1e6, nnz=9.6e7, N=16 fp64 1.63 -> 1.49 ms; uniform N=128 fp32, DRAM-bound,
+     * 1.456 -> 1.470 ms, hence left off for wide rows). */
     SX_OPT_PREFETCH = 7
 };
 

@@ -22,7 +22,7 @@ KIND = os.environ.get("PROBE_KIND", "powerlaw")
 M = K = int(float(os.environ.get("PROBE_M", 1e6)))
 NNZ = int(float(os.environ.get("PROBE_NNZ", 1e8 if KIND == "powerlaw" else 2e7)))
 N = int(os.environ.get("PROBE_N", 16 if KIND == "powerlaw" else 128))
-SETTINGS = [tuple(int(x) for x in s.split(":")) for s in os.environ.get("PROBE_SET", "0:0,0:1").split(",")]
+SETTINGS = [tuple(int(x) for x in s.split(":")) for s in os.environ.get("PROBE_SET", "0:0,0:1,0:-1").split(",")]
 REPS = int(os.environ.get("PROBE_REPS", 10))
 dtype = np.float64 if KIND == "powerlaw" else np.float32
 

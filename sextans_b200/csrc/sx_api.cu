@@ -137,7 +137,7 @@ struct sx_ctx {
     int split_nnz = 512;
     int kernel = 0;
     int item_nnz = 0;  // 0 = auto
-    int prefetch = 0;  // SX_OPT_PREFETCH
+    int prefetch = -1;  // SX_OPT_PREFETCH: -1 auto, 0 off, 1 on
     int64_t zerocopy_bytes = 3 << 19;  // 1.5 MiB: above that the copy engines win
     int last_path = 0;  // 1: the last host-facing call took the zero-copy path
     bool segments_dirty = false;
@@ -266,7 +266,13 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
         // a column-window pass runs the WIN instantiation with the parent's running sums
         auto kern = c->win_mode ? sx::spmm_staged_kernel<T, G, VPL, STRICT, true> : sx::spmm_staged_kernel<T, G, VPL, STRICT, false>;
         T *P = c->win_mode ? (T *)c->win_P + c->win_col0 : (T *)nullptr;
-        const int wflags = (c->win_mode ? c->win_flags : 0) | (c->prefetch ? sx::SX_FLAG_PREFETCH : 0);
+        // auto: prefetch the next batch's B rows into L2 when the gathers can miss L2 (B larger
+        // than ~a quarter of it) and the kernel is latency- rather than DRAM-bound (rows of at
+        // most 256 bytes: C5 1.63 -> 1.49 ms; with 512-byte rows C4 sits at 82 % of DRAM
+        // bandwidth and gains nothing, 1.456 -> 1.470 ms)
+        const bool pf = c->prefetch >= 0 ? c->prefetch != 0
+                                         : (G <= 16 && (size_t)c->K * (size_t)ldb * sizeof(T) > ((size_t)32 << 20));
+        const int wflags = (c->win_mode ? c->win_flags : 0) | (pf ? sx::SX_FLAG_PREFETCH : 0);
         if (smem > 48 * 1024)  // only the narrowest fp64 shape (128 lane groups per block) gets there
             SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (unsigned)(((int64_t)p->nitems + rows_per_block - 1) / rows_per_block);
@@ -1135,7 +1141,7 @@ int sx_set_option(sx_ctx *c, int option, int64_t value) {
             for (sx_ctx *k : c->wins) k->segments_dirty = true;
             return SX_OK;
         case SX_OPT_PREFETCH:
-            if (value != 0 && value != 1) return fail(SX_ERR_INVALID, "SX_OPT_PREFETCH is 0 or 1");
+            if (value < -1 || value > 1) return fail(SX_ERR_INVALID, "SX_OPT_PREFETCH is -1 (auto), 0 or 1");
             c->prefetch = (int)value;
             return SX_OK;
         case SX_OPT_COL_WINDOW_ROWS:

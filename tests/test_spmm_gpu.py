@@ -241,7 +241,22 @@ def test_l2_prefetch_of_the_next_batch_changes_nothing(eng, dtype, M, K, avg, N)
     finally:
         eng.set_option(sx.OPT_KERNEL, 0)
         eng.set_option(sx.OPT_ITEM_NNZ, 0)
-        eng.set_option(sx.OPT_PREFETCH, 0)
+        eng.set_option(sx.OPT_PREFETCH, -1)
+
+
+def test_auto_prefetch_regime_large_B_narrow_rows(eng):
+    # B of 77 MB (> 32 MiB) with 128-byte rows: the auto rule of SX_OPT_PREFETCH switches the
+    # prefetch on in the staged kernel; the result is the oracle's, bit for bit
+    M, K, N = 4000, 600000, 16
+    rp, ci, v = random_csr(M, K, 60, 4242, np.float64)
+    B, Cin = random_dense(M, K, N, 4242, np.float64)
+    eng.set_option(sx.OPT_KERNEL, 2)
+    try:
+        C, _ = run(eng, M, K, N, rp, ci, v, 0.85, B, -2.06, Cin)
+    finally:
+        eng.set_option(sx.OPT_KERNEL, 0)
+    ref = oracle.spmm_csr(M, N, K, rp, ci, v, 0.85, B, -2.06, Cin.copy())
+    assert np.array_equal(bits(C), bits(ref))
 
 
 def test_auto_kernel_choice(eng):
