@@ -65,6 +65,9 @@ def lib():
             f.restype = _I
         L.sx_oracle_verify_f32.argtypes = [C.c_int64, _PF, _PF, _I, _I, _PF]
         L.sx_oracle_verify_f32.restype = C.c_int64
+        L.sx_oracle_sextans_images.argtypes = [_PI, C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(_PF),
+                                               C.POINTER(_PF), C.POINTER(_PF), _I, _I, _I, _I, _I, _I]
+        L.sx_oracle_sextans_images.restype = _I
         L.sx_oracle_free.argtypes = [C.c_void_p]
         L.sx_oracle_max_threads.restype = _I
         _LIB = L
@@ -295,6 +298,26 @@ def unpack_C_images(imgs, M, N):
             sel = m % 8 == c
             out[n][sel] = imgs[c][pos[sel]]
     return out.ravel()
+
+
+def sextans_images(ptr, A_images, B_images, Cin_images, M, K, P_N, alpha_u, beta_u):
+    """Functional model of the accelerator dataflow (src/sextans.cpp:285-570, 196-233) on
+    the channel images themselves -> the 8 C output images (new arrays, zero beyond the
+    words the hardware writes)."""
+    ptr = np.ascontiguousarray(ptr, dtype=np.int32)
+    a = [np.ascontiguousarray(x, dtype=np.uint64) for x in A_images]
+    b = [np.ascontiguousarray(x, dtype=np.float32) for x in B_images]
+    ci = [np.ascontiguousarray(x, dtype=np.float32) for x in Cin_images]
+    co = [np.zeros_like(x) for x in ci]
+    pa = (C.POINTER(C.c_uint64) * 8)(*[x.ctypes.data_as(C.POINTER(C.c_uint64)) for x in a])
+    pb = (_PF * 4)(*[_ptr(x, C.c_float) for x in b])
+    pci = (_PF * 8)(*[_ptr(x, C.c_float) for x in ci])
+    pco = (_PF * 8)(*[_ptr(x, C.c_float) for x in co])
+    rc = lib().sx_oracle_sextans_images(_ptr(ptr, C.c_int), pa, pb, pci, pco, ptr.size - 1, M, K,
+                                        P_N, alpha_u, beta_u)
+    if rc:
+        raise RuntimeError(f"dataflow model failed: {rc}")
+    return co
 
 
 def pack_scalars(N, rp_time, alpha, beta):

@@ -19,6 +19,10 @@
  *                                  src/sparse_helper.h:475-509  CSC_2_CSR
  *   sx_oracle_verify_f32           src/sextans-host.cpp:262-289 mismatch criterion
  *   sx_oracle_init_dense_*         src/sextans-host.cpp:100-111 B = 1, C = (m+1)(n+1)/M/N
+ *   sx_oracle_sextans_images       src/sextans.cpp:285-570      the accelerator's own dataflow
+ *                                  (PEG_Bmtx, PEG_Cmtx), :196-233 (alpha/beta), run on
+ *                                  the FPGA channel images in the order the hardware
+ *                                  streams them (functional model, no timing)
  *
  * The reference is fp32-only; the f64 entry points are
  * the same statements instantiated for double.
@@ -368,6 +372,92 @@ int sx_oracle_load_mtx_f64(const char *path, int *M, int *K, int *nnz,
     void *v = NULL;
     int rc = sx_load(path, 1, M, K, nnz, rowptr, colidx, &v, code);
     *val = (double *)v;
+    return rc;
+}
+
+/*
+ * Functional model of the Sextans accelerator on its own channel images: what the
+ * task graph of src/sextans.cpp:836-984 computes, in the order it computes it.
+ *
+ *   for every block of 8 output columns             (l_rp loops, :331, :491; P_N decode :52-54)
+ *     local_C <- 0                                  (init_C, :497-507)
+ *     for every column window w                     (main loops, :349, :511)
+ *       local_B <- rows [4096 w, 4096 w + 4096) x the block's 8 columns of B, taken from
+ *                  the 4 B channel images           (read_B, :353-381; layout host.cpp:158-171)
+ *       for every slot of the window, for every PE  (computation, :385-420, :516-540)
+ *         word = col14 | row18 | fp32; bit 17 of the row field set: bubble, skipped (:404)
+ *         abvec[d] = val * local_B[d][col]          (PEcore_Bmtx, :285-295: one rounding)
+ *         local_C[PE][row][d] += abvec[d]           (PU2core_Cmtx, :425-447: one rounding)
+ *     C_out = alpha * local_C + beta * C_in         (FloatvMultConst x2, FloatvAddFloatv,
+ *                                                    :196-233: three roundings)
+ *     written as whole 16-row words into the 8 C channel images (:158-194; layout
+ *     host.cpp:181-195: channel m % 8, element roundup(M,16)*(n/8) + (m/8)*8 + n % 8)
+ *
+ * PE p reads word bitrev3(p / 8) of every 8-word slot of channel p % 8
+ * (src/sparse_helper.h:451-464 with Scatter_1_2, src/sextans.cpp:785-800) and owns the
+ * rows r with r % 64 == p at local address r / 64 (src/sparse_helper.h:314,370).
+ * rp_time repeats recompute the same thing from the same C_in (:143) and are not modelled.
+ * Returns 0, or 7 (out of memory) / 8 (a word addresses a row >= roundup(M,64) or a column
+ * beyond its window's part of K).
+ */
+int sx_oracle_sextans_images(const int32_t *ptr, const uint64_t *const A[8], const float *const B[4],
+                             const float *const Cin[8], float *const Cout[8], int NUM_ITE, int M, int K,
+                             int P_N, int alpha_u, int beta_u) {
+    const int N = P_N & 0xFFFF;
+    const int nblocks = (N + 7) >> 3;
+    float alpha, beta;
+    memcpy(&alpha, &alpha_u, 4);
+    memcpy(&beta, &beta_u, 4);
+    const int rows_per_pe = (M + 63) / 64;
+    const long colsz_b = (long)((K + 7) / 8) * 16; /* floats per 8-column block in a B image */
+    const long colsz_c = (long)((M + 15) / 16) * 16;
+    const int Mr = (int)colsz_c;
+    float *local_C = (float *)malloc(sizeof(float) * 64 * (size_t)(rows_per_pe ? rows_per_pe : 1) * 8);
+    float *local_B = (float *)malloc(sizeof(float) * 8 * 4096);
+    if (!local_C || !local_B) { free(local_C); free(local_B); return 7; }
+    int rc = 0;
+    for (int nb = 0; nb < nblocks && !rc; ++nb) {
+        memset(local_C, 0, sizeof(float) * 64 * (size_t)(rows_per_pe ? rows_per_pe : 1) * 8);
+        for (int w = 0; w < NUM_ITE && !rc; ++w) {
+            const int k0 = w * 4096;
+            const int kn = K - k0 < 4096 ? K - k0 : 4096;
+            for (int kk = 0; kk < kn; ++kk) {
+                const long word = (long)((k0 + kk) / 8) * 16 + (k0 + kk) % 8 + colsz_b * nb;
+                for (int d = 0; d < 8; ++d) local_B[d * 4096 + kk] = B[d / 2][word + (d % 2) * 8];
+            }
+            for (long s = ptr[w]; s < ptr[w + 1] && !rc; ++s) {
+                for (int pe = 0; pe < 64; ++pe) {
+                    const int q = pe / 8;
+                    const int pos = ((q & 1) << 2) | (q & 2) | ((q >> 2) & 1);
+                    const uint64_t x = A[pe % 8][s * 8 + pos];
+                    const uint32_t row = (uint32_t)(x >> 32) & 0x3FFFFu;
+                    if (row & 0x20000u) continue;
+                    const uint32_t col = (uint32_t)(x >> 50);
+                    if ((int)row >= rows_per_pe || (int)col >= kn) { rc = 8; break; }
+                    const uint32_t vb = (uint32_t)x;
+                    float val;
+                    memcpy(&val, &vb, 4);
+                    float *c = local_C + ((size_t)pe * rows_per_pe + row) * 8;
+                    for (int d = 0; d < 8; ++d) {
+                        const float ab = val * local_B[d * 4096 + col];
+                        c[d] = c[d] + ab;
+                    }
+                }
+            }
+        }
+        for (int m = 0; m < Mr && !rc; ++m) {
+            const int pe = m % 64, r = m / 64;
+            for (int d = 0; d < 8; ++d) {
+                const long p = colsz_c * nb + (long)(m / 8) * 8 + d;
+                const float acc = (r < rows_per_pe) ? local_C[((size_t)pe * rows_per_pe + r) * 8 + d] : 0.0f;
+                const float t1 = alpha * acc;
+                const float t2 = beta * Cin[m % 8][p];
+                Cout[m % 8][p] = t1 + t2;
+            }
+        }
+    }
+    free(local_C);
+    free(local_B);
     return rc;
 }
 

@@ -10,7 +10,7 @@ import pytest
 
 import oracle
 import sextans_b200 as sx
-from helpers import GOLDEN, SUITESPARSE, mtx_path, random_csr
+from helpers import GOLDEN, SUITESPARSE, mtx_path, random_csr, random_dense
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HAVE_REF = oracle.ref() is not None and hasattr(oracle.ref(), "sxref_build_images")
@@ -127,6 +127,45 @@ def test_dense_image_layouts_round_trip(M, K, N):
     exp = oracle.pack_C_images(Cm, M, N, fill_pad=a * np.float32(0) + b * np.float32(0.5))
     for o, e in zip(out, exp):
         assert np.array_equal(o[:used], e[:used]) and (o[used:] == 7.0).all()
+
+
+def test_dataflow_model_on_golden_images_equals_the_csr_oracle(golden):
+    """The accelerator's dataflow, modelled on its own images in hardware order
+    (oracle.sextans_images: src/sextans.cpp:285-570), gives cpu_spmm_CSR's result bit for
+    bit -- the property that lets cpu_spmm_CSR stand in for the kernel."""
+    g = np.load(os.path.join(GOLDEN, "images_small.npz"))
+    for tag in golden["image_cases"]:
+        M, K, _ = g[tag + "_dims"].tolist()
+        for N, alpha, beta in ((8, 0.85, -2.06), (24, -1.25, 0.5)):
+            B, Cin = random_dense(M, K, N, 17, np.float32)
+            P_N, au, bu = oracle.pack_scalars(N, 2, alpha, beta)
+            cin = oracle.pack_C_images(Cin, M, N, fill_pad=0.25)
+            co = oracle.sextans_images(g[tag + "_ptr"], [g[f"{tag}_A{c}"] for c in range(8)],
+                                       oracle.pack_B_images(B, K, N), cin, M, K, P_N, au, bu)
+            ref = oracle.spmm_csr(M, N, K, g[tag + "_rowptr"], g[tag + "_colidx"], g[tag + "_val"],
+                                  np.float32(alpha), B, np.float32(beta), Cin.copy())
+            assert np.array_equal(oracle.unpack_C_images(co, M, N).view(np.uint32), ref.view(np.uint32)), tag
+            # pad rows of the last 16-row word: alpha*0 + beta*pad, nothing beyond
+            pad = np.float32(alpha) * np.float32(0) + np.float32(beta) * np.float32(0.25)
+            exp = oracle.pack_C_images(ref, M, N, fill_pad=pad)
+            used = sx.lib().sx_images_C_floats(M, N)
+            for o, e in zip(co, exp):
+                assert np.array_equal(o[:used].view(np.uint32), e[:used].view(np.uint32)) and not o[used:].any()
+
+
+@needs_ref
+@pytest.mark.parametrize("name,N", [("nasa4704", 16), ("nasa4704", 8), ("pcrystk02", 8)])
+def test_dataflow_model_equals_the_compiled_reference_on_suitesparse(name, N):
+    M, K, nnz, rp, ci, v = oracle.ref_load_csr(mtx_path(name))
+    v = (1.0 + 0.001 * (np.arange(nnz) % 97)).astype(np.float32)
+    ptr, imgs, _ = oracle.ref_build_images(M, K, rp, ci, v)
+    B, Cin = random_dense(M, K, N, 3, np.float32)
+    P_N, au, bu = oracle.pack_scalars(N, 1, 0.85, -2.06)
+    co = oracle.sextans_images(ptr, imgs, oracle.pack_B_images(B, K, N), oracle.pack_C_images(Cin, M, N),
+                               M, K, P_N, au, bu)
+    ref = Cin.copy()
+    oracle.ref_spmm_csr(M, N, K, rp, ci, v, 0.85, B, -2.06, ref)   # the reference's own cpu_spmm_CSR
+    assert np.array_equal(oracle.unpack_C_images(co, M, N).view(np.uint32), ref.view(np.uint32))
 
 
 def test_scalar_packing_matches_the_host():

@@ -89,6 +89,28 @@ def test_random_images_bit_exact(eng, M, K, avg, N, alpha, beta):
     assert np.array_equal(C.view(np.uint32), ref.view(np.uint32))
 
 
+@pytest.mark.parametrize("tag", ["p", "q", "r"])
+def test_output_images_equal_the_dataflow_model_word_for_word(eng, tag):
+    """Not only the rows the host reads back: every float of the output images the hardware
+    would write (whole 16-row words, pad rows included) equals the functional model of the
+    accelerator dataflow run on the same images (oracle.sextans_images)."""
+    g = np.load(os.path.join(GOLDEN, "images_small.npz"))
+    M, K, _ = g[tag + "_dims"].tolist()
+    ptr, imgs = g[tag + "_ptr"], [g[f"{tag}_A{c}"] for c in range(8)]
+    for N, alpha, beta, rp_time in ((8, 0.85, -2.06, 1), (24, -1.25, 0.5, 3)):
+        B, Cin = random_dense(M, K, N, 23, np.float32)
+        P_N, au, bu = oracle.pack_scalars(N, rp_time, alpha, beta)
+        bi = oracle.pack_B_images(B, K, N)
+        ci = oracle.pack_C_images(Cin, M, N, fill_pad=0.25)
+        co = [np.full_like(x, 7.0) for x in ci]
+        eng.sextans_invoke(ptr, imgs, bi, ci, co, M, K, P_N, au, bu)
+        model = oracle.sextans_images(ptr, imgs, bi, ci, M, K, P_N, au, bu)
+        used = sx.lib().sx_images_C_floats(M, N)
+        for o, e in zip(co, model):
+            assert np.array_equal(o[:used].view(np.uint32), e[:used].view(np.uint32))
+            assert (o[used:] == 7.0).all()
+
+
 def test_user_upload_between_invokes_is_noticed(eng, golden):
     g = np.load(os.path.join(GOLDEN, "images_small.npz"))
     M, K, _ = g["q_dims"].tolist()
