@@ -113,7 +113,14 @@ enum sx_option {
      * larger than 32 MiB and a dense row is at most 256 bytes (measured: power-law
      * M=K=1e6, nnz=9.6e7, N=16 fp64 1.63 -> 1.49 ms; uniform N=128 fp32, DRAM-bound,
      * 1.456 -> 1.470 ms, hence left off for wide rows). */
-    SX_OPT_PREFETCH = 7
+    SX_OPT_PREFETCH = 7,
+    /* EXPERIMENTAL (off by default; not yet measured on hardware).  1: an sx_spmm_* call that
+     * takes the zero-copy path on a matrix that runs variant 3, with rp_time <= 1 and
+     * kernel_ns == NULL (nobody asks for the kernel-only time), lets the SpMM kernel read
+     * C_in from and write C to the caller's page-locked array itself: B staging + one kernel
+     * instead of three launches, C's inbound and outbound PCIe transfers overlapping each
+     * other and the compute.  Same arithmetic, same results.  SX_INFO_HOST_PATH reports 2. */
+    SX_OPT_HOST_FUSED = 8
 };
 
 enum sx_info {
@@ -127,7 +134,8 @@ enum sx_info {
     SX_INFO_LD = 7,          /* leading dimension (elements) of the context's row-major B/C */
     SX_INFO_ITEMS = 8,       /* work items of the main kernel */
     SX_INFO_ITEM_NNZ = 9,    /* nonzero budget per work item in use */
-    SX_INFO_HOST_PATH = 10,  /* 1 if the last sx_spmm_* call took the zero-copy path */
+    SX_INFO_HOST_PATH = 10,  /* last sx_spmm_* call: 0 copy engines, 1 zero-copy kernels, 2 zero-copy with
+                              * C carried by the SpMM kernel (SX_OPT_HOST_FUSED) */
     SX_INFO_TILE_NNZ = 11,   /* nonzeros held in dense tiles */
     SX_INFO_TILE_SLOTS = 12, /* tile slots incl. explicit zeros (fill = TILE_NNZ / TILE_SLOTS) */
     SX_INFO_REST_NNZ = 13,   /* nonzeros left to the CSR kernels */

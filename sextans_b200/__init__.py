@@ -27,7 +27,7 @@ _LIB = None
 SX_F32, SX_F64 = 0, 1
 STRICT, FAST = 0, 1
 (OPT_ARITH, OPT_SPLIT_ROW_NNZ, OPT_KERNEL, OPT_ITEM_NNZ, OPT_ZEROCOPY_BYTES, OPT_TILE_MIN_ROWS,
- OPT_COL_WINDOW_ROWS, OPT_PREFETCH) = range(8)
+ OPT_COL_WINDOW_ROWS, OPT_PREFETCH, OPT_HOST_FUSED) = range(9)
 (INFO_LAUNCHES, INFO_M, INFO_K, INFO_NNZ, INFO_DTYPE, INFO_SPLIT_ROWS, INFO_LAST_KERNEL, INFO_LD,
  INFO_ITEMS, INFO_ITEM_NNZ, INFO_HOST_PATH, INFO_TILE_NNZ, INFO_TILE_SLOTS, INFO_REST_NNZ,
  INFO_UPLOAD_SERIAL, INFO_COL_WINDOWS) = range(16)
@@ -377,10 +377,11 @@ class Engine:
         return self
 
     # -- the call ----------------------------------------------------------------------
-    def spmm(self, N, alpha, B, beta, C_inout, rp_time=1):
+    def spmm(self, N, alpha, B, beta, C_inout, rp_time=1, want_ns=True):
         """In place on ``C_inout`` (column-major 1-D, like the host program's vectors).
         Returns the kernel time in ns summed over the ``rp_time`` repeats, the value
-        ``tapa::invoke`` returns in the reference (src/sextans-host.cpp:237)."""
+        ``tapa::invoke`` returns in the reference (src/sextans-host.cpp:237); with
+        ``want_ns=False`` the C call gets ``kernel_ns = NULL`` and returns ``None``."""
         suf, ct, _ = _suffix(self.dtype)
         B = np.ascontiguousarray(B, dtype=self.dtype)
         if C_inout.dtype != self.dtype or not C_inout.flags.c_contiguous:
@@ -389,8 +390,9 @@ class Engine:
             raise ValueError("B must hold K*N and C must hold M*N elements")
         ns = C.c_double()
         _check(getattr(self._L, f"sx_spmm_{suf}")(self._ctx, N, ct(alpha), _host_ptr(B), ct(beta),
-                                                  _host_ptr(C_inout), rp_time, C.byref(ns)))
-        return ns.value
+                                                  _host_ptr(C_inout), rp_time,
+                                                  C.byref(ns) if want_ns else None))
+        return ns.value if want_ns else None
 
     def sextans_invoke(self, ptr, A_images, B_images, Cin_images, Cout_images, M, K, P_N,
                        alpha_u, beta_u):

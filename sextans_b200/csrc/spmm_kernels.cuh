@@ -567,6 +567,111 @@ spmm_window_kernel(const int M, const int4 *__restrict__ blocks, const int *__re
     }
 }
 
+// ---- variant 3 fused with the host boundary (experimental, SX_OPT_HOST_FUSED) -------------
+// For the small banded matrices that take variant 3 the host-facing call is dominated by
+// PCIe, not by the SpMM: B and C_in cross the bus into device images, the kernel runs, C
+// crosses back -- three launches in a row, each waiting for the one before.  This kernel
+// removes the C staging: a block reads the C_in tile of its 32 rows straight from the
+// caller's column-major page-locked array (one contiguous 32-row segment per column, 16
+// bytes per thread) into shared memory while its B window is on the way by TMA, computes
+// exactly like spmm_window_kernel, puts the result back into the same shared tile and
+// writes it to the caller's array, again one contiguous segment per column.  C's inbound and
+// outbound transfers of different blocks overlap each other and the compute (PCIe is full
+// duplex), and the call is two launches (B staging, this) instead of three.
+//   Ch     the caller's C, column-major, ld = M, in/out IN PLACE (a block reads its whole
+//          tile before it writes any of it, and tiles of different blocks are disjoint)
+//   host requirements: M % E == 0 and Ch 16-byte aligned (every segment piece is then a
+//          whole, aligned 16-byte unit), N <= G * E (one vector per lane)
+// dynamic smem = window + A slice (as spmm_window_kernel) + ncols_pad * (32 + E) * sizeof(T)
+template <typename T, int G, bool STRICT>
+__global__ void __launch_bounds__(32 * G)
+spmm_window_hostc_kernel(const int M, const int4 *__restrict__ blocks, const int *__restrict__ rowptr,
+                         const int *__restrict__ colidx, const T *__restrict__ val, const T *__restrict__ B,
+                         const uint32_t ldbv, T *Ch, const int N, const T alpha, const T beta, const int nvec,
+                         const uint32_t tile_off) {
+    using V = typename VecOf<T>::type;
+    constexpr int E = VecOf<T>::E;
+    constexpr int LDT = 32 + E;  // padded column of the C tile: keeps 16-byte alignment, spreads banks
+    constexpr int PPC = 32 / E;  // 16-byte pieces per 32-row column segment
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    const int lg = threadIdx.x & (G - 1);
+    const int rl = threadIdx.x / G;  // row inside the block
+    const int r0 = blockIdx.x * 32;
+    const int row = r0 + rl;
+    const int4 blk = __ldg(blocks + blockIdx.x);
+    const int jal = blk.z & ~3;
+    const uint32_t cnt = (uint32_t)((blk.w - jal + 3) & ~3);
+    const uint32_t wbytes = (uint32_t)blk.y * ldbv * 16u;
+    const V *win = reinterpret_cast<const V *>(smem_raw);
+    const T *sval = reinterpret_cast<const T *>(smem_raw + wbytes);
+    const int *scol = reinterpret_cast<const int *>(smem_raw + wbytes + (size_t)cnt * sizeof(T));
+    T *tile = reinterpret_cast<T *>(smem_raw + tile_off);  // tile[c * LDT + r], c < nvec * E
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && blk.w > blk.z) {
+        const uint64_t pol_a = policy_evict_first();
+        mbar_expect_tx(&bar, wbytes + cnt * (uint32_t)(sizeof(T) + 4));
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(B) + (size_t)blk.x * ldbv * 16u;
+        uint64_t pol_b;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_b));
+        for (uint32_t o = 0; o < wbytes; o += 32768u)
+            tma_bulk_g2s(smem_raw + o, src + o, min(32768u, wbytes - o), &bar, pol_b);
+        tma_bulk_g2s(const_cast<T *>(sval), val + jal, cnt * (uint32_t)sizeof(T), &bar, pol_a);
+        tma_bulk_g2s(const_cast<int *>(scol), colidx + jal, cnt * 4u, &bar, pol_a);
+    }
+    // C_in tile from the caller's array: piece p = (column c, 16-byte unit k of the segment)
+    const int npieces = N * PPC;
+    for (int p = threadIdx.x; p < npieces; p += 32 * G) {
+        const int c = p / PPC, k = p - c * PPC;
+        V v;
+        vzero(v);
+        if (r0 + k * E < M) v = *reinterpret_cast<const V *>(Ch + (size_t)M * c + r0 + k * E);
+        *reinterpret_cast<V *>(tile + c * LDT + k * E) = v;
+    }
+    __syncthreads();
+    const bool mine = lg < nvec && row < M;
+    if (mine) {
+        const int begin = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+        T cin[E], out[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) cin[e] = (lg * E + e < N) ? tile[(lg * E + e) * LDT + rl] : T(0);
+        V acc;
+        vzero(acc);
+        if (blk.w > blk.z) mbar_wait(&bar, 0);
+        const V *w = win + lg;
+        const int cmin = blk.x;
+        int j = begin;
+        for (; j + 4 <= end; j += 4) {
+            int c[4];
+            T a[4];
+            V b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { c[u] = scol[j + u - jal]; a[u] = sval[j + u - jal]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) b[u] = w[(uint32_t)(c[u] - cmin) * ldbv];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) vmac<STRICT>(acc, a[u], b[u]);
+        }
+        for (; j < end; ++j) vmac<STRICT>(acc, sval[j - jal], w[(uint32_t)(scol[j - jal] - cmin) * ldbv]);
+        const T *ap = reinterpret_cast<const T *>(&acc);
+#pragma unroll
+        for (int e = 0; e < E; ++e) out[e] = axpby<STRICT>(alpha, ap[e], beta, cin[e]);
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            if (lg * E + e < N) tile[(lg * E + e) * LDT + rl] = out[e];
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < npieces; p += 32 * G) {
+        const int c = p / PPC, k = p - c * PPC;
+        if (r0 + k * E < M)
+            *reinterpret_cast<V *>(Ch + (size_t)M * c + r0 + k * E) = *reinterpret_cast<const V *>(tile + c * LDT + k * E);
+    }
+}
+
 // ---- one row group per row (variant 1: matrices that fill less than one wave) ---
 // Latency-oriented walk of one row for G <= 8.  Entries travel in chunks of 8 (each
 // lane holds 8/G (col,val) pairs of a chunk), one chunk is one batch of 8 B-row gathers;

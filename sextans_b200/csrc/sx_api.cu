@@ -138,6 +138,7 @@ struct sx_ctx {
     int kernel = 0;
     int item_nnz = 0;  // 0 = auto
     int prefetch = -1;  // SX_OPT_PREFETCH: -1 auto, 0 off, 1 on
+    int host_fused = 0;  // SX_OPT_HOST_FUSED (experimental)
     int64_t zerocopy_bytes = 3 << 19;  // 1.5 MiB: above that the copy engines win
     int last_path = 0;  // 1: the last host-facing call took the zero-copy path
     bool segments_dirty = false;
@@ -949,6 +950,79 @@ void *mapped_alias(const void *host) {
     return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
 }
 
+// SX_OPT_HOST_FUSED: the zero-copy call for a matrix that takes variant 3, with C read
+// from and written to the caller's array by the SpMM kernel itself
+// (spmm_window_hostc_kernel): B staging + one kernel instead of three launches.  Returns
+// SX_OK with *done = false when the call does not qualify (the caller then takes the
+// regular zero-copy path).  The variant choice below mirrors launch_shape's.
+template <typename T, int G, bool STRICT>
+int launch_hostc(sx_ctx *c, int N, T alpha, T beta, T *dC, size_t wsmem) {
+    constexpr int E = sx::VecOf<T>::E;
+    const int nvec = (N * (int)sizeof(T) + 15) / 16;
+    const size_t tile_off = (wsmem + 15) & ~(size_t)15;
+    const size_t smem = tile_off + (size_t)nvec * E * (32 + E) * sizeof(T);
+    auto kern = sx::spmm_window_hostc_kernel<T, G, STRICT>;
+    if (smem > 48 * 1024 &&
+        std::find(c->big_smem_ok.begin(), c->big_smem_ok.end(), (const void *)kern) == c->big_smem_ok.end()) {
+        SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        c->big_smem_ok.push_back((const void *)kern);
+    }
+    kern<<<(unsigned)c->nwblocks, 32 * G, smem, c->stream>>>(
+        c->M, (const int4 *)c->wblocks.p, (const int *)c->rowptr.p, (const int *)c->colidx.p, (const T *)c->val.p,
+        (const T *)c->B.p, (uint32_t)(c->ld / E), dC, N, alpha, beta, nvec, (uint32_t)tile_off);
+    c->launches++;
+    c->last_kernel = 60000 + G * 100 + 10 + (STRICT ? 0 : 1);
+    SX_CUDA(cudaGetLastError());
+    return SX_OK;
+}
+
+template <typename T>
+int spmm_host_fused(sx_ctx *c, int N, T alpha, const void *dB, T beta, void *dC, bool *done) {
+    constexpr int E = sx::VecOf<T>::E;
+    *done = false;
+    if (!c->host_fused || c->tile_steps > 0 || !c->wins.empty() || c->M == 0 || c->nwblocks == 0) return SX_OK;
+    if (c->kernel != 0 && c->kernel != 3) return SX_OK;
+    if (c->M % E || c->K % E || (((uintptr_t)dB | (uintptr_t)dC) & 15)) return SX_OK;
+    const int nvec = (N * (int)sizeof(T) + 15) / 16;
+    Shape s;
+    if (!pick_shape(nvec, &s) || s.G > 16 || s.VPL != 1) return SX_OK;
+    int rc;
+    if ((rc = set_columns(c, N))) return rc;
+    const size_t wsmem = (size_t)c->max_span * (size_t)(c->ld / E) * 16 + ((size_t)c->max_block_nnz + 8) * (sizeof(T) + 4) + 16;
+    const size_t total = ((wsmem + 15) & ~(size_t)15) + (size_t)nvec * E * (32 + E) * sizeof(T);
+    if (wsmem > 200 * 1024 || total > 227 * 1024) return SX_OK;
+    const int cap = (int)std::max<size_t>(1, (220 * 1024) / wsmem);
+    if (c->kernel == 0 && !(cap >= 2 || (int64_t)c->nwblocks <= (int64_t)4 * c->sm_count * cap)) return SX_OK;
+    // B: column-major host -> row-major device image (the pair kernel with no C tiles)
+    const size_t szB = std::max<size_t>((size_t)c->K * c->ld * sizeof(T), 16);
+    if ((rc = c->B.ensure(szB))) return rc;
+    constexpr int VEC = 16 / (int)sizeof(T);
+    const int64_t tB = ((int64_t)c->K + 32 * VEC - 1) / (32 * VEC), tcol = (c->ld + 31) / 32;
+    if (tB * tcol > 0) {
+        dim3 block(32, 8), grid((unsigned)(tB * tcol));
+        sx::colmajor_to_rowmajor_pair_kernel<T, VEC><<<grid, block, 0, c->stream>>>(
+            c->K, 0, N, (const T *)dB, (const T *)dB, (T *)c->B.p, (T *)c->B.p, c->ld, (int)tcol, tB * tcol);
+        c->launches++;
+        SX_CUDA(cudaGetLastError());
+    }
+    c->has_B = true;
+    c->has_C = false;  // C never exists as a device image on this path
+    const bool strict = c->arith == 0;
+#define SX_HOSTC(GG)                                                                             \
+    rc = strict ? launch_hostc<T, GG, true>(c, N, alpha, beta, (T *)dC, wsmem)                   \
+                : launch_hostc<T, GG, false>(c, N, alpha, beta, (T *)dC, wsmem)
+    switch (s.G) {
+        case 2: SX_HOSTC(2); break;
+        case 4: SX_HOSTC(4); break;
+        case 8: SX_HOSTC(8); break;
+        default: SX_HOSTC(16); break;
+    }
+#undef SX_HOSTC
+    if (rc) return rc;
+    *done = true;
+    return SX_OK;
+}
+
 // The host-facing call.  Two ways in and out of the device:
 //   * page-locked B and C up to SX_OPT_ZEROCOPY_BYTES together: no copy-engine
 //     transfers at all -- one kernel reads both column-major host operands over PCIe and
@@ -968,6 +1042,15 @@ int spmm_host(sx_ctx *c, int N, T alpha, const T *B, T beta, T *C, int rp_time, 
     const void *dB = nullptr;
     void *dC = nullptr;
     if (N >= 1 && bytes <= (size_t)c->zerocopy_bytes && (dB = mapped_alias(B)) && (dC = mapped_alias(C))) {
+        if (!kernel_ns && rp_time <= 1) {
+            // nobody asked for the kernel-only time: the SpMM kernel may carry C's transfers
+            bool done = false;
+            if ((rc = spmm_host_fused<T>(c, N, alpha, dB, beta, dC, &done))) return rc;
+            if (done) {
+                c->last_path = 2;
+                return finish_stream(c, nullptr);
+            }
+        }
         if ((rc = set_columns(c, N))) return rc;
         const size_t szB = std::max<size_t>((size_t)c->K * c->ld * sizeof(T), 16);
         const size_t szC = std::max<size_t>((size_t)c->M * c->ld * sizeof(T), 16);
@@ -1139,6 +1222,10 @@ int sx_set_option(sx_ctx *c, int option, int64_t value) {
             c->segments_dirty = c->has_A;
             if (c->rest) c->rest->segments_dirty = true;
             for (sx_ctx *k : c->wins) k->segments_dirty = true;
+            return SX_OK;
+        case SX_OPT_HOST_FUSED:
+            if (value != 0 && value != 1) return fail(SX_ERR_INVALID, "SX_OPT_HOST_FUSED is 0 or 1");
+            c->host_fused = (int)value;
             return SX_OK;
         case SX_OPT_PREFETCH:
             if (value < -1 || value > 1) return fail(SX_ERR_INVALID, "SX_OPT_PREFETCH is -1 (auto), 0 or 1");
