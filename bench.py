@@ -66,6 +66,7 @@ def parse():
     p.add_argument("--band", type=int, default=2000, help="fem workload: couplings reach +-band nodes")
     p.add_argument("--tiles", type=int, default=0, help="SX_OPT_TILE_MIN_ROWS (fp64 dense-tile tensor-core variant; 0 off)")
     p.add_argument("--col-window-rows", type=int, default=0, help="SX_OPT_COL_WINDOW_ROWS (column-window passes keeping a window of B in L2; 0 off, -1 = 32 MiB of B per window)")
+    p.add_argument("--host-fused", action="store_true", help="SX_OPT_HOST_FUSED (experimental): e2e calls pass kernel_ns=NULL and the SpMM kernel carries C across PCIe")
     p.add_argument("--ref-threads", type=int, default=1, help="--impl reference: threads of the CPU path (1 = as the reference runs it; -1 = all cores, OpenMP port)")
     p.add_argument("--peer-bytes", type=int, default=8 << 20, help="N>1: B images up to this size travel by peer copy instead of NCCL")
     p.add_argument("--peer-mode", default="fused", choices=["fused", "memops"])
@@ -334,6 +335,7 @@ def run_native(args):
         if cw < 0:  # a window of B of ~32 MiB: well inside one L2 partition
             cw = max(1, (32 << 20) // (ld * s))
         e.set_option(sx.OPT_COL_WINDOW_ROWS, cw)
+        e.set_option(sx.OPT_HOST_FUSED, 1 if args.host_fused else 0)
         if args.split >= 0:
             e.set_option(sx.OPT_SPLIT_ROW_NNZ, args.split)
         e.upload_csr(M, K, w["rowptr"], w["colidx"], w["val"])
@@ -485,7 +487,7 @@ def run_native(args):
     hB[:] = w["B"]
     for _ in range(3):
         hC[:] = w["Cin"]
-        eng.spmm(N, ALPHA, hB, BETA, hC)
+        eng.spmm(N, ALPHA, hB, BETA, hC, want_ns=not args.host_fused)
     checksum = float(np.asarray(hC, dtype=np.float64).sum())
     barrier()
     l1 = launches()
@@ -493,7 +495,7 @@ def run_native(args):
     for _ in range(args.steps):
         hC[:] = w["Cin"]                       # restore the in/out operand (untimed)
         t0 = time.perf_counter()
-        eng.spmm(N, ALPHA, hB, BETA, hC)      # H2D B, H2D C, kernels, D2H C; returns synchronised
+        eng.spmm(N, ALPHA, hB, BETA, hC, want_ns=not args.host_fused)   # H2D B, H2D C, kernels, D2H C; returns synchronised
         e2e_s += time.perf_counter() - t0
     launches_e2e = launches() - l1
     barrier()
@@ -523,7 +525,7 @@ def run_native(args):
                    + f" <G={lk % 10000 // 100}, VPL={lk % 100 // 10}, {'fast' if lk % 10 else 'strict'}>"
                    if lk // 10000 != 5 else f"spmm_staged_kernel<WIN>, {lk % 10000} column-window passes of {cw} columns each") + (
                    (f", {eng.info(sx.INFO_ITEMS)} items of <= {eng.info(sx.INFO_ITEM_NNZ)} nnz, {eng.info(sx.INFO_SPLIT_ROWS)} split rows" if lk // 10000 == 2 else "") + tiles_note)
-    host_path = "zero-copy kernels over PCIe (no memcpy)" if eng.info(sx.INFO_HOST_PATH) == 1 else "cudaMemcpyAsync + layout kernels"
+    host_path = {1: "zero-copy kernels over PCIe (no memcpy)", 2: "zero-copy, C carried by the SpMM kernel (SX_OPT_HOST_FUSED)"}.get(eng.info(sx.INFO_HOST_PATH), "cudaMemcpyAsync + layout kernels")
     if rank == 0:
         line = {
             "metric": "SpMM GFLOP/s (2*nnz*N)", "value": value, "unit": "GFLOP/s",
