@@ -1,0 +1,18 @@
+#!/bin/bash
+# First GPU call of the next round: what could not be run at the end of round 1.
+#   1. the driver's own GPU test command
+#   2. the experimental paths' parity tests (SX_OPT_HOST_FUSED)
+#   3. e2e of the default bench with and without the fused host path
+#   4. staged-kernel tile size (SX_STAGE_KB) on the C5-like probe, with the L2 prefetch
+mkdir -p gpurun_out
+( time timeout 300 python -m pytest tests -x -q -m gpu -p no:cacheprovider ) > gpurun_out/r2a_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2a_pytest.log
+SX_TEST_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_experimental_gpu.py -q -p no:cacheprovider > gpurun_out/r2a_experimental.log 2>&1; echo "experimental rc=$?"; tail -15 gpurun_out/r2a_experimental.log
+for flag in "" "--host-fused"; do
+  python bench.py --no-cpu-baseline $flag > gpurun_out/r2a_bench_nasa$flag.json 2> gpurun_out/r2a_bench_nasa$flag.err; echo "bench nasa4704 $flag rc=$?"
+  python -c "import json,sys; d=json.load(open(sys.argv[1])); print('  kernel us', round(d['ms_per_step']*1e3,2), 'e2e us', round(d['e2e']['ms_per_step']*1e3,1), d['e2e']['path'])" gpurun_out/r2a_bench_nasa$flag.json
+  python bench.py --workload pcrystk02 --steps 200 --no-cpu-baseline $flag > gpurun_out/r2a_bench_pcrystk02$flag.json 2> /dev/null
+  python -c "import json,sys; d=json.load(open(sys.argv[1])); print('  kernel us', round(d['ms_per_step']*1e3,2), 'e2e us', round(d['e2e']['ms_per_step']*1e3,1), d['e2e']['path'])" gpurun_out/r2a_bench_pcrystk02$flag.json
+done
+for kb in 28 56 84; do
+  SX_STAGE_KB=$kb PROBE_SET=0:-1 timeout 100 python scripts/probe_windows.py 2>&1 | tail -1 | sed "s/^/stage_kb=$kb /"
+done | tee gpurun_out/r2a_stage_kb.log
