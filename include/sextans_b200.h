@@ -120,7 +120,13 @@ enum sx_option {
      * C_in from and write C to the caller's page-locked array itself: B staging + one kernel
      * instead of three launches, C's inbound and outbound PCIe transfers overlapping each
      * other and the compute.  Same arithmetic, same results.  SX_INFO_HOST_PATH reports 2. */
-    SX_OPT_HOST_FUSED = 8
+    SX_OPT_HOST_FUSED = 8,
+    /* EXPERIMENTAL (off by default; not yet measured on hardware).  1: variant 3 is launched
+     * with programmatic stream serialization (PDL): its A-side prologue (block record, row
+     * pointers, TMA of the colidx/val slice) may run while the previous kernel of the stream
+     * is still finishing; B and C_in are only touched after griddepcontrol.wait.  For the
+     * launch-bound SuiteSparse configs.  Results are unaffected. */
+    SX_OPT_PDL = 9
 };
 
 enum sx_info {

@@ -7,7 +7,7 @@
 mkdir -p gpurun_out
 ( time timeout 300 python -m pytest tests -x -q -m gpu -p no:cacheprovider ) > gpurun_out/r2a_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2a_pytest.log
 SX_TEST_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_experimental_gpu.py -q -p no:cacheprovider > gpurun_out/r2a_experimental.log 2>&1; echo "experimental rc=$?"; tail -15 gpurun_out/r2a_experimental.log
-for flag in "" "--host-fused"; do
+for flag in "" "--host-fused" "--pdl"; do
   python bench.py --no-cpu-baseline $flag > gpurun_out/r2a_bench_nasa$flag.json 2> gpurun_out/r2a_bench_nasa$flag.err; echo "bench nasa4704 $flag rc=$?"
   python -c "import json,sys; d=json.load(open(sys.argv[1])); print('  kernel us', round(d['ms_per_step']*1e3,2), 'e2e us', round(d['e2e']['ms_per_step']*1e3,1), d['e2e']['path'])" gpurun_out/r2a_bench_nasa$flag.json
   python bench.py --workload pcrystk02 --steps 200 --no-cpu-baseline $flag > gpurun_out/r2a_bench_pcrystk02$flag.json 2> /dev/null

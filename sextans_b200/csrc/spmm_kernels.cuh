@@ -505,7 +505,16 @@ spmm_staged_kernel(const int nitems, const int4 *__restrict__ items, const int t
 // gather, no shuffles, one row per group in stored order (bit-exact in strict mode).
 // The dependent chain is block record -> TMA -> shared-memory arithmetic.
 // block record = {cmin, span, nnz_begin, nnz_end}; dynamic smem = window + A slice + 16.
-template <typename T, int G, bool STRICT>
+//
+// PDL = true (experimental, SX_OPT_PDL): the launch carries the programmatic-stream-
+// serialization attribute, so this grid may start while the previous kernel of the stream
+// is still running.  Everything that only touches A -- block record, row pointers, the TMA
+// of the block's colidx/val slice -- happens before griddepcontrol.wait; B and C_in, which
+// the previous kernel may have produced, are only touched after it.  launch_dependents is
+// issued right after, so that the NEXT kernel's A-side prologue overlaps this kernel's body:
+// for the launch-bound SuiteSparse configs a step is a chain of latencies (block record ->
+// TMA -> arithmetic), and this takes the A-side part of it off the critical path.
+template <typename T, int G, bool STRICT, bool PDL = false>
 __global__ void __launch_bounds__(32 * G)
 spmm_window_kernel(const int M, const int4 *__restrict__ blocks, const int *__restrict__ rowptr,
                    const int *__restrict__ colidx, const T *__restrict__ val, const T *__restrict__ B,
@@ -534,17 +543,31 @@ spmm_window_kernel(const int M, const int4 *__restrict__ blocks, const int *__re
         const unsigned char *src = reinterpret_cast<const unsigned char *>(B) + (size_t)blk.x * ldbv * 16u;
         uint64_t pol_b;
         asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_b));
+        if (PDL) {  // A slice first, then wait for the previous kernel, then the B window
+            tma_bulk_g2s(const_cast<T *>(sval), val + jal, cnt * (uint32_t)sizeof(T), &bar, pol_a);
+            tma_bulk_g2s(const_cast<int *>(scol), colidx + jal, cnt * 4u, &bar, pol_a);
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+        }
         for (uint32_t o = 0; o < wbytes; o += 32768u)  // several copies in flight
             tma_bulk_g2s(smem_raw + o, src + o, min(32768u, wbytes - o), &bar, pol_b);
-        tma_bulk_g2s(const_cast<T *>(sval), val + jal, cnt * (uint32_t)sizeof(T), &bar, pol_a);
-        tma_bulk_g2s(const_cast<int *>(scol), colidx + jal, cnt * 4u, &bar, pol_a);
+        if (!PDL) {
+            tma_bulk_g2s(const_cast<T *>(sval), val + jal, cnt * (uint32_t)sizeof(T), &bar, pol_a);
+            tma_bulk_g2s(const_cast<int *>(scol), colidx + jal, cnt * 4u, &bar, pol_a);
+        }
     }
-    if (row >= M) return;  // after the barrier above; no block-wide barrier below
+    if (row >= M) {  // after the barrier above; no block-wide barrier below
+        if (PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        return;
+    }
     const int begin = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
     const bool mine = lg < nvec;
     V acc, cin;
     vzero(acc);
     vzero(cin);
+    if (PDL) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");               // C_in may come from the previous kernel
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next one may start its prologue
+    }
     if (mine) cin = reinterpret_cast<const V *>(Cin)[(size_t)row * ldcv + lg];
     if (blk.w > blk.z) mbar_wait(&bar, 0);
     if (mine) {

@@ -139,6 +139,7 @@ struct sx_ctx {
     int item_nnz = 0;  // 0 = auto
     int prefetch = -1;  // SX_OPT_PREFETCH: -1 auto, 0 off, 1 on
     int host_fused = 0;  // SX_OPT_HOST_FUSED (experimental)
+    int pdl = 0;         // SX_OPT_PDL (experimental)
     int64_t zerocopy_bytes = 3 << 19;  // 1.5 MiB: above that the copy engines win
     int last_path = 0;  // 1: the last host-facing call took the zero-copy path
     bool segments_dirty = false;
@@ -217,12 +218,29 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
     if constexpr (G <= 16 && VPL == 1) {
         if (variant == 3) {
             constexpr int E = sx::VecOf<T>::E;
-            auto kern = sx::spmm_window_kernel<T, G, STRICT>;
+            auto kern = c->pdl ? sx::spmm_window_kernel<T, G, STRICT, true> : sx::spmm_window_kernel<T, G, STRICT, false>;
             if (wsmem > 48 * 1024 &&
                 std::find(c->big_smem_ok.begin(), c->big_smem_ok.end(), (const void *)kern) == c->big_smem_ok.end()) {
                 SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                 c->big_smem_ok.push_back((const void *)kern);
             }
+            if (c->pdl) {
+                // programmatic dependent launch: this grid's A-side prologue may overlap the
+                // previous kernel of the stream (see the kernel)
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)c->nwblocks);
+                cfg.blockDim = dim3(32 * G);
+                cfg.dynamicSmemBytes = wsmem;
+                cfg.stream = c->stream;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at;
+                cfg.numAttrs = 1;
+                SX_CUDA(cudaLaunchKernelEx(&cfg, kern, c->M, (const int4 *)c->wblocks.p, (const int *)c->rowptr.p,
+                                           (const int *)c->colidx.p, (const T *)c->val.p, dB, (uint32_t)(ldb / E), dCin,
+                                           dCout, (uint32_t)(ldc / E), alpha, beta, nvec));
+            } else
             kern<<<(unsigned)c->nwblocks, 32 * G, wsmem, c->stream>>>(
                 c->M, (const int4 *)c->wblocks.p, (const int *)c->rowptr.p, (const int *)c->colidx.p,
                 (const T *)c->val.p, dB, (uint32_t)(ldb / E), dCin, dCout, (uint32_t)(ldc / E), alpha, beta, nvec);
@@ -1222,6 +1240,10 @@ int sx_set_option(sx_ctx *c, int option, int64_t value) {
             c->segments_dirty = c->has_A;
             if (c->rest) c->rest->segments_dirty = true;
             for (sx_ctx *k : c->wins) k->segments_dirty = true;
+            return SX_OK;
+        case SX_OPT_PDL:
+            if (value != 0 && value != 1) return fail(SX_ERR_INVALID, "SX_OPT_PDL is 0 or 1");
+            c->pdl = (int)value;
             return SX_OK;
         case SX_OPT_HOST_FUSED:
             if (value != 0 && value != 1) return fail(SX_ERR_INVALID, "SX_OPT_HOST_FUSED is 0 or 1");

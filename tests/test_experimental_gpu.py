@@ -84,3 +84,39 @@ def test_host_fused_on_the_canned_run(eng, golden):
     assert eng.info(sx.INFO_HOST_PATH) == 2
     run = [r for r in golden["suitesparse"]["nasa4704"]["runs"] if r["kind"] == "default" and r["N"] == 16][0]
     assert sha(np.asarray(hC)) == run["C_sha256"]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_pdl_window_kernel_in_a_dependent_chain(eng, dtype):
+    """SX_OPT_PDL: back-to-back launches of variant 3 whose C_in is the previous launch's
+    C_out (in place) and whose B was produced by a kernel just before -- the early-started
+    prologue must not touch either before the previous kernel is complete."""
+    torch = pytest.importorskip("torch")
+    M = K = 4096
+    N = 16
+    rp, ci, v = banded_csr(M, K, 200, 24, 77, dtype)
+    B, Cin = random_dense(M, K, N, 77, dtype)
+    ref = Cin.copy()
+    for _ in range(5):
+        ref = oracle.spmm_csr(M, N, K, rp, ci, v, dtype(0.5), B, dtype(0.25), ref)
+    eng.set_option(sx.OPT_KERNEL, 3)
+    eng.set_option(sx.OPT_PDL, 1)
+    eng.upload_csr(M, K, rp, ci, v)
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)
+    try:
+        with torch.cuda.stream(stream):
+            dB_cm = torch.from_numpy(B).cuda()
+            dC = torch.from_numpy(np.ascontiguousarray(Cin.reshape(N, M).T)).cuda()   # row-major M x N
+            dB = torch.empty(K * N, dtype=dB_cm.dtype, device="cuda")
+            for rep in range(3):                         # also exercises re-running the whole chain
+                dCw = dC.clone()
+                eng.colmajor_to_rowmajor(K, N, dB_cm, dB, N)   # B produced right before the first SpMM
+                for _ in range(5):
+                    eng.spmm_device(N, dtype(0.5), dB, N, dtype(0.25), dCw, dCw, N)
+                stream.synchronize()
+                assert eng.info(sx.INFO_LAST_KERNEL) // 10000 == 3
+                got = np.ascontiguousarray(dCw.cpu().numpy().T).ravel()
+                assert np.array_equal(bits(got), bits(ref)), rep
+    finally:
+        eng.set_stream(None)
