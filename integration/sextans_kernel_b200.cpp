@@ -9,8 +9,8 @@
 // -- its loader, its FPGA preprocessing, its B/C channel repacking, its verification --
 // runs against a B200 instead of the FPGA / the TAPA software simulation:
 //
-//   g++ -O2 -std=c++17 -I<repo>/include/tapa_compat -I<repo>/include -I<ref>/src \
-//       <ref>/src/sextans-host.cpp <repo>/integration/sextans_kernel_b200.cpp \
+//   g++ -O2 -std=c++17 -I<repo>/include/tapa_compat -I<repo>/include -I<ref>/src
+//       <ref>/src/sextans-host.cpp <repo>/integration/sextans_kernel_b200.cpp
 //       -L<repo>/sextans_b200 -lsextans_b200 -Wl,-rpath,<repo>/sextans_b200 -o sextans
 //
 // (oracle/Makefile target `ref_host` does exactly this into oracle/_ref/.)  It includes
