@@ -66,6 +66,7 @@ def parse():
     p.add_argument("--band", type=int, default=2000, help="fem workload: couplings reach +-band nodes")
     p.add_argument("--tiles", type=int, default=0, help="SX_OPT_TILE_MIN_ROWS (fp64 dense-tile tensor-core variant; 0 off)")
     p.add_argument("--col-window-rows", type=int, default=0, help="SX_OPT_COL_WINDOW_ROWS (column-window passes keeping a window of B in L2; 0 off, -1 = 32 MiB of B per window)")
+    p.add_argument("--window-rows", type=int, default=0, choices=[0, 32, 64, 128], help="SX_OPT_WINDOW_ROWS (experimental): rows per block of variant 3")
     p.add_argument("--pdl", action="store_true", help="SX_OPT_PDL (experimental): variant 3 launched with programmatic stream serialization")
     p.add_argument("--host-fused", action="store_true", help="SX_OPT_HOST_FUSED (experimental): e2e calls pass kernel_ns=NULL and the SpMM kernel carries C across PCIe")
     p.add_argument("--ref-threads", type=int, default=1, help="--impl reference: threads of the CPU path (1 = as the reference runs it; -1 = all cores, OpenMP port)")
@@ -338,6 +339,7 @@ def run_native(args):
         e.set_option(sx.OPT_COL_WINDOW_ROWS, cw)
         e.set_option(sx.OPT_HOST_FUSED, 1 if args.host_fused else 0)
         e.set_option(sx.OPT_PDL, 1 if args.pdl else 0)
+        e.set_option(sx.OPT_WINDOW_ROWS, args.window_rows)
         if args.split >= 0:
             e.set_option(sx.OPT_SPLIT_ROW_NNZ, args.split)
         e.upload_csr(M, K, w["rowptr"], w["colidx"], w["val"])

@@ -126,7 +126,15 @@ enum sx_option {
      * pointers, TMA of the colidx/val slice) may run while the previous kernel of the stream
      * is still finishing; B and C_in are only touched after griddepcontrol.wait.  For the
      * launch-bound SuiteSparse configs.  Results are unaffected. */
-    SX_OPT_PDL = 9
+    SX_OPT_PDL = 9,
+    /* EXPERIMENTAL (not yet measured on hardware); read by the NEXT sx_upload_csr_*.
+     * Rows per thread block of variant 3: 0 or 32 (default, the validated kernel), 64, 128.
+     * Consecutive 32-row blocks of a banded matrix stage almost the same B window, so taller
+     * blocks move proportionally fewer window bytes out of L2 and need fewer waves
+     * (pcrystk02: 437 blocks -> 219 / 110).  Used where the taller block's window and A
+     * slice still fit in shared memory and RB * lanes-per-row <= 1024 threads; otherwise
+     * the 32-row blocks run.  Results are unaffected. */
+    SX_OPT_WINDOW_ROWS = 10
 };
 
 enum sx_info {

@@ -13,6 +13,10 @@ for flag in "" "--host-fused" "--pdl"; do
   python bench.py --workload pcrystk02 --steps 200 --no-cpu-baseline $flag > gpurun_out/r2a_bench_pcrystk02$flag.json 2> /dev/null
   python -c "import json,sys; d=json.load(open(sys.argv[1])); print('  kernel us', round(d['ms_per_step']*1e3,2), 'e2e us', round(d['e2e']['ms_per_step']*1e3,1), d['e2e']['path'])" gpurun_out/r2a_bench_pcrystk02$flag.json
 done
+for n in 8 16 32; do for wr in 0 64 128; do
+  python bench.py --workload pcrystk02 --ncols $n --steps 200 --no-cpu-baseline --window-rows $wr > gpurun_out/r2a_pcrystk02_n${n}_wr$wr.json 2>/dev/null
+  python -c "import json,sys; d=json.load(open(sys.argv[1])); print('pcrystk02 N=$n window-rows=$wr: kernel us', round(d['ms_per_step']*1e3,2), d['roofline']['kernel'][:50])" gpurun_out/r2a_pcrystk02_n${n}_wr$wr.json
+done; done
 for kb in 28 56 84; do
   SX_STAGE_KB=$kb PROBE_SET=0:-1 timeout 100 python scripts/probe_windows.py 2>&1 | tail -1 | sed "s/^/stage_kb=$kb /"
 done | tee gpurun_out/r2a_stage_kb.log

@@ -514,8 +514,12 @@ spmm_staged_kernel(const int nitems, const int4 *__restrict__ items, const int t
 // issued right after, so that the NEXT kernel's A-side prologue overlaps this kernel's body:
 // for the launch-bound SuiteSparse configs a step is a chain of latencies (block record ->
 // TMA -> arithmetic), and this takes the A-side part of it off the critical path.
-template <typename T, int G, bool STRICT, bool PDL = false>
-__global__ void __launch_bounds__(32 * G)
+// RB = rows per block (32; 64 and 128 experimental, SX_OPT_WINDOW_ROWS): consecutive
+// 32-row blocks of a banded matrix stage almost the same window (pcrystk02: 437 windows of
+// ~950 B rows for a B of 13 965 rows), so a taller block moves proportionally fewer window
+// bytes from L2 and needs fewer waves; the block record then describes RB rows.
+template <typename T, int G, bool STRICT, bool PDL = false, int RB = 32>
+__global__ void __launch_bounds__(RB * G)
 spmm_window_kernel(const int M, const int4 *__restrict__ blocks, const int *__restrict__ rowptr,
                    const int *__restrict__ colidx, const T *__restrict__ val, const T *__restrict__ B,
                    const uint32_t ldbv, const T *Cin, T *Cout, const uint32_t ldcv, const T alpha,
@@ -524,7 +528,7 @@ spmm_window_kernel(const int M, const int4 *__restrict__ blocks, const int *__re
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     const int lg = threadIdx.x & (G - 1);
-    const int row = blockIdx.x * 32 + threadIdx.x / G;
+    const int row = blockIdx.x * RB + threadIdx.x / G;
     const int4 blk = __ldg(blocks + blockIdx.x);
     const int jal = blk.z & ~3;  // 16-byte aligned start of the A slice
     const uint32_t cnt = (uint32_t)((blk.w - jal + 3) & ~3);
@@ -551,8 +555,18 @@ spmm_window_kernel(const int M, const int4 *__restrict__ blocks, const int *__re
         for (uint32_t o = 0; o < wbytes; o += 32768u)  // several copies in flight
             tma_bulk_g2s(smem_raw + o, src + o, min(32768u, wbytes - o), &bar, pol_b);
         if (!PDL) {
-            tma_bulk_g2s(const_cast<T *>(sval), val + jal, cnt * (uint32_t)sizeof(T), &bar, pol_a);
-            tma_bulk_g2s(const_cast<int *>(scol), colidx + jal, cnt * 4u, &bar, pol_a);
+            if (RB == 32) {
+                tma_bulk_g2s(const_cast<T *>(sval), val + jal, cnt * (uint32_t)sizeof(T), &bar, pol_a);
+                tma_bulk_g2s(const_cast<int *>(scol), colidx + jal, cnt * 4u, &bar, pol_a);
+            } else {  // a taller block's A slice is tens of KB: several copies in flight, like the window
+                const uint32_t vb = cnt * (uint32_t)sizeof(T), cb = cnt * 4u;
+                for (uint32_t o = 0; o < vb; o += 16384u)
+                    tma_bulk_g2s(reinterpret_cast<unsigned char *>(const_cast<T *>(sval)) + o,
+                                 reinterpret_cast<const unsigned char *>(val + jal) + o, min(16384u, vb - o), &bar, pol_a);
+                for (uint32_t o = 0; o < cb; o += 16384u)
+                    tma_bulk_g2s(reinterpret_cast<unsigned char *>(const_cast<int *>(scol)) + o,
+                                 reinterpret_cast<const unsigned char *>(colidx + jal) + o, min(16384u, cb - o), &bar, pol_a);
+            }
         }
     }
     if (row >= M) {  // after the barrier above; no block-wide barrier below

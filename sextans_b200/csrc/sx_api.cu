@@ -105,6 +105,9 @@ struct sx_ctx {
     // variant 3: per block of 32 rows {first column, column span, nnz begin, nnz end}
     DevBuf wblocks;
     int nwblocks = 0, max_span = 0, max_block_nnz = 0;
+    // the same for blocks of 64 and 128 rows (SX_OPT_WINDOW_ROWS, experimental)
+    struct WideBlocks { DevBuf blocks; int n = 0, max_span = 0, max_block_nnz = 0; } wide[2];
+    int window_rows = 0;  // 0 / 32: the validated 32-row blocks; 64, 128: wide[0], wide[1]
     std::vector<const void *> big_smem_ok;  // kernels already allowed > 48 KB of dynamic smem
     // dense-tile split A = A_tiles + A_rest (fp64, SX_OPT_TILE_MIN_ROWS > 0 at upload)
     int tile_min_rows = 0;
@@ -215,6 +218,35 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
     int variant = c->kernel != 0 ? c->kernel : (window_auto ? 3 : (sub_wave ? 1 : 2));
     if (variant == 3 && !window_ok) variant = sub_wave ? 1 : 2;
     if (c->win_mode) variant = 2;  // a column-window pass: only the staged kernel carries running sums
+    // SX_OPT_WINDOW_ROWS (experimental): blocks of 64 / 128 rows where RB * G <= 1024 threads
+    if constexpr (G >= 4 && G <= 16 && VPL == 1) {
+        if (variant == 3 && c->window_rows > 32 && !c->pdl) {
+            constexpr int E = sx::VecOf<T>::E;
+            const int w = (c->window_rows >= 128 && G <= 8) ? 1 : 0;
+            const sx_ctx::WideBlocks &W = c->wide[w];
+            const size_t smem = (size_t)W.max_span * (size_t)(ldb / E) * 16 + ((size_t)W.max_block_nnz + 8) * (sizeof(T) + 4) + 16;
+            if (W.n > 0 && smem <= 200 * 1024) {
+                auto launch_rb = [&](auto kern, int RB) -> int {
+                    if (smem > 48 * 1024 &&
+                        std::find(c->big_smem_ok.begin(), c->big_smem_ok.end(), (const void *)kern) == c->big_smem_ok.end()) {
+                        SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                        c->big_smem_ok.push_back((const void *)kern);
+                    }
+                    kern<<<(unsigned)W.n, RB * G, smem, c->stream>>>(
+                        c->M, (const int4 *)W.blocks.p, (const int *)c->rowptr.p, (const int *)c->colidx.p,
+                        (const T *)c->val.p, dB, (uint32_t)(ldb / E), dCin, dCout, (uint32_t)(ldc / E), alpha, beta, nvec);
+                    c->launches++;
+                    c->last_kernel = 30000 + G * 100 + VPL * 10 + (STRICT ? 0 : 1);
+                    SX_CUDA(cudaGetLastError());
+                    return SX_OK;
+                };
+                if constexpr (G <= 8) {
+                    if (w == 1) return launch_rb(sx::spmm_window_kernel<T, G, STRICT, false, 128>, 128);
+                }
+                return launch_rb(sx::spmm_window_kernel<T, G, STRICT, false, 64>, 64);
+            }
+        }
+    }
     if constexpr (G <= 16 && VPL == 1) {
         if (variant == 3) {
             constexpr int E = sx::VecOf<T>::E;
@@ -628,6 +660,46 @@ int build_window_blocks(sx_ctx *c, int M, const int32_t *rowptr, const int32_t *
     return SX_OK;
 }
 
+// Block records for blocks of 64 and 128 rows (same rules as build_window_blocks).
+int build_wide_window_blocks(sx_ctx *c, int M, const int32_t *rowptr, const int32_t *colidx) {
+    for (int w = 0; w < 2; ++w) {
+        sx_ctx::WideBlocks &W = c->wide[w];
+        W.n = W.max_span = W.max_block_nnz = 0;
+        if (M == 0 || c->nwblocks == 0) continue;  // the 32-row blocks did not qualify: neither will these
+        const int RB = 64 << w;
+        const int nb = (M + RB - 1) / RB;
+        std::vector<int32_t> blk((size_t)nb * 4);
+        int64_t span_sum = 0;
+        int max_span = 0, max_block_nnz = 0;
+        bool ok = true;
+        for (int b = 0; b < nb && ok; ++b) {
+            const int r0 = b * RB, r1 = std::min(M, r0 + RB);
+            const int32_t jb = rowptr[r0], je = rowptr[r1];
+            int32_t lo = INT32_MAX, hi = -1;
+            for (int32_t j = jb; j < je; ++j) { lo = std::min(lo, colidx[j]); hi = std::max(hi, colidx[j]); }
+            if (je == jb) { lo = 0; hi = -1; }
+            const int span = hi - lo + 1;
+            if ((int64_t)span * 32 > 200 * 1024 || (int64_t)(je - jb) * 8 > 200 * 1024) ok = false;
+            blk[(size_t)b * 4 + 0] = lo;
+            blk[(size_t)b * 4 + 1] = span;
+            blk[(size_t)b * 4 + 2] = jb;
+            blk[(size_t)b * 4 + 3] = je;
+            span_sum += span;
+            max_span = std::max(max_span, span);
+            max_block_nnz = std::max(max_block_nnz, je - (jb & ~3));
+        }
+        if (!ok || span_sum > 2 * (int64_t)rowptr[M]) continue;
+        int rc = W.blocks.ensure(blk.size() * 4);
+        if (rc) return rc;
+        SX_CUDA(cudaMemcpyAsync(W.blocks.p, blk.data(), blk.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        SX_CUDA(cudaStreamSynchronize(c->stream));
+        W.n = nb;
+        W.max_span = max_span;
+        W.max_block_nnz = max_block_nnz;
+    }
+    return SX_OK;
+}
+
 void release_child(sx_ctx *r, cudaStream_t stream) {
     r->stream = stream;
     drop_plans(r);
@@ -833,6 +905,8 @@ int upload_csr(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rowptr, cons
     c->N = 0; c->ld = 0;
     if ((rc = refresh_segments(c))) return rc;
     if ((rc = build_window_blocks(c, M, rowptr, colidx))) return rc;
+    if (c->window_rows > 32 && (rc = build_wide_window_blocks(c, M, rowptr, colidx))) return rc;
+    if (c->window_rows <= 32) c->wide[0].n = c->wide[1].n = 0;
     if ((rc = maybe_build_panels<T>(c, M, K, nnz, rowptr, colidx, val))) return rc;
     if ((rc = maybe_build_windows<T>(c, M, K, nnz, rowptr, colidx, val))) return rc;
     c->has_A = true;
@@ -1193,7 +1267,7 @@ int sx_destroy(sx_ctx *c) {
     drop_plans(c);
     drop_tiles(c);
     drop_windows(c);
-    for (DevBuf *b : {&c->step_ptr, &c->tcols, &c->tvals, &c->psum}) b->release();
+    for (DevBuf *b : {&c->step_ptr, &c->tcols, &c->tvals, &c->psum, &c->wide[0].blocks, &c->wide[1].blocks}) b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -1240,6 +1314,11 @@ int sx_set_option(sx_ctx *c, int option, int64_t value) {
             c->segments_dirty = c->has_A;
             if (c->rest) c->rest->segments_dirty = true;
             for (sx_ctx *k : c->wins) k->segments_dirty = true;
+            return SX_OK;
+        case SX_OPT_WINDOW_ROWS:
+            if (value != 0 && value != 32 && value != 64 && value != 128)
+                return fail(SX_ERR_INVALID, "SX_OPT_WINDOW_ROWS is 0 (= 32), 32, 64 or 128");
+            c->window_rows = (int)value;  // block records are built at the next sx_upload_csr_*
             return SX_OK;
         case SX_OPT_PDL:
             if (value != 0 && value != 1) return fail(SX_ERR_INVALID, "SX_OPT_PDL is 0 or 1");

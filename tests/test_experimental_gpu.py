@@ -120,3 +120,43 @@ def test_pdl_window_kernel_in_a_dependent_chain(eng, dtype):
                 assert np.array_equal(bits(got), bits(ref)), rep
     finally:
         eng.set_stream(None)
+
+
+@pytest.mark.parametrize("rows", [64, 128])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("M,K,N", [(13965, 13965, 16), (1000, 1000, 8), (999, 1200, 32), (70, 64, 4), (4000, 4000, 64)])
+def test_taller_window_blocks_bit_exact(eng, rows, dtype, M, K, N):
+    """SX_OPT_WINDOW_ROWS = 64 / 128: variant 3 with taller row blocks (or its fall-back to
+    32-row blocks where a taller block does not fit) reproduces the oracle bit for bit."""
+    rp, ci, v = banded_csr(M, K, 200, 30, M + N + rows, dtype)
+    B, Cin = random_dense(M, K, N, M + N, dtype)
+    ref = oracle.spmm_csr(M, N, K, rp, ci, v, dtype(0.85), B, dtype(-2.06), Cin.copy())
+    eng.set_option(sx.OPT_KERNEL, 3)
+    eng.set_option(sx.OPT_WINDOW_ROWS, rows)
+    eng.upload_csr(M, K, rp, ci, v)
+    for rp_time in (1, 3):
+        C = Cin.copy()
+        eng.spmm(N, dtype(0.85), B, dtype(-2.06), C, rp_time)
+        assert np.array_equal(bits(C), bits(ref))
+    # and back to the validated 32-row blocks at the next upload
+    eng.set_option(sx.OPT_WINDOW_ROWS, 0)
+    eng.upload_csr(M, K, rp, ci, v)
+    C = Cin.copy()
+    eng.spmm(N, dtype(0.85), B, dtype(-2.06), C)
+    assert np.array_equal(bits(C), bits(ref))
+
+
+@pytest.mark.parametrize("rows", [64, 128])
+def test_taller_window_blocks_on_pcrystk02_golden(eng, golden, rows):
+    from helpers import sha
+    M, K, nnz, rp, ci, v = sx.load_mtx(mtx_path("pcrystk02"), np.float32)
+    eng.set_option(sx.OPT_WINDOW_ROWS, rows)
+    eng.upload_csr(M, K, rp, ci, v)
+    for run in golden["suitesparse"]["pcrystk02"]["runs"]:
+        if run["kind"] != "default":
+            continue
+        N = run["N"]
+        B, Cin = oracle.init_dense(M, K, N, np.float32)
+        C = Cin.copy()
+        eng.spmm(N, np.float32(0.85), B, np.float32(-2.06), C)
+        assert sha(C) == run["C_sha256"], (rows, N)
