@@ -1,0 +1,92 @@
+// cuda_emu.h -- TEST INFRASTRUCTURE: just enough of the CUDA execution model to run the
+// block-level kernels of sextans_b200/csrc/spmm_kernels.cuh on the CPU, so that their
+// index arithmetic, shared-memory staging and barrier structure can be checked without a
+// GPU (tests/test_kernel_emulation_cpu.py).  One OS thread per CUDA thread, one block at a
+// time; __syncthreads is a real barrier; TMA bulk copies are memcpys that complete on an
+// emulated mbarrier.  No timing, no memory model, no warp shuffles -- kernels that need
+// those (the lane-group kernels) are not emulated; their parity is established on the GPU.
+#pragma once
+#include <algorithm>
+#include <atomic>
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __align__(n) alignas(n)
+#define __shared__ static
+
+struct uint3e { unsigned x = 0, y = 0, z = 0; };
+struct dim3 { unsigned x = 1, y = 1, z = 1; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+inline thread_local uint3e threadIdx, blockIdx;
+inline dim3 blockDim, gridDim;
+
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(8) float2 { float x, y; };
+struct alignas(16) double2 { double x, y; };
+struct alignas(16) int4 { int x, y, z, w; };
+struct alignas(8) int2 { int x, y; };
+inline float4 make_float4(float a, float b, float c, float d) { return {a, b, c, d}; }
+inline double2 make_double2(double a, double b) { return {a, b}; }
+
+using std::max;
+using std::min;
+
+namespace sx_emu {
+inline std::barrier<> *cur_barrier = nullptr;
+inline unsigned char *cur_dyn_smem = nullptr;
+inline unsigned char *dyn_smem() { return cur_dyn_smem; }
+
+// Run `body` as a grid of `grid` blocks of `block` threads with `smem` bytes of dynamic
+// shared memory per block (blocks one after the other).
+inline void launch(unsigned grid, unsigned block, size_t smem, const std::function<void()> &body) {
+    gridDim = dim3(grid);
+    blockDim = dim3(block);
+    std::vector<unsigned char> storage(smem + 256);
+    unsigned char *base = storage.data();
+    base += (128 - reinterpret_cast<uintptr_t>(base) % 128) % 128;
+    for (unsigned b = 0; b < grid; ++b) {
+        std::barrier<> bar((std::ptrdiff_t)block);
+        cur_barrier = &bar;
+        cur_dyn_smem = base;
+        std::vector<std::thread> pool;
+        pool.reserve(block);
+        for (unsigned t = 0; t < block; ++t)
+            pool.emplace_back([&, t, b] {
+                threadIdx.x = t;
+                blockIdx.x = b;
+                body();
+                bar.arrive_and_drop();  // a thread that has returned no longer takes part in barriers
+            });
+        for (auto &th : pool) th.join();
+    }
+}
+}  // namespace sx_emu
+
+inline void __syncthreads() { sx_emu::cur_barrier->arrive_and_wait(); }
+inline void __syncwarp(unsigned = 0xffffffffu) {}
+template <typename T> inline T __ldg(const T *p) { return *p; }
+template <typename T> inline T __ldcv(const T *p) { return *p; }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
+// declared so that the kernels that are not emulated still compile
+template <typename T> inline T __shfl_sync(unsigned, T v, int, int = 32) { return v; }
+template <typename T> inline T __shfl_xor_sync(unsigned, T v, int, int = 32) { return v; }
+inline long long clock64() { return 0; }
+inline void __nanosleep(unsigned) {}
+inline void __threadfence() {}
+inline void __threadfence_system() {}
+inline unsigned atomicAdd(unsigned *p, unsigned v) { return std::atomic_ref<unsigned>(*p).fetch_add(v); }
+inline size_t __cvta_generic_to_shared(const void *p) { return reinterpret_cast<size_t>(p); }
