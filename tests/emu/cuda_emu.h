@@ -11,8 +11,12 @@
 #include <barrier>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -45,19 +49,28 @@ namespace sx_emu {
 inline std::barrier<> *cur_barrier = nullptr;
 inline unsigned char *cur_dyn_smem = nullptr;
 inline unsigned char *dyn_smem() { return cur_dyn_smem; }
+// __syncwarp(mask): a real barrier among the lanes named by the mask (the lane groups of the
+// staged kernel), one per (warp, mask), created by the first lane that gets there
+inline std::mutex warp_mu;
+inline std::map<uint64_t, std::unique_ptr<std::barrier<>>> warp_barriers;
+inline std::mutex mbar_mu;  // the emulated mbarrier operations are made atomic with one lock
 
 // Run `body` as a grid of `grid` blocks of `block` threads with `smem` bytes of dynamic
 // shared memory per block (blocks one after the other).
 inline void launch(unsigned grid, unsigned block, size_t smem, const std::function<void()> &body) {
     gridDim = dim3(grid);
     blockDim = dim3(block);
-    std::vector<unsigned char> storage(smem + 256);
-    unsigned char *base = storage.data();
-    base += (128 - reinterpret_cast<uintptr_t>(base) % 128) % 128;
+    // exactly `smem` bytes (rounded up to the 128-byte alignment unit), so that an address
+    // sanitizer build catches a kernel that runs off the end of its dynamic shared memory
+    const size_t bytes = (std::max<size_t>(smem, 1) + 127) / 128 * 128;
+    unsigned char *base = static_cast<unsigned char *>(std::aligned_alloc(128, bytes));
+    struct Free { unsigned char *p; ~Free() { std::free(p); } } guard{base};
     for (unsigned b = 0; b < grid; ++b) {
         std::barrier<> bar((std::ptrdiff_t)block);
         cur_barrier = &bar;
         cur_dyn_smem = base;
+        warp_barriers.clear();
+        std::memset(base, 0xCD, bytes);  // shared memory starts out as garbage
         std::vector<std::thread> pool;
         pool.reserve(block);
         for (unsigned t = 0; t < block; ++t)
@@ -73,7 +86,17 @@ inline void launch(unsigned grid, unsigned block, size_t smem, const std::functi
 }  // namespace sx_emu
 
 inline void __syncthreads() { sx_emu::cur_barrier->arrive_and_wait(); }
-inline void __syncwarp(unsigned = 0xffffffffu) {}
+inline void __syncwarp(unsigned mask = 0xffffffffu) {
+    const uint64_t key = ((uint64_t)(threadIdx.x / 32) << 32) | mask;
+    std::barrier<> *b;
+    {
+        std::lock_guard<std::mutex> lk(sx_emu::warp_mu);
+        auto &slot = sx_emu::warp_barriers[key];
+        if (!slot) slot = std::make_unique<std::barrier<>>((std::ptrdiff_t)__builtin_popcount(mask));
+        b = slot.get();
+    }
+    b->arrive_and_wait();
+}
 template <typename T> inline T __ldg(const T *p) { return *p; }
 template <typename T> inline T __ldcv(const T *p) { return *p; }
 inline float __fmul_rn(float a, float b) { return a * b; }

@@ -10,19 +10,28 @@ __device__ __forceinline__ double2 ld_once(const double2 *p, uint64_t) { return 
 __device__ __forceinline__ void st_once(float4 *p, const float4 &v, uint64_t) { *p = v; }
 __device__ __forceinline__ void st_once(double2 *p, const double2 &v, uint64_t) { *p = v; }
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)reinterpret_cast<uintptr_t>(p); }
-// mbarrier word: bit 63 = armed (the expect_tx arrival has happened), low 32 bits = bytes
-// still outstanding.  One phase only, which is all the block-level kernels use.
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int) { std::atomic_ref<uint64_t>(*bar).store(0); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    std::atomic_ref<uint64_t> w(*bar);
-    w.fetch_add(bytes);
-    w.fetch_or(1ull << 63);
+// mbarrier word: bit 63 = parity of the phase in progress, bit 62 = armed (the expect_tx
+// arrival of this phase has happened), low 32 bits = bytes still outstanding.  A phase
+// completes -- the parity flips -- when it is armed and no bytes are outstanding;
+// mbar_wait(P) returns once the phase of parity P has completed (try_wait.parity semantics).
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int) {
+    std::lock_guard<std::mutex> lk(sx_emu::mbar_mu);
+    *bar = 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t) {
-    std::atomic_ref<uint64_t> w(*bar);
+__device__ __forceinline__ void sx_emu_mbar_settle(uint64_t *bar) {
+    if ((*bar >> 62 & 1) && (uint32_t)*bar == 0) *bar = (*bar ^ (1ull << 63)) & ~(1ull << 62);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    std::lock_guard<std::mutex> lk(sx_emu::mbar_mu);
+    *bar = ((*bar & ~0xFFFFFFFFull) | (uint32_t)((uint32_t)*bar + bytes)) | (1ull << 62);
+    sx_emu_mbar_settle(bar);
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     for (;;) {
-        const uint64_t v = w.load();
-        if ((v >> 63) && (uint32_t)v == 0) return;
+        {
+            std::lock_guard<std::mutex> lk(sx_emu::mbar_mu);
+            if ((uint32_t)(*bar >> 63) != (parity & 1u)) return;
+        }
         std::this_thread::yield();
     }
 }
@@ -32,5 +41,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
         std::abort();
     }
     std::memcpy(dst, src, bytes);
-    std::atomic_ref<uint64_t>(*bar).fetch_sub(bytes);
+    std::lock_guard<std::mutex> lk(sx_emu::mbar_mu);
+    *bar = (*bar & ~0xFFFFFFFFull) | (uint32_t)((uint32_t)*bar - bytes);
+    sx_emu_mbar_settle(bar);
 }

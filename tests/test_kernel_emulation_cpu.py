@@ -5,8 +5,10 @@ thread, real __syncthreads, TMA bulk copies as memcpy completing on an emulated 
 This test builds the PRODUCT's kernel source against it -- textually the same file, with
 only the PTX helper section (cache-policy loads/stores, mbarrier, cp.async.bulk) replaced by
 tests/emu/emu_helpers.h and the dynamic shared-memory declaration pointed at the emulator's
-buffer -- and runs variant 3 (32/64/128-row blocks, with and without the PDL code path) and
-the host-boundary fusion kernel against the cpu_spmm_CSR loop, bit for bit.  It is how the
+buffer -- and runs variant 3 (32/64/128-row blocks, with and without the PDL code path), the
+host-boundary fusion kernel, and variant 2 (the TMA-staged lane-group kernel with its finalize
+kernel: every lane-group shape, split rows, the prefetch code path, column-window passes)
+against the cpu_spmm_CSR loop, bit for bit.  It is how the
 kernels that were written after the round's GPU time was spent had their index arithmetic,
 staging and barrier structure checked; it does not replace the GPU parity tests."""
 import os
@@ -46,7 +48,28 @@ def test_block_level_kernels_on_the_cpu_emulation(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "EMULATION: all bit-exact" in r.stdout and "MISMATCH" not in r.stdout
-    ran = re.findall(r"^(window RB=\d+(?: PDL)?|hostc[^f]*) +f(?:32|64).*bit-exact$", r.stdout, flags=re.M)
+    ran = re.findall(r"^(window RB=\d+(?: PDL)?|hostc.*?) +f(?:32|64) M=.*bit-exact$", r.stdout, flags=re.M)
     kinds = {k.strip() for k in ran}
     assert {"window RB=32", "window RB=32 PDL", "window RB=64", "window RB=128"} <= kinds
     assert any(k.startswith("hostc") for k in kinds)
+    staged = re.findall(r"^(staged.*?) +f(?:32|64) M=.*bit-exact$", r.stdout, flags=re.M)
+    assert {"staged", "staged + prefetch path", "staged as column-window passes"} <= {k.strip() for k in staged}
+    assert len(staged) >= 60
+
+
+@pytest.mark.skipif(CXX is None or os.environ.get("SX_EMU_ASAN") != "1",
+                    reason="address-sanitizer pass of the emulation: set SX_EMU_ASAN=1 (about two minutes)")
+def test_emulated_kernels_stay_inside_their_buffers(tmp_path):
+    """The same run under AddressSanitizer.  Device buffers are allocated at exactly the sizes
+    (and pads) the product allocates, dynamic shared memory at exactly the launch's size, so an
+    out-of-bounds access of a kernel is reported instead of going unnoticed."""
+    (tmp_path / "spmm_kernels_emu.cuh").write_text(emulated_header())
+    exe = tmp_path / "emu_kernels_asan"
+    cmd = [CXX, "-std=c++20", "-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer", "-ffp-contract=off",
+           "-pthread", "-w", f"-I{tmp_path}", f"-I{EMU}", f"-I{os.path.join(EMU, 'include')}",
+           os.path.join(EMU, "emu_kernels.cpp"), "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=1800)
+    assert r.returncode == 0 and "AddressSanitizer" not in r.stderr, r.stderr[-4000:]
+    assert "EMULATION: all bit-exact" in r.stdout
