@@ -187,3 +187,12 @@ def test_host_program_call_surface_without_gpu():
         assert r.returncode != 0
         assert "N = 16" in r.stdout and "A: sparse matrix, 4704 x 4704. NNZ = 104756" in r.stdout
         assert "NO_DEVICE" in r.stderr and "Success!" not in r.stdout
+
+
+def test_python_constants_match_the_header_enums():
+    text = open(os.path.join(ROOT, "include", "sextans_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    pairs = re.findall(r"\b(SX_(?:OPT|INFO)_[A-Z_]+)\s*=\s*(\d+)", text)
+    assert len(pairs) >= 25
+    for name, value in pairs:
+        assert getattr(sx, name[3:]) == int(value), name
