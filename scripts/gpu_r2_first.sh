@@ -17,6 +17,10 @@ for n in 8 16 32; do for wr in 0 64 128; do
   python bench.py --workload pcrystk02 --ncols $n --steps 200 --no-cpu-baseline --window-rows $wr > gpurun_out/r2a_pcrystk02_n${n}_wr$wr.json 2>/dev/null
   python -c "import json,sys; d=json.load(open(sys.argv[1])); print('pcrystk02 N=$n window-rows=$wr: kernel us', round(d['ms_per_step']*1e3,2), d['roofline']['kernel'][:50])" gpurun_out/r2a_pcrystk02_n${n}_wr$wr.json
 done; done
+for dt in f32 f64; do for wr in 0 64 128; do
+  python bench.py --workload fem --band 100 --dtype $dt --kernel 3 --steps 20 --no-cpu-baseline --window-rows $wr > gpurun_out/r2a_fem_band100_${dt}_wr$wr.json 2>/dev/null
+  python -c "import json,sys; d=json.load(open(sys.argv[1])); print('fem band=100 $dt window-rows=$wr: ms', round(d['ms_per_step'],4), 'frac', round(d['roofline']['frac'],3), d['roofline']['kernel'][:50])" gpurun_out/r2a_fem_band100_${dt}_wr$wr.json
+done; done
 for kb in 28 56 84; do
   SX_STAGE_KB=$kb PROBE_SET=0:-1 timeout 100 python scripts/probe_windows.py 2>&1 | tail -1 | sed "s/^/stage_kb=$kb /"
 done | tee gpurun_out/r2a_stage_kb.log
