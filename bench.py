@@ -60,12 +60,13 @@ def parse():
     p.add_argument("--dtype", default="", choices=["", "f32", "f64"])
     p.add_argument("--scale", type=float, default=1.0, help="shrink the synthetic workloads (testing)")
     p.add_argument("--arith", default="strict", choices=["strict", "fast"])
-    p.add_argument("--kernel", type=int, default=0, help="SX_OPT_KERNEL (0 auto, 1 row per lane group, 2 TMA-staged items, 3 TMA-staged B window)")
+    p.add_argument("--kernel", type=int, default=0, help="SX_OPT_KERNEL (0 auto, 1 row per lane group, 2 TMA-staged items, 3 TMA-staged B window, 4 sliding B window: experimental, needs --slide)")
     p.add_argument("--item-nnz", type=int, default=0, help="SX_OPT_ITEM_NNZ (0 auto)")
     p.add_argument("--split", type=int, default=-1, help="SX_OPT_SPLIT_ROW_NNZ (-1 default)")
     p.add_argument("--band", type=int, default=2000, help="fem workload: couplings reach +-band nodes")
     p.add_argument("--tiles", type=int, default=0, help="SX_OPT_TILE_MIN_ROWS (fp64 dense-tile tensor-core variant; 0 off)")
     p.add_argument("--col-window-rows", type=int, default=0, help="SX_OPT_COL_WINDOW_ROWS (column-window passes keeping a window of B in L2; 0 off, -1 = 32 MiB of B per window)")
+    p.add_argument("--slide", type=int, default=0, help="SX_OPT_SLIDE (experimental): chains per SM of the sliding-window kernel; use with --kernel 4")
     p.add_argument("--window-rows", type=int, default=0, choices=[0, 32, 64, 128], help="SX_OPT_WINDOW_ROWS (experimental): rows per block of variant 3")
     p.add_argument("--pdl", action="store_true", help="SX_OPT_PDL (experimental): variant 3 launched with programmatic stream serialization")
     p.add_argument("--host-fused", action="store_true", help="SX_OPT_HOST_FUSED (experimental): e2e calls pass kernel_ns=NULL and the SpMM kernel carries C across PCIe")
@@ -340,6 +341,7 @@ def run_native(args):
         e.set_option(sx.OPT_HOST_FUSED, 1 if args.host_fused else 0)
         e.set_option(sx.OPT_PDL, 1 if args.pdl else 0)
         e.set_option(sx.OPT_WINDOW_ROWS, args.window_rows)
+        e.set_option(sx.OPT_SLIDE, args.slide)
         if args.split >= 0:
             e.set_option(sx.OPT_SPLIT_ROW_NNZ, args.split)
         e.upload_csr(M, K, w["rowptr"], w["colidx"], w["val"])
@@ -525,7 +527,7 @@ def run_native(args):
                       f"{eng.info(sx.INFO_REST_NNZ)} nnz left to CSR")
     else:
         tiles_note = ""
-    kernel_name = ({1: "spmm_rows_kernel (+segments/finalize)", 2: "spmm_staged_kernel", 3: "spmm_window_kernel", 4: "spmm_panels_dmma_kernel"}.get(lk // 10000, "?")
+    kernel_name = ({1: "spmm_rows_kernel (+segments/finalize)", 2: "spmm_staged_kernel", 3: "spmm_window_kernel", 4: "spmm_panels_dmma_kernel", 6: "spmm_window_hostc_kernel", 7: "spmm_slide_kernel"}.get(lk // 10000, "?")
                    + f" <G={lk % 10000 // 100}, VPL={lk % 100 // 10}, {'fast' if lk % 10 else 'strict'}>"
                    if lk // 10000 != 5 else f"spmm_staged_kernel<WIN>, {lk % 10000} column-window passes of {cw} columns each") + (
                    (f", {eng.info(sx.INFO_ITEMS)} items of <= {eng.info(sx.INFO_ITEM_NNZ)} nnz, {eng.info(sx.INFO_SPLIT_ROWS)} split rows" if lk // 10000 == 2 else "") + tiles_note)

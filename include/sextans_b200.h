@@ -74,7 +74,8 @@ enum sx_option {
     /* kernel variant: 0 auto; 1 one lane group per row (+ one warp per
      * long-row segment); 2 TMA-staged nnz-balanced work items; 3 B window of each
      * 32-row block staged into shared memory by TMA (banded matrices whose windows fit;
-     * falls back to 1 otherwise).  Auto: matrices below one wave of lane groups take 3 if
+     * falls back to 1 otherwise); 4 (experimental) the sliding-window kernel for long banded
+     * matrices, see SX_OPT_SLIDE.  Auto: matrices below one wave of lane groups take 3 if
      * they qualify, else 1; everything larger takes 2. */
     SX_OPT_KERNEL = 2,
     /* nonzeros per work item; 0 = auto (512 for N*sizeof(T) <= 128 bytes, else 256;
@@ -134,7 +135,16 @@ enum sx_option {
      * (pcrystk02: 437 blocks -> 219 / 110).  Used where the taller block's window and A
      * slice still fit in shared memory and RB * lanes-per-row <= 1024 threads; otherwise
      * the 32-row blocks run.  Results are unaffected. */
-    SX_OPT_WINDOW_ROWS = 10
+    SX_OPT_WINDOW_ROWS = 10,
+    /* EXPERIMENTAL (not yet measured on hardware); read by the NEXT sx_upload_csr_*.
+     * n in 1..8: plan n chains per SM for the sliding-window kernel (variant 4, selected with
+     * SX_OPT_KERNEL = 4): a thread block walks a run of consecutive 32-row steps with B held in
+     * a shared-memory ring that follows the band -- each step loads only the B rows above the
+     * highest one loaded so far -- and the next steps' loads overlap the current step's
+     * arithmetic.  For LONG banded matrices, where variant 3 keeps re-fetching nearly the same
+     * window.  Falls back to the automatic choice where the ring the plan needs does not fit
+     * in shared memory for the N in use.  Results are unaffected.  0 (default): no plan. */
+    SX_OPT_SLIDE = 11
 };
 
 enum sx_info {
@@ -275,6 +285,18 @@ int sx_partition_rows(int M, const int32_t *rowptr, int parts, int32_t *bounds);
  *               inside (window, row) the stored order is kept
  *   ascending   (may be NULL) 1 if every row is stored in non-decreasing column order
  * Arrays are malloc'ed; release each with sx_free. */
+/* Plan of the sliding-window kernel (what SX_OPT_SLIDE builds at upload; host only): rows in
+ * steps of 32, chains = runs of consecutive steps with about equal nonzeros.
+ *   steps   4 ints per step: {load_lo, load_hi, nnz_begin, nnz_end} -- B rows [load_lo, load_hi)
+ *           enter the ring at this step (everything above the highest row loaded so far, up to
+ *           the highest column the step touches)
+ *   chains  2 ints per chain: {first step, last step + 1}
+ *   ring_rows         rows the ring must hold so that a step's columns stay resident while the
+ *                     next step's rows arrive (the kernel rounds it up to a power of two)
+ *   max_step_entries  capacity (entries, a multiple of 4) of one of the two A buffers
+ * Arrays are malloc'ed; release each with sx_free. */
+int sx_plan_slide(int M, const int32_t *rowptr, const int32_t *colidx, int nchains_wanted, int *nsteps,
+                  int32_t **steps, int *nchains, int32_t **chains, int *ring_rows, int *max_step_entries);
 int sx_split_col_windows(int M, int K, const int32_t *rowptr, const int32_t *colidx, int window_rows,
                          int *nwin, int32_t **win_rowptr, int64_t **win_base, int32_t **order,
                          int *ascending);

@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 __all__ = ["Engine", "SextansError", "lib", "library_path", "load_mtx", "partition_rows",
-           "split_col_windows",
+           "split_col_windows", "plan_slide",
            "pinned_empty", "STRICT", "FAST", "images_decode_A", "images_decode_B",
            "images_decode_C", "images_encode_C"]
 
@@ -27,7 +27,7 @@ _LIB = None
 SX_F32, SX_F64 = 0, 1
 STRICT, FAST = 0, 1
 (OPT_ARITH, OPT_SPLIT_ROW_NNZ, OPT_KERNEL, OPT_ITEM_NNZ, OPT_ZEROCOPY_BYTES, OPT_TILE_MIN_ROWS,
- OPT_COL_WINDOW_ROWS, OPT_PREFETCH, OPT_HOST_FUSED, OPT_PDL, OPT_WINDOW_ROWS) = range(11)
+ OPT_COL_WINDOW_ROWS, OPT_PREFETCH, OPT_HOST_FUSED, OPT_PDL, OPT_WINDOW_ROWS, OPT_SLIDE) = range(12)
 (INFO_LAUNCHES, INFO_M, INFO_K, INFO_NNZ, INFO_DTYPE, INFO_SPLIT_ROWS, INFO_LAST_KERNEL, INFO_LD,
  INFO_ITEMS, INFO_ITEM_NNZ, INFO_HOST_PATH, INFO_TILE_NNZ, INFO_TILE_SLOTS, INFO_REST_NNZ,
  INFO_UPLOAD_SERIAL, INFO_COL_WINDOWS) = range(16)
@@ -106,6 +106,8 @@ def lib():
                              C.POINTER(_PI32), C.POINTER(_PI32), C.POINTER(_PD)], i),
         "sx_split_col_windows": ([i, i, _PI32, _PI32, i, C.POINTER(i), C.POINTER(_PI32),
                                   C.POINTER(C.POINTER(i64)), C.POINTER(_PI32), C.POINTER(i)], i),
+        "sx_plan_slide": ([i, _PI32, _PI32, i, C.POINTER(i), C.POINTER(_PI32), C.POINTER(i), C.POINTER(_PI32),
+                           C.POINTER(i), C.POINTER(i)], i),
         "sx_free": ([vp], None),
         "sx_sextans_invoke": ([vp, _PI32, _A8, _F4, _F8, _F8, i, i, i, i, i, i, i, _PD], i),
         "sx_sextans_last_kernel_ns": ([], C.c_double),
@@ -176,6 +178,24 @@ def partition_rows(rowptr, parts):
     _check(lib().sx_partition_rows(rowptr.size - 1, rowptr.ctypes.data_as(_PI32), parts,
                                    bounds.ctypes.data_as(_PI32)))
     return bounds
+
+
+def plan_slide(M, rowptr, colidx, nchains):
+    """Plan of the sliding-window kernel (sx_plan_slide) ->
+    (steps [nsteps, 4], chains [nchains, 2], ring_rows, max_step_entries)."""
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+    colidx = np.ascontiguousarray(colidx, dtype=np.int32)
+    ns, nc, ring, ent = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    st, ch = _PI32(), _PI32()
+    L = lib()
+    _check(L.sx_plan_slide(M, rowptr.ctypes.data_as(_PI32), colidx.ctypes.data_as(_PI32), nchains, C.byref(ns),
+                           C.byref(st), C.byref(nc), C.byref(ch), C.byref(ring), C.byref(ent)))
+    try:
+        steps = np.ctypeslib.as_array(st, shape=(max(ns.value, 1) * 4,))[:ns.value * 4].reshape(-1, 4).copy()
+        chains = np.ctypeslib.as_array(ch, shape=(max(nc.value, 1) * 2,))[:nc.value * 2].reshape(-1, 2).copy()
+    finally:
+        L.sx_free(st), L.sx_free(ch)
+    return steps, chains, ring.value, ent.value
 
 
 def split_col_windows(M, K, rowptr, colidx, window_rows):

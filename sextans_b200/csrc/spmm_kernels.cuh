@@ -604,6 +604,115 @@ spmm_window_kernel(const int M, const int4 *__restrict__ blocks, const int *__re
     }
 }
 
+// ---- variant 4 (experimental, SX_OPT_SLIDE): long banded matrices, a SLIDING B window -------
+// Variant 3 gives every 32-row block its own copy of its B window; on a long banded matrix
+// consecutive blocks' windows are almost the same rows, so each SM keeps re-fetching ~100 KB
+// from L2 to do 32 rows of work, one block per SM, load and compute in turns (FEM-like
+// band=100, M=1e6, fp64: 1.11 ms against 0.22 ms at the HBM roof).  Here a thread block walks
+// a CHAIN of consecutive 32-row steps and keeps B in a shared-memory RING indexed by
+// (row & rmask): step s only brings in the rows above the highest row loaded so far
+// (~32 new rows instead of the whole window), together with its slice of colidx/val into one
+// of two A buffers, all completing on that buffer's mbarrier; the loads of step s+2 are
+// issued as soon as step s is done, so they fly while step s+1 computes.  This is the
+// reference's scheme in its native form -- A streamed once through a small buffer, B held
+// on chip while the rows that use it go by (src/sextans.cpp:337-420) -- with the window
+// following the band instead of standing still.  The host plan (sx_host.cpp: sx_plan_slide)
+// sizes the ring so that a step's columns stay resident while the next step's rows arrive.
+//   chain = {first step, last step + 1};  step = {load_lo, load_hi, nnz_begin, nnz_end}
+//   dynamic smem: ring (rmask+1) * ldbv * 16 | 2 * abuf values | 2 * abuf columns
+// One row per lane group, stored order, so strict mode is bit-identical to cpu_spmm_CSR.
+template <typename T, int G, bool STRICT>
+__global__ void __launch_bounds__(32 * G)
+spmm_slide_kernel(const int M, const int2 *__restrict__ chains, const int4 *__restrict__ steps,
+                  const int *__restrict__ rowptr, const int *__restrict__ colidx, const T *__restrict__ val,
+                  const T *__restrict__ B, const uint32_t ldbv, const T *Cin, T *Cout, const uint32_t ldcv,
+                  const T alpha, const T beta, const int nvec, const uint32_t rmask, const uint32_t abuf) {
+    using V = typename VecOf<T>::type;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t full[2];
+    const int lg = threadIdx.x & (G - 1);
+    const int rl = threadIdx.x / G;
+    const uint32_t rowbytes = ldbv * 16u;
+    const V *ring = reinterpret_cast<const V *>(smem_raw);
+    unsigned char *abase = smem_raw + (size_t)(rmask + 1) * rowbytes;
+    T *svals = reinterpret_cast<T *>(abase);                                            // [2][abuf]
+    int *scols = reinterpret_cast<int *>(abase + (size_t)2 * abuf * sizeof(T));           // [2][abuf]
+    const int2 ch = __ldg(chains + blockIdx.x);
+    if (threadIdx.x == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // thread 0: everything step s needs, into A buffer `slot` and the ring, on full[slot]
+    auto issue = [&](const int s, const int slot) {
+        const int4 st = __ldg(steps + s);
+        const int jal = st.z & ~3;
+        const uint32_t cnt = st.w > st.z ? (uint32_t)((st.w - jal + 3) & ~3) : 0u;
+        const uint32_t nrows = (uint32_t)(st.y - st.x);
+        const uint64_t pol_a = policy_evict_first();
+        uint64_t pol_b;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_b));
+        mbar_expect_tx(&full[slot], nrows * rowbytes + cnt * (uint32_t)(sizeof(T) + 4));
+        const uint32_t chunk = 32768u / rowbytes;  // rows per bulk copy
+        for (uint32_t r = (uint32_t)st.x; r < (uint32_t)st.y;) {
+            const uint32_t at = r & rmask;
+            const uint32_t n = min(min((uint32_t)st.y - r, rmask + 1 - at), chunk);  // up to the ring's wrap
+            tma_bulk_g2s(smem_raw + (size_t)at * rowbytes, reinterpret_cast<const unsigned char *>(B) + (size_t)r * rowbytes,
+                         n * rowbytes, &full[slot], pol_b);
+            r += n;
+        }
+        if (cnt) {
+            tma_bulk_g2s(svals + (size_t)slot * abuf, val + jal, cnt * (uint32_t)sizeof(T), &full[slot], pol_a);
+            tma_bulk_g2s(scols + (size_t)slot * abuf, colidx + jal, cnt * 4u, &full[slot], pol_a);
+        }
+    };
+    if (threadIdx.x == 0) {
+        issue(ch.x, 0);
+        if (ch.x + 1 < ch.y) issue(ch.x + 1, 1);
+    }
+    for (int s = ch.x, i = 0; s < ch.y; ++s, ++i) {
+        const int slot = i & 1;
+        const int row = s * 32 + rl;
+        const bool mine = row < M && lg < nvec;
+        int begin = 0, end = 0;
+        V acc, cin;
+        vzero(acc);
+        vzero(cin);
+        if (mine) {
+            begin = __ldg(rowptr + row);
+            end = __ldg(rowptr + row + 1);
+            cin = reinterpret_cast<const V *>(Cin)[(size_t)row * ldcv + lg];
+        }
+        const int jal = __ldg(&steps[s].z) & ~3;
+        mbar_wait(&full[slot], (uint32_t)((i >> 1) & 1));
+        if (mine) {
+            const T *sv = svals + (size_t)slot * abuf - jal;  // sv[j] = value of nonzero j
+            const int *sc = scols + (size_t)slot * abuf - jal;
+            const V *w = ring + lg;
+            int j = begin;
+            for (; j + 4 <= end; j += 4) {
+                int c[4];
+                T a[4];
+                V b[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { c[u] = sc[j + u]; a[u] = sv[j + u]; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) b[u] = w[((uint32_t)c[u] & rmask) * ldbv];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) vmac<STRICT>(acc, a[u], b[u]);
+            }
+            for (; j < end; ++j) vmac<STRICT>(acc, sv[j], w[((uint32_t)sc[j] & rmask) * ldbv]);
+            reinterpret_cast<V *>(Cout)[(size_t)row * ldcv + lg] = vaxpby<STRICT>(alpha, acc, beta, cin);
+        }
+        __syncthreads();  // everybody is done with A buffer `slot` and with the ring rows step s+2 will replace
+        if (threadIdx.x == 0 && s + 2 < ch.y) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(s + 2, slot);
+        }
+    }
+}
+
 // ---- variant 3 fused with the host boundary (experimental, SX_OPT_HOST_FUSED) -------------
 // For the small banded matrices that take variant 3 the host-facing call is dominated by
 // PCIe, not by the SpMM: B and C_in cross the bus into device images, the kernel runs, C

@@ -108,6 +108,10 @@ struct sx_ctx {
     // the same for blocks of 64 and 128 rows (SX_OPT_WINDOW_ROWS, experimental)
     struct WideBlocks { DevBuf blocks; int n = 0, max_span = 0, max_block_nnz = 0; } wide[2];
     int window_rows = 0;  // 0 / 32: the validated 32-row blocks; 64, 128: wide[0], wide[1]
+    // variant 4 (SX_OPT_SLIDE, experimental): chains of 32-row steps over a sliding B window
+    int slide = 0;  // option: chains per SM to plan at the next upload (0: no plan)
+    DevBuf slide_steps, slide_chains;
+    int slide_nsteps = 0, slide_nchains = 0, slide_ring_rows = 0, slide_max_entries = 0;
     std::vector<const void *> big_smem_ok;  // kernels already allowed > 48 KB of dynamic smem
     // dense-tile split A = A_tiles + A_rest (fp64, SX_OPT_TILE_MIN_ROWS > 0 at upload)
     int tile_min_rows = 0;
@@ -215,9 +219,35 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
     // (fem band=100 fp64, 143 KB windows: 1.11 ms against 1.04 ms; fp32, 78 KB: 0.58 against 0.84)
     const int window_cap = wsmem ? (int)std::max<size_t>(1, (220 * 1024) / wsmem) : 1;
     const bool window_auto = window_ok && (window_cap >= 2 || (int64_t)c->nwblocks <= (int64_t)4 * c->sm_count * window_cap);
-    int variant = c->kernel != 0 ? c->kernel : (window_auto ? 3 : (sub_wave ? 1 : 2));
+    int variant = (c->kernel != 0 && c->kernel != 4) ? c->kernel : (window_auto ? 3 : (sub_wave ? 1 : 2));
     if (variant == 3 && !window_ok) variant = sub_wave ? 1 : 2;
     if (c->win_mode) variant = 2;  // a column-window pass: only the staged kernel carries running sums
+    // SX_OPT_KERNEL = 4 (experimental): the sliding-window kernel, where a plan exists and fits
+    if constexpr (G <= 16 && VPL == 1) {
+        if (c->kernel == 4 && c->slide_nchains > 0 && !c->win_mode) {
+            constexpr int E = sx::VecOf<T>::E;
+            uint32_t R = 32;
+            while (R < (uint32_t)c->slide_ring_rows) R <<= 1;
+            const size_t rowbytes = (size_t)(ldb / E) * 16;
+            const size_t smem = (size_t)R * rowbytes + (size_t)2 * c->slide_max_entries * (sizeof(T) + 4);
+            if (smem <= 220 * 1024) {
+                auto kern = sx::spmm_slide_kernel<T, G, STRICT>;
+                if (smem > 48 * 1024 &&
+                    std::find(c->big_smem_ok.begin(), c->big_smem_ok.end(), (const void *)kern) == c->big_smem_ok.end()) {
+                    SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                    c->big_smem_ok.push_back((const void *)kern);
+                }
+                kern<<<(unsigned)c->slide_nchains, 32 * G, smem, c->stream>>>(
+                    c->M, (const int2 *)c->slide_chains.p, (const int4 *)c->slide_steps.p, (const int *)c->rowptr.p,
+                    (const int *)c->colidx.p, (const T *)c->val.p, dB, (uint32_t)(ldb / E), dCin, dCout, (uint32_t)(ldc / E),
+                    alpha, beta, nvec, R - 1, (uint32_t)c->slide_max_entries);
+                c->launches++;
+                c->last_kernel = 70000 + G * 100 + VPL * 10 + (STRICT ? 0 : 1);
+                SX_CUDA(cudaGetLastError());
+                return SX_OK;
+            }
+        }
+    }
     // SX_OPT_WINDOW_ROWS (experimental): blocks of 64 / 128 rows where RB * G <= 1024 threads
     if constexpr (G >= 4 && G <= 16 && VPL == 1) {
         if (variant == 3 && c->window_rows > 32 && !c->pdl) {
@@ -907,6 +937,21 @@ int upload_csr(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rowptr, cons
     if ((rc = build_window_blocks(c, M, rowptr, colidx))) return rc;
     if (c->window_rows > 32 && (rc = build_wide_window_blocks(c, M, rowptr, colidx))) return rc;
     if (c->window_rows <= 32) c->wide[0].n = c->wide[1].n = 0;
+    c->slide_nsteps = c->slide_nchains = 0;
+    if (c->slide > 0 && M > 0 && nnz > 0) {
+        int32_t *steps = nullptr, *chains = nullptr;
+        rc = sx_plan_slide(M, rowptr, colidx, c->slide * c->sm_count, &c->slide_nsteps, &steps, &c->slide_nchains, &chains,
+                           &c->slide_ring_rows, &c->slide_max_entries);
+        if (!rc && !(rc = c->slide_steps.ensure((size_t)c->slide_nsteps * 16)) && !(rc = c->slide_chains.ensure((size_t)c->slide_nchains * 8))) {
+            if (cudaMemcpyAsync(c->slide_steps.p, steps, (size_t)c->slide_nsteps * 16, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+                cudaMemcpyAsync(c->slide_chains.p, chains, (size_t)c->slide_nchains * 8, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+                cudaStreamSynchronize(c->stream) != cudaSuccess)
+                rc = fail(SX_ERR_CUDA, "slide plan upload failed");
+        }
+        sx_free(steps);
+        sx_free(chains);
+        if (rc) { c->slide_nsteps = c->slide_nchains = 0; return rc; }
+    }
     if ((rc = maybe_build_panels<T>(c, M, K, nnz, rowptr, colidx, val))) return rc;
     if ((rc = maybe_build_windows<T>(c, M, K, nnz, rowptr, colidx, val))) return rc;
     c->has_A = true;
@@ -1267,7 +1312,9 @@ int sx_destroy(sx_ctx *c) {
     drop_plans(c);
     drop_tiles(c);
     drop_windows(c);
-    for (DevBuf *b : {&c->step_ptr, &c->tcols, &c->tvals, &c->psum, &c->wide[0].blocks, &c->wide[1].blocks}) b->release();
+    for (DevBuf *b : {&c->step_ptr, &c->tcols, &c->tvals, &c->psum, &c->wide[0].blocks, &c->wide[1].blocks,
+                      &c->slide_steps, &c->slide_chains})
+        b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -1297,7 +1344,7 @@ int sx_set_option(sx_ctx *c, int option, int64_t value) {
             for (sx_ctx *k : c->wins) { k->split_nnz = (int)value; k->segments_dirty = true; }
             return SX_OK;
         case SX_OPT_KERNEL:
-            if (value < 0 || value > 3) return fail(SX_ERR_INVALID, "SX_OPT_KERNEL is 0 (auto), 1 (row per lane group), 2 (TMA-staged work items) or 3 (TMA-staged B window)");
+            if (value < 0 || value > 4) return fail(SX_ERR_INVALID, "SX_OPT_KERNEL is 0 (auto), 1 (row per lane group), 2 (TMA-staged work items), 3 (TMA-staged B window) or 4 (sliding B window, experimental: needs SX_OPT_SLIDE at upload)");
             c->kernel = (int)value;
             return SX_OK;
         case SX_OPT_TILE_MIN_ROWS:
@@ -1314,6 +1361,10 @@ int sx_set_option(sx_ctx *c, int option, int64_t value) {
             c->segments_dirty = c->has_A;
             if (c->rest) c->rest->segments_dirty = true;
             for (sx_ctx *k : c->wins) k->segments_dirty = true;
+            return SX_OK;
+        case SX_OPT_SLIDE:
+            if (value < 0 || value > 8) return fail(SX_ERR_INVALID, "SX_OPT_SLIDE is 0 (off) or the number of chains per SM (1..8)");
+            c->slide = (int)value;  // the plan is built at the next sx_upload_csr_*
             return SX_OK;
         case SX_OPT_WINDOW_ROWS:
             if (value != 0 && value != 32 && value != 64 && value != 128)

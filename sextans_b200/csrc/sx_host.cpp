@@ -542,4 +542,90 @@ int sx_split_col_windows(int M, int K, const int32_t *rowptr, const int32_t *col
     return SX_OK;
 }
 
+// Plan of the sliding-window kernel (spmm_slide_kernel, variant 4): rows are taken in steps
+// of 32; a chain is a run of consecutive steps that one thread block walks with the B rows it
+// needs held in a shared-memory ring.  Per step the plan says which NEW rows of B enter the
+// ring -- [load_lo, load_hi): everything between the highest row loaded so far and the
+// highest column the step touches -- and the step's nonzero range.  ring_rows is the number
+// of ring rows that keeps every step's columns resident while the next step's rows are
+// already arriving: max over consecutive steps of (highest row loaded for step s+1) -
+// (lowest column of step s) + 1.  Chains hold about the same number of nonzeros.
+int sx_plan_slide(int M, const int32_t *rowptr, const int32_t *colidx, int nchains_wanted, int *nsteps_out,
+                  int32_t **steps_out, int *nchains_out, int32_t **chains_out, int *ring_rows_out,
+                  int *max_step_entries_out) {
+    if (!nsteps_out || !steps_out || !nchains_out || !chains_out || !ring_rows_out || !max_step_entries_out) {
+        sx_internal_set_error("sx_plan_slide: null output pointer");
+        return SX_ERR_INVALID;
+    }
+    *nsteps_out = *nchains_out = *ring_rows_out = *max_step_entries_out = 0;
+    *steps_out = *chains_out = nullptr;
+    if (M < 0 || nchains_wanted < 1 || !rowptr || (M > 0 && rowptr[M] > 0 && !colidx)) {
+        sx_internal_set_error("sx_plan_slide: bad argument");
+        return SX_ERR_INVALID;
+    }
+    const int nsteps = (M + 31) / 32;
+    if (nsteps == 0) return SX_OK;
+    std::vector<int32_t> cmin((size_t)nsteps), cmax((size_t)nsteps);
+    const unsigned nt = rowptr[M] < (1 << 18) ? 1u : sxhost::host_threads();
+    sxhost::parallel_for(nt, [&](unsigned t) {
+        for (int s = (int)((int64_t)nsteps * t / nt); s < (int)((int64_t)nsteps * (t + 1) / nt); ++s) {
+            const int r0 = s * 32, r1 = std::min(M, r0 + 32);
+            int32_t lo = INT32_MAX, hi = -1;
+            for (int32_t j = rowptr[r0]; j < rowptr[r1]; ++j) { lo = std::min(lo, colidx[j]); hi = std::max(hi, colidx[j]); }
+            cmin[s] = lo;  // INT32_MAX / -1: the step has no nonzeros
+            cmax[s] = hi;
+        }
+    });
+    // chains: contiguous runs of steps with about nnz / nchains nonzeros each (at least one step)
+    const int nchains = std::min(nchains_wanted, nsteps);
+    int32_t *chains = (int32_t *)std::malloc((size_t)nchains * 2 * sizeof(int32_t));
+    int32_t *steps = (int32_t *)std::malloc((size_t)nsteps * 4 * sizeof(int32_t));
+    if (!chains || !steps) {
+        std::free(chains); std::free(steps);
+        sx_internal_set_error("sx_plan_slide: out of host memory");
+        return SX_ERR_NOMEM;
+    }
+    const int64_t nnz = rowptr[M];
+    int s = 0;
+    for (int c = 0; c < nchains; ++c) {
+        const int begin = s;
+        const int must_leave = nchains - 1 - c;  // steps that have to remain for the chains after this one
+        const int64_t target = nnz * (c + 1) / nchains;
+        ++s;
+        while (s < nsteps - must_leave && (c == nchains - 1 || (int64_t)rowptr[std::min(M, s * 32)] < target)) ++s;
+        chains[2 * c] = begin;
+        chains[2 * c + 1] = s;
+    }
+    int ring_rows = 1, max_entries = 4;
+    for (int c = 0; c < nchains; ++c) {
+        const int b = chains[2 * c], e = chains[2 * c + 1];
+        int32_t lo0 = INT32_MAX;
+        for (int t = b; t < e; ++t) lo0 = std::min(lo0, cmin[t]);
+        int32_t hi = (lo0 == INT32_MAX) ? -1 : lo0 - 1;  // highest B row loaded so far
+        int32_t prev_cmin = INT32_MAX;                    // lowest column of the previous step
+        for (int t = b; t < e; ++t) {
+            const int32_t new_hi = std::max(hi, cmax[t]);
+            const int r0 = t * 32, r1 = std::min(M, r0 + 32);
+            steps[4 * t + 0] = hi + 1;
+            steps[4 * t + 1] = new_hi + 1;
+            steps[4 * t + 2] = rowptr[r0];
+            steps[4 * t + 3] = rowptr[r1];
+            if (cmin[t] != INT32_MAX) ring_rows = std::max(ring_rows, new_hi - cmin[t] + 1);
+            // while the previous step computes, this step's rows are already arriving
+            if (prev_cmin != INT32_MAX) ring_rows = std::max(ring_rows, new_hi - prev_cmin + 1);
+            if (t == b && lo0 != INT32_MAX) ring_rows = std::max(ring_rows, new_hi - lo0 + 1);
+            max_entries = std::max(max_entries, (rowptr[r1] - (rowptr[r0] & ~3) + 3) & ~3);
+            hi = new_hi;
+            prev_cmin = cmin[t];
+        }
+    }
+    *nsteps_out = nsteps;
+    *steps_out = steps;
+    *nchains_out = nchains;
+    *chains_out = chains;
+    *ring_rows_out = ring_rows;
+    *max_step_entries_out = max_entries;
+    return SX_OK;
+}
+
 }  // extern "C"

@@ -18,6 +18,12 @@
 #define volatile(...)
 #include "spmm_kernels_emu.cuh"  // generated next to this file's object by the test
 
+extern "C" {  // host-side planner of the product (libsextans_b200.so; no GPU needed)
+int sx_plan_slide(int M, const int32_t *rowptr, const int32_t *colidx, int nchains_wanted, int *nsteps, int32_t **steps,
+                  int *nchains, int32_t **chains, int *ring_rows, int *max_step_entries);
+void sx_free(void *);
+}
+
 namespace {
 
 // 256-byte aligned like cudaMalloc, zero-filled, EXACTLY n elements + pad bytes (the pads the
@@ -198,6 +204,91 @@ void by_shape(const char *tname, int M, int K, int N, int half_band, int per_row
         case 8: one_case<T, 8>(tname, M, K, N, half_band, per_row, seed); break;
         case 16: one_case<T, 16>(tname, M, K, N, half_band, per_row, seed); break;
         default: std::printf("N=%d needs more than 16 lanes per row: not a variant-3 shape\n", N);
+    }
+}
+
+// ---- variant 4: the sliding-window kernel, planned by the product's own sx_plan_slide ----
+// band whose centre wanders (so that a step's lowest column is not monotone), with stretches of
+// empty rows longer than a 32-row step
+Csr wandering_band(int M, int K, int half_band, int per_row, unsigned seed) {
+    std::mt19937 rng(seed);
+    Csr a{M, K, std::vector<int>(M + 1, 0), {}};
+    for (int r = 0; r < M; ++r) {
+        const int jitter = (int)(rng() % 41) - 20;
+        const int centre = std::clamp((int)((long long)r * K / M) + jitter, 0, K - 1);
+        const int lo = std::max(0, centre - half_band), hi = std::min(K, centre + half_band + 1);
+        const bool hole = (r / 40) % 9 == 4;  // 40 consecutive empty rows now and then
+        const int want = hole ? 0 : std::min(per_row + (int)(rng() % 4), hi - lo);
+        std::vector<int> cols;
+        while ((int)cols.size() < want) {
+            const int c = lo + (int)(rng() % (unsigned)(hi - lo));
+            if (std::find(cols.begin(), cols.end(), c) == cols.end()) cols.push_back(c);
+        }
+        std::sort(cols.begin(), cols.end());
+        a.ci.insert(a.ci.end(), cols.begin(), cols.end());
+        a.rp[r + 1] = (int)a.ci.size();
+    }
+    return a;
+}
+
+template <typename T, int G>
+void slide_case(const char *tname, int M, int K, int N, int half_band, int per_row, int nchains_wanted, unsigned seed) {
+    constexpr int E = 16 / (int)sizeof(T);
+    const Csr a = wandering_band(M, K, half_band, per_row, seed);
+    const int nnz = a.rp[M];
+    std::mt19937 rng(seed * 3 + 11);
+    std::uniform_real_distribution<double> U01(-1.0, 1.0);
+    const int64_t ld = (N + 7) / 8 * 8;
+    Aligned<T> val((size_t)nnz, 32), B((size_t)K * ld), Cin((size_t)M * ld), Cout((size_t)M * ld), Ref((size_t)M * ld);
+    Aligned<int> ci((size_t)nnz, 16), rp((size_t)M + 1);
+    std::vector<T> hval((size_t)nnz);
+    for (int j = 0; j < nnz; ++j) { hval[j] = (T)U01(rng); val.p[j] = hval[j]; ci.p[j] = a.ci[j]; }
+    for (int i = 0; i <= M; ++i) rp.p[i] = a.rp[i];
+    for (int64_t i = 0; i < (int64_t)K * ld; ++i) B.p[i] = (i % ld) < N ? (T)U01(rng) : (T)0;
+    for (int64_t i = 0; i < (int64_t)M * ld; ++i) Cin.p[i] = (i % ld) < N ? (T)U01(rng) : (T)0;
+    const T alpha = (T)0.85f, beta = (T)-2.06f;
+    reference<T>(a, hval, N, B.p, ld, alpha, beta, Cin.p, Ref.p, ld);
+    int nsteps = 0, nchains = 0, ring_rows = 0, max_entries = 0;
+    int32_t *steps = nullptr, *chains = nullptr;
+    if (sx_plan_slide(M, a.rp.data(), a.ci.data(), nchains_wanted, &nsteps, &steps, &nchains, &chains, &ring_rows, &max_entries)) {
+        std::printf("sx_plan_slide failed\n");
+        ++failures;
+        return;
+    }
+    Aligned<int> dsteps((size_t)nsteps * 4), dchains((size_t)nchains * 2);
+    std::copy(steps, steps + (size_t)nsteps * 4, dsteps.p);
+    std::copy(chains, chains + (size_t)nchains * 2, dchains.p);
+    sx_free(steps);
+    sx_free(chains);
+    uint32_t R = 32;
+    while (R < (uint32_t)ring_rows) R <<= 1;
+    const uint32_t ldv = (uint32_t)(ld / E);
+    const size_t smem = (size_t)R * ldv * 16 + (size_t)2 * max_entries * (sizeof(T) + 4);
+    const int nvec = (N * (int)sizeof(T) + 15) / 16;
+    std::fill(Cout.p, Cout.p + (int64_t)M * ld, (T)777);
+    sx_emu::launch((unsigned)nchains, 32 * G, smem, [&] {
+        sx::spmm_slide_kernel<T, G, true>(M, reinterpret_cast<const int2 *>(dchains.p), reinterpret_cast<const int4 *>(dsteps.p),
+                                          rp.p, ci.p, val.p, B.p, ldv, Cin.p, Cout.p, ldv, alpha, beta, nvec, R - 1,
+                                          (uint32_t)max_entries);
+    });
+    bool ok = true;
+    for (int i = 0; i < M && ok; ++i) ok = same_bits(Cout.p + (int64_t)i * ld, Ref.p + (int64_t)i * ld, (size_t)N);
+    std::printf("%-34s %s M=%d K=%d N=%d G=%d: %d steps in %d chains, ring %u rows (needs %d): %s\n", "slide (variant 4)", tname, M,
+                K, N, G, nsteps, nchains, R, ring_rows, ok ? "bit-exact" : "MISMATCH");
+    if (!ok) ++failures;
+}
+
+template <typename T>
+void slide_by_shape(const char *tname, int M, int K, int N, int half_band, int per_row, int nchains, unsigned seed) {
+    const int nvec = (N * (int)sizeof(T) + 15) / 16;
+    int G = 2;
+    while (G < 32 && G < nvec) G <<= 1;
+    switch (G) {
+        case 2: slide_case<T, 2>(tname, M, K, N, half_band, per_row, nchains, seed); break;
+        case 4: slide_case<T, 4>(tname, M, K, N, half_band, per_row, nchains, seed); break;
+        case 8: slide_case<T, 8>(tname, M, K, N, half_band, per_row, nchains, seed); break;
+        case 16: slide_case<T, 16>(tname, M, K, N, half_band, per_row, nchains, seed); break;
+        default: break;
     }
 }
 
@@ -400,6 +491,13 @@ int main() {
     for (const auto &c : cases) {
         by_shape<float>("f32", c.M, c.K, c.N, c.hb, c.per, seed++);
         by_shape<double>("f64", c.M, c.K, c.N, c.hb, c.per, seed++);
+    }
+    const struct { int M, K, N, hb, per, nchains; } lcases[] = {
+        {1500, 1500, 16, 40, 9, 5}, {1500, 1700, 8, 25, 6, 1}, {2000, 1800, 4, 60, 7, 7}, {999, 1200, 32, 30, 5, 3},
+        {700, 700, 24, 90, 12, 2}, {64, 64, 16, 20, 6, 4}, {33, 40, 3, 10, 4, 9}, {3000, 3000, 16, 15, 5, 148}};
+    for (const auto &c : lcases) {
+        slide_by_shape<float>("f32", c.M, c.K, c.N, c.hb, c.per, c.nchains, seed++);
+        slide_by_shape<double>("f64", c.M, c.K, c.N, c.hb, c.per, c.nchains, seed++);
     }
     const struct { int M, K, N, avg, long_row, budget, split, W; } scases[] = {
         {300, 400, 16, 12, 0, 64, 0, 128},   {300, 400, 16, 12, 350, 64, 96, 128}, {150, 300, 8, 9, 0, 16, 0, 100},

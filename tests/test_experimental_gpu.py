@@ -160,3 +160,29 @@ def test_taller_window_blocks_on_pcrystk02_golden(eng, golden, rows):
         C = Cin.copy()
         eng.spmm(N, np.float32(0.85), B, np.float32(-2.06), C)
         assert sha(C) == run["C_sha256"], (rows, N)
+
+
+@pytest.mark.parametrize("chains_per_sm", [1, 2])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("M,K,N", [(20000, 20000, 16), (5000, 6000, 8), (999, 1200, 32), (70, 64, 4), (30000, 30000, 64)])
+def test_sliding_window_kernel_bit_exact(eng, chains_per_sm, dtype, M, K, N):
+    """SX_OPT_SLIDE + SX_OPT_KERNEL = 4: chains of 32-row steps over a shared-memory ring of B
+    rows (or the automatic choice where the ring does not fit) reproduce the oracle."""
+    rp, ci, v = banded_csr(M, K, 200, 30, M + N + chains_per_sm, dtype)
+    B, Cin = random_dense(M, K, N, M + N, dtype)
+    ref = oracle.spmm_csr(M, N, K, rp, ci, v, dtype(0.85), B, dtype(-2.06), Cin.copy())
+    eng.set_option(sx.OPT_SLIDE, chains_per_sm)
+    eng.set_option(sx.OPT_KERNEL, 4)
+    eng.upload_csr(M, K, rp, ci, v)
+    for rp_time in (1, 3):
+        C = Cin.copy()
+        eng.spmm(N, dtype(0.85), B, dtype(-2.06), C, rp_time)
+        assert np.array_equal(bits(C), bits(ref))
+    if N * np.dtype(dtype).itemsize <= 256:
+        assert eng.info(sx.INFO_LAST_KERNEL) // 10000 == 7
+    # without a plan kernel 4 is the automatic choice
+    eng.set_option(sx.OPT_SLIDE, 0)
+    eng.upload_csr(M, K, rp, ci, v)
+    C = Cin.copy()
+    eng.spmm(N, dtype(0.85), B, dtype(-2.06), C)
+    assert np.array_equal(bits(C), bits(ref)) and eng.info(sx.INFO_LAST_KERNEL) // 10000 != 7

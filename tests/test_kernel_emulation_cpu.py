@@ -8,6 +8,7 @@ tests/emu/emu_helpers.h and the dynamic shared-memory declaration pointed at the
 buffer -- and runs variant 3 (32/64/128-row blocks, with and without the PDL code path), the
 host-boundary fusion kernel, and variant 2 (the TMA-staged lane-group kernel with its finalize
 kernel: every lane-group shape, split rows, the prefetch code path, column-window passes)
+and variant 4 (the sliding-window kernel, planned by the product's own sx_plan_slide)
 against the cpu_spmm_CSR loop, bit for bit.  It is how the
 kernels that were written after the round's GPU time was spent had their index arithmetic,
 staging and barrier structure checked; it does not replace the GPU parity tests."""
@@ -21,6 +22,9 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "emu")
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+# the host-side planners (sx_plan_slide) come from the product library; it loads without a GPU
+LIBDIR = os.path.join(ROOT, "sextans_b200")
+LINK = [f"-L{LIBDIR}", "-lsextans_b200", f"-Wl,-rpath,{LIBDIR}"]
 
 
 def emulated_header():
@@ -42,7 +46,7 @@ def test_block_level_kernels_on_the_cpu_emulation(tmp_path):
     (tmp_path / "spmm_kernels_emu.cuh").write_text(emulated_header())
     exe = tmp_path / "emu_kernels"
     cmd = [CXX, "-std=c++20", "-O1", "-ffp-contract=off", "-pthread", "-w", f"-I{tmp_path}", f"-I{EMU}",
-           f"-I{os.path.join(EMU, 'include')}", os.path.join(EMU, "emu_kernels.cpp"), "-o", str(exe)]
+           f"-I{os.path.join(EMU, 'include')}", os.path.join(EMU, "emu_kernels.cpp"), "-o", str(exe)] + LINK
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
@@ -55,6 +59,8 @@ def test_block_level_kernels_on_the_cpu_emulation(tmp_path):
     staged = re.findall(r"^(staged.*?) +f(?:32|64) M=.*bit-exact$", r.stdout, flags=re.M)
     assert {"staged", "staged + prefetch path", "staged as column-window passes"} <= {k.strip() for k in staged}
     assert len(staged) >= 60
+    slide = re.findall(r"^slide \(variant 4\) +f(?:32|64) M=.*bit-exact$", r.stdout, flags=re.M)
+    assert len(slide) >= 14
 
 
 @pytest.mark.skipif(CXX is None or os.environ.get("SX_EMU_ASAN") != "1",
@@ -67,7 +73,7 @@ def test_emulated_kernels_stay_inside_their_buffers(tmp_path):
     exe = tmp_path / "emu_kernels_asan"
     cmd = [CXX, "-std=c++20", "-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer", "-ffp-contract=off",
            "-pthread", "-w", f"-I{tmp_path}", f"-I{EMU}", f"-I{os.path.join(EMU, 'include')}",
-           os.path.join(EMU, "emu_kernels.cpp"), "-o", str(exe)]
+           os.path.join(EMU, "emu_kernels.cpp"), "-o", str(exe)] + LINK
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=1800)

@@ -72,3 +72,61 @@ def test_row_partition_invariants(lens, parts):
             target = -(-nnz * p // parts)
             assert rp[b[p]] >= target or b[p] == M
             assert b[p] == 0 or rp[b[p] - 1] < target or b[p] == b[p - 1]
+
+
+@st.composite
+def banded_matrices(draw):
+    M = draw(st.integers(1, 400))
+    K = draw(st.integers(8, 500))
+    half = draw(st.integers(0, 60))
+    jitter = draw(st.integers(0, 40))
+    per_row = draw(st.integers(0, 6))
+    seed = draw(st.integers(0, 2**31 - 1))
+    rng = np.random.default_rng(seed)
+    rp = np.zeros(M + 1, dtype=np.int32)
+    cols = []
+    for r in range(M):
+        centre = int(np.clip(r * K // M + rng.integers(-jitter, jitter + 1), 0, K - 1))
+        lo, hi = max(0, centre - half), min(K, centre + half + 1)
+        n = 0 if rng.random() < 0.15 else min(per_row, hi - lo)
+        cols.append(np.sort(rng.choice(np.arange(lo, hi), size=n, replace=False)))
+        rp[r + 1] = rp[r] + n
+    ci = np.concatenate(cols + [np.zeros(0, dtype=np.int64)]).astype(np.int32)
+    return M, K, rp, ci
+
+
+@settings(max_examples=150, deadline=None)
+@given(a=banded_matrices(), nchains=st.integers(1, 12))
+def test_slide_plan_keeps_every_needed_row_in_the_ring(a, nchains):
+    """Worst-case replay of the sliding-window kernel's schedule (spmm_slide_kernel): the loads
+    of step s+1 may have landed completely before step s computes, the loads of step s+2 are
+    issued right after step s; with a ring of exactly ring_rows rows (tighter than the power
+    of two the kernel uses) every column a step touches must be resident when it computes,
+    and the A buffers must be large enough."""
+    M, K, rp, ci = a
+    steps, chains, ring_rows, max_entries = sx.plan_slide(M, rp, ci, nchains)
+    nsteps = (M + 31) // 32
+    assert steps.shape == (nsteps, 4) and 1 <= chains.shape[0] <= min(nchains, nsteps)
+    assert chains[0, 0] == 0 and chains[-1, 1] == nsteps and np.all(chains[1:, 0] == chains[:-1, 1])
+    assert np.all(chains[:, 1] > chains[:, 0]) and max_entries % 4 == 0
+    for R in (ring_rows, 1 << max(5, int(np.ceil(np.log2(max(ring_rows, 1)))))):
+        for b, e in chains:
+            ring = np.full(R, -1, dtype=np.int64)
+
+            def load(s):
+                lo, hi = int(steps[s, 0]), int(steps[s, 1])
+                assert 0 <= lo <= hi <= K
+                rows = np.arange(lo, hi)
+                ring[rows % R] = rows
+
+            load(b)
+            if b + 1 < e:
+                load(b + 1)
+            for s in range(b, e):
+                r0, r1 = s * 32, min(M, s * 32 + 32)
+                assert steps[s, 2] == rp[r0] and steps[s, 3] == rp[r1]
+                assert steps[s, 3] - (steps[s, 2] & ~3) <= max_entries
+                need = ci[rp[r0]:rp[r1]].astype(np.int64)
+                assert np.array_equal(ring[need % R], need), (s, R)
+                if s + 2 < e:
+                    load(s + 2)
