@@ -671,36 +671,65 @@ spmm_slide_kernel(const int M, const int2 *__restrict__ chains, const int4 *__re
         issue(ch.x, 0);
         if (ch.x + 1 < ch.y) issue(ch.x + 1, 1);
     }
+    // the row pointers and the A-slice origin of a step are fetched one step ahead, so that no
+    // global-memory latency sits between the arrival of a step's data and its arithmetic
+    int nbegin = 0, nend = 0, njal = 0;
+    {
+        const int row0 = ch.x * 32 + rl;
+        if (ch.x < ch.y) {
+            njal = __ldg(&steps[ch.x].z) & ~3;
+            if (row0 < M && lg < nvec) { nbegin = __ldg(rowptr + row0); nend = __ldg(rowptr + row0 + 1); }
+        }
+    }
     for (int s = ch.x, i = 0; s < ch.y; ++s, ++i) {
         const int slot = i & 1;
         const int row = s * 32 + rl;
         const bool mine = row < M && lg < nvec;
-        int begin = 0, end = 0;
+        const int begin = nbegin, end = nend, jal = njal;
         V acc, cin;
         vzero(acc);
         vzero(cin);
-        if (mine) {
-            begin = __ldg(rowptr + row);
-            end = __ldg(rowptr + row + 1);
-            cin = reinterpret_cast<const V *>(Cin)[(size_t)row * ldcv + lg];
+        if (mine) cin = reinterpret_cast<const V *>(Cin)[(size_t)row * ldcv + lg];
+        if (s + 1 < ch.y) {
+            const int nrow = row + 32;
+            njal = __ldg(&steps[s + 1].z) & ~3;
+            nbegin = nend = 0;
+            if (nrow < M && lg < nvec) { nbegin = __ldg(rowptr + nrow); nend = __ldg(rowptr + nrow + 1); }
         }
-        const int jal = __ldg(&steps[s].z) & ~3;
         mbar_wait(&full[slot], (uint32_t)((i >> 1) & 1));
         if (mine) {
             const T *sv = svals + (size_t)slot * abuf - jal;  // sv[j] = value of nonzero j
             const int *sc = scols + (size_t)slot * abuf - jal;
             const V *w = ring + lg;
+            // chunks of 8 nonzeros, software-pipelined: the (col, val) pairs of chunk k+1 and the
+            // eight B-row pieces of chunk k are in flight while the strictly ordered chain of
+            // additions of chunk k runs -- with one block of 8 warps per SM there is little else
+            // to hide shared-memory latency behind
+            constexpr int UC = 8;
             int j = begin;
-            for (; j + 4 <= end; j += 4) {
-                int c[4];
-                T a[4];
-                V b[4];
+            if (j + UC <= end) {
+                int c[UC];
+                T a[UC];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { c[u] = sc[j + u]; a[u] = sv[j + u]; }
+                for (int u = 0; u < UC; ++u) { c[u] = sc[j + u]; a[u] = sv[j + u]; }
+                for (;;) {
+                    V b[UC];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) b[u] = w[((uint32_t)c[u] & rmask) * ldbv];
+                    for (int u = 0; u < UC; ++u) b[u] = w[((uint32_t)c[u] & rmask) * ldbv];
+                    const int jn = j + UC;
+                    const bool more = jn + UC <= end;
+                    int c2[UC];
+                    T a2[UC];
+                    const int jl = more ? jn : j;  // unconditional loads (re-reading this chunk when there is no next one)
 #pragma unroll
-                for (int u = 0; u < 4; ++u) vmac<STRICT>(acc, a[u], b[u]);
+                    for (int u = 0; u < UC; ++u) { c2[u] = sc[jl + u]; a2[u] = sv[jl + u]; }
+#pragma unroll
+                    for (int u = 0; u < UC; ++u) vmac<STRICT>(acc, a[u], b[u]);
+                    j = jn;
+                    if (!more) break;
+#pragma unroll
+                    for (int u = 0; u < UC; ++u) { c[u] = c2[u]; a[u] = a2[u]; }
+                }
             }
             for (; j < end; ++j) vmac<STRICT>(acc, sv[j], w[((uint32_t)sc[j] & rmask) * ldbv]);
             reinterpret_cast<V *>(Cout)[(size_t)row * ldcv + lg] = vaxpby<STRICT>(alpha, acc, beta, cin);
