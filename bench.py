@@ -66,6 +66,7 @@ def parse():
     p.add_argument("--band", type=int, default=2000, help="fem workload: couplings reach +-band nodes")
     p.add_argument("--tiles", type=int, default=0, help="SX_OPT_TILE_MIN_ROWS (fp64 dense-tile tensor-core variant; 0 off)")
     p.add_argument("--col-window-rows", type=int, default=0, help="SX_OPT_COL_WINDOW_ROWS (column-window passes keeping a window of B in L2; 0 off, -1 = 32 MiB of B per window)")
+    p.add_argument("--autotune", action="store_true", help="SX_OPT_AUTOTUNE (experimental): time the applicable variants on the first call and keep the fastest")
     p.add_argument("--slide", type=int, default=0, help="SX_OPT_SLIDE (experimental): chains per SM of the sliding-window kernel; use with --kernel 4")
     p.add_argument("--window-rows", type=int, default=0, choices=[0, 32, 64, 128], help="SX_OPT_WINDOW_ROWS (experimental): rows per block of variant 3")
     p.add_argument("--pdl", action="store_true", help="SX_OPT_PDL (experimental): variant 3 launched with programmatic stream serialization")
@@ -342,6 +343,7 @@ def run_native(args):
         e.set_option(sx.OPT_PDL, 1 if args.pdl else 0)
         e.set_option(sx.OPT_WINDOW_ROWS, args.window_rows)
         e.set_option(sx.OPT_SLIDE, args.slide)
+        e.set_option(sx.OPT_AUTOTUNE, 1 if args.autotune else 0)
         if args.split >= 0:
             e.set_option(sx.OPT_SPLIT_ROW_NNZ, args.split)
         e.upload_csr(M, K, w["rowptr"], w["colidx"], w["val"])

@@ -144,7 +144,15 @@ enum sx_option {
      * arithmetic.  For LONG banded matrices, where variant 3 keeps re-fetching nearly the same
      * window.  Falls back to the automatic choice where the ring the plan needs does not fit
      * in shared memory for the N in use.  Results are unaffected.  0 (default): no plan. */
-    SX_OPT_SLIDE = 11
+    SX_OPT_SLIDE = 11,
+    /* EXPERIMENTAL (not yet run on hardware).  1: the first SpMM for a column count N (device
+     * operands with C_out != C_in, outside graph capture) times every kernel variant that
+     * applies to this matrix -- 1, 2 without / with the L2 prefetch, 3, and 4 when a plan
+     * exists -- on the caller's own operands (one warm-up, three timed launches each) and
+     * later calls with that N use the fastest; SX_INFO_TUNED_KERNEL reports it.  The selection
+     * rules of SX_OPT_KERNEL = 0 are thresholds measured on a handful of matrices; this
+     * measures the matrix at hand.  Cleared by the next upload. */
+    SX_OPT_AUTOTUNE = 12
 };
 
 enum sx_info {
@@ -165,7 +173,9 @@ enum sx_info {
     SX_INFO_REST_NNZ = 13,   /* nonzeros left to the CSR kernels */
     SX_INFO_UPLOAD_SERIAL = 14, /* process-wide serial number of the matrix this context holds
                                  * (every successful sx_upload_csr_* draws a new one; 0: none) */
-    SX_INFO_COL_WINDOWS = 15    /* column windows in use (0: the matrix is not windowed) */
+    SX_INFO_COL_WINDOWS = 15,   /* column windows in use (0: the matrix is not windowed) */
+    SX_INFO_TUNED_KERNEL = 16   /* SX_OPT_AUTOTUNE's choice for the current N: 10 * variant + (1 if
+                                 * with the L2 prefetch), 0 if nothing has been tuned */
 };
 
 /* ---- library ------------------------------------------------------------- */

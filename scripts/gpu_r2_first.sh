@@ -25,6 +25,10 @@ for dt in f32 f64; do for sl in 1 2; do
   python bench.py --workload fem --band 100 --dtype $dt --kernel 4 --slide $sl --steps 20 --no-cpu-baseline > gpurun_out/r2a_fem_band100_${dt}_slide$sl.json 2>/dev/null
   python -c "import json,sys; d=json.load(open(sys.argv[1])); print('fem band=100 $dt slide=$sl: ms', round(d['ms_per_step'],4), 'frac', round(d['roofline']['frac'],3), d['roofline']['kernel'][:50])" gpurun_out/r2a_fem_band100_${dt}_slide$sl.json
 done; done
+for wlk in nasa4704 pcrystk02 uniform powerlaw; do
+  python bench.py --workload $wlk --steps 20 --no-cpu-baseline --autotune --slide 1 > gpurun_out/r2a_autotune_$wlk.json 2>/dev/null
+  python -c "import json,sys; d=json.load(open(sys.argv[1])); print('autotune $wlk: ms', round(d['ms_per_step'],5), d['roofline']['kernel'][:60])" gpurun_out/r2a_autotune_$wlk.json
+done
 for kb in 28 56 84; do
   SX_STAGE_KB=$kb PROBE_SET=0:-1 timeout 100 python scripts/probe_windows.py 2>&1 | tail -1 | sed "s/^/stage_kb=$kb /"
 done | tee gpurun_out/r2a_stage_kb.log

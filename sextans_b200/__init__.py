@@ -27,10 +27,11 @@ _LIB = None
 SX_F32, SX_F64 = 0, 1
 STRICT, FAST = 0, 1
 (OPT_ARITH, OPT_SPLIT_ROW_NNZ, OPT_KERNEL, OPT_ITEM_NNZ, OPT_ZEROCOPY_BYTES, OPT_TILE_MIN_ROWS,
- OPT_COL_WINDOW_ROWS, OPT_PREFETCH, OPT_HOST_FUSED, OPT_PDL, OPT_WINDOW_ROWS, OPT_SLIDE) = range(12)
+ OPT_COL_WINDOW_ROWS, OPT_PREFETCH, OPT_HOST_FUSED, OPT_PDL, OPT_WINDOW_ROWS, OPT_SLIDE,
+ OPT_AUTOTUNE) = range(13)
 (INFO_LAUNCHES, INFO_M, INFO_K, INFO_NNZ, INFO_DTYPE, INFO_SPLIT_ROWS, INFO_LAST_KERNEL, INFO_LD,
  INFO_ITEMS, INFO_ITEM_NNZ, INFO_HOST_PATH, INFO_TILE_NNZ, INFO_TILE_SLOTS, INFO_REST_NNZ,
- INFO_UPLOAD_SERIAL, INFO_COL_WINDOWS) = range(16)
+ INFO_UPLOAD_SERIAL, INFO_COL_WINDOWS, INFO_TUNED_KERNEL) = range(17)
 
 _PI32 = C.POINTER(C.c_int32)
 _PF = C.POINTER(C.c_float)

@@ -109,6 +109,12 @@ struct sx_ctx {
     struct WideBlocks { DevBuf blocks; int n = 0, max_span = 0, max_block_nnz = 0; } wide[2];
     int window_rows = 0;  // 0 / 32: the validated 32-row blocks; 64, 128: wide[0], wide[1]
     // variant 4 (SX_OPT_SLIDE, experimental): chains of 32-row steps over a sliding B window
+    // SX_OPT_AUTOTUNE: per (N, arithmetic) the variant that measured fastest on this matrix
+    struct Tuned { int N, arith, kernel, prefetch; float us; };
+    std::vector<Tuned> tuned;
+    int autotune = 0;
+    bool tuning = false;  // inside a tuning / tuned launch: do not recurse
+    cudaEvent_t tune_ev0 = nullptr, tune_ev1 = nullptr;
     int slide = 0;  // option: chains per SM to plan at the next upload (0: no plan)
     DevBuf slide_steps, slide_chains;
     int slide_nsteps = 0, slide_nchains = 0, slide_ring_rows = 0, slide_max_entries = 0;
@@ -401,6 +407,8 @@ int launch_group(sx_ctx *c, Shape s, int N, T alpha, const T *dB, int64_t ldb, T
 
 template <typename T>
 int spmm_device(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, const T *dCin, T *dCout, int64_t ldc);
+template <typename T>
+int autotune(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, const T *dCin, T *dCout, int64_t ldc);
 
 // A = A_tiles + A_rest:  C_out = alpha*A_tiles*B + beta*C_in on the FP64 tensor cores,
 // then C_out += alpha*A_rest*B with the CSR kernels, in place.
@@ -477,6 +485,59 @@ int spmm_windows(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
     return SX_OK;
 }
 
+// SX_OPT_AUTOTUNE: measure, don't guess.  Runs every kernel variant that applies to this
+// matrix and N (1: row per lane group; 2: TMA-staged items without and with the L2 prefetch;
+// 3: B window per block; 4: sliding window, when a plan exists) on the caller's operands --
+// one warm-up launch, then three timed between two events -- and records the fastest.  A
+// variant that falls back to another one (its last_kernel id says so) is skipped.  All of them
+// write the same C, so the caller's output is simply written several times; skipped (nothing
+// recorded, the default rules apply) while the stream is being captured into a graph.
+template <typename T>
+int autotune(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, const T *dCin, T *dCout, int64_t ldc) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    SX_CUDA(cudaStreamIsCapturing(c->stream, &cap));
+    if (cap != cudaStreamCaptureStatusNone) return SX_OK;
+    if (!c->tune_ev0) {
+        SX_CUDA(cudaEventCreate(&c->tune_ev0));
+        SX_CUDA(cudaEventCreate(&c->tune_ev1));
+    }
+    struct Cand { int kernel, prefetch, family; };
+    const Cand cands[] = {{1, -1, 1}, {2, 0, 2}, {2, 1, 2}, {3, -1, 3}, {4, -1, 7}};
+    const int user_kernel = c->kernel, user_prefetch = c->prefetch;
+    float best_ms = 0.f;
+    sx_ctx::Tuned best = {N, c->arith, 0, -1, 0.f};
+    int rc = SX_OK;
+    c->tuning = true;
+    for (const Cand &k : cands) {
+        if (k.kernel == 4 && c->slide_nchains == 0) continue;
+        c->kernel = k.kernel;
+        c->prefetch = k.prefetch;
+        if ((rc = spmm_device<T>(c, N, alpha, dB, ldb, beta, dCin, dCout, ldc))) break;  // warm-up: plans, attributes
+        if (c->last_kernel / 10000 != k.family) continue;                                 // fell back to another variant
+        if (cudaEventRecord(c->tune_ev0, c->stream) != cudaSuccess) { rc = fail(SX_ERR_CUDA, "autotune: event record failed"); break; }
+        for (int r = 0; r < 3 && !rc; ++r) rc = spmm_device<T>(c, N, alpha, dB, ldb, beta, dCin, dCout, ldc);
+        if (rc) break;
+        float ms = 0.f;
+        if (cudaEventRecord(c->tune_ev1, c->stream) != cudaSuccess || cudaEventSynchronize(c->tune_ev1) != cudaSuccess ||
+            cudaEventElapsedTime(&ms, c->tune_ev0, c->tune_ev1) != cudaSuccess) {
+            rc = fail(SX_ERR_CUDA, "autotune: timing failed");
+            break;
+        }
+        if (best.kernel == 0 || ms < best_ms) {
+            best_ms = ms;
+            best.kernel = k.kernel;
+            best.prefetch = k.prefetch;
+            best.us = ms * 1000.f / 3.f;
+        }
+    }
+    c->tuning = false;
+    c->kernel = user_kernel;
+    c->prefetch = user_prefetch;
+    if (rc) return rc;
+    if (best.kernel != 0) c->tuned.push_back(best);
+    return SX_OK;
+}
+
 // One SpMM over device-resident row-major operands.  Column counts beyond what one
 // row group covers (4 vectors x 32 lanes) are processed in column panels.
 template <typename T>
@@ -499,6 +560,29 @@ int spmm_device(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, con
     if (!c->wins.empty()) return spmm_windows<T>(c, N, alpha, dB, ldb, beta, dCin, dCout, ldc);
 
     const int panel_cols = 4 * 32 * E;  // widest shape: G = 32, VPL = 4
+    // SX_OPT_AUTOTUNE: the first call for a column count times every variant that applies on
+    // the caller's own operands and keeps the fastest for later calls with that N
+    if (c->autotune && !c->tuning && !c->win_mode && N <= panel_cols && dCin != dCout) {
+        const sx_ctx::Tuned *t = nullptr;
+        for (const auto &e : c->tuned)
+            if (e.N == N && e.arith == c->arith) t = &e;
+        if (!t) {
+            if ((rc = autotune<T>(c, N, alpha, dB, ldb, beta, dCin, dCout, ldc))) return rc;
+            for (const auto &e : c->tuned)
+                if (e.N == N && e.arith == c->arith) t = &e;
+        }
+        if (t) {
+            const int user_kernel = c->kernel, user_prefetch = c->prefetch;
+            c->kernel = t->kernel;
+            c->prefetch = t->prefetch;
+            c->tuning = true;
+            rc = spmm_device<T>(c, N, alpha, dB, ldb, beta, dCin, dCout, ldc);
+            c->tuning = false;
+            c->kernel = user_kernel;
+            c->prefetch = user_prefetch;
+            return rc;
+        }
+    }
     for (int n0 = 0; n0 < N; n0 += panel_cols) {
         const int n = std::min(panel_cols, N - n0);
         const int nvec = (n * (int)sizeof(T) + 15) / 16;
@@ -917,6 +1001,7 @@ int upload_csr(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rowptr, cons
             return fail(SX_ERR_INVALID, "column index %d out of range at nonzero %lld", colidx[j], (long long)j);
     c->has_A = false;
     c->upload_serial = 0;
+    c->tuned.clear();
     if ((rc = c->rowptr.ensure(((size_t)M + 1) * 4))) return rc;
     if ((rc = c->colidx.ensure((size_t)nnz * 4 + 16))) return rc;  // +16: TMA reads whole 16-byte units
     if ((rc = c->val.ensure((size_t)nnz * sizeof(T) + 32))) return rc;
@@ -1315,6 +1400,8 @@ int sx_destroy(sx_ctx *c) {
     for (DevBuf *b : {&c->step_ptr, &c->tcols, &c->tvals, &c->psum, &c->wide[0].blocks, &c->wide[1].blocks,
                       &c->slide_steps, &c->slide_chains})
         b->release();
+    if (c->tune_ev0) cudaEventDestroy(c->tune_ev0);
+    if (c->tune_ev1) cudaEventDestroy(c->tune_ev1);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -1361,6 +1448,10 @@ int sx_set_option(sx_ctx *c, int option, int64_t value) {
             c->segments_dirty = c->has_A;
             if (c->rest) c->rest->segments_dirty = true;
             for (sx_ctx *k : c->wins) k->segments_dirty = true;
+            return SX_OK;
+        case SX_OPT_AUTOTUNE:
+            if (value != 0 && value != 1) return fail(SX_ERR_INVALID, "SX_OPT_AUTOTUNE is 0 or 1");
+            c->autotune = (int)value;
             return SX_OK;
         case SX_OPT_SLIDE:
             if (value < 0 || value > 8) return fail(SX_ERR_INVALID, "SX_OPT_SLIDE is 0 (off) or the number of chains per SM (1..8)");
@@ -1413,6 +1504,12 @@ int sx_get_info(sx_ctx *c, int what, int64_t *value) {
         case SX_INFO_HOST_PATH: *value = c->last_path; return SX_OK;
         case SX_INFO_ITEMS: *value = c->last_plan ? c->last_plan->nitems : 0; return SX_OK;
         case SX_INFO_ITEM_NNZ: *value = c->last_plan ? c->last_plan->budget : 0; return SX_OK;
+        case SX_INFO_TUNED_KERNEL: {
+            *value = 0;
+            for (const auto &e : c->tuned)
+                if (e.N == c->N || c->N == 0) *value = e.kernel * 10 + (e.prefetch > 0 ? 1 : 0);
+            return SX_OK;
+        }
         case SX_INFO_COL_WINDOWS: *value = (int64_t)c->wins.size(); return SX_OK;
         case SX_INFO_UPLOAD_SERIAL: *value = c->has_A ? c->upload_serial : 0; return SX_OK;
         default: return fail(SX_ERR_INVALID, "unknown info id %d", what);

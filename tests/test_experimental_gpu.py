@@ -186,3 +186,34 @@ def test_sliding_window_kernel_bit_exact(eng, chains_per_sm, dtype, M, K, N):
     C = Cin.copy()
     eng.spmm(N, dtype(0.85), B, dtype(-2.06), C)
     assert np.array_equal(bits(C), bits(ref)) and eng.info(sx.INFO_LAST_KERNEL) // 10000 != 7
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("kind", ["banded", "random"])
+def test_autotune_picks_a_variant_and_keeps_the_result(eng, dtype, kind):
+    """SX_OPT_AUTOTUNE: the first call times the variants that apply and later calls use the
+    fastest; whatever it picks, the result is the oracle's."""
+    from helpers import random_csr
+    M = K = 6000
+    N = 16
+    if kind == "banded":
+        rp, ci, v = banded_csr(M, K, 150, 20, 5, dtype)
+    else:
+        rp, ci, v = random_csr(M, K, 25, 5, dtype)
+    B, Cin = random_dense(M, K, N, 5, dtype)
+    ref = oracle.spmm_csr(M, N, K, rp, ci, v, dtype(0.85), B, dtype(-2.06), Cin.copy())
+    eng.set_option(sx.OPT_SLIDE, 1)
+    eng.set_option(sx.OPT_AUTOTUNE, 1)
+    eng.upload_csr(M, K, rp, ci, v)
+    assert eng.info(sx.INFO_TUNED_KERNEL) == 0
+    for _ in range(3):
+        C = Cin.copy()
+        eng.spmm(N, dtype(0.85), B, dtype(-2.06), C)
+        assert np.array_equal(bits(C), bits(ref))
+    choice = eng.info(sx.INFO_TUNED_KERNEL)
+    assert choice // 10 in (1, 2, 3, 4)
+    family = eng.info(sx.INFO_LAST_KERNEL) // 10000
+    assert family == {1: 1, 2: 2, 3: 3, 4: 7}[choice // 10]
+    # a new upload forgets the choice
+    eng.upload_csr(M, K, rp, ci, v)
+    assert eng.info(sx.INFO_TUNED_KERNEL) == 0
