@@ -104,9 +104,32 @@ inline float __fadd_rn(float a, float b) { return a + b; }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
-// declared so that the kernels that are not emulated still compile
-template <typename T> inline T __shfl_sync(unsigned, T v, int, int = 32) { return v; }
-template <typename T> inline T __shfl_xor_sync(unsigned, T v, int, int = 32) { return v; }
+// warp shuffles: every lane named by the mask posts its value in its warp's mailbox, the
+// lanes meet (the same per-(warp, mask) barrier as __syncwarp), read the slot they were asked
+// for, and meet again before the mailbox may be overwritten
+namespace sx_emu {
+struct alignas(16) Slot { unsigned char b[16]; };
+inline Slot mailbox[64][32];  // [warp of the block][lane]
+template <typename T> inline T exchange(unsigned mask, T v, int src_lane) {
+    static_assert(sizeof(T) <= 16, "shuffle of at most 16 bytes");
+    const unsigned warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    std::memcpy(mailbox[warp][lane].b, &v, sizeof(T));
+    __syncwarp(mask);
+    T out;
+    std::memcpy(&out, mailbox[warp][src_lane & 31].b, sizeof(T));
+    __syncwarp(mask);
+    return out;
+}
+}  // namespace sx_emu
+template <typename T> inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
+    const int lane = (int)(threadIdx.x % 32);
+    return sx_emu::exchange(mask, v, (lane & ~(width - 1)) | (src & (width - 1)));
+}
+template <typename T> inline T __shfl_xor_sync(unsigned mask, T v, int lanemask, int width = 32) {
+    const int lane = (int)(threadIdx.x % 32);
+    const int src = lane ^ lanemask;
+    return sx_emu::exchange(mask, v, (src & ~(width - 1)) == (lane & ~(width - 1)) ? src : lane);
+}
 inline long long clock64() { return 0; }
 inline void __nanosleep(unsigned) {}
 inline void __threadfence() {}

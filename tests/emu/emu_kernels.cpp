@@ -2,7 +2,8 @@
 // sextans_b200/csrc/spmm_kernels.cuh (variant 3 with 32/64/128-row blocks, with and without
 // the PDL code path; the host-boundary fusion spmm_window_hostc_kernel; variant 2, the
 // TMA-staged lane-group kernel with its finalize kernel, plain, with the prefetch code path,
-// and as column-window passes) on the CPU
+// and as column-window passes; variant 1, one lane group per row with warp shuffles, plus its
+// segment kernel; variant 4, the sliding-window kernel) on the CPU
 // emulation of tests/emu/cuda_emu.h and compares them, bit for bit, with the plain loop of
 // cpu_spmm_CSR (src/sparse_helper.h:262-290: stored order, separately rounded * and +;
 // built with -ffp-contract=off).  The kernel source is the product's, textually, with only
@@ -463,6 +464,90 @@ void staged_case(const char *tname, int M, int K, int N, int avg, int long_row, 
     }
 }
 
+// ---- variant 1: one lane group per row (shuffles) + one warp per long-row segment + finalize ----
+template <typename T, int G, int VPL>
+void rows_case(const char *tname, int M, int K, int N, int avg, int long_row, int split, unsigned seed) {
+    const Csr a = random_csr(M, K, avg, long_row, seed);
+    const int nnz = a.rp[M];
+    std::mt19937 rng(seed * 17 + 3);
+    std::uniform_real_distribution<double> U01(-1.0, 1.0);
+    const int64_t ld = (N + 7) / 8 * 8;
+    std::vector<T> hval((size_t)nnz);
+    for (auto &x : hval) x = (T)U01(rng);
+    Aligned<T> val((size_t)nnz, 32), B((size_t)K * ld), Cin((size_t)M * ld), Cout((size_t)M * ld), Ref((size_t)M * ld);
+    Aligned<int> ci((size_t)nnz, 16), rp((size_t)M + 1);
+    std::copy(hval.begin(), hval.end(), val.p);
+    std::copy(a.ci.begin(), a.ci.end(), ci.p);
+    std::copy(a.rp.begin(), a.rp.end(), rp.p);
+    for (int64_t i = 0; i < (int64_t)K * ld; ++i) B.p[i] = (i % ld) < N ? (T)U01(rng) : (T)0;
+    for (int64_t i = 0; i < (int64_t)M * ld; ++i) Cin.p[i] = (i % ld) < N ? (T)U01(rng) : (T)0;
+    const T alpha = (T)0.85f, beta = (T)-2.06f;
+    reference<T>(a, hval, N, B.p, ld, alpha, beta, Cin.p, Ref.p, ld);
+    // segments of the rows longer than `split` (sx_api.cu: refresh_segments)
+    std::vector<int> srow, sptr(1, 0), sb, se;
+    if (split > 0)
+        for (int i = 0; i < M; ++i) {
+            if (a.rp[i + 1] - a.rp[i] <= split) continue;
+            srow.push_back(i);
+            for (int p0 = a.rp[i]; p0 < a.rp[i + 1]; p0 += split) { sb.push_back(p0); se.push_back(std::min(a.rp[i + 1], p0 + split)); }
+            sptr.push_back((int)sb.size());
+        }
+    const int nseg = (int)sb.size(), nsplit = (int)srow.size();
+    Aligned<int> dsrow(srow.size()), dsptr(sptr.size()), dsb(sb.size()), dse(se.size());
+    Aligned<T> partial((size_t)std::max(nseg, 1) * ld);
+    std::copy(srow.begin(), srow.end(), dsrow.p);
+    std::copy(sptr.begin(), sptr.end(), dsptr.p);
+    std::copy(sb.begin(), sb.end(), dsb.p);
+    std::copy(se.begin(), se.end(), dse.p);
+    const int nvec = (N * (int)sizeof(T) + 15) / 16;
+    constexpr int RPB = 256 / G;
+    std::fill(Cout.p, Cout.p + (int64_t)M * ld, (T)777);
+    sx_emu::launch((unsigned)((M + RPB - 1) / RPB), 256, 0, [&] {
+        sx::spmm_rows_kernel<T, G, VPL, true>(M, rp.p, ci.p, val.p, B.p, ld, Cin.p, Cout.p, ld, alpha, beta, nvec, nseg > 0 ? split : 0);
+    });
+    if (nseg > 0) {
+        sx_emu::launch((unsigned)((nseg * 32 + 255) / 256), 256, 0, [&] {
+            sx::spmm_segments_kernel<T, G, VPL, true>(nseg, dsb.p, dse.p, ci.p, val.p, B.p, ld, partial.p, ld, nvec);
+        });
+        sx_emu::launch((unsigned)((nsplit + RPB - 1) / RPB), 256, 0, [&] {
+            sx::spmm_finalize_kernel<T, G, VPL, true, false>(nsplit, dsrow.p, dsptr.p, partial.p, ld, Cin.p, Cout.p, ld, alpha, beta, nvec,
+                                                             (T *)nullptr, 0);
+        });
+    }
+    bool exact = true, close = true;
+    const double tol = sizeof(T) == 4 ? 1e-5 : 1e-12;
+    for (int i = 0; i < M; ++i) {
+        const bool is_split = split > 0 && a.rp[i + 1] - a.rp[i] > split;
+        if (!is_split) exact = exact && same_bits(Cout.p + (int64_t)i * ld, Ref.p + (int64_t)i * ld, (size_t)N);
+        else
+            for (int n = 0; n < N; ++n) {
+                const double x = Cout.p[(int64_t)i * ld + n], y = Ref.p[(int64_t)i * ld + n];
+                close = close && std::fabs(x - y) <= tol * std::max(1.0, std::fabs(y)) * 50;
+            }
+    }
+    std::printf("%-34s %s M=%d K=%d N=%d G=%d VPL=%d split=%d (%d split rows): %s\n", "rows + segments (variant 1)", tname, M, K, N, G,
+                VPL, split, nsplit, exact && close ? "bit-exact" : "MISMATCH");
+    if (!(exact && close)) ++failures;
+}
+
+template <typename T>
+void rows_by_shape(const char *tname, int M, int K, int N, int avg, int long_row, int split, unsigned seed) {
+    const int nvec = (N * (int)sizeof(T) + 15) / 16;
+    int G = 2;
+    while (G < 32 && G < nvec) G <<= 1;
+    int vpl = (nvec + G - 1) / G;
+    if (vpl == 3) vpl = 4;
+#define SX_CASE(GG, VV) rows_case<T, GG, VV>(tname, M, K, N, avg, long_row, split, seed)
+    if (G == 2) SX_CASE(2, 1);
+    else if (G == 4) SX_CASE(4, 1);
+    else if (G == 8) SX_CASE(8, 1);
+    else if (G == 16) SX_CASE(16, 1);
+    else if (vpl == 1) SX_CASE(32, 1);
+    else if (vpl == 2) SX_CASE(32, 2);
+    else SX_CASE(32, 4);
+#undef SX_CASE
+}
+
 template <typename T>
 void staged_by_shape(const char *tname, int M, int K, int N, int avg, int long_row, int budget, int split, int W, unsigned seed) {
     const int nvec = (N * (int)sizeof(T) + 15) / 16;
@@ -498,6 +583,13 @@ int main() {
     for (const auto &c : lcases) {
         slide_by_shape<float>("f32", c.M, c.K, c.N, c.hb, c.per, c.nchains, seed++);
         slide_by_shape<double>("f64", c.M, c.K, c.N, c.hb, c.per, c.nchains, seed++);
+    }
+    const struct { int M, K, N, avg, long_row, split; } rcases[] = {
+        {120, 200, 16, 9, 0, 0}, {90, 300, 8, 11, 250, 64}, {70, 150, 4, 6, 0, 0}, {64, 400, 32, 14, 380, 96},
+        {50, 120, 64, 9, 0, 0}, {40, 100, 136, 7, 90, 32}, {30, 90, 3, 5, 0, 0}};
+    for (const auto &c : rcases) {
+        rows_by_shape<float>("f32", c.M, c.K, c.N, c.avg, c.long_row, c.split, seed++);
+        rows_by_shape<double>("f64", c.M, c.K, c.N, c.avg, c.long_row, c.split, seed++);
     }
     const struct { int M, K, N, avg, long_row, budget, split, W; } scases[] = {
         {300, 400, 16, 12, 0, 64, 0, 128},   {300, 400, 16, 12, 350, 64, 96, 128}, {150, 300, 8, 9, 0, 16, 0, 100},

@@ -59,6 +59,8 @@ def test_block_level_kernels_on_the_cpu_emulation(tmp_path):
     staged = re.findall(r"^(staged.*?) +f(?:32|64) M=.*bit-exact$", r.stdout, flags=re.M)
     assert {"staged", "staged + prefetch path", "staged as column-window passes"} <= {k.strip() for k in staged}
     assert len(staged) >= 60
+    rows = re.findall(r"^rows \+ segments \(variant 1\) +f(?:32|64) M=.*bit-exact$", r.stdout, flags=re.M)
+    assert len(rows) >= 14
     slide = re.findall(r"^slide \(variant 4\) +f(?:32|64) M=.*bit-exact$", r.stdout, flags=re.M)
     assert len(slide) >= 14
 
