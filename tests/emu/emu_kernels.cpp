@@ -211,11 +211,11 @@ void by_shape(const char *tname, int M, int K, int N, int half_band, int per_row
 // ---- variant 4: the sliding-window kernel, planned by the product's own sx_plan_slide ----
 // band whose centre wanders (so that a step's lowest column is not monotone), with stretches of
 // empty rows longer than a 32-row step
-Csr wandering_band(int M, int K, int half_band, int per_row, unsigned seed) {
+Csr wandering_band(int M, int K, int half_band, int per_row, unsigned seed, int max_jitter = 20) {
     std::mt19937 rng(seed);
     Csr a{M, K, std::vector<int>(M + 1, 0), {}};
     for (int r = 0; r < M; ++r) {
-        const int jitter = (int)(rng() % 41) - 20;
+        const int jitter = max_jitter > 0 ? (int)(rng() % (unsigned)(2 * max_jitter + 1)) - max_jitter : 0;
         const int centre = std::clamp((int)((long long)r * K / M) + jitter, 0, K - 1);
         const int lo = std::max(0, centre - half_band), hi = std::min(K, centre + half_band + 1);
         const bool hole = (r / 40) % 9 == 4;  // 40 consecutive empty rows now and then
@@ -233,9 +233,10 @@ Csr wandering_band(int M, int K, int half_band, int per_row, unsigned seed) {
 }
 
 template <typename T, int G>
-void slide_case(const char *tname, int M, int K, int N, int half_band, int per_row, int nchains_wanted, unsigned seed) {
+void slide_case(const char *tname, int M, int K, int N, int half_band, int per_row, int nchains_wanted, unsigned seed,
+                int max_jitter = 20) {
     constexpr int E = 16 / (int)sizeof(T);
-    const Csr a = wandering_band(M, K, half_band, per_row, seed);
+    const Csr a = wandering_band(M, K, half_band, per_row, seed, max_jitter);
     const int nnz = a.rp[M];
     std::mt19937 rng(seed * 3 + 11);
     std::uniform_real_distribution<double> U01(-1.0, 1.0);
@@ -280,15 +281,16 @@ void slide_case(const char *tname, int M, int K, int N, int half_band, int per_r
 }
 
 template <typename T>
-void slide_by_shape(const char *tname, int M, int K, int N, int half_band, int per_row, int nchains, unsigned seed) {
+void slide_by_shape(const char *tname, int M, int K, int N, int half_band, int per_row, int nchains, unsigned seed,
+                    int max_jitter = 20) {
     const int nvec = (N * (int)sizeof(T) + 15) / 16;
     int G = 2;
     while (G < 32 && G < nvec) G <<= 1;
     switch (G) {
-        case 2: slide_case<T, 2>(tname, M, K, N, half_band, per_row, nchains, seed); break;
-        case 4: slide_case<T, 4>(tname, M, K, N, half_band, per_row, nchains, seed); break;
-        case 8: slide_case<T, 8>(tname, M, K, N, half_band, per_row, nchains, seed); break;
-        case 16: slide_case<T, 16>(tname, M, K, N, half_band, per_row, nchains, seed); break;
+        case 2: slide_case<T, 2>(tname, M, K, N, half_band, per_row, nchains, seed, max_jitter); break;
+        case 4: slide_case<T, 4>(tname, M, K, N, half_band, per_row, nchains, seed, max_jitter); break;
+        case 8: slide_case<T, 8>(tname, M, K, N, half_band, per_row, nchains, seed, max_jitter); break;
+        case 16: slide_case<T, 16>(tname, M, K, N, half_band, per_row, nchains, seed, max_jitter); break;
         default: break;
     }
 }
@@ -584,6 +586,12 @@ int main() {
         slide_by_shape<float>("f32", c.M, c.K, c.N, c.hb, c.per, c.nchains, seed++);
         slide_by_shape<double>("f64", c.M, c.K, c.N, c.hb, c.per, c.nchains, seed++);
     }
+    // a straight, densely filled band: the ring the plan asks for is (almost) exactly a power of
+    // two, so a row arriving for the next step lands on the slot of the oldest row still in use
+    // by the previous one plus one -- no slack to hide an off-by-one in the plan or the kernel
+    slide_by_shape<float>("f32", 2048, 2048, 16, 32, 40, 4, seed++, 0);
+    slide_by_shape<double>("f64", 2048, 2048, 16, 96, 60, 3, seed++, 0);
+    slide_by_shape<double>("f64", 1024, 1024, 8, 32, 50, 1, seed++, 0);
     const struct { int M, K, N, avg, long_row, split; } rcases[] = {
         {120, 200, 16, 9, 0, 0}, {90, 300, 8, 11, 250, 64}, {70, 150, 4, 6, 0, 0}, {64, 400, 32, 14, 380, 96},
         {50, 120, 64, 9, 0, 0}, {40, 100, 136, 7, 90, 32}, {30, 90, 3, 5, 0, 0}};
