@@ -282,6 +282,24 @@ template <int U> __device__ __forceinline__ void lds_vec(const double *p, double
 // (windows ascend, columns ascend inside a window), so strict mode stays bit-identical.
 // P[row + 1] is fetched when row opens, like C_in, so its latency hides behind the row.
 constexpr int SX_WIN_INIT = 1, SX_WIN_RAW = 2;
+// Build-time tuning knobs of the staged kernel (defaults = the measured configuration; an
+// alternative library for an A/B run is `make EXTRA_DEFS="-DSX_STAGED_UMAX=16 -DSX_STAGED_MINBLOCKS_F64=2"`):
+// most B-row gathers a lane keeps in flight per batch, and the blocks per SM the register
+// allocation is held to (fp64 / fp32, one vector per lane).
+#ifndef SX_STAGED_UMAX
+#define SX_STAGED_UMAX 8
+#endif
+#ifndef SX_STAGED_MINBLOCKS_F64
+#define SX_STAGED_MINBLOCKS_F64 3
+#endif
+#ifndef SX_STAGED_MINBLOCKS_F32
+#define SX_STAGED_MINBLOCKS_F32 4
+#endif
+// gathers per batch per lane for a lane-group shape (shared with the host's tile sizing)
+template <int G, int VPL> struct StagedBatch {
+    static constexpr int U = (G < SX_STAGED_UMAX ? G : SX_STAGED_UMAX) / (VPL > 2 ? 4 : VPL);
+    static_assert(U == 2 || U == 4 || U == 8 || U == 16, "a batch is 2, 4, 8 or 16 nonzeros");
+};
 // wflags bit 2 (any instantiation): while a batch's gathers are in flight, ask L2 for the
 // B rows of the NEXT batch (its columns already sit in the shared-memory tile), so that
 // the next batch's gathers find them in L2 instead of paying the DRAM latency on the
@@ -292,7 +310,7 @@ __device__ __forceinline__ void prefetch_l2(const void *p) {
 }
 
 template <typename T, int G, int VPL, bool STRICT, bool WIN = false>
-__global__ void __launch_bounds__(256, (VPL > 1 ? 2 : (sizeof(T) == 8 ? 3 : 4)))
+__global__ void __launch_bounds__(256, (VPL > 1 ? 2 : (sizeof(T) == 8 ? SX_STAGED_MINBLOCKS_F64 : SX_STAGED_MINBLOCKS_F32)))
 spmm_staged_kernel(const int nitems, const int4 *__restrict__ items, const int ts,
                    const int *__restrict__ rowptr, const int *__restrict__ colidx,
                    const T *__restrict__ val, const T *__restrict__ B, const uint32_t ldbv, const T *Cin,
@@ -302,7 +320,7 @@ spmm_staged_kernel(const int nitems, const int4 *__restrict__ items, const int t
     const bool w_init = WIN && (wflags & SX_WIN_INIT);
     const bool w_raw = WIN && (wflags & SX_WIN_RAW);
     const bool pf = (wflags & SX_FLAG_PREFETCH) != 0;
-    constexpr int U = (G < 8 ? G : 8) / (VPL > 2 ? 4 : VPL);  // gathers per batch per lane
+    constexpr int U = StagedBatch<G, VPL>::U;  // gathers per batch per lane
     constexpr int GPB = 256 / G;                               // lane groups per block
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // layout: [GPB][2] mbarriers | [GPB][2*ts] T values | [GPB][2*ts] int columns
@@ -399,8 +417,8 @@ spmm_staged_kernel(const int nitems, const int4 *__restrict__ items, const int t
     };
 
     if (je > jb) {
-        constexpr int USH = U == 8 ? 3 : (U == 4 ? 2 : 1);
-        static_assert((1 << USH) == U, "U is 2, 4 or 8");
+        constexpr int USH = U == 16 ? 4 : (U == 8 ? 3 : (U == 4 ? 2 : 1));
+        static_assert((1 << USH) == U, "U is 2, 4, 8 or 16");
         const int bsh = tsh - USH;           // log2(batches per tile)
         const int bmask = (1 << bsh) - 1;
         const int nb = (len + U - 1) / U;

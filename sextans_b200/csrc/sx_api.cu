@@ -342,7 +342,7 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
         }
     } else if (c->M > 0) {
         // variant 2: TMA-staged work items (+ finalize for rows split into pieces)
-        constexpr int U = (G < 8 ? G : 8) / (VPL > 2 ? 4 : VPL);
+        constexpr int U = sx::StagedBatch<G, VPL>::U;
         constexpr int E = sx::VecOf<T>::E;
         Plan *p = nullptr;
         if ((rc = get_plan(c, pick_budget(c, G), &p))) return rc;

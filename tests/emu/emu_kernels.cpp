@@ -376,7 +376,7 @@ template <typename T, int G, int VPL, bool WIN>
 void launch_staged(const std::vector<int> &rp, const std::vector<int> &ci, const std::vector<T> &hval, int M, int N,
                    const T *B, int64_t ld, T alpha, T beta, const T *Cin, T *Cout, int budget, int split, T *P, int wflags) {
     constexpr int E = 16 / (int)sizeof(T);
-    constexpr int U = (G < 8 ? G : 8) / (VPL > 2 ? 4 : VPL);
+    constexpr int U = sx::StagedBatch<G, VPL>::U;
     constexpr int GPB = 256 / G;
     const PlanE plan = make_plan(rp, M, budget, split);
     const int nitems = (int)(plan.items.size() / 4);

@@ -25,6 +25,8 @@ CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
 # the host-side planners (sx_plan_slide) come from the product library; it loads without a GPU
 LIBDIR = os.path.join(ROOT, "sextans_b200")
 LINK = [f"-L{LIBDIR}", "-lsextans_b200", f"-Wl,-rpath,{LIBDIR}"]
+# SX_EMU_DEFS="-DSX_STAGED_UMAX=16" checks an alternative build-time configuration of the kernels
+LINK += os.environ.get("SX_EMU_DEFS", "").split()
 
 
 def emulated_header():
