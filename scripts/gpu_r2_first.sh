@@ -32,9 +32,9 @@ done
 for kb in 28 56 84; do
   SX_STAGE_KB=$kb PROBE_SET=0:-1 timeout 100 python scripts/probe_windows.py 2>&1 | tail -1 | sed "s/^/stage_kb=$kb /"
 done | tee gpurun_out/r2a_stage_kb.log
-# alternative build of the staged kernel: 16 gathers in flight per lane, 2 blocks per SM (fp64)
-cp sextans_b200/libsextans_b200.so /tmp/libsextans_b200.default.so
-make -C sextans_b200/csrc -B sx_api.o EXTRA_DEFS="-DSX_STAGED_UMAX=16 -DSX_STAGED_MINBLOCKS_F64=2" > gpurun_out/r2a_umax16_build.log 2>&1 && make -C sextans_b200/csrc >> gpurun_out/r2a_umax16_build.log 2>&1
-PROBE_SET=0:-1 timeout 100 python scripts/probe_windows.py 2>&1 | tail -1 | sed "s/^/umax16 /" | tee gpurun_out/r2a_umax16.log
-cp /tmp/libsextans_b200.default.so sextans_b200/libsextans_b200.so
-
+# alternative build of the staged kernel: 16 gathers in flight per lane, 2 blocks per SM (fp64).
+# Build it BEFORE the gpurun call, here on the CPU:
+#   scripts/build_variant.sh umax16 "-DSX_STAGED_UMAX=16 -DSX_STAGED_MINBLOCKS_F64=2"
+if [ -f sextans_b200/variants/libsextans_b200_umax16.so ]; then
+  SX_LIBRARY_PATH=$PWD/sextans_b200/variants/libsextans_b200_umax16.so PROBE_SET=0:-1 timeout 100 python scripts/probe_windows.py 2>&1 | tail -1 | sed "s/^/umax16 /" | tee gpurun_out/r2a_umax16.log
+fi

@@ -49,7 +49,9 @@ class SextansError(RuntimeError):
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libsextans_b200.so")
+    """The C-ABI library.  SX_LIBRARY_PATH selects an alternative build of it (a tuning
+    variant made by scripts/build_variant.sh); it is still this product's CUDA library."""
+    return os.environ.get("SX_LIBRARY_PATH") or os.path.join(_HERE, "libsextans_b200.so")
 
 
 def lib():
