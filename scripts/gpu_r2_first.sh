@@ -38,3 +38,12 @@ done | tee gpurun_out/r2a_stage_kb.log
 if [ -f sextans_b200/variants/libsextans_b200_umax16.so ]; then
   SX_LIBRARY_PATH=$PWD/sextans_b200/variants/libsextans_b200_umax16.so PROBE_SET=0:-1 timeout 100 python scripts/probe_windows.py 2>&1 | tail -1 | sed "s/^/umax16 /" | tee gpurun_out/r2a_umax16.log
 fi
+# compute-sanitizer on the small configs: memcheck and racecheck of the
+# golden / canned-run tests, default paths and (gated) experimental ones
+for tool in memcheck racecheck; do
+  timeout 600 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_spmm_gpu.py -q -p no:cacheprovider -k "small_golden or config2 or every_kernel_variant" > gpurun_out/r2a_sanitizer_$tool.log 2>&1
+  echo "compute-sanitizer $tool rc=$?"; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/r2a_sanitizer_$tool.log | tail -3
+done
+SX_TEST_EXPERIMENTAL=1 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_experimental_gpu.py -q -p no:cacheprovider -k "64-64-4 or 70-64-4 or 1000" > gpurun_out/r2a_sanitizer_experimental.log 2>&1
+echo "compute-sanitizer experimental rc=$?"; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/r2a_sanitizer_experimental.log | tail -3
+
