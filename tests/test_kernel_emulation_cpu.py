@@ -83,3 +83,24 @@ def test_emulated_kernels_stay_inside_their_buffers(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=1800)
     assert r.returncode == 0 and "AddressSanitizer" not in r.stderr, r.stderr[-4000:]
     assert "EMULATION: all bit-exact" in r.stdout
+
+
+@pytest.mark.skipif(CXX is None or os.environ.get("SX_EMU_TSAN") != "1",
+                    reason="thread-sanitizer pass of the emulation: set SX_EMU_TSAN=1 (about two minutes)")
+def test_emulated_kernels_have_no_shared_memory_races(tmp_path):
+    """The same run under ThreadSanitizer: the emulation's CUDA threads are OS threads, its
+    barriers / mbarriers are real synchronisation, so a missing __syncthreads, a TMA copy into
+    shared memory that other threads still read, or two threads writing one location shows up
+    as a data race.  (Removing one barrier from the host-boundary fusion kernel produces 64
+    reports.)  A CPU-side stand-in for `compute-sanitizer --tool racecheck`."""
+    (tmp_path / "spmm_kernels_emu.cuh").write_text(emulated_header())
+    exe = tmp_path / "emu_kernels_tsan"
+    cmd = [CXX, "-std=c++20", "-O1", "-g", "-fsanitize=thread", "-ffp-contract=off", "-pthread", "-w",
+           f"-I{tmp_path}", f"-I{EMU}", f"-I{os.path.join(EMU, 'include')}", os.path.join(EMU, "emu_kernels.cpp"),
+           "-o", str(exe)] + LINK
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=1800)
+    assert "ThreadSanitizer" not in r.stderr, r.stderr[:4000]
+    assert r.returncode == 0 and "EMULATION: all bit-exact" in r.stdout
+
