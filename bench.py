@@ -69,7 +69,8 @@ def parse():
     p.add_argument("--autotune", action="store_true", help="SX_OPT_AUTOTUNE (experimental): time the applicable variants on the first call and keep the fastest")
     p.add_argument("--slide", type=int, default=0, help="SX_OPT_SLIDE (experimental): chains per SM of the sliding-window kernel; use with --kernel 4")
     p.add_argument("--window-rows", type=int, default=0, choices=[0, 32, 64, 128], help="SX_OPT_WINDOW_ROWS (experimental): rows per block of variant 3")
-    p.add_argument("--pdl", action="store_true", help="SX_OPT_PDL (experimental): variant 3 launched with programmatic stream serialization")
+    p.add_argument("--pdl", type=int, default=-1, choices=[-1, 0, 1], help="SX_OPT_PDL: programmatic dependent launch (-1 auto: on for the edge-list kernel)")
+    p.add_argument("--prefetch", type=int, default=-1, choices=[-1, 0, 1], help="SX_OPT_PREFETCH: L2 prefetch hints (-1 auto)")
     p.add_argument("--host-fused", action="store_true", help="SX_OPT_HOST_FUSED (experimental): e2e calls pass kernel_ns=NULL and the SpMM kernel carries C across PCIe")
     p.add_argument("--ref-threads", type=int, default=1, help="--impl reference: threads of the CPU path (1 = as the reference runs it; -1 = all cores, OpenMP port)")
     p.add_argument("--peer-bytes", type=int, default=8 << 20, help="N>1: B images up to this size travel by peer copy instead of NCCL")
@@ -340,7 +341,8 @@ def run_native(args):
             cw = max(1, (32 << 20) // (ld * s))
         e.set_option(sx.OPT_COL_WINDOW_ROWS, cw)
         e.set_option(sx.OPT_HOST_FUSED, 1 if args.host_fused else 0)
-        e.set_option(sx.OPT_PDL, 1 if args.pdl else 0)
+        e.set_option(sx.OPT_PDL, args.pdl)
+        e.set_option(sx.OPT_PREFETCH, args.prefetch)
         e.set_option(sx.OPT_WINDOW_ROWS, args.window_rows)
         e.set_option(sx.OPT_SLIDE, args.slide)
         e.set_option(sx.OPT_AUTOTUNE, 1 if args.autotune else 0)
@@ -529,7 +531,7 @@ def run_native(args):
                       f"{eng.info(sx.INFO_REST_NNZ)} nnz left to CSR")
     else:
         tiles_note = ""
-    kernel_name = ({1: "spmm_rows_kernel (+segments/finalize)", 2: "spmm_staged_kernel", 3: "spmm_window_kernel", 4: "spmm_panels_dmma_kernel", 6: "spmm_window_hostc_kernel", 7: "spmm_slide_kernel"}.get(lk // 10000, "?")
+    kernel_name = ({1: "spmm_rows_kernel (+segments/finalize)", 2: "spmm_staged_kernel", 3: "spmm_window_kernel", 4: "spmm_panels_dmma_kernel", 6: "spmm_window_hostc_kernel", 7: "spmm_slide_kernel", 8: "spmm_edgelist_kernel"}.get(lk // 10000, "?")
                    + f" <G={lk % 10000 // 100}, VPL={lk % 100 // 10}, {'fast' if lk % 10 else 'strict'}>"
                    if lk // 10000 != 5 else f"spmm_staged_kernel<WIN>, {lk % 10000} column-window passes of {cw} columns each") + (
                    (f", {eng.info(sx.INFO_ITEMS)} items of <= {eng.info(sx.INFO_ITEM_NNZ)} nnz, {eng.info(sx.INFO_SPLIT_ROWS)} split rows" if lk // 10000 == 2 else "") + tiles_note)

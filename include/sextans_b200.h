@@ -307,6 +307,23 @@ int sx_partition_rows(int M, const int32_t *rowptr, int parts, int32_t *bounds);
  * Arrays are malloc'ed; release each with sx_free. */
 int sx_plan_slide(int M, const int32_t *rowptr, const int32_t *colidx, int nchains_wanted, int *nsteps,
                   int32_t **steps, int *nchains, int32_t **chains, int *ring_rows, int *max_step_entries);
+/* Plan of the edge-list kernel (variant 5; host only).  Row blocks of up to 32 consecutive
+ * rows, each with the ascending list of the DISTINCT columns its nonzeros touch -- the block's
+ * compacted B window, described as runs of consecutive columns -- and, per nonzero, the 16-bit
+ * index of its column inside that window: the GPU form of the reference's window-local column
+ * field (col14 of the packed edge word, src/sparse_helper.h:419-443, src/sextans.cpp:398-402).
+ *   row_bytes    bytes of one row of the row-major B image (leading dimension x element size)
+ *   smem_budget  shared memory one block may use (window + its slice of values and indices)
+ *   blocks  8 ints per block: {row_begin, nrows, nnz_begin, nnz_end, run_begin, run_end, ncols, smem_bytes}
+ *   runs    2 ints per run: {first column, (first local index << 16) | length}
+ *   lcol    one uint16 per nonzero, parallel to colidx
+ *   total_cols  sum of ncols over the blocks (B rows staged per SpMM)
+ *   max_smem    largest smem_bytes
+ * *nblocks = 0 (and SX_OK) if some single row does not fit the budget.  Arrays are malloc'ed;
+ * release each with sx_free. */
+int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colidx, int row_bytes, int elem_bytes,
+                       int smem_budget, int *nblocks, int32_t **blocks, int *nruns, int32_t **runs,
+                       uint16_t **lcol, int64_t *total_cols, int *max_smem);
 int sx_split_col_windows(int M, int K, const int32_t *rowptr, const int32_t *colidx, int window_rows,
                          int *nwin, int32_t **win_rowptr, int64_t **win_base, int32_t **order,
                          int *ascending);

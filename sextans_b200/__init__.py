@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 __all__ = ["Engine", "SextansError", "lib", "library_path", "load_mtx", "partition_rows",
-           "split_col_windows", "plan_slide",
+           "split_col_windows", "plan_slide", "plan_edge_lists",
            "pinned_empty", "STRICT", "FAST", "images_decode_A", "images_decode_B",
            "images_decode_C", "images_encode_C"]
 
@@ -111,6 +111,8 @@ def lib():
                                   C.POINTER(C.POINTER(i64)), C.POINTER(_PI32), C.POINTER(i)], i),
         "sx_plan_slide": ([i, _PI32, _PI32, i, C.POINTER(i), C.POINTER(_PI32), C.POINTER(i), C.POINTER(_PI32),
                            C.POINTER(i), C.POINTER(i)], i),
+        "sx_plan_edge_lists": ([i, i, _PI32, _PI32, i, i, i, C.POINTER(i), C.POINTER(_PI32), C.POINTER(i),
+                                C.POINTER(_PI32), C.POINTER(C.POINTER(C.c_uint16)), C.POINTER(i64), C.POINTER(i)], i),
         "sx_free": ([vp], None),
         "sx_sextans_invoke": ([vp, _PI32, _A8, _F4, _F8, _F8, i, i, i, i, i, i, i, _PD], i),
         "sx_sextans_last_kernel_ns": ([], C.c_double),
@@ -199,6 +201,30 @@ def plan_slide(M, rowptr, colidx, nchains):
     finally:
         L.sx_free(st), L.sx_free(ch)
     return steps, chains, ring.value, ent.value
+
+
+def plan_edge_lists(M, K, rowptr, colidx, row_bytes, elem_bytes, smem_budget):
+    """Plan of the edge-list kernel (sx_plan_edge_lists) ->
+    (blocks [nblocks, 8], runs [nruns, 2], lcol [nnz] uint16, total_cols, max_smem); nblocks == 0 if some row
+    does not fit ``smem_budget``."""
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+    colidx = np.ascontiguousarray(colidx, dtype=np.int32)
+    nb, nr, ms, tot = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+    bl, ru, lc = _PI32(), _PI32(), C.POINTER(C.c_uint16)()
+    L = lib()
+    _check(L.sx_plan_edge_lists(M, K, rowptr.ctypes.data_as(_PI32), colidx.ctypes.data_as(_PI32), row_bytes, elem_bytes,
+                                smem_budget, C.byref(nb), C.byref(bl), C.byref(nr), C.byref(ru), C.byref(lc),
+                                C.byref(tot), C.byref(ms)))
+    if nb.value == 0:
+        return np.zeros((0, 8), np.int32), np.zeros((0, 2), np.int32), np.zeros(0, np.uint16), 0, 0
+    try:
+        n = int(rowptr[M])
+        blocks = np.ctypeslib.as_array(bl, shape=(nb.value * 8,)).reshape(-1, 8).copy()
+        runs = np.ctypeslib.as_array(ru, shape=(max(nr.value, 1) * 2,))[:nr.value * 2].reshape(-1, 2).copy()
+        lcol = np.ctypeslib.as_array(lc, shape=(max(n, 1),))[:n].copy()
+    finally:
+        L.sx_free(bl), L.sx_free(ru), L.sx_free(lc)
+    return blocks, runs, lcol, tot.value, ms.value
 
 
 def split_col_windows(M, K, rowptr, colidx, window_rows):

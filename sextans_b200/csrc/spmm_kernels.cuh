@@ -202,6 +202,31 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
 
+// L2 prefetch of a contiguous piece of global memory (a hint: nothing is consumed, and L2 is
+// the point of coherence, so it may be issued before the data's producer has finished)
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// programmatic dependent launch (no-ops when the grid was launched without the attribute)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// step flags in peer-visible memory
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// generic-proxy writes (also a peer's, once acquired) before later async-proxy (TMA) reads
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 // ---- main kernel, staged: A streams through shared memory by TMA -------------------
 // A work item is a run of consecutive whole rows, or a piece of one long row, holding
 // about the same number of nonzeros as every other item (built at upload, sx_api.cu:
@@ -619,6 +644,189 @@ spmm_window_kernel(const int M, const int4 *__restrict__ blocks, const int *__re
         }
         for (; j < end; ++j) vmac<STRICT>(acc, sval[j - jal], w[(uint32_t)(scol[j - jal] - cmin) * ldbv]);
         reinterpret_cast<V *>(Cout)[(size_t)row * ldcv + lg] = vaxpby<STRICT>(alpha, acc, beta, cin);
+    }
+}
+
+// ---- variant 5: edge lists -- a row block's DISTINCT B rows staged by TMA, 16-bit local columns ----
+// The reference cuts A into column windows, keeps the window of B on chip and stores every
+// nonzero as a packed word whose column is LOCAL to the window (col14 | row18 | val32,
+// src/sparse_helper.h:419-443; decoded in src/sextans.cpp:398-402), so that a PE indexes its
+// on-chip B directly.  Here the "window" of a row block (up to 32 consecutive rows, one thread
+// block) is the ascending list of the distinct columns its nonzeros touch: exactly those rows
+// of B are staged into shared memory -- as a handful of TMA bulk copies, because on FEM-type
+// matrices the distinct columns come in runs of consecutive columns (nasa4704: 142 columns in
+// 7 runs per block against a span of 456; pcrystk02: 317 in 8 against 918) -- and every nonzero
+// carries a 16-bit index into that compacted window (sx_host.cpp: sx_plan_edge_lists).  Against
+// variant 3 (the whole contiguous span staged) that is a third of the bytes through L2 and a
+// third of the shared memory, so 4-6 blocks share an SM instead of 1-2, and the index stream
+// of A shrinks from 4 to 2 bytes per nonzero.
+//   block record (two int4): {row_begin, nrows, nnz_begin, nnz_end} {run_begin, run_end, ncols, -}
+//   run record (int2):       {first column, (first local index << 16) | length}
+//   shared memory:           window ncols x row bytes | values | local columns   (A slice from the
+//                            8-entry boundary at or below nnz_begin: whole 16-byte units)
+// One lane group per row, stored order, so strict mode is bit-identical to cpu_spmm_CSR.
+//
+// Launch chains: the kernel is written for programmatic dependent launch.  Everything that only
+// touches A (block and run records, row pointers, the TMA of the value / local-column slice)
+// and the L2 PREFETCH of the block's B rows and C_in rows (a hint, consumes nothing) happens
+// before griddepcontrol.wait; B and C_in themselves are read after it.  launch_dependents is the
+// first instruction: with 4-6 blocks per SM the next kernel of the stream becomes resident
+// beside this one and has its A side staged and its B rows on the way to L2 by the time this
+// kernel completes.  Launched without the attribute the two instructions do nothing.
+//
+// Multi-GPU (ready != nullptr): B is pushed into this GPU's image by the rank that holds it
+// (push_image_kernel); lane 0 of warp 0 waits until the local step flag reaches `step` before
+// the window copies are issued, and the last block to finish stores `step` into the pusher's
+// done flag -- the exchange costs this rank no launch of its own.
+constexpr int SX_EDGE_PREFETCH = 1;
+template <typename T, int G, bool STRICT>
+__global__ void __launch_bounds__(32 * G, 2)
+spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int2 *__restrict__ runs, const int *__restrict__ rowptr,
+                     const uint16_t *__restrict__ lcol, const T *__restrict__ val, const T *__restrict__ B,
+                     const uint32_t ldbv, const T *Cin, T *Cout, const uint32_t ldcv, const T alpha, const T beta,
+                     const int nvec, const int flags, const uint32_t *ready, const uint32_t step,
+                     unsigned int *done_counter, uint32_t *done_remote) {
+    using V = typename VecOf<T>::type;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar[2];  // [0]: the A slice, [1]: the B rows
+    pdl_launch_dependents();
+    const int lg = threadIdx.x & (G - 1);
+    const int rl = threadIdx.x / G;
+    const int4 b0 = __ldg(blocks + 2 * blockIdx.x), b1 = __ldg(blocks + 2 * blockIdx.x + 1);
+    const int jb = b0.z, je = b0.w;
+    const uint32_t rowbytes = ldbv * 16u;
+    const uint32_t wbytes = (uint32_t)b1.z * rowbytes;
+    const int jal = jb & ~7;
+    const bool has = je > jb;
+    const uint32_t na = has ? (uint32_t)((je - jal + 7) & ~7) : 0u;
+    const V *win = reinterpret_cast<const V *>(smem_raw);
+    const T *sval = reinterpret_cast<const T *>(smem_raw + wbytes);
+    const uint16_t *scol = reinterpret_cast<const uint16_t *>(smem_raw + wbytes + (size_t)na * sizeof(T));
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // ---- A side and hints: before the previous kernel of the stream is known to be complete ----
+    int2 run = make_int2(0, 0);  // warp 0: lane i holds run record run_begin + i
+    if (threadIdx.x < 32) {
+        if (threadIdx.x == 0 && has) {
+            const uint64_t pol_a = policy_evict_first();
+            mbar_expect_tx(&bar[0], na * (uint32_t)(sizeof(T) + 2));
+            tma_bulk_g2s(const_cast<T *>(sval), val + jal, na * (uint32_t)sizeof(T), &bar[0], pol_a);
+            tma_bulk_g2s(const_cast<uint16_t *>(scol), lcol + jal, na * 2u, &bar[0], pol_a);
+        }
+        if (b1.x + (int)threadIdx.x < b1.y) run = __ldg(runs + b1.x + threadIdx.x);
+        if (flags & SX_EDGE_PREFETCH) {
+            const unsigned char *Bb = reinterpret_cast<const unsigned char *>(B);
+            if ((run.y & 0xffff) != 0) bulk_prefetch_l2(Bb + (size_t)(uint32_t)run.x * rowbytes, (uint32_t)(run.y & 0xffff) * rowbytes);
+            for (int i = b1.x + 32 + (int)threadIdx.x; i < b1.y; i += 32) {
+                const int2 r = __ldg(runs + i);
+                bulk_prefetch_l2(Bb + (size_t)(uint32_t)r.x * rowbytes, (uint32_t)(r.y & 0xffff) * rowbytes);
+            }
+            if (threadIdx.x == 31 && b0.y > 0)
+                bulk_prefetch_l2(reinterpret_cast<const unsigned char *>(Cin) + (size_t)b0.x * ldcv * 16u, (uint32_t)b0.y * ldcv * 16u);
+        }
+    }
+    const int row = b0.x + rl;
+    const bool mine = rl < b0.y && lg < nvec;
+    int begin = 0, end = 0;
+    if (mine) { begin = __ldg(rowptr + row); end = __ldg(rowptr + row + 1); }
+    // ---- B and C_in: only after the previous kernel is complete ----
+    pdl_wait();
+    if (threadIdx.x < 32) {
+        if (ready != nullptr) {  // multi-GPU: the pushed B image of this step has landed
+            if (threadIdx.x == 0) {
+                const long long t0 = clock64();
+                while ((int)(ld_acquire_sys(ready) - step) < 0) {
+                    __nanosleep(32);
+                    if (clock64() - t0 > 4000000000ll) break;  // ~2 s: never hang the GPU on a lost peer
+                }
+                fence_proxy_async();
+            }
+            __syncwarp();
+        }
+        if (has) {
+            const uint64_t pol_b = policy_evict_last();
+            const unsigned char *Bb = reinterpret_cast<const unsigned char *>(B);
+            if (threadIdx.x == 0) mbar_expect_tx(&bar[1], wbytes);
+            __syncwarp();
+            if ((run.y & 0xffff) != 0)
+                tma_bulk_g2s(smem_raw + (size_t)((uint32_t)run.y >> 16) * rowbytes, Bb + (size_t)(uint32_t)run.x * rowbytes,
+                             (uint32_t)(run.y & 0xffff) * rowbytes, &bar[1], pol_b);
+            for (int i = b1.x + 32 + (int)threadIdx.x; i < b1.y; i += 32) {
+                const int2 r = __ldg(runs + i);
+                tma_bulk_g2s(smem_raw + (size_t)((uint32_t)r.y >> 16) * rowbytes, Bb + (size_t)(uint32_t)r.x * rowbytes,
+                             (uint32_t)(r.y & 0xffff) * rowbytes, &bar[1], pol_b);
+            }
+        }
+    }
+    V acc, cin;
+    vzero(acc);
+    vzero(cin);
+    if (mine) cin = reinterpret_cast<const V *>(Cin)[(size_t)row * ldcv + lg];
+    if (mine) {
+        if (end > begin) {
+            mbar_wait(&bar[0], 0);
+            mbar_wait(&bar[1], 0);
+        }
+        const T *sv = sval - jal;  // sv[j] = value of nonzero j
+        const uint16_t *sc = scol - jal;
+        const V *w = win + lg;     // w[local column * ldbv] = this lane's piece of that B row
+        // chunks of 8 nonzeros, software-pipelined: the (column, value) pairs of chunk k+1 and the
+        // eight B-row pieces of chunk k are in flight while the ordered chain of additions of chunk k runs
+        constexpr int UC = 8;
+        int j = begin;
+        if (j + UC <= end) {
+            uint32_t c[UC];
+            T a[UC];
+#pragma unroll
+            for (int u = 0; u < UC; ++u) { c[u] = sc[j + u]; a[u] = sv[j + u]; }
+            for (;;) {
+                V b[UC];
+#pragma unroll
+                for (int u = 0; u < UC; ++u) b[u] = w[c[u] * ldbv];
+                const int jn = j + UC;
+                const bool more = jn + UC <= end;
+                uint32_t c2[UC];
+                T a2[UC];
+                const int jl = more ? jn : j;  // unconditional loads (this chunk again when there is no next one)
+#pragma unroll
+                for (int u = 0; u < UC; ++u) { c2[u] = sc[jl + u]; a2[u] = sv[jl + u]; }
+#pragma unroll
+                for (int u = 0; u < UC; ++u) vmac<STRICT>(acc, a[u], b[u]);
+                j = jn;
+                if (!more) break;
+#pragma unroll
+                for (int u = 0; u < UC; ++u) { c[u] = c2[u]; a[u] = a2[u]; }
+            }
+        }
+        if (j < end) {
+            // the last, partial chunk: its loads all in flight at once (indices clamped to the row),
+            // the additions predicated -- an explicit +0 would turn a -0 sum into +0
+            uint32_t c[UC];
+            T a[UC];
+            V b[UC];
+#pragma unroll
+            for (int u = 0; u < UC; ++u) { const int ju = min(j + u, end - 1); c[u] = sc[ju]; a[u] = sv[ju]; }
+#pragma unroll
+            for (int u = 0; u < UC; ++u) b[u] = w[c[u] * ldbv];
+#pragma unroll
+            for (int u = 0; u < UC; ++u)
+                if (j + u < end) vmac<STRICT>(acc, a[u], b[u]);
+        }
+        reinterpret_cast<V *>(Cout)[(size_t)row * ldcv + lg] = vaxpby<STRICT>(alpha, acc, beta, cin);
+    }
+    if (done_remote != nullptr) {  // multi-GPU: tell the pusher that this rank is done with the image
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(done_counter, 1u) == gridDim.x - 1) {
+                *done_counter = 0;
+                st_release_sys(done_remote, step);
+            }
+        }
     }
 }
 

@@ -80,6 +80,16 @@ struct Plan {
     void release() { items.release(); split_row.release(); split_ptr.release(); }
 };
 
+// Edge lists of spmm_edgelist_kernel (variant 5) for one B-row size: built on first use.
+struct EdgePlan {
+    int row_bytes = 0;
+    bool usable = false;  // planned, and staging a block's distinct B rows beats gathering per nonzero
+    int nblocks = 0, nruns = 0, max_smem = 0;
+    int64_t total_cols = 0;
+    DevBuf blocks, runs, lcol;
+    void release() { blocks.release(); runs.release(); lcol.release(); }
+};
+
 struct sx_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
@@ -101,6 +111,16 @@ struct sx_ctx {
     // depends on the lane-group width, i.e. on N)
     std::vector<Plan *> plans;
     Plan *last_plan = nullptr;
+    // variant 5: upload-time estimate (sampled 32-row groups) of distinct columns per nonzero
+    // and of the largest group, and the plans built from it, one per B-row size
+    double edge_cols_per_nnz = 1.0;
+    int edge_max_cols = 0, edge_max_nnz = 0;
+    std::vector<EdgePlan *> edge_plans;
+    const EdgePlan *last_edge_plan = nullptr;
+    // multi-GPU exchange fused into the next SpMM launch (sx_spmm_expect_step; one-shot)
+    const uint32_t *x_ready = nullptr;
+    uint32_t *x_done = nullptr;
+    uint32_t x_step = 0;
     std::vector<int32_t> h_rowptr;  // kept to re-derive segments when the option changes
     // variant 3: per block of 32 rows {first column, column span, nnz begin, nnz end}
     DevBuf wblocks;
@@ -152,7 +172,7 @@ struct sx_ctx {
     int item_nnz = 0;  // 0 = auto
     int prefetch = -1;  // SX_OPT_PREFETCH: -1 auto, 0 off, 1 on
     int host_fused = 0;  // SX_OPT_HOST_FUSED (experimental)
-    int pdl = 0;         // SX_OPT_PDL (experimental)
+    int pdl = -1;        // SX_OPT_PDL: -1 auto (variant 5 always, variant 3 never), 0 off, 1 on
     int64_t zerocopy_bytes = 3 << 19;  // 1.5 MiB: above that the copy engines win
     int last_path = 0;  // 1: the last host-facing call took the zero-copy path
     bool segments_dirty = false;
@@ -178,7 +198,11 @@ int bind(sx_ctx *c) {
 }
 
 int refresh_segments(sx_ctx *c);
+void release_child(sx_ctx *r, cudaStream_t stream);
 int get_plan(sx_ctx *c, int budget, Plan **out);
+int get_edge_plan(sx_ctx *c, int row_bytes, int elem_bytes, const EdgePlan **out);
+int stream_wait_flag(sx_ctx *c, const void *flag, uint32_t value);
+int stream_write_flag(sx_ctx *c, void *flag, uint32_t value);
 int pick_budget(const sx_ctx *c, int G);
 template <typename T, int G> int pick_tile(int U);
 
@@ -225,6 +249,63 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
     // (fem band=100 fp64, 143 KB windows: 1.11 ms against 1.04 ms; fp32, 78 KB: 0.58 against 0.84)
     const int window_cap = wsmem ? (int)std::max<size_t>(1, (220 * 1024) / wsmem) : 1;
     const bool window_auto = window_ok && (window_cap >= 2 || (int64_t)c->nwblocks <= (int64_t)4 * c->sm_count * window_cap);
+    // variant 5 (edge lists: a block's distinct B rows staged by TMA, 16-bit local columns) is
+    // taken whenever the matrix has the reuse that pays for staging -- it supersedes variant 3 on
+    // the banded matrices that one was written for (a third of the window bytes, 4-6 blocks per SM)
+    if constexpr (G <= 16 && VPL == 1) {
+        if ((c->kernel == 0 || c->kernel == 5) && !c->win_mode && c->M > 0) {
+            const EdgePlan *ep = nullptr;
+            if ((rc = get_edge_plan(c, (int)(ldb * sizeof(T)), (int)sizeof(T), &ep))) return rc;
+            if (ep && ep->usable && ldb == ldc) {
+                constexpr int E = sx::VecOf<T>::E;
+                auto kern = sx::spmm_edgelist_kernel<T, G, STRICT>;
+                if (ep->max_smem > 48 * 1024 &&
+                    std::find(c->big_smem_ok.begin(), c->big_smem_ok.end(), (const void *)kern) == c->big_smem_ok.end()) {
+                    SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64));
+                    c->big_smem_ok.push_back((const void *)kern);
+                }
+                const bool pf = c->prefetch != 0;
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)ep->nblocks);
+                cfg.blockDim = dim3(32 * G);
+                cfg.dynamicSmemBytes = (size_t)std::max(ep->max_smem, 16);
+                cfg.stream = c->stream;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at;
+                cfg.numAttrs = c->pdl != 0 ? 1 : 0;
+                unsigned int *counter = nullptr;
+                if (c->x_done) {
+                    if ((rc = c->sync_words.ensure(16))) return rc;
+                    if (!c->sync_words_zeroed) {
+                        SX_CUDA(cudaMemsetAsync(c->sync_words.p, 0, 16, c->stream));
+                        c->sync_words_zeroed = true;
+                    }
+                    counter = (unsigned int *)c->sync_words.p + 2;
+                }
+                SX_CUDA(cudaLaunchKernelEx(&cfg, kern, (const int4 *)ep->blocks.p, (const int2 *)ep->runs.p,
+                                           (const int *)c->rowptr.p, (const uint16_t *)ep->lcol.p, (const T *)c->val.p, dB,
+                                           (uint32_t)(ldb / E), dCin, dCout, (uint32_t)(ldc / E), alpha, beta, nvec,
+                                           pf ? sx::SX_EDGE_PREFETCH : 0, c->x_ready, c->x_step, counter, c->x_done));
+                c->x_ready = nullptr;
+                c->x_done = nullptr;
+                c->launches++;
+                c->last_edge_plan = ep;
+                c->last_kernel = 80000 + G * 100 + VPL * 10 + (STRICT ? 0 : 1);
+                SX_CUDA(cudaGetLastError());
+                return SX_OK;
+            }
+        }
+    }
+    // the other kernels do not carry the multi-GPU step flags: stream memory operations around them
+    struct FlagGuard {
+        sx_ctx *c; const uint32_t *ready; uint32_t *done; uint32_t step;
+        ~FlagGuard() { if (done) stream_write_flag(c, done, step); }
+    } guard{c, c->x_ready, c->x_done, c->x_step};
+    c->x_ready = nullptr;
+    c->x_done = nullptr;
+    if (guard.ready && (rc = stream_wait_flag(c, guard.ready, guard.step))) return rc;
     int variant = (c->kernel != 0 && c->kernel != 4) ? c->kernel : (window_auto ? 3 : (sub_wave ? 1 : 2));
     if (variant == 3 && !window_ok) variant = sub_wave ? 1 : 2;
     if (c->win_mode) variant = 2;  // a column-window pass: only the staged kernel carries running sums
@@ -256,7 +337,7 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
     }
     // SX_OPT_WINDOW_ROWS (experimental): blocks of 64 / 128 rows where RB * G <= 1024 threads
     if constexpr (G >= 4 && G <= 16 && VPL == 1) {
-        if (variant == 3 && c->window_rows > 32 && !c->pdl) {
+        if (variant == 3 && c->window_rows > 32 && c->pdl <= 0) {
             constexpr int E = sx::VecOf<T>::E;
             const int w = (c->window_rows >= 128 && G <= 8) ? 1 : 0;
             const sx_ctx::WideBlocks &W = c->wide[w];
@@ -286,13 +367,13 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
     if constexpr (G <= 16 && VPL == 1) {
         if (variant == 3) {
             constexpr int E = sx::VecOf<T>::E;
-            auto kern = c->pdl ? sx::spmm_window_kernel<T, G, STRICT, true> : sx::spmm_window_kernel<T, G, STRICT, false>;
+            auto kern = c->pdl > 0 ? sx::spmm_window_kernel<T, G, STRICT, true> : sx::spmm_window_kernel<T, G, STRICT, false>;
             if (wsmem > 48 * 1024 &&
                 std::find(c->big_smem_ok.begin(), c->big_smem_ok.end(), (const void *)kern) == c->big_smem_ok.end()) {
                 SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                 c->big_smem_ok.push_back((const void *)kern);
             }
-            if (c->pdl) {
+            if (c->pdl > 0) {
                 // programmatic dependent launch: this grid's A-side prologue may overlap the
                 // previous kernel of the stream (see the kernel)
                 cudaLaunchConfig_t cfg = {};
@@ -699,6 +780,95 @@ int pick_tile(int U) {
     return std::max(ts, 2 * U);
 }
 
+// Upload-time look at the matrix for variant 5: distinct columns per nonzero of 32-row groups
+// (up to 256 groups, evenly spaced), and the largest sampled group.  Cheap; decides whether a
+// plan is worth building at all (unstructured matrices: ~1 distinct column per nonzero).
+void edge_screen(sx_ctx *c, int M, int K, const int32_t *rowptr, const int32_t *colidx) {
+    c->edge_cols_per_nnz = 1.0;
+    c->edge_max_cols = c->edge_max_nnz = 0;
+    const int ngroups = (M + 31) / 32;
+    if (ngroups == 0 || rowptr[M] == 0) return;
+    const int nsample = std::min(ngroups, 256);
+    std::vector<int32_t> cols;
+    int64_t distinct = 0, entries = 0;
+    for (int i = 0; i < nsample; ++i) {
+        const int g = (int)((int64_t)ngroups * i / nsample);
+        const int r0 = g * 32, r1 = std::min(M, r0 + 32);
+        cols.assign(colidx + rowptr[r0], colidx + rowptr[r1]);
+        std::sort(cols.begin(), cols.end());
+        const int d = (int)(std::unique(cols.begin(), cols.end()) - cols.begin());
+        distinct += d;
+        entries += rowptr[r1] - rowptr[r0];
+        c->edge_max_cols = std::max(c->edge_max_cols, d);
+        c->edge_max_nnz = std::max(c->edge_max_nnz, rowptr[r1] - rowptr[r0]);
+    }
+    (void)K;
+    if (entries > 0) c->edge_cols_per_nnz = (double)distinct / (double)entries;
+}
+
+void drop_edge_plans(sx_ctx *c) {
+    for (EdgePlan *p : c->edge_plans) { p->release(); delete p; }
+    c->edge_plans.clear();
+    c->last_edge_plan = nullptr;
+}
+
+// Shared memory a block may use so that k blocks share an SM (228 KB per SM, 1 KB reserved per
+// block, the kernel's static 16 bytes).
+int edge_budget(int k) { return (233472 / k - 1024 - 64) & ~127; }
+
+int get_edge_plan(sx_ctx *c, int row_bytes, int elem_bytes, const EdgePlan **out) {
+    *out = nullptr;
+    for (EdgePlan *p : c->edge_plans)
+        if (p->row_bytes == row_bytes) { *out = p; return SX_OK; }
+    EdgePlan *p = new (std::nothrow) EdgePlan();
+    if (!p) return fail(SX_ERR_NOMEM, "out of host memory");
+    p->row_bytes = row_bytes;
+    c->edge_plans.push_back(p);
+    *out = p;
+    // staging pays when a staged B row serves at least two nonzeros (forced with SX_OPT_KERNEL = 5:
+    // any matrix that can be planned)
+    if (c->nnz == 0 || (c->kernel != 5 && c->edge_cols_per_nnz > 0.5)) return SX_OK;
+    // blocks per SM: as many as the largest sampled group allows (with 10 % headroom), at most 6
+    const int64_t need = ((int64_t)c->edge_max_cols * row_bytes + ((int64_t)c->edge_max_nnz + 16) * (elem_bytes + 2)) * 11 / 10;
+    int k = 6;
+    while (k > 1 && edge_budget(k) < need) --k;
+    if (k == 5) k = 4;
+    std::vector<int32_t> ci((size_t)c->nnz);
+    SX_CUDA(cudaMemcpyAsync(ci.data(), c->colidx.p, (size_t)c->nnz * 4, cudaMemcpyDeviceToHost, c->stream));
+    SX_CUDA(cudaStreamSynchronize(c->stream));
+    int nb = 0, nr = 0, max_smem = 0;
+    int32_t *blocks = nullptr, *runs = nullptr;
+    uint16_t *lcol = nullptr;
+    int64_t total = 0;
+    int rc = sx_plan_edge_lists(c->M, c->K, c->h_rowptr.data(), ci.data(), row_bytes, elem_bytes, edge_budget(k), &nb,
+                                &blocks, &nr, &runs, &lcol, &total, &max_smem);
+    if (!rc && nb == 0 && k > 1)  // some row is larger than the sample suggested: one block per SM
+        rc = sx_plan_edge_lists(c->M, c->K, c->h_rowptr.data(), ci.data(), row_bytes, elem_bytes, edge_budget(1), &nb,
+                                &blocks, &nr, &runs, &lcol, &total, &max_smem);
+    if (rc) return rc;
+    if (nb > 0 && (c->kernel == 5 || total * 2 <= c->nnz)) {
+        if (!(rc = p->blocks.ensure((size_t)nb * 32)) && !(rc = p->runs.ensure(std::max<size_t>((size_t)nr * 8, 16))) &&
+            !(rc = p->lcol.ensure((size_t)c->nnz * 2 + 64))) {
+            if (cudaMemcpyAsync(p->blocks.p, blocks, (size_t)nb * 32, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+                (nr > 0 && cudaMemcpyAsync(p->runs.p, runs, (size_t)nr * 8, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) ||
+                cudaMemcpyAsync(p->lcol.p, lcol, (size_t)c->nnz * 2, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+                cudaStreamSynchronize(c->stream) != cudaSuccess)
+                rc = fail(SX_ERR_CUDA, "edge-list plan upload failed");
+        }
+        if (!rc) {
+            p->nblocks = nb;
+            p->nruns = nr;
+            p->max_smem = max_smem;
+            p->total_cols = total;
+            p->usable = true;
+        }
+    }
+    sx_free(blocks);
+    sx_free(runs);
+    sx_free(lcol);
+    return rc;
+}
+
 int refresh_segments(sx_ctx *c) {
     c->segments_dirty = false;
     c->nsplit = c->nseg = 0;
@@ -817,6 +987,7 @@ int build_wide_window_blocks(sx_ctx *c, int M, const int32_t *rowptr, const int3
 void release_child(sx_ctx *r, cudaStream_t stream) {
     r->stream = stream;
     drop_plans(r);
+    drop_edge_plans(r);
     for (DevBuf *b : {&r->rowptr, &r->colidx, &r->val, &r->split_row, &r->split_seg_ptr, &r->seg_begin,
                       &r->seg_end, &r->partial, &r->wblocks})
         b->release();
@@ -834,12 +1005,7 @@ void drop_tiles(sx_ctx *c) {
     if (c->rest) {
         sx_ctx *r = c->rest;
         c->rest = nullptr;
-        r->stream = c->stream;
-        drop_plans(r);
-        for (DevBuf *b : {&r->rowptr, &r->colidx, &r->val, &r->split_row, &r->split_seg_ptr, &r->seg_begin,
-                          &r->seg_end, &r->partial})
-            b->release();
-        delete r;
+        release_child(r, c->stream);
     }
 }
 
@@ -928,7 +1094,7 @@ int build_panels(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rowptr, co
     r->split_nnz = c->split_nnz;
     rc = upload_csr<double>(r, M, K, (int64_t)rci.size(), rrp.data(), rci.empty() ? rrp.data() : rci.data(),
                             rv.empty() ? val : rv.data());
-    if (rc) { delete r; return rc; }
+    if (rc) { release_child(r, c->stream); return rc; }
     c->rest = r;
     c->npanels = P;
     c->tile_steps = steps;
@@ -1004,7 +1170,7 @@ int upload_csr(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rowptr, cons
     c->tuned.clear();
     if ((rc = c->rowptr.ensure(((size_t)M + 1) * 4))) return rc;
     if ((rc = c->colidx.ensure((size_t)nnz * 4 + 16))) return rc;  // +16: TMA reads whole 16-byte units
-    if ((rc = c->val.ensure((size_t)nnz * sizeof(T) + 32))) return rc;
+    if ((rc = c->val.ensure((size_t)nnz * sizeof(T) + 64))) return rc;  // the edge-list A slice ends on an 8-entry boundary
     SX_CUDA(cudaMemcpyAsync(c->rowptr.p, rowptr, ((size_t)M + 1) * 4, cudaMemcpyHostToDevice, c->stream));
     if (nnz > 0) {
         SX_CUDA(cudaMemcpyAsync(c->colidx.p, colidx, (size_t)nnz * 4, cudaMemcpyHostToDevice, c->stream));
@@ -1019,6 +1185,8 @@ int upload_csr(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rowptr, cons
     c->has_B = c->has_C = false;
     c->N = 0; c->ld = 0;
     if ((rc = refresh_segments(c))) return rc;
+    drop_edge_plans(c);
+    edge_screen(c, M, K, rowptr, colidx);
     if ((rc = build_window_blocks(c, M, rowptr, colidx))) return rc;
     if (c->window_rows > 32 && (rc = build_wide_window_blocks(c, M, rowptr, colidx))) return rc;
     if (c->window_rows <= 32) c->wide[0].n = c->wide[1].n = 0;
@@ -1395,6 +1563,7 @@ int sx_destroy(sx_ctx *c) {
                       &c->seg_end, &c->partial, &c->sync_words, &c->wblocks, &c->B, &c->Cin, &c->Cout, &c->stage})
         b->release();
     drop_plans(c);
+    drop_edge_plans(c);
     drop_tiles(c);
     drop_windows(c);
     for (DevBuf *b : {&c->step_ptr, &c->tcols, &c->tvals, &c->psum, &c->wide[0].blocks, &c->wide[1].blocks,
@@ -1431,7 +1600,7 @@ int sx_set_option(sx_ctx *c, int option, int64_t value) {
             for (sx_ctx *k : c->wins) { k->split_nnz = (int)value; k->segments_dirty = true; }
             return SX_OK;
         case SX_OPT_KERNEL:
-            if (value < 0 || value > 4) return fail(SX_ERR_INVALID, "SX_OPT_KERNEL is 0 (auto), 1 (row per lane group), 2 (TMA-staged work items), 3 (TMA-staged B window) or 4 (sliding B window, experimental: needs SX_OPT_SLIDE at upload)");
+            if (value < 0 || value > 5) return fail(SX_ERR_INVALID, "SX_OPT_KERNEL is 0 (auto), 1 (row per lane group), 2 (TMA-staged work items), 3 (TMA-staged B window), 4 (sliding B window: needs SX_OPT_SLIDE at upload) or 5 (edge lists: distinct B rows of a row block staged by TMA)");
             c->kernel = (int)value;
             return SX_OK;
         case SX_OPT_TILE_MIN_ROWS:
@@ -1463,7 +1632,7 @@ int sx_set_option(sx_ctx *c, int option, int64_t value) {
             c->window_rows = (int)value;  // block records are built at the next sx_upload_csr_*
             return SX_OK;
         case SX_OPT_PDL:
-            if (value != 0 && value != 1) return fail(SX_ERR_INVALID, "SX_OPT_PDL is 0 or 1");
+            if (value < -1 || value > 1) return fail(SX_ERR_INVALID, "SX_OPT_PDL is -1 (auto), 0 or 1");
             c->pdl = (int)value;
             return SX_OK;
         case SX_OPT_HOST_FUSED:
@@ -1643,6 +1812,14 @@ int stream_value32(const char *name, sx_ctx *c, void *flag, uint32_t value, unsi
     const CUresult r = ((StreamValue32Fn)fn)((CUstream)c->stream, (CUdeviceptr)(uintptr_t)flag, value, flags);
     if (r != CUDA_SUCCESS) return fail(SX_ERR_CUDA, "%s failed with CUresult %d", name, (int)r);
     return SX_OK;
+}
+extern "C++" {
+int stream_wait_flag(sx_ctx *c, const void *flag, uint32_t value) {
+    return stream_value32("cuStreamWaitValue32", c, const_cast<void *>(flag), value, CU_STREAM_WAIT_VALUE_GEQ);
+}
+int stream_write_flag(sx_ctx *c, void *flag, uint32_t value) {
+    return stream_value32("cuStreamWriteValue32", c, flag, value, CU_STREAM_WRITE_VALUE_DEFAULT);
+}
 }
 }  // namespace
 

@@ -41,6 +41,7 @@ struct alignas(16) int4 { int x, y, z, w; };
 struct alignas(8) int2 { int x, y; };
 inline float4 make_float4(float a, float b, float c, float d) { return {a, b, c, d}; }
 inline double2 make_double2(double a, double b) { return {a, b}; }
+inline int2 make_int2(int a, int b) { return {a, b}; }
 
 using std::max;
 using std::min;

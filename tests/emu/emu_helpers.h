@@ -45,3 +45,19 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
     *bar = (*bar & ~0xFFFFFFFFull) | (uint32_t)((uint32_t)*bar - bytes);
     sx_emu_mbar_settle(bar);
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+    if (bytes % 16 || reinterpret_cast<uintptr_t>(src) % 16) {
+        std::fprintf(stderr, "emu: L2 bulk prefetch not 16-byte aligned/sized (%u bytes)\n", bytes);
+        std::abort();
+    }
+    // touch the first and last byte so that an address-sanitizer build sees a prefetch of memory the product does not own
+    volatile unsigned char sink = static_cast<const unsigned char *>(src)[0];
+    if (bytes) sink = static_cast<const unsigned char *>(src)[bytes - 1];
+    (void)sink;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() { return 0; }
+__device__ __forceinline__ void pdl_wait() {}
+__device__ __forceinline__ void pdl_launch_dependents() {}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) { return std::atomic_ref<const uint32_t>(*p).load(); }
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) { std::atomic_ref<uint32_t>(*p).store(v); }
+__device__ __forceinline__ void fence_proxy_async() {}

@@ -22,6 +22,9 @@
 extern "C" {  // host-side planner of the product (libsextans_b200.so; no GPU needed)
 int sx_plan_slide(int M, const int32_t *rowptr, const int32_t *colidx, int nchains_wanted, int *nsteps, int32_t **steps,
                   int *nchains, int32_t **chains, int *ring_rows, int *max_step_entries);
+int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colidx, int row_bytes, int elem_bytes,
+                       int smem_budget, int *nblocks, int32_t **blocks, int *nruns, int32_t **runs, uint16_t **lcol,
+                       int64_t *total_cols, int *max_smem);
 void sx_free(void *);
 }
 
@@ -570,6 +573,107 @@ void staged_by_shape(const char *tname, int M, int K, int N, int avg, int long_r
 
 }  // namespace
 
+// ---- variant 5: the edge-list kernel, planned by the product's own sx_plan_edge_lists ----
+// Matrices: banded (the case it is for), with unsorted / duplicate columns inside rows, with
+// runs of empty rows, and with shared-memory budgets so small that 32-row groups are cut.
+template <typename T, int G>
+void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, unsigned seed, bool with_flags) {
+    constexpr int E = 16 / (int)sizeof(T);
+    const int M = a.M, K = a.K;
+    std::mt19937 rng(seed * 13 + 5);
+    if (shuffle_rows)  // stored order inside a row is arbitrary, and a column may repeat
+        for (int r = 0; r < M; ++r) {
+            std::shuffle(a.ci.begin() + a.rp[r], a.ci.begin() + a.rp[r + 1], rng);
+            if (a.rp[r + 1] - a.rp[r] >= 2 && r % 3 == 0) a.ci[a.rp[r] + 1] = a.ci[a.rp[r]];
+        }
+    const int nnz = a.rp[M];
+    std::uniform_real_distribution<double> U(-1.0, 1.0);
+    const int64_t ld = (N + 7) / 8 * 8;
+    Aligned<T> val((size_t)nnz, 64), B((size_t)K * ld), Cin((size_t)M * ld), Cout((size_t)M * ld), Ref((size_t)M * ld);
+    Aligned<int> rp((size_t)M + 1);
+    std::vector<T> hval((size_t)nnz);
+    for (int j = 0; j < nnz; ++j) { hval[j] = (T)U(rng); val.p[j] = hval[j]; }
+    for (int i = 0; i <= M; ++i) rp.p[i] = a.rp[i];
+    for (int64_t i = 0; i < (int64_t)K * ld; ++i) B.p[i] = (i % ld) < N ? (T)U(rng) : (T)0;
+    for (int64_t i = 0; i < (int64_t)M * ld; ++i) Cin.p[i] = (i % ld) < N ? (T)U(rng) : (T)0;
+    const T alpha = (T)0.85f, beta = (T)-2.06f;
+    reference<T>(a, hval, N, B.p, ld, alpha, beta, Cin.p, Ref.p, ld);
+    int nb = 0, nr = 0, max_smem = 0;
+    int32_t *blocks = nullptr, *runs = nullptr;
+    uint16_t *lcol = nullptr;
+    int64_t total = 0;
+    if (sx_plan_edge_lists(M, K, a.rp.data(), a.ci.data(), (int)(ld * sizeof(T)), (int)sizeof(T), budget, &nb, &blocks, &nr,
+                           &runs, &lcol, &total, &max_smem) != 0) {
+        std::printf("edge lists: plan FAILED\n");
+        ++failures;
+        return;
+    }
+    char what[96];
+    std::snprintf(what, sizeof what, "edge lists (variant 5)%s%s", shuffle_rows ? " unsorted" : "", with_flags ? " +flags" : "");
+    if (nb == 0) {
+        std::printf("%-34s %s M=%d K=%d N=%d G=%d budget=%d: not plannable (a row exceeds the budget)\n", what, tname, M, K, N, G, budget);
+        return;
+    }
+    // device copies at exactly the product's sizes and pads (sx_api.cu: get_edge_plan, upload_csr)
+    Aligned<int> dblocks((size_t)nb * 8), druns((size_t)std::max(nr, 1) * 2);
+    Aligned<uint16_t> dlcol((size_t)nnz, 64);
+    std::copy(blocks, blocks + (size_t)nb * 8, dblocks.p);
+    std::copy(runs, runs + (size_t)nr * 2, druns.p);
+    std::copy(lcol, lcol + nnz, dlcol.p);
+    // plan invariants: blocks tile the rows in order, every nonzero's local column names its column
+    bool plan_ok = true;
+    int next_row = 0;
+    for (int b = 0; b < nb && plan_ok; ++b) {
+        const int32_t *r = blocks + (size_t)b * 8;
+        plan_ok = r[0] == next_row && r[1] >= 1 && r[1] <= 32 && r[2] == a.rp[r[0]] && r[3] == a.rp[r[0] + r[1]] && r[7] <= budget && r[7] <= max_smem;
+        next_row = r[0] + r[1];
+        std::vector<int> cols;
+        for (int q = r[4]; q < r[5]; ++q)
+            for (int t = 0; t < (runs[2 * q + 1] & 0xffff); ++t) {
+                plan_ok = plan_ok && (int)cols.size() == (int)((uint32_t)runs[2 * q + 1] >> 16) + t;
+                cols.push_back(runs[2 * q] + t);
+            }
+        plan_ok = plan_ok && (int)cols.size() == r[6];
+        for (int j = r[2]; j < r[3] && plan_ok; ++j) plan_ok = lcol[j] < cols.size() && cols[lcol[j]] == a.ci[j];
+    }
+    plan_ok = plan_ok && next_row == M;
+    if (!plan_ok) { std::printf("%-34s %s M=%d N=%d: PLAN INVARIANT MISMATCH\n", what, tname, M, N); ++failures; }
+    const int nvec = (N * (int)sizeof(T) + 15) / 16;
+    const uint32_t ldv = (uint32_t)(ld / E);
+    std::fill(Cout.p, Cout.p + (int64_t)M * ld, (T)777);
+    Aligned<uint32_t> flags(8);
+    flags.p[0] = 41;  // ready flag already at the step the kernel waits for
+    sx_emu::launch((unsigned)nb, 32 * G, (size_t)std::max(max_smem, 16), [&] {
+        sx::spmm_edgelist_kernel<T, G, true>(reinterpret_cast<const int4 *>(dblocks.p), reinterpret_cast<const int2 *>(druns.p),
+                                             rp.p, dlcol.p, val.p, B.p, ldv, Cin.p, Cout.p, ldv, alpha, beta, nvec,
+                                             sx::SX_EDGE_PREFETCH, with_flags ? flags.p : nullptr, 41u,
+                                             with_flags ? flags.p + 2 : nullptr, with_flags ? flags.p + 4 : nullptr);
+    });
+    bool ok = true;
+    for (int i = 0; i < M && ok; ++i) ok = same_bits(Cout.p + (int64_t)i * ld, Ref.p + (int64_t)i * ld, (size_t)N);
+    if (with_flags) ok = ok && flags.p[4] == 41u && flags.p[2] == 0u;  // the last block acknowledged and reset the counter
+    std::printf("%-34s %s M=%d K=%d N=%d G=%d budget=%d blocks=%d cols=%lld/%d: %s\n", what, tname, M, K, N, G, budget, nb,
+                (long long)total, nnz, ok ? "bit-exact" : "MISMATCH");
+    if (!ok) ++failures;
+    sx_free(blocks);
+    sx_free(runs);
+    sx_free(lcol);
+}
+
+template <typename T>
+void edge_by_shape(const char *tname, const Csr &a, int N, int budget, bool shuffle_rows, unsigned seed, bool with_flags = false) {
+    const int nvec = (N * (int)sizeof(T) + 15) / 16;
+    int G = 2;
+    while (G < 32 && G < nvec) G <<= 1;
+    switch (G) {
+        case 2: edge_case<T, 2>(tname, a, N, budget, shuffle_rows, seed, with_flags); break;
+        case 4: edge_case<T, 4>(tname, a, N, budget, shuffle_rows, seed, with_flags); break;
+        case 8: edge_case<T, 8>(tname, a, N, budget, shuffle_rows, seed, with_flags); break;
+        case 16: edge_case<T, 16>(tname, a, N, budget, shuffle_rows, seed, with_flags); break;
+        default: std::printf("N=%d needs more than 16 lanes per row: not a variant-5 shape\n", N);
+    }
+}
+
 int main() {
     const struct { int M, K, N, hb, per; } cases[] = {
         {200, 200, 16, 40, 9}, {130, 150, 8, 30, 6}, {96, 96, 4, 20, 5}, {257, 300, 24, 50, 11}, {64, 64, 32, 30, 7},
@@ -592,6 +696,16 @@ int main() {
     slide_by_shape<float>("f32", 2048, 2048, 16, 32, 40, 4, seed++, 0);
     slide_by_shape<double>("f64", 2048, 2048, 16, 96, 60, 3, seed++, 0);
     slide_by_shape<double>("f64", 1024, 1024, 8, 32, 50, 1, seed++, 0);
+    const struct { int M, K, N, hb, per, budget; } ecases[] = {
+        {200, 200, 16, 40, 9, 56000}, {130, 150, 8, 30, 6, 56000}, {96, 96, 4, 20, 5, 37000}, {257, 300, 24, 50, 11, 56000},
+        {64, 64, 32, 30, 7, 114000},  {300, 280, 3, 25, 4, 4096},  {128, 128, 64, 20, 6, 8192}, {1000, 1200, 16, 60, 20, 6000},
+        {70, 64, 1, 10, 3, 2048},     {500, 500, 16, 200, 30, 20000}};
+    for (const auto &c : ecases) {
+        edge_by_shape<float>("f32", banded(c.M, c.K, c.hb, c.per, seed), c.N, c.budget, false, seed, c.M == 200);
+        ++seed;
+        edge_by_shape<double>("f64", wandering_band(c.M, c.K, c.hb, c.per, seed), c.N, c.budget, c.M % 2 == 0, seed, c.M == 257);
+        ++seed;
+    }
     const struct { int M, K, N, avg, long_row, split; } rcases[] = {
         {120, 200, 16, 9, 0, 0}, {90, 300, 8, 11, 250, 64}, {70, 150, 4, 6, 0, 0}, {64, 400, 32, 14, 380, 96},
         {50, 120, 64, 9, 0, 0}, {40, 100, 136, 7, 90, 32}, {30, 90, 3, 5, 0, 0}};

@@ -1,0 +1,73 @@
+"""Host-side plan of the edge-list kernel (sx_plan_edge_lists; no GPU): the blocks tile the rows,
+every block's runs list its distinct columns in ascending order, every nonzero's 16-bit local
+column names its column, and no block exceeds the shared-memory budget."""
+import numpy as np
+import pytest
+
+import oracle
+import sextans_b200 as sx
+from helpers import mtx_path, random_csr
+
+
+def check_plan(M, K, rp, ci, row_bytes, elem, budget, blocks, runs, lcol, total, max_smem):
+    assert blocks.shape[1] == 8 and runs.shape[1] == 2 and lcol.size == ci.size
+    nxt = 0
+    tot = 0
+    for b in blocks:
+        r0, nr, jb, je, q0, q1, ncols, smem = (int(x) for x in b)
+        assert r0 == nxt and 1 <= nr <= 32 and (r0 // 32) == ((r0 + nr - 1) // 32)
+        assert jb == rp[r0] and je == rp[r0 + nr]
+        cols = []
+        for col, packed in runs[q0:q1]:
+            first, length = (int(packed) >> 16) & 0xffff, int(packed) & 0xffff
+            assert first == len(cols) and length >= 1 and length * row_bytes <= max(16384, row_bytes)
+            cols.extend(range(int(col), int(col) + length))
+        assert len(cols) == ncols and cols == sorted(set(ci[jb:je].tolist()))
+        assert np.array_equal(np.asarray(cols, dtype=np.int64)[lcol[jb:je]], ci[jb:je])
+        na = ((je - (jb & ~7) + 7) & ~7) if je > jb else 0
+        assert smem == ncols * row_bytes + na * (elem + 2) and smem <= budget and smem <= max_smem
+        nxt = r0 + nr
+        tot += ncols
+    assert nxt == M and tot == total
+
+
+@pytest.mark.parametrize("name,row_bytes,elem,distinct", [("nasa4704", 128, 8, 20897), ("pcrystk02", 64, 4, 138342)])
+def test_suitesparse_plans(name, row_bytes, elem, distinct):
+    """BASELINE configs[1] (N=16 fp64) and configs[2] (N=16 fp32) at four blocks per SM."""
+    M, K, nnz, rp, ci, v, _ = oracle.load_mtx(mtx_path(name), np.float32)
+    blocks, runs, lcol, total, max_smem = sx.plan_edge_lists(M, K, rp, ci, row_bytes, elem, 56192)
+    assert len(blocks) == (M + 31) // 32 and total == distinct      # no 32-row group had to be cut
+    check_plan(M, K, rp, ci, row_bytes, elem, 56192, blocks, runs, lcol, total, max_smem)
+    assert total * 2 <= nnz                                          # a staged B row serves >= 2 nonzeros
+    # a budget that forces cuts
+    small = sx.plan_edge_lists(M, K, rp, ci, row_bytes, elem, 12000)
+    assert len(small[0]) > len(blocks) and small[3] >= total
+    check_plan(M, K, rp, ci, row_bytes, elem, 12000, *small)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_matrices_with_empty_rows_and_unsorted_columns(seed):
+    rng = np.random.default_rng(seed)
+    M, K = int(rng.integers(1, 400)), int(rng.integers(40, 3000))
+    rp, ci, v = random_csr(M, K, int(rng.integers(1, 30)), seed, np.float32, long_row=min(K, 200))
+    for r in range(M):                       # stored order is arbitrary
+        rng.shuffle(ci[rp[r]:rp[r + 1]])
+    for row_bytes, elem, budget in ((32, 4, 4096), (64, 8, 20000), (256, 4, 114000)):
+        plan = sx.plan_edge_lists(M, K, rp, ci, row_bytes, elem, budget)
+        if len(plan[0]) == 0:                # some row alone exceeds the budget
+            lens = np.diff(rp)
+            worst = int(lens.max())
+            assert worst * row_bytes + (worst + 14) * (elem + 2) > budget * 0.5
+            continue
+        check_plan(M, K, rp, ci, row_bytes, elem, budget, *plan)
+
+
+def test_degenerate_inputs():
+    rp = np.zeros(1, np.int32)
+    b, r, l, t, m = sx.plan_edge_lists(0, 5, rp, np.zeros(0, np.int32), 64, 4, 4096)
+    assert len(b) == 0 and t == 0
+    rp = np.zeros(41, np.int32)              # 40 empty rows: blocks without runs
+    b, r, l, t, m = sx.plan_edge_lists(40, 5, rp, np.zeros(0, np.int32), 64, 4, 4096)
+    assert len(b) == 2 and t == 0 and len(r) == 0 and b[:, 6].sum() == 0
+    with pytest.raises(sx.SextansError):
+        sx.plan_edge_lists(4, 5, np.zeros(5, np.int32), np.zeros(0, np.int32), 60, 4, 4096)   # row_bytes % 16

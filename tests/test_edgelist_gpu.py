@@ -1,0 +1,141 @@
+"""GPU parity of variant 5, the edge-list kernel (spmm_edgelist_kernel): a row block's distinct
+B rows staged by TMA, 16-bit window-local columns -- the GPU form of the reference's packed
+edge words with a window-local column field (src/sparse_helper.h:419-443, src/sextans.cpp:398-402).
+Bit-exact against cpu_spmm_CSR in strict mode: one lane group per row, stored order."""
+import numpy as np
+import pytest
+
+import oracle
+import sextans_b200 as sx
+from helpers import GOLDEN, SUITESPARSE, mtx_path, perturbed_inputs, random_dense, sha
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def eng():
+    e = sx.Engine(0)
+    yield e
+    e.close()
+
+
+def bits(a):
+    return a.view(np.uint32 if a.dtype == np.float32 else np.uint64)
+
+
+def banded_csr(M, K, half_band, per_row, seed, dtype, sort=True):
+    rng = np.random.default_rng(seed)
+    rp = np.zeros(M + 1, dtype=np.int32)
+    cols = []
+    for r in range(M):
+        lo, hi = max(0, r * K // M - half_band), min(K, r * K // M + half_band + 1)
+        n = min(per_row if r % 7 else 0, hi - lo)
+        c = rng.choice(np.arange(lo, hi), size=n, replace=False)
+        cols.append(np.sort(c) if sort else c)
+        rp[r + 1] = rp[r] + n
+    ci = np.concatenate(cols).astype(np.int32)
+    return rp, ci, rng.uniform(-1, 1, ci.size).astype(dtype)
+
+
+@pytest.mark.parametrize("name", SUITESPARSE)
+def test_auto_takes_edge_lists_on_the_suitesparse_matrices_and_matches_golden(eng, golden, name):
+    """C1/C3 through the kernel the auto rule now picks for them: every golden run of the
+    reference's cpu_spmm_CSR, bit for bit (SHA-256 of C)."""
+    g = golden["suitesparse"][name]
+    M, K, nnz, rp, ci, v = sx.load_mtx(mtx_path(name), np.float32)
+    for r in g["runs"]:
+        N = r["N"]
+        if r["kind"] == "default":
+            B, C = oracle.init_dense(M, K, N, np.float32)
+            eng.upload_csr(M, K, rp, ci, v)
+        else:
+            val, B, C = perturbed_inputs(M, K, N, nnz, np.float32)
+            eng.upload_csr(M, K, rp, ci, val)
+        eng.spmm(N, r["alpha"], B, r["beta"], C, rp_time=2)
+        if N * 4 <= 256:
+            assert eng.info(sx.INFO_LAST_KERNEL) // 10000 == 8, (name, N)
+        assert sha(C) == r["C_sha256"], (name, r["kind"], N)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("M,K,N,hb,per", [(4704, 4704, 16, 200, 22), (1000, 1000, 8, 40, 9), (999, 1200, 32, 100, 30),
+                                          (70, 64, 4, 20, 5), (4000, 4000, 64, 300, 40), (33, 5000, 1, 2000, 60),
+                                          (20000, 20000, 24, 30, 12)])
+def test_banded_matrices_bit_exact_sorted_and_unsorted(eng, dtype, M, K, N, hb, per):
+    for sort in (True, False):
+        rp, ci, v = banded_csr(M, K, hb, per, M + N, dtype, sort=sort)
+        if not sort and ci.size > 4:
+            ci[1] = ci[0]                      # a duplicate (row, column) pair too
+        B, Cin = random_dense(M, K, N, M + N, dtype)
+        ref = oracle.spmm_csr(M, N, K, rp, ci, v, dtype(0.85), B, dtype(-2.06), Cin.copy())
+        eng.set_option(sx.OPT_KERNEL, 5)
+        eng.upload_csr(M, K, rp, ci, v)
+        for rp_time in (1, 3):
+            C = Cin.copy()
+            eng.spmm(N, dtype(0.85), B, dtype(-2.06), C, rp_time)
+            if N * np.dtype(dtype).itemsize <= 256:
+                assert eng.info(sx.INFO_LAST_KERNEL) // 10000 == 8
+            assert np.array_equal(bits(C), bits(ref)), (sort, rp_time)
+
+
+@pytest.mark.parametrize("pdl", [1, 0])
+@pytest.mark.parametrize("prefetch", [1, 0])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_dependent_chain_in_place_with_programmatic_launch(eng, dtype, pdl, prefetch):
+    """Back-to-back launches whose C_in is the previous launch's C_out (in place) and whose B
+    was produced by a kernel just before: the early-started prologue (A slice by TMA, L2
+    prefetch of B and C_in) must not consume either before the previous kernel is complete."""
+    torch = pytest.importorskip("torch")
+    M = K = 4096
+    N = 16
+    rp, ci, v = banded_csr(M, K, 200, 24, 77, dtype)
+    B, Cin = random_dense(M, K, N, 77, dtype)
+    ref = Cin.copy()
+    for _ in range(6):
+        ref = oracle.spmm_csr(M, N, K, rp, ci, v, dtype(0.5), B, dtype(0.25), ref)
+    eng.set_option(sx.OPT_PDL, pdl)
+    eng.set_option(sx.OPT_PREFETCH, prefetch)
+    eng.upload_csr(M, K, rp, ci, v)
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)
+    try:
+        with torch.cuda.stream(stream):
+            dB_cm = torch.from_numpy(B).cuda()
+            dC = torch.from_numpy(np.ascontiguousarray(Cin.reshape(N, M).T)).cuda()   # row-major M x N
+            dB = torch.empty(K * N, dtype=dB_cm.dtype, device="cuda")
+            for rep in range(3):
+                dCw = dC.clone()
+                dB.zero_()
+                eng.colmajor_to_rowmajor(K, N, dB_cm, dB, N)   # B produced right before the first SpMM
+                for _ in range(6):
+                    eng.spmm_device(N, dtype(0.5), dB, N, dtype(0.25), dCw, dCw, N)
+                stream.synchronize()
+                assert eng.info(sx.INFO_LAST_KERNEL) // 10000 == 8
+                got = np.ascontiguousarray(dCw.cpu().numpy().T).ravel()
+                assert np.array_equal(bits(got), bits(ref)), rep
+            # the same chain as ONE CUDA graph (what the bench replays)
+            dCw = dC.clone()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                for _ in range(6):
+                    eng.spmm_device(N, dtype(0.5), dB, N, dtype(0.25), dCw, dCw, N)
+            dCw.copy_(dC)
+            g.replay()
+            stream.synchronize()
+            got = np.ascontiguousarray(dCw.cpu().numpy().T).ravel()
+            assert np.array_equal(bits(got), bits(ref))
+    finally:
+        eng.set_stream(None)
+
+
+def test_unstructured_matrix_is_left_to_the_other_kernels(eng):
+    """No reuse (about one distinct column per nonzero): the auto rule does not build edge lists."""
+    from helpers import random_csr
+    M, K, N = 20000, 500000, 16
+    rp, ci, v = random_csr(M, K, 12, 5, np.float32)
+    B, Cin = random_dense(M, K, N, 5, np.float32)
+    eng.upload_csr(M, K, rp, ci, v)
+    C = Cin.copy()
+    eng.spmm(N, np.float32(0.85), B, np.float32(-2.06), C)
+    assert eng.info(sx.INFO_LAST_KERNEL) // 10000 in (1, 2)
+    assert np.array_equal(bits(C), bits(oracle.spmm_csr(M, N, K, rp, ci, v, np.float32(0.85), B, np.float32(-2.06), Cin.copy())))

@@ -65,6 +65,8 @@ def test_block_level_kernels_on_the_cpu_emulation(tmp_path):
     assert len(rows) >= 14
     slide = re.findall(r"^slide \(variant 4\) +f(?:32|64) M=.*bit-exact$", r.stdout, flags=re.M)
     assert len(slide) >= 14
+    edge = re.findall(r"^edge lists \(variant 5\).*? +f(?:32|64) M=.*bit-exact$", r.stdout, flags=re.M)
+    assert len(edge) >= 18 and "PLAN INVARIANT MISMATCH" not in r.stdout
 
 
 @pytest.mark.skipif(CXX is None or os.environ.get("SX_EMU_ASAN") != "1",

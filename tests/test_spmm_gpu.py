@@ -200,13 +200,15 @@ KERNEL_SHAPES = [(7, 5, 2, 8), (257, 300, 17, 32), (64, 1000, 40, 40), (500, 200
                  (300, 300, 30, 128), (130, 77, 9, 256), (1000, 1000, 3, 1), (2000, 3000, 70, 16)]
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 5])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("M,K,avg,N", KERNEL_SHAPES)
 def test_every_kernel_variant_bit_exact(eng, kernel, dtype, M, K, avg, N):
-    """Variants 1 (row per lane group), 2 (TMA-staged work items, at several item budgets)
-    and 3 (TMA-staged B window; defers to 1 when a window does not fit in shared memory or
-    a dense row is wider than 256 bytes) all reproduce the oracle bit for bit."""
+    """Variants 1 (row per lane group), 2 (TMA-staged work items, at several item budgets),
+    3 (TMA-staged B window; defers to 1 when a window does not fit in shared memory or
+    a dense row is wider than 256 bytes) and 5 (edge lists: a row block's distinct B rows staged
+    by TMA, 16-bit local columns; forced here on matrices without any reuse; dense rows wider
+    than 256 bytes go to the other variants) all reproduce the oracle bit for bit."""
     rp, ci, v = random_csr(M, K, avg, M * 17 + N + kernel, dtype, long_row=min(K, 300))
     B, Cin = random_dense(M, K, N, M * 17 + N, dtype)
     eng.set_option(sx.OPT_KERNEL, kernel)
@@ -216,7 +218,11 @@ def test_every_kernel_variant_bit_exact(eng, kernel, dtype, M, K, avg, N):
             C, _ = run(eng, M, K, N, rp, ci, v, dtype(0.85), B, dtype(-2.06), Cin)
             ref = oracle.spmm_csr(M, N, K, rp, ci, v, dtype(0.85), B, dtype(-2.06), Cin.copy())
             assert np.array_equal(bits(C), bits(ref)), (kernel, item_nnz)
-            assert eng.info(sx.INFO_LAST_KERNEL) // 10000 in ((kernel,) if kernel != 3 else (3, 1))
+            family = eng.info(sx.INFO_LAST_KERNEL) // 10000
+            if kernel == 5:
+                assert family == 8 if N * np.dtype(dtype).itemsize <= 256 else family in (1, 2, 3)
+            else:
+                assert family in ((kernel,) if kernel != 3 else (3, 1))
     finally:
         eng.set_option(sx.OPT_KERNEL, 0)
         eng.set_option(sx.OPT_ITEM_NNZ, 0)
@@ -272,14 +278,14 @@ def test_auto_kernel_choice(eng):
     C, _ = run(eng, 3000, 60000, 16, rp, ci, v, A32, B, B32, Cin)
     assert eng.info(sx.INFO_LAST_KERNEL) // 10000 == 1
     assert np.array_equal(bits(C), bits(oracle.spmm_csr(3000, 16, 60000, rp, ci, v, A32, B, B32, Cin.copy())))
-    # many rows, still narrow windows: variant 3 at any size
+    # many rows, two columns shared by all of them: a staged B row serves many nonzeros, variant 5
     M = 100000
     rp = (np.arange(M + 1) * 2).astype(np.int32)
     ci = np.tile(np.array([1, 7], dtype=np.int32), M)
     v = np.ones(2 * M, np.float32)
     B, Cin = random_dense(M, 16, 16, 2, np.float32)
     C, _ = run(eng, M, 16, 16, rp, ci, v, A32, B, B32, Cin)
-    assert eng.info(sx.INFO_LAST_KERNEL) // 10000 == 3
+    assert eng.info(sx.INFO_LAST_KERNEL) // 10000 == 8
     assert np.array_equal(bits(C), bits(oracle.spmm_csr(M, 16, 16, rp, ci, v, A32, B, B32, Cin.copy())))
     # many rows, columns all over a wide B: the nnz-balanced staged variant 2
     K = 500000
