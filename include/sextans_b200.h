@@ -174,6 +174,9 @@ enum sx_info {
     SX_INFO_UPLOAD_SERIAL = 14, /* process-wide serial number of the matrix this context holds
                                  * (every successful sx_upload_csr_* draws a new one; 0: none) */
     SX_INFO_COL_WINDOWS = 15,   /* column windows in use (0: the matrix is not windowed) */
+    SX_INFO_EXCHANGE_TIMEOUTS = 17, /* nonzero if a device-side wait on a peer flag ever gave up (~2 s) */
+    SX_INFO_EDGE_BLOCKS = 18,   /* row blocks of the edge-list plan of the last launch (variant 5) */
+    SX_INFO_EDGE_COLS = 19,     /* B rows those blocks stage per SpMM (sum of their distinct columns) */
     SX_INFO_TUNED_KERNEL = 16   /* SX_OPT_AUTOTUNE's choice for the current N: 10 * variant + (1 if
                                  * with the L2 prefetch), 0 if nothing has been tuned */
 };
@@ -270,6 +273,25 @@ int sx_flag_write(sx_ctx *ctx, void *flag_dptr, uint32_t value);
 int sx_flag_write_many(sx_ctx *ctx, void *const *flag_dptrs, int n, uint32_t value);
 /* enqueue on the context's stream: work after it starts when (int32)(*flag - value) >= 0 */
 int sx_flag_wait(sx_ctx *ctx, void *flag_dptr, uint32_t value);
+/* ---- exchange of B by PUSH (the row-block partition's one exchange step, small B) -------------
+ * The rank that holds B copies its image into every peer's image with ONE kernel (posted 16-byte
+ * stores over NVLink); the peers launch nothing for it: their next SpMM waits on a flag in its own
+ * prologue and acknowledges from its last block.  The multi-GPU form of the reference's chain that
+ * hands the B window from PEG to PEG (src/sextans.cpp:909-941).  All counters are 32-bit words in
+ * device memory (sx_device_alloc, zero-filled; exchanged with sx_ipc_*), so captured launches can
+ * be replayed:
+ *   on every peer, per image:   ready  (written by the pusher), epoch (SpMMs served; local)
+ *   on the pusher, per image:   pushes (pushes done; local), done[peer] (written by the peers)
+ * sx_push_B: waits until done[p] >= pushes for every peer (they have finished the SpMM that used the
+ *   previous contents), copies this context's B image (N columns) to peer_images[p], then stores
+ *   pushes + 1 into peer_ready_flags[p] and into pushes.  npeers <= 15.
+ * sx_spmm_expect_push: the NEXT SpMM launch of this context (sx_spmm_device_* / sx_launch_*) waits
+ *   until *ready_flag >= *epoch_counter + 1 before it reads B, and when it is complete advances
+ *   *epoch_counter and stores it into done_flag (the pusher's done[this peer], peer-mapped).
+ *   One-shot.  A wait that sees nothing for ~2 s gives up (SX_INFO_EXCHANGE_TIMEOUTS). */
+int sx_push_B(sx_ctx *ctx, int N, void *const *peer_images, void *const *peer_ready_flags, int npeers,
+              const void *done_flags, void *pushes_counter);
+int sx_spmm_expect_push(sx_ctx *ctx, const void *ready_flag, void *epoch_counter, void *done_flag);
 /* enqueue a copy of a peer's row-major B image (same K, same N, same dtype: the bytes
  * sx_device_B reports) into this context's image; marks B as staged. */
 int sx_pull_B(sx_ctx *ctx, int N, const void *peer_B_image);
@@ -307,23 +329,25 @@ int sx_partition_rows(int M, const int32_t *rowptr, int parts, int32_t *bounds);
  * Arrays are malloc'ed; release each with sx_free. */
 int sx_plan_slide(int M, const int32_t *rowptr, const int32_t *colidx, int nchains_wanted, int *nsteps,
                   int32_t **steps, int *nchains, int32_t **chains, int *ring_rows, int *max_step_entries);
-/* Plan of the edge-list kernel (variant 5; host only).  Row blocks of up to 32 consecutive
- * rows, each with the ascending list of the DISTINCT columns its nonzeros touch -- the block's
- * compacted B window, described as runs of consecutive columns -- and, per nonzero, the 16-bit
- * index of its column inside that window: the GPU form of the reference's window-local column
- * field (col14 of the packed edge word, src/sparse_helper.h:419-443, src/sextans.cpp:398-402).
+/* Plan of the edge-list kernel (variant 5; host only).  Row blocks of up to rows_per_block
+ * consecutive rows, each with the ascending list of the DISTINCT columns its nonzeros touch -- the
+ * block's compacted B window -- and, per nonzero, the 16-bit index of its column inside that
+ * window: the GPU form of the reference's window-local column field (col14 of the packed edge
+ * word, src/sparse_helper.h:419-443, src/sextans.cpp:398-402).
  *   row_bytes    bytes of one row of the row-major B image (leading dimension x element size)
- *   smem_budget  shared memory one block may use (window + its slice of values and indices)
- *   blocks  8 ints per block: {row_begin, nrows, nnz_begin, nnz_end, run_begin, run_end, ncols, smem_bytes}
- *   runs    2 ints per run: {first column, (first local index << 16) | length}
+ *   smem_budget  shared memory one block may use (window + its slices of values, local columns
+ *                and its column list)
+ *   blocks  8 ints per block: {row_begin, nrows, nnz_begin, nnz_end, col_begin, ncols, 0, smem_bytes}
+ *   cols    *ncols ints: the blocks' column lists back to back, each starting at a multiple of 4
+ *           entries; pad entries repeat the block's last column
  *   lcol    one uint16 per nonzero, parallel to colidx
  *   total_cols  sum of ncols over the blocks (B rows staged per SpMM)
  *   max_smem    largest smem_bytes
  * *nblocks = 0 (and SX_OK) if some single row does not fit the budget.  Arrays are malloc'ed;
  * release each with sx_free. */
 int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colidx, int row_bytes, int elem_bytes,
-                       int smem_budget, int *nblocks, int32_t **blocks, int *nruns, int32_t **runs,
-                       uint16_t **lcol, int64_t *total_cols, int *max_smem);
+                       int rows_per_block, int smem_budget, int *nblocks, int32_t **blocks, int64_t *ncols,
+                       int32_t **cols, uint16_t **lcol, int64_t *total_cols, int *max_smem);
 int sx_split_col_windows(int M, int K, const int32_t *rowptr, const int32_t *colidx, int window_rows,
                          int *nwin, int32_t **win_rowptr, int64_t **win_base, int32_t **order,
                          int *ascending);

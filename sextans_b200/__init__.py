@@ -31,7 +31,8 @@ STRICT, FAST = 0, 1
  OPT_AUTOTUNE) = range(13)
 (INFO_LAUNCHES, INFO_M, INFO_K, INFO_NNZ, INFO_DTYPE, INFO_SPLIT_ROWS, INFO_LAST_KERNEL, INFO_LD,
  INFO_ITEMS, INFO_ITEM_NNZ, INFO_HOST_PATH, INFO_TILE_NNZ, INFO_TILE_SLOTS, INFO_REST_NNZ,
- INFO_UPLOAD_SERIAL, INFO_COL_WINDOWS, INFO_TUNED_KERNEL) = range(17)
+ INFO_UPLOAD_SERIAL, INFO_COL_WINDOWS, INFO_TUNED_KERNEL, INFO_EXCHANGE_TIMEOUTS, INFO_EDGE_BLOCKS,
+ INFO_EDGE_COLS) = range(20)
 
 _PI32 = C.POINTER(C.c_int32)
 _PF = C.POINTER(C.c_float)
@@ -98,6 +99,8 @@ def lib():
         "sx_flag_write": ([vp, vp, C.c_uint32], i),
         "sx_flag_write_many": ([vp, C.POINTER(vp), i, C.c_uint32], i),
         "sx_flag_wait": ([vp, vp, C.c_uint32], i),
+        "sx_push_B": ([vp, i, C.POINTER(vp), C.POINTER(vp), i, vp, vp], i),
+        "sx_spmm_expect_push": ([vp, vp, vp, vp], i),
         "sx_pull_B": ([vp, i, vp], i),
         "sx_pull_B_fused": ([vp, i, vp, vp, vp, C.c_uint32], i),
         "sx_host_alloc": ([sz, C.POINTER(vp)], i),
@@ -111,7 +114,7 @@ def lib():
                                   C.POINTER(C.POINTER(i64)), C.POINTER(_PI32), C.POINTER(i)], i),
         "sx_plan_slide": ([i, _PI32, _PI32, i, C.POINTER(i), C.POINTER(_PI32), C.POINTER(i), C.POINTER(_PI32),
                            C.POINTER(i), C.POINTER(i)], i),
-        "sx_plan_edge_lists": ([i, i, _PI32, _PI32, i, i, i, C.POINTER(i), C.POINTER(_PI32), C.POINTER(i),
+        "sx_plan_edge_lists": ([i, i, _PI32, _PI32, i, i, i, i, C.POINTER(i), C.POINTER(_PI32), C.POINTER(i64),
                                 C.POINTER(_PI32), C.POINTER(C.POINTER(C.c_uint16)), C.POINTER(i64), C.POINTER(i)], i),
         "sx_free": ([vp], None),
         "sx_sextans_invoke": ([vp, _PI32, _A8, _F4, _F8, _F8, i, i, i, i, i, i, i, _PD], i),
@@ -203,28 +206,28 @@ def plan_slide(M, rowptr, colidx, nchains):
     return steps, chains, ring.value, ent.value
 
 
-def plan_edge_lists(M, K, rowptr, colidx, row_bytes, elem_bytes, smem_budget):
+def plan_edge_lists(M, K, rowptr, colidx, row_bytes, elem_bytes, smem_budget, rows_per_block=32):
     """Plan of the edge-list kernel (sx_plan_edge_lists) ->
-    (blocks [nblocks, 8], runs [nruns, 2], lcol [nnz] uint16, total_cols, max_smem); nblocks == 0 if some row
-    does not fit ``smem_budget``."""
+    (blocks [nblocks, 8], cols [ncols] int32, lcol [nnz] uint16, total_cols, max_smem); nblocks == 0 if some
+    row does not fit ``smem_budget``."""
     rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
     colidx = np.ascontiguousarray(colidx, dtype=np.int32)
-    nb, nr, ms, tot = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
-    bl, ru, lc = _PI32(), _PI32(), C.POINTER(C.c_uint16)()
+    nb, ms, tot, nc = C.c_int(), C.c_int(), C.c_int64(), C.c_int64()
+    bl, co, lc = _PI32(), _PI32(), C.POINTER(C.c_uint16)()
     L = lib()
     _check(L.sx_plan_edge_lists(M, K, rowptr.ctypes.data_as(_PI32), colidx.ctypes.data_as(_PI32), row_bytes, elem_bytes,
-                                smem_budget, C.byref(nb), C.byref(bl), C.byref(nr), C.byref(ru), C.byref(lc),
-                                C.byref(tot), C.byref(ms)))
+                                rows_per_block, smem_budget, C.byref(nb), C.byref(bl), C.byref(nc), C.byref(co),
+                                C.byref(lc), C.byref(tot), C.byref(ms)))
     if nb.value == 0:
-        return np.zeros((0, 8), np.int32), np.zeros((0, 2), np.int32), np.zeros(0, np.uint16), 0, 0
+        return np.zeros((0, 8), np.int32), np.zeros(0, np.int32), np.zeros(0, np.uint16), 0, 0
     try:
         n = int(rowptr[M])
         blocks = np.ctypeslib.as_array(bl, shape=(nb.value * 8,)).reshape(-1, 8).copy()
-        runs = np.ctypeslib.as_array(ru, shape=(max(nr.value, 1) * 2,))[:nr.value * 2].reshape(-1, 2).copy()
+        cols = np.ctypeslib.as_array(co, shape=(max(nc.value, 1),))[:nc.value].copy()
         lcol = np.ctypeslib.as_array(lc, shape=(max(n, 1),))[:n].copy()
     finally:
-        L.sx_free(bl), L.sx_free(ru), L.sx_free(lc)
-    return blocks, runs, lcol, tot.value, ms.value
+        L.sx_free(bl), L.sx_free(co), L.sx_free(lc)
+    return blocks, cols, lcol, tot.value, ms.value
 
 
 def split_col_windows(M, K, rowptr, colidx, window_rows):
@@ -534,6 +537,17 @@ class Engine:
     def pull_B_fused(self, N, peer_image_ptr, ready_flag, done_flag, step):
         _check(self._L.sx_pull_B_fused(self._ctx, N, C.c_void_p(peer_image_ptr), C.c_void_p(ready_flag),
                                        C.c_void_p(done_flag), step & 0xFFFFFFFF))
+
+    def push_B(self, N, peer_image_ptrs, peer_ready_ptrs, done_flags_ptr, pushes_ptr):
+        """Copy this context's B image into every peer's (one kernel); see sx_push_B."""
+        n = len(peer_image_ptrs)
+        imgs = (C.c_void_p * n)(*peer_image_ptrs)
+        rdy = (C.c_void_p * n)(*peer_ready_ptrs)
+        _check(self._L.sx_push_B(self._ctx, N, imgs, rdy, n, C.c_void_p(done_flags_ptr), C.c_void_p(pushes_ptr)))
+
+    def expect_push(self, ready_ptr, epoch_ptr, done_ptr):
+        """The next SpMM launch waits for the push into its B image and acknowledges it (sx_spmm_expect_push)."""
+        _check(self._L.sx_spmm_expect_push(self._ctx, C.c_void_p(ready_ptr), C.c_void_p(epoch_ptr), C.c_void_p(done_ptr)))
 
     def pull_B(self, N, peer_image_ptr):
         _check(self._L.sx_pull_B(self._ctx, N, C.c_void_p(peer_image_ptr)))

@@ -212,6 +212,11 @@ __device__ __forceinline__ uint64_t policy_evict_last() {
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+// 16-byte asynchronous copy global -> shared (LDGSTS, L2 only); completion with cp_async_wait_all
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // programmatic dependent launch (no-ops when the grid was launched without the attribute)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -647,133 +652,129 @@ spmm_window_kernel(const int M, const int4 *__restrict__ blocks, const int *__re
     }
 }
 
-// ---- variant 5: edge lists -- a row block's DISTINCT B rows staged by TMA, 16-bit local columns ----
+// ---- variant 5: edge lists -- a row block's DISTINCT B rows staged in shared memory, 16-bit local columns ----
 // The reference cuts A into column windows, keeps the window of B on chip and stores every
 // nonzero as a packed word whose column is LOCAL to the window (col14 | row18 | val32,
 // src/sparse_helper.h:419-443; decoded in src/sextans.cpp:398-402), so that a PE indexes its
-// on-chip B directly.  Here the "window" of a row block (up to 32 consecutive rows, one thread
+// on-chip B directly.  Here the "window" of a row block (ROWS consecutive rows, one thread
 // block) is the ascending list of the distinct columns its nonzeros touch: exactly those rows
-// of B are staged into shared memory -- as a handful of TMA bulk copies, because on FEM-type
-// matrices the distinct columns come in runs of consecutive columns (nasa4704: 142 columns in
-// 7 runs per block against a span of 456; pcrystk02: 317 in 8 against 918) -- and every nonzero
-// carries a 16-bit index into that compacted window (sx_host.cpp: sx_plan_edge_lists).  Against
-// variant 3 (the whole contiguous span staged) that is a third of the bytes through L2 and a
-// third of the shared memory, so 4-6 blocks share an SM instead of 1-2, and the index stream
-// of A shrinks from 4 to 2 bytes per nonzero.
-//   block record (two int4): {row_begin, nrows, nnz_begin, nnz_end} {run_begin, run_end, ncols, -}
-//   run record (int2):       {first column, (first local index << 16) | length}
-//   shared memory:           window ncols x row bytes | values | local columns   (A slice from the
-//                            8-entry boundary at or below nnz_begin: whole 16-byte units)
+// of B are staged into shared memory, and every nonzero carries a 16-bit index into that
+// compacted window (sx_host.cpp: sx_plan_edge_lists).  On FEM-type matrices that is a third of
+// the contiguous span variant 3 stages (nasa4704: 142 columns per 32 rows against a span of 456;
+// pcrystk02: 317 against 918): a third of the bytes through L2 and of the shared memory, so 4-6
+// blocks share an SM instead of 1-2, and the index stream of A shrinks from 4 to 2 bytes per nonzero.
+//   block record (two int4): {row_begin, nrows, nnz_begin, nnz_end} {col_begin, ncols, -, smem}
+//   shared memory:           window ncols x row bytes | values | local columns | column list
+//                            (A slice from the 8-entry boundary at or below nnz_begin: whole 16-byte units)
 // One lane group per row, stored order, so strict mode is bit-identical to cpu_spmm_CSR.
+// 256 threads per block (512 for 16-lane groups), i.e. ROWS = 128 / 64 / 32 / 32 rows for G = 2 / 4 / 8 / 16.
+//
+// How the window gets on chip was decided by measurement (scripts/micro/launch_floor.cu, B200):
+// behind a dependent-launch wait a TMA bulk copy of a cold 16 KB piece costs ~1.05 us per graph
+// node, a plain global load ~0.16 us -- and a warp whose lanes hold different copy operands
+// issues bulk copies one lane at a time.  So only the A side (values, local columns, the column
+// list: contiguous, known before the wait) travels by TMA; the B rows are copied by ALL threads
+// with 16-byte cp.async (LDGSTS), a lane group per row, 16*G contiguous bytes per row.
 //
 // Launch chains: the kernel is written for programmatic dependent launch.  Everything that only
-// touches A (block and run records, row pointers, the TMA of the value / local-column slice)
-// and the L2 PREFETCH of the block's B rows and C_in rows (a hint, consumes nothing) happens
-// before griddepcontrol.wait; B and C_in themselves are read after it.  launch_dependents is the
-// first instruction: with 4-6 blocks per SM the next kernel of the stream becomes resident
-// beside this one and has its A side staged and its B rows on the way to L2 by the time this
-// kernel completes.  Launched without the attribute the two instructions do nothing.
+// touches A (records, row pointers, the TMA of the A slice and the column list) and the L2
+// PREFETCH of the block's B rows and C_in rows (a hint, consumes nothing) happens before
+// griddepcontrol.wait; B and C_in themselves are read after it.  launch_dependents is the first
+// instruction: the next kernel of the stream becomes resident beside this one and has its A side
+// staged and its B rows on the way to L2 by the time this kernel completes.  Launched without the
+// attribute the two instructions do nothing.
 //
 // Multi-GPU (ready != nullptr): B is pushed into this GPU's image by the rank that holds it
-// (push_image_kernel); lane 0 of warp 0 waits until the local step flag reaches `step` before
-// the window copies are issued, and the last block to finish stores `step` into the pusher's
-// done flag -- the exchange costs this rank no launch of its own.
+// (push_image_kernel).  *epoch counts the SpMMs this image has served; lane 0 of every warp
+// waits until the local ready flag reaches *epoch + 1 (the push that follows the last SpMM on
+// this image) before the window copies are issued, and the last block to finish advances *epoch
+// and stores the new value into the pusher's done flag, which lets the pusher overwrite the
+// image again.  Counters live in device memory, so a captured launch can be replayed; the
+// exchange costs this rank no launch of its own.
 constexpr int SX_EDGE_PREFETCH = 1;
+template <int G> struct EdgeShape {
+    static constexpr int THREADS = G >= 16 ? 512 : 256;
+    static constexpr int ROWS = THREADS / G;
+};
 template <typename T, int G, bool STRICT>
-__global__ void __launch_bounds__(32 * G, 2)
-spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int2 *__restrict__ runs, const int *__restrict__ rowptr,
+__global__ void __launch_bounds__(EdgeShape<G>::THREADS, 2)
+spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ cols, const int *__restrict__ rowptr,
                      const uint16_t *__restrict__ lcol, const T *__restrict__ val, const T *__restrict__ B,
                      const uint32_t ldbv, const T *Cin, T *Cout, const uint32_t ldcv, const T alpha, const T beta,
-                     const int nvec, const int flags, const uint32_t *ready, const uint32_t step,
-                     unsigned int *done_counter, uint32_t *done_remote) {
+                     const int nvec, const int flags, const uint32_t *ready, uint32_t *epoch, uint32_t *done_remote,
+                     unsigned int *sync_words) {
     using V = typename VecOf<T>::type;
+    constexpr int THREADS = EdgeShape<G>::THREADS, ROWS = EdgeShape<G>::ROWS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t bar[2];  // [0]: the A slice, [1]: the B rows
+    __shared__ uint64_t bar;  // the A slice and the column list
     pdl_launch_dependents();
     const int lg = threadIdx.x & (G - 1);
     const int rl = threadIdx.x / G;
     const int4 b0 = __ldg(blocks + 2 * blockIdx.x), b1 = __ldg(blocks + 2 * blockIdx.x + 1);
     const int jb = b0.z, je = b0.w;
+    const int ncols = b1.y;
     const uint32_t rowbytes = ldbv * 16u;
-    const uint32_t wbytes = (uint32_t)b1.z * rowbytes;
+    const uint32_t wbytes = (uint32_t)ncols * rowbytes;
     const int jal = jb & ~7;
     const bool has = je > jb;
     const uint32_t na = has ? (uint32_t)((je - jal + 7) & ~7) : 0u;
-    const V *win = reinterpret_cast<const V *>(smem_raw);
+    const uint32_t ncp = (uint32_t)(ncols + 3) & ~3u;
+    unsigned char *win = smem_raw;
     const T *sval = reinterpret_cast<const T *>(smem_raw + wbytes);
     const uint16_t *scol = reinterpret_cast<const uint16_t *>(smem_raw + wbytes + (size_t)na * sizeof(T));
+    const int *scols = reinterpret_cast<const int *>(smem_raw + wbytes + (size_t)na * (sizeof(T) + 2));
     if (threadIdx.x == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
+        mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     // ---- A side and hints: before the previous kernel of the stream is known to be complete ----
-    int2 run = make_int2(0, 0);  // warp 0: lane i holds run record run_begin + i
-    if (threadIdx.x < 32) {
-        if (threadIdx.x == 0 && has) {
-            const uint64_t pol_a = policy_evict_first();
-            mbar_expect_tx(&bar[0], na * (uint32_t)(sizeof(T) + 2));
-            tma_bulk_g2s(const_cast<T *>(sval), val + jal, na * (uint32_t)sizeof(T), &bar[0], pol_a);
-            tma_bulk_g2s(const_cast<uint16_t *>(scol), lcol + jal, na * 2u, &bar[0], pol_a);
-        }
-        if (b1.x + (int)threadIdx.x < b1.y) run = __ldg(runs + b1.x + threadIdx.x);
-        if (flags & SX_EDGE_PREFETCH) {
-            const unsigned char *Bb = reinterpret_cast<const unsigned char *>(B);
-            if ((run.y & 0xffff) != 0) bulk_prefetch_l2(Bb + (size_t)(uint32_t)run.x * rowbytes, (uint32_t)(run.y & 0xffff) * rowbytes);
-            for (int i = b1.x + 32 + (int)threadIdx.x; i < b1.y; i += 32) {
-                const int2 r = __ldg(runs + i);
-                bulk_prefetch_l2(Bb + (size_t)(uint32_t)r.x * rowbytes, (uint32_t)(r.y & 0xffff) * rowbytes);
-            }
-            if (threadIdx.x == 31 && b0.y > 0)
-                bulk_prefetch_l2(reinterpret_cast<const unsigned char *>(Cin) + (size_t)b0.x * ldcv * 16u, (uint32_t)b0.y * ldcv * 16u);
-        }
+    if (threadIdx.x == 0 && has) {
+        const uint64_t pol_a = policy_evict_first();
+        mbar_expect_tx(&bar, na * (uint32_t)(sizeof(T) + 2) + ncp * 4u);
+        tma_bulk_g2s(const_cast<int *>(scols), cols + b1.x, ncp * 4u, &bar, pol_a);
+        tma_bulk_g2s(const_cast<T *>(sval), val + jal, na * (uint32_t)sizeof(T), &bar, pol_a);
+        tma_bulk_g2s(const_cast<uint16_t *>(scol), lcol + jal, na * 2u, &bar, pol_a);
     }
     const int row = b0.x + rl;
     const bool mine = rl < b0.y && lg < nvec;
     int begin = 0, end = 0;
     if (mine) { begin = __ldg(rowptr + row); end = __ldg(rowptr + row + 1); }
+    const unsigned char *Bb = reinterpret_cast<const unsigned char *>(B) + lg * 16;
+    if (has) mbar_wait(&bar, 0);
+    if (flags & SX_EDGE_PREFETCH) {
+        if (lg * 16 < (int)rowbytes && (lg & 7) == 0)  // one prefetch per 128-byte line of a row
+            for (int lr = rl; lr < ncols; lr += ROWS) prefetch_l2(Bb + (size_t)(uint32_t)scols[lr] * rowbytes);
+        if (threadIdx.x == THREADS - 1 && b0.y > 0)
+            bulk_prefetch_l2(reinterpret_cast<const unsigned char *>(Cin) + (size_t)b0.x * ldcv * 16u, (uint32_t)b0.y * ldcv * 16u);
+    }
     // ---- B and C_in: only after the previous kernel is complete ----
     pdl_wait();
-    if (threadIdx.x < 32) {
-        if (ready != nullptr) {  // multi-GPU: the pushed B image of this step has landed
-            if (threadIdx.x == 0) {
-                const long long t0 = clock64();
-                while ((int)(ld_acquire_sys(ready) - step) < 0) {
-                    __nanosleep(32);
-                    if (clock64() - t0 > 4000000000ll) break;  // ~2 s: never hang the GPU on a lost peer
-                }
-                fence_proxy_async();
-            }
-            __syncwarp();
-        }
-        if (has) {
-            const uint64_t pol_b = policy_evict_last();
-            const unsigned char *Bb = reinterpret_cast<const unsigned char *>(B);
-            if (threadIdx.x == 0) mbar_expect_tx(&bar[1], wbytes);
-            __syncwarp();
-            if ((run.y & 0xffff) != 0)
-                tma_bulk_g2s(smem_raw + (size_t)((uint32_t)run.y >> 16) * rowbytes, Bb + (size_t)(uint32_t)run.x * rowbytes,
-                             (uint32_t)(run.y & 0xffff) * rowbytes, &bar[1], pol_b);
-            for (int i = b1.x + 32 + (int)threadIdx.x; i < b1.y; i += 32) {
-                const int2 r = __ldg(runs + i);
-                tma_bulk_g2s(smem_raw + (size_t)((uint32_t)r.y >> 16) * rowbytes, Bb + (size_t)(uint32_t)r.x * rowbytes,
-                             (uint32_t)(r.y & 0xffff) * rowbytes, &bar[1], pol_b);
+    uint32_t step = 0;
+    if (ready != nullptr) {  // multi-GPU: the pushed B image of this step has landed
+        if ((threadIdx.x & 31) == 0) {
+            step = *reinterpret_cast<volatile uint32_t *>(epoch) + 1u;  // advanced only after every block is done
+            const long long t0 = clock64();
+            while ((int)(ld_acquire_sys(ready) - step) < 0) {
+                __nanosleep(32);
+                if (clock64() - t0 > 4000000000ll) { atomicExch(sync_words + 1, 1u); break; }  // ~2 s: never hang the GPU on a lost peer
             }
         }
+        __syncwarp();
     }
+    if (lg < nvec)
+        for (int lr = rl; lr < ncols; lr += ROWS)
+            cp_async_16(win + ((size_t)lr * ldbv + lg) * 16, Bb + (size_t)(uint32_t)scols[lr] * rowbytes);
     V acc, cin;
     vzero(acc);
     vzero(cin);
     if (mine) cin = reinterpret_cast<const V *>(Cin)[(size_t)row * ldcv + lg];
+    cp_async_wait_all();
+    __syncthreads();
     if (mine) {
-        if (end > begin) {
-            mbar_wait(&bar[0], 0);
-            mbar_wait(&bar[1], 0);
-        }
         const T *sv = sval - jal;  // sv[j] = value of nonzero j
         const uint16_t *sc = scol - jal;
-        const V *w = win + lg;     // w[local column * ldbv] = this lane's piece of that B row
+        const V *w = reinterpret_cast<const V *>(win) + lg;  // w[local column * ldbv] = this lane's piece of that B row
         // chunks of 8 nonzeros, software-pipelined: the (column, value) pairs of chunk k+1 and the
         // eight B-row pieces of chunk k are in flight while the ordered chain of additions of chunk k runs
         constexpr int UC = 8;
@@ -818,12 +819,13 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int2 *__restrict__ r
         }
         reinterpret_cast<V *>(Cout)[(size_t)row * ldcv + lg] = vaxpby<STRICT>(alpha, acc, beta, cin);
     }
-    if (done_remote != nullptr) {  // multi-GPU: tell the pusher that this rank is done with the image
+    if (ready != nullptr) {  // multi-GPU: tell the pusher that this rank is done with the image
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
-            if (atomicAdd(done_counter, 1u) == gridDim.x - 1) {
-                *done_counter = 0;
+            if (atomicAdd(sync_words + 2, 1u) == gridDim.x - 1) {
+                sync_words[2] = 0;
+                *reinterpret_cast<volatile uint32_t *>(epoch) = step;
                 st_release_sys(done_remote, step);
             }
         }
@@ -1426,6 +1428,66 @@ pull_image_kernel(int4 *__restrict__ dst, const int4 *src, const int64_t n16, co
             __threadfence_system();
             *reinterpret_cast<volatile uint32_t *>(done_remote) = step;
         }
+    }
+}
+
+// ---- push of the B image to the other ranks: the exchange step of the row-block partition -----
+// The rank that holds B runs ONE kernel per exchange: wait until every peer has finished the SpMM
+// that used the previous contents of its image (done[p] >= *pushes, stored by the peer's SpMM
+// kernel), copy the local image into every peer's image with plain 16-byte stores through the
+// NVLink peer mappings (posted writes: no round trip), fence, and store *pushes + 1 into every
+// peer's ready flag from the last block to finish.  The peers launch nothing for the exchange:
+// their SpMM kernel waits on the flag (spmm_edgelist_kernel) or a one-warp kernel does
+// (wait_push_kernel).  The multi-GPU form of the reference's daisy chain that hands the B window
+// from PEG to PEG (src/sextans.cpp:909-941).  All counters are in device memory.
+struct PushList { int4 *dst[15]; uint32_t *ready[15]; };
+__global__ void __launch_bounds__(256)
+push_image_kernel(const int4 *__restrict__ src, const int64_t n16, const PushList peers, const int npeers,
+                  const uint32_t *done, uint32_t *pushes, unsigned int *sync_words) {
+    __shared__ uint32_t t_sh;
+    if (threadIdx.x == 0) {
+        const uint32_t t = *reinterpret_cast<volatile uint32_t *>(pushes);
+        const long long t0 = clock64();
+        for (int p = 0; p < npeers; ++p)
+            while ((int)(ld_acquire_sys(done + p) - t) < 0) {
+                __nanosleep(64);
+                if (clock64() - t0 > 4000000000ll) { atomicExch(sync_words + 1, 1u); break; }
+            }
+        t_sh = t;
+    }
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+        const int4 v = __ldg(src + i);
+        for (int p = 0; p < npeers; ++p) peers.dst[p][i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(sync_words + 3, 1u) == gridDim.x - 1) {
+            sync_words[3] = 0;
+            __threadfence_system();
+            for (int p = 0; p < npeers; ++p) st_release_sys(peers.ready[p], t_sh + 1u);
+            *reinterpret_cast<volatile uint32_t *>(pushes) = t_sh + 1u;
+        }
+    }
+}
+// the same handshake around the SpMM kernels that do not carry it themselves
+__global__ void wait_push_kernel(const uint32_t *ready, const uint32_t *epoch, unsigned int *sync_words) {
+    if (threadIdx.x == 0) {
+        const uint32_t step = *reinterpret_cast<const volatile uint32_t *>(epoch) + 1u;
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_sys(ready) - step) < 0) {
+            __nanosleep(64);
+            if (clock64() - t0 > 4000000000ll) { atomicExch(sync_words + 1, 1u); break; }
+        }
+    }
+}
+__global__ void ack_push_kernel(uint32_t *epoch, uint32_t *done_remote) {
+    if (threadIdx.x == 0) {
+        const uint32_t step = *reinterpret_cast<volatile uint32_t *>(epoch) + 1u;
+        *reinterpret_cast<volatile uint32_t *>(epoch) = step;
+        __threadfence_system();
+        st_release_sys(done_remote, step);
     }
 }
 

@@ -82,12 +82,12 @@ struct Plan {
 
 // Edge lists of spmm_edgelist_kernel (variant 5) for one B-row size: built on first use.
 struct EdgePlan {
-    int row_bytes = 0;
+    int row_bytes = 0, rows = 0;  // key: bytes of a B row, rows per block
     bool usable = false;  // planned, and staging a block's distinct B rows beats gathering per nonzero
-    int nblocks = 0, nruns = 0, max_smem = 0;
+    int nblocks = 0, max_smem = 0;
     int64_t total_cols = 0;
-    DevBuf blocks, runs, lcol;
-    void release() { blocks.release(); runs.release(); lcol.release(); }
+    DevBuf blocks, cols, lcol;
+    void release() { blocks.release(); cols.release(); lcol.release(); }
 };
 
 struct sx_ctx {
@@ -117,10 +117,9 @@ struct sx_ctx {
     int edge_max_cols = 0, edge_max_nnz = 0;
     std::vector<EdgePlan *> edge_plans;
     const EdgePlan *last_edge_plan = nullptr;
-    // multi-GPU exchange fused into the next SpMM launch (sx_spmm_expect_step; one-shot)
+    // multi-GPU exchange fused into the next SpMM launch (sx_spmm_expect_push; one-shot)
     const uint32_t *x_ready = nullptr;
-    uint32_t *x_done = nullptr;
-    uint32_t x_step = 0;
+    uint32_t *x_epoch = nullptr, *x_done = nullptr;
     std::vector<int32_t> h_rowptr;  // kept to re-derive segments when the option changes
     // variant 3: per block of 32 rows {first column, column span, nnz begin, nnz end}
     DevBuf wblocks;
@@ -200,9 +199,8 @@ int bind(sx_ctx *c) {
 int refresh_segments(sx_ctx *c);
 void release_child(sx_ctx *r, cudaStream_t stream);
 int get_plan(sx_ctx *c, int budget, Plan **out);
-int get_edge_plan(sx_ctx *c, int row_bytes, int elem_bytes, const EdgePlan **out);
-int stream_wait_flag(sx_ctx *c, const void *flag, uint32_t value);
-int stream_write_flag(sx_ctx *c, void *flag, uint32_t value);
+int get_edge_plan(sx_ctx *c, int row_bytes, int elem_bytes, int rows, const EdgePlan **out);
+int ensure_sync_words(sx_ctx *c);
 int pick_budget(const sx_ctx *c, int G);
 template <typename T, int G> int pick_tile(int U);
 
@@ -255,19 +253,20 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
     if constexpr (G <= 16 && VPL == 1) {
         if ((c->kernel == 0 || c->kernel == 5) && !c->win_mode && c->M > 0) {
             const EdgePlan *ep = nullptr;
-            if ((rc = get_edge_plan(c, (int)(ldb * sizeof(T)), (int)sizeof(T), &ep))) return rc;
+            if ((rc = get_edge_plan(c, (int)(ldb * sizeof(T)), (int)sizeof(T), sx::EdgeShape<G>::ROWS, &ep))) return rc;
             if (ep && ep->usable && ldb == ldc) {
                 constexpr int E = sx::VecOf<T>::E;
                 auto kern = sx::spmm_edgelist_kernel<T, G, STRICT>;
                 if (ep->max_smem > 48 * 1024 &&
                     std::find(c->big_smem_ok.begin(), c->big_smem_ok.end(), (const void *)kern) == c->big_smem_ok.end()) {
-                    SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64));
+                    // the opt-in limit is 227 KB minus the kernel's static shared memory (its two mbarriers)
+                    SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
                     c->big_smem_ok.push_back((const void *)kern);
                 }
                 const bool pf = c->prefetch != 0;
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = dim3((unsigned)ep->nblocks);
-                cfg.blockDim = dim3(32 * G);
+                cfg.blockDim = dim3(sx::EdgeShape<G>::THREADS);
                 cfg.dynamicSmemBytes = (size_t)std::max(ep->max_smem, 16);
                 cfg.stream = c->stream;
                 cudaLaunchAttribute at[1];
@@ -275,21 +274,13 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
                 at[0].val.programmaticStreamSerializationAllowed = 1;
                 cfg.attrs = at;
                 cfg.numAttrs = c->pdl != 0 ? 1 : 0;
-                unsigned int *counter = nullptr;
-                if (c->x_done) {
-                    if ((rc = c->sync_words.ensure(16))) return rc;
-                    if (!c->sync_words_zeroed) {
-                        SX_CUDA(cudaMemsetAsync(c->sync_words.p, 0, 16, c->stream));
-                        c->sync_words_zeroed = true;
-                    }
-                    counter = (unsigned int *)c->sync_words.p + 2;
-                }
-                SX_CUDA(cudaLaunchKernelEx(&cfg, kern, (const int4 *)ep->blocks.p, (const int2 *)ep->runs.p,
+                if (c->x_ready && (rc = ensure_sync_words(c))) return rc;
+                SX_CUDA(cudaLaunchKernelEx(&cfg, kern, (const int4 *)ep->blocks.p, (const int *)ep->cols.p,
                                            (const int *)c->rowptr.p, (const uint16_t *)ep->lcol.p, (const T *)c->val.p, dB,
                                            (uint32_t)(ldb / E), dCin, dCout, (uint32_t)(ldc / E), alpha, beta, nvec,
-                                           pf ? sx::SX_EDGE_PREFETCH : 0, c->x_ready, c->x_step, counter, c->x_done));
+                                           pf ? sx::SX_EDGE_PREFETCH : 0, c->x_ready, c->x_epoch, c->x_done,
+                                           (unsigned int *)c->sync_words.p));
                 c->x_ready = nullptr;
-                c->x_done = nullptr;
                 c->launches++;
                 c->last_edge_plan = ep;
                 c->last_kernel = 80000 + G * 100 + VPL * 10 + (STRICT ? 0 : 1);
@@ -298,15 +289,20 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
             }
         }
     }
-    // the other kernels do not carry the multi-GPU step flags: stream memory operations around them
-    struct FlagGuard {
-        sx_ctx *c; const uint32_t *ready; uint32_t *done; uint32_t step;
-        ~FlagGuard() { if (done) stream_write_flag(c, done, step); }
-    } guard{c, c->x_ready, c->x_done, c->x_step};
+    // the other kernels do not carry the multi-GPU handshake: a one-warp kernel before and after
+    struct PushGuard {
+        sx_ctx *c; const uint32_t *ready; uint32_t *epoch, *done;
+        ~PushGuard() {
+            if (ready) { sx::ack_push_kernel<<<1, 32, 0, c->stream>>>(epoch, done); c->launches++; }
+        }
+    } guard{c, c->x_ready, c->x_epoch, c->x_done};
     c->x_ready = nullptr;
-    c->x_done = nullptr;
-    if (guard.ready && (rc = stream_wait_flag(c, guard.ready, guard.step))) return rc;
-    int variant = (c->kernel != 0 && c->kernel != 4) ? c->kernel : (window_auto ? 3 : (sub_wave ? 1 : 2));
+    if (guard.ready) {
+        if ((rc = ensure_sync_words(c))) return rc;
+        sx::wait_push_kernel<<<1, 32, 0, c->stream>>>(guard.ready, guard.epoch, (unsigned int *)c->sync_words.p);
+        c->launches++;
+    }
+    int variant = (c->kernel >= 1 && c->kernel <= 3) ? c->kernel : (window_auto ? 3 : (sub_wave ? 1 : 2));  // 4 and 5 were tried above
     if (variant == 3 && !window_ok) variant = sub_wave ? 1 : 2;
     if (c->win_mode) variant = 2;  // a column-window pass: only the staged kernel carries running sums
     // SX_OPT_KERNEL = 4 (experimental): the sliding-window kernel, where a plan exists and fits
@@ -806,6 +802,18 @@ void edge_screen(sx_ctx *c, int M, int K, const int32_t *rowptr, const int32_t *
     if (entries > 0) c->edge_cols_per_nnz = (double)distinct / (double)entries;
 }
 
+// [0] block counter of pull_image_kernel, [1] time-out flag of every flag wait, [2] block counter of
+// spmm_edgelist_kernel's acknowledgement, [3] block counter of push_image_kernel
+int ensure_sync_words(sx_ctx *c) {
+    int rc = c->sync_words.ensure(16);
+    if (rc) return rc;
+    if (!c->sync_words_zeroed) {
+        SX_CUDA(cudaMemsetAsync(c->sync_words.p, 0, 16, c->stream));
+        c->sync_words_zeroed = true;
+    }
+    return SX_OK;
+}
+
 void drop_edge_plans(sx_ctx *c) {
     for (EdgePlan *p : c->edge_plans) { p->release(); delete p; }
     c->edge_plans.clear();
@@ -814,57 +822,57 @@ void drop_edge_plans(sx_ctx *c) {
 
 // Shared memory a block may use so that k blocks share an SM (228 KB per SM, 1 KB reserved per
 // block, the kernel's static 16 bytes).
-int edge_budget(int k) { return (233472 / k - 1024 - 64) & ~127; }
+int edge_budget(int k) { return k == 1 ? 227 * 1024 - 1024 : (233472 / k - 1024 - 128) & ~127; }
 
-int get_edge_plan(sx_ctx *c, int row_bytes, int elem_bytes, const EdgePlan **out) {
+int get_edge_plan(sx_ctx *c, int row_bytes, int elem_bytes, int rows, const EdgePlan **out) {
     *out = nullptr;
     for (EdgePlan *p : c->edge_plans)
-        if (p->row_bytes == row_bytes) { *out = p; return SX_OK; }
+        if (p->row_bytes == row_bytes && p->rows == rows) { *out = p; return SX_OK; }
     EdgePlan *p = new (std::nothrow) EdgePlan();
     if (!p) return fail(SX_ERR_NOMEM, "out of host memory");
     p->row_bytes = row_bytes;
+    p->rows = rows;
     c->edge_plans.push_back(p);
     *out = p;
     // staging pays when a staged B row serves at least two nonzeros (forced with SX_OPT_KERNEL = 5:
     // any matrix that can be planned)
     if (c->nnz == 0 || (c->kernel != 5 && c->edge_cols_per_nnz > 0.5)) return SX_OK;
-    // blocks per SM: as many as the largest sampled group allows (with 10 % headroom), at most 6
-    const int64_t need = ((int64_t)c->edge_max_cols * row_bytes + ((int64_t)c->edge_max_nnz + 16) * (elem_bytes + 2)) * 11 / 10;
-    int k = 6;
-    while (k > 1 && edge_budget(k) < need) --k;
-    if (k == 5) k = 4;
     std::vector<int32_t> ci((size_t)c->nnz);
     SX_CUDA(cudaMemcpyAsync(ci.data(), c->colidx.p, (size_t)c->nnz * 4, cudaMemcpyDeviceToHost, c->stream));
     SX_CUDA(cudaStreamSynchronize(c->stream));
-    int nb = 0, nr = 0, max_smem = 0;
-    int32_t *blocks = nullptr, *runs = nullptr;
+    // four blocks per SM if (almost) every group of `rows` rows fits that budget uncut, else two, else one
+    const int ngroups = (c->M + rows - 1) / rows;
+    int nb = 0, max_smem = 0, rc = SX_OK;
+    int32_t *blocks = nullptr, *cols = nullptr;
     uint16_t *lcol = nullptr;
-    int64_t total = 0;
-    int rc = sx_plan_edge_lists(c->M, c->K, c->h_rowptr.data(), ci.data(), row_bytes, elem_bytes, edge_budget(k), &nb,
-                                &blocks, &nr, &runs, &lcol, &total, &max_smem);
-    if (!rc && nb == 0 && k > 1)  // some row is larger than the sample suggested: one block per SM
-        rc = sx_plan_edge_lists(c->M, c->K, c->h_rowptr.data(), ci.data(), row_bytes, elem_bytes, edge_budget(1), &nb,
-                                &blocks, &nr, &runs, &lcol, &total, &max_smem);
-    if (rc) return rc;
+    int64_t total = 0, ncols = 0;
+    for (int k : {4, 2, 1}) {
+        sx_free(blocks); sx_free(cols); sx_free(lcol);
+        blocks = cols = nullptr;
+        lcol = nullptr;
+        rc = sx_plan_edge_lists(c->M, c->K, c->h_rowptr.data(), ci.data(), row_bytes, elem_bytes, rows, edge_budget(k), &nb,
+                                &blocks, &ncols, &cols, &lcol, &total, &max_smem);
+        if (rc) return rc;
+        if (nb > 0 && (int64_t)nb * 4 <= (int64_t)ngroups * 5) break;
+    }
     if (nb > 0 && (c->kernel == 5 || total * 2 <= c->nnz)) {
-        if (!(rc = p->blocks.ensure((size_t)nb * 32)) && !(rc = p->runs.ensure(std::max<size_t>((size_t)nr * 8, 16))) &&
+        if (!(rc = p->blocks.ensure((size_t)nb * 32)) && !(rc = p->cols.ensure(std::max<size_t>((size_t)ncols * 4, 16))) &&
             !(rc = p->lcol.ensure((size_t)c->nnz * 2 + 64))) {
             if (cudaMemcpyAsync(p->blocks.p, blocks, (size_t)nb * 32, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
-                (nr > 0 && cudaMemcpyAsync(p->runs.p, runs, (size_t)nr * 8, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) ||
+                (ncols > 0 && cudaMemcpyAsync(p->cols.p, cols, (size_t)ncols * 4, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) ||
                 cudaMemcpyAsync(p->lcol.p, lcol, (size_t)c->nnz * 2, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
                 cudaStreamSynchronize(c->stream) != cudaSuccess)
                 rc = fail(SX_ERR_CUDA, "edge-list plan upload failed");
         }
         if (!rc) {
             p->nblocks = nb;
-            p->nruns = nr;
             p->max_smem = max_smem;
             p->total_cols = total;
             p->usable = true;
         }
     }
     sx_free(blocks);
-    sx_free(runs);
+    sx_free(cols);
     sx_free(lcol);
     return rc;
 }
@@ -1681,6 +1689,20 @@ int sx_get_info(sx_ctx *c, int what, int64_t *value) {
         }
         case SX_INFO_COL_WINDOWS: *value = (int64_t)c->wins.size(); return SX_OK;
         case SX_INFO_UPLOAD_SERIAL: *value = c->has_A ? c->upload_serial : 0; return SX_OK;
+        case SX_INFO_EXCHANGE_TIMEOUTS: {
+            *value = 0;
+            if (c->sync_words.p && c->sync_words_zeroed) {
+                int rc = bind(c);
+                if (rc) return rc;
+                unsigned int w = 0;
+                SX_CUDA(cudaStreamSynchronize(c->stream));
+                SX_CUDA(cudaMemcpy(&w, (const unsigned int *)c->sync_words.p + 1, 4, cudaMemcpyDeviceToHost));
+                *value = w;
+            }
+            return SX_OK;
+        }
+        case SX_INFO_EDGE_BLOCKS: *value = c->last_edge_plan ? c->last_edge_plan->nblocks : 0; return SX_OK;
+        case SX_INFO_EDGE_COLS: *value = c->last_edge_plan ? c->last_edge_plan->total_cols : 0; return SX_OK;
         default: return fail(SX_ERR_INVALID, "unknown info id %d", what);
     }
 }
@@ -1813,14 +1835,6 @@ int stream_value32(const char *name, sx_ctx *c, void *flag, uint32_t value, unsi
     if (r != CUDA_SUCCESS) return fail(SX_ERR_CUDA, "%s failed with CUresult %d", name, (int)r);
     return SX_OK;
 }
-extern "C++" {
-int stream_wait_flag(sx_ctx *c, const void *flag, uint32_t value) {
-    return stream_value32("cuStreamWaitValue32", c, const_cast<void *>(flag), value, CU_STREAM_WAIT_VALUE_GEQ);
-}
-int stream_write_flag(sx_ctx *c, void *flag, uint32_t value) {
-    return stream_value32("cuStreamWriteValue32", c, flag, value, CU_STREAM_WRITE_VALUE_DEFAULT);
-}
-}
 }  // namespace
 
 int sx_flag_write(sx_ctx *c, void *flag, uint32_t value) {
@@ -1870,6 +1884,40 @@ int sx_pull_B_fused(sx_ctx *c, int N, const void *peer_B_image, const void *read
     sx::pull_image_kernel<<<grid, 256, 0, c->stream>>>((int4 *)mine, (const int4 *)peer_B_image, n16,
                                                        (const uint32_t *)ready_flag, step, (uint32_t *)done_flag,
                                                        (unsigned int *)c->sync_words.p, (int *)c->sync_words.p + 1);
+    c->launches++;
+    SX_CUDA(cudaGetLastError());
+    return SX_OK;
+}
+
+int sx_spmm_expect_push(sx_ctx *c, const void *ready_flag, void *epoch_counter, void *done_flag) {
+    if (!c) return fail(SX_ERR_INVALID, "null context");
+    if (!ready_flag || !epoch_counter || !done_flag) return fail(SX_ERR_INVALID, "null flag");
+    c->x_ready = (const uint32_t *)ready_flag;
+    c->x_epoch = (uint32_t *)epoch_counter;
+    c->x_done = (uint32_t *)done_flag;
+    return SX_OK;
+}
+
+int sx_push_B(sx_ctx *c, int N, void *const *peer_images, void *const *peer_ready_flags, int npeers, const void *done_flags,
+              void *pushes_counter) {
+    void *mine = nullptr;
+    size_t bytes = 0;
+    int rc = sx_device_B(c, N, &mine, &bytes);
+    if (rc) return rc;
+    if (npeers < 0 || npeers > 15) return fail(SX_ERR_INVALID, "0..15 peers expected (got %d)", npeers);
+    if (npeers == 0) return SX_OK;
+    if (!peer_images || !peer_ready_flags || !done_flags || !pushes_counter) return fail(SX_ERR_INVALID, "null argument");
+    if ((rc = ensure_sync_words(c))) return rc;
+    sx::PushList pl = {};
+    for (int i = 0; i < npeers; ++i) {
+        if (!peer_images[i] || !peer_ready_flags[i]) return fail(SX_ERR_INVALID, "null peer pointer");
+        pl.dst[i] = (int4 *)peer_images[i];
+        pl.ready[i] = (uint32_t *)peer_ready_flags[i];
+    }
+    const int64_t n16 = (int64_t)((bytes + 15) / 16);  // images are allocated in whole 16-byte units
+    const int grid = (int)std::min<int64_t>(c->sm_count, std::max<int64_t>(1, (n16 + 255) / 256));
+    sx::push_image_kernel<<<grid, 256, 0, c->stream>>>((const int4 *)mine, n16, pl, npeers, (const uint32_t *)done_flags,
+                                                       (uint32_t *)pushes_counter, (unsigned int *)c->sync_words.p);
     c->launches++;
     SX_CUDA(cudaGetLastError());
     return SX_OK;

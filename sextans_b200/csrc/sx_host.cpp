@@ -632,45 +632,44 @@ int sx_plan_slide(int M, const int32_t *rowptr, const int32_t *colidx, int nchai
 // windows of 4096 columns and stores every nonzero of a PE as a packed word whose column field
 // is LOCAL to the window (14 bits; src/sparse_helper.h:419-443, src/sextans.cpp:398-402), so
 // that the PE indexes its on-chip copy of the B window directly.  The GPU analogue: a row
-// block (up to 32 consecutive rows, one thread block) stages exactly the B rows its nonzeros
-// touch -- the block's DISTINCT columns, in ascending order -- into shared memory, and every
-// nonzero carries a 16-bit index into that compacted window.  On FEM-type matrices a block's
-// distinct columns are a handful of contiguous runs (nasa4704: 142 columns in 7 runs per 32
-// rows, against a 456-column span), so the window arrives as a few TMA bulk copies and holds a
-// third of the bytes of the contiguous span.
-//   blocks  8 ints per block: {row_begin, nrows, nnz_begin, nnz_end, run_begin, run_end, ncols, smem_bytes}
-//   runs    2 ints per run:   {first column, (first local index << 16) | length}; a run is at most
-//           max(1, 16384 / row_bytes) columns, so that one bulk copy is at most 16 KB
+// block (up to rows_per_block consecutive rows, one thread block) stages exactly the B rows
+// its nonzeros touch -- the block's DISTINCT columns, in ascending order -- into shared memory,
+// and every nonzero carries a 16-bit index into that compacted window.  On FEM-type matrices
+// that is a third of the contiguous column span (nasa4704: 142 distinct columns per 32 rows
+// against a span of 456; pcrystk02: 317 against 918).
+//   blocks  8 ints per block: {row_begin, nrows, nnz_begin, nnz_end, col_begin, ncols, 0, smem_bytes}
+//   cols    the blocks' column lists, back to back, each starting at a multiple of 4 entries
+//           (16 bytes: the list travels to shared memory by TMA); pad entries repeat the last column
 //   lcol    nnz 16-bit local column indices, parallel to colidx
-// A 32-row group that does not fit the shared-memory budget is cut into shorter blocks; a
-// single row that does not fit makes the matrix unplannable (*nblocks = 0, SX_OK).
+// A group of rows_per_block rows that does not fit the shared-memory budget is cut into shorter
+// blocks; a single row that does not fit makes the matrix unplannable (*nblocks = 0, SX_OK).
 int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colidx, int row_bytes, int elem_bytes,
-                       int smem_budget, int *nblocks_out, int32_t **blocks_out, int *nruns_out, int32_t **runs_out,
-                       uint16_t **lcol_out, int64_t *total_cols_out, int *max_smem_out) {
-    if (!nblocks_out || !blocks_out || !nruns_out || !runs_out || !lcol_out || !total_cols_out || !max_smem_out) {
+                       int rows_per_block, int smem_budget, int *nblocks_out, int32_t **blocks_out, int64_t *ncols_out,
+                       int32_t **cols_out, uint16_t **lcol_out, int64_t *total_cols_out, int *max_smem_out) {
+    if (!nblocks_out || !blocks_out || !ncols_out || !cols_out || !lcol_out || !total_cols_out || !max_smem_out) {
         sx_internal_set_error("sx_plan_edge_lists: null output pointer");
         return SX_ERR_INVALID;
     }
-    *nblocks_out = *nruns_out = *max_smem_out = 0;
-    *total_cols_out = 0;
-    *blocks_out = *runs_out = nullptr;
+    *nblocks_out = *max_smem_out = 0;
+    *ncols_out = *total_cols_out = 0;
+    *blocks_out = *cols_out = nullptr;
     *lcol_out = nullptr;
     if (M < 0 || K < 0 || !rowptr || (M > 0 && rowptr[M] > 0 && !colidx) || row_bytes < 16 || row_bytes % 16 ||
-        (elem_bytes != 4 && elem_bytes != 8) || smem_budget < 1024) {
+        (elem_bytes != 4 && elem_bytes != 8) || smem_budget < 1024 || rows_per_block < 1 || rows_per_block > 1024) {
         sx_internal_set_error("sx_plan_edge_lists: bad argument");
         return SX_ERR_INVALID;
     }
     if (M == 0) return SX_OK;
+    const int RB = rows_per_block;
     const int64_t nnz = rowptr[M];
-    const int ngroups = (M + 31) / 32;
-    const int max_run = std::max(1, 16384 / row_bytes);
-    // shared memory of a block: window | values | local columns (the A slice starts at the
-    // 8-entry boundary at or below nnz_begin, so that both streams are whole 16-byte units)
+    const int ngroups = (M + RB - 1) / RB;
+    // shared memory of a block: window | values | local columns | column list (the A slice starts at
+    // the 8-entry boundary at or below nnz_begin, so that both streams are whole 16-byte units)
     auto smem_of = [&](int ncols, int jb, int je) -> int64_t {
         const int64_t na = je > jb ? (int64_t)((je - (jb & ~7) + 7) & ~7) : 0;
-        return (int64_t)ncols * row_bytes + na * elem_bytes + na * 2;
+        return (int64_t)ncols * row_bytes + na * elem_bytes + na * 2 + (int64_t)((ncols + 3) & ~3) * 4;
     };
-    struct Part { std::vector<int32_t> blocks, runs; int64_t cols = 0; int max_smem = 0; bool ok = true; };
+    struct Part { std::vector<int32_t> blocks, cols; int64_t total = 0; int max_smem = 0; bool ok = true; };
     const unsigned nt = (unsigned)std::min<int64_t>(nnz < (1 << 18) ? 1 : std::min(sxhost::host_threads(), 16u), ngroups);  // 6 bytes x K of scratch per thread
     std::vector<Part> parts(nt);
     uint16_t *lcol = (uint16_t *)std::malloc(std::max<size_t>((size_t)nnz, 8) * sizeof(uint16_t));
@@ -682,8 +681,8 @@ int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colid
         int32_t tag = 0;
         const int g0 = (int)((int64_t)ngroups * t / nt), g1 = (int)((int64_t)ngroups * (t + 1) / nt);
         for (int g = g0; g < g1 && P.ok; ++g) {
-            const int gend = std::min(M, g * 32 + 32);
-            int r = g * 32;
+            const int gend = (int)std::min<int64_t>(M, (int64_t)g * RB + RB);
+            int r = g * RB;
             while (r < gend) {
                 // greedy: rows r.. while the block still fits
                 const int rb = r;
@@ -706,56 +705,49 @@ int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colid
                 if (!P.ok) break;
                 const int je = rowptr[r];
                 std::sort(cols.begin(), cols.end());
-                const int run_begin = (int)(P.runs.size() / 2);
-                for (int i = 0; i < ncols;) {
-                    int e = i + 1;
-                    while (e < ncols && e - i < max_run && cols[e] == cols[e - 1] + 1) ++e;
-                    P.runs.push_back(cols[i]);
-                    P.runs.push_back((int32_t)(((uint32_t)i << 16) | (uint32_t)(e - i)));
-                    i = e;
-                }
                 for (int i = 0; i < ncols; ++i) local[cols[i]] = (uint16_t)i;
                 for (int32_t j = jb; j < je; ++j) lcol[j] = local[colidx[j]];
                 const int sm = (int)smem_of(ncols, jb, je);
-                P.blocks.insert(P.blocks.end(), {rb, r - rb, jb, je, run_begin, (int)(P.runs.size() / 2), ncols, sm});
-                P.cols += ncols;
+                P.blocks.insert(P.blocks.end(), {rb, r - rb, jb, je, (int32_t)P.cols.size(), ncols, 0, sm});
+                P.cols.insert(P.cols.end(), cols.begin(), cols.end());
+                while (P.cols.size() % 4) P.cols.push_back(ncols ? cols.back() : 0);
+                P.total += ncols;
                 P.max_smem = std::max(P.max_smem, sm);
             }
         }
     });
     bool ok = true;
-    size_t nb = 0, nr = 0;
-    for (const Part &P : parts) { ok = ok && P.ok; nb += P.blocks.size() / 8; nr += P.runs.size() / 2; }
-    if (!ok || nb > (size_t)INT32_MAX || nr > (size_t)INT32_MAX) {
+    size_t nb = 0, nc = 0;
+    for (const Part &P : parts) { ok = ok && P.ok; nb += P.blocks.size() / 8; nc += P.cols.size(); }
+    if (!ok || nb > (size_t)INT32_MAX || nc > (size_t)INT32_MAX) {
         std::free(lcol);
         return SX_OK;  // not plannable with this budget: the caller keeps its other kernels
     }
     int32_t *blocks = (int32_t *)std::malloc(std::max<size_t>(nb, 1) * 8 * sizeof(int32_t));
-    int32_t *runs = (int32_t *)std::malloc(std::max<size_t>(nr, 1) * 2 * sizeof(int32_t));
-    if (!blocks || !runs) {
-        std::free(blocks); std::free(runs); std::free(lcol);
+    int32_t *cols = (int32_t *)std::malloc(std::max<size_t>(nc, 4) * sizeof(int32_t));
+    if (!blocks || !cols) {
+        std::free(blocks); std::free(cols); std::free(lcol);
         sx_internal_set_error("sx_plan_edge_lists: out of host memory");
         return SX_ERR_NOMEM;
     }
-    size_t bo = 0, ro = 0;
+    size_t bo = 0, co = 0;
     int64_t total = 0;
     int max_smem = 0;
     for (const Part &P : parts) {
         for (size_t i = 0; i < P.blocks.size(); i += 8) {
             std::copy(P.blocks.begin() + i, P.blocks.begin() + i + 8, blocks + (bo + i));
-            blocks[bo + i + 4] += (int32_t)ro;  // run indices become global
-            blocks[bo + i + 5] += (int32_t)ro;
+            blocks[bo + i + 4] += (int32_t)co;  // column-list offsets become global
         }
-        std::copy(P.runs.begin(), P.runs.end(), runs + 2 * ro);
+        std::copy(P.cols.begin(), P.cols.end(), cols + co);
         bo += P.blocks.size();
-        ro += P.runs.size() / 2;
-        total += P.cols;
+        co += P.cols.size();
+        total += P.total;
         max_smem = std::max(max_smem, P.max_smem);
     }
     *nblocks_out = (int)nb;
     *blocks_out = blocks;
-    *nruns_out = (int)nr;
-    *runs_out = runs;
+    *ncols_out = (int64_t)nc;
+    *cols_out = cols;
     *lcol_out = lcol;
     *total_cols_out = total;
     *max_smem_out = max_smem;

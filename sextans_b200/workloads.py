@@ -71,13 +71,10 @@ def uniform_csr(M, K, per_row, seed=12345, dtype=np.float32):
     return rowptr, cols.ravel(), val
 
 
-def powerlaw_csr(M, K, nnz, seed=12345, dtype=np.float64, exponent=2.0, col_skew=2.0):
-    """Row lengths ~ Pareto(exponent) (min 1, cap K/4) rescaled towards ``nnz`` in total;
-    columns follow a power law over a fixed random permutation of [0, K) (hub columns),
-    de-duplicated and ascending inside a row; values uniform(-1, 1).  The returned nnz is
-    what is left after de-duplication (a few per cent below the request).
-    (C5: M = K = 1e6, nnz = 1e8.)"""
-    rng = np.random.default_rng(seed)
+def _powerlaw_keys(rng, M, K, nnz, exponent, col_skew, perm):
+    """Sorted unique keys row*K + col of a power-law matrix with about ``nnz`` entries before
+    de-duplication: row lengths ~ Pareto(exponent) (min 1, cap K/4) rescaled to ``nnz``, columns
+    ~ u**col_skew over the permutation (hub columns)."""
     raw = (1.0 - rng.random(M)) ** (-1.0 / (exponent - 1.0))        # Pareto, x_min = 1
     cap = max(1, K // 4)
     lens = np.minimum(raw, cap)
@@ -92,7 +89,6 @@ def powerlaw_csr(M, K, nnz, seed=12345, dtype=np.float64, exponent=2.0, col_skew
     total = int(lens.sum())
     rows = np.repeat(np.arange(M, dtype=np.int64), lens)
     u = rng.random(total)
-    perm = rng.permutation(K).astype(np.int64)
     cols = perm[np.minimum((K * u ** col_skew).astype(np.int64), K - 1)]
     key = rows * K + cols
     del rows, cols, u
@@ -100,7 +96,31 @@ def powerlaw_csr(M, K, nnz, seed=12345, dtype=np.float64, exponent=2.0, col_skew
     keep = np.empty(total, dtype=bool)
     keep[0:1] = True
     np.not_equal(key[1:], key[:-1], out=keep[1:])
-    key = key[keep]
+    return key[keep]
+
+
+def _trim_keys(rng, key, K, target, protect=None):
+    """Drop random entries until exactly ``target`` are left; never a row's first entry (so no
+    row becomes empty) and never an entry flagged in ``protect``."""
+    surplus = key.size - target
+    if surplus <= 0:
+        return key
+    free = np.empty(key.size, dtype=bool)
+    free[0:1] = False
+    np.not_equal(key[1:] // K, key[:-1] // K, out=free[1:])
+    np.logical_not(free, out=free)                                   # free = not the first entry of its row
+    if protect is not None:
+        free &= ~protect
+    cand = np.flatnonzero(free)
+    if cand.size < surplus:
+        raise ValueError("cannot trim to the requested number of nonzeros")
+    drop = rng.choice(cand, size=surplus, replace=False)
+    keep = np.ones(key.size, dtype=bool)
+    keep[drop] = False
+    return key[keep]
+
+
+def _keys_to_csr(rng, key, M, K, dtype):
     rows = key // K
     colidx = (key - rows * K).astype(np.int32)
     rowptr = np.zeros(M + 1, dtype=np.int64)
@@ -108,6 +128,55 @@ def powerlaw_csr(M, K, nnz, seed=12345, dtype=np.float64, exponent=2.0, col_skew
     val = rng.random(colidx.size).astype(dtype)
     val *= 2; val -= 1
     return rowptr.astype(np.int32), colidx, val
+
+
+def powerlaw_csr(M, K, nnz, seed=12345, dtype=np.float64, exponent=2.0, col_skew=2.0, oversample=1.06):
+    """EXACTLY ``nnz`` nonzeros ("rescaled to hit nnz exactly"): row lengths ~
+    Pareto(exponent) (min 1, cap K/4); columns follow a power law over a fixed random
+    permutation of [0, K) (hub columns), de-duplicated and ascending inside a row; values
+    uniform(-1, 1).  The draw asks for ``oversample`` x nnz entries (de-duplication of the hub
+    columns removes ~4 % at C5's size), more if that is not enough, and random surplus entries
+    are then dropped.  (C5: M = K = 1e6, nnz = 1e8.)"""
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(K).astype(np.int64)
+    nnz = int(min(nnz, M * (K // 4) if K >= 4 else M))
+    ask = oversample
+    key = _powerlaw_keys(rng, M, K, int(nnz * ask), exponent, col_skew, perm)
+    while key.size < nnz:                                            # very dense requests only
+        ask *= 1.25
+        key = _powerlaw_keys(rng, M, K, int(nnz * ask), exponent, col_skew, perm)
+    key = _trim_keys(rng, key, K, nnz)
+    return _keys_to_csr(rng, key, M, K, dtype)
+
+
+def powerlaw_blocked_csr(M, K, nnz, seed=12345, dtype=np.float64, block=16, block_frac=0.25,
+                         exponent=2.0, col_skew=2.0):
+    """C5's blocked sub-case: the power-law matrix with dense ``block`` x
+    ``block`` sub-blocks planted so that they hold ``block_frac`` of the EXACTLY ``nnz``
+    nonzeros -- what a blocked-ELL / dense-tile variant can find.  Blocks start at rows that are
+    multiples of ``block`` and at arbitrary columns (a block covers ``block`` consecutive
+    columns); the rest is powerlaw_csr's pattern.  Returns (rowptr, colidx, val, planted_nnz)."""
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(K).astype(np.int64)
+    nblocks = int(nnz * block_frac) // (block * block)
+    br = rng.integers(0, max(1, M // block), size=nblocks, dtype=np.int64) * block
+    bc = rng.integers(0, max(1, K - block + 1), size=nblocks, dtype=np.int64)
+    rr = (br[:, None, None] + np.arange(block, dtype=np.int64)[None, :, None])
+    cc = (bc[:, None, None] + np.arange(block, dtype=np.int64)[None, None, :])
+    planted = np.unique((rr * K + cc).ravel())
+    del rr, cc
+    rest = nnz - planted.size
+    ask = 1.08
+    while True:
+        key = _powerlaw_keys(rng, M, K, int(rest * ask), exponent, col_skew, perm)
+        key = np.union1d(key, planted)
+        if key.size >= nnz:
+            break
+        ask *= 1.25
+    protect = np.isin(key, planted, assume_unique=True)
+    key = _trim_keys(rng, key, K, nnz, protect=protect)
+    rp, ci, v = _keys_to_csr(rng, key, M, K, dtype)
+    return rp, ci, v, int(planted.size)
 
 
 def fem_like_csr(nodes, dof, nbrs, seed=12345, dtype=np.float64, band=2000, noise_per_row=0):

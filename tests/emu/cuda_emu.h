@@ -136,4 +136,5 @@ inline void __nanosleep(unsigned) {}
 inline void __threadfence() {}
 inline void __threadfence_system() {}
 inline unsigned atomicAdd(unsigned *p, unsigned v) { return std::atomic_ref<unsigned>(*p).fetch_add(v); }
+inline unsigned atomicExch(unsigned *p, unsigned v) { return std::atomic_ref<unsigned>(*p).exchange(v); }
 inline size_t __cvta_generic_to_shared(const void *p) { return reinterpret_cast<size_t>(p); }

@@ -61,3 +61,11 @@ __device__ __forceinline__ void pdl_launch_dependents() {}
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) { return std::atomic_ref<const uint32_t>(*p).load(); }
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) { std::atomic_ref<uint32_t>(*p).store(v); }
 __device__ __forceinline__ void fence_proxy_async() {}
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc) {
+    if (reinterpret_cast<uintptr_t>(smem_dst) % 16 || reinterpret_cast<uintptr_t>(gsrc) % 16) {
+        std::fprintf(stderr, "emu: cp.async of 16 bytes not 16-byte aligned\n");
+        std::abort();
+    }
+    std::memcpy(smem_dst, gsrc, 16);
+}
+__device__ __forceinline__ void cp_async_wait_all() {}

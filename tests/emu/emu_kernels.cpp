@@ -23,8 +23,8 @@ extern "C" {  // host-side planner of the product (libsextans_b200.so; no GPU ne
 int sx_plan_slide(int M, const int32_t *rowptr, const int32_t *colidx, int nchains_wanted, int *nsteps, int32_t **steps,
                   int *nchains, int32_t **chains, int *ring_rows, int *max_step_entries);
 int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colidx, int row_bytes, int elem_bytes,
-                       int smem_budget, int *nblocks, int32_t **blocks, int *nruns, int32_t **runs, uint16_t **lcol,
-                       int64_t *total_cols, int *max_smem);
+                       int rows_per_block, int smem_budget, int *nblocks, int32_t **blocks, int64_t *ncols, int32_t **cols,
+                       uint16_t **lcol, int64_t *total_cols, int *max_smem);
 void sx_free(void *);
 }
 
@@ -598,12 +598,13 @@ void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, u
     for (int64_t i = 0; i < (int64_t)M * ld; ++i) Cin.p[i] = (i % ld) < N ? (T)U(rng) : (T)0;
     const T alpha = (T)0.85f, beta = (T)-2.06f;
     reference<T>(a, hval, N, B.p, ld, alpha, beta, Cin.p, Ref.p, ld);
-    int nb = 0, nr = 0, max_smem = 0;
-    int32_t *blocks = nullptr, *runs = nullptr;
+    constexpr int ROWS = sx::EdgeShape<G>::ROWS, THREADS = sx::EdgeShape<G>::THREADS;
+    int nb = 0, max_smem = 0;
+    int32_t *blocks = nullptr, *cols = nullptr;
     uint16_t *lcol = nullptr;
-    int64_t total = 0;
-    if (sx_plan_edge_lists(M, K, a.rp.data(), a.ci.data(), (int)(ld * sizeof(T)), (int)sizeof(T), budget, &nb, &blocks, &nr,
-                           &runs, &lcol, &total, &max_smem) != 0) {
+    int64_t total = 0, ncols = 0;
+    if (sx_plan_edge_lists(M, K, a.rp.data(), a.ci.data(), (int)(ld * sizeof(T)), (int)sizeof(T), ROWS, budget, &nb, &blocks,
+                           &ncols, &cols, &lcol, &total, &max_smem) != 0) {
         std::printf("edge lists: plan FAILED\n");
         ++failures;
         return;
@@ -615,48 +616,46 @@ void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, u
         return;
     }
     // device copies at exactly the product's sizes and pads (sx_api.cu: get_edge_plan, upload_csr)
-    Aligned<int> dblocks((size_t)nb * 8), druns((size_t)std::max(nr, 1) * 2);
+    Aligned<int> dblocks((size_t)nb * 8), dcols((size_t)std::max<int64_t>(ncols, 4));
     Aligned<uint16_t> dlcol((size_t)nnz, 64);
     std::copy(blocks, blocks + (size_t)nb * 8, dblocks.p);
-    std::copy(runs, runs + (size_t)nr * 2, druns.p);
+    std::copy(cols, cols + ncols, dcols.p);
     std::copy(lcol, lcol + nnz, dlcol.p);
     // plan invariants: blocks tile the rows in order, every nonzero's local column names its column
     bool plan_ok = true;
     int next_row = 0;
     for (int b = 0; b < nb && plan_ok; ++b) {
         const int32_t *r = blocks + (size_t)b * 8;
-        plan_ok = r[0] == next_row && r[1] >= 1 && r[1] <= 32 && r[2] == a.rp[r[0]] && r[3] == a.rp[r[0] + r[1]] && r[7] <= budget && r[7] <= max_smem;
+        plan_ok = r[0] == next_row && r[1] >= 1 && r[1] <= ROWS && r[2] == a.rp[r[0]] && r[3] == a.rp[r[0] + r[1]] &&
+                  r[4] % 4 == 0 && r[7] <= budget && r[7] <= max_smem;
         next_row = r[0] + r[1];
-        std::vector<int> cols;
-        for (int q = r[4]; q < r[5]; ++q)
-            for (int t = 0; t < (runs[2 * q + 1] & 0xffff); ++t) {
-                plan_ok = plan_ok && (int)cols.size() == (int)((uint32_t)runs[2 * q + 1] >> 16) + t;
-                cols.push_back(runs[2 * q] + t);
-            }
-        plan_ok = plan_ok && (int)cols.size() == r[6];
-        for (int j = r[2]; j < r[3] && plan_ok; ++j) plan_ok = lcol[j] < cols.size() && cols[lcol[j]] == a.ci[j];
+        for (int i = 1; i < r[5] && plan_ok; ++i) plan_ok = cols[r[4] + i] > cols[r[4] + i - 1];
+        for (int j = r[2]; j < r[3] && plan_ok; ++j) plan_ok = lcol[j] < r[5] && cols[r[4] + lcol[j]] == a.ci[j];
     }
     plan_ok = plan_ok && next_row == M;
     if (!plan_ok) { std::printf("%-34s %s M=%d N=%d: PLAN INVARIANT MISMATCH\n", what, tname, M, N); ++failures; }
     const int nvec = (N * (int)sizeof(T) + 15) / 16;
     const uint32_t ldv = (uint32_t)(ld / E);
     std::fill(Cout.p, Cout.p + (int64_t)M * ld, (T)777);
+    // flags: [0] ready (already at the push the kernel waits for), [1] epoch, [2] the pusher's done flag, [4..8) sync words
     Aligned<uint32_t> flags(8);
-    flags.p[0] = 41;  // ready flag already at the step the kernel waits for
-    sx_emu::launch((unsigned)nb, 32 * G, (size_t)std::max(max_smem, 16), [&] {
-        sx::spmm_edgelist_kernel<T, G, true>(reinterpret_cast<const int4 *>(dblocks.p), reinterpret_cast<const int2 *>(druns.p),
+    flags.p[0] = 41;
+    flags.p[1] = 40;
+    sx_emu::launch((unsigned)nb, THREADS, (size_t)std::max(max_smem, 16), [&] {
+        sx::spmm_edgelist_kernel<T, G, true>(reinterpret_cast<const int4 *>(dblocks.p), dcols.p,
                                              rp.p, dlcol.p, val.p, B.p, ldv, Cin.p, Cout.p, ldv, alpha, beta, nvec,
-                                             sx::SX_EDGE_PREFETCH, with_flags ? flags.p : nullptr, 41u,
-                                             with_flags ? flags.p + 2 : nullptr, with_flags ? flags.p + 4 : nullptr);
+                                             sx::SX_EDGE_PREFETCH, with_flags ? flags.p : nullptr, flags.p + 1, flags.p + 2,
+                                             flags.p + 4);
     });
     bool ok = true;
     for (int i = 0; i < M && ok; ++i) ok = same_bits(Cout.p + (int64_t)i * ld, Ref.p + (int64_t)i * ld, (size_t)N);
-    if (with_flags) ok = ok && flags.p[4] == 41u && flags.p[2] == 0u;  // the last block acknowledged and reset the counter
+    // the last block advanced the epoch, acknowledged to the pusher and reset the block counter; no time-out
+    if (with_flags) ok = ok && flags.p[1] == 41u && flags.p[2] == 41u && flags.p[6] == 0u && flags.p[5] == 0u;
     std::printf("%-34s %s M=%d K=%d N=%d G=%d budget=%d blocks=%d cols=%lld/%d: %s\n", what, tname, M, K, N, G, budget, nb,
                 (long long)total, nnz, ok ? "bit-exact" : "MISMATCH");
     if (!ok) ++failures;
     sx_free(blocks);
-    sx_free(runs);
+    sx_free(cols);
     sx_free(lcol);
 }
 

@@ -9,23 +9,21 @@ import sextans_b200 as sx
 from helpers import mtx_path, random_csr
 
 
-def check_plan(M, K, rp, ci, row_bytes, elem, budget, blocks, runs, lcol, total, max_smem):
-    assert blocks.shape[1] == 8 and runs.shape[1] == 2 and lcol.size == ci.size
+def check_plan(M, K, rp, ci, row_bytes, elem, budget, blocks, cols, lcol, total, max_smem, rows=32):
+    assert blocks.shape[1] == 8 and lcol.size == ci.size and cols.size % 4 == 0
     nxt = 0
     tot = 0
     for b in blocks:
-        r0, nr, jb, je, q0, q1, ncols, smem = (int(x) for x in b)
-        assert r0 == nxt and 1 <= nr <= 32 and (r0 // 32) == ((r0 + nr - 1) // 32)
-        assert jb == rp[r0] and je == rp[r0 + nr]
-        cols = []
-        for col, packed in runs[q0:q1]:
-            first, length = (int(packed) >> 16) & 0xffff, int(packed) & 0xffff
-            assert first == len(cols) and length >= 1 and length * row_bytes <= max(16384, row_bytes)
-            cols.extend(range(int(col), int(col) + length))
-        assert len(cols) == ncols and cols == sorted(set(ci[jb:je].tolist()))
-        assert np.array_equal(np.asarray(cols, dtype=np.int64)[lcol[jb:je]], ci[jb:je])
+        r0, nr, jb, je, c0, ncols, _, smem = (int(x) for x in b)
+        assert r0 == nxt and 1 <= nr <= rows and (r0 // rows) == ((r0 + nr - 1) // rows)
+        assert jb == rp[r0] and je == rp[r0 + nr] and c0 % 4 == 0
+        mine = cols[c0:c0 + ncols]
+        assert mine.tolist() == sorted(set(ci[jb:je].tolist()))
+        assert np.array_equal(mine[lcol[jb:je]], ci[jb:je])
+        pad = cols[c0 + ncols:c0 + ((ncols + 3) & ~3)]
+        assert ncols == 0 or np.all(pad == mine[-1])                 # pad entries name a real column
         na = ((je - (jb & ~7) + 7) & ~7) if je > jb else 0
-        assert smem == ncols * row_bytes + na * (elem + 2) and smem <= budget and smem <= max_smem
+        assert smem == ncols * row_bytes + na * (elem + 2) + ((ncols + 3) & ~3) * 4 and smem <= budget and smem <= max_smem
         nxt = r0 + nr
         tot += ncols
     assert nxt == M and tot == total
@@ -57,9 +55,12 @@ def test_random_matrices_with_empty_rows_and_unsorted_columns(seed):
         if len(plan[0]) == 0:                # some row alone exceeds the budget
             lens = np.diff(rp)
             worst = int(lens.max())
-            assert worst * row_bytes + (worst + 14) * (elem + 2) > budget * 0.5
+            assert worst * (row_bytes + 4) + (worst + 14) * (elem + 2) > budget * 0.5
             continue
         check_plan(M, K, rp, ci, row_bytes, elem, budget, *plan)
+        plan = sx.plan_edge_lists(M, K, rp, ci, row_bytes, elem, budget, rows_per_block=128)
+        if len(plan[0]):
+            check_plan(M, K, rp, ci, row_bytes, elem, budget, *plan, rows=128)
 
 
 def test_degenerate_inputs():
@@ -68,6 +69,6 @@ def test_degenerate_inputs():
     assert len(b) == 0 and t == 0
     rp = np.zeros(41, np.int32)              # 40 empty rows: blocks without runs
     b, r, l, t, m = sx.plan_edge_lists(40, 5, rp, np.zeros(0, np.int32), 64, 4, 4096)
-    assert len(b) == 2 and t == 0 and len(r) == 0 and b[:, 6].sum() == 0
+    assert len(b) == 2 and t == 0 and b[:, 5].sum() == 0
     with pytest.raises(sx.SextansError):
         sx.plan_edge_lists(4, 5, np.zeros(5, np.int32), np.zeros(0, np.int32), 60, 4, 4096)   # row_bytes % 16
