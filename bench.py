@@ -3,31 +3,37 @@
 
 A "step" is one SpMM  C = alpha*A*B + beta*C  over the named workload.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--configs all|none|a,b,..]
 
-Workloads (BASELINE.json configs):
-  nasa4704   nasa4704.mtx  N=16 fp64   (configs[1]; the default)
-  pcrystk02  pcrystk02.mtx N=16 fp32   (configs[2]; --ncols 8|16|32|64)
-  uniform    synthetic M=K=1e6, 20 nnz/row, N=128 fp32      (configs[3])
-  powerlaw   synthetic power-law M=K=1e6, nnz~1e8, N=16 fp64 (configs[4])
-  fem        synthetic block-structured (4 dof/node) M=K=1e6, nnz~9.5e7, N=16 fp64: the
-             input of the dense-tile tensor-core variant (configs[4] tail; --tiles 4)
+Headline (value / ms_per_step / roofline / e2e): BASELINE.json configs[1], nasa4704.mtx N=16 fp64.
+`configs` (same JSON line, compact, emitted before the prose): every other BASELINE config --
+pcrystk02 N=8/16/32/64 fp32, the uniform synthetic C4, the power-law synthetic C5 -- each with
+{ms, gflops, frac, traffic_ratio, kernel, parity}; parity = the GPU result of one step against
+the CPU oracle over EVERY row (all host threads; rows are independent, so the threaded oracle
+is bitwise the single-threaded one).  At --gpus N>1 `configs` carries the STRONG scaling of
+the one C4 and the one C5 matrix over nnz-balanced row blocks (sx_partition_rows, one per GPU):
+kernel-only and including the broadcast of B, per-rank nnz imbalance, parity on every rank.
 
-Own arm, per rank (one process per GPU): A's row block resident on the device; at N>1
-the matrix is N row blocks of the workload stacked (weak scaling), every rank owns one,
-and each step starts with the NCCL broadcast of B from rank 0 over NVLink.
-  value : steps timed with CUDA events on the launching stream, inputs resident in
-          HBM, L2 flushed (a 512 MB buffer is overwritten) before every step
-  e2e   : the same step through the host-facing C-ABI call sx_spmm_* with pinned host
-          B and C (column-major, as the host program holds them): H2D copies, layout
-          change, kernel, layout change, D2H copy -- all inside the timed region
-Reference arm (--impl reference): the CPU path (the reference's cpu_spmm_CSR when the
-run is fp32 and oracle/_ref is built, else the oracle port) on the host cores.
+Own arm, per rank (one process per GPU):
+  value : K steps between CUDA events on the launching stream, replayed as CUDA graphs.  The
+          operands exist in R independent device copies (R x bytes > 2.2 x the 126 MB L2) and
+          step i uses copy i mod R, across replays too, so every step finds its operands in
+          HBM ("inputs larger than L2"; no flush kernel in the timed region).  The K-step
+          replay is repeated until the timed region is >= 50 ms; ms_per_step is the MEDIAN
+          repetition / K (max over ranks per repetition).
+  e2e   : the same step through the host-facing C-ABI call sx_spmm_* with pinned host B and C
+          (column-major, as the host program holds them), H2D + kernels + D2H inside the timed
+          region; at N>1 through ShardedSpMM (B on rank 0's host, exchange, C blocks back).
+  N>1 headline: weak scaling -- N stacked copies of the matrix, one row block per GPU, the
+          exchange of B from rank 0 inside every step.
+Reference arm (--impl reference): the reference's CPU path cpu_spmm_CSR on the host cores
+(oracle/_ref = the reference's own header for fp32, the line-for-line port for fp64).
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import sys
 import threading
@@ -44,77 +50,104 @@ WORKLOADS = {
     "pcrystk02": ("suitesparse", np.float32, 16),
     "uniform": ("uniform", np.float32, 128),
     "powerlaw": ("powerlaw", np.float64, 16),
+    "powerlaw_blocked": ("powerlaw_blocked", np.float64, 16),
     "fem": ("fem", np.float64, 16),
 }
+# the `configs` entries of the default run: (key, workload, N)
+CONFIGS_1GPU = [("pcrystk02_n8", "pcrystk02", 8), ("pcrystk02_n16", "pcrystk02", 16),
+                ("pcrystk02_n32", "pcrystk02", 32), ("pcrystk02_n64", "pcrystk02", 64),
+                ("uniform_c4", "uniform", 128), ("powerlaw_c5", "powerlaw", 16)]
+CONFIGS_EXTRA = [("powerlaw_blocked", "powerlaw_blocked", 16)]      # on request: --configs powerlaw_blocked
+CONFIGS_NGPU = [("uniform_c4", "uniform", 128), ("powerlaw_c5", "powerlaw", 16)]
 ALPHA, BETA = float(np.float32(0.85)), float(np.float32(-2.06))   # host.cpp:29-30
+L2_BYTES = 126 * 1024 * 1024
+KERNEL_NAMES = {1: "spmm_rows_kernel", 2: "spmm_staged_kernel", 3: "spmm_window_kernel", 4: "spmm_panels_dmma_kernel",
+                5: "spmm_staged_kernel<WIN>", 7: "spmm_slide_kernel", 8: "spmm_edgelist_kernel"}
 
 
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=50)
+    p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="native", choices=["native", "reference"])
     p.add_argument("--workload", default="nasa4704", choices=sorted(WORKLOADS))
+    p.add_argument("--configs", default="all", help="all | none | comma-separated keys of the `configs` entries to run")
     p.add_argument("--ncols", type=int, default=0, help="override the workload's N")
     p.add_argument("--dtype", default="", choices=["", "f32", "f64"])
-    p.add_argument("--scale", type=float, default=1.0, help="shrink the synthetic workloads (testing)")
+    p.add_argument("--scale", type=float, default=1.0, help="shrink the synthetic workloads (testing only; the line says so)")
     p.add_argument("--arith", default="strict", choices=["strict", "fast"])
-    p.add_argument("--kernel", type=int, default=0, help="SX_OPT_KERNEL (0 auto, 1 row per lane group, 2 TMA-staged items, 3 TMA-staged B window, 4 sliding B window: experimental, needs --slide)")
+    p.add_argument("--kernel", type=int, default=0, help="SX_OPT_KERNEL (0 auto, 1 row per lane group, 2 TMA-staged items, 3 TMA-staged B window, 4 sliding B window (needs --slide), 5 edge lists)")
     p.add_argument("--item-nnz", type=int, default=0, help="SX_OPT_ITEM_NNZ (0 auto)")
     p.add_argument("--split", type=int, default=-1, help="SX_OPT_SPLIT_ROW_NNZ (-1 default)")
     p.add_argument("--band", type=int, default=2000, help="fem workload: couplings reach +-band nodes")
     p.add_argument("--tiles", type=int, default=0, help="SX_OPT_TILE_MIN_ROWS (fp64 dense-tile tensor-core variant; 0 off)")
-    p.add_argument("--col-window-rows", type=int, default=0, help="SX_OPT_COL_WINDOW_ROWS (column-window passes keeping a window of B in L2; 0 off, -1 = 32 MiB of B per window)")
-    p.add_argument("--autotune", action="store_true", help="SX_OPT_AUTOTUNE (experimental): time the applicable variants on the first call and keep the fastest")
-    p.add_argument("--slide", type=int, default=0, help="SX_OPT_SLIDE (experimental): chains per SM of the sliding-window kernel; use with --kernel 4")
-    p.add_argument("--window-rows", type=int, default=0, choices=[0, 32, 64, 128], help="SX_OPT_WINDOW_ROWS (experimental): rows per block of variant 3")
+    p.add_argument("--col-window-rows", type=int, default=0, help="SX_OPT_COL_WINDOW_ROWS (0 off, -1 = 32 MiB of B per window)")
+    p.add_argument("--slide", type=int, default=0, help="SX_OPT_SLIDE: chains per SM of the sliding-window kernel; use with --kernel 4")
+    p.add_argument("--window-rows", type=int, default=0, choices=[0, 32, 64, 128], help="SX_OPT_WINDOW_ROWS: rows per block of variant 3")
     p.add_argument("--pdl", type=int, default=-1, choices=[-1, 0, 1], help="SX_OPT_PDL: programmatic dependent launch (-1 auto: on for the edge-list kernel)")
     p.add_argument("--prefetch", type=int, default=-1, choices=[-1, 0, 1], help="SX_OPT_PREFETCH: L2 prefetch hints (-1 auto)")
-    p.add_argument("--host-fused", action="store_true", help="SX_OPT_HOST_FUSED (experimental): e2e calls pass kernel_ns=NULL and the SpMM kernel carries C across PCIe")
-    p.add_argument("--ref-threads", type=int, default=1, help="--impl reference: threads of the CPU path (1 = as the reference runs it; -1 = all cores, OpenMP port)")
-    p.add_argument("--peer-bytes", type=int, default=8 << 20, help="N>1: B images up to this size travel by peer copy instead of NCCL")
-    p.add_argument("--peer-mode", default="fused", choices=["fused", "memops"])
+    p.add_argument("--ref-threads", type=int, default=-1, help="--impl reference: threads of the CPU path (-1 = all cores, row-parallel; 1 = as the reference runs it)")
+    p.add_argument("--peer-bytes", type=int, default=8 << 20, help="N>1: B images up to this size travel through peer memory instead of NCCL")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--no-flush", action="store_true", help="leave L2 warm between steps")
-    p.add_argument("--no-graph", action="store_true", help="launch the timed steps one by one instead of replaying a CUDA graph")
+    p.add_argument("--no-flush", action="store_true", help="one device copy: leave L2 warm between steps")
+    p.add_argument("--no-graph", action="store_true", help="launch the timed steps one by one instead of replaying CUDA graphs")
+    p.add_argument("--min-region-ms", type=float, default=50.0, help="repeat the K-step replay until the timed region is this long")
     return p.parse_args()
 
 
-def build_workload(args):
-    """-> dict(name, M, K, nnz, N, dtype, rowptr, colidx, val, B, Cin) for ONE row block."""
-    import sextans_b200 as sx
+# ---- workloads ------------------------------------------------------------------------------
+def build_workload(name, ncols=0, dtype_override="", scale=1.0, band=2000, loader="product"):
+    """-> dict(name, desc, M, K, nnz, N, dtype, rowptr, colidx, val, B, Cin); B, Cin column-major 1-D.
+    loader: "product" (sx_load_mtx_*) for the own arm, "oracle" for the reference arm, which must
+    not touch the product library."""
     from sextans_b200 import workloads as wl
-    kind, dtype, N = WORKLOADS[args.workload]
-    if args.dtype:
-        dtype = np.float32 if args.dtype == "f32" else np.float64
-    if args.ncols:
-        N = args.ncols
+    kind, dtype, N = WORKLOADS[name]
+    if dtype_override:
+        dtype = np.float32 if dtype_override == "f32" else np.float64
+    if ncols:
+        N = ncols
+    extra = {}
+    tname = np.dtype(dtype).name
     if kind == "suitesparse":
-        M, K, nnz, rp, ci, v = sx.load_mtx(wl.suitesparse_path(args.workload), dtype)
+        if loader == "oracle":
+            import oracle
+            M, K, nnz, rp, ci, v = oracle.load_mtx(wl.suitesparse_path(name), dtype)[:6]
+        else:
+            import sextans_b200 as sx
+            M, K, nnz, rp, ci, v = sx.load_mtx(wl.suitesparse_path(name), dtype)
         B, Cin = wl.host_dense(M, K, N, dtype)
-        desc = f"{args.workload}.mtx M=K={M} nnz={nnz} N={N} {np.dtype(dtype).name}, B=1, C_in=(m+1)(n+1)/M/N (host.cpp:100-111)"
+        desc = f"{name}.mtx M=K={M} nnz={nnz} N={N} {tname}, B=1, C_in=(m+1)(n+1)/M/N (host.cpp:100-111)"
     elif kind == "uniform":
-        M = K = max(1000, int(1_000_000 * args.scale))
+        M = K = max(1000, int(1_000_000 * scale))
         rp, ci, v = wl.uniform_csr(M, K, 20, 12345, dtype)
         nnz = int(ci.size)
         B, Cin = wl.random_dense(M, K, N, 12345, dtype)
-        desc = f"synthetic uniform CSR M=K={M} nnz={nnz} (20/row) N={N} {np.dtype(dtype).name}, seed 12345"
+        desc = f"synthetic uniform CSR M=K={M} nnz={nnz} (20/row) N={N} {tname}, seed 12345"
     elif kind == "fem":
-        nodes = max(250, int(250_000 * args.scale))
+        nodes = max(250, int(250_000 * scale))
         M = K = nodes * 4
-        rp, ci, v = wl.fem_like_csr(nodes, 4, 23, 12345, dtype, band=args.band)
+        rp, ci, v = wl.fem_like_csr(nodes, 4, 23, 12345, dtype, band=band)
         nnz = int(ci.size)
         B, Cin = wl.random_dense(M, K, N, 12345, dtype)
-        desc = f"synthetic FEM-like CSR (4 dof/node, dense 4x4 couplings within +-{args.band} nodes) M=K={M} nnz={nnz} N={N} {np.dtype(dtype).name}, seed 12345"
+        desc = f"synthetic FEM-like CSR (4 dof/node, dense 4x4 couplings within +-{band} nodes) M=K={M} nnz={nnz} N={N} {tname}, seed 12345"
+    elif kind == "powerlaw_blocked":
+        M = K = max(1000, int(1_000_000 * scale))
+        rp, ci, v, planted = wl.powerlaw_blocked_csr(M, K, int(100_000_000 * scale), 12345, dtype)
+        nnz = int(ci.size)
+        B, Cin = wl.random_dense(M, K, N, 12345, dtype)
+        extra["planted_nnz"] = planted
+        desc = f"synthetic power-law CSR with planted dense 16x16 blocks ({planted / nnz:.0%} of nnz) M=K={M} nnz={nnz} N={N} {tname}, seed 12345"
     else:
-        M = K = max(1000, int(1_000_000 * args.scale))
-        rp, ci, v = wl.powerlaw_csr(M, K, int(100_000_000 * args.scale), 12345, dtype)
+        M = K = max(1000, int(1_000_000 * scale))
+        rp, ci, v = wl.powerlaw_csr(M, K, int(100_000_000 * scale), 12345, dtype)
         nnz = int(ci.size)
         B, Cin = wl.random_dense(M, K, N, 12345, dtype)
-        desc = f"synthetic power-law CSR M=K={M} nnz={nnz} N={N} {np.dtype(dtype).name}, seed 12345"
-    return dict(name=args.workload, desc=desc, M=M, K=K, nnz=nnz, N=N, dtype=np.dtype(dtype),
-                rowptr=rp, colidx=ci, val=v, B=B, Cin=Cin)
+        desc = f"synthetic power-law CSR M=K={M} nnz={nnz} N={N} {tname}, seed 12345"
+    if scale != 1.0 and kind != "suitesparse":
+        desc += f" [SCALED x{scale}: not the BASELINE size]"
+    return dict(name=name, desc=desc, M=M, K=K, nnz=nnz, N=N, dtype=np.dtype(dtype),
+                rowptr=rp, colidx=ci, val=v, B=B, Cin=Cin, **extra)
 
 
 def measured_peak():
@@ -126,13 +159,27 @@ def measured_peak():
 
 
 def ncu_traffic(name, N, dtype):
-    """dram bytes per launch of the SpMM kernel from the committed ncu capture, or None."""
+    """dram bytes per launch of the SpMM kernel from the committed ncu capture (profiles/traffic.json), or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)
         return t.get(f"{name}_n{N}_{dtype}")
     except Exception:
         return None
+
+
+def max_rel_err(x, y):
+    """|x-y| / max(|y|, 1e-30), max over elements (SURVEY.md 8(c) definition)."""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    return float(np.max(np.abs(x - y) / np.maximum(np.abs(y), 1e-30))) if x.size else 0.0
+
+
+def scaled_err(x, y):
+    """max |x-y| / max|y| -- insensitive to cancellation in individual entries."""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    return float(np.max(np.abs(x - y)) / max(float(np.max(np.abs(y))), 1e-30)) if x.size else 0.0
 
 
 class ClockSampler(threading.Thread):
@@ -173,7 +220,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.005)
 
     def result(self):
         self.stop_flag = True
@@ -185,120 +232,360 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_baseline(w, threads, budget_s=12.0, min_runs=3):
-    """Time the CPU path on this workload (checker code, timed as a reported baseline).
-    fp32 + oracle/_ref present -> the reference's own cpu_spmm_CSR (1 thread, as written);
-    otherwise the oracle port, `threads` OpenMP threads over rows."""
-    import oracle
-    M, K, N, nnz = w["M"], w["K"], w["N"], w["nnz"]
-    rows_sample = None
-    # bound the work: if one full SpMM would take more than the budget (~2 GFLOP/s per
-    # thread), time a contiguous prefix of the rows with the same B
+# ---- CPU arms (checker code, timed as a reported baseline) -----------------------------------
+def bounded_sample(w, seconds, threads):
+    """A row prefix of the workload sized so that one CPU pass takes about `seconds` (full B)."""
+    M, N, nnz = w["M"], w["N"], w["nnz"]
     est = 2.0 * nnz * N / (1.5e9 * max(1, threads))
-    rp, ci, v = w["rowptr"], w["colidx"], w["val"]
-    Cin = w["Cin"]
-    if est > budget_s:
-        frac = budget_s / est
-        Ms = max(1, int(M * frac))
-        rows_sample = Ms
-        rp = np.ascontiguousarray(rp[:Ms + 1])
-        ci, v = ci[:rp[-1]], v[:rp[-1]]
-        Cin = np.ascontiguousarray(Cin.reshape(N, M)[:, :Ms]).ravel()
-        M = Ms
-        nnz = int(rp[-1])
-    use_ref = (w["dtype"] == np.float32 and threads == 1 and oracle.ref() is not None)
-    times = []
+    if est <= seconds:
+        return w["M"], w["nnz"], w["rowptr"], w["colidx"], w["val"], w["Cin"], "the whole workload"
+    Ms = max(1, int(M * seconds / est))
+    rp = np.ascontiguousarray(w["rowptr"][:Ms + 1])
+    nz = int(rp[-1])
+    Cin = np.ascontiguousarray(w["Cin"].reshape(N, M)[:, :Ms]).ravel()
+    return Ms, nz, rp, w["colidx"][:nz], w["val"][:nz], Cin, f"first {Ms} rows ({nz} nnz) of the workload, full B"
+
+
+def cpu_pass(w, M, rp, ci, v, C, threads):
+    import oracle
+    if w["dtype"] == np.float32 and threads == 1 and oracle.ref() is not None:
+        oracle.ref_spmm_csr(M, w["N"], w["K"], rp, ci, v, ALPHA, w["B"], BETA, C)
+        return "reference"
+    oracle.spmm_csr(M, w["N"], w["K"], rp, ci, v, w["dtype"].type(ALPHA), w["B"], w["dtype"].type(BETA), C, threads=threads)
+    return "port"
+
+
+def cpu_baseline(w, threads, budget_s=10.0):
+    M, nnz, rp, ci, v, Cin, sample = bounded_sample(w, budget_s / 3, threads)
+    times, kind = [], "port"
     t_all = time.perf_counter()
-    while len(times) < min_runs or (time.perf_counter() - t_all < budget_s / 2 and len(times) < 20):
+    while len(times) < 3 or (time.perf_counter() - t_all < budget_s / 2 and len(times) < 20):
         C = Cin.copy()
         t0 = time.perf_counter()
-        if use_ref:
-            oracle.ref_spmm_csr(M, N, K, rp, ci, v, ALPHA, w["B"], BETA, C)
-        else:
-            oracle.spmm_csr(M, N, K, rp, ci, v, w["dtype"].type(ALPHA), w["B"], w["dtype"].type(BETA), C, threads=threads)
+        kind = cpu_pass(w, M, rp, ci, v, C, threads)
         times.append(time.perf_counter() - t0)
-        if time.perf_counter() - t_all > budget_s * 2:
+        if time.perf_counter() - t_all > budget_s * 1.5:
             break
     best = min(times)
-    sample = "the whole workload" if rows_sample is None else f"first {rows_sample} rows ({nnz} nnz) of the workload, full B"
-    return {"value": 2.0 * nnz * N / best / 1e9, "unit": "GFLOP/s", "cores": threads,
-            "kind": "reference" if use_ref else "port",
-            "sample": f"{sample}; best of {len(times)} runs, {best * 1e3:.3f} ms",
-            "ms": best * 1e3, "mean_ms": float(np.mean(times)) * 1e3}
+    return {"value": 2.0 * nnz * w["N"] / best / 1e9, "unit": "GFLOP/s", "cores": threads, "kind": kind,
+            "sample": f"{sample}; best of {len(times)} runs, {best * 1e3:.3f} ms"}
 
 
 def run_reference(args):
-    """The reference arm: cpu_spmm_CSR as the reference runs it -- ONE thread, the function
-    has no threading (src/sparse_helper.h:262-290) -- through oracle/_ref (the reference's
-    own header, compiled unmodified) for fp32 and the line-for-line double port for fp64.
-    --ref-threads N times the port's row-parallel OpenMP variant instead; the default line
-    carries that all-core figure as extra information."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """The reference arm: cpu_spmm_CSR on the host cores.  The function itself is single-threaded
+    (src/sparse_helper.h:262-290); with all the host threads it can use, its rows -- which are
+    independent -- are dealt to OpenMP threads by the oracle port, bitwise the same result.  The
+    line also carries the 1-thread figure: the reference's own compiled header when the run is
+    fp32, the port otherwise."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     import oracle
-    w = build_workload(args)
+    w = build_workload(args.workload, args.ncols, args.dtype, args.scale, args.band, loader="oracle")
     all_threads = max(1, oracle.lib().sx_oracle_max_threads())
     threads = all_threads if args.ref_threads < 0 else max(1, args.ref_threads)
-    M, K, N, nnz = w["M"], w["K"], w["N"], w["nnz"]
-    est = 2.0 * nnz * N / (1.5e9 * threads)
-    rp, ci, v, Cin = w["rowptr"], w["colidx"], w["val"], w["Cin"]
-    sample = "the whole workload per step"
-    if est > 2.0:   # bounded sample: a row prefix sized to ~2 s per step
-        Ms = max(1, int(M * 2.0 / est))
-        rp = np.ascontiguousarray(rp[:Ms + 1])
-        ci, v = ci[:rp[-1]], v[:rp[-1]]
-        Cin = np.ascontiguousarray(Cin.reshape(N, M)[:, :Ms]).ravel()
-        M, nnz = Ms, int(rp[-1])
-        sample = f"first {Ms} rows ({nnz} nnz) of the workload per step, full B"
-    a, b = w["dtype"].type(ALPHA), w["dtype"].type(BETA)
-    use_ref = w["dtype"] == np.float32 and threads == 1 and oracle.ref() is not None
-
-    def one(C):
-        if use_ref:
-            oracle.ref_spmm_csr(M, N, K, rp, ci, v, ALPHA, w["B"], BETA, C)
-        else:
-            oracle.spmm_csr(M, N, K, rp, ci, v, a, w["B"], b, C, threads=threads)
-
-    steps = args.steps
-    if est * steps > 120:   # keep the whole run within a few minutes
-        steps = max(3, int(120 / est))
-    for _ in range(min(args.warmup, 3)):
-        one(Cin.copy())
-    total = 0.0
-    for _ in range(steps):
+    M, nnz, rp, ci, v, Cin, sample = bounded_sample(w, 2.0, threads)
+    warm = max(3, args.warmup)
+    for _ in range(warm):
+        cpu_pass(w, M, rp, ci, v, Cin.copy(), threads)
+    total, kind = 0.0, "port"
+    for _ in range(args.steps):
         C = Cin.copy()
         t0 = time.perf_counter()
-        one(C)
+        kind = cpu_pass(w, M, rp, ci, v, C, threads)
         total += time.perf_counter() - t0
-    val = 2.0 * nnz * N * steps / total / 1e9
-    extra = None
-    if threads == 1 and all_threads > 1:
-        extra = cpu_baseline(dict(w, M=M, nnz=nnz, rowptr=rp, colidx=ci, val=v, Cin=Cin), all_threads, budget_s=6.0)
-        extra["note"] = "row-parallel OpenMP over the oracle port (bitwise the same result); NOT the reference, which is single-threaded"
-    line = {
+    val = 2.0 * nnz * w["N"] * args.steps / total / 1e9
+    one = cpu_baseline(w, 1, budget_s=6.0) if threads != 1 else None
+    emit({
         "impl": "reference", "metric": "SpMM GFLOP/s (2*nnz*N)", "value": val, "unit": "GFLOP/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3),
-        "ms_per_step": total / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": warm,
+        "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64" if w["dtype"] == np.float64 else "f32",
-        "data": "synthetic" if w["name"] in ("uniform", "powerlaw") else "SuiteSparse fixture shipped with the reference, host program's B/C",
-        "config": {"workload": w["desc"], "alpha": ALPHA, "beta": BETA},
-        "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": threads, "kind": "reference" if use_ref else "port",
-                         "sample": sample,
-                         "note": "cpu_spmm_CSR as the reference runs it: one thread (src/sparse_helper.h:262-290 has no threading)"
-                                 if threads == 1 else "row-parallel OpenMP over the oracle port of cpu_spmm_CSR",
-                         "all_cores_openmp_port": extra},
+        "data": data_label(w), "config": config_of(w),
+        "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": threads, "kind": kind, "sample": sample + " per step",
+                         "note": "cpu_spmm_CSR (src/sparse_helper.h:262-290), rows dealt to OpenMP threads by the oracle port" if threads > 1
+                                 else "cpu_spmm_CSR as the reference runs it: one thread",
+                         "one_thread": one},
         "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }
-    emit(line)
+    })
+
+
+def data_label(w):
+    return "synthetic" if w["name"] not in ("nasa4704", "pcrystk02") else "SuiteSparse fixture shipped with the reference, host program's B/C (synthetic dense operands)"
+
+
+def config_of(w):
+    """The workload's identity: the same dict on both arms."""
+    return {"workload": w["desc"], "alpha": ALPHA, "beta": BETA}
+
+
+# ---- own arm ---------------------------------------------------------------------------------
+class Case:
+    """One workload (or one rank's row block of it) resident on the device in R rotating copies.
+    own_B: the engines' own B images are the operands (what a push exchange writes into)."""
+
+    def __init__(self, w, args, dev, stream, copies=None, fill_B=True, own_B=False):
+        import torch
+        import sextans_b200 as sx
+        from sextans_b200 import workloads as wl
+        self.w, self.args, self.dev, self.stream = w, args, dev, stream
+        M, K, N, nnz, dtype = w["M"], w["K"], w["N"], w["nnz"], w["dtype"]
+        self.s = dtype.itemsize
+        self.tdtype = torch.float64 if dtype == np.float64 else torch.float32
+        self.alg_bytes = wl.algorithmic_bytes(M, K, nnz, N, self.s)
+        if copies is None:
+            copies = 1 if (args.no_flush or self.alg_bytes >= 2 * L2_BYTES) else int(math.ceil(2.2 * L2_BYTES / self.alg_bytes))
+        self.R = copies
+        self.ld = (N + 7) // 8 * 8
+        self.engines, self.dB, self.dCin, self.dCout = [], [], [], []
+        with torch.cuda.stream(stream):
+            dB_cm = torch.from_numpy(w["B"]).to(dev)
+            dC_cm = torch.from_numpy(w["Cin"]).to(dev)
+        for _ in range(self.R):
+            e = sx.Engine(dev.index, arith=sx.STRICT if args.arith == "strict" else sx.FAST)
+            e.set_stream(stream.cuda_stream)
+            e.set_option(sx.OPT_KERNEL, args.kernel)
+            e.set_option(sx.OPT_ITEM_NNZ, args.item_nnz)
+            e.set_option(sx.OPT_TILE_MIN_ROWS, args.tiles if dtype == np.float64 else 0)
+            cw = args.col_window_rows
+            if cw < 0:
+                cw = max(1, (32 << 20) // (self.ld * self.s))
+            e.set_option(sx.OPT_COL_WINDOW_ROWS, cw)
+            e.set_option(sx.OPT_PDL, args.pdl)
+            e.set_option(sx.OPT_PREFETCH, args.prefetch)
+            e.set_option(sx.OPT_WINDOW_ROWS, args.window_rows)
+            e.set_option(sx.OPT_SLIDE, args.slide)
+            if args.split >= 0:
+                e.set_option(sx.OPT_SPLIT_ROW_NNZ, args.split)
+            e.upload_csr(M, K, w["rowptr"], w["colidx"], w["val"])
+            with torch.cuda.stream(stream):
+                dB = e.device_B(N)[0] if own_B else torch.zeros(K * self.ld, dtype=self.tdtype, device=dev)   # device_B: zero-filled
+                dCin = torch.zeros(M * self.ld, dtype=self.tdtype, device=dev)
+                dCout = torch.zeros(M * self.ld, dtype=self.tdtype, device=dev)
+                if fill_B:
+                    e.colmajor_to_rowmajor(K, N, dB_cm, dB, self.ld)
+                e.colmajor_to_rowmajor(M, N, dC_cm, dCin, self.ld)
+            self.engines.append(e); self.dB.append(dB); self.dCin.append(dCin); self.dCout.append(dCout)
+        del dB_cm, dC_cm
+        stream.synchronize()
+
+    def step(self, i):
+        j = i % self.R
+        self.engines[j].spmm_device(self.w["N"], ALPHA, self.dB[j], self.ld, BETA, self.dCin[j], self.dCout[j], self.ld)
+
+    def launches(self):
+        return sum(e.launches for e in self.engines)
+
+    def kernel_name(self):
+        import sextans_b200 as sx
+        e = self.engines[0]
+        lk = e.info(sx.INFO_LAST_KERNEL)
+        fam = lk // 10000
+        if fam == 5:
+            return f"spmm_staged_kernel<WIN>, {lk % 10000} column-window passes"
+        name = KERNEL_NAMES.get(fam, "?") + f"<G={lk % 10000 // 100},{'fast' if lk % 10 else 'strict'}>"
+        if fam == 2:
+            name += f" {e.info(sx.INFO_ITEMS)} items<={e.info(sx.INFO_ITEM_NNZ)}nnz, {e.info(sx.INFO_SPLIT_ROWS)} split rows"
+        if fam == 8:
+            name += f" {e.info(sx.INFO_EDGE_BLOCKS)} blocks staging {e.info(sx.INFO_EDGE_COLS)} B rows"
+        if e.info(sx.INFO_TILE_NNZ) > 0:
+            name += (f"; dense tiles {e.info(sx.INFO_TILE_NNZ)} nnz / {e.info(sx.INFO_TILE_SLOTS)} slots on "
+                     f"spmm_panels_dmma_kernel, {e.info(sx.INFO_REST_NNZ)} nnz left to CSR")
+        return name
+
+    def result_colmajor(self, j=0):
+        """C_out of copy j as the host holds it (column-major 1-D numpy)."""
+        import torch
+        M, N = self.w["M"], self.w["N"]
+        with torch.cuda.stream(self.stream):
+            out = torch.empty(M * N, dtype=self.tdtype, device=self.dev)
+            self.engines[j].rowmajor_to_colmajor(M, N, self.dCout[j], self.ld, out)
+        self.stream.synchronize()
+        return out.cpu().numpy()
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+        self.engines, self.dB, self.dCin, self.dCout = [], [], [], []
+
+
+def time_steps(step, R, K, warmup, stream, min_region_ms, use_graph, world, dev, max_reps=4000, extra_streams=()):
+    """Warm up, then repeat a K-step replay until the timed region is >= min_region_ms; every
+    repetition has its own event pair on `stream`.  Steps are numbered consecutively over warm-up
+    and all repetitions (copy = step mod R), so the rotation through the R copies never restarts.
+    Graph mode captures one graph per distinct K-step window of the rotation.
+    -> dict(ms_median, ms_min, ms_mean (per step, max over ranks per repetition), reps, region_ms, graphs, nwarm)"""
+    import torch
+    import torch.distributed as dist
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    nwarm = max(3, warmup, min(R, 256))
+    with torch.cuda.stream(stream):
+        for i in range(nwarm):
+            step(i)
+    barrier()
+    base = nwarm
+    graphs = None
+    if use_graph:
+        ngraphs = min(R // math.gcd(R, K) if R > 1 else 1, 64)
+        graphs = []
+        for g in range(ngraphs):
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=stream):
+                for x in extra_streams:
+                    x.wait_stream(stream)            # fork
+                for i in range(K):
+                    step(base + g * K + i)
+                for x in extra_streams:
+                    stream.wait_stream(x)            # join
+            graphs.append(gr)
+        with torch.cuda.stream(stream):
+            for gr in graphs:                        # one untimed pass over the whole rotation
+                gr.replay()
+        barrier()
+        base += ngraphs * K
+
+    def one_rep(r):
+        if graphs is not None:
+            graphs[r % len(graphs)].replay()
+        else:
+            for i in range(K):
+                step(base + r * K + i)
+
+    # pilot: three repetitions to size the run
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    with torch.cuda.stream(stream):
+        ev[0].record(stream)
+        for r in range(3):
+            one_rep(r)
+        ev[1].record(stream)
+    barrier()
+    t = torch.tensor([max(ev[0].elapsed_time(ev[1]) / 3, 1e-4)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    reps = int(min(max_reps, max(3, math.ceil(min_region_ms / float(t.item())))))
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    barrier()
+    with torch.cuda.stream(stream):
+        for r in range(reps):
+            ev[r].record(stream)
+            one_rep(3 + r)
+        ev[reps].record(stream)
+    barrier()
+    per_rep = torch.tensor([ev[r].elapsed_time(ev[r + 1]) for r in range(reps)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(per_rep, op=dist.ReduceOp.MAX)
+    per_rep = per_rep.cpu().numpy()
+    return {"ms_median": float(np.median(per_rep)) / K, "ms_min": float(per_rep.min()) / K,
+            "ms_mean": float(per_rep.mean()) / K, "reps": reps, "region_ms": float(per_rep.sum()),
+            "graphs": 0 if graphs is None else len(graphs), "nwarm": nwarm}
+
+
+def parity(case, w, rows0=0, rows1=None, threads=None):
+    """One step on copy 0 against the CPU oracle over every row of this case (rows0:rows1 of the
+    full workload `w` when the case is a row block).  Untimed.  -> dict"""
+    import oracle
+    M, K, N = w["M"], w["K"], w["N"]
+    rows1 = M if rows1 is None else rows1
+    if threads is None:
+        threads = max(1, oracle.lib().sx_oracle_max_threads())
+    with _on(case.stream):
+        case.step(0)
+    got = case.result_colmajor(0)
+    rp = w["rowptr"]
+    j0, j1 = int(rp[rows0]), int(rp[rows1])
+    m = rows1 - rows0
+    brp = (rp[rows0:rows1 + 1] - rp[rows0]).astype(np.int32)
+    Cin = np.ascontiguousarray(w["Cin"].reshape(N, M)[:, rows0:rows1]).ravel()
+    ref = oracle.spmm_csr(m, N, K, brp, w["colidx"][j0:j1], w["val"][j0:j1], w["dtype"].type(ALPHA), w["B"],
+                          w["dtype"].type(BETA), Cin, threads=threads)
+    return {"max_rel_err": max_rel_err(got, ref), "scaled_err": scaled_err(got, ref),
+            "bit_exact": bool(np.array_equal(got.view(np.uint8), ref.view(np.uint8))),
+            "rows": m, "checksum": float(np.asarray(got, dtype=np.float64).sum()),
+            "checksum_oracle": float(np.asarray(ref, dtype=np.float64).sum())}
+
+
+def _on(stream):
+    import torch
+    return torch.cuda.stream(stream)
+
+
+def run_config(key, wname, N, args, dev, stream, world, rank, peak):
+    """One `configs` entry.  world == 1: the whole matrix on this GPU.  world > 1: strong scaling,
+    this rank's nnz-balanced row block, B broadcast from rank 0 inside every step."""
+    import torch
+    import torch.distributed as dist
+    from sextans_b200 import workloads as wl
+    t_start = time.perf_counter()
+    w = build_workload(wname, N, "", args.scale, args.band)
+    s = w["dtype"].itemsize
+    alg_total = wl.algorithmic_bytes(w["M"], w["K"], w["nnz"], w["N"], s)
+    flops = 2.0 * w["nnz"] * w["N"]
+    traffic = ncu_traffic(w["name"], w["N"], "f64" if s == 8 else "f32")
+    K = max(3, min(args.steps, 20))
+    cargs = argparse.Namespace(**vars(args))
+    if wname == "powerlaw_blocked" and not cargs.tiles:
+        cargs.tiles = 4
+    if world == 1:
+        case = Case(w, cargs, dev, stream)
+        t = time_steps(case.step, case.R, K, args.warmup, stream, min(args.min_region_ms, 30.0), not args.no_graph, 1, dev)
+        par = parity(case, w)
+        out = {"ms": round(t["ms_median"], 6), "gflops": round(flops / (t["ms_median"] * 1e-3) / 1e9, 1),
+               "frac": round(alg_total / (t["ms_median"] * 1e-3) / 1e9 / peak, 4),
+               "traffic_ratio": None if traffic is None else round(traffic / alg_total, 2),
+               "kernel": case.kernel_name(), "parity": par["max_rel_err"], "bit_exact": par["bit_exact"],
+               "checksum": par["checksum"], "reps": t["reps"], "copies": case.R}
+        if w["name"] == "uniform":
+            # the gather-aware bound next to the algorithmic one (SURVEY.md 8(d)): every nonzero
+            # pulls one N*s-byte B row, and with B >> L2 and uniform columns they come from HBM
+            gather = w["nnz"] * w["N"] * s
+            out["frac_gather_bound"] = round(gather / (t["ms_median"] * 1e-3) / 1e9 / peak, 4)
+        case.close()
+        out["wall_s"] = round(time.perf_counter() - t_start, 1)
+        return out
+    # ---- strong scaling over row blocks ----
+    from sextans_b200.rowblock import RowBlock
+    blk = RowBlock(w["M"], w["K"], w["rowptr"], w["colidx"], w["val"], world, rank)
+    wb = dict(w, M=blk.rows, nnz=blk.nnz, rowptr=blk.rowptr, colidx=blk.colidx, val=blk.val, Cin=blk.take_C(w["Cin"], w["N"]))
+    case = Case(wb, cargs, dev, stream, copies=1, fill_B=(rank == 0))
+    with torch.cuda.stream(stream):
+        dist.broadcast(case.dB[0], src=0)              # kernel-only timing needs B everywhere: one untimed broadcast
+    stream.synchronize()
+    tk = time_steps(case.step, 1, K, args.warmup, stream, min(args.min_region_ms, 20.0), False, world, dev)
+
+    def step_x(i):
+        dist.broadcast(case.dB[0], src=0)              # NCCL over NVLink, on `stream`
+        case.step(i)
+    tx = time_steps(step_x, 1, K, args.warmup, stream, min(args.min_region_ms, 20.0), False, world, dev)
+    par = parity(case, w, blk.r0, blk.r1, threads=max(1, (os.cpu_count() or 8) // world))
+    errs = torch.tensor([par["max_rel_err"], 0.0 if par["bit_exact"] else 1.0], dtype=torch.float64, device=dev)
+    dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    nnzs = torch.tensor([float(blk.nnz)], dtype=torch.float64, device=dev)
+    allnnz = [torch.zeros_like(nnzs) for _ in range(world)]
+    dist.all_gather(allnnz, nnzs)
+    allnnz = [float(x.item()) for x in allnnz]
+    per_gpu_alg = wl.algorithmic_bytes(blk.rows, w["K"], blk.nnz, w["N"], s)
+    out = {"scaling": "strong", "ms_kernel": round(tk["ms_median"], 6), "ms_step": round(tx["ms_median"], 6),
+           "gflops_kernel": round(flops / (tk["ms_median"] * 1e-3) / 1e9, 1),
+           "gflops": round(flops / (tx["ms_median"] * 1e-3) / 1e9, 1),
+           "frac_kernel_per_gpu": round(per_gpu_alg / (tk["ms_median"] * 1e-3) / 1e9 / peak, 4),
+           "nnz_imbalance": round(max(allnnz) / (sum(allnnz) / world), 4),
+           "exchange": f"ncclBroadcast of B ({w['K'] * case.ld * s / 1e6:.0f} MB) from rank 0 inside every step",
+           "kernel": case.kernel_name(), "parity_all_ranks": float(errs[0].item()),
+           "bit_exact_all_ranks": bool(errs[1].item() == 0.0), "wall_s": round(time.perf_counter() - t_start, 1)}
+    case.close()
+    return out
 
 
 def run_native(args):
     import torch
     import torch.distributed as dist
     import sextans_b200 as sx
-    from sextans_b200 import workloads as wl
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -310,103 +597,9 @@ def run_native(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-
-    w = build_workload(args)
-    M, K, N, nnz, dtype = w["M"], w["K"], w["N"], w["nnz"], w["dtype"]
-    tdtype = torch.float64 if dtype == np.float64 else torch.float32
-    s = dtype.itemsize
-
-    # ---- replicas: "inputs larger than L2" ------------------------------------------------
-    # The timed steps run back to back with no flush kernel between them; instead the
-    # operands (A, B, C_in, C_out) exist in R independent device copies whose total size
-    # is > 2x the 126 MB L2, and step i uses copy i mod R, so every step finds its data
-    # in HBM, not in L2.  R = 1 when one copy alone is that large.
-    alg_bytes = wl.algorithmic_bytes(M, K, nnz, N, s)
-    L2_BYTES = 126 * 1024 * 1024
-    R = 1 if (args.no_flush or alg_bytes >= 2 * L2_BYTES) else int(np.ceil(2.2 * L2_BYTES / alg_bytes))
     stream = torch.cuda.Stream(device=dev)
-    ld = (N + 7) // 8 * 8
-    engines, dBs, dCins, dCouts = [], [], [], []
-    with torch.cuda.stream(stream):
-        dB_cm = torch.from_numpy(w["B"]).to(dev)
-        dC_cm = torch.from_numpy(w["Cin"]).to(dev)
-    for i in range(R):
-        e = sx.Engine(local, arith=sx.STRICT if args.arith == "strict" else sx.FAST)
-        e.set_stream(stream.cuda_stream)
-        e.set_option(sx.OPT_KERNEL, args.kernel)
-        e.set_option(sx.OPT_ITEM_NNZ, args.item_nnz)
-        e.set_option(sx.OPT_TILE_MIN_ROWS, args.tiles)
-        cw = args.col_window_rows
-        if cw < 0:  # a window of B of ~32 MiB: well inside one L2 partition
-            cw = max(1, (32 << 20) // (ld * s))
-        e.set_option(sx.OPT_COL_WINDOW_ROWS, cw)
-        e.set_option(sx.OPT_HOST_FUSED, 1 if args.host_fused else 0)
-        e.set_option(sx.OPT_PDL, args.pdl)
-        e.set_option(sx.OPT_PREFETCH, args.prefetch)
-        e.set_option(sx.OPT_WINDOW_ROWS, args.window_rows)
-        e.set_option(sx.OPT_SLIDE, args.slide)
-        e.set_option(sx.OPT_AUTOTUNE, 1 if args.autotune else 0)
-        if args.split >= 0:
-            e.set_option(sx.OPT_SPLIT_ROW_NNZ, args.split)
-        e.upload_csr(M, K, w["rowptr"], w["colidx"], w["val"])
-        with torch.cuda.stream(stream):
-            dB = torch.zeros(K * ld, dtype=tdtype, device=dev)
-            dCin = torch.zeros(M * ld, dtype=tdtype, device=dev)
-            dCout = torch.zeros(M * ld, dtype=tdtype, device=dev)
-            e.colmajor_to_rowmajor(K, N, dB_cm, dB, ld)
-            e.colmajor_to_rowmajor(M, N, dC_cm, dCin, ld)
-            if world > 1 and rank != 0:
-                dB.zero_()          # non-root ranks receive B through the broadcast
-        engines.append(e); dBs.append(dB); dCins.append(dCin); dCouts.append(dCout)
-    eng = engines[0]
-    stream.synchronize()
-
-    # N > 1: how B reaches the other ranks.  Small B: every rank pulls the root's image with a
-    # peer copy over NVLink ordered by device-side step counters (PeerBroadcast); large B
-    # (or if CUDA IPC is not available): one NCCL broadcast.
-    peer = None
-    exchange = "none"
-    if world > 1:
-        exchange = "one NCCL broadcast of B from rank 0 inside every step"
-        if K * ld * s <= args.peer_bytes:
-            try:
-                from sextans_b200.rowblock import PeerBroadcast
-                for j in range(R):                      # the engines' own B images are the operands here
-                    ptr, _ = engines[j].device_B(N)          # zero-filled; only the root holds B
-                    if rank == 0:
-                        engines[j].colmajor_to_rowmajor(K, N, dB_cm, ptr, ld)
-                    dBs[j] = ptr
-                stream.synchronize()
-                peer = PeerBroadcast(engines, N, fused=(args.peer_mode == "fused"))
-                exchange = ("B pulled from rank 0 over NVLink by one fused kernel per step (spin on the step flag, copy, acknowledge)" if args.peer_mode == "fused" else "peer copy of B from rank 0 over NVLink (copy engine) ordered by stream memory operations") + ", inside every step"
-            except Exception as ex:                     # no IPC in this sandbox: keep NCCL
-                peer = None
-                exchange += f" (peer path unavailable: {type(ex).__name__})"
-    step_no = [0]
-    copy_stream = torch.cuda.Stream(device=dev) if peer is not None else None
-
-    def step_device(i):
-        j = i % R
-        if peer is not None:
-            # the pull of step k runs on its own stream, so it overlaps the SpMM of step k-1
-            step_no[0] += 1
-            assert (step_no[0] - 1) % R == j
-            if rank == 0:
-                # B is resident and constant here, so publishing step k does not depend on the
-                # SpMM stream: it runs beside it (in a pipeline it would follow B's producer)
-                engines[j].set_stream(copy_stream.cuda_stream)
-                peer.publish(step_no[0])
-                engines[j].set_stream(stream.cuda_stream)
-            else:
-                engines[j].set_stream(copy_stream.cuda_stream)
-                peer.pull(step_no[0])
-                engines[j].set_stream(stream.cuda_stream)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-                stream.wait_event(ev)
-        elif world > 1:
-            dist.broadcast(dBs[j], src=0)
-        engines[j].spmm_device(N, ALPHA, dBs[j], ld, BETA, dCins[j], dCouts[j], ld)
+    peak, peak_src = measured_peak()
+    K = args.steps
 
     def barrier():
         torch.cuda.synchronize()
@@ -414,160 +607,181 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def launches():
-        return sum(e.launches for e in engines)
+    # ---- headline ----------------------------------------------------------------------------
+    w = build_workload(args.workload, args.ncols, args.dtype, args.scale, args.band)
+    M, Kc, N, nnz, dtype = w["M"], w["K"], w["N"], w["nnz"], w["dtype"]
+    s = dtype.itemsize
+    ld = (N + 7) // 8 * 8
+    # N > 1 (weak scaling: every rank owns one stacked copy of the matrix): how B reaches the
+    # other ranks inside every step.  Small B: pushed through peer memory; large B: one NCCL broadcast.
+    push = world > 1 and Kc * ld * s <= args.peer_bytes
+    case = Case(w, args, dev, stream, fill_B=(world == 1 or rank == 0), own_B=push)
+    R = case.R
+    alg_bytes = case.alg_bytes
+    xch = None
+    exchange = "none (1 GPU)"
+    extra_streams = ()
+    if world > 1:
+        exchange = "one ncclBroadcast of B from rank 0 inside every step"
+        if push:
+            from sextans_b200.rowblock import PushExchange
+            xch = PushExchange(case.engines, N, device=dev)
+            exchange = xch.describe()
+            extra_streams = xch.extra_streams()
 
-    nwarm = max(3, args.warmup, R)     # every copy is touched (and its plan built) before timing
-    with torch.cuda.stream(stream):
-        for i in range(nwarm):
-            step_device(i)
-    barrier()
+    def step(i):
+        if xch is not None:
+            xch.before_step(i, stream)
+        elif world > 1:
+            dist.broadcast(case.dB[i % R], src=0)
+        case.step(i)
 
     sampler = ClockSampler(local)
     sampler.start()
-    # ---- timed: exactly K steps between two events on the launching stream ------------
-    # The K steps are captured once into a CUDA graph (launch-bound loop: a nasa4704 SpMM
-    # is ~10 us of device work) and the graph is replayed inside the timed region;
-    # --no-graph launches them one by one instead.
+    use_graph = not args.no_graph and (world == 1 or xch is not None)   # NCCL collectives are launched eagerly
+    l0 = case.launches()
+    t = time_steps(step, R, K, args.warmup, stream, args.min_region_ms, use_graph, world, dev, extra_streams=extra_streams)
+    # launches in the timed region: a captured graph holds the launches of its K steps and is replayed once per repetition
+    enq_steps = t["nwarm"] + (t["graphs"] * K if use_graph else (3 + t["reps"]) * K)
+    per_step = (case.launches() - l0) / max(1, enq_steps)
+    launches_dev = int(round(per_step * K * t["reps"]))
+    kern_ms = t["ms_median"]
+    timeouts = case.engines[0].info(sx.INFO_EXCHANGE_TIMEOUTS) if world > 1 else 0
+
+    # the same on ONE copy (L2 warm when the working set fits), for comparison
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0 = launches()
-    graph = None
-    use_graph = not args.no_graph and (world == 1 or peer is not None)   # NCCL collectives are launched eagerly
-    if use_graph:
-        def capture():
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=stream):
-                if copy_stream is not None:
-                    copy_stream.wait_stream(stream)          # fork
-                for i in range(args.steps):
-                    step_device(next_i[0])
-                    next_i[0] += 1
-                if copy_stream is not None:
-                    stream.wait_stream(copy_stream)          # join
-            return g
-        next_i = [nwarm]
-        warm_graph = capture()
-        launches_dev = launches() - l0       # kernels recorded into one graph = launched per replay
-        # step counters only move forward: the timed replay is a second graph over the NEXT K steps
-        graph = capture() if peer is not None else warm_graph
+    nwarm_steps = 200 if alg_bytes < L2_BYTES else 5
+    warm_ms = None
+    if world == 1:
         with torch.cuda.stream(stream):
-            warm_graph.replay()              # one untimed replay
-    barrier()
-    with torch.cuda.stream(stream):
-        e0.record(stream)
-        if graph is not None:
-            graph.replay()
-        else:
-            for i in range(args.steps):
-                step_device(nwarm + i)
-        e1.record(stream)
-    barrier()
-    if graph is None:
-        launches_dev = launches() - l0
-    total_ms = float(e0.elapsed_time(e1))
+            e0.record(stream)
+            for _ in range(nwarm_steps):
+                case.engines[0].spmm_device(N, ALPHA, case.dB[0], ld, BETA, case.dCin[0], case.dCout[0], ld)
+            e1.record(stream)
+        barrier()
+        warm_ms = e0.elapsed_time(e1) / nwarm_steps
 
-    # ---- the same on ONE copy (L2 warm when the working set fits), for comparison ------
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        e0.record(stream)
-        for _ in range(args.steps):
-            eng.spmm_device(N, ALPHA, dBs[0], ld, BETA, dCins[0], dCouts[0], ld)
-        e1.record(stream)
+    # parity of the headline step on every rank (each owns one copy of the matrix; after the timed
+    # region every rank's image 0 holds the B that rank 0 sent)
     barrier()
-    warm_ms = e0.elapsed_time(e1) / args.steps
+    par = parity(case, w, threads=max(1, (os.cpu_count() or 8) // world))
+    perr = torch.tensor([par["max_rel_err"], 0.0 if par["bit_exact"] else 1.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(perr, op=dist.ReduceOp.MAX)
 
-    # ---- one isolated cold launch: flush L2 by overwriting 512 MB, then a single step ---
-    with torch.cuda.stream(stream):
-        flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)
-        iso = []
-        for i in range(5):
-            flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            eng.spmm_device(N, ALPHA, dBs[0], ld, BETA, dCins[0], dCouts[0], ld)
-            b.record(stream)
-            iso.append((a, b))
-    barrier()
-    isolated_ms = float(np.median([a.elapsed_time(b) for a, b in iso]))
-    del flush
-
-    # ---- e2e: host-facing call, pinned host buffers -----------------------------------
-    hB = sx.pinned_empty(K * N, dtype)
+    # ---- e2e: host-facing call, pinned host buffers ------------------------------------------
+    hB = sx.pinned_empty(Kc * N, dtype)
     hC = sx.pinned_empty(M * N, dtype)
     hB[:] = w["B"]
+    e2e_note = "host wall clock around the blocking sx_spmm_* call (H2D of B and C_in, kernels, D2H of C)"
+    sharded = None
+    eng = case.engines[0]
+    if world > 1:
+        from sextans_b200.rowblock import ShardedSpMM
+        if xch is not None:
+            xch.close()
+            xch = None
+        # the stacked matrix: rank r's nnz-balanced row block IS copy r
+        sharded = ShardedSpMM.around(eng, w["val"].dtype, M, Kc, stream, dev.index, peer_bytes=args.peer_bytes)
+        e2e_note = "host wall clock around ShardedSpMM.spmm: B on rank 0's host -> staged, exchanged, every rank's C block in and out over PCIe"
+
+    def e2e_call():
+        if sharded is not None:
+            sharded.spmm(N, ALPHA, hB if rank == 0 else None, BETA, hC)
+        else:
+            eng.spmm(N, ALPHA, hB, BETA, hC)
     for _ in range(3):
         hC[:] = w["Cin"]
-        eng.spmm(N, ALPHA, hB, BETA, hC, want_ns=not args.host_fused)
+        e2e_call()
     checksum = float(np.asarray(hC, dtype=np.float64).sum())
     barrier()
-    l1 = launches()
-    e2e_s = 0.0
-    for _ in range(args.steps):
+    l2 = case.launches()
+    e2e_times = []
+    e2e_steps = max(K, 50)
+    for _ in range(e2e_steps):
         hC[:] = w["Cin"]                       # restore the in/out operand (untimed)
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
-        eng.spmm(N, ALPHA, hB, BETA, hC, want_ns=not args.host_fused)   # H2D B, H2D C, kernels, D2H C; returns synchronised
-        e2e_s += time.perf_counter() - t0
-    launches_e2e = launches() - l1
+        e2e_call()                             # returns synchronised
+        e2e_times.append(time.perf_counter() - t0)
+    launches_e2e = case.launches() - l2
     barrier()
     clocks = sampler.result()
-
-    # ---- reduce over ranks: max time ---------------------------------------------------
-    t = torch.tensor([total_ms, e2e_s, warm_ms], dtype=torch.float64, device=dev)
+    e2e_t = torch.tensor(e2e_times, dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_s, warm_ms = t.tolist()
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_t.median().item()) * 1e3
+    host_path = {1: "zero-copy kernels over PCIe (no memcpy)", 2: "zero-copy, C carried by the SpMM kernel"}.get(
+        eng.info(sx.INFO_HOST_PATH), "cudaMemcpyAsync + layout kernels")
+    if sharded is not None:
+        host_path = f"ShardedSpMM ({sharded.last_exchange} exchange of B)"
+        sharded.close(keep_engine=True)
+    kernel_name = case.kernel_name()
+    case.close()
+    del hB, hC
+
+    # ---- the other BASELINE configs ------------------------------------------------------------
+    configs = {}
+    pool = (CONFIGS_1GPU + CONFIGS_EXTRA) if world == 1 else CONFIGS_NGPU
+    if args.configs == "none":
+        wanted = []
+    elif args.configs == "all":
+        wanted = CONFIGS_1GPU if world == 1 else CONFIGS_NGPU
+    else:
+        keys = set(args.configs.split(","))
+        wanted = [c for c in pool if c[0] in keys]
+    for key, wname, n in wanted:
+        try:
+            configs[key] = run_config(key, wname, n, args, dev, stream, world, rank, peak)
+        except Exception as ex:                                  # one config must not take the line down
+            if world > 1:
+                raise
+            configs[key] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
 
     flops_step = 2.0 * nnz * N * world
-    value = flops_step * args.steps / (total_ms * 1e-3) / 1e9
-    e2e = flops_step * args.steps / e2e_s / 1e9
-    kern_ms = total_ms / args.steps       # N=1: the step is exactly one SpMM kernel launch
-    peak, peak_src = measured_peak()
-    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-
-    lk = eng.info(sx.INFO_LAST_KERNEL)
-    if eng.info(sx.INFO_TILE_NNZ) > 0:
-        tiles_note = (f"; dense tiles: {eng.info(sx.INFO_TILE_NNZ)} nnz in {eng.info(sx.INFO_TILE_SLOTS)} slots "
-                      f"(fill {eng.info(sx.INFO_TILE_NNZ) / max(1, eng.info(sx.INFO_TILE_SLOTS)):.2f}) on spmm_panels_dmma_kernel, "
-                      f"{eng.info(sx.INFO_REST_NNZ)} nnz left to CSR")
-    else:
-        tiles_note = ""
-    kernel_name = ({1: "spmm_rows_kernel (+segments/finalize)", 2: "spmm_staged_kernel", 3: "spmm_window_kernel", 4: "spmm_panels_dmma_kernel", 6: "spmm_window_hostc_kernel", 7: "spmm_slide_kernel", 8: "spmm_edgelist_kernel"}.get(lk // 10000, "?")
-                   + f" <G={lk % 10000 // 100}, VPL={lk % 100 // 10}, {'fast' if lk % 10 else 'strict'}>"
-                   if lk // 10000 != 5 else f"spmm_staged_kernel<WIN>, {lk % 10000} column-window passes of {cw} columns each") + (
-                   (f", {eng.info(sx.INFO_ITEMS)} items of <= {eng.info(sx.INFO_ITEM_NNZ)} nnz, {eng.info(sx.INFO_SPLIT_ROWS)} split rows" if lk // 10000 == 2 else "") + tiles_note)
-    host_path = {1: "zero-copy kernels over PCIe (no memcpy)", 2: "zero-copy, C carried by the SpMM kernel (SX_OPT_HOST_FUSED)"}.get(eng.info(sx.INFO_HOST_PATH), "cudaMemcpyAsync + layout kernels")
+    value = flops_step / (kern_ms * 1e-3) / 1e9
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9        # per GPU: every rank moves its own copy's bytes
     if rank == 0:
         line = {
             "metric": "SpMM GFLOP/s (2*nnz*N)", "value": value, "unit": "GFLOP/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
             "ms_per_step": kern_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64" if dtype == np.float64 else "f32",
-            "data": "synthetic" if w["name"] in ("uniform", "powerlaw") else "SuiteSparse fixture shipped with the reference, host program's B/C",
-            "config": {"workload": w["desc"], "alpha": ALPHA, "beta": BETA, "arith": args.arith,
-                       "l2": "warm (--no-flush)" if args.no_flush else (f"inputs larger than L2: {R} independent device copies of A/B/C ({R * alg_bytes / 1e6:.0f} MB > 2 x 126 MB L2), step i uses copy i mod {R}; no flush kernel in the timed region" if R > 1 else f"inputs larger than L2: one copy is {alg_bytes / 1e6:.0f} MB; steps run back to back"),
-                       "launch": f"the {args.steps} steps are one CUDA graph replay" if use_graph else "one by one",
-                       "partition": "1 row block" if world == 1 else f"{world} stacked row blocks, one per GPU; {exchange}"},
-            "gflops_ref_formula": 2.0 * (nnz + M) * N * world * args.steps / (total_ms * 1e-3) / 1e9,
-            "single_copy_back_to_back": {"ms_per_step": warm_ms, "value": flops_step / (warm_ms * 1e-3) / 1e9,
-                                         "gbs": alg_bytes / (warm_ms * 1e-3) / 1e9, "note": "L2-warm when one copy fits in L2"},
-            "isolated_cold_launch": {"ms": isolated_ms, "note": "512 MB overwritten, then ONE step between two events (includes ~5 us event-to-event launch floor)"},
+            "data": data_label(w),
+            "configs": configs,
+            "parity": {"max_rel_err_all_ranks": float(perr[0].item()), "bit_exact_all_ranks": bool(perr[1].item() == 0.0),
+                       "rows_checked_per_rank": M, "against": "oracle.spmm_csr (cpu_spmm_CSR restated), every row",
+                       "exchange_timeouts": int(timeouts)},
+            "config": config_of(w),
+            "run": {"arith": args.arith,
+                    "l2": "warm (--no-flush)" if args.no_flush else (
+                        f"cold: {R} device copies of A/B/C ({R * alg_bytes / 1e6:.0f} MB > 2 x 126 MB L2), step i uses copy i mod {R} across all replays"
+                        if R > 1 else f"cold: one copy is {alg_bytes / 1e6:.0f} MB > 2 x L2"),
+                    "timed": f"{t['reps']} repetitions x {K} steps = {t['region_ms']:.1f} ms; ms_per_step = median repetition / {K} (min {t['ms_min'] * 1e3:.3f} us, mean {t['ms_mean'] * 1e3:.3f} us)",
+                    "launch": f"{t['graphs']} CUDA graphs of {K} steps" if use_graph else "one by one",
+                    "partition": "1 row block" if world == 1 else f"{world} stacked copies, one row block per GPU",
+                    "exchange": exchange},
+            "gflops_ref_formula": 2.0 * (nnz + M) * N * world / (kern_ms * 1e-3) / 1e9,
+            "single_copy_back_to_back": None if warm_ms is None else {
+                "ms_per_step": warm_ms, "gflops": 2.0 * nnz * N / (warm_ms * 1e-3) / 1e9, "note": "one copy, launched one by one (L2-warm when it fits)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(w["name"], N, "f64" if s == 8 else "f32"),
-                         "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
-                         "kernel": kernel_name},
-            "e2e": {"value": e2e, "unit": "GFLOP/s", "ms_per_step": e2e_s / args.steps * 1e3,
-                    "h2d_bytes_per_step": (K * N + M * N) * s, "d2h_bytes_per_step": M * N * s,
-                    "timer": "host wall clock around the blocking sx_spmm_* call", "path": host_path},
+                         "algorithmic_bytes": alg_bytes, "peak_source": peak_src, "kernel": kernel_name},
+            "e2e": {"value": flops_step / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": (Kc * N + M * N * world) * s, "d2h_bytes_per_step": M * N * s * world,
+                    "timer": e2e_note, "path": host_path, "steps": e2e_steps, "stat": "median, max over ranks per step"},
             "gpu_launches": int(launches_dev + launches_e2e),
-            "gpu_launches_detail": {"device_steps": int(launches_dev), "e2e_steps": int(launches_e2e)},
+            "gpu_launches_detail": {"timed_device_steps": launches_dev, "e2e_steps": int(launches_e2e)},
             "clocks": clocks, "checksum_C": checksum,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(w, 1)
+            import oracle
+            line["cpu_baseline"] = cpu_baseline(w, max(1, oracle.lib().sx_oracle_max_threads()))
+            line["cpu_baseline"]["one_thread"] = cpu_baseline(w, 1, budget_s=5.0)
         emit(line)
-    for e in engines:
-        e.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -263,7 +263,11 @@ int sx_rowmajor_to_colmajor(sx_ctx *ctx, int dtype, int64_t rows, int cols, cons
 #define SX_IPC_HANDLE_BYTES 64
 int sx_device_alloc(sx_ctx *ctx, size_t bytes, void **dptr);  /* zero-filled */
 int sx_device_free(sx_ctx *ctx, void *dptr);
+/* The handle names the whole driver allocation that contains dptr (small cudaMalloc requests are
+ * carved out of larger blocks); sx_ipc_offset gives dptr's offset inside it, which the importing
+ * side adds to the address sx_ipc_import returns.  A process must open a given handle only once. */
 int sx_ipc_export(sx_ctx *ctx, const void *dptr, unsigned char handle[SX_IPC_HANDLE_BYTES]);
+int sx_ipc_offset(sx_ctx *ctx, const void *dptr, size_t *offset);
 int sx_ipc_import(sx_ctx *ctx, const unsigned char handle[SX_IPC_HANDLE_BYTES], void **dptr);
 int sx_ipc_close(sx_ctx *ctx, void *dptr);
 /* enqueue on the context's stream: *flag = value once everything before it has finished */
@@ -283,14 +287,15 @@ int sx_flag_wait(sx_ctx *ctx, void *flag_dptr, uint32_t value);
  *   on every peer, per image:   ready  (written by the pusher), epoch (SpMMs served; local)
  *   on the pusher, per image:   pushes (pushes done; local), done[peer] (written by the peers)
  * sx_push_B: waits until done[p] >= pushes for every peer (they have finished the SpMM that used the
- *   previous contents), copies this context's B image (N columns) to peer_images[p], then stores
- *   pushes + 1 into peer_ready_flags[p] and into pushes.  npeers <= 15.
+ *   previous contents), copies `bytes` bytes of the row-major B image `image` (16-byte units; what
+ *   sx_device_B reports) to peer_images[p], then stores pushes + 1 into peer_ready_flags[p] and
+ *   into pushes.  npeers <= 15.
  * sx_spmm_expect_push: the NEXT SpMM launch of this context (sx_spmm_device_* / sx_launch_*) waits
  *   until *ready_flag >= *epoch_counter + 1 before it reads B, and when it is complete advances
  *   *epoch_counter and stores it into done_flag (the pusher's done[this peer], peer-mapped).
  *   One-shot.  A wait that sees nothing for ~2 s gives up (SX_INFO_EXCHANGE_TIMEOUTS). */
-int sx_push_B(sx_ctx *ctx, int N, void *const *peer_images, void *const *peer_ready_flags, int npeers,
-              const void *done_flags, void *pushes_counter);
+int sx_push_B(sx_ctx *ctx, const void *image, size_t bytes, void *const *peer_images,
+              void *const *peer_ready_flags, int npeers, const void *done_flags, void *pushes_counter);
 int sx_spmm_expect_push(sx_ctx *ctx, const void *ready_flag, void *epoch_counter, void *done_flag);
 /* enqueue a copy of a peer's row-major B image (same K, same N, same dtype: the bytes
  * sx_device_B reports) into this context's image; marks B as staged. */

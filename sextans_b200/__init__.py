@@ -94,12 +94,13 @@ def lib():
         "sx_device_alloc": ([vp, sz, C.POINTER(vp)], i),
         "sx_device_free": ([vp, vp], i),
         "sx_ipc_export": ([vp, vp, C.c_char_p], i),
+        "sx_ipc_offset": ([vp, vp, C.POINTER(sz)], i),
         "sx_ipc_import": ([vp, C.c_char_p, C.POINTER(vp)], i),
         "sx_ipc_close": ([vp, vp], i),
         "sx_flag_write": ([vp, vp, C.c_uint32], i),
         "sx_flag_write_many": ([vp, C.POINTER(vp), i, C.c_uint32], i),
         "sx_flag_wait": ([vp, vp, C.c_uint32], i),
-        "sx_push_B": ([vp, i, C.POINTER(vp), C.POINTER(vp), i, vp, vp], i),
+        "sx_push_B": ([vp, vp, sz, C.POINTER(vp), C.POINTER(vp), i, vp, vp], i),
         "sx_spmm_expect_push": ([vp, vp, vp, vp], i),
         "sx_pull_B": ([vp, i, vp], i),
         "sx_pull_B_fused": ([vp, i, vp, vp, vp, C.c_uint32], i),
@@ -516,6 +517,12 @@ class Engine:
         _check(self._L.sx_ipc_export(self._ctx, C.c_void_p(ptr), buf))
         return buf.raw
 
+    def ipc_export_ref(self, ptr):
+        """(handle of the allocation that contains ptr, offset of ptr inside it) -- what a peer needs."""
+        off = C.c_size_t()
+        _check(self._L.sx_ipc_offset(self._ctx, C.c_void_p(ptr), C.byref(off)))
+        return self.ipc_export(ptr), off.value
+
     def ipc_import(self, handle: bytes) -> int:
         p = C.c_void_p()
         _check(self._L.sx_ipc_import(self._ctx, C.create_string_buffer(handle, 64), C.byref(p)))
@@ -538,12 +545,13 @@ class Engine:
         _check(self._L.sx_pull_B_fused(self._ctx, N, C.c_void_p(peer_image_ptr), C.c_void_p(ready_flag),
                                        C.c_void_p(done_flag), step & 0xFFFFFFFF))
 
-    def push_B(self, N, peer_image_ptrs, peer_ready_ptrs, done_flags_ptr, pushes_ptr):
-        """Copy this context's B image into every peer's (one kernel); see sx_push_B."""
+    def push_B(self, image_ptr, nbytes, peer_image_ptrs, peer_ready_ptrs, done_flags_ptr, pushes_ptr):
+        """Copy a row-major B image into every peer's (one kernel); see sx_push_B."""
         n = len(peer_image_ptrs)
         imgs = (C.c_void_p * n)(*peer_image_ptrs)
         rdy = (C.c_void_p * n)(*peer_ready_ptrs)
-        _check(self._L.sx_push_B(self._ctx, N, imgs, rdy, n, C.c_void_p(done_flags_ptr), C.c_void_p(pushes_ptr)))
+        _check(self._L.sx_push_B(self._ctx, C.c_void_p(image_ptr), nbytes, imgs, rdy, n, C.c_void_p(done_flags_ptr),
+                                 C.c_void_p(pushes_ptr)))
 
     def expect_push(self, ready_ptr, epoch_ptr, done_ptr):
         """The next SpMM launch waits for the push into its B image and acknowledges it (sx_spmm_expect_push)."""

@@ -692,6 +692,22 @@ spmm_window_kernel(const int M, const int4 *__restrict__ blocks, const int *__re
 // image again.  Counters live in device memory, so a captured launch can be replayed; the
 // exchange costs this rank no launch of its own.
 constexpr int SX_EDGE_PREFETCH = 1;
+// -DSX_EDGE_TRACE (scripts/build_variant.sh): every block records %globaltimer at its phase
+// boundaries into a device array read back by sx_debug_edge_trace -- how a ~3.5 us step splits
+// into launch, prologue, dependent-launch wait, window staging and arithmetic.
+#ifdef SX_EDGE_TRACE
+constexpr int SX_TRACE_ROWS = 1 << 16;
+__device__ unsigned long long sx_edge_trace[SX_TRACE_ROWS][8];
+__device__ unsigned int sx_edge_trace_count;
+__device__ __forceinline__ unsigned long long sx_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define SX_TRACE_MARK(i) do { if (threadIdx.x == 0 && trace_row < SX_TRACE_ROWS) sx_edge_trace[trace_row][i] = sx_now(); } while (0)
+#else
+#define SX_TRACE_MARK(i) do { } while (0)
+#endif
 template <int G> struct EdgeShape {
     static constexpr int THREADS = G >= 16 ? 512 : 256;
     static constexpr int ROWS = THREADS / G;
@@ -707,6 +723,19 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
     constexpr int THREADS = EdgeShape<G>::THREADS, ROWS = EdgeShape<G>::ROWS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;  // the A slice and the column list
+#ifdef SX_EDGE_TRACE
+    unsigned int trace_row = SX_TRACE_ROWS;
+    if (threadIdx.x == 0) {
+        trace_row = atomicAdd(&sx_edge_trace_count, 1u);
+        if (trace_row < SX_TRACE_ROWS) {
+            unsigned int smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            sx_edge_trace[trace_row][6] = blockIdx.x;
+            sx_edge_trace[trace_row][7] = smid;
+        }
+    }
+    SX_TRACE_MARK(0);
+#endif
     pdl_launch_dependents();
     const int lg = threadIdx.x & (G - 1);
     const int rl = threadIdx.x / G;
@@ -749,7 +778,9 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
             bulk_prefetch_l2(reinterpret_cast<const unsigned char *>(Cin) + (size_t)b0.x * ldcv * 16u, (uint32_t)b0.y * ldcv * 16u);
     }
     // ---- B and C_in: only after the previous kernel is complete ----
+    SX_TRACE_MARK(1);
     pdl_wait();
+    SX_TRACE_MARK(2);
     uint32_t step = 0;
     if (ready != nullptr) {  // multi-GPU: the pushed B image of this step has landed
         if ((threadIdx.x & 31) == 0) {
@@ -771,6 +802,7 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
     if (mine) cin = reinterpret_cast<const V *>(Cin)[(size_t)row * ldcv + lg];
     cp_async_wait_all();
     __syncthreads();
+    SX_TRACE_MARK(3);
     if (mine) {
         const T *sv = sval - jal;  // sv[j] = value of nonzero j
         const uint16_t *sc = scol - jal;
@@ -819,6 +851,11 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
         }
         reinterpret_cast<V *>(Cout)[(size_t)row * ldcv + lg] = vaxpby<STRICT>(alpha, acc, beta, cin);
     }
+#ifdef SX_EDGE_TRACE
+    SX_TRACE_MARK(4);      // thread 0 done with its own row
+    __syncthreads();
+    SX_TRACE_MARK(5);      // every row of the block done
+#endif
     if (ready != nullptr) {  // multi-GPU: tell the pusher that this rank is done with the image
         __syncthreads();
         if (threadIdx.x == 0) {

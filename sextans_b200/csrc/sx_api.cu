@@ -1794,14 +1794,44 @@ int sx_device_free(sx_ctx *c, void *dptr) {
     return SX_OK;
 }
 
+namespace {
+// base address of the allocation that contains dptr (the driver sub-allocates small cudaMalloc
+// requests from larger blocks, and an IPC handle always names the whole block)
+typedef CUresult (*GetAddressRangeFn)(CUdeviceptr *, size_t *, CUdeviceptr);
+int allocation_base(const void *dptr, void **base) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    SX_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) return fail(SX_ERR_CUDA, "cuMemGetAddressRange is not available in this driver");
+    CUdeviceptr b = 0;
+    size_t size = 0;
+    const CUresult r = ((GetAddressRangeFn)fn)(&b, &size, (CUdeviceptr)(uintptr_t)dptr);
+    if (r != CUDA_SUCCESS) return fail(SX_ERR_CUDA, "cuMemGetAddressRange failed with CUresult %d", (int)r);
+    *base = (void *)(uintptr_t)b;
+    return SX_OK;
+}
+}  // namespace
+
 int sx_ipc_export(sx_ctx *c, const void *dptr, unsigned char handle[SX_IPC_HANDLE_BYTES]) {
     int rc = bind(c);
     if (rc) return rc;
     static_assert(sizeof(cudaIpcMemHandle_t) == SX_IPC_HANDLE_BYTES, "IPC handle size");
     if (!dptr || !handle) return fail(SX_ERR_INVALID, "null argument");
+    void *base = nullptr;
+    if ((rc = allocation_base(dptr, &base))) return rc;
     cudaIpcMemHandle_t h;
-    SX_CUDA(cudaIpcGetMemHandle(&h, const_cast<void *>(dptr)));
+    SX_CUDA(cudaIpcGetMemHandle(&h, base));
     std::memcpy(handle, &h, sizeof h);
+    return SX_OK;
+}
+
+int sx_ipc_offset(sx_ctx *c, const void *dptr, size_t *offset) {
+    int rc = bind(c);
+    if (rc) return rc;
+    if (!dptr || !offset) return fail(SX_ERR_INVALID, "null argument");
+    void *base = nullptr;
+    if ((rc = allocation_base(dptr, &base))) return rc;
+    *offset = (size_t)((const unsigned char *)dptr - (const unsigned char *)base);
     return SX_OK;
 }
 
@@ -1898,25 +1928,24 @@ int sx_spmm_expect_push(sx_ctx *c, const void *ready_flag, void *epoch_counter, 
     return SX_OK;
 }
 
-int sx_push_B(sx_ctx *c, int N, void *const *peer_images, void *const *peer_ready_flags, int npeers, const void *done_flags,
-              void *pushes_counter) {
-    void *mine = nullptr;
-    size_t bytes = 0;
-    int rc = sx_device_B(c, N, &mine, &bytes);
+int sx_push_B(sx_ctx *c, const void *image, size_t bytes, void *const *peer_images, void *const *peer_ready_flags, int npeers,
+              const void *done_flags, void *pushes_counter) {
+    int rc = bind(c);
     if (rc) return rc;
     if (npeers < 0 || npeers > 15) return fail(SX_ERR_INVALID, "0..15 peers expected (got %d)", npeers);
     if (npeers == 0) return SX_OK;
-    if (!peer_images || !peer_ready_flags || !done_flags || !pushes_counter) return fail(SX_ERR_INVALID, "null argument");
+    if (!image || !peer_images || !peer_ready_flags || !done_flags || !pushes_counter) return fail(SX_ERR_INVALID, "null argument");
+    if (((uintptr_t)image & 15) || (bytes & 15)) return fail(SX_ERR_INVALID, "the image must be 16-byte aligned and a whole number of 16-byte units");
     if ((rc = ensure_sync_words(c))) return rc;
     sx::PushList pl = {};
     for (int i = 0; i < npeers; ++i) {
-        if (!peer_images[i] || !peer_ready_flags[i]) return fail(SX_ERR_INVALID, "null peer pointer");
+        if (!peer_images[i] || !peer_ready_flags[i] || ((uintptr_t)peer_images[i] & 15)) return fail(SX_ERR_INVALID, "bad peer pointer");
         pl.dst[i] = (int4 *)peer_images[i];
         pl.ready[i] = (uint32_t *)peer_ready_flags[i];
     }
-    const int64_t n16 = (int64_t)((bytes + 15) / 16);  // images are allocated in whole 16-byte units
+    const int64_t n16 = (int64_t)(bytes / 16);
     const int grid = (int)std::min<int64_t>(c->sm_count, std::max<int64_t>(1, (n16 + 255) / 256));
-    sx::push_image_kernel<<<grid, 256, 0, c->stream>>>((const int4 *)mine, n16, pl, npeers, (const uint32_t *)done_flags,
+    sx::push_image_kernel<<<grid, 256, 0, c->stream>>>((const int4 *)image, n16, pl, npeers, (const uint32_t *)done_flags,
                                                        (uint32_t *)pushes_counter, (unsigned int *)c->sync_words.p);
     c->launches++;
     SX_CUDA(cudaGetLastError());
@@ -1932,6 +1961,25 @@ int sx_pull_B(sx_ctx *c, int N, const void *peer_B_image) {
     if (bytes) SX_CUDA(cudaMemcpyAsync(mine, peer_B_image, bytes, cudaMemcpyDefault, c->stream));
     return SX_OK;
 }
+
+#ifdef SX_EDGE_TRACE
+// variant builds only (scripts/build_variant.sh trace "-DSX_EDGE_TRACE"): copy out and reset the
+// per-block phase timestamps of spmm_edgelist_kernel; rows of 8 x uint64:
+// {entry, before the dependent-launch wait, after it, window staged, thread 0 done, block done, block, SM}
+int sx_debug_edge_trace(sx_ctx *c, unsigned long long *rows, int max_rows, int *nrows) {
+    int rc = bind(c);
+    if (rc) return rc;
+    SX_CUDA(cudaStreamSynchronize(c->stream));
+    unsigned int n = 0;
+    SX_CUDA(cudaMemcpyFromSymbol(&n, sx::sx_edge_trace_count, 4));
+    n = std::min<unsigned int>(n, (unsigned int)std::min(max_rows, sx::SX_TRACE_ROWS));
+    if (n) SX_CUDA(cudaMemcpyFromSymbol(rows, sx::sx_edge_trace, (size_t)n * 64));
+    const unsigned int zero = 0;
+    SX_CUDA(cudaMemcpyToSymbol(sx::sx_edge_trace_count, &zero, 4));
+    *nrows = (int)n;
+    return SX_OK;
+}
+#endif
 
 int sx_host_alloc(size_t bytes, void **ptr) {
     if (!ptr) return fail(SX_ERR_INVALID, "null ptr");

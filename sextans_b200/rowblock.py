@@ -9,7 +9,8 @@ are no reductions, and a row's arithmetic does not depend on the partition, so t
 result is bitwise the single-GPU result.
 
 ``RowBlock`` is pure host logic (no GPU, no torch); ``ShardedSpMM`` drives one
-``Engine`` per process with ``torch.distributed`` (NCCL over NVLink on the GPUs).
+``Engine`` per process with ``torch.distributed`` (NCCL over NVLink on the GPUs);
+``PushExchange`` is the exchange of a small B through peer memory.
 """
 from __future__ import annotations
 
@@ -47,91 +48,112 @@ class RowBlock:
         return C_colmajor
 
 
-class PeerBroadcast:
-    """B from the root rank's engine(s) to every other rank WITHOUT a collective: each
-    rank pulls the root's row-major B image with a copy-engine peer copy over NVLink, and
-    the ordering is carried by 32-bit step counters in peer-mapped device memory, written
-    and waited on by stream memory operations (sx_flag_write / sx_flag_wait) -- no kernel,
-    no host round trip.  For the SuiteSparse-sized configs this replaces ~60 us of NCCL
-    launch latency per broadcast by a ~10 us peer copy.
+class PushExchange:
+    """B from the root rank to every other rank WITHOUT a collective and without a launch on the
+    receiving side: the root copies its row-major B image into every peer's image with ONE kernel
+    (sx_push_B: posted 16-byte stores over NVLink through CUDA-IPC peer mappings), and a peer's
+    next SpMM waits for the push in its own prologue and acknowledges it from its last block
+    (sx_spmm_expect_push).  All counters are 32-bit words in device memory -- per image: ``ready``
+    and ``epoch`` on a peer, ``pushes`` and ``done[peer]`` on the root -- so captured launches can
+    be replayed.  The multi-GPU form of the reference's chain that hands the B window from PEG to
+    PEG (src/sextans.cpp:909-941).
 
-    ``engines``: this rank's Engine objects (one, or several replicas used round-robin),
-    each with A uploaded.  Step numbers start at 1 and must increase by one per call.
-      root : publish(k)      after B of replica (k-1) % R is staged
-             reclaim(k)      before that replica's B is overwritten again (waits until every
-                             peer has finished pulling step k)
-      peers: pull(k)         waits for publish(k), copies, acknowledges
+    ``engines``: this rank's Engine objects (one, or R replicas used round-robin), each with A
+    uploaded; their own B images (``Engine.device_B(N)``) are the operands.  Step i uses image
+    i % R.  The root enqueues its pushes on a side stream of its own, so they run beside its SpMMs.
     """
+    WORDS = 8192          # mailbox: ready[j] at j, epoch[j] at 256 + j, pushes[j] at 512 + j, done[j][p] at 1024 + 16 j + p
 
-    def __init__(self, engines, N, group=None, root=0, fused=True):
+    def __init__(self, engines, N, device=None, group=None, root=0, side_stream=True):
+        import torch
         import torch.distributed as dist
-        self.engines, self.N, self.root, self.fused, self.group = list(engines), N, root, fused, group
+        self.engines, self.N, self.root, self.group = list(engines), N, root, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.R = len(self.engines)
+        if self.R > 256 or self.world > 16:
+            raise ValueError("PushExchange: at most 256 images and 16 ranks")
         e0 = self.engines[0]
-        self._imported = []
-        if self.rank == root:
-            self.done = e0.device_alloc(4 * self.world)                 # done[r]: last step rank r pulled
-            mine = {"images": [e0_.ipc_export(e0_.device_B(N)[0]) for e0_ in self.engines],
-                    "done": e0.ipc_export(self.done)}
-        else:
-            self.ready = e0.device_alloc(4)                              # last step the root published
-            mine = {"ready": e0.ipc_export(self.ready)}
+        self.images, self.nbytes = [], None
+        for e in self.engines:
+            ptr, nb = e.device_B(N)
+            self.images.append(ptr)
+            self.nbytes = (nb + 15) // 16 * 16
+        self.box = e0.device_alloc(4 * self.WORDS)
+        mine = {"box": e0.ipc_export_ref(self.box), "images": [e0.ipc_export_ref(p) for p in self.images]}
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine, group=group)
+        self._opened = {}                      # IPC handle -> base address in this process (a handle is opened once)
+        self._launches = 0
+        self.side = None
         if self.rank == root:
-            self.peer_ready = {}
-            for r, obj in enumerate(everyone):
-                if r != root:
-                    self.peer_ready[r] = e0.ipc_import(obj["ready"])
-                    self._imported.append(self.peer_ready[r])
+            self.peers = [r for r in range(self.world) if r != root]
+            self.peer_box = {r: self._open(everyone[r]["box"]) for r in self.peers}
+            self.peer_images = {r: [self._open(ref) for ref in everyone[r]["images"]] for r in self.peers}
+            if side_stream:      # B does not change between pushes (or its producer is ordered otherwise): push beside the SpMMs
+                dev = device if device is not None else torch.device("cuda", e0.device)
+                self.side = torch.cuda.Stream(device=dev)
         else:
-            self.root_images = [e0.ipc_import(h) for h in everyone[root]["images"]]
-            self.root_done = e0.ipc_import(everyone[root]["done"])
-            self._imported += self.root_images + [self.root_done]
+            self.pi = [r for r in range(self.world) if r != root].index(self.rank)     # my index among the peers
+            self.root_box = self._open(everyone[root]["box"])
         dist.barrier(group=group)
 
-    def publish(self, k):
-        e = self.engines[(k - 1) % self.R]
-        ptrs = list(self.peer_ready.values())
-        for i in range(0, len(ptrs), 16):              # one small kernel per 16 peers
-            e.flag_write_many(ptrs[i:i + 16], k)
+    def _open(self, ref):
+        handle, offset = ref
+        if handle not in self._opened:
+            self._opened[handle] = self.engines[0].ipc_import(handle)
+        return self._opened[handle] + offset
 
-    def reclaim(self, k):
-        e = self.engines[(k - 1) % self.R]
-        for r in self.peer_ready:
-            e.flag_wait(self.done + 4 * r, k)
+    def describe(self):
+        return (f"B ({self.nbytes / 1e3:.0f} KB) pushed by rank {self.root} into every peer's image over NVLink with one kernel per step "
+                "(posted peer stores); the receiving SpMM kernel waits on the step flag in its prologue and acknowledges from its "
+                "last block: no launch and no collective on the receiving ranks")
 
-    def pull(self, k):
-        j = (k - 1) % self.R
+    def extra_streams(self):
+        return (self.side,) if self.side is not None else ()
+
+    def before_step(self, i, stream=None):
+        """Call right before the SpMM of step i is enqueued on engine i % R."""
+        j = i % self.R
         e = self.engines[j]
-        if self.fused:      # one kernel: spin on the local flag, copy over NVLink, acknowledge
-            e.pull_B_fused(self.N, self.root_images[j], self.ready, self.root_done + 4 * self.rank, k)
-        else:               # stream memory operations around a copy-engine peer copy
-            e.flag_wait(self.ready, k)
-            e.pull_B(self.N, self.root_images[j])
-            e.flag_write(self.root_done + 4 * self.rank, k)
+        if self.rank == self.root:
+            if self.peers:
+                main = None
+                if self.side is not None:
+                    e.set_stream(self.side.cuda_stream)
+                    main = stream
+                e.push_B(self.images[j], self.nbytes, [self.peer_images[r][j] for r in self.peers],
+                         [self.peer_box[r] + 4 * j for r in self.peers], self.box + 4 * (1024 + 16 * j), self.box + 4 * (512 + j))
+                self._launches += 1
+                if main is not None:
+                    e.set_stream(main.cuda_stream)
+        else:
+            e.expect_push(self.box + 4 * j, self.box + 4 * (256 + j), self.root_box + 4 * (1024 + 16 * j + self.pi))
+
+    def launches(self):
+        return self._launches
 
     def close(self):
-        """Collective: every rank unmaps what it imported, then the owners free their flags."""
+        """Collective: every rank unmaps what it imported, then frees its mailbox."""
         import torch.distributed as dist
         e0 = self.engines[0]
-        e0.synchronize()
-        for ptr in self._imported:
-            e0.ipc_close(ptr)
-        self._imported = []
+        for e in self.engines:
+            e.synchronize()
+        if self.side is not None:
+            self.side.synchronize()
         dist.barrier(group=self.group)
-        for name in ("done", "ready"):
-            ptr = getattr(self, name, None)
-            if ptr:
-                e0.device_free(ptr)
-                setattr(self, name, None)
+        for base in self._opened.values():
+            e0.ipc_close(base)
+        self._opened = {}
+        dist.barrier(group=self.group)
+        if self.box:
+            e0.device_free(self.box)
+            self.box = None
 
 
 class ShardedSpMM:
     """One process per GPU.  ``spmm`` moves B from the rank that has it to the others --
-    by peer copy (PeerBroadcast) when the B image is at most ``peer_bytes``, by one NCCL
-    broadcast otherwise -- and runs the local row block; C stays sharded unless ``gather``
+    pushed through peer memory (PushExchange) when the B image is at most ``peer_bytes``, by one
+    NCCL broadcast otherwise -- and runs the local row block; C stays sharded unless ``gather``
     is asked for."""
 
     def __init__(self, M, K, rowptr, colidx, val, device, group=None, arith=0, peer_bytes=8 << 20):
@@ -148,18 +170,33 @@ class ShardedSpMM:
         self.engine.set_stream(self.stream.cuda_stream)
         self.engine.upload_csr(self.block.rows, K, self.block.rowptr, self.block.colidx, self.block.val)
         self.dtype = self.block.val.dtype
+        self.K = K
         self.device = device
         self.peer_bytes = peer_bytes
-        self._peer = None        # (N, src, PeerBroadcast) once set up
-        self._peer_failed = False
-        self._step = 0
+        self._xch = None         # (N, src, image address, PushExchange) once set up
+        self._xch_failed = False
         self.last_exchange = None
 
-    def close(self):
-        if self._peer is not None:
-            self._peer[2].close()
-            self._peer = None
-        self.engine.close()
+    @classmethod
+    def around(cls, engine, dtype, rows, K, stream, device, group=None, peer_bytes=8 << 20):
+        """Wrap an Engine that already holds this rank's row block (no second upload)."""
+        import torch.distributed as dist
+        self = cls.__new__(cls)
+        self.dist, self.group = dist, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.block = None
+        self.engine, self.stream, self.dtype, self.K, self.device = engine, stream, np.dtype(dtype), K, device
+        self.engine.set_stream(stream.cuda_stream)
+        self.peer_bytes = peer_bytes
+        self._xch, self._xch_failed, self.last_exchange = None, False, None
+        return self
+
+    def close(self, keep_engine=False):
+        if self._xch is not None:
+            self._xch[3].close()
+            self._xch = None
+        if not keep_engine:
+            self.engine.close()
 
     def device_B(self, N):
         """torch view of the engine's row-major B image [K, ld] (the broadcast target)."""
@@ -171,42 +208,54 @@ class ShardedSpMM:
         class _Arr:
             __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8" if self.dtype == np.float64 else "<f4",
                                         "data": (ptr, False), "version": 3}
-        return torch.as_tensor(_Arr(), device=f"cuda:{self.device}").view(self.block.K, ld)
+        return torch.as_tensor(_Arr(), device=f"cuda:{self.device}").view(self.K, ld)
 
-    def _peer_for(self, N, src):
-        if self._peer is not None and self._peer[:2] == (N, src):
-            return self._peer[2]
-        if self._peer is not None or self._peer_failed or self.world == 1:
-            return None              # a different N / root than the one the handles were made for
-        _, nbytes = self.engine.device_B(N)
-        ok = nbytes <= self.peer_bytes
-        flags = [None] * self.world
-        self.dist.all_gather_object(flags, bool(ok), group=self.group)
-        if not all(flags):
-            self._peer_failed = True
+    def _exchange_for(self, N, src):
+        """The push exchange for (N, src), rebuilt (collectively) whenever any rank's B image has
+        moved -- a different N re-allocates it, and the peer mappings of the old one would dangle."""
+        if self.world == 1 or self._xch_failed:
             return None
-        try:
-            self._peer = (N, src, PeerBroadcast([self.engine], N, self.group, root=src))
-        except Exception:
-            self._peer_failed = True
+        ptr, nbytes = self.engine.device_B(N)
+        stale = self._xch is None or self._xch[:3] != (N, src, ptr)
+        votes = [None] * self.world
+        self.dist.all_gather_object(votes, (bool(stale), bool(nbytes <= self.peer_bytes)), group=self.group)
+        if not all(v[1] for v in votes):
+            if self._xch is not None:
+                self._xch[3].close()
+                self._xch = None
             return None
-        return self._peer[2]
+        if any(v[0] for v in votes):
+            if self._xch is not None:
+                self._xch[3].close()
+                self._xch = None
+            try:
+                # B is re-staged every call: the push follows it on the engine's stream
+                self._xch = (N, src, ptr, PushExchange([self.engine], N, group=self.group, root=src, side_stream=False))
+            except Exception:
+                self._xch_failed = True
+                self._xch = None
+            flags = [None] * self.world
+            self.dist.all_gather_object(flags, self._xch is not None, group=self.group)
+            if not all(flags):
+                if self._xch is not None:
+                    self._xch[3].close()
+                self._xch, self._xch_failed = None, True
+                return None
+        return self._xch[3]
 
     def spmm(self, N, alpha, B_colmajor_root, beta, C_block_colmajor, src=0, rp_time=1):
         """B_colmajor_root: the K x N column-major host B on rank ``src`` (ignored elsewhere).
         C_block_colmajor: this rank's block (in/out).  Returns the local kernel ns."""
         import torch
-        pb = self._peer_for(N, src)
-        if pb is not None:
-            self._step += 1
+        x = self._exchange_for(N, src)
+        if x is not None:
             if self.rank == src:
-                if self._step > 1:
-                    pb.reclaim(self._step - 1)             # every peer has finished with the previous B
                 self.engine.stage_B(N, B_colmajor_root)    # H2D + layout change on the root only
-                pb.publish(self._step)
+                x.before_step(0)                           # waits for the peers' acknowledgement of the previous B, then pushes
             else:
-                pb.pull(self._step)
-            self.last_exchange = "peer"
+                self.engine.device_B(N)                    # marks B as staged: the push fills it
+                x.before_step(0)                           # the launch below waits for the push and acknowledges it
+            self.last_exchange = "push"
         else:
             if self.rank == src:
                 self.engine.stage_B(N, B_colmajor_root)

@@ -29,7 +29,7 @@ def main():
     cases.append(("random f64 N=32 with a long row", M, K, N, rp, ci, v, B, Cin))
     for name, M, K, N, rp, ci, v, B, Cin in cases:
         dtype = v.dtype.type
-        for peer_bytes, want in ((8 << 20, "peer"), (0, "nccl")):      # both ways of moving B
+        for peer_bytes, want in ((8 << 20, "push"), (0, "nccl")):      # both ways of moving B
             sh = ShardedSpMM(M, K, rp, ci, v, local, peer_bytes=peer_bytes)
             sh.engine.set_option(sx.OPT_SPLIT_ROW_NNZ, 0)          # everything in stored order: bitwise
             for rep in range(2):                                       # twice: B is re-staged and re-sent
@@ -43,39 +43,80 @@ def main():
             if rank == 0:
                 print(f"OK {name} via {want}: {world} row blocks == oracle bitwise; rank-0 kernel {ns / 2e3:.1f} us", flush=True)
             sh.close()
-    # the same exchange without a collective: peers pull the root's B over NVLink, ordered by
-    # device-side step counters (PeerBroadcast); several steps with a B that changes each time
-    from sextans_b200.rowblock import PeerBroadcast, RowBlock
+    # the push exchange on its own (PushExchange): several steps with a B that changes each time,
+    # R = 3 images used round-robin, launches captured in a CUDA graph and replayed (the counters
+    # live in device memory), and a different N afterwards through ShardedSpMM (the exchange is rebuilt)
+    from sextans_b200.rowblock import PushExchange, RowBlock
     M, K, N = 4000, 3000, 16
     rp, ci, v = random_csr(M, K, 10, 5, np.float64)
     blk = RowBlock(M, K, rp, ci, v, world, rank)
-    eng = sx.Engine(local)
-    eng.upload_csr(blk.rows, K, blk.rowptr, blk.colidx, blk.val)
-    eng.device_B(N)
-    for fused in (True, False):      # one fused kernel per pull / stream memory ops around a peer copy
-        pb = PeerBroadcast([eng], N, fused=fused)
-        for k in range(1, 6):
-            B, Cin = random_dense(M, K, N, 100 + k + 10 * fused, np.float64)   # every rank can rebuild the root's B to check
-            Cb = blk.take_C(Cin, N)
-            if rank == 0:
-                if k > 1:
-                    pb.reclaim(k - 1)                                  # peers are done with the previous B
-                eng.stage_B(N, B)
-                pb.publish(k)
-            else:
-                pb.pull(k)
-            eng.stage_C(N, Cb)
-            eng.launch(0.85, -2.06)
-            eng.fetch_C(Cb)
-            ref = oracle.spmm_csr(blk.rows, N, K, blk.rowptr, blk.colidx, blk.val, 0.85, B, -2.06, blk.take_C(Cin, N))
-            assert Cb.tobytes() == ref.tobytes(), (rank, k, fused)
+    engs = []
+    stream = torch.cuda.Stream()
+    for _ in range(3):
+        e = sx.Engine(local)
+        e.set_stream(stream.cuda_stream)
+        e.upload_csr(blk.rows, K, blk.rowptr, blk.colidx, blk.val)
+        engs.append(e)
+    px = PushExchange(engs, N, side_stream=False)      # B changes every step: the push follows its staging in stream order
+    ld = 16
+    for k in range(7):
+        j = k % 3
+        eng = engs[j]
+        B, Cin = random_dense(M, K, N, 100 + k, np.float64)   # every rank can rebuild the root's B to check
+        Cb = blk.take_C(Cin, N)
         if rank == 0:
-            pb.reclaim(5)
-        eng.synchronize()
-        dist.barrier()
-        pb.close()
+            eng.stage_B(N, B)
+        else:
+            eng.device_B(N)
+        px.before_step(k, stream)
+        eng.stage_C(N, Cb)
+        eng.launch(0.85, -2.06)
+        eng.fetch_C(Cb)
+        ref = oracle.spmm_csr(blk.rows, N, K, blk.rowptr, blk.colidx, blk.val, 0.85, B, -2.06, blk.take_C(Cin, N))
+        assert Cb.tobytes() == ref.tobytes(), (rank, k)
+        assert eng.info(sx.INFO_EXCHANGE_TIMEOUTS) == 0
+    # graph replay: the same three launches (and, on the root, pushes) replayed four times
+    dCin = [torch.zeros(blk.rows * ld, dtype=torch.float64, device="cuda") for _ in range(3)]
+    dCout = [torch.zeros(blk.rows * ld, dtype=torch.float64, device="cuda") for _ in range(3)]
+    torch.cuda.synchronize()
+    dist.barrier()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=stream):
+        for x in px.extra_streams():
+            x.wait_stream(stream)
+        for k in range(3):
+            px.before_step(k, stream)
+            engs[k].spmm_device(N, 0.85, engs[k].device_B(N)[0], ld, -2.06, dCin[k], dCout[k], ld)
+        for x in px.extra_streams():
+            stream.wait_stream(x)
+    for _ in range(4):
+        with torch.cuda.stream(stream):
+            g.replay()
+    torch.cuda.synchronize()
+    assert all(e.info(sx.INFO_EXCHANGE_TIMEOUTS) == 0 for e in engs)
+    dist.barrier()
+    px.close()
     if rank == 0:
-        print("OK peer pull of B over NVLink (fused kernel and memory-op variants): 5 steps each, bitwise on every rank", flush=True)
+        print("OK push of B through peer memory: 7 steps over 3 images bitwise on every rank, 4 graph replays without a time-out", flush=True)
+    for e in engs[1:]:
+        e.close()
+    eng = engs[0]
+    # a different N on the same ShardedSpMM: the B image moves, the exchange is rebuilt, no stale mapping
+    M, K = 3000, 2500
+    rp, ci, v = random_csr(M, K, 9, 8, np.float32)
+    sh = ShardedSpMM(M, K, rp, ci, v, local)
+    for N in (8, 40, 8):
+        B, Cin = random_dense(M, K, N, 50 + N, np.float32)
+        Cb = sh.block.take_C(Cin, N)
+        sh.spmm(N, np.float32(0.85), B if rank == 0 else None, np.float32(-2.06), Cb)
+        assert sh.last_exchange == "push"
+        full = sh.gather(Cb, N, dst=0)
+        if rank == 0:
+            ref = oracle.spmm_csr(M, N, K, rp, ci, v, np.float32(0.85), B, np.float32(-2.06), Cin.copy())
+            assert full.tobytes() == ref.tobytes(), N
+    sh.close()
+    if rank == 0:
+        print("OK ShardedSpMM with N = 8, 40, 8: the push exchange follows the B image, bitwise", flush=True)
     eng.close()
     dist.barrier()
     dist.destroy_process_group()
