@@ -664,7 +664,7 @@ spmm_window_kernel(const int M, const int4 *__restrict__ blocks, const int *__re
 // pcrystk02: 317 against 918): a third of the bytes through L2 and of the shared memory, so 4-6
 // blocks share an SM instead of 1-2, and the index stream of A shrinks from 4 to 2 bytes per nonzero.
 //   block record (two int4): {row_begin, nrows, nnz_begin, nnz_end} {col_begin, ncols, -, smem}
-//   shared memory:           window ncols x row bytes | values | local columns | column list
+//   shared memory:           window ncols x (G x 16 bytes) | values | local columns | column list
 //                            (A slice from the 8-entry boundary at or below nnz_begin: whole 16-byte units)
 // One lane group per row, stored order, so strict mode is bit-identical to cpu_spmm_CSR.
 // 256 threads per block (512 for 16-lane groups), i.e. ROWS = 128 / 64 / 32 / 32 rows for G = 2 / 4 / 8 / 16.
@@ -742,8 +742,8 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
     const int4 b0 = __ldg(blocks + 2 * blockIdx.x), b1 = __ldg(blocks + 2 * blockIdx.x + 1);
     const int jb = b0.z, je = b0.w;
     const int ncols = b1.y;
-    const uint32_t rowbytes = ldbv * 16u;
-    const uint32_t wbytes = (uint32_t)ncols * rowbytes;
+    const uint32_t rowbytes = ldbv * 16u;                     // a row of the B image in global memory
+    const uint32_t wbytes = (uint32_t)ncols * (G * 16u);      // a staged row: G vectors, whatever the image's leading dimension
     const int jal = jb & ~7;
     const bool has = je > jb;
     const uint32_t na = has ? (uint32_t)((je - jal + 7) & ~7) : 0u;
@@ -795,7 +795,7 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
     }
     if (lg < nvec)
         for (int lr = rl; lr < ncols; lr += ROWS)
-            cp_async_16(win + ((size_t)lr * ldbv + lg) * 16, Bb + (size_t)(uint32_t)scols[lr] * rowbytes);
+            cp_async_16(win + ((size_t)lr * G + lg) * 16, Bb + (size_t)(uint32_t)scols[lr] * rowbytes);
     V acc, cin;
     vzero(acc);
     vzero(cin);
@@ -806,7 +806,7 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
     if (mine) {
         const T *sv = sval - jal;  // sv[j] = value of nonzero j
         const uint16_t *sc = scol - jal;
-        const V *w = reinterpret_cast<const V *>(win) + lg;  // w[local column * ldbv] = this lane's piece of that B row
+        const V *w = reinterpret_cast<const V *>(win) + lg;  // w[local column * G] = this lane's piece of that B row
         // chunks of 8 nonzeros, software-pipelined: the (column, value) pairs of chunk k+1 and the
         // eight B-row pieces of chunk k are in flight while the ordered chain of additions of chunk k runs
         constexpr int UC = 8;
@@ -819,7 +819,7 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
             for (;;) {
                 V b[UC];
 #pragma unroll
-                for (int u = 0; u < UC; ++u) b[u] = w[c[u] * ldbv];
+                for (int u = 0; u < UC; ++u) b[u] = w[c[u] * G];
                 const int jn = j + UC;
                 const bool more = jn + UC <= end;
                 uint32_t c2[UC];
@@ -844,7 +844,7 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
 #pragma unroll
             for (int u = 0; u < UC; ++u) { const int ju = min(j + u, end - 1); c[u] = sc[ju]; a[u] = sv[ju]; }
 #pragma unroll
-            for (int u = 0; u < UC; ++u) b[u] = w[c[u] * ldbv];
+            for (int u = 0; u < UC; ++u) b[u] = w[c[u] * G];
 #pragma unroll
             for (int u = 0; u < UC; ++u)
                 if (j + u < end) vmac<STRICT>(acc, a[u], b[u]);

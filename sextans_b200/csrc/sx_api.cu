@@ -239,7 +239,8 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
     bool window_ok = false;
     if constexpr (G <= 16 && VPL == 1) {
         wsmem = (size_t)c->max_span * (size_t)(ldb / sx::VecOf<T>::E) * 16 + ((size_t)c->max_block_nnz + 8) * (sizeof(T) + 4) + 16;
-        window_ok = c->nwblocks > 0 && wsmem <= 200 * 1024;
+        // the window is copied as whole rows of the image: only for a panel that starts at column 0
+        window_ok = c->nwblocks > 0 && wsmem <= 200 * 1024 && c->win_col0 == 0;
     }
     // ... and it is chosen automatically when two blocks fit on an SM, or when the whole
     // matrix is a few waves of one block per SM (the latency regime, where it is 1.3-2.7x
@@ -253,8 +254,9 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
     if constexpr (G <= 16 && VPL == 1) {
         if ((c->kernel == 0 || c->kernel == 5) && !c->win_mode && c->M > 0) {
             const EdgePlan *ep = nullptr;
-            if ((rc = get_edge_plan(c, (int)(ldb * sizeof(T)), (int)sizeof(T), sx::EdgeShape<G>::ROWS, &ep))) return rc;
-            if (ep && ep->usable && ldb == ldc) {
+            // a staged row is G vectors wide whatever the leading dimension: the plan depends on G only
+            if ((rc = get_edge_plan(c, G * 16, (int)sizeof(T), sx::EdgeShape<G>::ROWS, &ep))) return rc;
+            if (ep && ep->usable) {
                 constexpr int E = sx::VecOf<T>::E;
                 auto kern = sx::spmm_edgelist_kernel<T, G, STRICT>;
                 if (ep->max_smem > 48 * 1024 &&
@@ -307,7 +309,7 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
     if (c->win_mode) variant = 2;  // a column-window pass: only the staged kernel carries running sums
     // SX_OPT_KERNEL = 4 (experimental): the sliding-window kernel, where a plan exists and fits
     if constexpr (G <= 16 && VPL == 1) {
-        if (c->kernel == 4 && c->slide_nchains > 0 && !c->win_mode) {
+        if (c->kernel == 4 && c->slide_nchains > 0 && !c->win_mode && c->win_col0 == 0) {
             constexpr int E = sx::VecOf<T>::E;
             uint32_t R = 32;
             while (R < (uint32_t)c->slide_ring_rows) R <<= 1;

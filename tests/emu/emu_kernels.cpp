@@ -603,7 +603,7 @@ void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, u
     int32_t *blocks = nullptr, *cols = nullptr;
     uint16_t *lcol = nullptr;
     int64_t total = 0, ncols = 0;
-    if (sx_plan_edge_lists(M, K, a.rp.data(), a.ci.data(), (int)(ld * sizeof(T)), (int)sizeof(T), ROWS, budget, &nb, &blocks,
+    if (sx_plan_edge_lists(M, K, a.rp.data(), a.ci.data(), G * 16, (int)sizeof(T), ROWS, budget, &nb, &blocks,
                            &ncols, &cols, &lcol, &total, &max_smem) != 0) {
         std::printf("edge lists: plan FAILED\n");
         ++failures;
