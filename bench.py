@@ -625,13 +625,12 @@ def run_native(args):
         exchange = "one ncclBroadcast of B from rank 0 inside every step"
         if push:
             from sextans_b200.rowblock import PushExchange
-            xch = PushExchange(case.engines, N, device=dev)
+            xch = PushExchange(case.engines, N)
             exchange = xch.describe()
-            extra_streams = xch.extra_streams()
 
     def step(i):
         if xch is not None:
-            xch.before_step(i, stream)
+            xch.before_step(i)
         elif world > 1:
             dist.broadcast(case.dB[i % R], src=0)
         case.step(i)

@@ -297,6 +297,14 @@ int sx_flag_wait(sx_ctx *ctx, void *flag_dptr, uint32_t value);
 int sx_push_B(sx_ctx *ctx, const void *image, size_t bytes, void *const *peer_images,
               void *const *peer_ready_flags, int npeers, const void *done_flags, void *pushes_counter);
 int sx_spmm_expect_push(sx_ctx *ctx, const void *ready_flag, void *epoch_counter, void *done_flag);
+/* sx_spmm_fuse_push: on the rank that holds B, make the push PART OF the next SpMM launch of this
+ *   context (sx_spmm_device_* / sx_launch_*): its thread blocks copy the B image that launch reads
+ *   (all K rows, from column 0) into the peers' images on their way to their rows, and its last
+ *   block publishes the step -- compute and exchange in one kernel, nothing else launched on any
+ *   rank.  Same arguments and counters as sx_push_B.  One-shot.  (Kernels other than the
+ *   edge-list variant run the push as a kernel of its own right before them.) */
+int sx_spmm_fuse_push(sx_ctx *ctx, void *const *peer_images, void *const *peer_ready_flags, int npeers,
+                      const void *done_flags, void *pushes_counter);
 /* enqueue a copy of a peer's row-major B image (same K, same N, same dtype: the bytes
  * sx_device_B reports) into this context's image; marks B as staged. */
 int sx_pull_B(sx_ctx *ctx, int N, const void *peer_B_image);
@@ -334,14 +342,17 @@ int sx_partition_rows(int M, const int32_t *rowptr, int parts, int32_t *bounds);
  * Arrays are malloc'ed; release each with sx_free. */
 int sx_plan_slide(int M, const int32_t *rowptr, const int32_t *colidx, int nchains_wanted, int *nsteps,
                   int32_t **steps, int *nchains, int32_t **chains, int *ring_rows, int *max_step_entries);
-/* Plan of the edge-list kernel (variant 5; host only).  Row blocks of up to rows_per_block
- * consecutive rows, each with the ascending list of the DISTINCT columns its nonzeros touch -- the
- * block's compacted B window -- and, per nonzero, the 16-bit index of its column inside that
- * window: the GPU form of the reference's window-local column field (col14 of the packed edge
- * word, src/sparse_helper.h:419-443, src/sextans.cpp:398-402).
- *   row_bytes    bytes of one row of the row-major B image (leading dimension x element size)
- *   smem_budget  shared memory one block may use (window + its slices of values, local columns
- *                and its column list)
+/* Plan of the edge-list kernel (variant 5; host only).  Row blocks of consecutive rows holding
+ * about the same number of nonzeros, each with the ascending list of the DISTINCT columns its
+ * nonzeros touch -- the block's compacted B window -- and, per nonzero, the 16-bit index of its
+ * column inside that window: the GPU form of the reference's window-local column field (col14 of
+ * the packed edge word, src/sparse_helper.h:419-443, src/sextans.cpp:398-402) and of its
+ * equal-length PE lists (:345-403).
+ *   row_bytes    bytes of one staged B row in shared memory (lanes per row x 16)
+ *   max_rows     most rows a block may hold
+ *   nnz_target   nonzeros per block to aim for (0: blocks of max_rows rows)
+ *   smem_budget  shared memory one block may use (window + its slices of values and local
+ *                columns + its column list + its row pointers)
  *   blocks  8 ints per block: {row_begin, nrows, nnz_begin, nnz_end, col_begin, ncols, 0, smem_bytes}
  *   cols    *ncols ints: the blocks' column lists back to back, each starting at a multiple of 4
  *           entries; pad entries repeat the block's last column
@@ -351,8 +362,8 @@ int sx_plan_slide(int M, const int32_t *rowptr, const int32_t *colidx, int nchai
  * *nblocks = 0 (and SX_OK) if some single row does not fit the budget.  Arrays are malloc'ed;
  * release each with sx_free. */
 int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colidx, int row_bytes, int elem_bytes,
-                       int rows_per_block, int smem_budget, int *nblocks, int32_t **blocks, int64_t *ncols,
-                       int32_t **cols, uint16_t **lcol, int64_t *total_cols, int *max_smem);
+                       int max_rows, int64_t nnz_target, int smem_budget, int *nblocks, int32_t **blocks,
+                       int64_t *ncols, int32_t **cols, uint16_t **lcol, int64_t *total_cols, int *max_smem);
 int sx_split_col_windows(int M, int K, const int32_t *rowptr, const int32_t *colidx, int window_rows,
                          int *nwin, int32_t **win_rowptr, int64_t **win_base, int32_t **order,
                          int *ascending);

@@ -102,6 +102,7 @@ def lib():
         "sx_flag_wait": ([vp, vp, C.c_uint32], i),
         "sx_push_B": ([vp, vp, sz, C.POINTER(vp), C.POINTER(vp), i, vp, vp], i),
         "sx_spmm_expect_push": ([vp, vp, vp, vp], i),
+        "sx_spmm_fuse_push": ([vp, C.POINTER(vp), C.POINTER(vp), i, vp, vp], i),
         "sx_pull_B": ([vp, i, vp], i),
         "sx_pull_B_fused": ([vp, i, vp, vp, vp, C.c_uint32], i),
         "sx_host_alloc": ([sz, C.POINTER(vp)], i),
@@ -115,7 +116,7 @@ def lib():
                                   C.POINTER(C.POINTER(i64)), C.POINTER(_PI32), C.POINTER(i)], i),
         "sx_plan_slide": ([i, _PI32, _PI32, i, C.POINTER(i), C.POINTER(_PI32), C.POINTER(i), C.POINTER(_PI32),
                            C.POINTER(i), C.POINTER(i)], i),
-        "sx_plan_edge_lists": ([i, i, _PI32, _PI32, i, i, i, i, C.POINTER(i), C.POINTER(_PI32), C.POINTER(i64),
+        "sx_plan_edge_lists": ([i, i, _PI32, _PI32, i, i, i, i64, i, C.POINTER(i), C.POINTER(_PI32), C.POINTER(i64),
                                 C.POINTER(_PI32), C.POINTER(C.POINTER(C.c_uint16)), C.POINTER(i64), C.POINTER(i)], i),
         "sx_free": ([vp], None),
         "sx_sextans_invoke": ([vp, _PI32, _A8, _F4, _F8, _F8, i, i, i, i, i, i, i, _PD], i),
@@ -207,7 +208,7 @@ def plan_slide(M, rowptr, colidx, nchains):
     return steps, chains, ring.value, ent.value
 
 
-def plan_edge_lists(M, K, rowptr, colidx, row_bytes, elem_bytes, smem_budget, rows_per_block=32):
+def plan_edge_lists(M, K, rowptr, colidx, row_bytes, elem_bytes, smem_budget, max_rows=32, nnz_target=0):
     """Plan of the edge-list kernel (sx_plan_edge_lists) ->
     (blocks [nblocks, 8], cols [ncols] int32, lcol [nnz] uint16, total_cols, max_smem); nblocks == 0 if some
     row does not fit ``smem_budget``."""
@@ -217,7 +218,7 @@ def plan_edge_lists(M, K, rowptr, colidx, row_bytes, elem_bytes, smem_budget, ro
     bl, co, lc = _PI32(), _PI32(), C.POINTER(C.c_uint16)()
     L = lib()
     _check(L.sx_plan_edge_lists(M, K, rowptr.ctypes.data_as(_PI32), colidx.ctypes.data_as(_PI32), row_bytes, elem_bytes,
-                                rows_per_block, smem_budget, C.byref(nb), C.byref(bl), C.byref(nc), C.byref(co),
+                                max_rows, nnz_target, smem_budget, C.byref(nb), C.byref(bl), C.byref(nc), C.byref(co),
                                 C.byref(lc), C.byref(tot), C.byref(ms)))
     if nb.value == 0:
         return np.zeros((0, 8), np.int32), np.zeros(0, np.int32), np.zeros(0, np.uint16), 0, 0
@@ -552,6 +553,13 @@ class Engine:
         rdy = (C.c_void_p * n)(*peer_ready_ptrs)
         _check(self._L.sx_push_B(self._ctx, C.c_void_p(image_ptr), nbytes, imgs, rdy, n, C.c_void_p(done_flags_ptr),
                                  C.c_void_p(pushes_ptr)))
+
+    def fuse_push(self, peer_image_ptrs, peer_ready_ptrs, done_flags_ptr, pushes_ptr):
+        """The next SpMM launch also pushes the B image it reads to the peers (sx_spmm_fuse_push)."""
+        n = len(peer_image_ptrs)
+        imgs = (C.c_void_p * n)(*peer_image_ptrs)
+        rdy = (C.c_void_p * n)(*peer_ready_ptrs)
+        _check(self._L.sx_spmm_fuse_push(self._ctx, imgs, rdy, n, C.c_void_p(done_flags_ptr), C.c_void_p(pushes_ptr)))
 
     def expect_push(self, ready_ptr, epoch_ptr, done_ptr):
         """The next SpMM launch waits for the push into its B image and acknowledges it (sx_spmm_expect_push)."""

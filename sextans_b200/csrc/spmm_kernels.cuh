@@ -664,10 +664,12 @@ spmm_window_kernel(const int M, const int4 *__restrict__ blocks, const int *__re
 // pcrystk02: 317 against 918): a third of the bytes through L2 and of the shared memory, so 4-6
 // blocks share an SM instead of 1-2, and the index stream of A shrinks from 4 to 2 bytes per nonzero.
 //   block record (two int4): {row_begin, nrows, nnz_begin, nnz_end} {col_begin, ncols, -, smem}
-//   shared memory:           window ncols x (G x 16 bytes) | values | local columns | column list
+//   shared memory:           window ncols x (G x 16 bytes) | values | local columns | column list | row pointers
 //                            (A slice from the 8-entry boundary at or below nnz_begin: whole 16-byte units)
 // One lane group per row, stored order, so strict mode is bit-identical to cpu_spmm_CSR.
-// 256 threads per block (512 for 16-lane groups), i.e. ROWS = 128 / 64 / 32 / 32 rows for G = 2 / 4 / 8 / 16.
+// 256 threads per block (512 for 16-lane groups), i.e. ROWS = 128 / 64 / 32 / 32 lane groups for G = 2 / 4 / 8 / 16;
+// a lane group takes rows rl, rl + ROWS, ... of its block (blocks are cut by nonzeros, not by rows: a
+// small matrix becomes one block per SM with equal work, the reference's equal-length PE lists).
 //
 // How the window gets on chip was decided by measurement (scripts/micro/launch_floor.cu, B200):
 // behind a dependent-launch wait a TMA bulk copy of a cold 16 KB piece costs ~1.05 us per graph
@@ -684,14 +686,22 @@ spmm_window_kernel(const int M, const int4 *__restrict__ blocks, const int *__re
 // staged and its B rows on the way to L2 by the time this kernel completes.  Launched without the
 // attribute the two instructions do nothing.
 //
-// Multi-GPU (ready != nullptr): B is pushed into this GPU's image by the rank that holds it
-// (push_image_kernel).  *epoch counts the SpMMs this image has served; lane 0 of every warp
+// Multi-GPU, the rank that holds B (npush > 0): the exchange is part of THIS kernel.  After the
+// dependent-launch wait every block waits until the peers have finished with the previous
+// contents of their images (done[p] >= *pushes), copies its 1/gridDim share of the B image into
+// every peer's image with plain 16-byte stores through the NVLink peer mappings (posted writes),
+// and goes on with its rows; the last block to finish stores *pushes + 1 into every peer's ready
+// flag.  No launch, no stream and no collective for the exchange on any rank.
+// Multi-GPU, a receiving rank (ready != nullptr): B is pushed into this GPU's image by the rank
+// that holds it.  *epoch counts the SpMMs this image has served; lane 0 of every warp
 // waits until the local ready flag reaches *epoch + 1 (the push that follows the last SpMM on
 // this image) before the window copies are issued, and the last block to finish advances *epoch
 // and stores the new value into the pusher's done flag, which lets the pusher overwrite the
 // image again.  Counters live in device memory, so a captured launch can be replayed; the
 // exchange costs this rank no launch of its own.
 constexpr int SX_EDGE_PREFETCH = 1;
+// where a pushed B image goes: up to 15 peers' images and ready flags (peer-mapped addresses)
+struct PushList { int4 *dst[15]; uint32_t *ready[15]; };
 // -DSX_EDGE_TRACE (scripts/build_variant.sh): every block records %globaltimer at its phase
 // boundaries into a device array read back by sx_debug_edge_trace -- how a ~3.5 us step splits
 // into launch, prologue, dependent-launch wait, window staging and arithmetic.
@@ -718,7 +728,8 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
                      const uint16_t *__restrict__ lcol, const T *__restrict__ val, const T *__restrict__ B,
                      const uint32_t ldbv, const T *Cin, T *Cout, const uint32_t ldcv, const T alpha, const T beta,
                      const int nvec, const int flags, const uint32_t *ready, uint32_t *epoch, uint32_t *done_remote,
-                     unsigned int *sync_words) {
+                     unsigned int *sync_words, const int npush, const PushList push, const int64_t push_n16,
+                     const uint32_t *push_done, uint32_t *pushes) {
     using V = typename VecOf<T>::type;
     constexpr int THREADS = EdgeShape<G>::THREADS, ROWS = EdgeShape<G>::ROWS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -740,7 +751,7 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
     const int lg = threadIdx.x & (G - 1);
     const int rl = threadIdx.x / G;
     const int4 b0 = __ldg(blocks + 2 * blockIdx.x), b1 = __ldg(blocks + 2 * blockIdx.x + 1);
-    const int jb = b0.z, je = b0.w;
+    const int row0 = b0.x, nrows = b0.y, jb = b0.z, je = b0.w;
     const int ncols = b1.y;
     const uint32_t rowbytes = ldbv * 16u;                     // a row of the B image in global memory
     const uint32_t wbytes = (uint32_t)ncols * (G * 16u);      // a staged row: G vectors, whatever the image's leading dimension
@@ -752,6 +763,7 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
     const T *sval = reinterpret_cast<const T *>(smem_raw + wbytes);
     const uint16_t *scol = reinterpret_cast<const uint16_t *>(smem_raw + wbytes + (size_t)na * sizeof(T));
     const int *scols = reinterpret_cast<const int *>(smem_raw + wbytes + (size_t)na * (sizeof(T) + 2));
+    int *srp = const_cast<int *>(scols) + ncp;  // row pointers of the block's rows, nrows + 1 of them
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -765,17 +777,14 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
         tma_bulk_g2s(const_cast<T *>(sval), val + jal, na * (uint32_t)sizeof(T), &bar, pol_a);
         tma_bulk_g2s(const_cast<uint16_t *>(scol), lcol + jal, na * 2u, &bar, pol_a);
     }
-    const int row = b0.x + rl;
-    const bool mine = rl < b0.y && lg < nvec;
-    int begin = 0, end = 0;
-    if (mine) { begin = __ldg(rowptr + row); end = __ldg(rowptr + row + 1); }
+    for (int i = threadIdx.x; i <= nrows; i += THREADS) srp[i] = __ldg(rowptr + row0 + i);
     const unsigned char *Bb = reinterpret_cast<const unsigned char *>(B) + lg * 16;
     if (has) mbar_wait(&bar, 0);
     if (flags & SX_EDGE_PREFETCH) {
         if (lg * 16 < (int)rowbytes && (lg & 7) == 0)  // one prefetch per 128-byte line of a row
             for (int lr = rl; lr < ncols; lr += ROWS) prefetch_l2(Bb + (size_t)(uint32_t)scols[lr] * rowbytes);
-        if (threadIdx.x == THREADS - 1 && b0.y > 0)
-            bulk_prefetch_l2(reinterpret_cast<const unsigned char *>(Cin) + (size_t)b0.x * ldcv * 16u, (uint32_t)b0.y * ldcv * 16u);
+        if (threadIdx.x == THREADS - 1 && nrows > 0)
+            bulk_prefetch_l2(reinterpret_cast<const unsigned char *>(Cin) + (size_t)row0 * ldcv * 16u, (uint32_t)nrows * ldcv * 16u);
     }
     // ---- B and C_in: only after the previous kernel is complete ----
     SX_TRACE_MARK(1);
@@ -796,74 +805,110 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
     if (lg < nvec)
         for (int lr = rl; lr < ncols; lr += ROWS)
             cp_async_16(win + ((size_t)lr * G + lg) * 16, Bb + (size_t)(uint32_t)scols[lr] * rowbytes);
-    V acc, cin;
-    vzero(acc);
-    vzero(cin);
-    if (mine) cin = reinterpret_cast<const V *>(Cin)[(size_t)row * ldcv + lg];
+    uint32_t pushed = 0;
+    if (npush > 0) {  // multi-GPU, this rank holds B: this block's share of the image goes to every peer
+        if ((threadIdx.x & 31) == 0) {
+            pushed = *reinterpret_cast<volatile uint32_t *>(pushes);  // advanced only after every block is done
+            const long long t0 = clock64();
+            for (int p = 0; p < npush; ++p)
+                while ((int)(ld_acquire_sys(push_done + p) - pushed) < 0) {
+                    __nanosleep(32);
+                    if (clock64() - t0 > 4000000000ll) { atomicExch(sync_words + 1, 1u); break; }
+                }
+        }
+        __syncwarp();
+        const int4 *src = reinterpret_cast<const int4 *>(B);
+        const int64_t lo = push_n16 * blockIdx.x / gridDim.x, hi = push_n16 * (blockIdx.x + 1) / gridDim.x;
+        for (int64_t i = lo + threadIdx.x; i < hi; i += THREADS) {
+            const int4 v = __ldg(src + i);
+            for (int p = 0; p < npush; ++p) push.dst[p][i] = v;
+        }
+    }
+    // a lane group takes rows rl, rl + ROWS, ... of the block; C_in of the next one is fetched while this one is computed
+    const bool lane_on = lg < nvec;
+    const V *Cv = reinterpret_cast<const V *>(Cin) + (size_t)row0 * ldcv + lg;
+    V *Ov = reinterpret_cast<V *>(Cout) + (size_t)row0 * ldcv + lg;
+    V cin_next;
+    vzero(cin_next);
+    if (lane_on && rl < nrows) cin_next = Cv[(size_t)rl * ldcv];
     cp_async_wait_all();
     __syncthreads();
     SX_TRACE_MARK(3);
-    if (mine) {
-        const T *sv = sval - jal;  // sv[j] = value of nonzero j
-        const uint16_t *sc = scol - jal;
-        const V *w = reinterpret_cast<const V *>(win) + lg;  // w[local column * G] = this lane's piece of that B row
-        // chunks of 8 nonzeros, software-pipelined: the (column, value) pairs of chunk k+1 and the
-        // eight B-row pieces of chunk k are in flight while the ordered chain of additions of chunk k runs
-        constexpr int UC = 8;
-        int j = begin;
-        if (j + UC <= end) {
-            uint32_t c[UC];
-            T a[UC];
+    const T *sv = sval - jal;  // sv[j] = value of nonzero j
+    const uint16_t *sc = scol - jal;
+    const V *w = reinterpret_cast<const V *>(win) + lg;  // w[local column * G] = this lane's piece of that B row
+    if (lane_on)
+        for (int rr = rl; rr < nrows; rr += ROWS) {
+            const int begin = srp[rr], end = srp[rr + 1];
+            const V cin = cin_next;
+            if (rr + ROWS < nrows) cin_next = Cv[(size_t)(rr + ROWS) * ldcv];
+            V acc;
+            vzero(acc);
+            // chunks of 8 nonzeros, software-pipelined: the (column, value) pairs of chunk k+1 and the
+            // eight B-row pieces of chunk k are in flight while the ordered chain of additions of chunk k runs
+            constexpr int UC = 8;
+            int j = begin;
+            if (j + UC <= end) {
+                uint32_t c[UC];
+                T a[UC];
 #pragma unroll
-            for (int u = 0; u < UC; ++u) { c[u] = sc[j + u]; a[u] = sv[j + u]; }
-            for (;;) {
+                for (int u = 0; u < UC; ++u) { c[u] = sc[j + u]; a[u] = sv[j + u]; }
+                for (;;) {
+                    V b[UC];
+#pragma unroll
+                    for (int u = 0; u < UC; ++u) b[u] = w[c[u] * G];
+                    const int jn = j + UC;
+                    const bool more = jn + UC <= end;
+                    uint32_t c2[UC];
+                    T a2[UC];
+                    const int jl = more ? jn : j;  // unconditional loads (this chunk again when there is no next one)
+#pragma unroll
+                    for (int u = 0; u < UC; ++u) { c2[u] = sc[jl + u]; a2[u] = sv[jl + u]; }
+#pragma unroll
+                    for (int u = 0; u < UC; ++u) vmac<STRICT>(acc, a[u], b[u]);
+                    j = jn;
+                    if (!more) break;
+#pragma unroll
+                    for (int u = 0; u < UC; ++u) { c[u] = c2[u]; a[u] = a2[u]; }
+                }
+            }
+            if (j < end) {
+                // the last, partial chunk: its loads all in flight at once (indices clamped to the row),
+                // the additions predicated -- an explicit +0 would turn a -0 sum into +0
+                uint32_t c[UC];
+                T a[UC];
                 V b[UC];
 #pragma unroll
+                for (int u = 0; u < UC; ++u) { const int ju = min(j + u, end - 1); c[u] = sc[ju]; a[u] = sv[ju]; }
+#pragma unroll
                 for (int u = 0; u < UC; ++u) b[u] = w[c[u] * G];
-                const int jn = j + UC;
-                const bool more = jn + UC <= end;
-                uint32_t c2[UC];
-                T a2[UC];
-                const int jl = more ? jn : j;  // unconditional loads (this chunk again when there is no next one)
 #pragma unroll
-                for (int u = 0; u < UC; ++u) { c2[u] = sc[jl + u]; a2[u] = sv[jl + u]; }
-#pragma unroll
-                for (int u = 0; u < UC; ++u) vmac<STRICT>(acc, a[u], b[u]);
-                j = jn;
-                if (!more) break;
-#pragma unroll
-                for (int u = 0; u < UC; ++u) { c[u] = c2[u]; a[u] = a2[u]; }
+                for (int u = 0; u < UC; ++u)
+                    if (j + u < end) vmac<STRICT>(acc, a[u], b[u]);
             }
+            Ov[(size_t)rr * ldcv] = vaxpby<STRICT>(alpha, acc, beta, cin);
         }
-        if (j < end) {
-            // the last, partial chunk: its loads all in flight at once (indices clamped to the row),
-            // the additions predicated -- an explicit +0 would turn a -0 sum into +0
-            uint32_t c[UC];
-            T a[UC];
-            V b[UC];
-#pragma unroll
-            for (int u = 0; u < UC; ++u) { const int ju = min(j + u, end - 1); c[u] = sc[ju]; a[u] = sv[ju]; }
-#pragma unroll
-            for (int u = 0; u < UC; ++u) b[u] = w[c[u] * G];
-#pragma unroll
-            for (int u = 0; u < UC; ++u)
-                if (j + u < end) vmac<STRICT>(acc, a[u], b[u]);
-        }
-        reinterpret_cast<V *>(Cout)[(size_t)row * ldcv + lg] = vaxpby<STRICT>(alpha, acc, beta, cin);
-    }
 #ifdef SX_EDGE_TRACE
-    SX_TRACE_MARK(4);      // thread 0 done with its own row
+    SX_TRACE_MARK(4);      // thread 0 done with its own rows
     __syncthreads();
     SX_TRACE_MARK(5);      // every row of the block done
 #endif
-    if (ready != nullptr) {  // multi-GPU: tell the pusher that this rank is done with the image
+    if (ready != nullptr || npush > 0) {
         __syncthreads();
         if (threadIdx.x == 0) {
-            __threadfence();
+            if (npush > 0) __threadfence_system();  // this block's peer stores are performed before it counts itself done
+            else __threadfence();
             if (atomicAdd(sync_words + 2, 1u) == gridDim.x - 1) {
                 sync_words[2] = 0;
-                *reinterpret_cast<volatile uint32_t *>(epoch) = step;
-                st_release_sys(done_remote, step);
+                if (ready != nullptr) {  // tell the pusher that this rank is done with the image
+                    *reinterpret_cast<volatile uint32_t *>(epoch) = step;
+                    st_release_sys(done_remote, step);
+                }
+                if (npush > 0) {         // tell the peers that their images hold this B
+                    __threadfence_system();
+                    for (int p = 0; p < npush; ++p) st_release_sys(push.ready[p], pushed + 1u);
+                    *reinterpret_cast<volatile uint32_t *>(pushes) = pushed + 1u;
+                }
             }
         }
     }
@@ -1477,7 +1522,6 @@ pull_image_kernel(int4 *__restrict__ dst, const int4 *src, const int64_t n16, co
 // their SpMM kernel waits on the flag (spmm_edgelist_kernel) or a one-warp kernel does
 // (wait_push_kernel).  The multi-GPU form of the reference's daisy chain that hands the B window
 // from PEG to PEG (src/sextans.cpp:909-941).  All counters are in device memory.
-struct PushList { int4 *dst[15]; uint32_t *ready[15]; };
 __global__ void __launch_bounds__(256)
 push_image_kernel(const int4 *__restrict__ src, const int64_t n16, const PushList peers, const int npeers,
                   const uint32_t *done, uint32_t *pushes, unsigned int *sync_words) {

@@ -120,6 +120,11 @@ struct sx_ctx {
     // multi-GPU exchange fused into the next SpMM launch (sx_spmm_expect_push; one-shot)
     const uint32_t *x_ready = nullptr;
     uint32_t *x_epoch = nullptr, *x_done = nullptr;
+    // ... and, on the rank that holds B, the push fused into it (sx_spmm_fuse_push; one-shot)
+    int p_npeers = 0;
+    sx::PushList p_list = {};
+    const uint32_t *p_done = nullptr;
+    uint32_t *p_pushes = nullptr;
     std::vector<int32_t> h_rowptr;  // kept to re-derive segments when the option changes
     // variant 3: per block of 32 rows {first column, column span, nnz begin, nnz end}
     DevBuf wblocks;
@@ -276,13 +281,17 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
                 at[0].val.programmaticStreamSerializationAllowed = 1;
                 cfg.attrs = at;
                 cfg.numAttrs = c->pdl != 0 ? 1 : 0;
-                if (c->x_ready && (rc = ensure_sync_words(c))) return rc;
+                if ((c->x_ready || c->p_npeers) && (rc = ensure_sync_words(c))) return rc;
+                // the fused push sends the image this launch reads: K rows of ldb elements, from column 0
+                const int npush = c->win_col0 == 0 ? c->p_npeers : 0;
+                const int64_t push_n16 = (int64_t)((size_t)c->K * (size_t)ldb * sizeof(T) / 16);
                 SX_CUDA(cudaLaunchKernelEx(&cfg, kern, (const int4 *)ep->blocks.p, (const int *)ep->cols.p,
                                            (const int *)c->rowptr.p, (const uint16_t *)ep->lcol.p, (const T *)c->val.p, dB,
                                            (uint32_t)(ldb / E), dCin, dCout, (uint32_t)(ldc / E), alpha, beta, nvec,
                                            pf ? sx::SX_EDGE_PREFETCH : 0, c->x_ready, c->x_epoch, c->x_done,
-                                           (unsigned int *)c->sync_words.p));
+                                           (unsigned int *)c->sync_words.p, npush, c->p_list, push_n16, c->p_done, c->p_pushes));
                 c->x_ready = nullptr;
+                if (npush) c->p_npeers = 0;
                 c->launches++;
                 c->last_edge_plan = ep;
                 c->last_kernel = 80000 + G * 100 + VPL * 10 + (STRICT ? 0 : 1);
@@ -291,7 +300,17 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
             }
         }
     }
-    // the other kernels do not carry the multi-GPU handshake: a one-warp kernel before and after
+    // the other kernels do not carry the multi-GPU exchange: the push as a kernel of its own ...
+    if (c->p_npeers > 0 && c->win_col0 == 0) {
+        if ((rc = ensure_sync_words(c))) return rc;
+        const int64_t n16 = (int64_t)((size_t)c->K * (size_t)ldb * sizeof(T) / 16);
+        const int grid = (int)std::min<int64_t>(c->sm_count, std::max<int64_t>(1, (n16 + 255) / 256));
+        sx::push_image_kernel<<<grid, 256, 0, c->stream>>>((const int4 *)dB, n16, c->p_list, c->p_npeers, c->p_done, c->p_pushes,
+                                                           (unsigned int *)c->sync_words.p);
+        c->launches++;
+        c->p_npeers = 0;
+    }
+    // ... and the receiving side's handshake as a one-warp kernel before and after
     struct PushGuard {
         sx_ctx *c; const uint32_t *ready; uint32_t *epoch, *done;
         ~PushGuard() {
@@ -842,8 +861,20 @@ int get_edge_plan(sx_ctx *c, int row_bytes, int elem_bytes, int rows, const Edge
     std::vector<int32_t> ci((size_t)c->nnz);
     SX_CUDA(cudaMemcpyAsync(ci.data(), c->colidx.p, (size_t)c->nnz * 4, cudaMemcpyDeviceToHost, c->stream));
     SX_CUDA(cudaStreamSynchronize(c->stream));
-    // four blocks per SM if (almost) every group of `rows` rows fits that budget uncut, else two, else one
-    const int ngroups = (c->M + rows - 1) / rows;
+    // A matrix of at most a few waves of `rows`-row blocks is cut by NONZEROS into m blocks per SM
+    // (the reference's equal-length PE lists, src/sparse_helper.h:345-403): the kernel ends when its
+    // slowest block does, and with one wave nothing evens out differences.  A large matrix keeps
+    // blocks of `rows` rows and leaves the balance to the block scheduler.
+    const int nfixed = (c->M + rows - 1) / rows;
+    int max_rows = rows, expect = nfixed;
+    int64_t nnz_target = 0;
+    if (nfixed <= 4 * c->sm_count) {
+        const int m = (nfixed + c->sm_count - 1) / c->sm_count;
+        expect = m * c->sm_count;
+        nnz_target = (c->nnz + expect - 1) / expect;
+        max_rows = 4 * rows;
+    }
+    // four blocks per SM if (almost) every block fits that budget uncut, else two, else one
     int nb = 0, max_smem = 0, rc = SX_OK;
     int32_t *blocks = nullptr, *cols = nullptr;
     uint16_t *lcol = nullptr;
@@ -852,10 +883,10 @@ int get_edge_plan(sx_ctx *c, int row_bytes, int elem_bytes, int rows, const Edge
         sx_free(blocks); sx_free(cols); sx_free(lcol);
         blocks = cols = nullptr;
         lcol = nullptr;
-        rc = sx_plan_edge_lists(c->M, c->K, c->h_rowptr.data(), ci.data(), row_bytes, elem_bytes, rows, edge_budget(k), &nb,
-                                &blocks, &ncols, &cols, &lcol, &total, &max_smem);
+        rc = sx_plan_edge_lists(c->M, c->K, c->h_rowptr.data(), ci.data(), row_bytes, elem_bytes, max_rows, nnz_target,
+                                edge_budget(k), &nb, &blocks, &ncols, &cols, &lcol, &total, &max_smem);
         if (rc) return rc;
-        if (nb > 0 && (int64_t)nb * 4 <= (int64_t)ngroups * 5) break;
+        if (nb > 0 && (int64_t)nb * 4 <= (int64_t)expect * 5 + 8) break;
     }
     if (nb > 0 && (c->kernel == 5 || total * 2 <= c->nnz)) {
         if (!(rc = p->blocks.ensure((size_t)nb * 32)) && !(rc = p->cols.ensure(std::max<size_t>((size_t)ncols * 4, 16))) &&
@@ -1927,6 +1958,24 @@ int sx_spmm_expect_push(sx_ctx *c, const void *ready_flag, void *epoch_counter, 
     c->x_ready = (const uint32_t *)ready_flag;
     c->x_epoch = (uint32_t *)epoch_counter;
     c->x_done = (uint32_t *)done_flag;
+    return SX_OK;
+}
+
+int sx_spmm_fuse_push(sx_ctx *c, void *const *peer_images, void *const *peer_ready_flags, int npeers, const void *done_flags,
+                      void *pushes_counter) {
+    if (!c) return fail(SX_ERR_INVALID, "null context");
+    if (npeers < 0 || npeers > 15) return fail(SX_ERR_INVALID, "0..15 peers expected (got %d)", npeers);
+    c->p_npeers = 0;
+    if (npeers == 0) return SX_OK;
+    if (!peer_images || !peer_ready_flags || !done_flags || !pushes_counter) return fail(SX_ERR_INVALID, "null argument");
+    for (int i = 0; i < npeers; ++i) {
+        if (!peer_images[i] || !peer_ready_flags[i] || ((uintptr_t)peer_images[i] & 15)) return fail(SX_ERR_INVALID, "bad peer pointer");
+        c->p_list.dst[i] = (int4 *)peer_images[i];
+        c->p_list.ready[i] = (uint32_t *)peer_ready_flags[i];
+    }
+    c->p_done = (const uint32_t *)done_flags;
+    c->p_pushes = (uint32_t *)pushes_counter;
+    c->p_npeers = npeers;
     return SX_OK;
 }
 

@@ -631,21 +631,25 @@ int sx_plan_slide(int M, const int32_t *rowptr, const int32_t *colidx, int nchai
 // Plan of the edge-list kernel (spmm_edgelist_kernel, variant 5).  The reference cuts A into
 // windows of 4096 columns and stores every nonzero of a PE as a packed word whose column field
 // is LOCAL to the window (14 bits; src/sparse_helper.h:419-443, src/sextans.cpp:398-402), so
-// that the PE indexes its on-chip copy of the B window directly.  The GPU analogue: a row
-// block (up to rows_per_block consecutive rows, one thread block) stages exactly the B rows
-// its nonzeros touch -- the block's DISTINCT columns, in ascending order -- into shared memory,
-// and every nonzero carries a 16-bit index into that compacted window.  On FEM-type matrices
-// that is a third of the contiguous column span (nasa4704: 142 distinct columns per 32 rows
-// against a span of 456; pcrystk02: 317 against 918).
+// that the PE indexes its on-chip copy of the B window directly, and it deals rows to PEs so
+// that every PE list has the same length (:345-403).  The GPU analogue: a row block (consecutive
+// rows, one thread block) stages exactly the B rows its nonzeros touch -- the block's DISTINCT
+// columns, in ascending order -- into shared memory, and every nonzero carries a 16-bit index
+// into that compacted window; blocks are cut so that they hold about the same number of
+// nonzeros.  On FEM-type matrices the compacted window is a third of the contiguous column span
+// (nasa4704: 142 distinct columns per 32 rows against a span of 456; pcrystk02: 317 against 918).
 //   blocks  8 ints per block: {row_begin, nrows, nnz_begin, nnz_end, col_begin, ncols, 0, smem_bytes}
 //   cols    the blocks' column lists, back to back, each starting at a multiple of 4 entries
 //           (16 bytes: the list travels to shared memory by TMA); pad entries repeat the last column
 //   lcol    nnz 16-bit local column indices, parallel to colidx
-// A group of rows_per_block rows that does not fit the shared-memory budget is cut into shorter
-// blocks; a single row that does not fit makes the matrix unplannable (*nblocks = 0, SX_OK).
+// A block is closed when it holds max_rows rows, when its nonzeros reach nnz_target (0: no such
+// limit; compared at the row that brings it closest), or when the next row would not fit the
+// shared-memory budget; a single row that does not fit makes the matrix unplannable (*nblocks =
+// 0, SX_OK).  Cuts restart every 4096 rows, so the plan does not depend on the thread count.
 int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colidx, int row_bytes, int elem_bytes,
-                       int rows_per_block, int smem_budget, int *nblocks_out, int32_t **blocks_out, int64_t *ncols_out,
-                       int32_t **cols_out, uint16_t **lcol_out, int64_t *total_cols_out, int *max_smem_out) {
+                       int max_rows, int64_t nnz_target, int smem_budget, int *nblocks_out, int32_t **blocks_out,
+                       int64_t *ncols_out, int32_t **cols_out, uint16_t **lcol_out, int64_t *total_cols_out,
+                       int *max_smem_out) {
     if (!nblocks_out || !blocks_out || !ncols_out || !cols_out || !lcol_out || !total_cols_out || !max_smem_out) {
         sx_internal_set_error("sx_plan_edge_lists: null output pointer");
         return SX_ERR_INVALID;
@@ -655,19 +659,19 @@ int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colid
     *blocks_out = *cols_out = nullptr;
     *lcol_out = nullptr;
     if (M < 0 || K < 0 || !rowptr || (M > 0 && rowptr[M] > 0 && !colidx) || row_bytes < 16 || row_bytes % 16 ||
-        (elem_bytes != 4 && elem_bytes != 8) || smem_budget < 1024 || rows_per_block < 1 || rows_per_block > 1024) {
+        (elem_bytes != 4 && elem_bytes != 8) || smem_budget < 1024 || max_rows < 1 || max_rows > 4096 || nnz_target < 0) {
         sx_internal_set_error("sx_plan_edge_lists: bad argument");
         return SX_ERR_INVALID;
     }
     if (M == 0) return SX_OK;
-    const int RB = rows_per_block;
+    constexpr int SG = 4096;  // rows per super-group: cuts restart here
     const int64_t nnz = rowptr[M];
-    const int ngroups = (M + RB - 1) / RB;
-    // shared memory of a block: window | values | local columns | column list (the A slice starts at
-    // the 8-entry boundary at or below nnz_begin, so that both streams are whole 16-byte units)
-    auto smem_of = [&](int ncols, int jb, int je) -> int64_t {
+    const int ngroups = (M + SG - 1) / SG;
+    // shared memory of a block: window | values | local columns | column list | row pointers (the A
+    // slice starts at the 8-entry boundary at or below nnz_begin: both streams are whole 16-byte units)
+    auto smem_of = [&](int ncols, int nrows, int jb, int je) -> int64_t {
         const int64_t na = je > jb ? (int64_t)((je - (jb & ~7) + 7) & ~7) : 0;
-        return (int64_t)ncols * row_bytes + na * elem_bytes + na * 2 + (int64_t)((ncols + 3) & ~3) * 4;
+        return (int64_t)ncols * row_bytes + na * elem_bytes + na * 2 + (int64_t)((ncols + 3) & ~3) * 4 + (int64_t)((nrows + 4) & ~3) * 4;
     };
     struct Part { std::vector<int32_t> blocks, cols; int64_t total = 0; int max_smem = 0; bool ok = true; };
     const unsigned nt = (unsigned)std::min<int64_t>(nnz < (1 << 18) ? 1 : std::min(sxhost::host_threads(), 16u), ngroups);  // 6 bytes x K of scratch per thread
@@ -681,20 +685,22 @@ int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colid
         int32_t tag = 0;
         const int g0 = (int)((int64_t)ngroups * t / nt), g1 = (int)((int64_t)ngroups * (t + 1) / nt);
         for (int g = g0; g < g1 && P.ok; ++g) {
-            const int gend = (int)std::min<int64_t>(M, (int64_t)g * RB + RB);
-            int r = g * RB;
+            const int gend = (int)std::min<int64_t>(M, (int64_t)g * SG + SG);
+            int r = g * SG;
             while (r < gend) {
-                // greedy: rows r.. while the block still fits
+                // greedy: rows r.. while the block still fits and is short of its share of nonzeros
                 const int rb = r;
                 const int jb = rowptr[rb];
                 int ncols = 0;
                 ++tag;
                 cols.clear();
-                while (r < gend) {
+                while (r < gend && r - rb < max_rows) {
+                    const int64_t have = rowptr[r] - jb, with = rowptr[r + 1] - jb;
+                    if (nnz_target > 0 && r > rb && with - nnz_target > nnz_target - have) break;  // closer to the target without this row
                     int fresh = 0;
                     for (int32_t j = rowptr[r]; j < rowptr[r + 1]; ++j)
                         if (stamp[colidx[j]] != tag) { stamp[colidx[j]] = tag; cols.push_back(colidx[j]); ++fresh; }
-                    if (smem_of(ncols + fresh, jb, rowptr[r + 1]) > smem_budget || ncols + fresh > 65535) {
+                    if (smem_of(ncols + fresh, r - rb + 1, jb, rowptr[r + 1]) > smem_budget || ncols + fresh > 65535) {
                         if (r == rb) { P.ok = false; break; }  // one row alone does not fit
                         for (int k = 0; k < fresh; ++k) { stamp[cols.back()] = -1; cols.pop_back(); }
                         break;
@@ -707,7 +713,7 @@ int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colid
                 std::sort(cols.begin(), cols.end());
                 for (int i = 0; i < ncols; ++i) local[cols[i]] = (uint16_t)i;
                 for (int32_t j = jb; j < je; ++j) lcol[j] = local[colidx[j]];
-                const int sm = (int)smem_of(ncols, jb, je);
+                const int sm = (int)smem_of(ncols, r - rb, jb, je);
                 P.blocks.insert(P.blocks.end(), {rb, r - rb, jb, je, (int32_t)P.cols.size(), ncols, 0, sm});
                 P.cols.insert(P.cols.end(), cols.begin(), cols.end());
                 while (P.cols.size() % 4) P.cols.push_back(ncols ? cols.back() : 0);

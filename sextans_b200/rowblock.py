@@ -49,23 +49,22 @@ class RowBlock:
 
 
 class PushExchange:
-    """B from the root rank to every other rank WITHOUT a collective and without a launch on the
-    receiving side: the root copies its row-major B image into every peer's image with ONE kernel
-    (sx_push_B: posted 16-byte stores over NVLink through CUDA-IPC peer mappings), and a peer's
-    next SpMM waits for the push in its own prologue and acknowledges it from its last block
-    (sx_spmm_expect_push).  All counters are 32-bit words in device memory -- per image: ``ready``
-    and ``epoch`` on a peer, ``pushes`` and ``done[peer]`` on the root -- so captured launches can
-    be replayed.  The multi-GPU form of the reference's chain that hands the B window from PEG to
-    PEG (src/sextans.cpp:909-941).
+    """B from the root rank to every other rank with NOTHING launched for the exchange on any
+    rank: the root's SpMM kernel itself copies the B image it reads into every peer's image on
+    the way to its rows (sx_spmm_fuse_push: posted 16-byte stores over NVLink through CUDA-IPC
+    peer mappings, the step published by its last block), and a peer's SpMM waits for the push in
+    its own prologue and acknowledges it from its last block (sx_spmm_expect_push).  All counters
+    are 32-bit words in device memory -- per image: ``ready`` and ``epoch`` on a peer, ``pushes``
+    and ``done[peer]`` on the root -- so captured launches can be replayed.  The multi-GPU form of
+    the reference's chain that hands the B window from PEG to PEG (src/sextans.cpp:909-941).
 
     ``engines``: this rank's Engine objects (one, or R replicas used round-robin), each with A
     uploaded; their own B images (``Engine.device_B(N)``) are the operands.  Step i uses image
-    i % R.  The root enqueues its pushes on a side stream of its own, so they run beside its SpMMs.
+    i % R: call ``before_step(i)`` right before the SpMM of step i is enqueued on engine i % R.
     """
     WORDS = 8192          # mailbox: ready[j] at j, epoch[j] at 256 + j, pushes[j] at 512 + j, done[j][p] at 1024 + 16 j + p
 
-    def __init__(self, engines, N, device=None, group=None, root=0, side_stream=True):
-        import torch
+    def __init__(self, engines, N, group=None, root=0):
         import torch.distributed as dist
         self.engines, self.N, self.root, self.group = list(engines), N, root, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
@@ -77,21 +76,16 @@ class PushExchange:
         for e in self.engines:
             ptr, nb = e.device_B(N)
             self.images.append(ptr)
-            self.nbytes = (nb + 15) // 16 * 16
+            self.nbytes = nb
         self.box = e0.device_alloc(4 * self.WORDS)
         mine = {"box": e0.ipc_export_ref(self.box), "images": [e0.ipc_export_ref(p) for p in self.images]}
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine, group=group)
         self._opened = {}                      # IPC handle -> base address in this process (a handle is opened once)
-        self._launches = 0
-        self.side = None
         if self.rank == root:
             self.peers = [r for r in range(self.world) if r != root]
             self.peer_box = {r: self._open(everyone[r]["box"]) for r in self.peers}
             self.peer_images = {r: [self._open(ref) for ref in everyone[r]["images"]] for r in self.peers}
-            if side_stream:      # B does not change between pushes (or its producer is ordered otherwise): push beside the SpMMs
-                dev = device if device is not None else torch.device("cuda", e0.device)
-                self.side = torch.cuda.Stream(device=dev)
         else:
             self.pi = [r for r in range(self.world) if r != root].index(self.rank)     # my index among the peers
             self.root_box = self._open(everyone[root]["box"])
@@ -104,33 +98,20 @@ class PushExchange:
         return self._opened[handle] + offset
 
     def describe(self):
-        return (f"B ({self.nbytes / 1e3:.0f} KB) pushed by rank {self.root} into every peer's image over NVLink with one kernel per step "
-                "(posted peer stores); the receiving SpMM kernel waits on the step flag in its prologue and acknowledges from its "
-                "last block: no launch and no collective on the receiving ranks")
+        return (f"B ({self.nbytes / 1e3:.0f} KB) pushed into every peer's image over NVLink BY rank {self.root}'s SpMM kernel itself "
+                "(its blocks copy their share of the image with posted peer stores, its last block publishes the step); the "
+                "receiving SpMM kernel waits on the step flag in its prologue and acknowledges from its last block: no launch, "
+                "no stream and no collective for the exchange on any rank")
 
-    def extra_streams(self):
-        return (self.side,) if self.side is not None else ()
-
-    def before_step(self, i, stream=None):
-        """Call right before the SpMM of step i is enqueued on engine i % R."""
+    def before_step(self, i):
         j = i % self.R
         e = self.engines[j]
         if self.rank == self.root:
             if self.peers:
-                main = None
-                if self.side is not None:
-                    e.set_stream(self.side.cuda_stream)
-                    main = stream
-                e.push_B(self.images[j], self.nbytes, [self.peer_images[r][j] for r in self.peers],
-                         [self.peer_box[r] + 4 * j for r in self.peers], self.box + 4 * (1024 + 16 * j), self.box + 4 * (512 + j))
-                self._launches += 1
-                if main is not None:
-                    e.set_stream(main.cuda_stream)
+                e.fuse_push([self.peer_images[r][j] for r in self.peers], [self.peer_box[r] + 4 * j for r in self.peers],
+                            self.box + 4 * (1024 + 16 * j), self.box + 4 * (512 + j))
         else:
             e.expect_push(self.box + 4 * j, self.box + 4 * (256 + j), self.root_box + 4 * (1024 + 16 * j + self.pi))
-
-    def launches(self):
-        return self._launches
 
     def close(self):
         """Collective: every rank unmaps what it imported, then frees its mailbox."""
@@ -138,8 +119,6 @@ class PushExchange:
         e0 = self.engines[0]
         for e in self.engines:
             e.synchronize()
-        if self.side is not None:
-            self.side.synchronize()
         dist.barrier(group=self.group)
         for base in self._opened.values():
             e0.ipc_close(base)
@@ -211,36 +190,31 @@ class ShardedSpMM:
         return torch.as_tensor(_Arr(), device=f"cuda:{self.device}").view(self.K, ld)
 
     def _exchange_for(self, N, src):
-        """The push exchange for (N, src), rebuilt (collectively) whenever any rank's B image has
-        moved -- a different N re-allocates it, and the peer mappings of the old one would dangle."""
+        """The push exchange for (N, src), rebuilt (collectively) when this rank's B image has
+        moved -- a different N re-allocates it, and the peer mappings of the old one would dangle.
+        Every rank sees the same sequence of N and holds a B image of the same size, so they all
+        take the same decision without asking each other."""
         if self.world == 1 or self._xch_failed:
             return None
         ptr, nbytes = self.engine.device_B(N)
-        stale = self._xch is None or self._xch[:3] != (N, src, ptr)
-        votes = [None] * self.world
-        self.dist.all_gather_object(votes, (bool(stale), bool(nbytes <= self.peer_bytes)), group=self.group)
-        if not all(v[1] for v in votes):
-            if self._xch is not None:
-                self._xch[3].close()
-                self._xch = None
+        if self._xch is not None and self._xch[:3] == (N, src, ptr):
+            return self._xch[3]
+        if self._xch is not None:
+            self._xch[3].close()
+            self._xch = None
+        if nbytes > self.peer_bytes:
             return None
-        if any(v[0] for v in votes):
+        try:
+            self._xch = (N, src, ptr, PushExchange([self.engine], N, group=self.group, root=src))
+        except Exception:
+            self._xch = None
+        flags = [None] * self.world          # at build time only: did CUDA IPC work everywhere?
+        self.dist.all_gather_object(flags, self._xch is not None, group=self.group)
+        if not all(flags):
             if self._xch is not None:
                 self._xch[3].close()
-                self._xch = None
-            try:
-                # B is re-staged every call: the push follows it on the engine's stream
-                self._xch = (N, src, ptr, PushExchange([self.engine], N, group=self.group, root=src, side_stream=False))
-            except Exception:
-                self._xch_failed = True
-                self._xch = None
-            flags = [None] * self.world
-            self.dist.all_gather_object(flags, self._xch is not None, group=self.group)
-            if not all(flags):
-                if self._xch is not None:
-                    self._xch[3].close()
-                self._xch, self._xch_failed = None, True
-                return None
+            self._xch, self._xch_failed = None, True
+            return None
         return self._xch[3]
 
     def spmm(self, N, alpha, B_colmajor_root, beta, C_block_colmajor, src=0, rp_time=1):
@@ -251,7 +225,7 @@ class ShardedSpMM:
         if x is not None:
             if self.rank == src:
                 self.engine.stage_B(N, B_colmajor_root)    # H2D + layout change on the root only
-                x.before_step(0)                           # waits for the peers' acknowledgement of the previous B, then pushes
+                x.before_step(0)                           # the launch below also pushes B (once the peers are done with the previous one)
             else:
                 self.engine.device_B(N)                    # marks B as staged: the push fills it
                 x.before_step(0)                           # the launch below waits for the push and acknowledges it

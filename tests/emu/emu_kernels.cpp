@@ -23,8 +23,8 @@ extern "C" {  // host-side planner of the product (libsextans_b200.so; no GPU ne
 int sx_plan_slide(int M, const int32_t *rowptr, const int32_t *colidx, int nchains_wanted, int *nsteps, int32_t **steps,
                   int *nchains, int32_t **chains, int *ring_rows, int *max_step_entries);
 int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colidx, int row_bytes, int elem_bytes,
-                       int rows_per_block, int smem_budget, int *nblocks, int32_t **blocks, int64_t *ncols, int32_t **cols,
-                       uint16_t **lcol, int64_t *total_cols, int *max_smem);
+                       int max_rows, int64_t nnz_target, int smem_budget, int *nblocks, int32_t **blocks, int64_t *ncols,
+                       int32_t **cols, uint16_t **lcol, int64_t *total_cols, int *max_smem);
 void sx_free(void *);
 }
 
@@ -603,7 +603,10 @@ void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, u
     int32_t *blocks = nullptr, *cols = nullptr;
     uint16_t *lcol = nullptr;
     int64_t total = 0, ncols = 0;
-    if (sx_plan_edge_lists(M, K, a.rp.data(), a.ci.data(), G * 16, (int)sizeof(T), ROWS, budget, &nb, &blocks,
+    // every other case cuts by nonzeros with up to 4 sweeps of the lane groups (what sx_api.cu does for small matrices)
+    const int max_rows = (seed & 1) ? 4 * ROWS : ROWS;
+    const int64_t nnz_target = (seed & 1) ? std::max(8, a.rp[M] / 5) : 0;
+    if (sx_plan_edge_lists(M, K, a.rp.data(), a.ci.data(), G * 16, (int)sizeof(T), max_rows, nnz_target, budget, &nb, &blocks,
                            &ncols, &cols, &lcol, &total, &max_smem) != 0) {
         std::printf("edge lists: plan FAILED\n");
         ++failures;
@@ -626,7 +629,7 @@ void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, u
     int next_row = 0;
     for (int b = 0; b < nb && plan_ok; ++b) {
         const int32_t *r = blocks + (size_t)b * 8;
-        plan_ok = r[0] == next_row && r[1] >= 1 && r[1] <= ROWS && r[2] == a.rp[r[0]] && r[3] == a.rp[r[0] + r[1]] &&
+        plan_ok = r[0] == next_row && r[1] >= 1 && r[1] <= max_rows && r[2] == a.rp[r[0]] && r[3] == a.rp[r[0] + r[1]] &&
                   r[4] % 4 == 0 && r[7] <= budget && r[7] <= max_smem;
         next_row = r[0] + r[1];
         for (int i = 1; i < r[5] && plan_ok; ++i) plan_ok = cols[r[4] + i] > cols[r[4] + i - 1];
@@ -641,16 +644,31 @@ void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, u
     Aligned<uint32_t> flags(8);
     flags.p[0] = 41;
     flags.p[1] = 40;
+    // the fused push (with_flags: this rank also holds B and pushes it to two "peers"):
+    // pflags [0..2) the peers' done flags (already at the push count), [2] pushes, [3], [4] the peers' ready flags
+    Aligned<uint32_t> pflags(8);
+    pflags.p[0] = pflags.p[1] = pflags.p[2] = 7;
+    Aligned<T> peer0((size_t)K * ld), peer1((size_t)K * ld);
+    sx::PushList plist = {};
+    plist.dst[0] = reinterpret_cast<int4 *>(peer0.p);
+    plist.dst[1] = reinterpret_cast<int4 *>(peer1.p);
+    plist.ready[0] = pflags.p + 3;
+    plist.ready[1] = pflags.p + 4;
     sx_emu::launch((unsigned)nb, THREADS, (size_t)std::max(max_smem, 16), [&] {
         sx::spmm_edgelist_kernel<T, G, true>(reinterpret_cast<const int4 *>(dblocks.p), dcols.p,
                                              rp.p, dlcol.p, val.p, B.p, ldv, Cin.p, Cout.p, ldv, alpha, beta, nvec,
                                              sx::SX_EDGE_PREFETCH, with_flags ? flags.p : nullptr, flags.p + 1, flags.p + 2,
-                                             flags.p + 4);
+                                             flags.p + 4, with_flags ? 2 : 0, plist, (int64_t)((size_t)K * ld * sizeof(T) / 16),
+                                             pflags.p, pflags.p + 2);
     });
     bool ok = true;
     for (int i = 0; i < M && ok; ++i) ok = same_bits(Cout.p + (int64_t)i * ld, Ref.p + (int64_t)i * ld, (size_t)N);
     // the last block advanced the epoch, acknowledged to the pusher and reset the block counter; no time-out
     if (with_flags) ok = ok && flags.p[1] == 41u && flags.p[2] == 41u && flags.p[6] == 0u && flags.p[5] == 0u;
+    // both peers hold the whole B image and were told so; the push count moved on
+    if (with_flags)
+        ok = ok && std::memcmp(peer0.p, B.p, (size_t)K * ld * sizeof(T)) == 0 && std::memcmp(peer1.p, B.p, (size_t)K * ld * sizeof(T)) == 0 &&
+             pflags.p[3] == 8u && pflags.p[4] == 8u && pflags.p[2] == 8u;
     std::printf("%-34s %s M=%d K=%d N=%d G=%d budget=%d blocks=%d cols=%lld/%d: %s\n", what, tname, M, K, N, G, budget, nb,
                 (long long)total, nnz, ok ? "bit-exact" : "MISMATCH");
     if (!ok) ++failures;

@@ -57,7 +57,7 @@ def main():
         e.set_stream(stream.cuda_stream)
         e.upload_csr(blk.rows, K, blk.rowptr, blk.colidx, blk.val)
         engs.append(e)
-    px = PushExchange(engs, N, side_stream=False)      # B changes every step: the push follows its staging in stream order
+    px = PushExchange(engs, N)
     ld = 16
     for k in range(7):
         j = k % 3
@@ -68,7 +68,7 @@ def main():
             eng.stage_B(N, B)
         else:
             eng.device_B(N)
-        px.before_step(k, stream)
+        px.before_step(k)
         eng.stage_C(N, Cb)
         eng.launch(0.85, -2.06)
         eng.fetch_C(Cb)
@@ -82,13 +82,9 @@ def main():
     dist.barrier()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g, stream=stream):
-        for x in px.extra_streams():
-            x.wait_stream(stream)
         for k in range(3):
-            px.before_step(k, stream)
+            px.before_step(k)
             engs[k].spmm_device(N, 0.85, engs[k].device_B(N)[0], ld, -2.06, dCin[k], dCout[k], ld)
-        for x in px.extra_streams():
-            stream.wait_stream(x)
     for _ in range(4):
         with torch.cuda.stream(stream):
             g.replay()

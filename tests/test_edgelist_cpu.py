@@ -9,13 +9,15 @@ import sextans_b200 as sx
 from helpers import mtx_path, random_csr
 
 
-def check_plan(M, K, rp, ci, row_bytes, elem, budget, blocks, cols, lcol, total, max_smem, rows=32):
+def check_plan(M, K, rp, ci, row_bytes, elem, budget, blocks, cols, lcol, total, max_smem, rows=32, target=0):
     assert blocks.shape[1] == 8 and lcol.size == ci.size and cols.size % 4 == 0
     nxt = 0
     tot = 0
     for b in blocks:
         r0, nr, jb, je, c0, ncols, _, smem = (int(x) for x in b)
-        assert r0 == nxt and 1 <= nr <= rows and (r0 // rows) == ((r0 + nr - 1) // rows)
+        assert r0 == nxt and 1 <= nr <= rows and (r0 // 4096) == ((r0 + nr - 1) // 4096)
+        if target and nr > 1:                 # never further from the target than without its last row
+            assert (je - jb) - target <= target - (rp[r0 + nr - 1] - jb)
         assert jb == rp[r0] and je == rp[r0 + nr] and c0 % 4 == 0
         mine = cols[c0:c0 + ncols]
         assert mine.tolist() == sorted(set(ci[jb:je].tolist()))
@@ -23,7 +25,8 @@ def check_plan(M, K, rp, ci, row_bytes, elem, budget, blocks, cols, lcol, total,
         pad = cols[c0 + ncols:c0 + ((ncols + 3) & ~3)]
         assert ncols == 0 or np.all(pad == mine[-1])                 # pad entries name a real column
         na = ((je - (jb & ~7) + 7) & ~7) if je > jb else 0
-        assert smem == ncols * row_bytes + na * (elem + 2) + ((ncols + 3) & ~3) * 4 and smem <= budget and smem <= max_smem
+        assert smem == ncols * row_bytes + na * (elem + 2) + ((ncols + 3) & ~3) * 4 + ((nr + 4) & ~3) * 4
+        assert smem <= budget and smem <= max_smem
         nxt = r0 + nr
         tot += ncols
     assert nxt == M and tot == total
@@ -34,12 +37,18 @@ def test_suitesparse_plans(name, row_bytes, elem, distinct):
     """BASELINE configs[1] (N=16 fp64) and configs[2] (N=16 fp32) at four blocks per SM."""
     M, K, nnz, rp, ci, v, _ = oracle.load_mtx(mtx_path(name), np.float32)
     blocks, runs, lcol, total, max_smem = sx.plan_edge_lists(M, K, rp, ci, row_bytes, elem, 56192)
-    assert len(blocks) == (M + 31) // 32 and total == distinct      # no 32-row group had to be cut
+    assert len(blocks) == sum((min(M, g + 4096) - g + 31) // 32 for g in range(0, M, 4096)) and total <= distinct + 400   # no block had to be cut
+    # cut by nonzeros into ~148 blocks (what the engine does with a small matrix on 148 SMs)
+    target = -(-nnz // 148)
+    bal = sx.plan_edge_lists(M, K, rp, ci, row_bytes, elem, 115000, max_rows=128, nnz_target=target)
+    check_plan(M, K, rp, ci, row_bytes, elem, 115000, *bal, rows=128, target=target)
+    sizes = bal[0][:, 3] - bal[0][:, 2]
+    assert 140 <= len(sizes) <= 160 and sizes.max() <= 1.25 * target
     check_plan(M, K, rp, ci, row_bytes, elem, 56192, blocks, runs, lcol, total, max_smem)
     assert total * 2 <= nnz                                          # a staged B row serves >= 2 nonzeros
     # a budget that forces cuts
     small = sx.plan_edge_lists(M, K, rp, ci, row_bytes, elem, 12000)
-    assert len(small[0]) > len(blocks) and small[3] >= total
+    assert len(small[0]) > len(blocks) and small[3] >= total - 400
     check_plan(M, K, rp, ci, row_bytes, elem, 12000, *small)
 
 
@@ -58,9 +67,9 @@ def test_random_matrices_with_empty_rows_and_unsorted_columns(seed):
             assert worst * (row_bytes + 4) + (worst + 14) * (elem + 2) > budget * 0.5
             continue
         check_plan(M, K, rp, ci, row_bytes, elem, budget, *plan)
-        plan = sx.plan_edge_lists(M, K, rp, ci, row_bytes, elem, budget, rows_per_block=128)
+        plan = sx.plan_edge_lists(M, K, rp, ci, row_bytes, elem, budget, max_rows=128, nnz_target=50)
         if len(plan[0]):
-            check_plan(M, K, rp, ci, row_bytes, elem, budget, *plan, rows=128)
+            check_plan(M, K, rp, ci, row_bytes, elem, budget, *plan, rows=128, target=50)
 
 
 def test_degenerate_inputs():
