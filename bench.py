@@ -84,9 +84,9 @@ def parse():
     p.add_argument("--tiles", type=int, default=0, help="SX_OPT_TILE_MIN_ROWS (fp64 dense-tile tensor-core variant; 0 off)")
     p.add_argument("--col-window-rows", type=int, default=0, help="SX_OPT_COL_WINDOW_ROWS (0 off, -1 = 32 MiB of B per window)")
     p.add_argument("--slide", type=int, default=0, help="SX_OPT_SLIDE: chains per SM of the sliding-window kernel; use with --kernel 4")
-    p.add_argument("--window-rows", type=int, default=0, choices=[0, 32, 64, 128], help="SX_OPT_WINDOW_ROWS: rows per block of variant 3")
     p.add_argument("--pdl", type=int, default=-1, choices=[-1, 0, 1], help="SX_OPT_PDL: programmatic dependent launch (-1 auto: on for the edge-list kernel)")
     p.add_argument("--prefetch", type=int, default=-1, choices=[-1, 0, 1], help="SX_OPT_PREFETCH: L2 prefetch hints (-1 auto)")
+    p.add_argument("--host-fused", type=int, default=-1, choices=[-1, 0, 1], help="SX_OPT_HOST_FUSED: e2e calls let the SpMM kernel carry C across PCIe (-1 auto: on)")
     p.add_argument("--ref-threads", type=int, default=-1, help="--impl reference: threads of the CPU path (-1 = all cores, row-parallel; 1 = as the reference runs it)")
     p.add_argument("--peer-bytes", type=int, default=8 << 20, help="N>1: B images up to this size travel through peer memory instead of NCCL")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -353,7 +353,7 @@ class Case:
             e.set_option(sx.OPT_COL_WINDOW_ROWS, cw)
             e.set_option(sx.OPT_PDL, args.pdl)
             e.set_option(sx.OPT_PREFETCH, args.prefetch)
-            e.set_option(sx.OPT_WINDOW_ROWS, args.window_rows)
+            e.set_option(sx.OPT_HOST_FUSED, args.host_fused)
             e.set_option(sx.OPT_SLIDE, args.slide)
             if args.split >= 0:
                 e.set_option(sx.OPT_SPLIT_ROW_NNZ, args.split)
@@ -688,7 +688,7 @@ def run_native(args):
         if sharded is not None:
             sharded.spmm(N, ALPHA, hB if rank == 0 else None, BETA, hC)
         else:
-            eng.spmm(N, ALPHA, hB, BETA, hC)
+            eng.spmm(N, ALPHA, hB, BETA, hC, want_ns=False)     # kernel_ns = NULL: nobody needs the kernel-only time here
     for _ in range(3):
         hC[:] = w["Cin"]
         e2e_call()
@@ -711,7 +711,7 @@ def run_native(args):
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_t.median().item()) * 1e3
-    host_path = {1: "zero-copy kernels over PCIe (no memcpy)", 2: "zero-copy, C carried by the SpMM kernel"}.get(
+    host_path = {1: "zero-copy kernels over PCIe (no memcpy): B/C_in staging, SpMM, C out", 2: "zero-copy, two launches: B staging, then the SpMM kernel reads C_in from and writes C to the caller's array itself"}.get(
         eng.info(sx.INFO_HOST_PATH), "cudaMemcpyAsync + layout kernels")
     if sharded is not None:
         host_path = f"ShardedSpMM ({sharded.last_exchange} exchange of B)"

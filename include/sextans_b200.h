@@ -74,9 +74,11 @@ enum sx_option {
     /* kernel variant: 0 auto; 1 one lane group per row (+ one warp per
      * long-row segment); 2 TMA-staged nnz-balanced work items; 3 B window of each
      * 32-row block staged into shared memory by TMA (banded matrices whose windows fit;
-     * falls back to 1 otherwise); 4 (experimental) the sliding-window kernel for long banded
-     * matrices, see SX_OPT_SLIDE.  Auto: matrices below one wave of lane groups take 3 if
-     * they qualify, else 1; everything larger takes 2. */
+     * falls back to 1 otherwise); 4 the sliding-window kernel for long banded matrices, see
+     * SX_OPT_SLIDE; 5 edge lists: a row block's DISTINCT B rows staged in shared memory, 16-bit
+     * window-local column indices (any matrix whose rows fit; dense rows of at most 256 bytes).
+     * Auto: 5 where a staged B row serves at least two nonzeros (FEM-type matrices); else 3 for
+     * matrices below one wave of lane groups whose windows fit, else 1 below one wave, else 2. */
     SX_OPT_KERNEL = 2,
     /* nonzeros per work item; 0 = auto (512 for N*sizeof(T) <= 128 bytes, else 256;
      * smaller for small matrices) */
@@ -107,7 +109,9 @@ enum sx_option {
      * (rounding-level differences).  Ignored when SX_OPT_TILE_MIN_ROWS is in effect or when
      * K <= W. */
     SX_OPT_COL_WINDOW_ROWS = 6,
-    /* TMA-staged kernel: 1 = while a batch's B-row gathers are in flight, prefetch the next
+    /* L2 prefetch hints.  Edge-list kernel: before the dependent-launch wait, ask L2 for the B rows
+     * and C_in rows the block is about to read (on unless 0).
+     * TMA-staged kernel: 1 = while a batch's B-row gathers are in flight, prefetch the next
      * batch's B rows into L2 (prefetch.global.L2; their column indices are already in the
      * shared-memory tile), taking the DRAM latency of the gathers off the lane group's
      * critical path.  Results are unaffected.  0 = off.  -1 (default) = auto: on when B is
@@ -115,35 +119,31 @@ enum sx_option {
      * M=K=1e6, nnz=9.6e7, N=16 fp64 1.63 -> 1.49 ms; uniform N=128 fp32, DRAM-bound,
      * 1.456 -> 1.470 ms, hence left off for wide rows). */
     SX_OPT_PREFETCH = 7,
-    /* EXPERIMENTAL (off by default; not yet measured on hardware).  1: an sx_spmm_* call that
-     * takes the zero-copy path on a matrix that runs variant 3, with rp_time <= 1 and
-     * kernel_ns == NULL (nobody asks for the kernel-only time), lets the SpMM kernel read
-     * C_in from and write C to the caller's page-locked array itself: B staging + one kernel
-     * instead of three launches, C's inbound and outbound PCIe transfers overlapping each
-     * other and the compute.  Same arithmetic, same results.  SX_INFO_HOST_PATH reports 2. */
+    /* -1 (default) / 1: an sx_spmm_* call that takes the zero-copy path on a matrix that runs the
+     * edge-list kernel, with rp_time <= 1 and kernel_ns == NULL (nobody asks for the kernel-only
+     * time), lets the SpMM kernel read C_in from and write C to the caller's page-locked array
+     * itself: B staging + one kernel (its programmatic dependent) instead of three launches, C's
+     * inbound and outbound PCIe transfers overlapping each other, B's transfer and the compute.
+     * Same arithmetic, same results.  SX_INFO_HOST_PATH reports 2.  0: off. */
     SX_OPT_HOST_FUSED = 8,
-    /* EXPERIMENTAL (off by default; not yet measured on hardware).  1: variant 3 is launched
-     * with programmatic stream serialization (PDL): its A-side prologue (block record, row
-     * pointers, TMA of the colidx/val slice) may run while the previous kernel of the stream
-     * is still finishing; B and C_in are only touched after griddepcontrol.wait.  For the
-     * launch-bound SuiteSparse configs.  Results are unaffected. */
+    /* Programmatic dependent launch.  -1 (default): the edge-list kernel is launched with
+     * programmatic stream serialization -- its A-side prologue (records, row pointers, TMA of its
+     * slice of A, L2 prefetch hints for B and C_in) runs while the previous kernel of the stream
+     * is still finishing; B and C_in are only read after griddepcontrol.wait (nasa4704: 4.3 ->
+     * 3.5 us per step).  1: variant 3 as well.  0: never.  Results are unaffected. */
     SX_OPT_PDL = 9,
-    /* EXPERIMENTAL (not yet measured on hardware); read by the NEXT sx_upload_csr_*.
-     * Rows per thread block of variant 3: 0 or 32 (default, the validated kernel), 64, 128.
-     * Consecutive 32-row blocks of a banded matrix stage almost the same B window, so taller
-     * blocks move proportionally fewer window bytes out of L2 and need fewer waves
-     * (pcrystk02: 437 blocks -> 219 / 110).  Used where the taller block's window and A
-     * slice still fit in shared memory and RB * lanes-per-row <= 1024 threads; otherwise
-     * the 32-row blocks run.  Results are unaffected. */
+    /* retired (taller row blocks of variant 3: measured 10 % at best, superseded by variant 5);
+     * the value is accepted and ignored */
     SX_OPT_WINDOW_ROWS = 10,
-    /* EXPERIMENTAL (not yet measured on hardware); read by the NEXT sx_upload_csr_*.
+    /* Read by the NEXT sx_upload_csr_*.
      * n in 1..8: plan n chains per SM for the sliding-window kernel (variant 4, selected with
      * SX_OPT_KERNEL = 4): a thread block walks a run of consecutive 32-row steps with B held in
      * a shared-memory ring that follows the band -- each step loads only the B rows above the
      * highest one loaded so far -- and the next steps' loads overlap the current step's
      * arithmetic.  For LONG banded matrices, where variant 3 keeps re-fetching nearly the same
-     * window.  Falls back to the automatic choice where the ring the plan needs does not fit
-     * in shared memory for the N in use.  Results are unaffected.  0 (default): no plan. */
+     * window (FEM-like band of 100, M = 1e6, fp64: 0.78 ms against 1.11 ms).  Falls back to the
+     * automatic choice where the ring the plan needs does not fit in shared memory for the N in
+     * use.  Results are unaffected.  0 (default): no plan. */
     SX_OPT_SLIDE = 11,
     /* EXPERIMENTAL (not yet run on hardware).  1: the first SpMM for a column count N (device
      * operands with C_out != C_in, outside graph capture) times every kernel variant that

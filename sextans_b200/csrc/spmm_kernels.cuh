@@ -562,12 +562,8 @@ spmm_staged_kernel(const int nitems, const int4 *__restrict__ items, const int t
 // issued right after, so that the NEXT kernel's A-side prologue overlaps this kernel's body:
 // for the launch-bound SuiteSparse configs a step is a chain of latencies (block record ->
 // TMA -> arithmetic), and this takes the A-side part of it off the critical path.
-// RB = rows per block (32; 64 and 128 experimental, SX_OPT_WINDOW_ROWS): consecutive
-// 32-row blocks of a banded matrix stage almost the same window (pcrystk02: 437 windows of
-// ~950 B rows for a B of 13 965 rows), so a taller block moves proportionally fewer window
-// bytes from L2 and needs fewer waves; the block record then describes RB rows.
-template <typename T, int G, bool STRICT, bool PDL = false, int RB = 32>
-__global__ void __launch_bounds__(RB * G)
+template <typename T, int G, bool STRICT, bool PDL = false>
+__global__ void __launch_bounds__(32 * G)
 spmm_window_kernel(const int M, const int4 *__restrict__ blocks, const int *__restrict__ rowptr,
                    const int *__restrict__ colidx, const T *__restrict__ val, const T *__restrict__ B,
                    const uint32_t ldbv, const T *Cin, T *Cout, const uint32_t ldcv, const T alpha,
@@ -576,7 +572,7 @@ spmm_window_kernel(const int M, const int4 *__restrict__ blocks, const int *__re
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     const int lg = threadIdx.x & (G - 1);
-    const int row = blockIdx.x * RB + threadIdx.x / G;
+    const int row = blockIdx.x * 32 + threadIdx.x / G;
     const int4 blk = __ldg(blocks + blockIdx.x);
     const int jal = blk.z & ~3;  // 16-byte aligned start of the A slice
     const uint32_t cnt = (uint32_t)((blk.w - jal + 3) & ~3);
@@ -603,18 +599,8 @@ spmm_window_kernel(const int M, const int4 *__restrict__ blocks, const int *__re
         for (uint32_t o = 0; o < wbytes; o += 32768u)  // several copies in flight
             tma_bulk_g2s(smem_raw + o, src + o, min(32768u, wbytes - o), &bar, pol_b);
         if (!PDL) {
-            if (RB == 32) {
-                tma_bulk_g2s(const_cast<T *>(sval), val + jal, cnt * (uint32_t)sizeof(T), &bar, pol_a);
-                tma_bulk_g2s(const_cast<int *>(scol), colidx + jal, cnt * 4u, &bar, pol_a);
-            } else {  // a taller block's A slice is tens of KB: several copies in flight, like the window
-                const uint32_t vb = cnt * (uint32_t)sizeof(T), cb = cnt * 4u;
-                for (uint32_t o = 0; o < vb; o += 16384u)
-                    tma_bulk_g2s(reinterpret_cast<unsigned char *>(const_cast<T *>(sval)) + o,
-                                 reinterpret_cast<const unsigned char *>(val + jal) + o, min(16384u, vb - o), &bar, pol_a);
-                for (uint32_t o = 0; o < cb; o += 16384u)
-                    tma_bulk_g2s(reinterpret_cast<unsigned char *>(const_cast<int *>(scol)) + o,
-                                 reinterpret_cast<const unsigned char *>(colidx + jal) + o, min(16384u, cb - o), &bar, pol_a);
-            }
+            tma_bulk_g2s(const_cast<T *>(sval), val + jal, cnt * (uint32_t)sizeof(T), &bar, pol_a);
+            tma_bulk_g2s(const_cast<int *>(scol), colidx + jal, cnt * 4u, &bar, pol_a);
         }
     }
     if (row >= M) {  // after the barrier above; no block-wide barrier below
@@ -686,6 +672,13 @@ spmm_window_kernel(const int M, const int4 *__restrict__ blocks, const int *__re
 // staged and its B rows on the way to L2 by the time this kernel completes.  Launched without the
 // attribute the two instructions do nothing.
 //
+// HOSTC = true is the host-facing call's kernel (sx_spmm_* with page-locked operands and no
+// kernel time asked for): C never exists as a device image.  A block reads the C_in tile of its
+// rows straight from the caller's column-major array over PCIe in its prologue -- before the
+// dependent-launch wait, i.e. while the kernel that stages B is still running -- and writes the
+// result tile back the same way, so C's two PCIe directions overlap each other, B's transfer and
+// the arithmetic, and the call is two launches (B staging, this) instead of three.
+//
 // Multi-GPU, the rank that holds B (npush > 0): the exchange is part of THIS kernel.  After the
 // dependent-launch wait every block waits until the peers have finished with the previous
 // contents of their images (done[p] >= *pushes), copies its 1/gridDim share of the B image into
@@ -722,16 +715,17 @@ template <int G> struct EdgeShape {
     static constexpr int THREADS = G >= 16 ? 512 : 256;
     static constexpr int ROWS = THREADS / G;
 };
-template <typename T, int G, bool STRICT>
+template <typename T, int G, bool STRICT, bool HOSTC = false>
 __global__ void __launch_bounds__(EdgeShape<G>::THREADS, 2)
 spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ cols, const int *__restrict__ rowptr,
                      const uint16_t *__restrict__ lcol, const T *__restrict__ val, const T *__restrict__ B,
                      const uint32_t ldbv, const T *Cin, T *Cout, const uint32_t ldcv, const T alpha, const T beta,
                      const int nvec, const int flags, const uint32_t *ready, uint32_t *epoch, uint32_t *done_remote,
                      unsigned int *sync_words, const int npush, const PushList push, const int64_t push_n16,
-                     const uint32_t *push_done, uint32_t *pushes) {
+                     const uint32_t *push_done, uint32_t *pushes, T *Ch, const int64_t ldh, const int N,
+                     const uint32_t tile_off, const int tile_ld) {
     using V = typename VecOf<T>::type;
-    constexpr int THREADS = EdgeShape<G>::THREADS, ROWS = EdgeShape<G>::ROWS;
+    constexpr int THREADS = EdgeShape<G>::THREADS, ROWS = EdgeShape<G>::ROWS, E = VecOf<T>::E;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;  // the A slice and the column list
 #ifdef SX_EDGE_TRACE
@@ -778,12 +772,20 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
         tma_bulk_g2s(const_cast<uint16_t *>(scol), lcol + jal, na * 2u, &bar, pol_a);
     }
     for (int i = threadIdx.x; i <= nrows; i += THREADS) srp[i] = __ldg(rowptr + row0 + i);
+    T *tile = reinterpret_cast<T *>(smem_raw + tile_off);  // HOSTC: tile[column * tile_ld + row of the block]
+    if (HOSTC) {
+        // the caller's C_in, straight from its page-locked column-major array over PCIe: a warp per
+        // column, lanes along the rows (consecutive addresses).  It is the CALLER's data, not the
+        // previous kernel's, so it is fetched here, while that kernel (the staging of B) still runs.
+        for (int cidx = threadIdx.x >> 5; cidx < N; cidx += THREADS / 32)
+            for (int r = threadIdx.x & 31; r < nrows; r += 32) tile[cidx * tile_ld + r] = Ch[(size_t)cidx * ldh + row0 + r];
+    }
     const unsigned char *Bb = reinterpret_cast<const unsigned char *>(B) + lg * 16;
     if (has) mbar_wait(&bar, 0);
     if (flags & SX_EDGE_PREFETCH) {
         if (lg * 16 < (int)rowbytes && (lg & 7) == 0)  // one prefetch per 128-byte line of a row
             for (int lr = rl; lr < ncols; lr += ROWS) prefetch_l2(Bb + (size_t)(uint32_t)scols[lr] * rowbytes);
-        if (threadIdx.x == THREADS - 1 && nrows > 0)
+        if (!HOSTC && threadIdx.x == THREADS - 1 && nrows > 0)
             bulk_prefetch_l2(reinterpret_cast<const unsigned char *>(Cin) + (size_t)row0 * ldcv * 16u, (uint32_t)nrows * ldcv * 16u);
     }
     // ---- B and C_in: only after the previous kernel is complete ----
@@ -830,7 +832,7 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
     V *Ov = reinterpret_cast<V *>(Cout) + (size_t)row0 * ldcv + lg;
     V cin_next;
     vzero(cin_next);
-    if (lane_on && rl < nrows) cin_next = Cv[(size_t)rl * ldcv];
+    if (!HOSTC && lane_on && rl < nrows) cin_next = Cv[(size_t)rl * ldcv];
     cp_async_wait_all();
     __syncthreads();
     SX_TRACE_MARK(3);
@@ -840,8 +842,14 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
     if (lane_on)
         for (int rr = rl; rr < nrows; rr += ROWS) {
             const int begin = srp[rr], end = srp[rr + 1];
-            const V cin = cin_next;
-            if (rr + ROWS < nrows) cin_next = Cv[(size_t)(rr + ROWS) * ldcv];
+            V cin = cin_next;
+            if (HOSTC) {
+                T *cp = reinterpret_cast<T *>(&cin);
+#pragma unroll
+                for (int e = 0; e < E; ++e) cp[e] = (lg * E + e < N) ? tile[(lg * E + e) * tile_ld + rr] : T(0);
+            } else if (rr + ROWS < nrows) {
+                cin_next = Cv[(size_t)(rr + ROWS) * ldcv];
+            }
             V acc;
             vzero(acc);
             // chunks of 8 nonzeros, software-pipelined: the (column, value) pairs of chunk k+1 and the
@@ -886,8 +894,21 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
                 for (int u = 0; u < UC; ++u)
                     if (j + u < end) vmac<STRICT>(acc, a[u], b[u]);
             }
-            Ov[(size_t)rr * ldcv] = vaxpby<STRICT>(alpha, acc, beta, cin);
+            const V out = vaxpby<STRICT>(alpha, acc, beta, cin);
+            if (HOSTC) {
+                const T *op = reinterpret_cast<const T *>(&out);
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    if (lg * E + e < N) tile[(lg * E + e) * tile_ld + rr] = op[e];
+            } else {
+                Ov[(size_t)rr * ldcv] = out;
+            }
         }
+    if (HOSTC) {  // the result tile back into the caller's array, a warp per column again
+        __syncthreads();
+        for (int cidx = threadIdx.x >> 5; cidx < N; cidx += THREADS / 32)
+            for (int r = threadIdx.x & 31; r < nrows; r += 32) Ch[(size_t)cidx * ldh + row0 + r] = tile[cidx * tile_ld + r];
+    }
 #ifdef SX_EDGE_TRACE
     SX_TRACE_MARK(4);      // thread 0 done with its own rows
     __syncthreads();
@@ -1049,111 +1070,6 @@ spmm_slide_kernel(const int M, const int2 *__restrict__ chains, const int4 *__re
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             issue(s + 2, slot);
         }
-    }
-}
-
-// ---- variant 3 fused with the host boundary (experimental, SX_OPT_HOST_FUSED) -------------
-// For the small banded matrices that take variant 3 the host-facing call is dominated by
-// PCIe, not by the SpMM: B and C_in cross the bus into device images, the kernel runs, C
-// crosses back -- three launches in a row, each waiting for the one before.  This kernel
-// removes the C staging: a block reads the C_in tile of its 32 rows straight from the
-// caller's column-major page-locked array (one contiguous 32-row segment per column, 16
-// bytes per thread) into shared memory while its B window is on the way by TMA, computes
-// exactly like spmm_window_kernel, puts the result back into the same shared tile and
-// writes it to the caller's array, again one contiguous segment per column.  C's inbound and
-// outbound transfers of different blocks overlap each other and the compute (PCIe is full
-// duplex), and the call is two launches (B staging, this) instead of three.
-//   Ch     the caller's C, column-major, ld = M, in/out IN PLACE (a block reads its whole
-//          tile before it writes any of it, and tiles of different blocks are disjoint)
-//   host requirements: M % E == 0 and Ch 16-byte aligned (every segment piece is then a
-//          whole, aligned 16-byte unit), N <= G * E (one vector per lane)
-// dynamic smem = window + A slice (as spmm_window_kernel) + ncols_pad * (32 + E) * sizeof(T)
-template <typename T, int G, bool STRICT>
-__global__ void __launch_bounds__(32 * G)
-spmm_window_hostc_kernel(const int M, const int4 *__restrict__ blocks, const int *__restrict__ rowptr,
-                         const int *__restrict__ colidx, const T *__restrict__ val, const T *__restrict__ B,
-                         const uint32_t ldbv, T *Ch, const int N, const T alpha, const T beta, const int nvec,
-                         const uint32_t tile_off) {
-    using V = typename VecOf<T>::type;
-    constexpr int E = VecOf<T>::E;
-    constexpr int LDT = 32 + E;  // padded column of the C tile: keeps 16-byte alignment, spreads banks
-    constexpr int PPC = 32 / E;  // 16-byte pieces per 32-row column segment
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t bar;
-    const int lg = threadIdx.x & (G - 1);
-    const int rl = threadIdx.x / G;  // row inside the block
-    const int r0 = blockIdx.x * 32;
-    const int row = r0 + rl;
-    const int4 blk = __ldg(blocks + blockIdx.x);
-    const int jal = blk.z & ~3;
-    const uint32_t cnt = (uint32_t)((blk.w - jal + 3) & ~3);
-    const uint32_t wbytes = (uint32_t)blk.y * ldbv * 16u;
-    const V *win = reinterpret_cast<const V *>(smem_raw);
-    const T *sval = reinterpret_cast<const T *>(smem_raw + wbytes);
-    const int *scol = reinterpret_cast<const int *>(smem_raw + wbytes + (size_t)cnt * sizeof(T));
-    T *tile = reinterpret_cast<T *>(smem_raw + tile_off);  // tile[c * LDT + r], c < nvec * E
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && blk.w > blk.z) {
-        const uint64_t pol_a = policy_evict_first();
-        mbar_expect_tx(&bar, wbytes + cnt * (uint32_t)(sizeof(T) + 4));
-        const unsigned char *src = reinterpret_cast<const unsigned char *>(B) + (size_t)blk.x * ldbv * 16u;
-        uint64_t pol_b;
-        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_b));
-        for (uint32_t o = 0; o < wbytes; o += 32768u)
-            tma_bulk_g2s(smem_raw + o, src + o, min(32768u, wbytes - o), &bar, pol_b);
-        tma_bulk_g2s(const_cast<T *>(sval), val + jal, cnt * (uint32_t)sizeof(T), &bar, pol_a);
-        tma_bulk_g2s(const_cast<int *>(scol), colidx + jal, cnt * 4u, &bar, pol_a);
-    }
-    // C_in tile from the caller's array: piece p = (column c, 16-byte unit k of the segment)
-    const int npieces = N * PPC;
-    for (int p = threadIdx.x; p < npieces; p += 32 * G) {
-        const int c = p / PPC, k = p - c * PPC;
-        V v;
-        vzero(v);
-        if (r0 + k * E < M) v = *reinterpret_cast<const V *>(Ch + (size_t)M * c + r0 + k * E);
-        *reinterpret_cast<V *>(tile + c * LDT + k * E) = v;
-    }
-    __syncthreads();
-    const bool mine = lg < nvec && row < M;
-    if (mine) {
-        const int begin = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
-        T cin[E], out[E];
-#pragma unroll
-        for (int e = 0; e < E; ++e) cin[e] = (lg * E + e < N) ? tile[(lg * E + e) * LDT + rl] : T(0);
-        V acc;
-        vzero(acc);
-        if (blk.w > blk.z) mbar_wait(&bar, 0);
-        const V *w = win + lg;
-        const int cmin = blk.x;
-        int j = begin;
-        for (; j + 4 <= end; j += 4) {
-            int c[4];
-            T a[4];
-            V b[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { c[u] = scol[j + u - jal]; a[u] = sval[j + u - jal]; }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) b[u] = w[(uint32_t)(c[u] - cmin) * ldbv];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) vmac<STRICT>(acc, a[u], b[u]);
-        }
-        for (; j < end; ++j) vmac<STRICT>(acc, sval[j - jal], w[(uint32_t)(scol[j - jal] - cmin) * ldbv]);
-        const T *ap = reinterpret_cast<const T *>(&acc);
-#pragma unroll
-        for (int e = 0; e < E; ++e) out[e] = axpby<STRICT>(alpha, ap[e], beta, cin[e]);
-#pragma unroll
-        for (int e = 0; e < E; ++e)
-            if (lg * E + e < N) tile[(lg * E + e) * LDT + rl] = out[e];
-    }
-    __syncthreads();
-    for (int p = threadIdx.x; p < npieces; p += 32 * G) {
-        const int c = p / PPC, k = p - c * PPC;
-        if (r0 + k * E < M)
-            *reinterpret_cast<V *>(Ch + (size_t)M * c + r0 + k * E) = *reinterpret_cast<const V *>(tile + c * LDT + k * E);
     }
 }
 
@@ -1610,6 +1526,7 @@ colmajor_to_rowmajor_pair_kernel(const int64_t rowsB, const int64_t rowsC, const
                                  const int tcol, const int64_t tilesB) {
     constexpr int TR = 32 * VEC;  // rows per tile
     __shared__ T tile[32][TR + 1];
+    pdl_launch_dependents();  // a dependent launch (the fused SpMM) may run its A-side prologue beside this kernel
     int64_t t = blockIdx.x;
     const bool isC = t >= tilesB;
     if (isC) t -= tilesB;

@@ -129,9 +129,6 @@ struct sx_ctx {
     // variant 3: per block of 32 rows {first column, column span, nnz begin, nnz end}
     DevBuf wblocks;
     int nwblocks = 0, max_span = 0, max_block_nnz = 0;
-    // the same for blocks of 64 and 128 rows (SX_OPT_WINDOW_ROWS, experimental)
-    struct WideBlocks { DevBuf blocks; int n = 0, max_span = 0, max_block_nnz = 0; } wide[2];
-    int window_rows = 0;  // 0 / 32: the validated 32-row blocks; 64, 128: wide[0], wide[1]
     // variant 4 (SX_OPT_SLIDE, experimental): chains of 32-row steps over a sliding B window
     // SX_OPT_AUTOTUNE: per (N, arithmetic) the variant that measured fastest on this matrix
     struct Tuned { int N, arith, kernel, prefetch; float us; };
@@ -175,7 +172,7 @@ struct sx_ctx {
     int kernel = 0;
     int item_nnz = 0;  // 0 = auto
     int prefetch = -1;  // SX_OPT_PREFETCH: -1 auto, 0 off, 1 on
-    int host_fused = 0;  // SX_OPT_HOST_FUSED (experimental)
+    int host_fused = -1;  // SX_OPT_HOST_FUSED: -1 auto (on), 0 off, 1 on
     int pdl = -1;        // SX_OPT_PDL: -1 auto (variant 5 always, variant 3 never), 0 off, 1 on
     int64_t zerocopy_bytes = 3 << 19;  // 1.5 MiB: above that the copy engines win
     int last_path = 0;  // 1: the last host-facing call took the zero-copy path
@@ -223,6 +220,54 @@ bool pick_shape(int nvec, Shape *s) {
     return true;
 }
 
+// One launch of spmm_edgelist_kernel over a plan.  Ch != nullptr: the host-facing form (HOSTC), C read
+// from and written to the caller's page-locked column-major array by the kernel itself.
+template <typename T, int G, bool STRICT, bool HOSTC>
+int launch_edge(sx_ctx *c, const EdgePlan *ep, int N, T alpha, const T *dB, int64_t ldb, T beta, const T *dCin, T *dCout,
+                int64_t ldc, T *Ch) {
+    constexpr int E = sx::VecOf<T>::E;
+    const int nvec = (N * (int)sizeof(T) + 15) / 16;
+    auto kern = sx::spmm_edgelist_kernel<T, G, STRICT, HOSTC>;
+    const int tile_ld = sx::EdgeShape<G>::ROWS + 1;
+    const size_t tile_off = ((size_t)std::max(ep->max_smem, 16) + 15) & ~(size_t)15;
+    const size_t smem = HOSTC ? tile_off + (size_t)N * tile_ld * sizeof(T) : (size_t)std::max(ep->max_smem, 16);
+    if (smem > 48 * 1024 &&
+        std::find(c->big_smem_ok.begin(), c->big_smem_ok.end(), (const void *)kern) == c->big_smem_ok.end()) {
+        // the opt-in limit is 227 KB minus the kernel's static shared memory (its mbarrier)
+        SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+        c->big_smem_ok.push_back((const void *)kern);
+    }
+    if (smem > 227 * 1024 - 1024) return fail(SX_ERR_INVALID, "internal: edge-list block needs %zu bytes of shared memory", smem);
+    const bool pf = c->prefetch != 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ep->nblocks);
+    cfg.blockDim = dim3(sx::EdgeShape<G>::THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = c->pdl != 0 ? 1 : 0;
+    int rc;
+    if ((c->x_ready || c->p_npeers) && (rc = ensure_sync_words(c))) return rc;
+    // the fused push sends the image this launch reads: K rows of ldb elements, from column 0
+    const int npush = c->win_col0 == 0 ? c->p_npeers : 0;
+    const int64_t push_n16 = (int64_t)((size_t)c->K * (size_t)ldb * sizeof(T) / 16);
+    SX_CUDA(cudaLaunchKernelEx(&cfg, kern, (const int4 *)ep->blocks.p, (const int *)ep->cols.p, (const int *)c->rowptr.p,
+                               (const uint16_t *)ep->lcol.p, (const T *)c->val.p, dB, (uint32_t)(ldb / E), dCin, dCout,
+                               (uint32_t)(ldc / E), alpha, beta, nvec, pf ? sx::SX_EDGE_PREFETCH : 0, c->x_ready, c->x_epoch,
+                               c->x_done, (unsigned int *)c->sync_words.p, npush, c->p_list, push_n16, c->p_done, c->p_pushes,
+                               Ch, (int64_t)c->M, N, (uint32_t)tile_off, tile_ld));
+    c->x_ready = nullptr;
+    if (npush) c->p_npeers = 0;
+    c->launches++;
+    c->last_edge_plan = ep;
+    c->last_kernel = (HOSTC ? 90000 : 80000) + G * 100 + 10 + (STRICT ? 0 : 1);
+    SX_CUDA(cudaGetLastError());
+    return SX_OK;
+}
+
 template <typename T, int G, int VPL, bool STRICT>
 int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, const T *dCin,
                  T *dCout, int64_t ldc) {
@@ -262,41 +307,7 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
             // a staged row is G vectors wide whatever the leading dimension: the plan depends on G only
             if ((rc = get_edge_plan(c, G * 16, (int)sizeof(T), sx::EdgeShape<G>::ROWS, &ep))) return rc;
             if (ep && ep->usable) {
-                constexpr int E = sx::VecOf<T>::E;
-                auto kern = sx::spmm_edgelist_kernel<T, G, STRICT>;
-                if (ep->max_smem > 48 * 1024 &&
-                    std::find(c->big_smem_ok.begin(), c->big_smem_ok.end(), (const void *)kern) == c->big_smem_ok.end()) {
-                    // the opt-in limit is 227 KB minus the kernel's static shared memory (its two mbarriers)
-                    SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-                    c->big_smem_ok.push_back((const void *)kern);
-                }
-                const bool pf = c->prefetch != 0;
-                cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3((unsigned)ep->nblocks);
-                cfg.blockDim = dim3(sx::EdgeShape<G>::THREADS);
-                cfg.dynamicSmemBytes = (size_t)std::max(ep->max_smem, 16);
-                cfg.stream = c->stream;
-                cudaLaunchAttribute at[1];
-                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-                at[0].val.programmaticStreamSerializationAllowed = 1;
-                cfg.attrs = at;
-                cfg.numAttrs = c->pdl != 0 ? 1 : 0;
-                if ((c->x_ready || c->p_npeers) && (rc = ensure_sync_words(c))) return rc;
-                // the fused push sends the image this launch reads: K rows of ldb elements, from column 0
-                const int npush = c->win_col0 == 0 ? c->p_npeers : 0;
-                const int64_t push_n16 = (int64_t)((size_t)c->K * (size_t)ldb * sizeof(T) / 16);
-                SX_CUDA(cudaLaunchKernelEx(&cfg, kern, (const int4 *)ep->blocks.p, (const int *)ep->cols.p,
-                                           (const int *)c->rowptr.p, (const uint16_t *)ep->lcol.p, (const T *)c->val.p, dB,
-                                           (uint32_t)(ldb / E), dCin, dCout, (uint32_t)(ldc / E), alpha, beta, nvec,
-                                           pf ? sx::SX_EDGE_PREFETCH : 0, c->x_ready, c->x_epoch, c->x_done,
-                                           (unsigned int *)c->sync_words.p, npush, c->p_list, push_n16, c->p_done, c->p_pushes));
-                c->x_ready = nullptr;
-                if (npush) c->p_npeers = 0;
-                c->launches++;
-                c->last_edge_plan = ep;
-                c->last_kernel = 80000 + G * 100 + VPL * 10 + (STRICT ? 0 : 1);
-                SX_CUDA(cudaGetLastError());
-                return SX_OK;
+                return launch_edge<T, G, STRICT, false>(c, ep, N, alpha, dB, ldb, beta, dCin, dCout, ldc, nullptr);
             }
         }
     }
@@ -349,35 +360,6 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
                 c->last_kernel = 70000 + G * 100 + VPL * 10 + (STRICT ? 0 : 1);
                 SX_CUDA(cudaGetLastError());
                 return SX_OK;
-            }
-        }
-    }
-    // SX_OPT_WINDOW_ROWS (experimental): blocks of 64 / 128 rows where RB * G <= 1024 threads
-    if constexpr (G >= 4 && G <= 16 && VPL == 1) {
-        if (variant == 3 && c->window_rows > 32 && c->pdl <= 0) {
-            constexpr int E = sx::VecOf<T>::E;
-            const int w = (c->window_rows >= 128 && G <= 8) ? 1 : 0;
-            const sx_ctx::WideBlocks &W = c->wide[w];
-            const size_t smem = (size_t)W.max_span * (size_t)(ldb / E) * 16 + ((size_t)W.max_block_nnz + 8) * (sizeof(T) + 4) + 16;
-            if (W.n > 0 && smem <= 200 * 1024) {
-                auto launch_rb = [&](auto kern, int RB) -> int {
-                    if (smem > 48 * 1024 &&
-                        std::find(c->big_smem_ok.begin(), c->big_smem_ok.end(), (const void *)kern) == c->big_smem_ok.end()) {
-                        SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                        c->big_smem_ok.push_back((const void *)kern);
-                    }
-                    kern<<<(unsigned)W.n, RB * G, smem, c->stream>>>(
-                        c->M, (const int4 *)W.blocks.p, (const int *)c->rowptr.p, (const int *)c->colidx.p,
-                        (const T *)c->val.p, dB, (uint32_t)(ldb / E), dCin, dCout, (uint32_t)(ldc / E), alpha, beta, nvec);
-                    c->launches++;
-                    c->last_kernel = 30000 + G * 100 + VPL * 10 + (STRICT ? 0 : 1);
-                    SX_CUDA(cudaGetLastError());
-                    return SX_OK;
-                };
-                if constexpr (G <= 8) {
-                    if (w == 1) return launch_rb(sx::spmm_window_kernel<T, G, STRICT, false, 128>, 128);
-                }
-                return launch_rb(sx::spmm_window_kernel<T, G, STRICT, false, 64>, 64);
             }
         }
     }
@@ -861,19 +843,13 @@ int get_edge_plan(sx_ctx *c, int row_bytes, int elem_bytes, int rows, const Edge
     std::vector<int32_t> ci((size_t)c->nnz);
     SX_CUDA(cudaMemcpyAsync(ci.data(), c->colidx.p, (size_t)c->nnz * 4, cudaMemcpyDeviceToHost, c->stream));
     SX_CUDA(cudaStreamSynchronize(c->stream));
-    // A matrix of at most a few waves of `rows`-row blocks is cut by NONZEROS into m blocks per SM
-    // (the reference's equal-length PE lists, src/sparse_helper.h:345-403): the kernel ends when its
-    // slowest block does, and with one wave nothing evens out differences.  A large matrix keeps
-    // blocks of `rows` rows and leaves the balance to the block scheduler.
-    const int nfixed = (c->M + rows - 1) / rows;
-    int max_rows = rows, expect = nfixed;
-    int64_t nnz_target = 0;
-    if (nfixed <= 4 * c->sm_count) {
-        const int m = (nfixed + c->sm_count - 1) / c->sm_count;
-        expect = m * c->sm_count;
-        nnz_target = (c->nnz + expect - 1) / expect;
-        max_rows = 4 * rows;
-    }
+    // Blocks of `rows` rows, one sweep of the lane groups.  (Cutting a small matrix by NONZEROS into
+    // one block per SM -- the planner can: max_rows, nnz_target -- was measured and lost on nasa4704,
+    // 4.30 against 3.58 us per step: blocks of many short rows need several sweeps, and a sweep of
+    // short rows costs its latency, not its nonzeros.)
+    const int expect = (c->M + rows - 1) / rows;
+    const int max_rows = rows;
+    const int64_t nnz_target = 0;
     // four blocks per SM if (almost) every block fits that budget uncut, else two, else one
     int nb = 0, max_smem = 0, rc = SX_OK;
     int32_t *blocks = nullptr, *cols = nullptr;
@@ -982,46 +958,6 @@ int build_window_blocks(sx_ctx *c, int M, const int32_t *rowptr, const int32_t *
     SX_CUDA(cudaMemcpyAsync(c->wblocks.p, blk.data(), blk.size() * 4, cudaMemcpyHostToDevice, c->stream));
     SX_CUDA(cudaStreamSynchronize(c->stream));
     c->nwblocks = nb;
-    return SX_OK;
-}
-
-// Block records for blocks of 64 and 128 rows (same rules as build_window_blocks).
-int build_wide_window_blocks(sx_ctx *c, int M, const int32_t *rowptr, const int32_t *colidx) {
-    for (int w = 0; w < 2; ++w) {
-        sx_ctx::WideBlocks &W = c->wide[w];
-        W.n = W.max_span = W.max_block_nnz = 0;
-        if (M == 0 || c->nwblocks == 0) continue;  // the 32-row blocks did not qualify: neither will these
-        const int RB = 64 << w;
-        const int nb = (M + RB - 1) / RB;
-        std::vector<int32_t> blk((size_t)nb * 4);
-        int64_t span_sum = 0;
-        int max_span = 0, max_block_nnz = 0;
-        bool ok = true;
-        for (int b = 0; b < nb && ok; ++b) {
-            const int r0 = b * RB, r1 = std::min(M, r0 + RB);
-            const int32_t jb = rowptr[r0], je = rowptr[r1];
-            int32_t lo = INT32_MAX, hi = -1;
-            for (int32_t j = jb; j < je; ++j) { lo = std::min(lo, colidx[j]); hi = std::max(hi, colidx[j]); }
-            if (je == jb) { lo = 0; hi = -1; }
-            const int span = hi - lo + 1;
-            if ((int64_t)span * 32 > 200 * 1024 || (int64_t)(je - jb) * 8 > 200 * 1024) ok = false;
-            blk[(size_t)b * 4 + 0] = lo;
-            blk[(size_t)b * 4 + 1] = span;
-            blk[(size_t)b * 4 + 2] = jb;
-            blk[(size_t)b * 4 + 3] = je;
-            span_sum += span;
-            max_span = std::max(max_span, span);
-            max_block_nnz = std::max(max_block_nnz, je - (jb & ~3));
-        }
-        if (!ok || span_sum > 2 * (int64_t)rowptr[M]) continue;
-        int rc = W.blocks.ensure(blk.size() * 4);
-        if (rc) return rc;
-        SX_CUDA(cudaMemcpyAsync(W.blocks.p, blk.data(), blk.size() * 4, cudaMemcpyHostToDevice, c->stream));
-        SX_CUDA(cudaStreamSynchronize(c->stream));
-        W.n = nb;
-        W.max_span = max_span;
-        W.max_block_nnz = max_block_nnz;
-    }
     return SX_OK;
 }
 
@@ -1229,8 +1165,6 @@ int upload_csr(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rowptr, cons
     drop_edge_plans(c);
     edge_screen(c, M, K, rowptr, colidx);
     if ((rc = build_window_blocks(c, M, rowptr, colidx))) return rc;
-    if (c->window_rows > 32 && (rc = build_wide_window_blocks(c, M, rowptr, colidx))) return rc;
-    if (c->window_rows <= 32) c->wide[0].n = c->wide[1].n = 0;
     c->slide_nsteps = c->slide_nchains = 0;
     if (c->slide > 0 && M > 0 && nnz > 0) {
         int32_t *steps = nullptr, *chains = nullptr;
@@ -1381,67 +1315,50 @@ void *mapped_alias(const void *host) {
     return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
 }
 
-// SX_OPT_HOST_FUSED: the zero-copy call for a matrix that takes variant 3, with C read
-// from and written to the caller's array by the SpMM kernel itself
-// (spmm_window_hostc_kernel): B staging + one kernel instead of three launches.  Returns
-// SX_OK with *done = false when the call does not qualify (the caller then takes the
-// regular zero-copy path).  The variant choice below mirrors launch_shape's.
-template <typename T, int G, bool STRICT>
-int launch_hostc(sx_ctx *c, int N, T alpha, T beta, T *dC, size_t wsmem) {
-    constexpr int E = sx::VecOf<T>::E;
-    const int nvec = (N * (int)sizeof(T) + 15) / 16;
-    const size_t tile_off = (wsmem + 15) & ~(size_t)15;
-    const size_t smem = tile_off + (size_t)nvec * E * (32 + E) * sizeof(T);
-    auto kern = sx::spmm_window_hostc_kernel<T, G, STRICT>;
-    if (smem > 48 * 1024 &&
-        std::find(c->big_smem_ok.begin(), c->big_smem_ok.end(), (const void *)kern) == c->big_smem_ok.end()) {
-        SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        c->big_smem_ok.push_back((const void *)kern);
-    }
-    kern<<<(unsigned)c->nwblocks, 32 * G, smem, c->stream>>>(
-        c->M, (const int4 *)c->wblocks.p, (const int *)c->rowptr.p, (const int *)c->colidx.p, (const T *)c->val.p,
-        (const T *)c->B.p, (uint32_t)(c->ld / E), dC, N, alpha, beta, nvec, (uint32_t)tile_off);
-    c->launches++;
-    c->last_kernel = 60000 + G * 100 + 10 + (STRICT ? 0 : 1);
-    SX_CUDA(cudaGetLastError());
-    return SX_OK;
-}
-
+// The host-facing call when nobody asked for the kernel time (kernel_ns == NULL) and the matrix
+// takes the edge-list kernel: TWO launches.  The B staging kernel reads the caller's column-major B
+// over PCIe and writes the row-major device image; the SpMM kernel (HOSTC) reads its C_in tiles from
+// the caller's C and writes its result tiles back into it, launched as a programmatic dependent of
+// the staging kernel, so its A-side prologue and its C_in reads run beside the transfer of B.
+// Returns SX_OK with *done = false when the call does not qualify.
 template <typename T>
 int spmm_host_fused(sx_ctx *c, int N, T alpha, const void *dB, T beta, void *dC, bool *done) {
-    constexpr int E = sx::VecOf<T>::E;
     *done = false;
-    if (!c->host_fused || c->tile_steps > 0 || !c->wins.empty() || c->M == 0 || c->nwblocks == 0) return SX_OK;
-    if (c->kernel != 0 && c->kernel != 3) return SX_OK;
-    if (c->M % E || c->K % E || (((uintptr_t)dB | (uintptr_t)dC) & 15)) return SX_OK;
+    if (c->host_fused == 0 || c->tile_steps > 0 || !c->wins.empty() || c->M == 0) return SX_OK;
+    if (c->kernel != 0 && c->kernel != 5) return SX_OK;
     const int nvec = (N * (int)sizeof(T) + 15) / 16;
     Shape s;
     if (!pick_shape(nvec, &s) || s.G > 16 || s.VPL != 1) return SX_OK;
     int rc;
     if ((rc = set_columns(c, N))) return rc;
-    const size_t wsmem = (size_t)c->max_span * (size_t)(c->ld / E) * 16 + ((size_t)c->max_block_nnz + 8) * (sizeof(T) + 4) + 16;
-    const size_t total = ((wsmem + 15) & ~(size_t)15) + (size_t)nvec * E * (32 + E) * sizeof(T);
-    if (wsmem > 200 * 1024 || total > 227 * 1024) return SX_OK;
-    const int cap = (int)std::max<size_t>(1, (220 * 1024) / wsmem);
-    if (c->kernel == 0 && !(cap >= 2 || (int64_t)c->nwblocks <= (int64_t)4 * c->sm_count * cap)) return SX_OK;
-    // B: column-major host -> row-major device image (the pair kernel with no C tiles)
+    const int rows = s.G >= 16 ? 32 : 256 / s.G;  // sx::EdgeShape<G>::ROWS
+    const EdgePlan *ep = nullptr;
+    if ((rc = get_edge_plan(c, s.G * 16, (int)sizeof(T), rows, &ep))) return rc;
+    if (!ep || !ep->usable) return SX_OK;
     const size_t szB = std::max<size_t>((size_t)c->K * c->ld * sizeof(T), 16);
     if ((rc = c->B.ensure(szB))) return rc;
     constexpr int VEC = 16 / (int)sizeof(T);
-    const int64_t tB = ((int64_t)c->K + 32 * VEC - 1) / (32 * VEC), tcol = (c->ld + 31) / 32;
+    const bool vec = c->K % VEC == 0 && ((uintptr_t)dB & 15) == 0;
+    const int tr = vec ? 32 * VEC : 32;
+    const int64_t tB = ((int64_t)c->K + tr - 1) / tr, tcol = (c->ld + 31) / 32;
     if (tB * tcol > 0) {
         dim3 block(32, 8), grid((unsigned)(tB * tcol));
-        sx::colmajor_to_rowmajor_pair_kernel<T, VEC><<<grid, block, 0, c->stream>>>(
-            c->K, 0, N, (const T *)dB, (const T *)dB, (T *)c->B.p, (T *)c->B.p, c->ld, (int)tcol, tB * tcol);
+        if (vec)
+            sx::colmajor_to_rowmajor_pair_kernel<T, VEC><<<grid, block, 0, c->stream>>>(
+                c->K, 0, N, (const T *)dB, (const T *)dB, (T *)c->B.p, (T *)c->B.p, c->ld, (int)tcol, tB * tcol);
+        else
+            sx::colmajor_to_rowmajor_pair_kernel<T, 1><<<grid, block, 0, c->stream>>>(
+                c->K, 0, N, (const T *)dB, (const T *)dB, (T *)c->B.p, (T *)c->B.p, c->ld, (int)tcol, tB * tcol);
         c->launches++;
         SX_CUDA(cudaGetLastError());
     }
     c->has_B = true;
     c->has_C = false;  // C never exists as a device image on this path
+    c->win_col0 = 0;
     const bool strict = c->arith == 0;
-#define SX_HOSTC(GG)                                                                             \
-    rc = strict ? launch_hostc<T, GG, true>(c, N, alpha, beta, (T *)dC, wsmem)                   \
-                : launch_hostc<T, GG, false>(c, N, alpha, beta, (T *)dC, wsmem)
+#define SX_HOSTC(GG)                                                                                                        \
+    rc = strict ? launch_edge<T, GG, true, true>(c, ep, N, alpha, (const T *)c->B.p, c->ld, beta, nullptr, nullptr, c->ld, (T *)dC) \
+                : launch_edge<T, GG, false, true>(c, ep, N, alpha, (const T *)c->B.p, c->ld, beta, nullptr, nullptr, c->ld, (T *)dC)
     switch (s.G) {
         case 2: SX_HOSTC(2); break;
         case 4: SX_HOSTC(4); break;
@@ -1607,8 +1524,7 @@ int sx_destroy(sx_ctx *c) {
     drop_edge_plans(c);
     drop_tiles(c);
     drop_windows(c);
-    for (DevBuf *b : {&c->step_ptr, &c->tcols, &c->tvals, &c->psum, &c->wide[0].blocks, &c->wide[1].blocks,
-                      &c->slide_steps, &c->slide_chains})
+    for (DevBuf *b : {&c->step_ptr, &c->tcols, &c->tvals, &c->psum, &c->slide_steps, &c->slide_chains})
         b->release();
     if (c->tune_ev0) cudaEventDestroy(c->tune_ev0);
     if (c->tune_ev1) cudaEventDestroy(c->tune_ev1);
@@ -1668,16 +1584,13 @@ int sx_set_option(sx_ctx *c, int option, int64_t value) {
             c->slide = (int)value;  // the plan is built at the next sx_upload_csr_*
             return SX_OK;
         case SX_OPT_WINDOW_ROWS:
-            if (value != 0 && value != 32 && value != 64 && value != 128)
-                return fail(SX_ERR_INVALID, "SX_OPT_WINDOW_ROWS is 0 (= 32), 32, 64 or 128");
-            c->window_rows = (int)value;  // block records are built at the next sx_upload_csr_*
-            return SX_OK;
+            return SX_OK;  // retired: accepted and ignored
         case SX_OPT_PDL:
             if (value < -1 || value > 1) return fail(SX_ERR_INVALID, "SX_OPT_PDL is -1 (auto), 0 or 1");
             c->pdl = (int)value;
             return SX_OK;
         case SX_OPT_HOST_FUSED:
-            if (value != 0 && value != 1) return fail(SX_ERR_INVALID, "SX_OPT_HOST_FUSED is 0 or 1");
+            if (value < -1 || value > 1) return fail(SX_ERR_INVALID, "SX_OPT_HOST_FUSED is -1 (auto), 0 or 1");
             c->host_fused = (int)value;
             return SX_OK;
         case SX_OPT_PREFETCH:

@@ -1,6 +1,6 @@
 // emu_kernels.cpp -- TEST INFRASTRUCTURE: runs SpMM kernels of
-// sextans_b200/csrc/spmm_kernels.cuh (variant 3 with 32/64/128-row blocks, with and without
-// the PDL code path; the host-boundary fusion spmm_window_hostc_kernel; variant 2, the
+// sextans_b200/csrc/spmm_kernels.cuh (variant 3 with and without the PDL code path; variant 5,
+// the edge-list kernel, with its multi-GPU push/acknowledge code and in its host-facing form; variant 2, the
 // TMA-staged lane-group kernel with its finalize kernel, plain, with the prefetch code path,
 // and as column-window passes; variant 1, one lane group per row with warp shuffles, plus its
 // segment kernel; variant 4, the sliding-window kernel) on the CPU
@@ -104,21 +104,12 @@ void reference(const Csr &a, const std::vector<T> &val, int N, const T *B, int64
         }
 }
 
-template <typename T, int G, int RB, bool PDL>
+template <typename T, int G, bool PDL>
 void run_window(const Csr &a, const T *val, const int *blk, int nblk, size_t smem, const T *B, uint32_t ldbv,
                 const T *Cin, T *Cout, uint32_t ldcv, T alpha, T beta, int nvec, const int *rp, const int *ci) {
-    sx_emu::launch((unsigned)nblk, RB * G, smem, [&] {
-        sx::spmm_window_kernel<T, G, true, PDL, RB>(a.M, reinterpret_cast<const int4 *>(blk), rp, ci, val, B, ldbv, Cin,
-                                                     Cout, ldcv, alpha, beta, nvec);
-    });
-}
-
-template <typename T, int G>
-void run_hostc(const Csr &a, const T *val, const int *blk, int nblk, size_t smem, uint32_t tile_off, const T *B,
-               uint32_t ldbv, T *Ch, int N, T alpha, T beta, int nvec, const int *rp, const int *ci) {
     sx_emu::launch((unsigned)nblk, 32 * G, smem, [&] {
-        sx::spmm_window_hostc_kernel<T, G, true>(a.M, reinterpret_cast<const int4 *>(blk), rp, ci, val, B, ldbv, Ch, N,
-                                                 alpha, beta, nvec, tile_off);
+        sx::spmm_window_kernel<T, G, true, PDL>(a.M, reinterpret_cast<const int4 *>(blk), rp, ci, val, B, ldbv, Cin,
+                                                     Cout, ldcv, alpha, beta, nvec);
     });
 }
 
@@ -167,34 +158,8 @@ void one_case(const char *tname, int M, int K, int N, int half_band, int per_row
         runner(dblk.p, (int)(blk.size() / 4), smem);
         check(what, Cout.p);
     };
-    window([&](const int *blk, int nb, size_t smem) { run_window<T, G, 32, false>(a, val.p, blk, nb, smem, B.p, ldv, Cin.p, Cout.p, ldv, alpha, beta, nvec, rp.p, ci.p); }, 32, "window RB=32");
-    window([&](const int *blk, int nb, size_t smem) { run_window<T, G, 32, true>(a, val.p, blk, nb, smem, B.p, ldv, Cin.p, Cout.p, ldv, alpha, beta, nvec, rp.p, ci.p); }, 32, "window RB=32 PDL");
-    if constexpr (G >= 4) {
-        window([&](const int *blk, int nb, size_t smem) { run_window<T, G, 64, false>(a, val.p, blk, nb, smem, B.p, ldv, Cin.p, Cout.p, ldv, alpha, beta, nvec, rp.p, ci.p); }, 64, "window RB=64");
-        if constexpr (G <= 8)
-            window([&](const int *blk, int nb, size_t smem) { run_window<T, G, 128, false>(a, val.p, blk, nb, smem, B.p, ldv, Cin.p, Cout.p, ldv, alpha, beta, nvec, rp.p, ci.p); }, 128, "window RB=128");
-    }
-    // host-boundary fusion: C column-major, in place
-    if (M % E == 0) {
-        std::vector<int> blk;
-        int max_span, max_nnz;
-        block_records(a, 32, &blk, &max_span, &max_nnz);
-        Aligned<int> dblk(blk.size());
-        std::copy(blk.begin(), blk.end(), dblk.p);
-        const size_t wsmem = (size_t)max_span * ldv * 16 + ((size_t)max_nnz + 8) * (sizeof(T) + 4) + 16;
-        const size_t tile_off = (wsmem + 15) & ~(size_t)15;
-        const size_t smem = tile_off + (size_t)nvec * E * (32 + E) * sizeof(T);
-        Aligned<T> Ch((size_t)M * N, 16 * sizeof(T));
-        for (int i = 0; i < M; ++i)
-            for (int n = 0; n < N; ++n) Ch.p[(size_t)M * n + i] = Cin.p[(int64_t)i * ld + n];
-        run_hostc<T, G>(a, val.p, dblk.p, (int)(blk.size() / 4), smem, (uint32_t)tile_off, B.p, ldv, Ch.p, N, alpha, beta, nvec, rp.p, ci.p);
-        for (int i = 0; i < M; ++i)
-            for (int n = 0; n < N; ++n) Cout.p[(int64_t)i * ld + n] = Ch.p[(size_t)M * n + i];
-        check("hostc (C column-major, in place)", Cout.p);
-        bool clean = true;  // nothing written past the M*N array
-        for (int i = 0; i < 16; ++i) clean = clean && Ch.p[(size_t)M * N + i] == (T)0;
-        if (!clean) { std::printf("hostc wrote past the end of C\n"); ++failures; }
-    }
+    window([&](const int *blk, int nb, size_t smem) { run_window<T, G, false>(a, val.p, blk, nb, smem, B.p, ldv, Cin.p, Cout.p, ldv, alpha, beta, nvec, rp.p, ci.p); }, 32, "window RB=32");
+    window([&](const int *blk, int nb, size_t smem) { run_window<T, G, true>(a, val.p, blk, nb, smem, B.p, ldv, Cin.p, Cout.p, ldv, alpha, beta, nvec, rp.p, ci.p); }, 32, "window RB=32 PDL");
 }
 
 template <typename T>
@@ -659,7 +624,7 @@ void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, u
                                              rp.p, dlcol.p, val.p, B.p, ldv, Cin.p, Cout.p, ldv, alpha, beta, nvec,
                                              sx::SX_EDGE_PREFETCH, with_flags ? flags.p : nullptr, flags.p + 1, flags.p + 2,
                                              flags.p + 4, with_flags ? 2 : 0, plist, (int64_t)((size_t)K * ld * sizeof(T) / 16),
-                                             pflags.p, pflags.p + 2);
+                                             pflags.p, pflags.p + 2, nullptr, 0, N, 0u, 0);
     });
     bool ok = true;
     for (int i = 0; i < M && ok; ++i) ok = same_bits(Cout.p + (int64_t)i * ld, Ref.p + (int64_t)i * ld, (size_t)N);
@@ -672,6 +637,25 @@ void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, u
     std::printf("%-34s %s M=%d K=%d N=%d G=%d budget=%d blocks=%d cols=%lld/%d: %s\n", what, tname, M, K, N, G, budget, nb,
                 (long long)total, nnz, ok ? "bit-exact" : "MISMATCH");
     if (!ok) ++failures;
+    {   // the host-facing form: C column-major (ld = M) in the caller's array, in place, tile through shared memory
+        Aligned<T> Ch((size_t)M * N, 16 * sizeof(T));
+        for (int i = 0; i < M; ++i)
+            for (int n = 0; n < N; ++n) Ch.p[(size_t)M * n + i] = Cin.p[(int64_t)i * ld + n];
+        const int tile_ld = max_rows + 1;
+        const size_t tile_off = ((size_t)std::max(max_smem, 16) + 15) & ~(size_t)15;
+        sx_emu::launch((unsigned)nb, THREADS, tile_off + (size_t)N * tile_ld * sizeof(T), [&] {
+            sx::spmm_edgelist_kernel<T, G, true, true>(reinterpret_cast<const int4 *>(dblocks.p), dcols.p, rp.p, dlcol.p, val.p,
+                                                       B.p, ldv, nullptr, nullptr, ldv, alpha, beta, nvec, sx::SX_EDGE_PREFETCH,
+                                                       nullptr, nullptr, nullptr, flags.p + 4, 0, plist, 0, nullptr, nullptr,
+                                                       Ch.p, (int64_t)M, N, (uint32_t)tile_off, tile_ld);
+        });
+        bool okh = true;
+        for (int i = 0; i < M && okh; ++i)
+            for (int n = 0; n < N && okh; ++n) okh = same_bits(&Ch.p[(size_t)M * n + i], &Ref.p[(int64_t)i * ld + n], 1);
+        for (int i = 0; i < 16; ++i) okh = okh && Ch.p[(size_t)M * N + i] == (T)0;  // nothing written past the M*N array
+        std::printf("%-34s %s M=%d K=%d N=%d G=%d: %s\n", "edge lists HOSTC (C in the caller's array)", tname, M, K, N, G, okh ? "bit-exact" : "MISMATCH");
+        if (!okh) ++failures;
+    }
     sx_free(blocks);
     sx_free(cols);
     sx_free(lcol);

@@ -139,3 +139,45 @@ def test_unstructured_matrix_is_left_to_the_other_kernels(eng):
     eng.spmm(N, np.float32(0.85), B, np.float32(-2.06), C)
     assert eng.info(sx.INFO_LAST_KERNEL) // 10000 in (1, 2)
     assert np.array_equal(bits(C), bits(oracle.spmm_csr(M, N, K, rp, ci, v, np.float32(0.85), B, np.float32(-2.06), Cin.copy())))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("M,K,N", [(4704, 4704, 16), (1000, 1000, 8), (997, 1201, 24), (70, 64, 4), (4000, 4000, 32),
+                                   (333, 777, 1), (2500, 2500, 64)])
+def test_host_facing_call_with_C_carried_by_the_kernel(eng, dtype, M, K, N):
+    """sx_spmm_* with page-locked operands and kernel_ns = NULL: B staging + ONE kernel that reads
+    C_in from and writes C to the caller's column-major array itself (SX_INFO_HOST_PATH = 2).  Same
+    bits as the oracle; with kernel_ns asked for, the three-launch path (1), same bits again."""
+    rp, ci, v = banded_csr(M, K, 150, 20, M + N, dtype)
+    B, Cin = random_dense(M, K, N, M + N, dtype)
+    ref = oracle.spmm_csr(M, N, K, rp, ci, v, dtype(0.85), B, dtype(-2.06), Cin.copy())
+    eng.upload_csr(M, K, rp, ci, v)
+    hB, hC = sx.pinned_empty(K * N, dtype), sx.pinned_empty(M * N, dtype)
+    hB[:] = B
+    for rep in range(3):
+        hC[:] = Cin
+        assert eng.spmm(N, dtype(0.85), hB, dtype(-2.06), hC, want_ns=False) is None
+        if N * np.dtype(dtype).itemsize <= 256:
+            assert eng.info(sx.INFO_HOST_PATH) == 2 and eng.info(sx.INFO_LAST_KERNEL) // 10000 == 9
+        assert np.array_equal(bits(np.asarray(hC)), bits(ref)), rep
+    hC[:] = Cin
+    ns = eng.spmm(N, dtype(0.85), hB, dtype(-2.06), hC)
+    assert ns > 0 and eng.info(sx.INFO_HOST_PATH) == 1 and np.array_equal(bits(np.asarray(hC)), bits(ref))
+    eng.set_option(sx.OPT_HOST_FUSED, 0)
+    hC[:] = Cin
+    eng.spmm(N, dtype(0.85), hB, dtype(-2.06), hC, want_ns=False)
+    assert eng.info(sx.INFO_HOST_PATH) == 1 and np.array_equal(bits(np.asarray(hC)), bits(ref))
+
+
+def test_host_facing_call_on_the_canned_run(eng, golden):
+    """nasa4704 N=16 with the host program's operands through the two-launch path: the golden SHA-256."""
+    M, K, nnz, rp, ci, v = sx.load_mtx(mtx_path("nasa4704"), np.float32)
+    run = [r for r in golden["suitesparse"]["nasa4704"]["runs"] if r["kind"] == "default" and r["N"] == 16][0]
+    B, Cin = oracle.init_dense(M, K, 16, np.float32)
+    eng.upload_csr(M, K, rp, ci, v)
+    hB, hC = sx.pinned_empty(K * 16, np.float32), sx.pinned_empty(M * 16, np.float32)
+    hB[:] = B
+    hC[:] = Cin
+    eng.spmm(16, run["alpha"], hB, run["beta"], hC, want_ns=False)
+    assert eng.info(sx.INFO_HOST_PATH) == 2
+    assert sha(np.asarray(hC)) == run["C_sha256"]

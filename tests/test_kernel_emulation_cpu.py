@@ -54,10 +54,9 @@ def test_block_level_kernels_on_the_cpu_emulation(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "EMULATION: all bit-exact" in r.stdout and "MISMATCH" not in r.stdout
-    ran = re.findall(r"^(window RB=\d+(?: PDL)?|hostc.*?) +f(?:32|64) M=.*bit-exact$", r.stdout, flags=re.M)
+    ran = re.findall(r"^(window RB=\d+(?: PDL)?) +f(?:32|64) M=.*bit-exact$", r.stdout, flags=re.M)
     kinds = {k.strip() for k in ran}
-    assert {"window RB=32", "window RB=32 PDL", "window RB=64", "window RB=128"} <= kinds
-    assert any(k.startswith("hostc") for k in kinds)
+    assert {"window RB=32", "window RB=32 PDL"} <= kinds
     staged = re.findall(r"^(staged.*?) +f(?:32|64) M=.*bit-exact$", r.stdout, flags=re.M)
     assert {"staged", "staged + prefetch path", "staged as column-window passes"} <= {k.strip() for k in staged}
     assert len(staged) >= 60
@@ -67,6 +66,8 @@ def test_block_level_kernels_on_the_cpu_emulation(tmp_path):
     assert len(slide) >= 14
     edge = re.findall(r"^edge lists \(variant 5\).*? +f(?:32|64) M=.*bit-exact$", r.stdout, flags=re.M)
     assert len(edge) >= 18 and "PLAN INVARIANT MISMATCH" not in r.stdout
+    hostc = re.findall(r"^edge lists HOSTC .*? +f(?:32|64) M=.*bit-exact$", r.stdout, flags=re.M)
+    assert len(hostc) >= 18
 
 
 @pytest.mark.skipif(CXX is None or os.environ.get("SX_EMU_ASAN") != "1",

@@ -1,8 +1,6 @@
-"""GPU tests of paths that were written without GPU time left in the round and are OFF by
-default (SX_OPT_HOST_FUSED).  They run only with SX_TEST_EXPERIMENTAL=1 in the environment;
-once they have passed on hardware they move into the regular files."""
-import os
-
+"""GPU parity of the opt-in kernel paths: variant 3 under programmatic dependent launch
+(SX_OPT_PDL = 1), the sliding-window kernel (SX_OPT_SLIDE + SX_OPT_KERNEL = 4) and the measured
+variant choice (SX_OPT_AUTOTUNE).  All of them passed on a B200 in round 2 (profiles/)."""
 import numpy as np
 import pytest
 
@@ -10,9 +8,7 @@ import oracle
 import sextans_b200 as sx
 from helpers import mtx_path, random_dense
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SX_TEST_EXPERIMENTAL") != "1",
-                                 reason="experimental paths: set SX_TEST_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture()
@@ -38,52 +34,6 @@ def banded_csr(M, K, half_band, per_row, seed, dtype):
         rp[r + 1] = rp[r] + n
     ci = np.concatenate(cols).astype(np.int32)
     return rp, ci, rng.uniform(-1, 1, ci.size).astype(dtype)
-
-
-@pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("M,K,N", [(4704, 4704, 16), (1000, 1000, 8), (998, 1200, 24), (64, 64, 4), (4000, 4000, 32)])
-def test_host_fused_equals_the_oracle_bit_for_bit(eng, dtype, M, K, N):
-    rp, ci, v = banded_csr(M, K, 150, 20, M + N, dtype)
-    B, Cin = random_dense(M, K, N, M + N, dtype)
-    ref = oracle.spmm_csr(M, N, K, rp, ci, v, dtype(0.85), B, dtype(-2.06), Cin.copy())
-    eng.upload_csr(M, K, rp, ci, v)
-    hB, hC = sx.pinned_empty(K * N, dtype), sx.pinned_empty(M * N, dtype)
-    hB[:] = B
-    # the regular zero-copy path first (kernel_ns wanted -> never fused)
-    eng.set_option(sx.OPT_HOST_FUSED, 1)
-    hC[:] = Cin
-    eng.spmm(N, dtype(0.85), hB, dtype(-2.06), hC)
-    assert eng.info(sx.INFO_HOST_PATH) == 1 and np.array_equal(bits(np.asarray(hC)), bits(ref))
-    # kernel_ns = NULL: C travels with the SpMM kernel
-    for _ in range(2):
-        hC[:] = Cin
-        assert eng.spmm(N, dtype(0.85), hB, dtype(-2.06), hC, want_ns=False) is None
-        fused = eng.info(sx.INFO_HOST_PATH) == 2
-        assert np.array_equal(bits(np.asarray(hC)), bits(ref))
-    # it must have been taken for the shapes with one vector per lane and whole 16-byte rows
-    E = 16 // np.dtype(dtype).itemsize
-    if M % E == 0 and K % E == 0 and N * np.dtype(dtype).itemsize <= 256 and eng.info(sx.INFO_LAST_KERNEL) // 10000 in (3, 6):
-        assert fused and eng.info(sx.INFO_LAST_KERNEL) // 10000 == 6
-    # option off: back to three launches
-    eng.set_option(sx.OPT_HOST_FUSED, 0)
-    hC[:] = Cin
-    eng.spmm(N, dtype(0.85), hB, dtype(-2.06), hC, want_ns=False)
-    assert eng.info(sx.INFO_HOST_PATH) == 1 and np.array_equal(bits(np.asarray(hC)), bits(ref))
-
-
-def test_host_fused_on_the_canned_run(eng, golden):
-    from helpers import sha
-    M, K, nnz, rp, ci, v = sx.load_mtx(mtx_path("nasa4704"), np.float32)
-    B, Cin = oracle.init_dense(M, K, 16, np.float32)
-    eng.upload_csr(M, K, rp, ci, v)
-    eng.set_option(sx.OPT_HOST_FUSED, 1)
-    hB, hC = sx.pinned_empty(K * 16, np.float32), sx.pinned_empty(M * 16, np.float32)
-    hB[:] = B
-    hC[:] = Cin
-    eng.spmm(16, np.float32(0.85), hB, np.float32(-2.06), hC, want_ns=False)
-    assert eng.info(sx.INFO_HOST_PATH) == 2
-    run = [r for r in golden["suitesparse"]["nasa4704"]["runs"] if r["kind"] == "default" and r["N"] == 16][0]
-    assert sha(np.asarray(hC)) == run["C_sha256"]
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
@@ -120,46 +70,6 @@ def test_pdl_window_kernel_in_a_dependent_chain(eng, dtype):
                 assert np.array_equal(bits(got), bits(ref)), rep
     finally:
         eng.set_stream(None)
-
-
-@pytest.mark.parametrize("rows", [64, 128])
-@pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("M,K,N", [(13965, 13965, 16), (1000, 1000, 8), (999, 1200, 32), (70, 64, 4), (4000, 4000, 64)])
-def test_taller_window_blocks_bit_exact(eng, rows, dtype, M, K, N):
-    """SX_OPT_WINDOW_ROWS = 64 / 128: variant 3 with taller row blocks (or its fall-back to
-    32-row blocks where a taller block does not fit) reproduces the oracle bit for bit."""
-    rp, ci, v = banded_csr(M, K, 200, 30, M + N + rows, dtype)
-    B, Cin = random_dense(M, K, N, M + N, dtype)
-    ref = oracle.spmm_csr(M, N, K, rp, ci, v, dtype(0.85), B, dtype(-2.06), Cin.copy())
-    eng.set_option(sx.OPT_KERNEL, 3)
-    eng.set_option(sx.OPT_WINDOW_ROWS, rows)
-    eng.upload_csr(M, K, rp, ci, v)
-    for rp_time in (1, 3):
-        C = Cin.copy()
-        eng.spmm(N, dtype(0.85), B, dtype(-2.06), C, rp_time)
-        assert np.array_equal(bits(C), bits(ref))
-    # and back to the validated 32-row blocks at the next upload
-    eng.set_option(sx.OPT_WINDOW_ROWS, 0)
-    eng.upload_csr(M, K, rp, ci, v)
-    C = Cin.copy()
-    eng.spmm(N, dtype(0.85), B, dtype(-2.06), C)
-    assert np.array_equal(bits(C), bits(ref))
-
-
-@pytest.mark.parametrize("rows", [64, 128])
-def test_taller_window_blocks_on_pcrystk02_golden(eng, golden, rows):
-    from helpers import sha
-    M, K, nnz, rp, ci, v = sx.load_mtx(mtx_path("pcrystk02"), np.float32)
-    eng.set_option(sx.OPT_WINDOW_ROWS, rows)
-    eng.upload_csr(M, K, rp, ci, v)
-    for run in golden["suitesparse"]["pcrystk02"]["runs"]:
-        if run["kind"] != "default":
-            continue
-        N = run["N"]
-        B, Cin = oracle.init_dense(M, K, N, np.float32)
-        C = Cin.copy()
-        eng.spmm(N, np.float32(0.85), B, np.float32(-2.06), C)
-        assert sha(C) == run["C_sha256"], (rows, N)
 
 
 @pytest.mark.parametrize("chains_per_sm", [1, 2])
