@@ -62,7 +62,7 @@ CONFIGS_NGPU = [("uniform_c4", "uniform", 128), ("powerlaw_c5", "powerlaw", 16)]
 ALPHA, BETA = float(np.float32(0.85)), float(np.float32(-2.06))   # host.cpp:29-30
 L2_BYTES = 126 * 1024 * 1024
 KERNEL_NAMES = {1: "spmm_rows_kernel", 2: "spmm_staged_kernel", 3: "spmm_window_kernel", 4: "spmm_panels_dmma_kernel",
-                5: "spmm_staged_kernel<WIN>", 7: "spmm_slide_kernel", 8: "spmm_edgelist_kernel"}
+                5: "spmm_staged_kernel<WIN>", 7: "spmm_slide_kernel", 8: "spmm_edgelist_kernel", 9: "spmm_edgelist_kernel<HOSTC>"}
 
 
 def parse():
@@ -668,6 +668,7 @@ def run_native(args):
     if world > 1:
         dist.all_reduce(perr, op=dist.ReduceOp.MAX)
 
+    kernel_name = case.kernel_name()
     # ---- e2e: host-facing call, pinned host buffers ------------------------------------------
     hB = sx.pinned_empty(Kc * N, dtype)
     hC = sx.pinned_empty(M * N, dtype)
@@ -716,7 +717,6 @@ def run_native(args):
     if sharded is not None:
         host_path = f"ShardedSpMM ({sharded.last_exchange} exchange of B)"
         sharded.close(keep_engine=True)
-    kernel_name = case.kernel_name()
     case.close()
     del hB, hC
 

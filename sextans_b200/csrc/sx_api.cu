@@ -850,19 +850,20 @@ int get_edge_plan(sx_ctx *c, int row_bytes, int elem_bytes, int rows, const Edge
     const int expect = (c->M + rows - 1) / rows;
     const int max_rows = rows;
     const int64_t nnz_target = 0;
-    // four blocks per SM if (almost) every block fits that budget uncut, else two, else one
+    // as many blocks per SM as leave every block uncut (6, 4, 3, 2 or 1); if even one block per SM
+    // needs cuts, that plan is taken with its cuts
     int nb = 0, max_smem = 0, rc = SX_OK;
     int32_t *blocks = nullptr, *cols = nullptr;
     uint16_t *lcol = nullptr;
     int64_t total = 0, ncols = 0;
-    for (int k : {4, 2, 1}) {
+    for (int k : {6, 4, 3, 2, 1}) {
         sx_free(blocks); sx_free(cols); sx_free(lcol);
         blocks = cols = nullptr;
         lcol = nullptr;
         rc = sx_plan_edge_lists(c->M, c->K, c->h_rowptr.data(), ci.data(), row_bytes, elem_bytes, max_rows, nnz_target,
                                 edge_budget(k), &nb, &blocks, &ncols, &cols, &lcol, &total, &max_smem);
         if (rc) return rc;
-        if (nb > 0 && (int64_t)nb * 4 <= (int64_t)expect * 5 + 8) break;
+        if (nb == expect) break;
     }
     if (nb > 0 && (c->kernel == 5 || total * 2 <= c->nnz)) {
         if (!(rc = p->blocks.ensure((size_t)nb * 32)) && !(rc = p->cols.ensure(std::max<size_t>((size_t)ncols * 4, 16))) &&
