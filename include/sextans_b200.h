@@ -252,14 +252,13 @@ int sx_colmajor_to_rowmajor(sx_ctx *ctx, int dtype, int64_t rows, int cols, cons
 int sx_rowmajor_to_colmajor(sx_ctx *ctx, int dtype, int64_t rows, int cols, const void *d_src,
                             int64_t ld_src, void *d_dst);
 
-/* ---- peer memory: B from another GPU's context over NVLink, no collective ---- */
+/* ---- peer memory: B to the other GPUs' contexts over NVLink, no collective ---- */
 /* One process per GPU.  For a small B the launch latency of a collective dwarfs the
- * transfer (600 KB: ~60 us through NCCL against ~10 us of SpMM), so the row-block path
- * can instead let every rank PULL the root's B image with a copy-engine peer copy,
- * ordered by 32-bit flags in peer-mapped device memory (stream memory operations: no
- * kernel, no host round trip).  Handles are CUDA IPC handles (64 bytes) to be exchanged
- * by whatever transport the host program has (torch.distributed object gather in
- * sextans_b200/rowblock.py). */
+ * transfer (600 KB: ~60 us through NCCL against ~4 us of SpMM), so the row-block path
+ * instead lets the rank that holds B PUSH its image into the other ranks' images through
+ * CUDA-IPC peer mappings (below: "exchange of B by PUSH").  Handles are CUDA IPC handles
+ * (64 bytes) to be exchanged by whatever transport the host program has
+ * (torch.distributed object gather in sextans_b200/rowblock.py). */
 #define SX_IPC_HANDLE_BYTES 64
 int sx_device_alloc(sx_ctx *ctx, size_t bytes, void **dptr);  /* zero-filled */
 int sx_device_free(sx_ctx *ctx, void *dptr);
@@ -270,13 +269,6 @@ int sx_ipc_export(sx_ctx *ctx, const void *dptr, unsigned char handle[SX_IPC_HAN
 int sx_ipc_offset(sx_ctx *ctx, const void *dptr, size_t *offset);
 int sx_ipc_import(sx_ctx *ctx, const unsigned char handle[SX_IPC_HANDLE_BYTES], void **dptr);
 int sx_ipc_close(sx_ctx *ctx, void *dptr);
-/* enqueue on the context's stream: *flag = value once everything before it has finished */
-int sx_flag_write(sx_ctx *ctx, void *flag_dptr, uint32_t value);
-/* the same for up to 16 flags with ONE small kernel (the root publishing a step to all
- * its peers: a chain of stream memory operations costs ~3 us each) */
-int sx_flag_write_many(sx_ctx *ctx, void *const *flag_dptrs, int n, uint32_t value);
-/* enqueue on the context's stream: work after it starts when (int32)(*flag - value) >= 0 */
-int sx_flag_wait(sx_ctx *ctx, void *flag_dptr, uint32_t value);
 /* ---- exchange of B by PUSH (the row-block partition's one exchange step, small B) -------------
  * The rank that holds B copies its image into every peer's image with ONE kernel (posted 16-byte
  * stores over NVLink); the peers launch nothing for it: their next SpMM waits on a flag in its own
@@ -305,17 +297,6 @@ int sx_spmm_expect_push(sx_ctx *ctx, const void *ready_flag, void *epoch_counter
  *   edge-list variant run the push as a kernel of its own right before them.) */
 int sx_spmm_fuse_push(sx_ctx *ctx, void *const *peer_images, void *const *peer_ready_flags, int npeers,
                       const void *done_flags, void *pushes_counter);
-/* enqueue a copy of a peer's row-major B image (same K, same N, same dtype: the bytes
- * sx_device_B reports) into this context's image; marks B as staged. */
-int sx_pull_B(sx_ctx *ctx, int N, const void *peer_B_image);
-/* the three steps of a pull in ONE kernel: spin until (int32)(*ready_flag - step) >= 0
- * (ready_flag in this GPU's memory), copy the peer's image over NVLink, then store step
- * into done_flag (the root's, peer-mapped).  ~5 us for 600 KB against ~13 us for
- * sx_flag_wait + sx_pull_B + sx_flag_write. */
-int sx_pull_B_fused(sx_ctx *ctx, int N, const void *peer_B_image, const void *ready_flag,
-                    void *done_flag, uint32_t step);
-
-/* ---- host-side helpers of the drop-in surface ----------------------------- */
 /* Page-locked host memory for B and C (stands in for tapa::aligned_allocator). */
 int sx_host_alloc(size_t bytes, void **ptr);
 int sx_host_free(void *ptr);

@@ -97,14 +97,9 @@ def lib():
         "sx_ipc_offset": ([vp, vp, C.POINTER(sz)], i),
         "sx_ipc_import": ([vp, C.c_char_p, C.POINTER(vp)], i),
         "sx_ipc_close": ([vp, vp], i),
-        "sx_flag_write": ([vp, vp, C.c_uint32], i),
-        "sx_flag_write_many": ([vp, C.POINTER(vp), i, C.c_uint32], i),
-        "sx_flag_wait": ([vp, vp, C.c_uint32], i),
         "sx_push_B": ([vp, vp, sz, C.POINTER(vp), C.POINTER(vp), i, vp, vp], i),
         "sx_spmm_expect_push": ([vp, vp, vp, vp], i),
         "sx_spmm_fuse_push": ([vp, C.POINTER(vp), C.POINTER(vp), i, vp, vp], i),
-        "sx_pull_B": ([vp, i, vp], i),
-        "sx_pull_B_fused": ([vp, i, vp, vp, vp, C.c_uint32], i),
         "sx_host_alloc": ([sz, C.POINTER(vp)], i),
         "sx_host_free": ([vp], i),
         "sx_partition_rows": ([i, _PI32, i, _PI32], i),
@@ -532,20 +527,6 @@ class Engine:
     def ipc_close(self, ptr):
         _check(self._L.sx_ipc_close(self._ctx, C.c_void_p(ptr)))
 
-    def flag_write(self, flag_ptr, value):
-        _check(self._L.sx_flag_write(self._ctx, C.c_void_p(flag_ptr), value & 0xFFFFFFFF))
-
-    def flag_write_many(self, flag_ptrs, value):
-        arr = (C.c_void_p * len(flag_ptrs))(*flag_ptrs)
-        _check(self._L.sx_flag_write_many(self._ctx, arr, len(flag_ptrs), value & 0xFFFFFFFF))
-
-    def flag_wait(self, flag_ptr, value):
-        _check(self._L.sx_flag_wait(self._ctx, C.c_void_p(flag_ptr), value & 0xFFFFFFFF))
-
-    def pull_B_fused(self, N, peer_image_ptr, ready_flag, done_flag, step):
-        _check(self._L.sx_pull_B_fused(self._ctx, N, C.c_void_p(peer_image_ptr), C.c_void_p(ready_flag),
-                                       C.c_void_p(done_flag), step & 0xFFFFFFFF))
-
     def push_B(self, image_ptr, nbytes, peer_image_ptrs, peer_ready_ptrs, done_flags_ptr, pushes_ptr):
         """Copy a row-major B image into every peer's (one kernel); see sx_push_B."""
         n = len(peer_image_ptrs)
@@ -564,9 +545,6 @@ class Engine:
     def expect_push(self, ready_ptr, epoch_ptr, done_ptr):
         """The next SpMM launch waits for the push into its B image and acknowledges it (sx_spmm_expect_push)."""
         _check(self._L.sx_spmm_expect_push(self._ctx, C.c_void_p(ready_ptr), C.c_void_p(epoch_ptr), C.c_void_p(done_ptr)))
-
-    def pull_B(self, N, peer_image_ptr):
-        _check(self._L.sx_pull_B(self._ctx, N, C.c_void_p(peer_image_ptr)))
 
     # -- device-resident -----------------------------------------------------------------
     def spmm_device(self, N, alpha, dB, ldb, beta, dCin, dCout, ldc):

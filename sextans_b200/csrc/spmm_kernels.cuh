@@ -319,15 +319,15 @@ constexpr int SX_WIN_INIT = 1, SX_WIN_RAW = 2;
 #ifndef SX_STAGED_UMAX
 #define SX_STAGED_UMAX 8
 #endif
-// software-pipelined batch loop (two batches of gathers in flight per lane); 0 = one batch at a time
-#ifndef SX_STAGED_PIPELINE
-#define SX_STAGED_PIPELINE 1
-#endif
+// (A software-pipelined batch loop -- the gathers of batch q+1 issued before batch q is accumulated,
+// 2*U in flight per lane -- was built and measured on a B200: at ~122 registers only two blocks fit
+// an SM and it LOST, C5 2.28 ms against 1.59 ms, C4 1.66 against 1.46; more threads with one batch
+// each keep more bytes in flight than fewer threads with two.  Removed.)
 #ifndef SX_STAGED_MINBLOCKS_F64
-#define SX_STAGED_MINBLOCKS_F64 (SX_STAGED_PIPELINE ? 2 : 3)
+#define SX_STAGED_MINBLOCKS_F64 3
 #endif
 #ifndef SX_STAGED_MINBLOCKS_F32
-#define SX_STAGED_MINBLOCKS_F32 (SX_STAGED_PIPELINE ? 2 : 4)
+#define SX_STAGED_MINBLOCKS_F32 4
 #endif
 // gathers per batch per lane for a lane-group shape (shared with the host's tile sizing)
 template <int G, int VPL> struct StagedBatch {
@@ -450,91 +450,6 @@ spmm_staged_kernel(const int nitems, const int4 *__restrict__ items, const int t
         }
     };
 
-#if SX_STAGED_PIPELINE
-    // Software-pipelined batch loop: the B-row gathers of batch q+1 are issued BEFORE batch q is
-    // accumulated, so a lane keeps up to 2*U gathers in flight all the time instead of U in bursts
-    // with a full L2/DRAM latency between them (ncu on C5: long_scoreboard was the top stall, one
-    // batch per lane group in flight at ~30 % occupancy).  Same order of additions, same results.
-    if (je > jb) {
-        constexpr int USH = U == 16 ? 4 : (U == 8 ? 3 : (U == 4 ? 2 : 1));
-        static_assert((1 << USH) == U, "U is 2, 4, 8 or 16");
-        const int bsh = tsh - USH;           // log2(batches per tile)
-        const int bmask = (1 << bsh) - 1;
-        const int nb = (len + U - 1) / U;
-        // gathers of batch q into b (dead entries of the first / last batch read B row 0 and are never used)
-        auto issue = [&](const int q, V (&b)[U][VPL]) {
-            const int e0 = q * U;
-            if ((q & bmask) == 0) mbar_wait(bar + ((q >> bsh) & 1), (uint32_t)(((q >> bsh) >> 1) & 1));
-            const int idx = e0 & ring;
-            int cc[U];
-            lds_vec<U>(scol + idx, cc);
-            const bool whole = e0 >= off && e0 + U <= len;
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const bool live = whole || (e0 + u >= off && e0 + u < len);
-                const V *brow = reinterpret_cast<const V *>(Bb + (uint64_t)(uint32_t)(live ? cc[u] : 0) * ldbb);
-#pragma unroll
-                for (int v = 0; v < VPL; ++v) {
-                    if (VPL == 1 || lg + v * G < nvec) b[u][v] = ldg_vec(brow + v * G);
-                    else vzero(b[u][v]);
-                }
-            }
-            // the batch after this one, if it lies in the same tile: ask L2 for its rows now
-            if (pf && ((q + 1) & bmask) != 0 && e0 + 2 * U <= len) {
-                int cn[U];
-                lds_vec<U>(scol + idx + U, cn);
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const unsigned char *nrow = Bb + (uint64_t)(uint32_t)cn[u] * ldbb;
-#pragma unroll
-                    for (int v = 0; v < VPL; ++v)
-                        if (VPL == 1 || lg + v * G < nvec) prefetch_l2(nrow + v * G * 16);
-                }
-            }
-        };
-        auto consume = [&](const int q, V (&b)[U][VPL]) {
-            const int e0 = q * U;
-            T av[U];
-            lds_vec<U>(sval + (e0 & ring), av);
-            if (e0 >= off && e0 + U <= len && (unsigned)(rend - e0) >= (unsigned)U) {
-                // clean: every entry belongs to the item and no row ends inside the batch
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-#pragma unroll
-                    for (int v = 0; v < VPL; ++v) vmac<STRICT>(acc[v], av[u], b[u][v]);
-            } else {
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (e0 + u >= off && e0 + u < len) {
-                        while (e0 + u == rend) close_row();  // also steps over empty rows
-#pragma unroll
-                        for (int v = 0; v < VPL; ++v) vmac<STRICT>(acc[v], av[u], b[u][v]);
-                    }
-                }
-            }
-            if (((q + 1) & bmask) == 0) {
-                // the whole group is done with this tile (its columns were read when the batch was
-                // issued, its values just now): refill its buffer with tile +2
-                const int k = q >> bsh;
-                __syncwarp(gmask);
-                if (lg == 0 && k + 2 < nt) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    load_tile(k + 2);
-                }
-            }
-        };
-        V b0[U][VPL], b1[U][VPL];
-        issue(0, b0);
-        int q = 0;
-        for (; q + 1 < nb; q += 2) {  // two batches per trip, so that the buffers never move between registers
-            issue(q + 1, b1);
-            consume(q, b0);
-            if (q + 2 < nb) issue(q + 2, b0);
-            consume(q + 1, b1);
-        }
-        if (q < nb) consume(q, b0);
-    }
-#else
     if (je > jb) {
         constexpr int USH = U == 16 ? 4 : (U == 8 ? 3 : (U == 4 ? 2 : 1));
         static_assert((1 << USH) == U, "U is 2, 4, 8 or 16");
@@ -620,7 +535,6 @@ spmm_staged_kernel(const int nitems, const int4 *__restrict__ items, const int t
             }
         }
     }
-#endif
     if (piece) {
         V *out = reinterpret_cast<V *>(partial) + (size_t)(~it.y) * ldpv + lg;
 #pragma unroll
@@ -1465,56 +1379,6 @@ spmm_panels_dmma_kernel(const int npanels, const int M, const int *__restrict__ 
                 for (int i = 0; i < 4; ++i)
                     if (n + i < N) co[i] = axpby<STRICT>(alpha, v[i], beta, ci[i]);
             }
-        }
-    }
-}
-
-// ---- peer flags -------------------------------------------------------------------
-// One launch publishes a step number to up to 16 peer-mapped flags (one per rank that
-// pulls B): 16 stream memory operations in a row cost ~3 us EACH on the root's stream,
-// one kernel with 16 stores costs ~3 us in total.
-struct FlagList { uint32_t *p[16]; };
-__global__ void flag_store_kernel(const FlagList flags, const int n, const uint32_t value) {
-    const int i = threadIdx.x;
-    if (i < n) {
-        __threadfence_system();  // everything this stream did before is visible to the peers first
-        *reinterpret_cast<volatile uint32_t *>(flags.p[i]) = value;
-    }
-}
-
-// ---- pull of the root's B image, fused: wait for the step, copy over NVLink, acknowledge --
-// One launch on the pulling rank replaces [stream wait-value, copy-engine peer copy, stream
-// write-value] (~13 us for the 600 KB B of nasa4704) by ~5 us: every block spins on the
-// LOCAL ready flag (the root stores the step number into it through its peer mapping),
-// all threads then copy 16-byte units from the root's memory with cache-volatile loads
-// (peer data may sit in L1 only, and L1 is clean at launch), and the last block to finish
-// stores the step number into the root's done flag.  The spin gives up after ~2 s and
-// raises *error instead of hanging the GPU if the root never publishes.
-__global__ void __launch_bounds__(256)
-pull_image_kernel(int4 *__restrict__ dst, const int4 *src, const int64_t n16, const uint32_t *ready,
-                  const uint32_t step, uint32_t *done_remote, unsigned int *counter, int *error) {
-    __shared__ int ok;
-    if (threadIdx.x == 0) {
-        ok = 1;
-        const long long t0 = clock64();
-        while ((int)(*reinterpret_cast<const volatile uint32_t *>(ready) - step) < 0) {
-            __nanosleep(64);
-            if (clock64() - t0 > 4000000000ll) { ok = 0; break; }
-        }
-    }
-    __syncthreads();
-    if (ok) {
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x)
-            dst[i] = __ldcv(src + i);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (!ok) *error = 1;
-        __threadfence();
-        if (atomicAdd(counter, 1u) == gridDim.x - 1) {
-            *counter = 0;
-            __threadfence_system();
-            *reinterpret_cast<volatile uint32_t *>(done_remote) = step;
         }
     }
 }

@@ -163,7 +163,7 @@ struct sx_ctx {
     int64_t ld = 0;
     bool has_B = false, has_C = false;
     DevBuf B, Cin, Cout, stage;
-    DevBuf sync_words;  // [0] block counter of pull_image_kernel, [1] its time-out flag
+    DevBuf sync_words;  // device-side counters of the push exchange (see ensure_sync_words)
     bool sync_words_zeroed = false;
 
     // options
@@ -805,8 +805,8 @@ void edge_screen(sx_ctx *c, int M, int K, const int32_t *rowptr, const int32_t *
     if (entries > 0) c->edge_cols_per_nnz = (double)distinct / (double)entries;
 }
 
-// [0] block counter of pull_image_kernel, [1] time-out flag of every flag wait, [2] block counter of
-// spmm_edgelist_kernel's acknowledgement, [3] block counter of push_image_kernel
+// [1] time-out flag of every device-side flag wait, [2] block counter of spmm_edgelist_kernel's
+// acknowledgement / publication, [3] block counter of push_image_kernel
 int ensure_sync_words(sx_ctx *c) {
     int rc = c->sync_words.ensure(16);
     if (rc) return rc;
@@ -1799,73 +1799,6 @@ int sx_ipc_close(sx_ctx *c, void *dptr) {
     return SX_OK;
 }
 
-namespace {
-// the two stream memory operations come from the driver; resolved through the runtime so
-// that the library does not link libcuda (it must still load on a machine without a GPU)
-typedef CUresult (*StreamValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
-int stream_value32(const char *name, sx_ctx *c, void *flag, uint32_t value, unsigned flags) {
-    void *fn = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    SX_CUDA(cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q));
-    if (!fn || q != cudaDriverEntryPointSuccess) return fail(SX_ERR_CUDA, "%s is not available in this driver", name);
-    const CUresult r = ((StreamValue32Fn)fn)((CUstream)c->stream, (CUdeviceptr)(uintptr_t)flag, value, flags);
-    if (r != CUDA_SUCCESS) return fail(SX_ERR_CUDA, "%s failed with CUresult %d", name, (int)r);
-    return SX_OK;
-}
-}  // namespace
-
-int sx_flag_write(sx_ctx *c, void *flag, uint32_t value) {
-    int rc = bind(c);
-    if (rc) return rc;
-    if (!flag) return fail(SX_ERR_INVALID, "null flag");
-    return stream_value32("cuStreamWriteValue32", c, flag, value, CU_STREAM_WRITE_VALUE_DEFAULT);
-}
-
-int sx_flag_write_many(sx_ctx *c, void *const *flags, int n, uint32_t value) {
-    int rc = bind(c);
-    if (rc) return rc;
-    if (n < 0 || n > 16 || (n > 0 && !flags)) return fail(SX_ERR_INVALID, "0..16 flags expected (got %d)", n);
-    if (n == 0) return SX_OK;
-    sx::FlagList fl = {};
-    for (int i = 0; i < n; ++i) {
-        if (!flags[i]) return fail(SX_ERR_INVALID, "null flag");
-        fl.p[i] = (uint32_t *)flags[i];
-    }
-    sx::flag_store_kernel<<<1, 32, 0, c->stream>>>(fl, n, value);
-    c->launches++;
-    SX_CUDA(cudaGetLastError());
-    return SX_OK;
-}
-
-int sx_flag_wait(sx_ctx *c, void *flag, uint32_t value) {
-    int rc = bind(c);
-    if (rc) return rc;
-    if (!flag) return fail(SX_ERR_INVALID, "null flag");
-    return stream_value32("cuStreamWaitValue32", c, flag, value, CU_STREAM_WAIT_VALUE_GEQ);
-}
-
-int sx_pull_B_fused(sx_ctx *c, int N, const void *peer_B_image, const void *ready_flag, void *done_flag,
-                    uint32_t step) {
-    void *mine = nullptr;
-    size_t bytes = 0;
-    int rc = sx_device_B(c, N, &mine, &bytes);
-    if (rc) return rc;
-    if (!peer_B_image || !ready_flag || !done_flag) return fail(SX_ERR_INVALID, "null argument");
-    if ((rc = c->sync_words.ensure(16))) return rc;
-    if (!c->sync_words_zeroed) {
-        SX_CUDA(cudaMemsetAsync(c->sync_words.p, 0, 16, c->stream));
-        c->sync_words_zeroed = true;
-    }
-    const int64_t n16 = (int64_t)((bytes + 15) / 16);  // images are allocated in whole 16-byte units
-    const int grid = (int)std::min<int64_t>(c->sm_count, std::max<int64_t>(1, (n16 + 255) / 256));
-    sx::pull_image_kernel<<<grid, 256, 0, c->stream>>>((int4 *)mine, (const int4 *)peer_B_image, n16,
-                                                       (const uint32_t *)ready_flag, step, (uint32_t *)done_flag,
-                                                       (unsigned int *)c->sync_words.p, (int *)c->sync_words.p + 1);
-    c->launches++;
-    SX_CUDA(cudaGetLastError());
-    return SX_OK;
-}
-
 int sx_spmm_expect_push(sx_ctx *c, const void *ready_flag, void *epoch_counter, void *done_flag) {
     if (!c) return fail(SX_ERR_INVALID, "null context");
     if (!ready_flag || !epoch_counter || !done_flag) return fail(SX_ERR_INVALID, "null flag");
@@ -1914,16 +1847,6 @@ int sx_push_B(sx_ctx *c, const void *image, size_t bytes, void *const *peer_imag
                                                        (uint32_t *)pushes_counter, (unsigned int *)c->sync_words.p);
     c->launches++;
     SX_CUDA(cudaGetLastError());
-    return SX_OK;
-}
-
-int sx_pull_B(sx_ctx *c, int N, const void *peer_B_image) {
-    void *mine = nullptr;
-    size_t bytes = 0;
-    int rc = sx_device_B(c, N, &mine, &bytes);
-    if (rc) return rc;
-    if (!peer_B_image) return fail(SX_ERR_INVALID, "null peer image");
-    if (bytes) SX_CUDA(cudaMemcpyAsync(mine, peer_B_image, bytes, cudaMemcpyDefault, c->stream));
     return SX_OK;
 }
 

@@ -252,3 +252,92 @@ class ShardedSpMM:
         for r, b in enumerate(blocks):
             self.block.put_C(out, b, N, rank=r)
         return out
+
+
+class PanelPipeline:
+    """A LARGE B at N > 1: B travels, and is consumed, in column panels.
+
+    The reference handles N in passes of 8 columns, re-streaming A once per pass
+    (``rp_time_N = rp_time * ((N + 7) >> 3)``, src/sextans.cpp:57,84,328,474), and hands the B
+    window down its PEG chain while the PEGs compute (:909-941).  The multi-GPU form: the dense
+    operands are held as P column panels of ``panel_cols`` columns (row-major images of their
+    own: a column-major K x N host array IS its panels, back to back); panel p is broadcast from
+    the rank that holds B on a communication stream (NCCL over NVLink / NVSwitch) while the SpMM
+    of panel p-1 runs on the compute stream, so a step costs about  max(sum of broadcasts, sum
+    of SpMMs) + one panel  instead of broadcast + SpMM.  Every output element is computed by the
+    same chain of operations as in one pass, so results are bitwise those of the unpanelled call.
+
+    Device-resident: ``load`` stages the operands once; ``step`` enqueues one whole SpMM
+    (broadcasts included); ``result`` brings this rank's C block back (column-major).
+    """
+
+    def __init__(self, engine, rows, K, N, dtype, device, stream, panel_cols=None, group=None, src=0):
+        import torch
+        import torch.distributed as dist
+        self.dist, self.group, self.src = dist, group, src
+        self.engine, self.rows, self.K, self.N, self.dtype = engine, rows, K, N, np.dtype(dtype)
+        self.device, self.stream = device, stream
+        s = self.dtype.itemsize
+        if panel_cols is None:
+            panel_cols = 128 // s                      # 128-byte B rows: one lane group of 8 lanes
+        self.pw = min(panel_cols, N)
+        self.P = (N + self.pw - 1) // self.pw
+        self.widths = [min(self.pw, N - p * self.pw) for p in range(self.P)]
+        self.lds = [(w + 7) // 8 * 8 for w in self.widths]
+        td = torch.float64 if self.dtype == np.float64 else torch.float32
+        self.comm = torch.cuda.Stream(device=device)
+        with torch.cuda.stream(stream):
+            self.dB = [torch.zeros(K * ld, dtype=td, device=device) for ld in self.lds]
+            self.dCin = [torch.zeros(rows * ld, dtype=td, device=device) for ld in self.lds]
+            self.dCout = [torch.zeros(rows * ld, dtype=td, device=device) for ld in self.lds]
+        self.landed = [torch.cuda.Event() for _ in range(self.P)]
+        self.freed = [torch.cuda.Event() for _ in range(self.P)]
+        self._first = True
+        self.td = td
+
+    def load(self, B_colmajor, Cin_block_colmajor):
+        """Stage the operands: B (on the source rank; None elsewhere) and this rank's C_in block."""
+        import torch
+        e, K, rows = self.engine, self.K, self.rows
+        with torch.cuda.stream(self.stream):
+            c0 = 0
+            for p, (w, ld) in enumerate(zip(self.widths, self.lds)):
+                if B_colmajor is not None:
+                    src = torch.from_numpy(np.ascontiguousarray(B_colmajor[c0 * K:(c0 + w) * K])).to(self.device)
+                    e.colmajor_to_rowmajor(K, w, src, self.dB[p], ld)
+                src = torch.from_numpy(np.ascontiguousarray(Cin_block_colmajor[c0 * rows:(c0 + w) * rows])).to(self.device)
+                e.colmajor_to_rowmajor(rows, w, src, self.dCin[p], ld)
+                c0 += w
+        self.stream.synchronize()
+
+    def step(self, alpha, beta):
+        import torch
+        for p in range(self.P):
+            with torch.cuda.stream(self.comm):
+                if self._first:
+                    self.comm.wait_stream(self.stream)              # the staging of B has finished
+                else:
+                    self.comm.wait_event(self.freed[p])             # the previous SpMM on this panel has finished reading it
+                self.dist.broadcast(self.dB[p], src=self.src, group=self.group)
+                self.landed[p].record(self.comm)
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(self.landed[p])
+                self.engine.spmm_device(self.widths[p], alpha, self.dB[p], self.lds[p], beta, self.dCin[p], self.dCout[p], self.lds[p])
+                self.freed[p].record(self.stream)
+            self._first = False
+
+    def result(self):
+        import torch
+        out = np.empty(self.rows * self.N, dtype=self.dtype)
+        c0 = 0
+        with torch.cuda.stream(self.stream):
+            parts = []
+            for p, (w, ld) in enumerate(zip(self.widths, self.lds)):
+                t = torch.empty(self.rows * w, dtype=self.td, device=self.device)
+                self.engine.rowmajor_to_colmajor(self.rows, w, self.dCout[p], ld, t)
+                parts.append((c0, w, t))
+                c0 += w
+        self.stream.synchronize()
+        for c0, w, t in parts:
+            out[c0 * self.rows:(c0 + w) * self.rows] = t.cpu().numpy()
+        return out
