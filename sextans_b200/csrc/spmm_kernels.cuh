@@ -229,6 +229,15 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 // generic-proxy writes (also a peer's, once acquired) before later async-proxy (TMA) reads
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
@@ -687,11 +696,12 @@ spmm_window_kernel(const int M, const int4 *__restrict__ blocks, const int *__re
 // dependent-launch wait every block waits until the peers have finished with the previous
 // contents of their images (done[p] >= *pushes), copies its 1/gridDim share of the B image into
 // every peer's image with plain 16-byte stores through the NVLink peer mappings (posted writes),
-// and goes on with its rows; the last block to finish stores *pushes + 1 into every peer's ready
-// flag.  No launch, no stream and no collective for the exchange on any rank.
+// and goes on with its rows; a one-warp kernel right behind it (publish_push_kernel, a programmatic
+// dependent) stores *pushes + 1 into every peer's ready flag -- the kernel boundary is the fence, so
+// no block waits for NVLink acknowledgements.  No stream and no collective for the exchange.
 // Multi-GPU, a receiving rank (ready != nullptr): B is pushed into this GPU's image by the rank
 // that holds it.  *epoch counts the SpMMs this image has served; lane 0 of every warp
-// waits until the local ready flag reaches *epoch + 1 (the push that follows the last SpMM on
+// block waits until the local ready flag reaches *epoch + 1 (the push that follows the last SpMM on
 // this image) before the window copies are issued, and the last block to finish advances *epoch
 // and stores the new value into the pusher's done flag, which lets the pusher overwrite the
 // image again.  Counters live in device memory, so a captured launch can be replayed; the
@@ -796,33 +806,34 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
     SX_TRACE_MARK(1);
     pdl_wait();
     SX_TRACE_MARK(2);
-    uint32_t step = 0;
-    if (ready != nullptr) {  // multi-GPU: the pushed B image of this step has landed
-        if ((threadIdx.x & 31) == 0) {
-            step = *reinterpret_cast<volatile uint32_t *>(epoch) + 1u;  // advanced only after every block is done
+    // ---- multi-GPU: one thread polls (plain system-scope loads, one fence when the flag is there) ----
+    uint32_t step = 0, pushed = 0;
+    if (ready != nullptr || npush > 0) {
+        if (threadIdx.x == 0) {
             const long long t0 = clock64();
-            while ((int)(ld_acquire_sys(ready) - step) < 0) {
-                __nanosleep(32);
-                if (clock64() - t0 > 4000000000ll) { atomicExch(sync_words + 1, 1u); break; }  // ~2 s: never hang the GPU on a lost peer
+            if (ready != nullptr) {  // a receiving rank: the pushed B image of this step has landed
+                step = *reinterpret_cast<volatile uint32_t *>(epoch) + 1u;  // advanced only after every block is done
+                while ((int)(ld_relaxed_sys(ready) - step) < 0) {
+                    __nanosleep(20);
+                    if (clock64() - t0 > 4000000000ll) { atomicExch(sync_words + 1, 1u); break; }  // ~2 s: never hang the GPU on a lost peer
+                }
             }
+            if (npush > 0) {         // the rank that holds B: the peers are done with the previous contents of their images
+                pushed = *reinterpret_cast<volatile uint32_t *>(pushes);  // advanced by publish_push_kernel, after this kernel
+                for (int p = 0; p < npush; ++p)
+                    while ((int)(ld_relaxed_sys(push_done + p) - pushed) < 0) {
+                        __nanosleep(20);
+                        if (clock64() - t0 > 4000000000ll) { atomicExch(sync_words + 1, 1u); break; }
+                    }
+            }
+            fence_acq_rel_sys();
         }
-        __syncwarp();
+        __syncthreads();
     }
     if (lg < nvec)
         for (int lr = rl; lr < ncols; lr += ROWS)
             cp_async_16(win + ((size_t)lr * G + lg) * 16, Bb + (size_t)(uint32_t)scols[lr] * rowbytes);
-    uint32_t pushed = 0;
-    if (npush > 0) {  // multi-GPU, this rank holds B: this block's share of the image goes to every peer
-        if ((threadIdx.x & 31) == 0) {
-            pushed = *reinterpret_cast<volatile uint32_t *>(pushes);  // advanced only after every block is done
-            const long long t0 = clock64();
-            for (int p = 0; p < npush; ++p)
-                while ((int)(ld_acquire_sys(push_done + p) - pushed) < 0) {
-                    __nanosleep(32);
-                    if (clock64() - t0 > 4000000000ll) { atomicExch(sync_words + 1, 1u); break; }
-                }
-        }
-        __syncwarp();
+    if (npush > 0) {  // this block's share of the B image goes to every peer: posted 16-byte stores over NVLink
         const int4 *src = reinterpret_cast<const int4 *>(B);
         const int64_t lo = push_n16 * blockIdx.x / gridDim.x, hi = push_n16 * (blockIdx.x + 1) / gridDim.x;
         for (int64_t i = lo + threadIdx.x; i < hi; i += THREADS) {
@@ -918,25 +929,19 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
     __syncthreads();
     SX_TRACE_MARK(5);      // every row of the block done
 #endif
-    if (ready != nullptr || npush > 0) {
-        __syncthreads();
+    if (ready != nullptr) {  // a receiving rank: tell the pusher that this rank is done with the image
+        __syncthreads();     // (its reads of the image have all returned: a plain store is enough)
         if (threadIdx.x == 0) {
-            if (npush > 0) __threadfence_system();  // this block's peer stores are performed before it counts itself done
-            else __threadfence();
+            __threadfence();
             if (atomicAdd(sync_words + 2, 1u) == gridDim.x - 1) {
                 sync_words[2] = 0;
-                if (ready != nullptr) {  // tell the pusher that this rank is done with the image
-                    *reinterpret_cast<volatile uint32_t *>(epoch) = step;
-                    st_release_sys(done_remote, step);
-                }
-                if (npush > 0) {         // tell the peers that their images hold this B
-                    __threadfence_system();
-                    for (int p = 0; p < npush; ++p) st_release_sys(push.ready[p], pushed + 1u);
-                    *reinterpret_cast<volatile uint32_t *>(pushes) = pushed + 1u;
-                }
+                *reinterpret_cast<volatile uint32_t *>(epoch) = step;
+                st_relaxed_sys(done_remote, step);
             }
         }
     }
+    // (the rank that holds B publishes the step from publish_push_kernel, launched right behind this
+    // kernel: the kernel boundary is the fence, and this kernel's tail stays free of system-scope fences)
 }
 
 // ---- variant 4 (experimental, SX_OPT_SLIDE): long banded matrices, a SLIDING B window -------
@@ -1420,6 +1425,19 @@ push_image_kernel(const int4 *__restrict__ src, const int64_t n16, const PushLis
             for (int p = 0; p < npeers; ++p) st_release_sys(peers.ready[p], t_sh + 1u);
             *reinterpret_cast<volatile uint32_t *>(pushes) = t_sh + 1u;
         }
+    }
+}
+// publication of a push that an SpMM kernel carried (spmm_edgelist_kernel, npush > 0): launched right
+// behind it as a programmatic dependent; everything that kernel stored to the peers is complete when
+// the wait returns.
+__global__ void publish_push_kernel(const PushList peers, const int npeers, uint32_t *pushes) {
+    pdl_launch_dependents();
+    pdl_wait();
+    if (threadIdx.x == 0) {
+        const uint32_t t = *reinterpret_cast<volatile uint32_t *>(pushes);
+        __threadfence_system();
+        for (int p = 0; p < npeers; ++p) st_relaxed_sys(peers.ready[p], t + 1u);
+        *reinterpret_cast<volatile uint32_t *>(pushes) = t + 1u;
     }
 }
 // the same handshake around the SpMM kernels that do not carry it themselves

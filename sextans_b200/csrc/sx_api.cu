@@ -261,8 +261,18 @@ int launch_edge(sx_ctx *c, const EdgePlan *ep, int N, T alpha, const T *dB, int6
                                c->x_done, (unsigned int *)c->sync_words.p, npush, c->p_list, push_n16, c->p_done, c->p_pushes,
                                Ch, (int64_t)c->M, N, (uint32_t)tile_off, tile_ld));
     c->x_ready = nullptr;
-    if (npush) c->p_npeers = 0;
     c->launches++;
+    if (npush) {  // the publication of the push, right behind the kernel that carried it (its programmatic dependent)
+        cudaLaunchConfig_t pc = {};
+        pc.gridDim = dim3(1);
+        pc.blockDim = dim3(32);
+        pc.stream = c->stream;
+        pc.attrs = at;
+        pc.numAttrs = c->pdl != 0 ? 1 : 0;
+        SX_CUDA(cudaLaunchKernelEx(&pc, sx::publish_push_kernel, c->p_list, npush, c->p_pushes));
+        c->launches++;
+        c->p_npeers = 0;
+    }
     c->last_edge_plan = ep;
     c->last_kernel = (HOSTC ? 90000 : 80000) + G * 100 + 10 + (STRICT ? 0 : 1);
     SX_CUDA(cudaGetLastError());

@@ -69,3 +69,6 @@ __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc) {
     std::memcpy(smem_dst, gsrc, 16);
 }
 __device__ __forceinline__ void cp_async_wait_all() {}
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t *p) { return std::atomic_ref<const uint32_t>(*p).load(); }
+__device__ __forceinline__ void st_relaxed_sys(uint32_t *p, uint32_t v) { std::atomic_ref<uint32_t>(*p).store(v); }
+__device__ __forceinline__ void fence_acq_rel_sys() {}

@@ -630,10 +630,13 @@ void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, u
     for (int i = 0; i < M && ok; ++i) ok = same_bits(Cout.p + (int64_t)i * ld, Ref.p + (int64_t)i * ld, (size_t)N);
     // the last block advanced the epoch, acknowledged to the pusher and reset the block counter; no time-out
     if (with_flags) ok = ok && flags.p[1] == 41u && flags.p[2] == 41u && flags.p[6] == 0u && flags.p[5] == 0u;
-    // both peers hold the whole B image and were told so; the push count moved on
-    if (with_flags)
+    // both peers hold the whole B image; the publication kernel behind it tells them so and moves the push count on
+    if (with_flags) {
         ok = ok && std::memcmp(peer0.p, B.p, (size_t)K * ld * sizeof(T)) == 0 && std::memcmp(peer1.p, B.p, (size_t)K * ld * sizeof(T)) == 0 &&
-             pflags.p[3] == 8u && pflags.p[4] == 8u && pflags.p[2] == 8u;
+             pflags.p[3] == 0u && pflags.p[4] == 0u && pflags.p[2] == 7u;
+        sx_emu::launch(1, 32, 0, [&] { sx::publish_push_kernel(plist, 2, pflags.p + 2); });
+        ok = ok && pflags.p[3] == 8u && pflags.p[4] == 8u && pflags.p[2] == 8u;
+    }
     std::printf("%-34s %s M=%d K=%d N=%d G=%d budget=%d blocks=%d cols=%lld/%d: %s\n", what, tname, M, K, N, G, budget, nb,
                 (long long)total, nnz, ok ? "bit-exact" : "MISMATCH");
     if (!ok) ++failures;
