@@ -806,8 +806,12 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
     SX_TRACE_MARK(1);
     pdl_wait();
     SX_TRACE_MARK(2);
-    // ---- multi-GPU: one thread polls (plain system-scope loads, one fence when the flag is there) ----
-    uint32_t step = 0, pushed = 0;
+    // ---- multi-GPU: one thread polls.  No system-scope FENCE anywhere in this kernel: on sm_100a
+    // fence.acq_rel.sys / st.release.sys are MEMBAR.ALL.SYS, measured at 4-5 us per block with peer
+    // mappings live (profiles/r02_exchange_trace_n2.txt), more than the whole SpMM.  The flag is
+    // polled with relaxed loads and read once more with ld.acquire.sys (LDG.STRONG.SYS + an L1
+    // invalidate; the B rows are then fetched with cp.async.cg, i.e. from L2, where the pushed data is).
+    uint32_t step = 0;
     if (ready != nullptr || npush > 0) {
         if (threadIdx.x == 0) {
             const long long t0 = clock64();
@@ -817,19 +821,21 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
                     __nanosleep(20);
                     if (clock64() - t0 > 4000000000ll) { atomicExch(sync_words + 1, 1u); break; }  // ~2 s: never hang the GPU on a lost peer
                 }
+                (void)ld_acquire_sys(ready);
             }
-            if (npush > 0) {         // the rank that holds B: the peers are done with the previous contents of their images
-                pushed = *reinterpret_cast<volatile uint32_t *>(pushes);  // advanced by publish_push_kernel, after this kernel
+            if (npush > 0) {         // the rank that holds B: the peers are done READING the previous contents of their
+                                     // images (nothing of theirs is read here, so relaxed loads are all it takes)
+                const uint32_t pushed = *reinterpret_cast<volatile uint32_t *>(pushes);  // advanced by publish_push_kernel
                 for (int p = 0; p < npush; ++p)
                     while ((int)(ld_relaxed_sys(push_done + p) - pushed) < 0) {
                         __nanosleep(20);
                         if (clock64() - t0 > 4000000000ll) { atomicExch(sync_words + 1, 1u); break; }
                     }
             }
-            fence_acq_rel_sys();
         }
         __syncthreads();
     }
+    SX_TRACE_MARK(4);  // multi-GPU: the step flag has been seen (else: right after the wait)
     if (lg < nvec)
         for (int lr = rl; lr < ncols; lr += ROWS)
             cp_async_16(win + ((size_t)lr * G + lg) * 16, Bb + (size_t)(uint32_t)scols[lr] * rowbytes);
@@ -925,14 +931,12 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
             for (int r = threadIdx.x & 31; r < nrows; r += 32) Ch[(size_t)cidx * ldh + row0 + r] = tile[cidx * tile_ld + r];
     }
 #ifdef SX_EDGE_TRACE
-    SX_TRACE_MARK(4);      // thread 0 done with its own rows
     __syncthreads();
     SX_TRACE_MARK(5);      // every row of the block done
 #endif
     if (ready != nullptr) {  // a receiving rank: tell the pusher that this rank is done with the image
         __syncthreads();     // (its reads of the image have all returned: a plain store is enough)
         if (threadIdx.x == 0) {
-            __threadfence();
             if (atomicAdd(sync_words + 2, 1u) == gridDim.x - 1) {
                 sync_words[2] = 0;
                 *reinterpret_cast<volatile uint32_t *>(epoch) = step;
@@ -1432,10 +1436,9 @@ push_image_kernel(const int4 *__restrict__ src, const int64_t n16, const PushLis
 // the wait returns.
 __global__ void publish_push_kernel(const PushList peers, const int npeers, uint32_t *pushes) {
     pdl_launch_dependents();
-    pdl_wait();
+    pdl_wait();  // the carrying kernel is complete: its stores, the peer stores included, have been performed
     if (threadIdx.x == 0) {
         const uint32_t t = *reinterpret_cast<volatile uint32_t *>(pushes);
-        __threadfence_system();
         for (int p = 0; p < npeers; ++p) st_relaxed_sys(peers.ready[p], t + 1u);
         *reinterpret_cast<volatile uint32_t *>(pushes) = t + 1u;
     }
