@@ -412,7 +412,9 @@ spmm_staged_kernel(const int nitems, const int4 *__restrict__ items, const int t
     const bool piece = it.y < 0;
     const int re = piece ? r + 1 : it.y;
     int rend = piece ? -1 : __ldg(rowptr + r + 1) - jal;  // in stream coordinates
-    const V *Bv = reinterpret_cast<const V *>(B) + lg;
+    // lanes beyond the dense row's last vector (lg >= nvec; one vector per lane only) gather lane 0's piece:
+    // their loads are unconditional in the clean path, and must not run past the last row of B
+    const V *Bv = reinterpret_cast<const V *>(B) + ((VPL > 1 || lg < nvec) ? lg : 0);
     // a B row's address is base + column * (row bytes): one IMAD.WIDE.U32 per gather
     const unsigned char *Bb = reinterpret_cast<const unsigned char *>(Bv);
     const uint32_t ldbb = ldbv * 16u;

@@ -867,6 +867,7 @@ int get_edge_plan(sx_ctx *c, int row_bytes, int elem_bytes, int rows, const Edge
     int32_t *blocks = nullptr, *cols = nullptr;
     uint16_t *lcol = nullptr;
     int64_t total = 0, ncols = 0;
+    int k_used = 1;
     for (int k : {6, 4, 3, 2, 1}) {
         sx_free(blocks); sx_free(cols); sx_free(lcol);
         blocks = cols = nullptr;
@@ -874,9 +875,14 @@ int get_edge_plan(sx_ctx *c, int row_bytes, int elem_bytes, int rows, const Edge
         rc = sx_plan_edge_lists(c->M, c->K, c->h_rowptr.data(), ci.data(), row_bytes, elem_bytes, max_rows, nnz_target,
                                 edge_budget(k), &nb, &blocks, &ncols, &cols, &lcol, &total, &max_smem);
         if (rc) return rc;
+        k_used = k;
         if (nb == expect) break;
     }
-    if (nb > 0 && (c->kernel == 5 || total * 2 <= c->nnz)) {
+    // A matrix of many waves needs at least four blocks per SM: a block stages its window and then
+    // computes, and with one or two fat blocks per SM nothing overlaps the two (FEM-like couplings
+    // within +-2000 nodes, M = 1e6, 97 KB windows: 3.75 ms against 0.89 ms for the staged kernel).
+    const bool fits = k_used >= 4 || (int64_t)nb <= (int64_t)4 * c->sm_count * k_used;
+    if (nb > 0 && (c->kernel == 5 || (total * 2 <= c->nnz && fits))) {
         if (!(rc = p->blocks.ensure((size_t)nb * 32)) && !(rc = p->cols.ensure(std::max<size_t>((size_t)ncols * 4, 16))) &&
             !(rc = p->lcol.ensure((size_t)c->nnz * 2 + 64))) {
             if (cudaMemcpyAsync(p->blocks.p, blocks, (size_t)nb * 32, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
