@@ -546,6 +546,18 @@ def run_config(key, wname, N, args, dev, stream, world, rank, peak):
             gather = w["nnz"] * w["N"] * s
             out["frac_gather_bound"] = round(gather / (t["ms_median"] * 1e-3) / 1e9 / peak, 4)
         case.close()
+        if wname == "powerlaw_blocked" and cargs.tiles:
+            # the same matrix through the CSR path alone, beside the dense-tile variant
+            plain = argparse.Namespace(**vars(args))
+            plain.tiles = 0
+            case = Case(w, plain, dev, stream)
+            t2 = time_steps(case.step, case.R, K, args.warmup, stream, min(args.min_region_ms, 30.0), not args.no_graph, 1, dev)
+            par2 = parity(case, w)
+            out["csr_path"] = {"ms": round(t2["ms_median"], 6), "frac": round(alg_total / (t2["ms_median"] * 1e-3) / 1e9 / peak, 4),
+                               "kernel": case.kernel_name(), "parity": par2["max_rel_err"]}
+            out["note"] = ("dense-tile FP64 tensor-core variant (SX_OPT_TILE_MIN_ROWS=4, mma.sync m8n8k4 f64) + CSR remainder; parity is "
+                           "tolerance-level (the MMA's summation order), an explicit zero times a non-finite B entry would give NaN")
+            case.close()
         out["wall_s"] = round(time.perf_counter() - t_start, 1)
         return out
     # ---- strong scaling over row blocks ----

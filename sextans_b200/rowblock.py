@@ -50,27 +50,32 @@ class RowBlock:
 
 class PushExchange:
     """B from the root rank to every other rank with NOTHING launched for the exchange on any
-    rank: the root's SpMM kernel itself copies the B image it reads into every peer's image on
-    the way to its rows (sx_spmm_fuse_push: posted 16-byte stores over NVLink through CUDA-IPC
-    peer mappings, the step published by its last block), and a peer's SpMM waits for the push in
-    its own prologue and acknowledges it from its last block (sx_spmm_expect_push).  All counters
-    are 32-bit words in device memory -- per image: ``ready`` and ``epoch`` on a peer, ``pushes``
-    and ``done[peer]`` on the root -- so captured launches can be replayed.  The multi-GPU form of
+    rank: a rank that holds B has its SpMM kernel itself copy the B image it reads into its
+    children's images on the way to its rows (sx_spmm_fuse_push: posted 16-byte stores over
+    NVLink through CUDA-IPC peer mappings, the step published by a one-warp dependent kernel),
+    and a receiving rank's SpMM waits for the push in its own prologue and acknowledges it from
+    its last block (sx_spmm_expect_push).  Ranks form a binary tree under the root (children of
+    position i: 2i+1, 2i+2), so no GPU sends more than two images per step -- an inner rank's
+    kernel waits for its parent's push and forwards the image to its own children in the same
+    launch; depth adds latency to the pipeline, not to its period.  All counters are 32-bit words
+    in device memory -- per image: ``ready`` and ``epoch`` on a receiver, ``pushes`` and
+    ``done[child]`` on a sender -- so captured launches can be replayed.  The multi-GPU form of
     the reference's chain that hands the B window from PEG to PEG (src/sextans.cpp:909-941).
 
     ``engines``: this rank's Engine objects (one, or R replicas used round-robin), each with A
     uploaded; their own B images (``Engine.device_B(N)``) are the operands.  Step i uses image
     i % R: call ``before_step(i)`` right before the SpMM of step i is enqueued on engine i % R.
     """
-    WORDS = 8192          # mailbox: ready[j] at j, epoch[j] at 256 + j, pushes[j] at 512 + j, done[j][p] at 1024 + 16 j + p
+    WORDS = 8192          # mailbox: ready[j] at j, epoch[j] at 256 + j, pushes[j] at 512 + j, done[j][c] at 1024 + 16 j + c
 
-    def __init__(self, engines, N, group=None, root=0):
+    def __init__(self, engines, N, group=None, root=0, fanout=2):
         import torch.distributed as dist
         self.engines, self.N, self.root, self.group = list(engines), N, root, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.R = len(self.engines)
-        if self.R > 256 or self.world > 16:
-            raise ValueError("PushExchange: at most 256 images and 16 ranks")
+        if self.R > 256 or self.world > 16 or not 1 <= fanout <= 15:
+            raise ValueError("PushExchange: at most 256 images, 16 ranks, fan-out 1..15")
+        self.parent, self.child_index, self.children, self.depth = self.tree(self.world, self.rank, root, fanout)
         e0 = self.engines[0]
         self.images, self.nbytes = [], None
         for e in self.engines:
@@ -82,14 +87,24 @@ class PushExchange:
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine, group=group)
         self._opened = {}                      # IPC handle -> base address in this process (a handle is opened once)
-        if self.rank == root:
-            self.peers = [r for r in range(self.world) if r != root]
-            self.peer_box = {r: self._open(everyone[r]["box"]) for r in self.peers}
-            self.peer_images = {r: [self._open(ref) for ref in everyone[r]["images"]] for r in self.peers}
-        else:
-            self.pi = [r for r in range(self.world) if r != root].index(self.rank)     # my index among the peers
-            self.root_box = self._open(everyone[root]["box"])
+        self.child_box = {r: self._open(everyone[r]["box"]) for r in self.children}
+        self.child_images = {r: [self._open(ref) for ref in everyone[r]["images"]] for r in self.children}
+        self.parent_box = None if self.parent is None else self._open(everyone[self.parent]["box"])
         dist.barrier(group=group)
+
+    @staticmethod
+    def tree(world, rank, root=0, fanout=2):
+        """(parent, index among the parent's children, children, depth) of ``rank``: the root is
+        position 0, the other ranks follow in rank order; children of position i are fanout*i+1 ..."""
+        order = [root] + [r for r in range(world) if r != root]
+        pos = order.index(rank)
+        parent = None if pos == 0 else order[(pos - 1) // fanout]
+        child_index = None if pos == 0 else (pos - 1) % fanout
+        children = [order[c] for c in range(fanout * pos + 1, fanout * pos + 1 + fanout) if c < world]
+        depth = 0
+        while pos:
+            pos, depth = (pos - 1) // fanout, depth + 1
+        return parent, child_index, children, depth
 
     def _open(self, ref):
         handle, offset = ref
@@ -98,20 +113,19 @@ class PushExchange:
         return self._opened[handle] + offset
 
     def describe(self):
-        return (f"B ({self.nbytes / 1e3:.0f} KB) pushed into every peer's image over NVLink BY rank {self.root}'s SpMM kernel itself "
-                "(its blocks copy their share of the image with posted peer stores, its last block publishes the step); the "
-                "receiving SpMM kernel waits on the step flag in its prologue and acknowledges from its last block: no launch, "
-                "no stream and no collective for the exchange on any rank")
+        return (f"B ({self.nbytes / 1e3:.0f} KB) pushed down a binary tree of ranks over NVLink BY the SpMM kernels themselves (a sender's "
+                "blocks copy their share of the image into its <= 2 children's images with posted peer stores, a one-warp dependent "
+                "kernel publishes the step; a receiver's kernel waits on the step flag in its prologue, forwards if it has children, "
+                "and acknowledges from its last block): no stream and no collective for the exchange on any rank")
 
     def before_step(self, i):
         j = i % self.R
         e = self.engines[j]
-        if self.rank == self.root:
-            if self.peers:
-                e.fuse_push([self.peer_images[r][j] for r in self.peers], [self.peer_box[r] + 4 * j for r in self.peers],
-                            self.box + 4 * (1024 + 16 * j), self.box + 4 * (512 + j))
-        else:
-            e.expect_push(self.box + 4 * j, self.box + 4 * (256 + j), self.root_box + 4 * (1024 + 16 * j + self.pi))
+        if self.parent is not None:
+            e.expect_push(self.box + 4 * j, self.box + 4 * (256 + j), self.parent_box + 4 * (1024 + 16 * j + self.child_index))
+        if self.children:
+            e.fuse_push([self.child_images[r][j] for r in self.children], [self.child_box[r] + 4 * j for r in self.children],
+                        self.box + 4 * (1024 + 16 * j), self.box + 4 * (512 + j))
 
     def close(self):
         """Collective: every rank unmaps what it imported, then frees its mailbox."""

@@ -166,14 +166,20 @@ def powerlaw_blocked_csr(M, K, nnz, seed=12345, dtype=np.float64, block=16, bloc
     planted = np.unique((rr * K + cc).ravel())
     del rr, cc
     rest = nnz - planted.size
-    ask = 1.08
+    ask = 1.10
     while True:
         key = _powerlaw_keys(rng, M, K, int(rest * ask), exponent, col_skew, perm)
-        key = np.union1d(key, planted)
+        key = np.concatenate([key, planted])
+        key.sort()
+        keep = np.empty(key.size, dtype=bool)
+        keep[0:1] = True
+        np.not_equal(key[1:], key[:-1], out=keep[1:])
+        key = key[keep]
         if key.size >= nnz:
             break
         ask *= 1.25
-    protect = np.isin(key, planted, assume_unique=True)
+    at = np.minimum(np.searchsorted(planted, key), planted.size - 1)
+    protect = planted[at] == key
     key = _trim_keys(rng, key, K, nnz, protect=protect)
     rp, ci, v = _keys_to_csr(rng, key, M, K, dtype)
     return rp, ci, v, int(planted.size)

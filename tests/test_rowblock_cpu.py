@@ -10,7 +10,7 @@ import pytest
 
 import oracle
 from helpers import random_csr, random_dense
-from sextans_b200.rowblock import RowBlock
+from sextans_b200.rowblock import PushExchange, RowBlock
 
 
 def test_row_blocks_tile_the_matrix():
@@ -28,6 +28,25 @@ def test_row_blocks_tile_the_matrix():
             assert np.array_equal(np.diff(b.rowptr), np.diff(rp[b.r0:b.r1 + 1]))
         # balance: no block exceeds the ideal share by more than the longest row
         assert max(b.nnz for b in blocks) <= rp[-1] / world + np.diff(rp).max()
+
+
+def test_push_tree_reaches_every_rank_once():
+    """The tree the push exchange sends B down: every rank but the root has exactly one parent that lists
+    it as a child at the index it acknowledges to, nobody sends to more than `fanout` ranks, depth is log."""
+    for world in (1, 2, 3, 4, 7, 8, 16):
+        for root in (0, world - 1):
+            for fanout in (1, 2, 3):
+                info = {r: PushExchange.tree(world, r, root, fanout) for r in range(world)}
+                assert info[root][0] is None and info[root][3] == 0
+                seen = []
+                for r, (parent, idx, children, depth) in info.items():
+                    assert len(children) <= fanout and r not in children
+                    seen += children
+                    if r != root:
+                        assert info[parent][2][idx] == r and depth == info[parent][3] + 1
+                assert sorted(seen) == sorted(r for r in range(world) if r != root)
+                if fanout == 2:
+                    assert max(v[3] for v in info.values()) <= max(0, (world).bit_length() - 1)
 
 
 def test_take_and_put_C_round_trip():
