@@ -692,7 +692,10 @@ spmm_window_kernel(const int M, const int4 *__restrict__ blocks, const int *__re
 // rows straight from the caller's column-major array over PCIe in its prologue -- before the
 // dependent-launch wait, i.e. while the kernel that stages B is still running -- and writes the
 // result tile back the same way, so C's two PCIe directions overlap each other, B's transfer and
-// the arithmetic, and the call is two launches (B staging, this) instead of three.
+// the arithmetic, and the call is two launches (B staging, this) instead of three.  (Letting the
+// blocks take turns on the inbound link in four groups, so that early groups' results leave while
+// late groups' C_in arrives, was measured: 74 us against 62 us per call on nasa4704 -- each turn
+// pays the PCIe read latency again.  Not kept.)
 //
 // Multi-GPU, the rank that holds B (npush > 0): the exchange is part of THIS kernel.  After the
 // dependent-launch wait every block waits until the peers have finished with the previous
