@@ -112,8 +112,7 @@ def lib():
         "sx_plan_slide": ([i, _PI32, _PI32, i, C.POINTER(i), C.POINTER(_PI32), C.POINTER(i), C.POINTER(_PI32),
                            C.POINTER(i), C.POINTER(i)], i),
         "sx_plan_edge_lists": ([i, i, _PI32, _PI32, i, i, i, i64, i, C.POINTER(i), C.POINTER(_PI32), C.POINTER(i64),
-                                C.POINTER(_PI32), C.POINTER(C.POINTER(C.c_uint16)), C.POINTER(i64),
-                                C.POINTER(C.POINTER(C.c_uint16)), C.POINTER(i64), C.POINTER(i)], i),
+                                C.POINTER(_PI32), C.POINTER(C.POINTER(C.c_uint16)), C.POINTER(i64), C.POINTER(i)], i),
         "sx_free": ([vp], None),
         "sx_sextans_invoke": ([vp, _PI32, _A8, _F4, _F8, _F8, i, i, i, i, i, i, i, _PD], i),
         "sx_sextans_last_kernel_ns": ([], C.c_double),
@@ -206,27 +205,26 @@ def plan_slide(M, rowptr, colidx, nchains):
 
 def plan_edge_lists(M, K, rowptr, colidx, row_bytes, elem_bytes, smem_budget, max_rows=32, nnz_target=0):
     """Plan of the edge-list kernel (sx_plan_edge_lists) ->
-    (blocks [nblocks, 8], cols [ncols] int32, lcol [nnz] uint16, total_cols, max_smem, srows uint16); nblocks == 0
-    if some row does not fit ``smem_budget``."""
+    (blocks [nblocks, 8], cols [ncols] int32, lcol [nnz] uint16, total_cols, max_smem); nblocks == 0 if some
+    row does not fit ``smem_budget``."""
     rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
     colidx = np.ascontiguousarray(colidx, dtype=np.int32)
-    nb, ms, tot, nc, ns = C.c_int(), C.c_int(), C.c_int64(), C.c_int64(), C.c_int64()
-    bl, co, lc, sr = _PI32(), _PI32(), C.POINTER(C.c_uint16)(), C.POINTER(C.c_uint16)()
+    nb, ms, tot, nc = C.c_int(), C.c_int(), C.c_int64(), C.c_int64()
+    bl, co, lc = _PI32(), _PI32(), C.POINTER(C.c_uint16)()
     L = lib()
     _check(L.sx_plan_edge_lists(M, K, rowptr.ctypes.data_as(_PI32), colidx.ctypes.data_as(_PI32), row_bytes, elem_bytes,
                                 max_rows, nnz_target, smem_budget, C.byref(nb), C.byref(bl), C.byref(nc), C.byref(co),
-                                C.byref(lc), C.byref(ns), C.byref(sr), C.byref(tot), C.byref(ms)))
+                                C.byref(lc), C.byref(tot), C.byref(ms)))
     if nb.value == 0:
-        return np.zeros((0, 8), np.int32), np.zeros(0, np.int32), np.zeros(0, np.uint16), 0, 0, np.zeros(0, np.uint16)
+        return np.zeros((0, 8), np.int32), np.zeros(0, np.int32), np.zeros(0, np.uint16), 0, 0
     try:
         n = int(rowptr[M])
         blocks = np.ctypeslib.as_array(bl, shape=(nb.value * 8,)).reshape(-1, 8).copy()
         cols = np.ctypeslib.as_array(co, shape=(max(nc.value, 1),))[:nc.value].copy()
         lcol = np.ctypeslib.as_array(lc, shape=(max(n, 1),))[:n].copy()
-        srows = np.ctypeslib.as_array(sr, shape=(max(ns.value, 1),))[:ns.value].copy()
     finally:
-        L.sx_free(bl), L.sx_free(co), L.sx_free(lc), L.sx_free(sr)
-    return blocks, cols, lcol, tot.value, ms.value, srows
+        L.sx_free(bl), L.sx_free(co), L.sx_free(lc)
+    return blocks, cols, lcol, tot.value, ms.value
 
 
 def split_col_windows(M, K, rowptr, colidx, window_rows):

@@ -665,9 +665,15 @@ spmm_window_kernel(const int M, const int4 *__restrict__ blocks, const int *__re
 // pcrystk02: 317 against 918): a third of the bytes through L2 and of the shared memory, so 4-6
 // blocks share an SM instead of 1-2, and the index stream of A shrinks from 4 to 2 bytes per nonzero.
 //   block record (two int4): {row_begin, nrows, nnz_begin, nnz_end} {col_begin, ncols, -, smem}
-//   shared memory:           window ncols x (G x 16 bytes) | values | local columns | column list | row pointers | super-rows
+//   shared memory:           window ncols x (G x 16 bytes) | values | local columns | column list | row pointers
 //                            (A slice from the 8-entry boundary at or below nnz_begin: whole 16-byte units)
 // One lane group per row, stored order, so strict mode is bit-identical to cpu_spmm_CSR.
+// (Round 2 also built "super-rows": the 2-3 consecutive rows of a FEM node share their column
+// sequence -- nasa4704 1.7 rows per pattern, pcrystk02 2.9 -- so one lane group walked them together
+// and read each B piece from shared memory once for all of them.  Bit-exact, and SLOWER on a B200:
+// nasa4704 4.40 against 3.68 us, pcrystk02 N=16 9.4 against 7.0 us -- a third of the lane groups
+// doing three times the work lengthens the dependent chains more than the saved LDS traffic buys.
+// Reverted; the planner and kernel are in the history.)
 // 256 threads per block (512 for 16-lane groups), i.e. ROWS = 128 / 64 / 32 / 32 lane groups for G = 2 / 4 / 8 / 16;
 // a lane group takes rows rl, rl + ROWS, ... of its block (blocks are cut by nonzeros, not by rows: a
 // small matrix becomes one block per SM with equal work, the reference's equal-length PE lists).
@@ -736,8 +742,8 @@ template <int G> struct EdgeShape {
 };
 template <typename T, int G, bool STRICT, bool HOSTC = false>
 __global__ void __launch_bounds__(EdgeShape<G>::THREADS, 2)
-spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ cols, const uint16_t *__restrict__ srows,
-                     const int *__restrict__ rowptr, const uint16_t *__restrict__ lcol, const T *__restrict__ val, const T *__restrict__ B,
+spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ cols, const int *__restrict__ rowptr,
+                     const uint16_t *__restrict__ lcol, const T *__restrict__ val, const T *__restrict__ B,
                      const uint32_t ldbv, const T *Cin, T *Cout, const uint32_t ldcv, const T alpha, const T beta,
                      const int nvec, const int flags, const uint32_t *ready, uint32_t *epoch, uint32_t *done_remote,
                      unsigned int *sync_words, const int npush, const PushList push, const int64_t push_n16,
@@ -764,7 +770,7 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
     const int lg = threadIdx.x & (G - 1);
     const int rl = threadIdx.x / G;
     const int4 b0 = __ldg(blocks + 2 * blockIdx.x), b1 = __ldg(blocks + 2 * blockIdx.x + 1);
-    const int row0 = b0.x, nrows = b0.y & 0xffff, nsr = (int)((uint32_t)b0.y >> 16), jb = b0.z, je = b0.w;
+    const int row0 = b0.x, nrows = b0.y, jb = b0.z, je = b0.w;
     const int ncols = b1.y;
     const uint32_t rowbytes = ldbv * 16u;                     // a row of the B image in global memory
     const uint32_t wbytes = (uint32_t)ncols * (G * 16u);      // a staged row: G vectors, whatever the image's leading dimension
@@ -777,23 +783,18 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
     const uint16_t *scol = reinterpret_cast<const uint16_t *>(smem_raw + wbytes + (size_t)na * sizeof(T));
     const int *scols = reinterpret_cast<const int *>(smem_raw + wbytes + (size_t)na * (sizeof(T) + 2));
     int *srp = const_cast<int *>(scols) + ncp;  // row pointers of the block's rows, nrows + 1 of them
-    const uint32_t nsp = (uint32_t)(nsr + 7) & ~7u;
-    const uint16_t *ssr = reinterpret_cast<const uint16_t *>(srp + ((nrows + 4) & ~3));  // super-row table
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     // ---- A side and hints: before the previous kernel of the stream is known to be complete ----
-    if (threadIdx.x == 0) {  // (a block of empty rows still has its super-row table: its rows get beta * C_in)
+    if (threadIdx.x == 0 && has) {
         const uint64_t pol_a = policy_evict_first();
-        mbar_expect_tx(&bar, na * (uint32_t)(sizeof(T) + 2) + ncp * 4u + nsp * 2u);
-        tma_bulk_g2s(const_cast<uint16_t *>(ssr), srows + b1.z, nsp * 2u, &bar, pol_a);
-        if (has) {
-            tma_bulk_g2s(const_cast<int *>(scols), cols + b1.x, ncp * 4u, &bar, pol_a);
-            tma_bulk_g2s(const_cast<T *>(sval), val + jal, na * (uint32_t)sizeof(T), &bar, pol_a);
-            tma_bulk_g2s(const_cast<uint16_t *>(scol), lcol + jal, na * 2u, &bar, pol_a);
-        }
+        mbar_expect_tx(&bar, na * (uint32_t)(sizeof(T) + 2) + ncp * 4u);
+        tma_bulk_g2s(const_cast<int *>(scols), cols + b1.x, ncp * 4u, &bar, pol_a);
+        tma_bulk_g2s(const_cast<T *>(sval), val + jal, na * (uint32_t)sizeof(T), &bar, pol_a);
+        tma_bulk_g2s(const_cast<uint16_t *>(scol), lcol + jal, na * 2u, &bar, pol_a);
     }
     for (int i = threadIdx.x; i <= nrows; i += THREADS) srp[i] = __ldg(rowptr + row0 + i);
     T *tile = reinterpret_cast<T *>(smem_raw + tile_off);  // HOSTC: tile[column * tile_ld + row of the block]
@@ -805,7 +806,7 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
             for (int r = threadIdx.x & 31; r < nrows; r += 32) tile[cidx * tile_ld + r] = Ch[(size_t)cidx * ldh + row0 + r];
     }
     const unsigned char *Bb = reinterpret_cast<const unsigned char *>(B) + lg * 16;
-    mbar_wait(&bar, 0);
+    if (has) mbar_wait(&bar, 0);
     if (flags & SX_EDGE_PREFETCH) {
         if (lg * 16 < (int)rowbytes && (lg & 7) == 0)  // one prefetch per 128-byte line of a row
             for (int lr = rl; lr < ncols; lr += ROWS) prefetch_l2(Bb + (size_t)(uint32_t)scols[lr] * rowbytes);
@@ -857,135 +858,82 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
             for (int p = 0; p < npush; ++p) push.dst[p][i] = v;
         }
     }
-    // A lane group takes super-rows rl, rl + ROWS, ... of the block.  A super-row is 1-3 consecutive rows
-    // with the SAME column sequence (the rows of one FEM node; sx_plan_edge_lists): the group walks them
-    // together, so a column index and the B piece it selects are read from shared memory ONCE for all
-    // of them -- the arithmetic phase is bound by the shared-memory crossbar (128 bytes of B per
-    // nonzero), and on pcrystk02 nearly every row is one of three such rows.  Every row still adds its
-    // own products in stored order, one accumulator per output column: bit-identical to cpu_spmm_CSR.
+    // a lane group takes rows rl, rl + ROWS, ... of the block; C_in of the next one is fetched while this one is computed
     const bool lane_on = lg < nvec;
     const V *Cv = reinterpret_cast<const V *>(Cin) + (size_t)row0 * ldcv + lg;
     V *Ov = reinterpret_cast<V *>(Cout) + (size_t)row0 * ldcv + lg;
+    V cin_next;
+    vzero(cin_next);
+    if (!HOSTC && lane_on && rl < nrows) cin_next = Cv[(size_t)rl * ldcv];
     cp_async_wait_all();
     __syncthreads();
     SX_TRACE_MARK(3);
     const T *sv = sval - jal;  // sv[j] = value of nonzero j
     const uint16_t *sc = scol - jal;
     const V *w = reinterpret_cast<const V *>(win) + lg;  // w[local column * G] = this lane's piece of that B row
-    auto load_cin = [&](const int r) -> V {
-        V c;
-        if (HOSTC) {
-            T *cp = reinterpret_cast<T *>(&c);
-#pragma unroll
-            for (int e = 0; e < E; ++e) cp[e] = (lg * E + e < N) ? tile[(lg * E + e) * tile_ld + r] : T(0);
-        } else {
-            c = Cv[(size_t)r * ldcv];
-        }
-        return c;
-    };
-    auto store_out = [&](const int r, const V &acc, const V &cin) {
-        const V out = vaxpby<STRICT>(alpha, acc, beta, cin);
-        if (HOSTC) {
-            const T *op = reinterpret_cast<const T *>(&out);
-#pragma unroll
-            for (int e = 0; e < E; ++e)
-                if (lg * E + e < N) tile[(lg * E + e) * tile_ld + r] = op[e];
-        } else {
-            Ov[(size_t)r * ldcv] = out;
-        }
-    };
     if (lane_on)
-        for (int si = rl; si < nsr; si += ROWS) {
-            const uint32_t ent = ssr[si];
-            const int rr = (int)(ent & 0x3fffu), cnt = (int)(ent >> 14) + 1;
+        for (int rr = rl; rr < nrows; rr += ROWS) {
             const int begin = srp[rr], end = srp[rr + 1];
-            if (cnt == 1) {
-                const V cin = load_cin(rr);
-                V acc;
-                vzero(acc);
-                // chunks of 8 nonzeros, software-pipelined: the (column, value) pairs of chunk k+1 and the
-                // eight B-row pieces of chunk k are in flight while the ordered chain of additions of chunk k runs
-                constexpr int UC = 8;
-                int j = begin;
-                if (j + UC <= end) {
-                    uint32_t c[UC];
-                    T a[UC];
+            V cin = cin_next;
+            if (HOSTC) {
+                T *cp = reinterpret_cast<T *>(&cin);
 #pragma unroll
-                    for (int u = 0; u < UC; ++u) { c[u] = sc[j + u]; a[u] = sv[j + u]; }
-                    for (;;) {
-                        V b[UC];
+                for (int e = 0; e < E; ++e) cp[e] = (lg * E + e < N) ? tile[(lg * E + e) * tile_ld + rr] : T(0);
+            } else if (rr + ROWS < nrows) {
+                cin_next = Cv[(size_t)(rr + ROWS) * ldcv];
+            }
+            V acc;
+            vzero(acc);
+            // chunks of 8 nonzeros, software-pipelined: the (column, value) pairs of chunk k+1 and the
+            // eight B-row pieces of chunk k are in flight while the ordered chain of additions of chunk k runs
+            constexpr int UC = 8;
+            int j = begin;
+            if (j + UC <= end) {
+                uint32_t c[UC];
+                T a[UC];
 #pragma unroll
-                        for (int u = 0; u < UC; ++u) b[u] = w[c[u] * G];
-                        const int jn = j + UC;
-                        const bool more = jn + UC <= end;
-                        uint32_t c2[UC];
-                        T a2[UC];
-                        const int jl = more ? jn : j;  // unconditional loads (this chunk again when there is no next one)
-#pragma unroll
-                        for (int u = 0; u < UC; ++u) { c2[u] = sc[jl + u]; a2[u] = sv[jl + u]; }
-#pragma unroll
-                        for (int u = 0; u < UC; ++u) vmac<STRICT>(acc, a[u], b[u]);
-                        j = jn;
-                        if (!more) break;
-#pragma unroll
-                        for (int u = 0; u < UC; ++u) { c[u] = c2[u]; a[u] = a2[u]; }
-                    }
-                }
-                if (j < end) {
-                    // the last, partial chunk: its loads all in flight at once (indices clamped to the row),
-                    // the additions predicated -- an explicit +0 would turn a -0 sum into +0
-                    uint32_t c[UC];
-                    T a[UC];
+                for (int u = 0; u < UC; ++u) { c[u] = sc[j + u]; a[u] = sv[j + u]; }
+                for (;;) {
                     V b[UC];
 #pragma unroll
-                    for (int u = 0; u < UC; ++u) { const int ju = min(j + u, end - 1); c[u] = sc[ju]; a[u] = sv[ju]; }
-#pragma unroll
                     for (int u = 0; u < UC; ++u) b[u] = w[c[u] * G];
+                    const int jn = j + UC;
+                    const bool more = jn + UC <= end;
+                    uint32_t c2[UC];
+                    T a2[UC];
+                    const int jl = more ? jn : j;  // unconditional loads (this chunk again when there is no next one)
 #pragma unroll
-                    for (int u = 0; u < UC; ++u)
-                        if (j + u < end) vmac<STRICT>(acc, a[u], b[u]);
+                    for (int u = 0; u < UC; ++u) { c2[u] = sc[jl + u]; a2[u] = sv[jl + u]; }
+#pragma unroll
+                    for (int u = 0; u < UC; ++u) vmac<STRICT>(acc, a[u], b[u]);
+                    j = jn;
+                    if (!more) break;
+#pragma unroll
+                    for (int u = 0; u < UC; ++u) { c[u] = c2[u]; a[u] = a2[u]; }
                 }
-                store_out(rr, acc, cin);
+            }
+            if (j < end) {
+                // the last, partial chunk: its loads all in flight at once (indices clamped to the row),
+                // the additions predicated -- an explicit +0 would turn a -0 sum into +0
+                uint32_t c[UC];
+                T a[UC];
+                V b[UC];
+#pragma unroll
+                for (int u = 0; u < UC; ++u) { const int ju = min(j + u, end - 1); c[u] = sc[ju]; a[u] = sv[ju]; }
+#pragma unroll
+                for (int u = 0; u < UC; ++u) b[u] = w[c[u] * G];
+#pragma unroll
+                for (int u = 0; u < UC; ++u)
+                    if (j + u < end) vmac<STRICT>(acc, a[u], b[u]);
+            }
+            const V out = vaxpby<STRICT>(alpha, acc, beta, cin);
+            if (HOSTC) {
+                const T *op = reinterpret_cast<const T *>(&out);
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    if (lg * E + e < N) tile[(lg * E + e) * tile_ld + rr] = op[e];
             } else {
-                // 2 or 3 rows, same columns: values of row t at sv[begin + t*len + j] (consecutive rows of equal length)
-                const int len = end - begin;
-                const bool three = cnt == 3;
-                const V cin0 = load_cin(rr), cin1 = load_cin(rr + 1);
-                V cin2;
-                vzero(cin2);
-                if (three) cin2 = load_cin(rr + 2);
-                V acc0, acc1, acc2;
-                vzero(acc0);
-                vzero(acc1);
-                vzero(acc2);
-                const T *v0 = sv + begin, *v1 = v0 + len, *v2 = three ? v1 + len : v1;  // (two rows: the third stream re-reads the second)
-                const uint16_t *cs = sc + begin;
-                constexpr int UG = 4;
-                int j = 0;
-                for (; j + UG <= len; j += UG) {
-                    uint32_t c[UG];
-                    V b[UG];
-                    T a0[UG], a1[UG], a2[UG];
-#pragma unroll
-                    for (int u = 0; u < UG; ++u) { c[u] = cs[j + u]; a0[u] = v0[j + u]; a1[u] = v1[j + u]; a2[u] = v2[j + u]; }
-#pragma unroll
-                    for (int u = 0; u < UG; ++u) b[u] = w[c[u] * G];
-#pragma unroll
-                    for (int u = 0; u < UG; ++u) {
-                        vmac<STRICT>(acc0, a0[u], b[u]);
-                        vmac<STRICT>(acc1, a1[u], b[u]);
-                        if (three) vmac<STRICT>(acc2, a2[u], b[u]);
-                    }
-                }
-                for (; j < len; ++j) {
-                    const V b = w[(uint32_t)cs[j] * G];
-                    vmac<STRICT>(acc0, v0[j], b);
-                    vmac<STRICT>(acc1, v1[j], b);
-                    if (three) vmac<STRICT>(acc2, v2[j], b);
-                }
-                store_out(rr, acc0, cin0);
-                store_out(rr + 1, acc1, cin1);
-                if (three) store_out(rr + 2, acc2, cin2);
+                Ov[(size_t)rr * ldcv] = out;
             }
         }
     if (HOSTC) {  // the result tile back into the caller's array, a warp per column again

@@ -86,8 +86,8 @@ struct EdgePlan {
     bool usable = false;  // planned, and staging a block's distinct B rows beats gathering per nonzero
     int nblocks = 0, max_smem = 0;
     int64_t total_cols = 0;
-    DevBuf blocks, cols, lcol, srows;
-    void release() { blocks.release(); cols.release(); lcol.release(); srows.release(); }
+    DevBuf blocks, cols, lcol;
+    void release() { blocks.release(); cols.release(); lcol.release(); }
 };
 
 struct sx_ctx {
@@ -255,7 +255,7 @@ int launch_edge(sx_ctx *c, const EdgePlan *ep, int N, T alpha, const T *dB, int6
     // the fused push sends the image this launch reads: K rows of ldb elements, from column 0
     const int npush = c->win_col0 == 0 ? c->p_npeers : 0;
     const int64_t push_n16 = (int64_t)((size_t)c->K * (size_t)ldb * sizeof(T) / 16);
-    SX_CUDA(cudaLaunchKernelEx(&cfg, kern, (const int4 *)ep->blocks.p, (const int *)ep->cols.p, (const uint16_t *)ep->srows.p, (const int *)c->rowptr.p,
+    SX_CUDA(cudaLaunchKernelEx(&cfg, kern, (const int4 *)ep->blocks.p, (const int *)ep->cols.p, (const int *)c->rowptr.p,
                                (const uint16_t *)ep->lcol.p, (const T *)c->val.p, dB, (uint32_t)(ldb / E), dCin, dCout,
                                (uint32_t)(ldc / E), alpha, beta, nvec, pf ? sx::SX_EDGE_PREFETCH : 0, c->x_ready, c->x_epoch,
                                c->x_done, (unsigned int *)c->sync_words.p, npush, c->p_list, push_n16, c->p_done, c->p_pushes,
@@ -865,15 +865,15 @@ int get_edge_plan(sx_ctx *c, int row_bytes, int elem_bytes, int rows, const Edge
     // needs cuts, that plan is taken with its cuts
     int nb = 0, max_smem = 0, rc = SX_OK;
     int32_t *blocks = nullptr, *cols = nullptr;
-    uint16_t *lcol = nullptr, *srows = nullptr;
-    int64_t total = 0, ncols = 0, nsrows = 0;
+    uint16_t *lcol = nullptr;
+    int64_t total = 0, ncols = 0;
     int k_used = 1;
     for (int k : {6, 4, 3, 2, 1}) {
-        sx_free(blocks); sx_free(cols); sx_free(lcol); sx_free(srows);
+        sx_free(blocks); sx_free(cols); sx_free(lcol);
         blocks = cols = nullptr;
-        lcol = srows = nullptr;
+        lcol = nullptr;
         rc = sx_plan_edge_lists(c->M, c->K, c->h_rowptr.data(), ci.data(), row_bytes, elem_bytes, max_rows, nnz_target,
-                                edge_budget(k), &nb, &blocks, &ncols, &cols, &lcol, &nsrows, &srows, &total, &max_smem);
+                                edge_budget(k), &nb, &blocks, &ncols, &cols, &lcol, &total, &max_smem);
         if (rc) return rc;
         k_used = k;
         if (nb == expect) break;
@@ -884,9 +884,8 @@ int get_edge_plan(sx_ctx *c, int row_bytes, int elem_bytes, int rows, const Edge
     const bool fits = k_used >= 4 || (int64_t)nb <= (int64_t)4 * c->sm_count * k_used;
     if (nb > 0 && (c->kernel == 5 || (total * 2 <= c->nnz && fits))) {
         if (!(rc = p->blocks.ensure((size_t)nb * 32)) && !(rc = p->cols.ensure(std::max<size_t>((size_t)ncols * 4, 16))) &&
-            !(rc = p->lcol.ensure((size_t)c->nnz * 2 + 64)) && !(rc = p->srows.ensure(std::max<size_t>((size_t)nsrows * 2, 16)))) {
+            !(rc = p->lcol.ensure((size_t)c->nnz * 2 + 64))) {
             if (cudaMemcpyAsync(p->blocks.p, blocks, (size_t)nb * 32, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
-                (nsrows > 0 && cudaMemcpyAsync(p->srows.p, srows, (size_t)nsrows * 2, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) ||
                 (ncols > 0 && cudaMemcpyAsync(p->cols.p, cols, (size_t)ncols * 4, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) ||
                 cudaMemcpyAsync(p->lcol.p, lcol, (size_t)c->nnz * 2, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
                 cudaStreamSynchronize(c->stream) != cudaSuccess)
@@ -902,7 +901,6 @@ int get_edge_plan(sx_ctx *c, int row_bytes, int elem_bytes, int rows, const Edge
     sx_free(blocks);
     sx_free(cols);
     sx_free(lcol);
-    sx_free(srows);
     return rc;
 }
 

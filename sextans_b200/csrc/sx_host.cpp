@@ -638,29 +638,26 @@ int sx_plan_slide(int M, const int32_t *rowptr, const int32_t *colidx, int nchai
 // into that compacted window; blocks are cut so that they hold about the same number of
 // nonzeros.  On FEM-type matrices the compacted window is a third of the contiguous column span
 // (nasa4704: 142 distinct columns per 32 rows against a span of 456; pcrystk02: 317 against 918).
-//   blocks  8 ints per block: {row_begin, nrows | nsuper << 16, nnz_begin, nnz_end, col_begin, ncols, super_begin, smem_bytes}
+//   blocks  8 ints per block: {row_begin, nrows, nnz_begin, nnz_end, col_begin, ncols, 0, smem_bytes}
 //   cols    the blocks' column lists, back to back, each starting at a multiple of 4 entries
 //           (16 bytes: the list travels to shared memory by TMA); pad entries repeat the last column
 //   lcol    nnz 16-bit local column indices, parallel to colidx
-//   srows   the blocks' super-row tables, back to back, each starting at a multiple of 8 entries:
-//           first row (local to the block) | (rows - 1) << 14, rows in 1..3 with identical column sequences
 // A block is closed when it holds max_rows rows, when its nonzeros reach nnz_target (0: no such
 // limit; compared at the row that brings it closest), or when the next row would not fit the
 // shared-memory budget; a single row that does not fit makes the matrix unplannable (*nblocks =
 // 0, SX_OK).  Cuts restart every 4096 rows, so the plan does not depend on the thread count.
 int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colidx, int row_bytes, int elem_bytes,
                        int max_rows, int64_t nnz_target, int smem_budget, int *nblocks_out, int32_t **blocks_out,
-                       int64_t *ncols_out, int32_t **cols_out, uint16_t **lcol_out, int64_t *nsrows_out,
-                       uint16_t **srows_out, int64_t *total_cols_out, int *max_smem_out) {
-    if (!nblocks_out || !blocks_out || !ncols_out || !cols_out || !lcol_out || !nsrows_out || !srows_out || !total_cols_out ||
-        !max_smem_out) {
+                       int64_t *ncols_out, int32_t **cols_out, uint16_t **lcol_out, int64_t *total_cols_out,
+                       int *max_smem_out) {
+    if (!nblocks_out || !blocks_out || !ncols_out || !cols_out || !lcol_out || !total_cols_out || !max_smem_out) {
         sx_internal_set_error("sx_plan_edge_lists: null output pointer");
         return SX_ERR_INVALID;
     }
     *nblocks_out = *max_smem_out = 0;
-    *ncols_out = *total_cols_out = *nsrows_out = 0;
+    *ncols_out = *total_cols_out = 0;
     *blocks_out = *cols_out = nullptr;
-    *lcol_out = *srows_out = nullptr;
+    *lcol_out = nullptr;
     if (M < 0 || K < 0 || !rowptr || (M > 0 && rowptr[M] > 0 && !colidx) || row_bytes < 16 || row_bytes % 16 ||
         (elem_bytes != 4 && elem_bytes != 8) || smem_budget < 1024 || max_rows < 1 || max_rows > 4096 || nnz_target < 0) {
         sx_internal_set_error("sx_plan_edge_lists: bad argument");
@@ -672,13 +669,11 @@ int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colid
     const int ngroups = (M + SG - 1) / SG;
     // shared memory of a block: window | values | local columns | column list | row pointers (the A
     // slice starts at the 8-entry boundary at or below nnz_begin: both streams are whole 16-byte units)
-    // (the super-row table is sized for the worst case, one entry per row)
     auto smem_of = [&](int ncols, int nrows, int jb, int je) -> int64_t {
         const int64_t na = je > jb ? (int64_t)((je - (jb & ~7) + 7) & ~7) : 0;
-        return (int64_t)ncols * row_bytes + na * elem_bytes + na * 2 + (int64_t)((ncols + 3) & ~3) * 4 + (int64_t)((nrows + 4) & ~3) * 4 +
-               (int64_t)((nrows + 7) & ~7) * 2;
+        return (int64_t)ncols * row_bytes + na * elem_bytes + na * 2 + (int64_t)((ncols + 3) & ~3) * 4 + (int64_t)((nrows + 4) & ~3) * 4;
     };
-    struct Part { std::vector<int32_t> blocks, cols; std::vector<uint16_t> srows; int64_t total = 0; int max_smem = 0; bool ok = true; };
+    struct Part { std::vector<int32_t> blocks, cols; int64_t total = 0; int max_smem = 0; bool ok = true; };
     const unsigned nt = (unsigned)std::min<int64_t>(nnz < (1 << 18) ? 1 : std::min(sxhost::host_threads(), 16u), ngroups);  // 6 bytes x K of scratch per thread
     std::vector<Part> parts(nt);
     uint16_t *lcol = (uint16_t *)std::malloc(std::max<size_t>((size_t)nnz, 8) * sizeof(uint16_t));
@@ -718,23 +713,8 @@ int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colid
                 std::sort(cols.begin(), cols.end());
                 for (int i = 0; i < ncols; ++i) local[cols[i]] = (uint16_t)i;
                 for (int32_t j = jb; j < je; ++j) lcol[j] = local[colidx[j]];
-                // super-rows: up to 3 consecutive rows with the SAME column sequence (the rows of one FEM
-                // node) are walked together by one lane group, which then fetches each B piece once for all
-                // of them.  Entry = first row (local) | (rows - 1) << 14.
-                const int sr_begin = (int)P.srows.size();
-                for (int i = rb; i < r;) {
-                    int c = 1;
-                    const int32_t b0 = rowptr[i], len = rowptr[i + 1] - b0;
-                    while (c < 3 && i + c < r && len > 0 && rowptr[i + c + 1] - rowptr[i + c] == len &&
-                           std::memcmp(colidx + b0, colidx + rowptr[i + c], (size_t)len * 4) == 0)
-                        ++c;
-                    P.srows.push_back((uint16_t)((i - rb) | ((c - 1) << 14)));
-                    i += c;
-                }
-                const int nsr = (int)P.srows.size() - sr_begin;
-                while (P.srows.size() % 8) P.srows.push_back(0);
                 const int sm = (int)smem_of(ncols, r - rb, jb, je);
-                P.blocks.insert(P.blocks.end(), {rb, (r - rb) | (nsr << 16), jb, je, (int32_t)P.cols.size(), ncols, sr_begin, sm});
+                P.blocks.insert(P.blocks.end(), {rb, r - rb, jb, je, (int32_t)P.cols.size(), ncols, 0, sm});
                 P.cols.insert(P.cols.end(), cols.begin(), cols.end());
                 while (P.cols.size() % 4) P.cols.push_back(ncols ? cols.back() : 0);
                 P.total += ncols;
@@ -743,34 +723,30 @@ int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colid
         }
     });
     bool ok = true;
-    size_t nb = 0, nc = 0, ns = 0;
-    for (const Part &P : parts) { ok = ok && P.ok; nb += P.blocks.size() / 8; nc += P.cols.size(); ns += P.srows.size(); }
-    if (!ok || nb > (size_t)INT32_MAX || nc > (size_t)INT32_MAX || ns > (size_t)INT32_MAX) {
+    size_t nb = 0, nc = 0;
+    for (const Part &P : parts) { ok = ok && P.ok; nb += P.blocks.size() / 8; nc += P.cols.size(); }
+    if (!ok || nb > (size_t)INT32_MAX || nc > (size_t)INT32_MAX) {
         std::free(lcol);
         return SX_OK;  // not plannable with this budget: the caller keeps its other kernels
     }
     int32_t *blocks = (int32_t *)std::malloc(std::max<size_t>(nb, 1) * 8 * sizeof(int32_t));
     int32_t *cols = (int32_t *)std::malloc(std::max<size_t>(nc, 4) * sizeof(int32_t));
-    uint16_t *srows = (uint16_t *)std::malloc(std::max<size_t>(ns, 8) * sizeof(uint16_t));
-    if (!blocks || !cols || !srows) {
-        std::free(blocks); std::free(cols); std::free(lcol); std::free(srows);
+    if (!blocks || !cols) {
+        std::free(blocks); std::free(cols); std::free(lcol);
         sx_internal_set_error("sx_plan_edge_lists: out of host memory");
         return SX_ERR_NOMEM;
     }
-    size_t bo = 0, co = 0, so = 0;
+    size_t bo = 0, co = 0;
     int64_t total = 0;
     int max_smem = 0;
     for (const Part &P : parts) {
         for (size_t i = 0; i < P.blocks.size(); i += 8) {
             std::copy(P.blocks.begin() + i, P.blocks.begin() + i + 8, blocks + (bo + i));
-            blocks[bo + i + 4] += (int32_t)co;  // column-list and super-row offsets become global
-            blocks[bo + i + 6] += (int32_t)so;
+            blocks[bo + i + 4] += (int32_t)co;  // column-list offsets become global
         }
         std::copy(P.cols.begin(), P.cols.end(), cols + co);
-        std::copy(P.srows.begin(), P.srows.end(), srows + so);
         bo += P.blocks.size();
         co += P.cols.size();
-        so += P.srows.size();
         total += P.total;
         max_smem = std::max(max_smem, P.max_smem);
     }
@@ -779,8 +755,6 @@ int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colid
     *ncols_out = (int64_t)nc;
     *cols_out = cols;
     *lcol_out = lcol;
-    *nsrows_out = (int64_t)ns;
-    *srows_out = srows;
     *total_cols_out = total;
     *max_smem_out = max_smem;
     return SX_OK;

@@ -24,7 +24,7 @@ int sx_plan_slide(int M, const int32_t *rowptr, const int32_t *colidx, int nchai
                   int *nchains, int32_t **chains, int *ring_rows, int *max_step_entries);
 int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colidx, int row_bytes, int elem_bytes,
                        int max_rows, int64_t nnz_target, int smem_budget, int *nblocks, int32_t **blocks, int64_t *ncols,
-                       int32_t **cols, uint16_t **lcol, int64_t *nsrows, uint16_t **srows, int64_t *total_cols, int *max_smem);
+                       int32_t **cols, uint16_t **lcol, int64_t *total_cols, int *max_smem);
 void sx_free(void *);
 }
 
@@ -546,15 +546,6 @@ void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, u
     constexpr int E = 16 / (int)sizeof(T);
     const int M = a.M, K = a.K;
     std::mt19937 rng(seed * 13 + 5);
-    if (seed % 3 != 0) {  // FEM-like: rows 3i, 3i+1, 3i+2 (sometimes only two of them) share the column sequence of row 3i
-        Csr f{M, K, std::vector<int>(M + 1, 0), {}};
-        for (int r = 0; r < M; ++r) {
-            const int src = (r % 3 == 2 && (r / 3) % 4 == 1) ? r : r - r % 3;
-            f.ci.insert(f.ci.end(), a.ci.begin() + a.rp[src], a.ci.begin() + a.rp[src + 1]);
-            f.rp[r + 1] = (int)f.ci.size();
-        }
-        a = f;
-    }
     if (shuffle_rows)  // stored order inside a row is arbitrary, and a column may repeat
         for (int r = 0; r < M; ++r) {
             std::shuffle(a.ci.begin() + a.rp[r], a.ci.begin() + a.rp[r + 1], rng);
@@ -575,13 +566,13 @@ void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, u
     constexpr int ROWS = sx::EdgeShape<G>::ROWS, THREADS = sx::EdgeShape<G>::THREADS;
     int nb = 0, max_smem = 0;
     int32_t *blocks = nullptr, *cols = nullptr;
-    uint16_t *lcol = nullptr, *srows = nullptr;
-    int64_t total = 0, ncols = 0, nsrows = 0;
+    uint16_t *lcol = nullptr;
+    int64_t total = 0, ncols = 0;
     // every other case cuts by nonzeros with up to 4 sweeps of the lane groups (what sx_api.cu does for small matrices)
     const int max_rows = (seed & 1) ? 4 * ROWS : ROWS;
     const int64_t nnz_target = (seed & 1) ? std::max(8, a.rp[M] / 5) : 0;
     if (sx_plan_edge_lists(M, K, a.rp.data(), a.ci.data(), G * 16, (int)sizeof(T), max_rows, nnz_target, budget, &nb, &blocks,
-                           &ncols, &cols, &lcol, &nsrows, &srows, &total, &max_smem) != 0) {
+                           &ncols, &cols, &lcol, &total, &max_smem) != 0) {
         std::printf("edge lists: plan FAILED\n");
         ++failures;
         return;
@@ -594,8 +585,7 @@ void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, u
     }
     // device copies at exactly the product's sizes and pads (sx_api.cu: get_edge_plan, upload_csr)
     Aligned<int> dblocks((size_t)nb * 8), dcols((size_t)std::max<int64_t>(ncols, 4));
-    Aligned<uint16_t> dlcol((size_t)nnz, 64), dsrows((size_t)std::max<int64_t>(nsrows, 8));
-    std::copy(srows, srows + nsrows, dsrows.p);
+    Aligned<uint16_t> dlcol((size_t)nnz, 64);
     std::copy(blocks, blocks + (size_t)nb * 8, dblocks.p);
     std::copy(cols, cols + ncols, dcols.p);
     std::copy(lcol, lcol + nnz, dlcol.p);
@@ -604,16 +594,9 @@ void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, u
     int next_row = 0;
     for (int b = 0; b < nb && plan_ok; ++b) {
         const int32_t *r = blocks + (size_t)b * 8;
-        const int nr = r[1] & 0xffff, nsr = (int)((uint32_t)r[1] >> 16);
-        plan_ok = r[0] == next_row && nr >= 1 && nr <= max_rows && r[2] == a.rp[r[0]] && r[3] == a.rp[r[0] + nr] &&
-                  r[4] % 4 == 0 && r[6] % 8 == 0 && r[7] <= budget && r[7] <= max_smem;
-        next_row = r[0] + nr;
-        int covered = 0;  // the super-rows cover the block's rows in order
-        for (int q = 0; q < nsr && plan_ok; ++q) {
-            plan_ok = (srows[r[6] + q] & 0x3fff) == covered;
-            covered += (srows[r[6] + q] >> 14) + 1;
-        }
-        plan_ok = plan_ok && covered == nr;
+        plan_ok = r[0] == next_row && r[1] >= 1 && r[1] <= max_rows && r[2] == a.rp[r[0]] && r[3] == a.rp[r[0] + r[1]] &&
+                  r[4] % 4 == 0 && r[7] <= budget && r[7] <= max_smem;
+        next_row = r[0] + r[1];
         for (int i = 1; i < r[5] && plan_ok; ++i) plan_ok = cols[r[4] + i] > cols[r[4] + i - 1];
         for (int j = r[2]; j < r[3] && plan_ok; ++j) plan_ok = lcol[j] < r[5] && cols[r[4] + lcol[j]] == a.ci[j];
     }
@@ -637,7 +620,7 @@ void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, u
     plist.ready[0] = pflags.p + 3;
     plist.ready[1] = pflags.p + 4;
     sx_emu::launch((unsigned)nb, THREADS, (size_t)std::max(max_smem, 16), [&] {
-        sx::spmm_edgelist_kernel<T, G, true>(reinterpret_cast<const int4 *>(dblocks.p), dcols.p, dsrows.p,
+        sx::spmm_edgelist_kernel<T, G, true>(reinterpret_cast<const int4 *>(dblocks.p), dcols.p,
                                              rp.p, dlcol.p, val.p, B.p, ldv, Cin.p, Cout.p, ldv, alpha, beta, nvec,
                                              sx::SX_EDGE_PREFETCH, with_flags ? flags.p : nullptr, flags.p + 1, flags.p + 2,
                                              flags.p + 4, with_flags ? 2 : 0, plist, (int64_t)((size_t)K * ld * sizeof(T) / 16),
@@ -664,7 +647,7 @@ void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, u
         const int tile_ld = max_rows + 1;
         const size_t tile_off = ((size_t)std::max(max_smem, 16) + 15) & ~(size_t)15;
         sx_emu::launch((unsigned)nb, THREADS, tile_off + (size_t)N * tile_ld * sizeof(T), [&] {
-            sx::spmm_edgelist_kernel<T, G, true, true>(reinterpret_cast<const int4 *>(dblocks.p), dcols.p, dsrows.p, rp.p, dlcol.p, val.p,
+            sx::spmm_edgelist_kernel<T, G, true, true>(reinterpret_cast<const int4 *>(dblocks.p), dcols.p, rp.p, dlcol.p, val.p,
                                                        B.p, ldv, nullptr, nullptr, ldv, alpha, beta, nvec, sx::SX_EDGE_PREFETCH,
                                                        nullptr, nullptr, nullptr, flags.p + 4, 0, plist, 0, nullptr, nullptr,
                                                        Ch.p, (int64_t)M, N, (uint32_t)tile_off, tile_ld);
@@ -679,7 +662,6 @@ void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, u
     sx_free(blocks);
     sx_free(cols);
     sx_free(lcol);
-    sx_free(srows);
 }
 
 template <typename T>

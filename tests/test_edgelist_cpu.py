@@ -9,25 +9,12 @@ import sextans_b200 as sx
 from helpers import mtx_path, random_csr
 
 
-def check_plan(M, K, rp, ci, row_bytes, elem, budget, blocks, cols, lcol, total, max_smem, srows, rows=32, target=0):
-    assert blocks.shape[1] == 8 and lcol.size == ci.size and cols.size % 4 == 0 and srows.size % 8 == 0
+def check_plan(M, K, rp, ci, row_bytes, elem, budget, blocks, cols, lcol, total, max_smem, rows=32, target=0):
+    assert blocks.shape[1] == 8 and lcol.size == ci.size and cols.size % 4 == 0
     nxt = 0
     tot = 0
     for b in blocks:
-        r0, packed, jb, je, c0, ncols, s0, smem = (int(x) for x in b)
-        nr, nsr = packed & 0xffff, packed >> 16
-        # super-rows: consecutive runs of 1-3 rows with identical column sequences, covering the block in order
-        assert s0 % 8 == 0
-        at = 0
-        for e in srows[s0:s0 + nsr]:
-            first, cnt = int(e) & 0x3fff, (int(e) >> 14) + 1
-            assert first == at and 1 <= cnt <= 3
-            for t in range(1, cnt):
-                a0, a1 = rp[r0 + first], rp[r0 + first + 1]
-                b0, b1 = rp[r0 + first + t], rp[r0 + first + t + 1]
-                assert a1 > a0 and a1 - a0 == b1 - b0 and np.array_equal(ci[a0:a1], ci[b0:b1])
-            at += cnt
-        assert at == nr
+        r0, nr, jb, je, c0, ncols, _, smem = (int(x) for x in b)
         assert r0 == nxt and 1 <= nr <= rows and (r0 // 4096) == ((r0 + nr - 1) // 4096)
         if target and nr > 1:                 # never further from the target than without its last row
             assert (je - jb) - target <= target - (rp[r0 + nr - 1] - jb)
@@ -38,7 +25,7 @@ def check_plan(M, K, rp, ci, row_bytes, elem, budget, blocks, cols, lcol, total,
         pad = cols[c0 + ncols:c0 + ((ncols + 3) & ~3)]
         assert ncols == 0 or np.all(pad == mine[-1])                 # pad entries name a real column
         na = ((je - (jb & ~7) + 7) & ~7) if je > jb else 0
-        assert smem == ncols * row_bytes + na * (elem + 2) + ((ncols + 3) & ~3) * 4 + ((nr + 4) & ~3) * 4 + ((nr + 7) & ~7) * 2
+        assert smem == ncols * row_bytes + na * (elem + 2) + ((ncols + 3) & ~3) * 4 + ((nr + 4) & ~3) * 4
         assert smem <= budget and smem <= max_smem
         nxt = r0 + nr
         tot += ncols
@@ -49,7 +36,7 @@ def check_plan(M, K, rp, ci, row_bytes, elem, budget, blocks, cols, lcol, total,
 def test_suitesparse_plans(name, row_bytes, elem, distinct):
     """BASELINE configs[1] (N=16 fp64) and configs[2] (N=16 fp32) at four blocks per SM."""
     M, K, nnz, rp, ci, v, _ = oracle.load_mtx(mtx_path(name), np.float32)
-    blocks, cols, lcol, total, max_smem, srows = sx.plan_edge_lists(M, K, rp, ci, row_bytes, elem, 56192)
+    blocks, runs, lcol, total, max_smem = sx.plan_edge_lists(M, K, rp, ci, row_bytes, elem, 56192)
     assert len(blocks) == sum((min(M, g + 4096) - g + 31) // 32 for g in range(0, M, 4096)) and total <= distinct + 400   # no block had to be cut
     # cut by nonzeros into ~148 blocks (what the engine does with a small matrix on 148 SMs)
     target = -(-nnz // 148)
@@ -57,9 +44,7 @@ def test_suitesparse_plans(name, row_bytes, elem, distinct):
     check_plan(M, K, rp, ci, row_bytes, elem, 115000, *bal, rows=128, target=target)
     sizes = bal[0][:, 3] - bal[0][:, 2]
     assert 140 <= len(sizes) <= 160 and sizes.max() <= 1.25 * target
-    check_plan(M, K, rp, ci, row_bytes, elem, 56192, blocks, cols, lcol, total, max_smem, srows)
-    nsr = int((blocks[:, 1] >> 16).sum())
-    assert nsr <= (2900 if name == "nasa4704" else 5200)          # rows of a FEM node share their columns: 4704 -> ~2700, 13965 -> ~4800 super-rows
+    check_plan(M, K, rp, ci, row_bytes, elem, 56192, blocks, runs, lcol, total, max_smem)
     assert total * 2 <= nnz                                          # a staged B row serves >= 2 nonzeros
     # a budget that forces cuts
     small = sx.plan_edge_lists(M, K, rp, ci, row_bytes, elem, 12000)
@@ -89,10 +74,10 @@ def test_random_matrices_with_empty_rows_and_unsorted_columns(seed):
 
 def test_degenerate_inputs():
     rp = np.zeros(1, np.int32)
-    b, r, l, t, m, _ = sx.plan_edge_lists(0, 5, rp, np.zeros(0, np.int32), 64, 4, 4096)
+    b, r, l, t, m = sx.plan_edge_lists(0, 5, rp, np.zeros(0, np.int32), 64, 4, 4096)
     assert len(b) == 0 and t == 0
     rp = np.zeros(41, np.int32)              # 40 empty rows: blocks without runs
-    b, r, l, t, m, _ = sx.plan_edge_lists(40, 5, rp, np.zeros(0, np.int32), 64, 4, 4096)
+    b, r, l, t, m = sx.plan_edge_lists(40, 5, rp, np.zeros(0, np.int32), 64, 4, 4096)
     assert len(b) == 2 and t == 0 and b[:, 5].sum() == 0
     with pytest.raises(sx.SextansError):
         sx.plan_edge_lists(4, 5, np.zeros(5, np.int32), np.zeros(0, np.int32), 60, 4, 4096)   # row_bytes % 16
