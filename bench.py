@@ -86,6 +86,9 @@ def parse():
     p.add_argument("--slide", type=int, default=0, help="SX_OPT_SLIDE: chains per SM of the sliding-window kernel; use with --kernel 4")
     p.add_argument("--pdl", type=int, default=-1, choices=[-1, 0, 1], help="SX_OPT_PDL: programmatic dependent launch (-1 auto: on for the edge-list kernel)")
     p.add_argument("--prefetch", type=int, default=-1, choices=[-1, 0, 1], help="SX_OPT_PREFETCH: L2 prefetch hints (-1 auto)")
+    p.add_argument("--batch", type=int, default=20, help="also time sx_spmm_device_batch_* with this many (B, C) pairs per launch on the headline workload (0/1: skip)")
+    p.add_argument("--host-groups", type=int, default=0, help="SX_OPT_HOST_GROUPS: column groups of the fused host-facing call (0 auto, 1 no pipeline)")
+    p.add_argument("--panel-cols", type=int, default=0, help="SX_OPT_PANEL_COLS: columns of B and C per pass (0 auto)")
     p.add_argument("--host-fused", type=int, default=-1, choices=[-1, 0, 1], help="SX_OPT_HOST_FUSED: e2e calls let the SpMM kernel carry C across PCIe (-1 auto: on)")
     p.add_argument("--ref-threads", type=int, default=-1, help="--impl reference: threads of the CPU path (-1 = all cores, row-parallel; 1 = as the reference runs it)")
     p.add_argument("--peer-bytes", type=int, default=8 << 20, help="N>1: B images up to this size travel through peer memory instead of NCCL")
@@ -353,6 +356,8 @@ class Case:
             e.set_option(sx.OPT_COL_WINDOW_ROWS, cw)
             e.set_option(sx.OPT_PDL, args.pdl)
             e.set_option(sx.OPT_PREFETCH, args.prefetch)
+            e.set_option(sx.OPT_PANEL_COLS, args.panel_cols)
+            e.set_option(sx.OPT_HOST_GROUPS, args.host_groups)
             e.set_option(sx.OPT_HOST_FUSED, args.host_fused)
             e.set_option(sx.OPT_SLIDE, args.slide)
             if args.split >= 0:
@@ -508,6 +513,65 @@ def parity(case, w, rows0=0, rows1=None, threads=None):
             "bit_exact": bool(np.array_equal(got.view(np.uint8), ref.view(np.uint8))),
             "rows": m, "checksum": float(np.asarray(got, dtype=np.float64).sum()),
             "checksum_oracle": float(np.asarray(ref, dtype=np.float64).sum())}
+
+
+def run_batched(w, args, dev, stream, peak, nb):
+    """`nb` SpMMs of the headline workload in ONE launch (sx_spmm_device_batch_*):
+    nb distinct (B, C_in, C_out) triples with the same A.  Cold operands: T >= nb triples, T * bytes >
+    2.2 x L2, call i takes triples [i*nb mod T, ...); A itself is the one matrix every triple shares.
+    Every triple of the last call is compared with the oracle's result (they hold the same B and C_in)."""
+    import torch
+    import sextans_b200 as sx
+    import oracle
+    M, K, N, nnz, dtype = w["M"], w["K"], w["N"], w["nnz"], w["dtype"]
+    s = dtype.itemsize
+    td = torch.float64 if dtype == np.float64 else torch.float32
+    ld = (N + 7) // 8 * 8
+    sB, sC = K * ld, M * ld
+    per = (sB + 2 * sC) * s
+    T = max(nb, int(math.ceil(2.2 * L2_BYTES / per)))
+    T = (T + nb - 1) // nb * nb
+    e = sx.Engine(dev.index, arith=sx.STRICT if args.arith == "strict" else sx.FAST)
+    e.set_stream(stream.cuda_stream)
+    e.set_option(sx.OPT_PDL, args.pdl)
+    e.upload_csr(M, K, w["rowptr"], w["colidx"], w["val"])
+    with torch.cuda.stream(stream):
+        dB = torch.zeros(T * sB, dtype=td, device=dev)
+        dCin = torch.zeros(T * sC, dtype=td, device=dev)
+        dCout = torch.zeros(T * sC, dtype=td, device=dev)
+        b_cm = torch.from_numpy(w["B"]).to(dev)
+        c_cm = torch.from_numpy(w["Cin"]).to(dev)
+        e.colmajor_to_rowmajor(K, N, b_cm, dB, ld)
+        e.colmajor_to_rowmajor(M, N, c_cm, dCin, ld)
+        dB.view(T, sB)[1:] = dB.view(T, sB)[0]
+        dCin.view(T, sC)[1:] = dCin.view(T, sC)[0]
+    stream.synchronize()
+    ncalls = T // nb
+
+    def call(i):
+        o = (i % ncalls) * nb
+        e.spmm_device_batch(N, nb, ALPHA, dB[o * sB:], ld, sB, BETA, dCin[o * sC:], dCout[o * sC:], ld, sC)
+    t = time_steps(call, ncalls, ncalls, args.warmup, stream, min(args.min_region_ms, 30.0), not args.no_graph, 1, dev)
+    l0 = e.info(sx.INFO_LAUNCHES)
+    with torch.cuda.stream(stream):
+        call(0)
+    stream.synchronize()
+    launches = e.info(sx.INFO_LAUNCHES) - l0
+    kernel = e.info(sx.INFO_LAST_KERNEL)
+    ref = oracle.spmm_csr(M, N, K, w["rowptr"], w["colidx"], w["val"], dtype.type(ALPHA), w["B"], dtype.type(BETA), w["Cin"].copy(),
+                          threads=max(1, oracle.lib().sx_oracle_max_threads()))
+    ref_rm = np.zeros((M, ld), dtype)
+    ref_rm[:, :N] = ref.reshape(N, M).T
+    got = dCout.view(T, M, ld).cpu().numpy()
+    bit_exact = bool(all(np.array_equal(got[b].view(np.uint8), ref_rm.view(np.uint8)) for b in range(T)))
+    e.close()
+    ms = t["ms_median"] / nb
+    alg = per + nnz * (4 + s) / nb                      # per SpMM: its own B, C_in, C_out; A once per batch
+    return {"nb": nb, "ms_per_spmm": round(ms, 6), "gflops": round(2.0 * nnz * N / (ms * 1e-3) / 1e9, 1),
+            "frac": round(alg / (ms * 1e-3) / 1e9 / peak, 4), "launches_per_batch": int(launches),
+            "kernel_family": int(kernel // 10000), "triples": T, "bit_exact_every_triple": bit_exact,
+            "note": f"{nb} distinct (B, C_in, C_out) triples per launch, same A (grid.y = nb); cold: {T} triples = {T * per / 1e6:.0f} MB rotate; "
+                    "frac counts A once per batch"}
 
 
 def _on(stream):
@@ -742,7 +806,8 @@ def run_native(args):
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_t.median().item()) * 1e3
-    host_path = {1: "zero-copy kernels over PCIe (no memcpy): B/C_in staging, SpMM, C out", 2: "zero-copy, two launches: B staging, then the SpMM kernel reads C_in from and writes C to the caller's array itself"}.get(
+    host_path = {1: "zero-copy kernels over PCIe (no memcpy): B/C_in staging, SpMM, C out", 2: "zero-copy, two launches: B staging, then the SpMM kernel reads C_in from and writes C to the caller's array itself",
+                 3: "zero-copy, ONE launch: blocks fetch their share of B and their C_in tile from the caller's arrays (cp.async over PCIe), exchange B through L2 behind a counter, and write C back, pipelined over column groups so that both directions of the link are busy"}.get(
         eng.info(sx.INFO_HOST_PATH), "cudaMemcpyAsync + layout kernels")
     if sharded is not None:
         host_path = f"ShardedSpMM ({sharded.last_exchange} exchange of B)"
@@ -768,6 +833,13 @@ def run_native(args):
                 raise
             configs[key] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
 
+    batched = None
+    if world == 1 and args.batch > 1:
+        try:
+            batched = run_batched(w, args, dev, stream, peak, args.batch)
+        except Exception as ex:
+            batched = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+
     flops_step = 2.0 * nnz * N * world
     value = flops_step / (kern_ms * 1e-3) / 1e9
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9        # per GPU: every rank moves its own copy's bytes
@@ -779,6 +851,7 @@ def run_native(args):
             "vs_baseline": None, "dtype": "f64" if dtype == np.float64 else "f32",
             "data": data_label(w),
             "configs": configs,
+            "batched": batched,
             "parity": {"max_rel_err_all_ranks": float(perr[0].item()), "bit_exact_all_ranks": bool(perr[1].item() == 0.0),
                        "rows_checked_per_rank": M, "against": "oracle.spmm_csr (cpu_spmm_CSR restated), every row",
                        "exchange_timeouts": int(timeouts)},

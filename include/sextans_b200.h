@@ -119,12 +119,19 @@ enum sx_option {
      * M=K=1e6, nnz=9.6e7, N=16 fp64 1.63 -> 1.49 ms; uniform N=128 fp32, DRAM-bound,
      * 1.456 -> 1.470 ms, hence left off for wide rows). */
     SX_OPT_PREFETCH = 7,
-    /* -1 (default) / 1: an sx_spmm_* call that takes the zero-copy path on a matrix that runs the
-     * edge-list kernel, with rp_time <= 1 and kernel_ns == NULL (nobody asks for the kernel-only
-     * time), lets the SpMM kernel read C_in from and write C to the caller's page-locked array
-     * itself: B staging + one kernel (its programmatic dependent) instead of three launches, C's
-     * inbound and outbound PCIe transfers overlapping each other, B's transfer and the compute.
-     * Same arithmetic, same results.  SX_INFO_HOST_PATH reports 2.  0: off. */
+    /* An sx_spmm_* call that takes the zero-copy path on a matrix that runs the edge-list kernel, with
+     * rp_time <= 1 and kernel_ns == NULL (nobody asks for the kernel-only time), does not stage C on the
+     * device at all.
+     * 1: two launches -- a kernel stages B, and the SpMM kernel (its programmatic dependent) reads C_in
+     *    from and writes C to the caller's page-locked array itself.  SX_INFO_HOST_PATH reports 2.
+     * -1 (default) / 2: ONE launch where the kernel's grid is resident at once (else as 1): every block
+     *    fetches its share of B and its C_in tile from the caller's arrays with cp.async over PCIe, the
+     *    blocks exchange B through the device image (L2) behind a counter, and the call is pipelined over
+     *    SX_OPT_HOST_GROUPS column groups, so that the first columns of C leave over PCIe while the last
+     *    columns of B and C_in are still arriving -- the link's two directions overlap (measured floors,
+     *    scripts/micro/pcie_floor.cu: in then out 52 us, both at once 43 us, for nasa4704 N=16 fp64).
+     *    SX_INFO_HOST_PATH reports 3.
+     * 0: off (three launches, C staged on the device).  Same arithmetic, same results in every mode. */
     SX_OPT_HOST_FUSED = 8,
     /* Programmatic dependent launch.  -1 (default): the edge-list kernel is launched with
      * programmatic stream serialization -- its A-side prologue (records, row pointers, TMA of its
@@ -152,7 +159,22 @@ enum sx_option {
      * later calls with that N use the fastest; SX_INFO_TUNED_KERNEL reports it.  The selection
      * rules of SX_OPT_KERNEL = 0 are thresholds measured on a handful of matrices; this
      * measures the matrix at hand.  Cleared by the next upload. */
-    SX_OPT_AUTOTUNE = 12
+    SX_OPT_AUTOTUNE = 12,
+    /* N passes: columns of B and C per pass of the SpMM kernel (a multiple of 8).  The reference runs
+     * every SpMM as ceil(N/8) passes over A, 8 columns of B and C at a time (rp_time_N,
+     * src/sextans.cpp:57,84,328,474), so that a window of B fits its on-chip buffers; here a pass
+     * gathers a panel-wide slice of every B row, and the slice of the WHOLE of B (K * panel * sizeof(T)
+     * bytes) stays resident in the 126 MB L2 -- it comes from HBM once per pass instead of once per
+     * nonzero, at the price of streaming A once per pass.  0 (default) = auto.  Results are unaffected
+     * (the same chain of operations per element of C). */
+    SX_OPT_PANEL_COLS = 13,
+    /* Column groups of the fused host-facing call (SX_OPT_HOST_FUSED): the columns of C are independent
+     * and the caller's arrays are column-major, so the call is pipelined over this many groups of
+     * consecutive columns.  One-launch form: 0 (default) = auto (2), at most 8.  Two-launch form: that
+     * many (B staging, SpMM) kernel pairs chained by programmatic dependent launch; 0 = auto (1: on
+     * the measured host every further launch costs ~3.7 us, more than the overlap buys).
+     * Results are unaffected. */
+    SX_OPT_HOST_GROUPS = 14
 };
 
 enum sx_info {
@@ -167,7 +189,7 @@ enum sx_info {
     SX_INFO_ITEMS = 8,       /* work items of the main kernel */
     SX_INFO_ITEM_NNZ = 9,    /* nonzero budget per work item in use */
     SX_INFO_HOST_PATH = 10,  /* last sx_spmm_* call: 0 copy engines, 1 zero-copy kernels, 2 zero-copy with
-                              * C carried by the SpMM kernel (SX_OPT_HOST_FUSED) */
+                              * C carried by the SpMM kernel, 3 the whole call as one kernel (SX_OPT_HOST_FUSED) */
     SX_INFO_TILE_NNZ = 11,   /* nonzeros held in dense tiles */
     SX_INFO_TILE_SLOTS = 12, /* tile slots incl. explicit zeros (fill = TILE_NNZ / TILE_SLOTS) */
     SX_INFO_REST_NNZ = 13,   /* nonzeros left to the CSR kernels */
@@ -243,6 +265,19 @@ int sx_spmm_device_f32(sx_ctx *ctx, int N, float alpha, const float *dB, int64_t
                        float beta, const float *dCin, float *dCout, int64_t ldc);
 int sx_spmm_device_f64(sx_ctx *ctx, int N, double alpha, const double *dB, int64_t ldb,
                        double beta, const double *dCin, double *dCout, int64_t ldc);
+/* Several B's at once (the reference's call is one B per invoke, src/sextans-host.cpp:237-251; a
+ * caller with nb right-hand-side blocks invokes it nb times): C_out[b] = alpha * A * B[b] + beta *
+ * C_in[b] for b < nb, operand b at base + b * stride (elements; strides multiples of 16/sizeof(T),
+ * strideC >= M * ldc, strideB may be 0).  A matrix that runs the edge-list kernel takes the whole
+ * batch in ONE launch (grid.y = nb): the launch cost that dominates a small SpMM is paid once and
+ * the slice of A a block reads is shared by the nb blocks that use it.  Other kernels are launched
+ * once per operand triple.  Every result is bitwise what nb sx_spmm_device_* calls produce. */
+int sx_spmm_device_batch_f32(sx_ctx *ctx, int N, int nb, float alpha, const float *dB, int64_t ldb,
+                             int64_t strideB, float beta, const float *dCin, float *dCout,
+                             int64_t ldc, int64_t strideC);
+int sx_spmm_device_batch_f64(sx_ctx *ctx, int N, int nb, double alpha, const double *dB, int64_t ldb,
+                             int64_t strideB, double beta, const double *dCin, double *dCout,
+                             int64_t ldc, int64_t strideC);
 /* Layout changes between the host program's column-major operands and the
  * engine's row-major ones, on device memory, enqueued on the context's stream:
  * src is rows x cols column-major (ld rows); dst is row-major with leading

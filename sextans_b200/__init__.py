@@ -28,7 +28,7 @@ SX_F32, SX_F64 = 0, 1
 STRICT, FAST = 0, 1
 (OPT_ARITH, OPT_SPLIT_ROW_NNZ, OPT_KERNEL, OPT_ITEM_NNZ, OPT_ZEROCOPY_BYTES, OPT_TILE_MIN_ROWS,
  OPT_COL_WINDOW_ROWS, OPT_PREFETCH, OPT_HOST_FUSED, OPT_PDL, OPT_WINDOW_ROWS, OPT_SLIDE,
- OPT_AUTOTUNE) = range(13)
+ OPT_AUTOTUNE, OPT_PANEL_COLS, OPT_HOST_GROUPS) = range(15)
 (INFO_LAUNCHES, INFO_M, INFO_K, INFO_NNZ, INFO_DTYPE, INFO_SPLIT_ROWS, INFO_LAST_KERNEL, INFO_LD,
  INFO_ITEMS, INFO_ITEM_NNZ, INFO_HOST_PATH, INFO_TILE_NNZ, INFO_TILE_SLOTS, INFO_REST_NNZ,
  INFO_UPLOAD_SERIAL, INFO_COL_WINDOWS, INFO_TUNED_KERNEL, INFO_EXCHANGE_TIMEOUTS, INFO_EDGE_BLOCKS,
@@ -89,6 +89,8 @@ def lib():
         "sx_device_B": ([vp, i, C.POINTER(vp), C.POINTER(sz)], i),
         "sx_spmm_device_f32": ([vp, i, C.c_float, vp, i64, C.c_float, vp, vp, i64], i),
         "sx_spmm_device_f64": ([vp, i, C.c_double, vp, i64, C.c_double, vp, vp, i64], i),
+        "sx_spmm_device_batch_f32": ([vp, i, i, C.c_float, vp, i64, i64, C.c_float, vp, vp, i64, i64], i),
+        "sx_spmm_device_batch_f64": ([vp, i, i, C.c_double, vp, i64, i64, C.c_double, vp, vp, i64, i64], i),
         "sx_colmajor_to_rowmajor": ([vp, i, i64, i, vp, vp, i64], i),
         "sx_rowmajor_to_colmajor": ([vp, i, i64, i, vp, i64, vp], i),
         "sx_device_alloc": ([vp, sz, C.POINTER(vp)], i),
@@ -552,6 +554,13 @@ class Engine:
         suf, ct, _ = _suffix(self.dtype)
         _check(getattr(self._L, f"sx_spmm_device_{suf}")(
             self._ctx, N, ct(alpha), _dev_ptr(dB), ldb, ct(beta), _dev_ptr(dCin), _dev_ptr(dCout), ldc))
+
+    def spmm_device_batch(self, N, nb, alpha, dB, ldb, strideB, beta, dCin, dCout, ldc, strideC):
+        """Enqueue nb SpMMs with the same A: operand b at base + b * stride elements (one launch on
+        the edge-list kernel)."""
+        suf, ct, _ = _suffix(self.dtype)
+        _check(getattr(self._L, f"sx_spmm_device_batch_{suf}")(
+            self._ctx, N, nb, ct(alpha), _dev_ptr(dB), ldb, strideB, ct(beta), _dev_ptr(dCin), _dev_ptr(dCout), ldc, strideC))
 
     def colmajor_to_rowmajor(self, rows, cols, d_src, d_dst, ld_dst, dtype=None):
         code = _suffix(dtype or self.dtype)[2]

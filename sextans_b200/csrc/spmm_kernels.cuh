@@ -217,6 +217,34 @@ __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// element-sized asynchronous copies (the one-kernel host call: straight from page-locked host memory), commit groups
+__device__ __forceinline__ void cp_async_elem(float *smem_dst, const float *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_elem(double *smem_dst, const double *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// at most n (0..7) of the most recently committed groups still pending
+__device__ __forceinline__ void cp_async_wait_pending(int n) {
+    switch (n) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+        case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+    }
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_l2(const float4 *p) { return __ldcg(p); }
+__device__ __forceinline__ double2 ld_l2(const double2 *p) { return __ldcg(p); }
 // programmatic dependent launch (no-ops when the grid was launched without the attribute)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -736,6 +764,58 @@ __device__ __forceinline__ unsigned long long sx_now() {
 #else
 #define SX_TRACE_MARK(i) do { } while (0)
 #endif
+// One row of the edge-list kernels out of shared memory: sc[j] / sv[j] = local column / value of nonzero j,
+// w[local column * G] = this lane's 16-byte piece of that B row.  Stored order, chunks of 8 nonzeros,
+// software-pipelined: the (column, value) pairs of chunk k+1 and the eight B-row pieces of chunk k are in
+// flight while the ordered chain of additions of chunk k runs.
+template <typename T, int G, bool STRICT>
+__device__ __forceinline__ typename VecOf<T>::type edge_row_walk(const uint16_t *sc, const T *sv, const typename VecOf<T>::type *w,
+                                                                 const int begin, const int end) {
+    using V = typename VecOf<T>::type;
+    V acc;
+    vzero(acc);
+    constexpr int UC = 8;
+    int j = begin;
+    if (j + UC <= end) {
+        uint32_t c[UC];
+        T a[UC];
+#pragma unroll
+        for (int u = 0; u < UC; ++u) { c[u] = sc[j + u]; a[u] = sv[j + u]; }
+        for (;;) {
+            V b[UC];
+#pragma unroll
+            for (int u = 0; u < UC; ++u) b[u] = w[c[u] * G];
+            const int jn = j + UC;
+            const bool more = jn + UC <= end;
+            uint32_t c2[UC];
+            T a2[UC];
+            const int jl = more ? jn : j;  // unconditional loads (this chunk again when there is no next one)
+#pragma unroll
+            for (int u = 0; u < UC; ++u) { c2[u] = sc[jl + u]; a2[u] = sv[jl + u]; }
+#pragma unroll
+            for (int u = 0; u < UC; ++u) vmac<STRICT>(acc, a[u], b[u]);
+            j = jn;
+            if (!more) break;
+#pragma unroll
+            for (int u = 0; u < UC; ++u) { c[u] = c2[u]; a[u] = a2[u]; }
+        }
+    }
+    if (j < end) {
+        // the last, partial chunk: its loads all in flight at once (indices clamped to the row),
+        // the additions predicated -- an explicit +0 would turn a -0 sum into +0
+        uint32_t c[UC];
+        T a[UC];
+        V b[UC];
+#pragma unroll
+        for (int u = 0; u < UC; ++u) { const int ju = min(j + u, end - 1); c[u] = sc[ju]; a[u] = sv[ju]; }
+#pragma unroll
+        for (int u = 0; u < UC; ++u) b[u] = w[c[u] * G];
+#pragma unroll
+        for (int u = 0; u < UC; ++u)
+            if (j + u < end) vmac<STRICT>(acc, a[u], b[u]);
+    }
+    return acc;
+}
 template <int G> struct EdgeShape {
     static constexpr int THREADS = G >= 16 ? 512 : 256;
     static constexpr int ROWS = THREADS / G;
@@ -743,14 +823,19 @@ template <int G> struct EdgeShape {
 template <typename T, int G, bool STRICT, bool HOSTC = false>
 __global__ void __launch_bounds__(EdgeShape<G>::THREADS, 2)
 spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ cols, const int *__restrict__ rowptr,
-                     const uint16_t *__restrict__ lcol, const T *__restrict__ val, const T *__restrict__ B,
-                     const uint32_t ldbv, const T *Cin, T *Cout, const uint32_t ldcv, const T alpha, const T beta,
+                     const uint16_t *__restrict__ lcol, const T *__restrict__ val, const T *__restrict__ B0,
+                     const uint32_t ldbv, const T *Cin0, T *Cout0, const uint32_t ldcv, const T alpha, const T beta,
                      const int nvec, const int flags, const uint32_t *ready, uint32_t *epoch, uint32_t *done_remote,
                      unsigned int *sync_words, const int npush, const PushList push, const int64_t push_n16,
                      const uint32_t *push_done, uint32_t *pushes, T *Ch, const int64_t ldh, const int N,
-                     const uint32_t tile_off, const int tile_ld) {
+                     const uint32_t tile_off, const int tile_ld, const int64_t batch_strideB, const int64_t batch_strideC) {
     using V = typename VecOf<T>::type;
     constexpr int THREADS = EdgeShape<G>::THREADS, ROWS = EdgeShape<G>::ROWS, E = VecOf<T>::E;
+    // several B's at once (sx_spmm_device_batch_*): blockIdx.y picks the (B, C_in, C_out) triple; the block's
+    // slice of A is the same for every one of them and stays in L2 between the blocks that share it
+    const T *__restrict__ B = B0 + (size_t)blockIdx.y * batch_strideB;
+    const T *Cin = HOSTC ? Cin0 : Cin0 + (size_t)blockIdx.y * batch_strideC;
+    T *Cout = HOSTC ? Cout0 : Cout0 + (size_t)blockIdx.y * batch_strideC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;  // the A slice and the column list
 #ifdef SX_EDGE_TRACE
@@ -882,50 +967,7 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
             } else if (rr + ROWS < nrows) {
                 cin_next = Cv[(size_t)(rr + ROWS) * ldcv];
             }
-            V acc;
-            vzero(acc);
-            // chunks of 8 nonzeros, software-pipelined: the (column, value) pairs of chunk k+1 and the
-            // eight B-row pieces of chunk k are in flight while the ordered chain of additions of chunk k runs
-            constexpr int UC = 8;
-            int j = begin;
-            if (j + UC <= end) {
-                uint32_t c[UC];
-                T a[UC];
-#pragma unroll
-                for (int u = 0; u < UC; ++u) { c[u] = sc[j + u]; a[u] = sv[j + u]; }
-                for (;;) {
-                    V b[UC];
-#pragma unroll
-                    for (int u = 0; u < UC; ++u) b[u] = w[c[u] * G];
-                    const int jn = j + UC;
-                    const bool more = jn + UC <= end;
-                    uint32_t c2[UC];
-                    T a2[UC];
-                    const int jl = more ? jn : j;  // unconditional loads (this chunk again when there is no next one)
-#pragma unroll
-                    for (int u = 0; u < UC; ++u) { c2[u] = sc[jl + u]; a2[u] = sv[jl + u]; }
-#pragma unroll
-                    for (int u = 0; u < UC; ++u) vmac<STRICT>(acc, a[u], b[u]);
-                    j = jn;
-                    if (!more) break;
-#pragma unroll
-                    for (int u = 0; u < UC; ++u) { c[u] = c2[u]; a[u] = a2[u]; }
-                }
-            }
-            if (j < end) {
-                // the last, partial chunk: its loads all in flight at once (indices clamped to the row),
-                // the additions predicated -- an explicit +0 would turn a -0 sum into +0
-                uint32_t c[UC];
-                T a[UC];
-                V b[UC];
-#pragma unroll
-                for (int u = 0; u < UC; ++u) { const int ju = min(j + u, end - 1); c[u] = sc[ju]; a[u] = sv[ju]; }
-#pragma unroll
-                for (int u = 0; u < UC; ++u) b[u] = w[c[u] * G];
-#pragma unroll
-                for (int u = 0; u < UC; ++u)
-                    if (j + u < end) vmac<STRICT>(acc, a[u], b[u]);
-            }
+            const V acc = edge_row_walk<T, G, STRICT>(sc, sv, w, begin, end);
             const V out = vaxpby<STRICT>(alpha, acc, beta, cin);
             if (HOSTC) {
                 const T *op = reinterpret_cast<const T *>(&out);
@@ -957,6 +999,148 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
     }
     // (the rank that holds B publishes the step from publish_push_kernel, launched right behind this
     // kernel: the kernel boundary is the fence, and this kernel's tail stays free of system-scope fences)
+}
+
+// ---- the host-facing call as ONE kernel (sx_spmm_* with small page-locked operands, kernel_ns == NULL) ----
+// The pieces of the call were measured on the host's clock (scripts/micro/pcie_floor.cu, profiles/r02_pcie_floor.txt):
+// an empty launch + cudaStreamSynchronize costs 10 us, every further launch ~3.7 us, reading B and C_in of
+// nasa4704 N=16 fp64 (1.2 MB) over PCIe 25 us, writing C (0.6 MB) 14 us -- one after the other 52 us -- and both
+// directions AT ONCE 43 us: the link is full duplex, the two-launch call (staging kernel, then the HOSTC form of
+// spmm_edgelist_kernel: 60 us) only ever uses one direction at a time.  So:
+//   * ONE launch.  Every block first fetches a 1/gridDim share of the rows of the caller's column-major B and the
+//     C_in tile of its own rows into shared memory with cp.async straight from host memory (LDGSTS over PCIe;
+//     nothing waits on them yet), one commit group per COLUMN GROUP of gw columns, issued in group order.
+//   * Column groups are independent SpMMs (C[:, n] depends on B[:, n] only).  For group g = 0, 1, ...: wait for
+//     that group's copies, write the B share into the row-major device image, fence, count the block in on
+//     counters[g]; when all blocks are in, fetch the group's slice of the window rows from L2 (ld.global.cg -- the
+//     image was written by other SMs), walk the rows (same order of operations as everywhere: bit-identical to
+//     cpu_spmm_CSR), and store the result columns into the caller's array -- posted PCIe writes that leave
+//     while the later groups' operands are still arriving.
+// Measured (scripts/micro/e2e_c.cpp, nasa4704 N=16 fp64, median per call on the host's clock; profiles/r02_e2e_call.txt):
+// two launches 58.9 us; this kernel with 1 / 2 / 4 / 8 groups 58.6 / 56.5 / 61.8 / 77.6 us (one group requested ahead;
+// two or three ahead: 58.8-59.1 / 59.3-60.3 / 75.8-76.6) -- every group costs a grid-wide wait (~2 us), and the floor of
+// this box for "1.2 MB in, then 0.6 MB out" in ONE launch is 9.6 + 25 + 14 = 49 us before any arithmetic.  Default: 2 groups.
+// The grid must be co-resident (blocks wait for one another): the host checks the occupancy and falls back to the
+// two-launch path otherwise; a wait that sees nothing for ~2 s gives up and raises *timeout_flag (host memory).
+// counters[0..7]: every block adds 1 to each of them exactly once per launch, so they all stand at `target -
+// gridDim.x` when a launch starts, whatever the number of groups of the launches before it.
+constexpr int SX_HOST_MAX_GROUPS = 8;
+
+template <typename T, int G, bool STRICT>
+__global__ void __launch_bounds__(EdgeShape<G>::THREADS, 2)
+spmm_edgelist_host_kernel(const int4 *__restrict__ blocks, const int *__restrict__ cols, const int *__restrict__ rowptr,
+                          const uint16_t *__restrict__ lcol, const T *__restrict__ val, const T *Bh, T *Bimg,
+                          const uint32_t ldbv, T *Ch, const int64_t M, const int64_t K, const int N, const T alpha,
+                          const T beta, const int gw, uint32_t *counters, const uint32_t target, uint32_t *timeout_flag,
+                          const uint32_t tile_off, const int tile_ld, const uint32_t share_off, const int share_ld, const int depth) {
+    using V = typename VecOf<T>::type;
+    constexpr int THREADS = EdgeShape<G>::THREADS, ROWS = EdgeShape<G>::ROWS, E = VecOf<T>::E, NWARPS = THREADS / 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    const int lg = threadIdx.x & (G - 1);
+    const int rl = threadIdx.x / G;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int4 b0 = __ldg(blocks + 2 * blockIdx.x), b1 = __ldg(blocks + 2 * blockIdx.x + 1);
+    const int row0 = b0.x, nrows = b0.y, jb = b0.z, je = b0.w;
+    const int ncols = b1.y;
+    const uint32_t wbytes = (uint32_t)ncols * (G * 16u);
+    const int jal = jb & ~7;
+    const bool has = je > jb;
+    const uint32_t na = has ? (uint32_t)((je - jal + 7) & ~7) : 0u;
+    const uint32_t ncp = (uint32_t)(ncols + 3) & ~3u;
+    V *win = reinterpret_cast<V *>(smem_raw);
+    const T *sval = reinterpret_cast<const T *>(smem_raw + wbytes);
+    const uint16_t *scol = reinterpret_cast<const uint16_t *>(smem_raw + wbytes + (size_t)na * sizeof(T));
+    const int *scols = reinterpret_cast<const int *>(smem_raw + wbytes + (size_t)na * (sizeof(T) + 2));
+    int *srp = const_cast<int *>(scols) + ncp;
+    T *tile = reinterpret_cast<T *>(smem_raw + tile_off);    // tile[column * tile_ld + row of the block]
+    T *share = reinterpret_cast<T *>(smem_raw + share_off);  // share[column * share_ld + row of the share]
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && has) {  // the A side by TMA, as in spmm_edgelist_kernel
+        const uint64_t pol_a = policy_evict_first();
+        mbar_expect_tx(&bar, na * (uint32_t)(sizeof(T) + 2) + ncp * 4u);
+        tma_bulk_g2s(const_cast<int *>(scols), cols + b1.x, ncp * 4u, &bar, pol_a);
+        tma_bulk_g2s(const_cast<T *>(sval), val + jal, na * (uint32_t)sizeof(T), &bar, pol_a);
+        tma_bulk_g2s(const_cast<uint16_t *>(scol), lcol + jal, na * 2u, &bar, pol_a);
+    }
+    // ---- inbound: this block's share of B's rows and its C_in tile, group by group, nothing waited for yet ----
+    const int ks0 = (int)(K * (int64_t)blockIdx.x / gridDim.x), ks1 = (int)(K * (int64_t)(blockIdx.x + 1) / gridDim.x);
+    const int nshare = ks1 - ks0;
+    const int ngroups = (N + gw - 1) / gw;
+    // `depth` groups in flight: with everything requested at once the link serves all groups side by side and the
+    // first one is complete no earlier than the last; two in flight keep the link busy and the groups in order
+    auto fetch_group = [&](const int g) {
+        const int n_lo = g * gw, n_hi = min(N, n_lo + gw);
+        for (int cidx = n_lo + warp; cidx < n_hi; cidx += NWARPS) {  // a warp per column, lanes along the rows
+            for (int r = lane; r < nshare; r += 32) cp_async_elem(share + cidx * share_ld + r, Bh + (size_t)cidx * K + ks0 + r);
+            for (int r = lane; r < nrows; r += 32) cp_async_elem(tile + cidx * tile_ld + r, Ch + (size_t)cidx * M + row0 + r);
+        }
+        cp_async_commit();
+    };
+    for (int g = 0; g < min(depth, ngroups); ++g) fetch_group(g);
+    for (int i = threadIdx.x; i <= nrows; i += THREADS) srp[i] = __ldg(rowptr + row0 + i);
+    if (has) mbar_wait(&bar, 0);
+    const T *sv = sval - jal;
+    const uint16_t *sc = scol - jal;
+    V *Bv = reinterpret_cast<V *>(Bimg);
+    bool gave_up = false;
+    for (int g = 0; g < ngroups; ++g) {
+        const int n_lo = g * gw, n_hi = min(N, n_lo + gw);
+        const int v_lo = n_lo / E, nvg = ((g == ngroups - 1 ? (int)ldbv * E : n_hi) + E - 1) / E - v_lo;  // the last group zero-fills the padding
+        cp_async_wait_pending(min(depth, ngroups - g) - 1);
+        __syncthreads();
+        if (g + depth < ngroups) fetch_group(g + depth);  // (its tile and share slots are its own: no hazard with the groups in progress)
+        // the share of this group's columns of B into the row-major device image, 16 bytes per store
+        for (int i = threadIdx.x; i < nshare * nvg; i += THREADS) {
+            const int r = i / nvg, v = v_lo + i % nvg;
+            V x;
+            T *xp = reinterpret_cast<T *>(&x);
+#pragma unroll
+            for (int e = 0; e < E; ++e) xp[e] = (v * E + e < N) ? share[(v * E + e) * share_ld + r] : T(0);
+            Bv[(size_t)(ks0 + r) * ldbv + v] = x;
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            atomicAdd(counters + g, 1u);
+            const long long t0 = clock64();
+            while ((int)(ld_acquire_gpu(counters + g) - target) < 0) {
+                __nanosleep(20);
+                if (clock64() - t0 > 4000000000ll) { *reinterpret_cast<volatile uint32_t *>(timeout_flag) = 1u; break; }
+            }
+        }
+        __syncthreads();
+        // this group's slice of the window rows, from L2
+        const int nvw = min(nvg, G - v_lo);
+        for (int i = threadIdx.x; i < ncols * nvw; i += THREADS) {
+            const int lr = i / nvw, v = v_lo + i % nvw;
+            win[lr * G + v] = ld_l2(Bv + (size_t)(uint32_t)scols[lr] * ldbv + v);
+        }
+        __syncthreads();
+        if (lg >= v_lo && lg < v_lo + nvw && lg * E < N)
+            for (int rr = rl; rr < nrows; rr += ROWS) {
+                V cin;
+                T *cp = reinterpret_cast<T *>(&cin);
+#pragma unroll
+                for (int e = 0; e < E; ++e) cp[e] = (lg * E + e < N) ? tile[(lg * E + e) * tile_ld + rr] : T(0);
+                const V acc = edge_row_walk<T, G, STRICT>(sc, sv, win + lg, srp[rr], srp[rr + 1]);
+                const V out = vaxpby<STRICT>(alpha, acc, beta, cin);
+                const T *op = reinterpret_cast<const T *>(&out);
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    if (lg * E + e < N) tile[(lg * E + e) * tile_ld + rr] = op[e];
+            }
+        __syncthreads();
+        for (int cidx = n_lo + warp; cidx < n_hi; cidx += NWARPS)  // the result columns into the caller's array: posted writes
+            for (int r = lane; r < nrows; r += 32) Ch[(size_t)cidx * M + row0 + r] = tile[cidx * tile_ld + r];
+    }
+    (void)gave_up;
+    if (threadIdx.x == 0)
+        for (int g = ngroups; g < SX_HOST_MAX_GROUPS; ++g) atomicAdd(counters + g, 1u);  // keep the eight counters level
 }
 
 // ---- variant 4 (experimental, SX_OPT_SLIDE): long banded matrices, a SLIDING B window -------
@@ -1503,13 +1687,14 @@ colmajor_to_rowmajor_kernel(const int64_t rows, const int cols, const T *__restr
 // along a column and every thread moves VEC consecutive rows with one 16-byte access
 // when VEC > 1 (the host passes VEC = 16/sizeof(T) only if both row counts are multiples
 // of it, which keeps every column start 16-byte aligned), so a warp reads 512 contiguous
-// bytes over PCIe per instruction.
+// bytes over PCIe per instruction.  dst may point at a column group of a wider image (ld = the
+// image's leading dimension, wcols = columns of the group): the host-facing call's column pipeline.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
 colmajor_to_rowmajor_pair_kernel(const int64_t rowsB, const int64_t rowsC, const int cols,
                                  const T *__restrict__ srcB, const T *__restrict__ srcC,
                                  T *__restrict__ dstB, T *__restrict__ dstC, const int64_t ld,
-                                 const int tcol, const int64_t tilesB) {
+                                 const int tcol, const int64_t tilesB, const int wcols) {
     constexpr int TR = 32 * VEC;  // rows per tile
     __shared__ T tile[32][TR + 1];
     pdl_launch_dependents();  // a dependent launch (the fused SpMM) may run its A-side prologue beside this kernel
@@ -1539,7 +1724,7 @@ colmajor_to_rowmajor_pair_kernel(const int64_t rowsB, const int64_t rowsC, const
     for (int j = threadIdx.y; j < TR; j += 8) {
         const int64_t r = r0 + j;
         const int c = c0 + threadIdx.x;
-        if (r < rows && c < ld) dst[r * ld + c] = tile[threadIdx.x][j];
+        if (r < rows && c < wcols) dst[r * ld + c] = tile[threadIdx.x][j];  // wcols: columns written (cols..wcols-1 zero-filled)
     }
 }
 

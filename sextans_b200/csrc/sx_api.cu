@@ -157,6 +157,10 @@ struct sx_ctx {
     int win_flags = 0;
     void *win_P = nullptr;  // parent's psum, same leading dimension as C
     int win_col0 = 0;       // first column of the column panel being launched
+    // sx_spmm_device_batch_*: operand triples the next edge-list launch covers (grid.y) and their strides
+    int batch = 1;
+    int64_t batch_sB = 0, batch_sC = 0;
+    bool batch_taken = false;
 
     // dense operands (row-major, ld elements per row)
     int N = 0;
@@ -173,6 +177,17 @@ struct sx_ctx {
     int item_nnz = 0;  // 0 = auto
     int prefetch = -1;  // SX_OPT_PREFETCH: -1 auto, 0 off, 1 on
     int host_fused = -1;  // SX_OPT_HOST_FUSED: -1 auto (on), 0 off, 1 on
+    // the host-facing call as one kernel: eight block counters (device), what they all stand at, a time-out flag
+    // in page-locked host memory (the kernel raises it, the host looks after the sync), occupancy per (kernel, smem)
+    DevBuf host_counters;
+    uint32_t host_base = 0;
+    int64_t exchange_timeouts_host = 0;
+    uint32_t *host_flag = nullptr, *host_flag_dev = nullptr;
+    struct Occ { const void *kern; size_t smem; int per_sm; };
+    std::vector<Occ> host_occ;
+    int host_depth = 0;  // experiment knob (env SX_HOST_DEPTH): column groups requested ahead in the one-kernel call
+    int host_groups = 0; // SX_OPT_HOST_GROUPS: column groups of the fused host-facing call (0 auto)
+    int panel_cols = 0;  // SX_OPT_PANEL_COLS: 0 auto, else columns per pass
     int pdl = -1;        // SX_OPT_PDL: -1 auto (variant 5 always, variant 3 never), 0 off, 1 on
     int64_t zerocopy_bytes = 3 << 19;  // 1.5 MiB: above that the copy engines win
     int last_path = 0;  // 1: the last host-facing call took the zero-copy path
@@ -241,7 +256,9 @@ int launch_edge(sx_ctx *c, const EdgePlan *ep, int N, T alpha, const T *dB, int6
     if (smem > 227 * 1024 - 1024) return fail(SX_ERR_INVALID, "internal: edge-list block needs %zu bytes of shared memory", smem);
     const bool pf = c->prefetch != 0;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)ep->nblocks);
+    const int nbatch = HOSTC ? 1 : c->batch;
+    if (nbatch > 1 && (c->x_ready || c->p_npeers)) return fail(SX_ERR_STATE, "a batched SpMM cannot carry the multi-GPU exchange");
+    cfg.gridDim = dim3((unsigned)ep->nblocks, (unsigned)nbatch);
     cfg.blockDim = dim3(sx::EdgeShape<G>::THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = c->stream;
@@ -259,7 +276,9 @@ int launch_edge(sx_ctx *c, const EdgePlan *ep, int N, T alpha, const T *dB, int6
                                (const uint16_t *)ep->lcol.p, (const T *)c->val.p, dB, (uint32_t)(ldb / E), dCin, dCout,
                                (uint32_t)(ldc / E), alpha, beta, nvec, pf ? sx::SX_EDGE_PREFETCH : 0, c->x_ready, c->x_epoch,
                                c->x_done, (unsigned int *)c->sync_words.p, npush, c->p_list, push_n16, c->p_done, c->p_pushes,
-                               Ch, (int64_t)c->M, N, (uint32_t)tile_off, tile_ld));
+                               Ch, (int64_t)c->M, N, (uint32_t)tile_off, tile_ld, nbatch > 1 ? c->batch_sB : (int64_t)0,
+                               nbatch > 1 ? c->batch_sC : (int64_t)0));
+    c->batch_taken = nbatch > 1;
     c->x_ready = nullptr;
     c->launches++;
     if (npush) {  // the publication of the push, right behind the kernel that carried it (its programmatic dependent)
@@ -629,6 +648,14 @@ int autotune(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, const 
     return SX_OK;
 }
 
+// Automatic pass width (columns), see spmm_device.  Measured on C4 (uniform, M = K = 1e6, 20 nonzeros per row,
+// N = 128 fp32: B = 512 MB, every B row used 20 times): TODO
+template <typename T>
+int auto_panel_cols(const sx_ctx *c, int N, int64_t ldb) {
+    (void)c; (void)N; (void)ldb;
+    return 1 << 30;
+}
+
 // One SpMM over device-resident row-major operands.  Column counts beyond what one
 // row group covers (4 vectors x 32 lanes) are processed in column panels.
 template <typename T>
@@ -650,7 +677,13 @@ int spmm_device(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, con
     if (c->tile_steps > 0) return spmm_tiles<T>(c, N, alpha, dB, ldb, beta, dCin, dCout, ldc);
     if (!c->wins.empty()) return spmm_windows<T>(c, N, alpha, dB, ldb, beta, dCin, dCout, ldc);
 
-    const int panel_cols = 4 * 32 * E;  // widest shape: G = 32, VPL = 4
+    int panel_cols = 4 * 32 * E;  // widest shape: G = 32, VPL = 4
+    // N passes (the reference's own schedule: 8 columns of B and C per pass, rp_time_N = rp_time * ((N + 7) >> 3),
+    // src/sextans.cpp:57,84,328,474) with L2 in the role of the on-chip B buffer: a pass gathers only a
+    // panel_cols-wide slice of every B row, so the slice of the whole B stays L2-resident and comes from HBM
+    // once per pass instead of once per nonzero, at the price of streaming A once per pass
+    if (c->panel_cols > 0) panel_cols = std::min(panel_cols, c->panel_cols);
+    else if (!c->win_mode) panel_cols = std::min(panel_cols, auto_panel_cols<T>(c, N, ldb));
     // SX_OPT_AUTOTUNE: the first call for a column count times every variant that applies on
     // the caller's own operands and keeps the fastest for later calls with that N
     if (c->autotune && !c->tuning && !c->win_mode && N <= panel_cols && dCin != dCout) {
@@ -687,6 +720,36 @@ int spmm_device(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, con
         if (rc) return rc;
     }
     return SX_OK;
+}
+
+// Several B's at once: C_out[b] = alpha * A * B[b] + beta * C_in[b] for b < nb, operand b at
+// base + b * stride.  A matrix on the edge-list kernel takes the whole batch in ONE launch (grid.y = nb: the launch
+// cost that dominates a small SpMM is paid once, and the block's slice of A is read from HBM once for all of them);
+// every other kernel is launched once per operand triple.
+template <typename T>
+int spmm_device_batch(sx_ctx *c, int N, int nb, T alpha, const T *dB, int64_t ldb, int64_t sB, T beta, const T *dCin,
+                      T *dCout, int64_t ldc, int64_t sC) {
+    if (!c) return fail(SX_ERR_INVALID, "null context");
+    constexpr int E = sx::VecOf<T>::E;
+    if (nb < 0) return fail(SX_ERR_INVALID, "batch count must be >= 0 (got %d)", nb);
+    if (sB < 0 || sC < 0 || sB % E || sC % E) return fail(SX_ERR_INVALID, "batch strides must be >= 0 and multiples of %d elements", E);
+    if (nb > 1 && sC < (int64_t)c->M * ldc && sC != 0) return fail(SX_ERR_INVALID, "C operands of a batch overlap (stride %lld < M * ldc)", (long long)sC);
+    if (nb > 1 && sC == 0) return fail(SX_ERR_INVALID, "C operands of a batch must be distinct (stride 0)");
+    const bool one_launch = N <= 4 * 32 * E && (c->panel_cols == 0 || N <= c->panel_cols) && c->tile_steps == 0 && c->wins.empty() && !c->autotune;
+    int rc = SX_OK;
+    for (int b0 = 0; b0 < nb && !rc;) {
+        const int chunk = one_launch ? std::min(nb - b0, 65535) : 1;
+        c->batch = chunk;
+        c->batch_sB = sB;
+        c->batch_sC = sC;
+        c->batch_taken = false;
+        rc = spmm_device<T>(c, N, alpha, dB + (size_t)b0 * sB, ldb, beta, dCin + (size_t)b0 * sC, dCout + (size_t)b0 * sC, ldc);
+        const bool taken = c->batch_taken;
+        c->batch = 1;
+        c->batch_taken = false;
+        b0 += taken ? chunk : 1;
+    }
+    return rc;
 }
 
 // ---- A upload ---------------------------------------------------------------------
@@ -1343,6 +1406,58 @@ void *mapped_alias(const void *host) {
     return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
 }
 
+// The host-facing call as ONE launch (spmm_edgelist_host_kernel).  *done = false (and SX_OK) where it does not apply:
+// the blocks wait for one another, so the whole grid must be resident at once.
+template <typename T, int G, bool STRICT>
+int launch_edge_host(sx_ctx *c, const EdgePlan *ep, int N, T alpha, const T *Bh, T beta, T *Ch, bool *done) {
+    constexpr int E = sx::VecOf<T>::E, THREADS = sx::EdgeShape<G>::THREADS;
+    *done = false;
+    auto kern = sx::spmm_edgelist_host_kernel<T, G, STRICT>;
+    const int tile_ld = sx::EdgeShape<G>::ROWS + 1;
+    const int share_ld = ((c->K + ep->nblocks - 1) / ep->nblocks) | 1;
+    const size_t tile_off = ((size_t)std::max(ep->max_smem, 16) + 15) & ~(size_t)15;
+    const size_t share_off = tile_off + (((size_t)N * tile_ld * sizeof(T) + 15) & ~(size_t)15);
+    const size_t smem = share_off + (size_t)N * share_ld * sizeof(T);
+    if (smem > 227 * 1024 - 1024) return SX_OK;
+    int per_sm = -1;
+    for (const auto &o : c->host_occ)
+        if (o.kern == (const void *)kern && o.smem == smem) per_sm = o.per_sm;
+    if (per_sm < 0) {
+        if (smem > 48 * 1024) SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+        SX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+        c->host_occ.push_back({(const void *)kern, smem, per_sm});
+    }
+    if ((int64_t)per_sm * c->sm_count < ep->nblocks) return SX_OK;
+    int rc;
+    if (!c->host_counters.p) {
+        if ((rc = c->host_counters.ensure(64))) return rc;
+        SX_CUDA(cudaMemsetAsync(c->host_counters.p, 0, 64, c->stream));
+        c->host_base = 0;
+    }
+    if (!c->host_flag) {
+        SX_CUDA(cudaHostAlloc((void **)&c->host_flag, 64, cudaHostAllocMapped));
+        *c->host_flag = 0;
+        SX_CUDA(cudaHostGetDevicePointer((void **)&c->host_flag_dev, c->host_flag, 0));
+    }
+    int groups = c->host_groups > 0 ? std::min(c->host_groups, sx::SX_HOST_MAX_GROUPS) : 2;  // measured best (profiles/r02_e2e_call.txt)
+    int gw = (N + groups - 1) / groups;
+    gw = std::max(E, (gw + E - 1) / E * E);  // a group starts on a 16-byte boundary of the image row
+    while ((N + gw - 1) / gw > sx::SX_HOST_MAX_GROUPS) gw += E;
+    const uint32_t target = c->host_base + (uint32_t)ep->nblocks;
+    kern<<<(unsigned)ep->nblocks, THREADS, smem, c->stream>>>(
+        (const int4 *)ep->blocks.p, (const int *)ep->cols.p, (const int *)c->rowptr.p, (const uint16_t *)ep->lcol.p,
+        (const T *)c->val.p, Bh, (T *)c->B.p, (uint32_t)(c->ld / E), Ch, (int64_t)c->M, (int64_t)c->K, N, alpha, beta, gw,
+        (uint32_t *)c->host_counters.p, target, c->host_flag_dev, (uint32_t)tile_off, tile_ld, (uint32_t)share_off, share_ld,
+        c->host_depth > 0 ? std::min(c->host_depth, sx::SX_HOST_MAX_GROUPS) : 1);
+    SX_CUDA(cudaGetLastError());
+    c->host_base = target;
+    c->launches++;
+    c->last_edge_plan = ep;
+    c->last_kernel = 100000 + G * 100 + 10 + (STRICT ? 0 : 1);
+    *done = true;
+    return SX_OK;
+}
+
 // The host-facing call when nobody asked for the kernel time (kernel_ns == NULL) and the matrix
 // takes the edge-list kernel: TWO launches.  The B staging kernel reads the caller's column-major B
 // over PCIe and writes the row-major device image; the SpMM kernel (HOSTC) reads its C_in tiles from
@@ -1368,32 +1483,75 @@ int spmm_host_fused(sx_ctx *c, int N, T alpha, const void *dB, T beta, void *dC,
     constexpr int VEC = 16 / (int)sizeof(T);
     const bool vec = c->K % VEC == 0 && ((uintptr_t)dB & 15) == 0;
     const int tr = vec ? 32 * VEC : 32;
-    const int64_t tB = ((int64_t)c->K + tr - 1) / tr, tcol = (c->ld + 31) / 32;
-    if (tB * tcol > 0) {
-        dim3 block(32, 8), grid((unsigned)(tB * tcol));
-        if (vec)
-            sx::colmajor_to_rowmajor_pair_kernel<T, VEC><<<grid, block, 0, c->stream>>>(
-                c->K, 0, N, (const T *)dB, (const T *)dB, (T *)c->B.p, (T *)c->B.p, c->ld, (int)tcol, tB * tcol);
-        else
-            sx::colmajor_to_rowmajor_pair_kernel<T, 1><<<grid, block, 0, c->stream>>>(
-                c->K, 0, N, (const T *)dB, (const T *)dB, (T *)c->B.p, (T *)c->B.p, c->ld, (int)tcol, tB * tcol);
-        c->launches++;
-        SX_CUDA(cudaGetLastError());
-    }
+    const int64_t tB = ((int64_t)c->K + tr - 1) / tr;
     c->has_B = true;
     c->has_C = false;  // C never exists as a device image on this path
     c->win_col0 = 0;
     const bool strict = c->arith == 0;
-#define SX_HOSTC(GG)                                                                                                        \
-    rc = strict ? launch_edge<T, GG, true, true>(c, ep, N, alpha, (const T *)c->B.p, c->ld, beta, nullptr, nullptr, c->ld, (T *)dC) \
-                : launch_edge<T, GG, false, true>(c, ep, N, alpha, (const T *)c->B.p, c->ld, beta, nullptr, nullptr, c->ld, (T *)dC)
-    switch (s.G) {
-        case 2: SX_HOSTC(2); break;
-        case 4: SX_HOSTC(4); break;
-        case 8: SX_HOSTC(8); break;
-        default: SX_HOSTC(16); break;
+    if (c->host_fused != 1) {  // -1 (auto) / 2: the whole call as ONE kernel, where its grid is resident at once
+        bool one = false;
+#define SX_HOST1(GG)                                                                                           \
+    rc = strict ? launch_edge_host<T, GG, true>(c, ep, N, alpha, (const T *)dB, beta, (T *)dC, &one)           \
+                : launch_edge_host<T, GG, false>(c, ep, N, alpha, (const T *)dB, beta, (T *)dC, &one)
+        switch (s.G) {
+            case 2: SX_HOST1(2); break;
+            case 4: SX_HOST1(4); break;
+            case 8: SX_HOST1(8); break;
+            default: SX_HOST1(16); break;
+        }
+#undef SX_HOST1
+        if (rc) return rc;
+        if (one) {
+            *done = true;
+            return SX_OK;
+        }
     }
+    // Column pipeline: the columns of C are independent and the caller's arrays are column-major, so the
+    // call runs as `groups` (staging, SpMM) pairs over consecutive column groups, all launched as
+    // programmatic dependents of one another.  Group g's results leave over PCIe while group g+1's B and
+    // C_in columns arrive: the two directions of the link overlap instead of taking turns.  Every element
+    // of C sees the same chain of operations as in one pass.
+    int groups = c->host_groups > 0 ? c->host_groups : 1;  // measured: every further launch costs more than the overlap buys
+    int gw = (N + groups - 1) / groups;
+    gw = std::max(VEC, (gw + VEC - 1) / VEC * VEC);  // a group starts on a 16-byte boundary of the image row
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    for (int n0 = 0; n0 < N; n0 += gw) {
+        const int n = std::min(gw, N - n0);
+        const int wcols = n0 + n >= N ? (int)c->ld - n0 : n;  // the last group zero-fills the image's padding columns
+        const int64_t tcol = (wcols + 31) / 32;
+        if (tB * tcol > 0) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(tB * tcol));
+            cfg.blockDim = dim3(32, 8);
+            cfg.stream = c->stream;
+            cfg.attrs = at;
+            cfg.numAttrs = (n0 > 0 && c->pdl != 0) ? 1 : 0;  // the first one is an ordinary launch: it orders the call behind the stream
+            const T *src = (const T *)dB + (size_t)n0 * (size_t)c->K;
+            T *dst = (T *)c->B.p + n0;
+            if (vec)
+                SX_CUDA(cudaLaunchKernelEx(&cfg, sx::colmajor_to_rowmajor_pair_kernel<T, VEC>, (int64_t)c->K, (int64_t)0, n, src, src, dst, dst,
+                                           (int64_t)c->ld, (int)tcol, tB * tcol, wcols));
+            else
+                SX_CUDA(cudaLaunchKernelEx(&cfg, sx::colmajor_to_rowmajor_pair_kernel<T, 1>, (int64_t)c->K, (int64_t)0, n, src, src, dst, dst,
+                                           (int64_t)c->ld, (int)tcol, tB * tcol, wcols));
+            c->launches++;
+        }
+        const T *Bg = (const T *)c->B.p + n0;
+        T *Cg = (T *)dC + (size_t)n0 * (size_t)c->M;
+#define SX_HOSTC(GG)                                                                                                        \
+    rc = strict ? launch_edge<T, GG, true, true>(c, ep, n, alpha, Bg, c->ld, beta, nullptr, nullptr, c->ld, Cg) \
+                : launch_edge<T, GG, false, true>(c, ep, n, alpha, Bg, c->ld, beta, nullptr, nullptr, c->ld, Cg)
+        switch (s.G) {
+            case 2: SX_HOSTC(2); break;
+            case 4: SX_HOSTC(4); break;
+            case 8: SX_HOSTC(8); break;
+            default: SX_HOSTC(16); break;
+        }
 #undef SX_HOSTC
+        if (rc) return rc;
+    }
     if (rc) return rc;
     *done = true;
     return SX_OK;
@@ -1423,8 +1581,15 @@ int spmm_host(sx_ctx *c, int N, T alpha, const T *B, T beta, T *C, int rp_time, 
             bool done = false;
             if ((rc = spmm_host_fused<T>(c, N, alpha, dB, beta, dC, &done))) return rc;
             if (done) {
-                c->last_path = 2;
-                return finish_stream(c, nullptr);
+                c->last_path = c->last_kernel / 10000 == 10 ? 3 : 2;
+                if ((rc = finish_stream(c, nullptr))) return rc;
+                if (c->host_flag && *c->host_flag) {  // a block of the one-kernel call gave up waiting for the others
+                    *c->host_flag = 0;
+                    c->host_counters.release();
+                    c->exchange_timeouts_host++;
+                    return fail(SX_ERR_STATE, "the one-kernel host call timed out waiting for its own blocks (is another kernel holding the GPU?)");
+                }
+                return SX_OK;
             }
         }
         if ((rc = set_columns(c, N))) return rc;
@@ -1440,10 +1605,10 @@ int spmm_host(sx_ctx *c, int N, T alpha, const T *B, T beta, T *C, int rp_time, 
             dim3 block(32, 8), grid((unsigned)((tB + tC) * tcol));
             if (vec)
                 sx::colmajor_to_rowmajor_pair_kernel<T, VEC><<<grid, block, 0, c->stream>>>(
-                    c->K, c->M, N, (const T *)dB, (const T *)dC, (T *)c->B.p, (T *)c->Cin.p, c->ld, (int)tcol, tB * tcol);
+                    c->K, c->M, N, (const T *)dB, (const T *)dC, (T *)c->B.p, (T *)c->Cin.p, c->ld, (int)tcol, tB * tcol, (int)c->ld);
             else
                 sx::colmajor_to_rowmajor_pair_kernel<T, 1><<<grid, block, 0, c->stream>>>(
-                    c->K, c->M, N, (const T *)dB, (const T *)dC, (T *)c->B.p, (T *)c->Cin.p, c->ld, (int)tcol, tB * tcol);
+                    c->K, c->M, N, (const T *)dB, (const T *)dC, (T *)c->B.p, (T *)c->Cin.p, c->ld, (int)tcol, tB * tcol, (int)c->ld);
             c->launches++;
             SX_CUDA(cudaGetLastError());
         }
@@ -1528,6 +1693,7 @@ int sx_create(int device, sx_ctx **out) {
     if (!c) return fail(SX_ERR_NOMEM, "out of host memory");
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    if (const char *e = std::getenv("SX_HOST_DEPTH")) c->host_depth = std::atoi(e);
     cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
@@ -1546,8 +1712,10 @@ int sx_destroy(sx_ctx *c) {
     sx_internal_images_forget(c);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (DevBuf *b : {&c->rowptr, &c->colidx, &c->val, &c->split_row, &c->split_seg_ptr, &c->seg_begin,
-                      &c->seg_end, &c->partial, &c->sync_words, &c->wblocks, &c->B, &c->Cin, &c->Cout, &c->stage})
+                      &c->seg_end, &c->partial, &c->sync_words, &c->wblocks, &c->B, &c->Cin, &c->Cout, &c->stage,
+                      &c->host_counters})
         b->release();
+    if (c->host_flag) cudaFreeHost(c->host_flag);
     drop_plans(c);
     drop_edge_plans(c);
     drop_tiles(c);
@@ -1603,6 +1771,14 @@ int sx_set_option(sx_ctx *c, int option, int64_t value) {
             if (c->rest) c->rest->segments_dirty = true;
             for (sx_ctx *k : c->wins) k->segments_dirty = true;
             return SX_OK;
+        case SX_OPT_HOST_GROUPS:
+            if (value < 0 || value > 64) return fail(SX_ERR_INVALID, "SX_OPT_HOST_GROUPS is 0 (auto) or 1..64");
+            c->host_groups = (int)value;
+            return SX_OK;
+        case SX_OPT_PANEL_COLS:
+            if (value < 0 || value > 4096 || value % 8) return fail(SX_ERR_INVALID, "SX_OPT_PANEL_COLS is 0 (auto) or a multiple of 8 columns");
+            c->panel_cols = (int)value;
+            return SX_OK;
         case SX_OPT_AUTOTUNE:
             if (value != 0 && value != 1) return fail(SX_ERR_INVALID, "SX_OPT_AUTOTUNE is 0 or 1");
             c->autotune = (int)value;
@@ -1618,7 +1794,7 @@ int sx_set_option(sx_ctx *c, int option, int64_t value) {
             c->pdl = (int)value;
             return SX_OK;
         case SX_OPT_HOST_FUSED:
-            if (value < -1 || value > 1) return fail(SX_ERR_INVALID, "SX_OPT_HOST_FUSED is -1 (auto), 0 or 1");
+            if (value < -1 || value > 2) return fail(SX_ERR_INVALID, "SX_OPT_HOST_FUSED is -1 (auto), 0, 1 or 2");
             c->host_fused = (int)value;
             return SX_OK;
         case SX_OPT_PREFETCH:
@@ -1673,6 +1849,7 @@ int sx_get_info(sx_ctx *c, int what, int64_t *value) {
                 SX_CUDA(cudaMemcpy(&w, (const unsigned int *)c->sync_words.p + 1, 4, cudaMemcpyDeviceToHost));
                 *value = w;
             }
+            *value += c->exchange_timeouts_host;  // ... and the one-kernel host call's waits
             return SX_OK;
         }
         case SX_INFO_EDGE_BLOCKS: *value = c->last_edge_plan ? c->last_edge_plan->nblocks : 0; return SX_OK;
@@ -1706,6 +1883,14 @@ int sx_stage_B_f32(sx_ctx *c, int N, const float *B) { return stage_dense<float>
 int sx_stage_B_f64(sx_ctx *c, int N, const double *B) { return stage_dense<double>(c, N, B, true); }
 int sx_stage_C_f32(sx_ctx *c, int N, const float *C) { return stage_dense<float>(c, N, C, false); }
 int sx_stage_C_f64(sx_ctx *c, int N, const double *C) { return stage_dense<double>(c, N, C, false); }
+int sx_spmm_device_batch_f32(sx_ctx *c, int N, int nb, float alpha, const float *dB, int64_t ldb, int64_t strideB, float beta,
+                             const float *dCin, float *dCout, int64_t ldc, int64_t strideC) {
+    return spmm_device_batch<float>(c, N, nb, alpha, dB, ldb, strideB, beta, dCin, dCout, ldc, strideC);
+}
+int sx_spmm_device_batch_f64(sx_ctx *c, int N, int nb, double alpha, const double *dB, int64_t ldb, int64_t strideB, double beta,
+                             const double *dCin, double *dCout, int64_t ldc, int64_t strideC) {
+    return spmm_device_batch<double>(c, N, nb, alpha, dB, ldb, strideB, beta, dCin, dCout, ldc, strideC);
+}
 int sx_launch_f32(sx_ctx *c, float alpha, float beta, int rp_time, double *ns) { return launch<float>(c, alpha, beta, rp_time, ns); }
 int sx_launch_f64(sx_ctx *c, double alpha, double beta, int rp_time, double *ns) { return launch<double>(c, alpha, beta, rp_time, ns); }
 int sx_fetch_C_f32(sx_ctx *c, float *C) { return fetch_C<float>(c, C); }

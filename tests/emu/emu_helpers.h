@@ -72,3 +72,12 @@ __device__ __forceinline__ void cp_async_wait_all() {}
 __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t *p) { return std::atomic_ref<const uint32_t>(*p).load(); }
 __device__ __forceinline__ void st_relaxed_sys(uint32_t *p, uint32_t v) { std::atomic_ref<uint32_t>(*p).store(v); }
 __device__ __forceinline__ void fence_acq_rel_sys() {}
+__device__ __forceinline__ void cp_async_elem(float *smem_dst, const float *gsrc) { *smem_dst = *gsrc; }
+__device__ __forceinline__ void cp_async_elem(double *smem_dst, const double *gsrc) { *smem_dst = *gsrc; }
+__device__ __forceinline__ void cp_async_commit() {}
+__device__ __forceinline__ void cp_async_wait_pending(int n) {
+    if (n < 0 || n > 7) { std::fprintf(stderr, "emu: cp.async.wait_group %d\n", n); std::abort(); }
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) { return std::atomic_ref<const uint32_t>(*p).load(); }
+__device__ __forceinline__ float4 ld_l2(const float4 *p) { return *p; }
+__device__ __forceinline__ double2 ld_l2(const double2 *p) { return *p; }

@@ -159,7 +159,8 @@ def test_host_facing_call_with_C_carried_by_the_kernel(eng, dtype, M, K, N):
         assert eng.spmm(N, dtype(0.85), hB, dtype(-2.06), hC, want_ns=False) is None
         fused = N * np.dtype(dtype).itemsize <= 256 and (M + K) * N * np.dtype(dtype).itemsize <= (3 << 19)   # SX_OPT_ZEROCOPY_BYTES
         if fused:
-            assert eng.info(sx.INFO_HOST_PATH) == 2 and eng.info(sx.INFO_LAST_KERNEL) // 10000 == 9
+            # 3 / family 10: the whole call as one kernel (its grid is resident at once); 2 / family 9: two launches
+            assert (eng.info(sx.INFO_HOST_PATH), eng.info(sx.INFO_LAST_KERNEL) // 10000) in ((3, 10), (2, 9))
         assert np.array_equal(bits(np.asarray(hC)), bits(ref)), rep
     hC[:] = Cin
     zero_copy = (M + K) * N * np.dtype(dtype).itemsize <= (3 << 19)
@@ -180,6 +181,84 @@ def test_host_facing_call_on_the_canned_run(eng, golden):
     hB, hC = sx.pinned_empty(K * 16, np.float32), sx.pinned_empty(M * 16, np.float32)
     hB[:] = B
     hC[:] = Cin
-    eng.spmm(16, run["alpha"], hB, run["beta"], hC, want_ns=False)
-    assert eng.info(sx.INFO_HOST_PATH) == 2
-    assert sha(np.asarray(hC)) == run["C_sha256"]
+    for fused, path in ((-1, 3), (2, 3), (1, 2)):
+        eng.set_option(sx.OPT_HOST_FUSED, fused)
+        hC[:] = Cin
+        eng.spmm(16, run["alpha"], hB, run["beta"], hC, want_ns=False)
+        assert eng.info(sx.INFO_HOST_PATH) == path
+        assert sha(np.asarray(hC)) == run["C_sha256"]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("fused", [1, 2])
+@pytest.mark.parametrize("groups", [1, 2, 3, 4, 8, 64])
+@pytest.mark.parametrize("M,K,N", [(4704, 4704, 16), (997, 1201, 24), (333, 777, 1), (1500, 1400, 10), (9000, 300, 16), (200, 9000, 12)])
+def test_host_facing_call_column_pipeline(eng, dtype, fused, groups, M, K, N):
+    """SX_OPT_HOST_GROUPS: the fused host-facing call pipelined over column groups of the caller's
+    column-major arrays -- inside ONE kernel (SX_OPT_HOST_FUSED = 2: cp.async from host memory, the
+    blocks meet behind a counter per group) or as a chain of (B staging, SpMM) pairs (= 1).  Columns
+    are independent: the same bits for every group count, including counts that do not divide N and
+    more groups than columns; tall and wide shapes (B shares of one row / of many rows per block)."""
+    rp, ci, v = banded_csr(M, K, 150, 20, M + N, dtype)
+    B, Cin = random_dense(M, K, N, M + N + 1, dtype)
+    ref = oracle.spmm_csr(M, N, K, rp, ci, v, dtype(0.85), B, dtype(-2.06), Cin.copy())
+    eng.set_option(sx.OPT_HOST_GROUPS, groups)
+    eng.set_option(sx.OPT_HOST_FUSED, fused)
+    eng.upload_csr(M, K, rp, ci, v)
+    hB, hC = sx.pinned_empty(K * N, dtype), sx.pinned_empty(M * N, dtype)
+    hB[:] = B
+    for rep in range(3):
+        hC[:] = Cin
+        eng.spmm(N, dtype(0.85), hB, dtype(-2.06), hC, want_ns=False)
+        # (1: the matrix does not take the edge-list kernel at all -- wide, hardly any reuse of a staged B row)
+        assert eng.info(sx.INFO_HOST_PATH) in ((3 if fused == 2 else 2), 1)
+        assert K > 4 * M or eng.info(sx.INFO_HOST_PATH) != 1
+        assert np.array_equal(bits(np.asarray(hC)), bits(ref)), rep
+    assert eng.info(sx.INFO_EXCHANGE_TIMEOUTS) == 0
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("kernel", [0, 2])
+@pytest.mark.parametrize("M,K,N,nb", [(4704, 4704, 16, 5), (997, 1201, 8, 3), (70, 64, 4, 17), (600, 600, 40, 2)])
+def test_batched_call_matches_one_call_per_operand(eng, dtype, kernel, M, K, N, nb):
+    """sx_spmm_device_batch_*: nb (B, C_in, C_out) triples with the same A -- one launch on the edge-list
+    kernel (kernel 0 on these banded matrices), one launch per triple otherwise -- every result
+    bit-identical to cpu_spmm_CSR; in place as well."""
+    import torch
+    rp, ci, v = banded_csr(M, K, 150, 20, M + N, dtype)
+    eng.set_option(sx.OPT_KERNEL, kernel)
+    eng.upload_csr(M, K, rp, ci, v)
+    ld = (N + 7) // 8 * 8
+    td = torch.float64 if dtype == np.float64 else torch.float32
+    dev = torch.device("cuda", 0)
+    sB, sC = K * ld + 8, M * ld + 16                      # strides with slack between operands
+    dB = torch.zeros(nb * sB, dtype=td, device=dev)
+    dCin = torch.zeros(nb * sC, dtype=td, device=dev)
+    dCout = torch.full((nb * sC,), 7.0, dtype=td, device=dev)
+    refs = []
+    for b in range(nb):
+        B, Cin = random_dense(M, K, N, 100 * b + N, dtype)
+        refs.append(oracle.spmm_csr(M, N, K, rp, ci, v, dtype(0.85), B, dtype(-2.06), Cin.copy()))
+        Brm = np.zeros((K, ld), dtype); Brm[:, :N] = B.reshape(N, K).T
+        Crm = np.zeros((M, ld), dtype); Crm[:, :N] = Cin.reshape(N, M).T
+        dB[b * sB: b * sB + K * ld] = torch.from_numpy(Brm.ravel()).to(dev)
+        dCin[b * sC: b * sC + M * ld] = torch.from_numpy(Crm.ravel()).to(dev)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    l0 = eng.info(sx.INFO_LAUNCHES)
+    eng.spmm_device_batch(N, nb, dtype(0.85), dB, ld, sB, dtype(-2.06), dCin, dCout, ld, sC)
+    torch.cuda.synchronize()
+    if kernel == 0 and N * np.dtype(dtype).itemsize <= 256:
+        assert eng.info(sx.INFO_LAST_KERNEL) // 10000 == 8 and eng.info(sx.INFO_LAUNCHES) - l0 == 1
+    out = dCout.cpu().numpy()
+    for b in range(nb):
+        got = out[b * sC: b * sC + M * ld].reshape(M, ld)[:, :N].T.ravel()
+        assert np.array_equal(bits(np.ascontiguousarray(got)), bits(refs[b])), b
+        assert np.all(out[b * sC + M * ld: (b + 1) * sC] == 7.0)      # the slack between operands is untouched
+    eng.spmm_device_batch(N, nb, dtype(0.85), dB, ld, sB, dtype(-2.06), dCin, dCin, ld, sC)   # in place
+    torch.cuda.synchronize()
+    out = dCin.cpu().numpy()
+    for b in range(nb):
+        got = out[b * sC: b * sC + M * ld].reshape(M, ld)[:, :N].T.ravel()
+        assert np.array_equal(bits(np.ascontiguousarray(got)), bits(refs[b])), b
+    with pytest.raises(sx.SextansError):
+        eng.spmm_device_batch(N, 2, dtype(0.85), dB, ld, sB, dtype(-2.06), dCin, dCout, ld, 0)
