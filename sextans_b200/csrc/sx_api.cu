@@ -766,6 +766,11 @@ void drop_plans(sx_ctx *c) {
 int get_plan(sx_ctx *c, int budget, Plan **out) {
     for (Plan *p : c->plans)
         if (p->budget == budget) { *out = p; return SX_OK; }
+    {   // a plan is uploaded with allocations and a host sync: not inside a stream capture
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(c->stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone)
+            return fail(SX_ERR_STATE, "the first SpMM of a (matrix, N) builds its plan and cannot be captured into a CUDA graph: run it once before the capture");
+    }
     Plan *p = new (std::nothrow) Plan();
     if (!p) return fail(SX_ERR_NOMEM, "out of host memory");
     p->budget = budget;
@@ -914,6 +919,15 @@ int get_edge_plan(sx_ctx *c, int row_bytes, int elem_bytes, int rows, const Edge
     // staging pays when a staged B row serves at least two nonzeros (forced with SX_OPT_KERNEL = 5:
     // any matrix that can be planned)
     if (c->nnz == 0 || (c->kernel != 5 && c->edge_cols_per_nnz > 0.5)) return SX_OK;
+    {   // the plan is built on the host from the device's copy of A: not inside a stream capture
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(c->stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) {
+            c->edge_plans.pop_back();
+            delete p;
+            *out = nullptr;
+            return fail(SX_ERR_STATE, "the first SpMM of a (matrix, N) builds its plan and cannot be captured into a CUDA graph: run it once before the capture");
+        }
+    }
     std::vector<int32_t> ci((size_t)c->nnz);
     SX_CUDA(cudaMemcpyAsync(ci.data(), c->colidx.p, (size_t)c->nnz * 4, cudaMemcpyDeviceToHost, c->stream));
     SX_CUDA(cudaStreamSynchronize(c->stream));

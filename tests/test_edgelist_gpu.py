@@ -262,3 +262,41 @@ def test_batched_call_matches_one_call_per_operand(eng, dtype, kernel, M, K, N, 
         assert np.array_equal(bits(np.ascontiguousarray(got)), bits(refs[b])), b
     with pytest.raises(sx.SextansError):
         eng.spmm_device_batch(N, 2, dtype(0.85), dB, ld, sB, dtype(-2.06), dCin, dCout, ld, 0)
+
+
+@pytest.mark.parametrize("kernel", [0, 2])
+def test_first_call_inside_a_graph_capture_is_refused_not_broken(eng, kernel):
+    """The first SpMM of a (matrix, N) builds its plan on the host (allocations, a sync): inside a
+    stream capture the library says so (SX_ERR_STATE) before touching the stream, the capture stays
+    valid, and after one call outside a capture the same launch is captured and replayed bit-exact."""
+    import torch
+    M, K, N, dtype = 1000, 1000, 16, np.float64
+    rp, ci, v = banded_csr(M, K, 150, 20, 3, dtype)
+    B, Cin = random_dense(M, K, N, 4, dtype)
+    ref = oracle.spmm_csr(M, N, K, rp, ci, v, dtype(0.85), B, dtype(-2.06), Cin.copy())
+    eng.set_option(sx.OPT_KERNEL, kernel)
+    eng.upload_csr(M, K, rp, ci, v)
+    dev = torch.device("cuda", 0)
+    s = torch.cuda.Stream(device=dev)
+    eng.set_stream(s.cuda_stream)
+    ld = 16
+    dB = torch.from_numpy(np.ascontiguousarray(B.reshape(N, K).T)).to(dev)
+    dCin = torch.from_numpy(np.ascontiguousarray(Cin.reshape(N, M).T)).to(dev)
+    dCout = torch.zeros(M * ld, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        with pytest.raises(sx.SextansError, match="cannot be captured"):
+            eng.spmm_device(N, 0.85, dB, ld, -2.06, dCin, dCout, ld)
+    with torch.cuda.stream(s):
+        eng.spmm_device(N, 0.85, dB, ld, -2.06, dCin, dCout, ld)
+    s.synchronize()
+    dCout.zero_()
+    torch.cuda.synchronize()
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g2, stream=s):
+        eng.spmm_device(N, 0.85, dB, ld, -2.06, dCin, dCout, ld)
+    g2.replay()
+    torch.cuda.synchronize()
+    got = dCout.cpu().numpy().reshape(M, ld)[:, :N].T.ravel()
+    assert np.array_equal(bits(np.ascontiguousarray(got)), bits(ref))
