@@ -15,12 +15,17 @@ the one C4 and the one C5 matrix over nnz-balanced row blocks (sx_partition_rows
 kernel-only and including the broadcast of B, per-rank nnz imbalance, parity on every rank.
 
 Own arm, per rank (one process per GPU):
-  value : K steps between CUDA events on the launching stream, replayed as CUDA graphs.  The
+  value : steps between CUDA events on the launching stream, replayed as a CUDA graph.  The
           operands exist in R independent device copies (R x bytes > 2.2 x the 126 MB L2) and
           step i uses copy i mod R, across replays too, so every step finds its operands in
-          HBM ("inputs larger than L2"; no flush kernel in the timed region).  The K-step
-          replay is repeated until the timed region is >= 50 ms; ms_per_step is the MEDIAN
-          repetition / K (max over ranks per repetition).
+          HBM ("inputs larger than L2"; no flush kernel in the timed region).  One graph holds
+          every distinct K-step window of the rotation back to back (S = W*K steps, a whole
+          number of passes over the copies): the steady state of a long chain of dependent
+          SpMMs.  The replay is repeated until the timed region is >= 50 ms; ms_per_step is the
+          MEDIAN repetition / S (max over ranks per repetition).  `run.k_step_graphs` holds
+          the same steps replayed as separate K-step graphs (every K steps then pay a graph
+          launch), what earlier records of this bench reported.
+  batched: the headline workload through sx_spmm_device_batch_* (20 operand triples per launch).
   e2e   : the same step through the host-facing C-ABI call sx_spmm_* with pinned host B and C
           (column-major, as the host program holds them), H2D + kernels + D2H inside the timed
           region; at N>1 through ShardedSpMM (B on rank 0's host, exchange, C blocks back).
@@ -414,12 +419,17 @@ class Case:
         self.engines, self.dB, self.dCin, self.dCout = [], [], [], []
 
 
-def time_steps(step, R, K, warmup, stream, min_region_ms, use_graph, world, dev, max_reps=4000, extra_streams=()):
-    """Warm up, then repeat a K-step replay until the timed region is >= min_region_ms; every
-    repetition has its own event pair on `stream`.  Steps are numbered consecutively over warm-up
-    and all repetitions (copy = step mod R), so the rotation through the R copies never restarts.
-    Graph mode captures one graph per distinct K-step window of the rotation.
-    -> dict(ms_median, ms_min, ms_mean (per step, max over ranks per repetition), reps, region_ms, graphs, nwarm)"""
+def time_steps(step, R, K, warmup, stream, min_region_ms, use_graph, world, dev, max_reps=4000, extra_streams=(), chain=True):
+    """Warm up, then repeat a replay until the timed region is >= min_region_ms; every repetition
+    has its own event pair on `stream`.  Steps are numbered consecutively over warm-up and all
+    repetitions (copy = step mod R), so the rotation through the R copies never restarts.
+    Graph mode, chain=True: ONE graph holds every distinct K-step window of the rotation back to
+    back (W windows = W*K steps, a whole number of passes over the R copies) and a repetition is one
+    replay of it -- the steady state of a long chain of dependent SpMMs.  chain=False: one graph per
+    K-step window, a repetition is one K-step replay (every K steps pay a graph launch and lose the
+    overlap of the next launch's prologue across the graph boundary).
+    -> dict(ms_median, ms_min, ms_mean (per step, max over ranks per repetition), reps, region_ms, graphs,
+            steps_per_rep, nwarm)"""
     import torch
     import torch.distributed as dist
 
@@ -436,16 +446,18 @@ def time_steps(step, R, K, warmup, stream, min_region_ms, use_graph, world, dev,
     barrier()
     base = nwarm
     graphs = None
+    S = K                                            # steps per repetition
     if use_graph:
-        ngraphs = min(R // math.gcd(R, K) if R > 1 else 1, 64)
+        nwin = min(R // math.gcd(R, K) if R > 1 else 1, 64)
+        per_graph = nwin if chain else 1             # K-step windows per graph
         graphs = []
-        for g in range(ngraphs):
+        for g in range(nwin // per_graph):
             gr = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gr, stream=stream):
                 for x in extra_streams:
                     x.wait_stream(stream)            # fork
-                for i in range(K):
-                    step(base + g * K + i)
+                for i in range(per_graph * K):
+                    step(base + g * per_graph * K + i)
                 for x in extra_streams:
                     stream.wait_stream(x)            # join
             graphs.append(gr)
@@ -453,7 +465,8 @@ def time_steps(step, R, K, warmup, stream, min_region_ms, use_graph, world, dev,
             for gr in graphs:                        # one untimed pass over the whole rotation
                 gr.replay()
         barrier()
-        base += ngraphs * K
+        base += nwin * K
+        S = per_graph * K
 
     def one_rep(r):
         if graphs is not None:
@@ -486,9 +499,9 @@ def time_steps(step, R, K, warmup, stream, min_region_ms, use_graph, world, dev,
     if world > 1:
         dist.all_reduce(per_rep, op=dist.ReduceOp.MAX)
     per_rep = per_rep.cpu().numpy()
-    return {"ms_median": float(np.median(per_rep)) / K, "ms_min": float(per_rep.min()) / K,
-            "ms_mean": float(per_rep.mean()) / K, "reps": reps, "region_ms": float(per_rep.sum()),
-            "graphs": 0 if graphs is None else len(graphs), "nwarm": nwarm}
+    return {"ms_median": float(np.median(per_rep)) / S, "ms_min": float(per_rep.min()) / S,
+            "ms_mean": float(per_rep.mean()) / S, "reps": reps, "region_ms": float(per_rep.sum()),
+            "graphs": 0 if graphs is None else len(graphs), "steps_per_rep": S, "nwarm": nwarm}
 
 
 def parity(case, w, rows0=0, rows1=None, threads=None):
@@ -735,10 +748,15 @@ def run_native(args):
     l0 = case.launches()
     t = time_steps(step, R, K, args.warmup, stream, args.min_region_ms, use_graph, world, dev, extra_streams=extra_streams)
     # launches in the timed region: a captured graph holds the launches of its K steps and is replayed once per repetition
-    enq_steps = t["nwarm"] + (t["graphs"] * K if use_graph else (3 + t["reps"]) * K)
+    S = t["steps_per_rep"]
+    enq_steps = t["nwarm"] + (t["graphs"] * S if use_graph else (3 + t["reps"]) * K)
     per_step = (case.launches() - l0) / max(1, enq_steps)
-    launches_dev = int(round(per_step * K * t["reps"]))
+    launches_dev = int(round(per_step * S * t["reps"]))
     kern_ms = t["ms_median"]
+    # the same steps replayed as separate K-step graphs (what round 1 and the first half of round 2 reported)
+    t_k = time_steps(step, R, K, 0, stream, min(args.min_region_ms, 20.0), True, world, dev, extra_streams=extra_streams, chain=False) if use_graph and S > K else None
+    if t_k is not None:
+        launches_dev += int(round(per_step * K * t_k["reps"]))
     timeouts = case.engines[0].info(sx.INFO_EXCHANGE_TIMEOUTS) if world > 1 else 0
 
     # the same on ONE copy (L2 warm when the working set fits), for comparison
@@ -860,8 +878,12 @@ def run_native(args):
                     "l2": "warm (--no-flush)" if args.no_flush else (
                         f"cold: {R} device copies of A/B/C ({R * alg_bytes / 1e6:.0f} MB > 2 x 126 MB L2), step i uses copy i mod {R} across all replays"
                         if R > 1 else f"cold: one copy is {alg_bytes / 1e6:.0f} MB > 2 x L2"),
-                    "timed": f"{t['reps']} repetitions x {K} steps = {t['region_ms']:.1f} ms; ms_per_step = median repetition / {K} (min {t['ms_min'] * 1e3:.3f} us, mean {t['ms_mean'] * 1e3:.3f} us)",
-                    "launch": f"{t['graphs']} CUDA graphs of {K} steps" if use_graph else "one by one",
+                    "timed": f"{t['reps']} repetitions x {S} steps = {t['region_ms']:.1f} ms; ms_per_step = median repetition / {S} (min {t['ms_min'] * 1e3:.3f} us, mean {t['ms_mean'] * 1e3:.3f} us)",
+                    "launch": (f"one CUDA graph of {S} steps = {S // K} windows of K = {K} steps back to back (a whole number of passes over the copies); one replay per repetition"
+                               if use_graph and S > K else f"{t['graphs']} CUDA graphs of {K} steps" if use_graph else "one by one"),
+                    "k_step_graphs": None if t_k is None else {
+                        "ms_per_step": t_k["ms_median"], "reps": t_k["reps"],
+                        "note": f"the same steps as separate graphs of K = {K} steps, one replay per repetition: every K steps pay a graph launch and the first step of a graph cannot overlap its prologue with the previous kernel"},
                     "partition": "1 row block" if world == 1 else f"{world} stacked copies, one row block per GPU",
                     "exchange": exchange},
             "gflops_ref_formula": 2.0 * (nnz + M) * N * world / (kern_ms * 1e-3) / 1e9,

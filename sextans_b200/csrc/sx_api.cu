@@ -185,6 +185,7 @@ struct sx_ctx {
     uint32_t *host_flag = nullptr, *host_flag_dev = nullptr;
     struct Occ { const void *kern; size_t smem; int per_sm; };
     std::vector<Occ> host_occ;
+    int host_coop = 1;   // experiment knob (env SX_HOST_COOP=0): launch the one-kernel call without the cooperative attribute
     int host_depth = 0;  // experiment knob (env SX_HOST_DEPTH): column groups requested ahead in the one-kernel call
     int host_groups = 0; // SX_OPT_HOST_GROUPS: column groups of the fused host-facing call (0 auto)
     int panel_cols = 0;  // SX_OPT_PANEL_COLS: 0 auto, else columns per pass
@@ -1458,11 +1459,23 @@ int launch_edge_host(sx_ctx *c, const EdgePlan *ep, int N, T alpha, const T *Bh,
     gw = std::max(E, (gw + E - 1) / E * E);  // a group starts on a 16-byte boundary of the image row
     while ((N + gw - 1) / gw > sx::SX_HOST_MAX_GROUPS) gw += E;
     const uint32_t target = c->host_base + (uint32_t)ep->nblocks;
-    kern<<<(unsigned)ep->nblocks, THREADS, smem, c->stream>>>(
-        (const int4 *)ep->blocks.p, (const int *)ep->cols.p, (const int *)c->rowptr.p, (const uint16_t *)ep->lcol.p,
-        (const T *)c->val.p, Bh, (T *)c->B.p, (uint32_t)(c->ld / E), Ch, (int64_t)c->M, (int64_t)c->K, N, alpha, beta, gw,
-        (uint32_t *)c->host_counters.p, target, c->host_flag_dev, (uint32_t)tile_off, tile_ld, (uint32_t)share_off, share_ld,
-        c->host_depth > 0 ? std::min(c->host_depth, sx::SX_HOST_MAX_GROUPS) : 1);
+    // a cooperative launch: the grid is scheduled only as a whole, so two such calls on one GPU (two contexts, two
+    // host threads) cannot each hold half of the SMs and wait for the other half
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ep->nblocks);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = c->host_coop != 0 ? 1 : 0;
+    SX_CUDA(cudaLaunchKernelEx(&cfg, kern, (const int4 *)ep->blocks.p, (const int *)ep->cols.p, (const int *)c->rowptr.p,
+                               (const uint16_t *)ep->lcol.p, (const T *)c->val.p, Bh, (T *)c->B.p, (uint32_t)(c->ld / E), Ch,
+                               (int64_t)c->M, (int64_t)c->K, N, alpha, beta, gw, (uint32_t *)c->host_counters.p, target,
+                               c->host_flag_dev, (uint32_t)tile_off, tile_ld, (uint32_t)share_off, share_ld,
+                               c->host_depth > 0 ? std::min(c->host_depth, sx::SX_HOST_MAX_GROUPS) : 1));
     SX_CUDA(cudaGetLastError());
     c->host_base = target;
     c->launches++;
@@ -1708,6 +1721,7 @@ int sx_create(int device, sx_ctx **out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     if (const char *e = std::getenv("SX_HOST_DEPTH")) c->host_depth = std::atoi(e);
+    if (const char *e = std::getenv("SX_HOST_COOP")) c->host_coop = std::atoi(e);
     cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
