@@ -799,7 +799,7 @@ def run_native(args):
 
     def e2e_call():
         if sharded is not None:
-            sharded.spmm(N, ALPHA, hB if rank == 0 else None, BETA, hC)
+            sharded.spmm(N, ALPHA, hB if rank == 0 else None, BETA, hC, want_ns=False)
         else:
             eng.spmm(N, ALPHA, hB, BETA, hC, want_ns=False)     # kernel_ns = NULL: nobody needs the kernel-only time here
     for _ in range(3):

@@ -251,6 +251,13 @@ int sx_launch_f32(sx_ctx *ctx, float alpha, float beta, int rp_time, double *ker
 int sx_launch_f64(sx_ctx *ctx, double alpha, double beta, int rp_time, double *kernel_ns);
 int sx_fetch_C_f32(sx_ctx *ctx, float *C_colmajor);
 int sx_fetch_C_f64(sx_ctx *ctx, double *C_colmajor);
+/* One blocking call on the B image the context already holds -- staged by sx_stage_B_*, pushed by a
+ * peer (sx_spmm_expect_push) or filled by a collective through sx_device_B -- and the caller's
+ * column-major host C (M x N, in/out): what a rank that does NOT hold the host B calls in the
+ * row-block path.  Page-locked C on a matrix that runs the edge-list kernel: one launch, C never
+ * staged on the device (SX_OPT_HOST_FUSED); otherwise C is staged, multiplied and fetched. */
+int sx_spmm_staged_B_f32(sx_ctx *ctx, int N, float alpha, float beta, float *C);
+int sx_spmm_staged_B_f64(sx_ctx *ctx, int N, double alpha, double beta, double *C);
 /* Device address of the context's staged row-major B (K x ld, ld from SX_INFO_LD):
  * the buffer a collective (NCCL broadcast over NVLink) fills on the non-root
  * ranks.  Allocates it for N columns if needed. */

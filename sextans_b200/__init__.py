@@ -83,6 +83,8 @@ def lib():
         "sx_spmm_f64": ([vp, i, C.c_double, vp, C.c_double, vp, i, _PD], i),
         "sx_stage_B_f32": ([vp, i, vp], i), "sx_stage_B_f64": ([vp, i, vp], i),
         "sx_stage_C_f32": ([vp, i, vp], i), "sx_stage_C_f64": ([vp, i, vp], i),
+        "sx_spmm_staged_B_f32": ([vp, i, C.c_float, C.c_float, vp], i),
+        "sx_spmm_staged_B_f64": ([vp, i, C.c_double, C.c_double, vp], i),
         "sx_launch_f32": ([vp, C.c_float, C.c_float, i, _PD], i),
         "sx_launch_f64": ([vp, C.c_double, C.c_double, i, _PD], i),
         "sx_fetch_C_f32": ([vp, vp], i), "sx_fetch_C_f64": ([vp, vp], i),
@@ -444,6 +446,14 @@ class Engine:
                                                   _host_ptr(C_inout), rp_time,
                                                   C.byref(ns) if want_ns else None))
         return ns.value if want_ns else None
+
+    def spmm_staged_B(self, N, alpha, beta, C_inout):
+        """One blocking SpMM on the B image the context already holds (stage_B, a peer's push, a
+        broadcast into device_B) and the host C (column-major 1-D, in place)."""
+        suf, ct, _ = _suffix(self.dtype)
+        if C_inout.dtype != self.dtype or not C_inout.flags.c_contiguous or C_inout.size != self.M * N:
+            raise ValueError("C must be a contiguous array of M*N elements of the matrix dtype")
+        _check(getattr(self._L, f"sx_spmm_staged_B_{suf}")(self._ctx, N, ct(alpha), ct(beta), _host_ptr(C_inout)))
 
     def sextans_invoke(self, ptr, A_images, B_images, Cin_images, Cout_images, M, K, P_N,
                        alpha_u, beta_u):

@@ -1515,7 +1515,8 @@ int spmm_host_fused(sx_ctx *c, int N, T alpha, const void *dB, T beta, void *dC,
     c->has_C = false;  // C never exists as a device image on this path
     c->win_col0 = 0;
     const bool strict = c->arith == 0;
-    if (c->host_fused != 1) {  // -1 (auto) / 2: the whole call as ONE kernel, where its grid is resident at once
+    if (c->host_fused != 1 && !c->x_ready && !c->p_npeers) {  // -1 (auto) / 2: the whole call as ONE kernel, where its grid is resident at once
+                                                               // (a launch that carries the multi-GPU exchange takes the two-launch form)
         bool one = false;
 #define SX_HOST1(GG)                                                                                           \
     rc = strict ? launch_edge_host<T, GG, true>(c, ep, N, alpha, (const T *)dB, beta, (T *)dC, &one)           \
@@ -1582,6 +1583,59 @@ int spmm_host_fused(sx_ctx *c, int N, T alpha, const void *dB, T beta, void *dC,
     if (rc) return rc;
     *done = true;
     return SX_OK;
+}
+
+// The SpMM with whatever the context's B image holds -- staged by sx_stage_B_*, pushed by a peer (sx_spmm_expect_push)
+// or filled by a collective (sx_device_B) -- and the caller's column-major host C, in place: the receiving ranks' call
+// of the row-block path.  Page-locked C of at most SX_OPT_ZEROCOPY_BYTES on a matrix that runs the edge-list kernel:
+// ONE launch, the kernel reads its C_in tiles from and writes its result tiles to the caller's array (HOSTC); else
+// C is staged, multiplied and fetched.
+template <typename T>
+int spmm_host_deviceB(sx_ctx *c, int N, T alpha, T beta, T *C) {
+    int rc = bind(c);
+    if (rc) return rc;
+    if (!c->has_A) return fail(SX_ERR_STATE, "no matrix uploaded (call sx_upload_csr_* first)");
+    if (c->dtype != DtypeOf<T>::value) return fail(SX_ERR_INVALID, "dtype differs from the uploaded matrix");
+    if (!C) return fail(SX_ERR_INVALID, "null host operand");
+    if (!c->has_B || c->N != N) return fail(SX_ERR_STATE, "no B image for N = %d (sx_stage_B_* / sx_device_B first)", N);
+    void *dC = nullptr;
+    const size_t bytes = (size_t)c->M * (size_t)N * sizeof(T);
+    const int nvec = (N * (int)sizeof(T) + 15) / 16;
+    Shape s;
+    if (c->host_fused != 0 && c->tile_steps == 0 && c->wins.empty() && c->M > 0 && (c->kernel == 0 || c->kernel == 5) &&
+        bytes <= (size_t)c->zerocopy_bytes && pick_shape(nvec, &s) && s.G <= 16 && s.VPL == 1 && (dC = mapped_alias(C))) {
+        const int rows = s.G >= 16 ? 32 : 256 / s.G;
+        const EdgePlan *ep = nullptr;
+        if ((rc = get_edge_plan(c, s.G * 16, (int)sizeof(T), rows, &ep))) return rc;
+        if (ep && ep->usable) {
+            c->win_col0 = 0;
+            const bool strict = c->arith == 0;
+#define SX_HOSTC(GG)                                                                                                                 \
+    rc = strict ? launch_edge<T, GG, true, true>(c, ep, N, alpha, (const T *)c->B.p, c->ld, beta, nullptr, nullptr, c->ld, (T *)dC)  \
+                : launch_edge<T, GG, false, true>(c, ep, N, alpha, (const T *)c->B.p, c->ld, beta, nullptr, nullptr, c->ld, (T *)dC)
+            switch (s.G) {
+                case 2: SX_HOSTC(2); break;
+                case 4: SX_HOSTC(4); break;
+                case 8: SX_HOSTC(8); break;
+                default: SX_HOSTC(16); break;
+            }
+#undef SX_HOSTC
+            if (rc) return rc;
+            c->has_C = false;
+            c->last_path = 2;
+            return finish_stream(c, nullptr);
+        }
+    }
+    if ((rc = stage_dense<T>(c, N, C, false))) return rc;
+    const int64_t key = c->warm_key;   // no untimed warm-up launch here: nobody reads a kernel time
+    rc = spmm_device<T>(c, N, alpha, (const T *)c->B.p, c->ld, beta, (const T *)c->Cin.p, (T *)c->Cout.p, c->ld);
+    c->warm_key = key;
+    if (rc) return rc;
+    if ((rc = c->stage.ensure(std::max<size_t>(bytes, 16)))) return rc;
+    if ((rc = transpose_out(c, c->dtype, c->M, N, c->Cout.p, c->ld, c->stage.p))) return rc;
+    if (bytes) SX_CUDA(cudaMemcpyAsync(C, c->stage.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    c->last_path = 0;
+    return finish_stream(c, nullptr);
 }
 
 // The host-facing call.  Two ways in and out of the device:
@@ -1919,6 +1973,8 @@ int sx_spmm_device_batch_f64(sx_ctx *c, int N, int nb, double alpha, const doubl
                              const double *dCin, double *dCout, int64_t ldc, int64_t strideC) {
     return spmm_device_batch<double>(c, N, nb, alpha, dB, ldb, strideB, beta, dCin, dCout, ldc, strideC);
 }
+int sx_spmm_staged_B_f32(sx_ctx *c, int N, float alpha, float beta, float *C) { return spmm_host_deviceB<float>(c, N, alpha, beta, C); }
+int sx_spmm_staged_B_f64(sx_ctx *c, int N, double alpha, double beta, double *C) { return spmm_host_deviceB<double>(c, N, alpha, beta, C); }
 int sx_launch_f32(sx_ctx *c, float alpha, float beta, int rp_time, double *ns) { return launch<float>(c, alpha, beta, rp_time, ns); }
 int sx_launch_f64(sx_ctx *c, double alpha, double beta, int rp_time, double *ns) { return launch<double>(c, alpha, beta, rp_time, ns); }
 int sx_fetch_C_f32(sx_ctx *c, float *C) { return fetch_C<float>(c, C); }

@@ -231,11 +231,24 @@ class ShardedSpMM:
             return None
         return self._xch[3]
 
-    def spmm(self, N, alpha, B_colmajor_root, beta, C_block_colmajor, src=0, rp_time=1):
+    def spmm(self, N, alpha, B_colmajor_root, beta, C_block_colmajor, src=0, rp_time=1, want_ns=True):
         """B_colmajor_root: the K x N column-major host B on rank ``src`` (ignored elsewhere).
-        C_block_colmajor: this rank's block (in/out).  Returns the local kernel ns."""
+        C_block_colmajor: this rank's block (in/out).  Returns the local kernel ns; with
+        ``want_ns=False`` (nobody reads the kernel-only time) and a pushed B the call is the
+        engine's host-facing call itself on every rank -- the holder's sx_spmm_* (B staging + an
+        SpMM kernel that carries the push and C), the others' sx_spmm_staged_B_* (one kernel that
+        waits for the push and carries C) -- and None is returned."""
         import torch
         x = self._exchange_for(N, src)
+        if x is not None and not want_ns and rp_time <= 1:
+            x.before_step(0)
+            if self.rank == src:
+                self.engine.spmm(N, alpha, B_colmajor_root, beta, C_block_colmajor, want_ns=False)
+            else:
+                self.engine.device_B(N)                    # marks B as present: the push fills it
+                self.engine.spmm_staged_B(N, alpha, beta, C_block_colmajor)
+            self.last_exchange = "push"
+            return None
         if x is not None:
             if self.rank == src:
                 self.engine.stage_B(N, B_colmajor_root)    # H2D + layout change on the root only

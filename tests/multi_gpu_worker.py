@@ -113,6 +113,27 @@ def main():
     sh.close()
     if rank == 0:
         print("OK ShardedSpMM with N = 8, 40, 8: the push exchange follows the B image, bitwise", flush=True)
+    # the host-facing call on every rank (want_ns=False): the holder's sx_spmm_* carries the push and its C block,
+    # the others' sx_spmm_staged_B_* waits for the push and carries theirs; page-locked operands, FEM-type matrix
+    M, K, nnz, rp, ci, v = sx.load_mtx(mtx_path("nasa4704"), np.float64)
+    sh = ShardedSpMM(M, K, rp, ci, v, local)
+    N = 16
+    hB = sx.pinned_empty(K * N, np.float64)
+    hC = sx.pinned_empty(sh.block.rows * N, np.float64)
+    for rep in range(4):
+        B, Cin = random_dense(M, K, N, 70 + rep, np.float64)
+        hB[:] = B
+        hC[:] = sh.block.take_C(Cin, N)
+        assert sh.spmm(N, 0.85, hB if rank == 0 else None, -2.06, hC, want_ns=False) is None
+        assert sh.last_exchange == "push" and sh.engine.info(sx.INFO_HOST_PATH) == 2
+        assert sh.engine.info(sx.INFO_EXCHANGE_TIMEOUTS) == 0
+        full = sh.gather(np.asarray(hC).copy(), N, dst=0)
+        if rank == 0:
+            ref = oracle.spmm_csr(M, N, K, rp, ci, v, 0.85, B, -2.06, Cin.copy())
+            assert full.tobytes() == ref.tobytes(), rep
+    sh.close()
+    if rank == 0:
+        print("OK ShardedSpMM host-facing call on every rank (push carried by the holder's SpMM, C by every rank's kernel): bitwise", flush=True)
     eng.close()
     dist.barrier()
     dist.destroy_process_group()

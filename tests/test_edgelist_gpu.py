@@ -300,3 +300,28 @@ def test_first_call_inside_a_graph_capture_is_refused_not_broken(eng, kernel):
     torch.cuda.synchronize()
     got = dCout.cpu().numpy().reshape(M, ld)[:, :N].T.ravel()
     assert np.array_equal(bits(np.ascontiguousarray(got)), bits(ref))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("pinned", [True, False])
+@pytest.mark.parametrize("M,K,N", [(4704, 4704, 16), (997, 1201, 24), (333, 777, 1), (200, 9000, 12)])
+def test_spmm_on_the_staged_B_image_with_host_C(eng, dtype, pinned, M, K, N):
+    """sx_spmm_staged_B_*: B already on the device (sx_stage_B_*), C the caller's host array -- one
+    launch with C carried by the kernel when C is page-locked and the matrix runs the edge-list
+    kernel, staged / multiplied / fetched otherwise.  Bitwise the oracle either way; B stays staged."""
+    rp, ci, v = banded_csr(M, K, 150, 20, M + N, dtype)
+    B, Cin = random_dense(M, K, N, M + N + 2, dtype)
+    ref = oracle.spmm_csr(M, N, K, rp, ci, v, dtype(0.85), B, dtype(-2.06), Cin.copy())
+    eng.upload_csr(M, K, rp, ci, v)
+    with pytest.raises(sx.SextansError):
+        eng.spmm_staged_B(N, dtype(0.85), dtype(-2.06), Cin.copy())     # no B image yet
+    eng.stage_B(N, B)
+    hC = sx.pinned_empty(M * N, dtype) if pinned else np.empty(M * N, dtype)
+    for rep in range(2):
+        hC[:] = Cin
+        eng.spmm_staged_B(N, dtype(0.85), dtype(-2.06), hC)
+        assert np.array_equal(bits(np.asarray(hC)), bits(ref)), rep
+        if pinned and K <= 4 * M:
+            assert eng.info(sx.INFO_HOST_PATH) == 2 and eng.info(sx.INFO_LAST_KERNEL) // 10000 == 9
+        if not pinned:
+            assert eng.info(sx.INFO_HOST_PATH) == 0

@@ -25,7 +25,7 @@ def test_row_blocks_over_nccl_match_oracle_bitwise():
            "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "multi_gpu_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=560)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("OK ") == 6, r.stdout
+    assert r.stdout.count("OK ") == 7, r.stdout
 
 
 @pytest.mark.timeout(300)
