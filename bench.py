@@ -419,7 +419,7 @@ class Case:
         self.engines, self.dB, self.dCin, self.dCout = [], [], [], []
 
 
-def time_steps(step, R, K, warmup, stream, min_region_ms, use_graph, world, dev, max_reps=4000, extra_streams=(), chain=True):
+def time_steps(step, R, K, warmup, stream, min_region_ms, use_graph, world, dev, max_reps=4000, extra_streams=(), chain=True, tail=None):
     """Warm up, then repeat a replay until the timed region is >= min_region_ms; every repetition
     has its own event pair on `stream`.  Steps are numbered consecutively over warm-up and all
     repetitions (copy = step mod R), so the rotation through the R copies never restarts.
@@ -428,6 +428,8 @@ def time_steps(step, R, K, warmup, stream, min_region_ms, use_graph, world, dev,
     replay of it -- the steady state of a long chain of dependent SpMMs.  chain=False: one graph per
     K-step window, a repetition is one K-step replay (every K steps pay a graph launch and lose the
     overlap of the next launch's prologue across the graph boundary).
+    `tail` (optional) is enqueued once behind every run of steps -- at the end of every captured graph, of
+    the warm-up and of every eager repetition (the push exchange's flush of a deferred publication).
     -> dict(ms_median, ms_min, ms_mean (per step, max over ranks per repetition), reps, region_ms, graphs,
             steps_per_rep, nwarm)"""
     import torch
@@ -443,6 +445,8 @@ def time_steps(step, R, K, warmup, stream, min_region_ms, use_graph, world, dev,
     with torch.cuda.stream(stream):
         for i in range(nwarm):
             step(i)
+        if tail is not None:
+            tail()
     barrier()
     base = nwarm
     graphs = None
@@ -458,6 +462,8 @@ def time_steps(step, R, K, warmup, stream, min_region_ms, use_graph, world, dev,
                     x.wait_stream(stream)            # fork
                 for i in range(per_graph * K):
                     step(base + g * per_graph * K + i)
+                if tail is not None:
+                    tail()
                 for x in extra_streams:
                     stream.wait_stream(x)            # join
             graphs.append(gr)
@@ -474,6 +480,8 @@ def time_steps(step, R, K, warmup, stream, min_region_ms, use_graph, world, dev,
         else:
             for i in range(K):
                 step(base + r * K + i)
+            if tail is not None:
+                tail()
 
     # pilot: three repetitions to size the run
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
@@ -746,7 +754,8 @@ def run_native(args):
     sampler.start()
     use_graph = not args.no_graph and (world == 1 or xch is not None)   # NCCL collectives are launched eagerly
     l0 = case.launches()
-    t = time_steps(step, R, K, args.warmup, stream, args.min_region_ms, use_graph, world, dev, extra_streams=extra_streams)
+    tail = xch.flush if xch is not None else None
+    t = time_steps(step, R, K, args.warmup, stream, args.min_region_ms, use_graph, world, dev, extra_streams=extra_streams, tail=tail)
     # launches in the timed region: a captured graph holds the launches of its K steps and is replayed once per repetition
     S = t["steps_per_rep"]
     enq_steps = t["nwarm"] + (t["graphs"] * S if use_graph else (3 + t["reps"]) * K)
@@ -754,7 +763,7 @@ def run_native(args):
     launches_dev = int(round(per_step * S * t["reps"]))
     kern_ms = t["ms_median"]
     # the same steps replayed as separate K-step graphs (what round 1 and the first half of round 2 reported)
-    t_k = time_steps(step, R, K, 0, stream, min(args.min_region_ms, 20.0), True, world, dev, extra_streams=extra_streams, chain=False) if use_graph and S > K else None
+    t_k = time_steps(step, R, K, 0, stream, min(args.min_region_ms, 20.0), True, world, dev, extra_streams=extra_streams, chain=False, tail=tail) if use_graph and S > K else None
     if t_k is not None:
         launches_dev += int(round(per_step * K * t_k["reps"]))
     timeouts = case.engines[0].info(sx.INFO_EXCHANGE_TIMEOUTS) if world > 1 else 0

@@ -199,6 +199,8 @@ enum sx_info {
     SX_INFO_EXCHANGE_TIMEOUTS = 17, /* nonzero if a device-side wait on a peer flag ever gave up (~2 s) */
     SX_INFO_EDGE_BLOCKS = 18,   /* row blocks of the edge-list plan of the last launch (variant 5) */
     SX_INFO_EDGE_COLS = 19,     /* B rows those blocks stage per SpMM (sum of their distinct columns) */
+    SX_INFO_PUSH_PENDING = 20,  /* 1 if the last SpMM launch carried a push whose publication was deferred
+                                 * (sx_spmm_fuse_push_deferred) and is still owed; 0 if nothing is owed */
     SX_INFO_TUNED_KERNEL = 16   /* SX_OPT_AUTOTUNE's choice for the current N: 10 * variant + (1 if
                                  * with the L2 prefetch), 0 if nothing has been tuned */
 };
@@ -339,6 +341,23 @@ int sx_spmm_expect_push(sx_ctx *ctx, const void *ready_flag, void *epoch_counter
  *   edge-list variant run the push as a kernel of its own right before them.) */
 int sx_spmm_fuse_push(sx_ctx *ctx, void *const *peer_images, void *const *peer_ready_flags, int npeers,
                       const void *done_flags, void *pushes_counter);
+/* Deferred publication: in a chain of dependent launches the one-warp publish kernel behind every
+ * pushing SpMM gates the next SpMM's dependent-launch wait (~1.1 us per step).  A caller that keeps
+ * at least two images in rotation can take it out of the chain:
+ * sx_spmm_fuse_push_deferred: as sx_spmm_fuse_push, but nothing publishes the push behind the launch.
+ *   SX_INFO_PUSH_PENDING tells afterwards whether the publication is still owed (1) or the launch
+ *   published it itself after all (0: a kernel other than the edge-list variant ran).
+ * sx_spmm_fuse_publish: the NEXT SpMM launch of this context -- on the same stream as the launch
+ *   that carried the push, a different image's counter -- stores pushes + 1 into the peers' ready
+ *   flags and into the counter right after its dependent-launch wait, i.e. once the carrying
+ *   kernel is complete.  One-shot.  (Kernels other than the edge-list variant run a one-warp
+ *   kernel for it first.)
+ * sx_push_publish: the same as a one-warp kernel of its own -- what ends a sequence (before a host
+ *   sync, at the end of a captured graph). */
+int sx_spmm_fuse_push_deferred(sx_ctx *ctx, void *const *peer_images, void *const *peer_ready_flags,
+                               int npeers, const void *done_flags, void *pushes_counter);
+int sx_spmm_fuse_publish(sx_ctx *ctx, void *const *peer_ready_flags, int npeers, void *pushes_counter);
+int sx_push_publish(sx_ctx *ctx, void *const *peer_ready_flags, int npeers, void *pushes_counter);
 /* Page-locked host memory for B and C (stands in for tapa::aligned_allocator). */
 int sx_host_alloc(size_t bytes, void **ptr);
 int sx_host_free(void *ptr);

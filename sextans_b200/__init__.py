@@ -32,7 +32,7 @@ STRICT, FAST = 0, 1
 (INFO_LAUNCHES, INFO_M, INFO_K, INFO_NNZ, INFO_DTYPE, INFO_SPLIT_ROWS, INFO_LAST_KERNEL, INFO_LD,
  INFO_ITEMS, INFO_ITEM_NNZ, INFO_HOST_PATH, INFO_TILE_NNZ, INFO_TILE_SLOTS, INFO_REST_NNZ,
  INFO_UPLOAD_SERIAL, INFO_COL_WINDOWS, INFO_TUNED_KERNEL, INFO_EXCHANGE_TIMEOUTS, INFO_EDGE_BLOCKS,
- INFO_EDGE_COLS) = range(20)
+ INFO_EDGE_COLS, INFO_PUSH_PENDING) = range(21)
 
 _PI32 = C.POINTER(C.c_int32)
 _PF = C.POINTER(C.c_float)
@@ -104,6 +104,9 @@ def lib():
         "sx_push_B": ([vp, vp, sz, C.POINTER(vp), C.POINTER(vp), i, vp, vp], i),
         "sx_spmm_expect_push": ([vp, vp, vp, vp], i),
         "sx_spmm_fuse_push": ([vp, C.POINTER(vp), C.POINTER(vp), i, vp, vp], i),
+        "sx_spmm_fuse_push_deferred": ([vp, C.POINTER(vp), C.POINTER(vp), i, vp, vp], i),
+        "sx_spmm_fuse_publish": ([vp, C.POINTER(vp), i, vp], i),
+        "sx_push_publish": ([vp, C.POINTER(vp), i, vp], i),
         "sx_host_alloc": ([sz, C.POINTER(vp)], i),
         "sx_host_free": ([vp], i),
         "sx_partition_rows": ([i, _PI32, i, _PI32], i),
@@ -553,6 +556,25 @@ class Engine:
         imgs = (C.c_void_p * n)(*peer_image_ptrs)
         rdy = (C.c_void_p * n)(*peer_ready_ptrs)
         _check(self._L.sx_spmm_fuse_push(self._ctx, imgs, rdy, n, C.c_void_p(done_flags_ptr), C.c_void_p(pushes_ptr)))
+
+    def fuse_push_deferred(self, peer_image_ptrs, peer_ready_ptrs, done_flags_ptr, pushes_ptr):
+        """As fuse_push, the publication left to a later launch (sx_spmm_fuse_push_deferred)."""
+        n = len(peer_image_ptrs)
+        imgs = (C.c_void_p * n)(*peer_image_ptrs)
+        rdy = (C.c_void_p * n)(*peer_ready_ptrs)
+        _check(self._L.sx_spmm_fuse_push_deferred(self._ctx, imgs, rdy, n, C.c_void_p(done_flags_ptr), C.c_void_p(pushes_ptr)))
+
+    def fuse_publish(self, peer_ready_ptrs, pushes_ptr):
+        """The next SpMM launch publishes an earlier launch's push (sx_spmm_fuse_publish)."""
+        n = len(peer_ready_ptrs)
+        rdy = (C.c_void_p * n)(*peer_ready_ptrs)
+        _check(self._L.sx_spmm_fuse_publish(self._ctx, rdy, n, C.c_void_p(pushes_ptr)))
+
+    def push_publish(self, peer_ready_ptrs, pushes_ptr):
+        """Publish an earlier launch's push with a one-warp kernel (sx_push_publish)."""
+        n = len(peer_ready_ptrs)
+        rdy = (C.c_void_p * n)(*peer_ready_ptrs)
+        _check(self._L.sx_push_publish(self._ctx, rdy, n, C.c_void_p(pushes_ptr)))
 
     def expect_push(self, ready_ptr, epoch_ptr, done_ptr):
         """The next SpMM launch waits for the push into its B image and acknowledges it (sx_spmm_expect_push)."""

@@ -748,6 +748,8 @@ spmm_window_kernel(const int M, const int4 *__restrict__ blocks, const int *__re
 constexpr int SX_EDGE_PREFETCH = 1;
 // where a pushed B image goes: up to 15 peers' images and ready flags (peer-mapped addresses)
 struct PushList { int4 *dst[15]; uint32_t *ready[15]; };
+// deferred publication (sx_spmm_fuse_publish): the ready flags of a push that an EARLIER kernel of the stream carried
+struct PubList { uint32_t *ready[15]; };
 // -DSX_EDGE_TRACE (scripts/build_variant.sh): every block records %globaltimer at its phase
 // boundaries into a device array read back by sx_debug_edge_trace -- how a ~3.5 us step splits
 // into launch, prologue, dependent-launch wait, window staging and arithmetic.
@@ -828,7 +830,8 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
                      const int nvec, const int flags, const uint32_t *ready, uint32_t *epoch, uint32_t *done_remote,
                      unsigned int *sync_words, const int npush, const PushList push, const int64_t push_n16,
                      const uint32_t *push_done, uint32_t *pushes, T *Ch, const int64_t ldh, const int N,
-                     const uint32_t tile_off, const int tile_ld, const int64_t batch_strideB, const int64_t batch_strideC) {
+                     const uint32_t tile_off, const int tile_ld, const int64_t batch_strideB, const int64_t batch_strideC,
+                     const PubList pub, const int npub, uint32_t *pub_pushes) {
     using V = typename VecOf<T>::type;
     constexpr int THREADS = EdgeShape<G>::THREADS, ROWS = EdgeShape<G>::ROWS, E = VecOf<T>::E;
     // several B's at once (sx_spmm_device_batch_*): blockIdx.y picks the (B, C_in, C_out) triple; the block's
@@ -902,6 +905,15 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
     SX_TRACE_MARK(1);
     pdl_wait();
     SX_TRACE_MARK(2);
+    // ---- multi-GPU, deferred publication: the push an earlier kernel of this stream carried is complete (the wait above
+    // has returned: everything that kernel stored, the peer stores included, has been performed), so one thread tells
+    // the peers -- the job of publish_push_kernel, without a kernel of its own in the chain of dependent launches
+    // (a one-warp kernel between two SpMMs costs the chain ~1.1 us per step: its completion gates the next wait).
+    if (npub > 0 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 32) {
+        const uint32_t t = *reinterpret_cast<volatile uint32_t *>(pub_pushes);
+        for (int p = 0; p < npub; ++p) st_relaxed_sys(pub.ready[p], t + 1u);
+        *reinterpret_cast<volatile uint32_t *>(pub_pushes) = t + 1u;
+    }
     // ---- multi-GPU: one thread polls.  No system-scope FENCE anywhere in this kernel: on sm_100a
     // fence.acq_rel.sys / st.release.sys are MEMBAR.ALL.SYS, measured at 4-5 us per block with peer
     // mappings live (profiles/r02_exchange_trace_n2.txt), more than the whole SpMM.  The flag is
@@ -1632,6 +1644,14 @@ push_image_kernel(const int4 *__restrict__ src, const int64_t n16, const PushLis
 __global__ void publish_push_kernel(const PushList peers, const int npeers, uint32_t *pushes) {
     pdl_launch_dependents();
     pdl_wait();  // the carrying kernel is complete: its stores, the peer stores included, have been performed
+    if (threadIdx.x == 0) {
+        const uint32_t t = *reinterpret_cast<volatile uint32_t *>(pushes);
+        for (int p = 0; p < npeers; ++p) st_relaxed_sys(peers.ready[p], t + 1u);
+        *reinterpret_cast<volatile uint32_t *>(pushes) = t + 1u;
+    }
+}
+// the same from a list of ready flags alone: a deferred publication that no SpMM launch picked up (sx_push_publish)
+__global__ void publish_list_kernel(const PubList peers, const int npeers, uint32_t *pushes) {
     if (threadIdx.x == 0) {
         const uint32_t t = *reinterpret_cast<volatile uint32_t *>(pushes);
         for (int p = 0; p < npeers; ++p) st_relaxed_sys(peers.ready[p], t + 1u);

@@ -125,6 +125,12 @@ struct sx_ctx {
     sx::PushList p_list = {};
     const uint32_t *p_done = nullptr;
     uint32_t *p_pushes = nullptr;
+    bool push_pending = false;  // SX_INFO_PUSH_PENDING: the last launch carried a push whose publication is still owed
+    bool p_defer = false;  // sx_spmm_fuse_push_deferred: no publish kernel behind the launch; a later launch publishes
+    // ... and the publication of an EARLIER launch's push carried by the next launch (sx_spmm_fuse_publish; one-shot)
+    int pub_n = 0;
+    sx::PubList pub_list = {};
+    uint32_t *pub_pushes = nullptr;
     std::vector<int32_t> h_rowptr;  // kept to re-derive segments when the option changes
     // variant 3: per block of 32 rows {first column, column span, nnz begin, nnz end}
     DevBuf wblocks;
@@ -272,16 +278,27 @@ int launch_edge(sx_ctx *c, const EdgePlan *ep, int N, T alpha, const T *dB, int6
     if ((c->x_ready || c->p_npeers) && (rc = ensure_sync_words(c))) return rc;
     // the fused push sends the image this launch reads: K rows of ldb elements, from column 0
     const int npush = c->win_col0 == 0 ? c->p_npeers : 0;
+    const int npub = c->win_col0 == 0 ? c->pub_n : 0;
+    if (npub && npush && c->pub_pushes == c->p_pushes)
+        return fail(SX_ERR_INVALID, "a launch cannot publish an earlier push of the very image counter it pushes with (use at least two images, or do not defer)");
+    if (npub && (rc = ensure_sync_words(c))) return rc;
     const int64_t push_n16 = (int64_t)((size_t)c->K * (size_t)ldb * sizeof(T) / 16);
     SX_CUDA(cudaLaunchKernelEx(&cfg, kern, (const int4 *)ep->blocks.p, (const int *)ep->cols.p, (const int *)c->rowptr.p,
                                (const uint16_t *)ep->lcol.p, (const T *)c->val.p, dB, (uint32_t)(ldb / E), dCin, dCout,
                                (uint32_t)(ldc / E), alpha, beta, nvec, pf ? sx::SX_EDGE_PREFETCH : 0, c->x_ready, c->x_epoch,
                                c->x_done, (unsigned int *)c->sync_words.p, npush, c->p_list, push_n16, c->p_done, c->p_pushes,
                                Ch, (int64_t)c->M, N, (uint32_t)tile_off, tile_ld, nbatch > 1 ? c->batch_sB : (int64_t)0,
-                               nbatch > 1 ? c->batch_sC : (int64_t)0));
+                               nbatch > 1 ? c->batch_sC : (int64_t)0, c->pub_list, npub, c->pub_pushes));
     c->batch_taken = nbatch > 1;
     c->x_ready = nullptr;
+    c->pub_n = 0;
     c->launches++;
+    c->push_pending = false;
+    if (npush && c->p_defer) {  // the caller publishes later: sx_spmm_fuse_publish on a later launch, or sx_push_publish
+        c->p_npeers = 0;
+        c->p_defer = false;
+        c->push_pending = true;
+    } else
     if (npush) {  // the publication of the push, right behind the kernel that carried it (its programmatic dependent)
         cudaLaunchConfig_t pc = {};
         pc.gridDim = dim3(1);
@@ -342,7 +359,13 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
             }
         }
     }
-    // the other kernels do not carry the multi-GPU exchange: the push as a kernel of its own ...
+    // the other kernels do not carry the multi-GPU exchange: a pending deferred publication as a kernel of its own ...
+    if (c->pub_n > 0 && c->win_col0 == 0) {
+        sx::publish_list_kernel<<<1, 32, 0, c->stream>>>(c->pub_list, c->pub_n, c->pub_pushes);
+        c->launches++;
+        c->pub_n = 0;
+    }
+    // ... the push as a kernel of its own ...
     if (c->p_npeers > 0 && c->win_col0 == 0) {
         if ((rc = ensure_sync_words(c))) return rc;
         const int64_t n16 = (int64_t)((size_t)c->K * (size_t)ldb * sizeof(T) / 16);
@@ -351,6 +374,8 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
                                                            (unsigned int *)c->sync_words.p);
         c->launches++;
         c->p_npeers = 0;
+        c->p_defer = false;        // this kernel publishes its own push: nothing is owed
+        c->push_pending = false;
     }
     // ... and the receiving side's handshake as a one-warp kernel before and after
     struct PushGuard {
@@ -1934,6 +1959,7 @@ int sx_get_info(sx_ctx *c, int what, int64_t *value) {
             *value += c->exchange_timeouts_host;  // ... and the one-kernel host call's waits
             return SX_OK;
         }
+        case SX_INFO_PUSH_PENDING: *value = c->push_pending ? 1 : 0; return SX_OK;
         case SX_INFO_EDGE_BLOCKS: *value = c->last_edge_plan ? c->last_edge_plan->nblocks : 0; return SX_OK;
         case SX_INFO_EDGE_COLS: *value = c->last_edge_plan ? c->last_edge_plan->total_cols : 0; return SX_OK;
         default: return fail(SX_ERR_INVALID, "unknown info id %d", what);
@@ -2119,6 +2145,45 @@ int sx_spmm_fuse_push(sx_ctx *c, void *const *peer_images, void *const *peer_rea
     c->p_done = (const uint32_t *)done_flags;
     c->p_pushes = (uint32_t *)pushes_counter;
     c->p_npeers = npeers;
+    return SX_OK;
+}
+
+int sx_spmm_fuse_push_deferred(sx_ctx *c, void *const *peer_images, void *const *peer_ready_flags, int npeers,
+                               const void *done_flags, void *pushes_counter) {
+    int rc = sx_spmm_fuse_push(c, peer_images, peer_ready_flags, npeers, done_flags, pushes_counter);
+    if (rc == SX_OK && npeers > 0) c->p_defer = true;
+    return rc;
+}
+
+int sx_spmm_fuse_publish(sx_ctx *c, void *const *peer_ready_flags, int npeers, void *pushes_counter) {
+    if (!c) return fail(SX_ERR_INVALID, "null context");
+    if (npeers < 0 || npeers > 15) return fail(SX_ERR_INVALID, "0..15 peers expected (got %d)", npeers);
+    c->pub_n = 0;
+    if (npeers == 0) return SX_OK;
+    if (!peer_ready_flags || !pushes_counter) return fail(SX_ERR_INVALID, "null argument");
+    for (int i = 0; i < npeers; ++i) {
+        if (!peer_ready_flags[i]) return fail(SX_ERR_INVALID, "bad peer pointer");
+        c->pub_list.ready[i] = (uint32_t *)peer_ready_flags[i];
+    }
+    c->pub_pushes = (uint32_t *)pushes_counter;
+    c->pub_n = npeers;
+    return SX_OK;
+}
+
+int sx_push_publish(sx_ctx *c, void *const *peer_ready_flags, int npeers, void *pushes_counter) {
+    int rc = bind(c);
+    if (rc) return rc;
+    if (npeers < 0 || npeers > 15) return fail(SX_ERR_INVALID, "0..15 peers expected (got %d)", npeers);
+    if (npeers == 0) return SX_OK;
+    if (!peer_ready_flags || !pushes_counter) return fail(SX_ERR_INVALID, "null argument");
+    sx::PubList pl = {};
+    for (int i = 0; i < npeers; ++i) {
+        if (!peer_ready_flags[i]) return fail(SX_ERR_INVALID, "bad peer pointer");
+        pl.ready[i] = (uint32_t *)peer_ready_flags[i];
+    }
+    sx::publish_list_kernel<<<1, 32, 0, c->stream>>>(pl, npeers, (uint32_t *)pushes_counter);
+    SX_CUDA(cudaGetLastError());
+    c->launches++;
     return SX_OK;
 }
 

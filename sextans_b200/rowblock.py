@@ -68,9 +68,14 @@ class PushExchange:
     """
     WORDS = 8192          # mailbox: ready[j] at j, epoch[j] at 256 + j, pushes[j] at 512 + j, done[j][c] at 1024 + 16 j + c
 
-    def __init__(self, engines, N, group=None, root=0, fanout=2):
+    def __init__(self, engines, N, group=None, root=0, fanout=2, defer_publish=None):
         import torch.distributed as dist
         self.engines, self.N, self.root, self.group = list(engines), N, root, group
+        # deferred publication (R >= 2 images in rotation on ONE stream): the step is published by the NEXT step's SpMM
+        # kernel right after its dependent-launch wait instead of by a one-warp kernel of its own, which would gate
+        # that wait (~1.1 us per step); the caller ends every sequence of steps with flush()
+        self.defer = (len(self.engines) >= 2) if defer_publish is None else (bool(defer_publish) and len(self.engines) >= 2)
+        self._owed = None                      # (engine index, children's ready flags, pushes counter) of the last step
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.R = len(self.engines)
         if self.R > 256 or self.world > 16 or not 1 <= fanout <= 15:
@@ -114,23 +119,50 @@ class PushExchange:
 
     def describe(self):
         return (f"B ({self.nbytes / 1e3:.0f} KB) pushed down a binary tree of ranks over NVLink BY the SpMM kernels themselves (a sender's "
-                "blocks copy their share of the image into its <= 2 children's images with posted peer stores, a one-warp dependent "
-                "kernel publishes the step; a receiver's kernel waits on the step flag in its prologue, forwards if it has children, "
+                "blocks copy their share of the image into its <= 2 children's images with posted peer stores; the step is published "
+                + ("by the NEXT step's SpMM kernel right after its dependent-launch wait (deferred publication: no kernel of its own in the chain)"
+                   if self.defer else "by a one-warp dependent kernel") +
+                "; a receiver's kernel waits on the step flag in its prologue, forwards if it has children, "
                 "and acknowledges from its last block): no stream and no collective for the exchange on any rank")
 
     def before_step(self, i):
+        from . import INFO_PUSH_PENDING
         j = i % self.R
         e = self.engines[j]
         if self.parent is not None:
             e.expect_push(self.box + 4 * j, self.box + 4 * (256 + j), self.parent_box + 4 * (1024 + 16 * j + self.child_index))
         if self.children:
-            e.fuse_push([self.child_images[r][j] for r in self.children], [self.child_box[r] + 4 * j for r in self.children],
-                        self.box + 4 * (1024 + 16 * j), self.box + 4 * (512 + j))
+            ready = [self.child_box[r] + 4 * j for r in self.children]
+            args = ([self.child_images[r][j] for r in self.children], ready, self.box + 4 * (1024 + 16 * j), self.box + 4 * (512 + j))
+            if not self.defer:
+                e.fuse_push(*args)
+                return
+            if self._owed is not None:
+                jp, rp, pp = self._owed
+                self._owed = None
+                if self.engines[jp].info(INFO_PUSH_PENDING):
+                    if jp == j:                # the same image twice in a row: its own launch cannot publish for it
+                        self.engines[jp].push_publish(rp, pp)
+                    else:
+                        e.fuse_publish(rp, pp)
+            e.fuse_push_deferred(*args)
+            self._owed = (j, ready, self.box + 4 * (512 + j))
+
+    def flush(self):
+        """Publish the last step's push if that is still owed (deferred publication): before a host
+        sync, at the end of a captured graph, before another stream takes over."""
+        from . import INFO_PUSH_PENDING
+        if self._owed is not None:
+            jp, rp, pp = self._owed
+            self._owed = None
+            if self.engines[jp].info(INFO_PUSH_PENDING):
+                self.engines[jp].push_publish(rp, pp)
 
     def close(self):
         """Collective: every rank unmaps what it imported, then frees its mailbox."""
         import torch.distributed as dist
         e0 = self.engines[0]
+        self.flush()
         for e in self.engines:
             e.synchronize()
         dist.barrier(group=self.group)

@@ -624,7 +624,7 @@ void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, u
                                              rp.p, dlcol.p, val.p, B.p, ldv, Cin.p, Cout.p, ldv, alpha, beta, nvec,
                                              sx::SX_EDGE_PREFETCH, with_flags ? flags.p : nullptr, flags.p + 1, flags.p + 2,
                                              flags.p + 4, with_flags ? 2 : 0, plist, (int64_t)((size_t)K * ld * sizeof(T) / 16),
-                                             pflags.p, pflags.p + 2, nullptr, 0, N, 0u, 0, 0, 0);
+                                             pflags.p, pflags.p + 2, nullptr, 0, N, 0u, 0, 0, 0, sx::PubList{}, 0, nullptr);
     });
     bool ok = true;
     for (int i = 0; i < M && ok; ++i) ok = same_bits(Cout.p + (int64_t)i * ld, Ref.p + (int64_t)i * ld, (size_t)N);
@@ -650,7 +650,7 @@ void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, u
             sx::spmm_edgelist_kernel<T, G, true, true>(reinterpret_cast<const int4 *>(dblocks.p), dcols.p, rp.p, dlcol.p, val.p,
                                                        B.p, ldv, nullptr, nullptr, ldv, alpha, beta, nvec, sx::SX_EDGE_PREFETCH,
                                                        nullptr, nullptr, nullptr, flags.p + 4, 0, plist, 0, nullptr, nullptr,
-                                                       Ch.p, (int64_t)M, N, (uint32_t)tile_off, tile_ld, 0, 0);
+                                                       Ch.p, (int64_t)M, N, (uint32_t)tile_off, tile_ld, 0, 0, sx::PubList{}, 0, nullptr);
         });
         bool okh = true;
         for (int i = 0; i < M && okh; ++i)

@@ -71,6 +71,7 @@ def main():
         px.before_step(k)
         eng.stage_C(N, Cb)
         eng.launch(0.85, -2.06)
+        px.flush()                       # deferred publication (3 images in rotation): a host sync ends the sequence
         eng.fetch_C(Cb)
         ref = oracle.spmm_csr(blk.rows, N, K, blk.rowptr, blk.colidx, blk.val, 0.85, B, -2.06, blk.take_C(Cin, N))
         assert Cb.tobytes() == ref.tobytes(), (rank, k)
@@ -85,6 +86,8 @@ def main():
         for k in range(3):
             px.before_step(k)
             engs[k].spmm_device(N, 0.85, engs[k].device_B(N)[0], ld, -2.06, dCin[k], dCout[k], ld)
+        px.flush()                       # the last step's publication is part of the graph
+    assert px.defer
     for _ in range(4):
         with torch.cuda.stream(stream):
             g.replay()
