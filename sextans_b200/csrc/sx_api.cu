@@ -365,19 +365,8 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
         c->launches++;
         c->pub_n = 0;
     }
-    // ... the push as a kernel of its own ...
-    if (c->p_npeers > 0 && c->win_col0 == 0) {
-        if ((rc = ensure_sync_words(c))) return rc;
-        const int64_t n16 = (int64_t)((size_t)c->K * (size_t)ldb * sizeof(T) / 16);
-        const int grid = (int)std::min<int64_t>(c->sm_count, std::max<int64_t>(1, (n16 + 255) / 256));
-        sx::push_image_kernel<<<grid, 256, 0, c->stream>>>((const int4 *)dB, n16, c->p_list, c->p_npeers, c->p_done, c->p_pushes,
-                                                           (unsigned int *)c->sync_words.p);
-        c->launches++;
-        c->p_npeers = 0;
-        c->p_defer = false;        // this kernel publishes its own push: nothing is owed
-        c->push_pending = false;
-    }
-    // ... and the receiving side's handshake as a one-warp kernel before and after
+    // ... the receiving side's handshake as a one-warp kernel before and after (a rank that receives AND forwards must
+    // have the parent's push before it sends the image on) ...
     struct PushGuard {
         sx_ctx *c; const uint32_t *ready; uint32_t *epoch, *done;
         ~PushGuard() {
@@ -389,6 +378,18 @@ int launch_shape(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, co
         if ((rc = ensure_sync_words(c))) return rc;
         sx::wait_push_kernel<<<1, 32, 0, c->stream>>>(guard.ready, guard.epoch, (unsigned int *)c->sync_words.p);
         c->launches++;
+    }
+    // ... and the push as a kernel of its own
+    if (c->p_npeers > 0 && c->win_col0 == 0) {
+        if ((rc = ensure_sync_words(c))) return rc;
+        const int64_t n16 = (int64_t)((size_t)c->K * (size_t)ldb * sizeof(T) / 16);
+        const int grid = (int)std::min<int64_t>(c->sm_count, std::max<int64_t>(1, (n16 + 255) / 256));
+        sx::push_image_kernel<<<grid, 256, 0, c->stream>>>((const int4 *)dB, n16, c->p_list, c->p_npeers, c->p_done, c->p_pushes,
+                                                           (unsigned int *)c->sync_words.p);
+        c->launches++;
+        c->p_npeers = 0;
+        c->p_defer = false;        // this kernel publishes its own push: nothing is owed
+        c->push_pending = false;
     }
     int variant = (c->kernel >= 1 && c->kernel <= 3) ? c->kernel : (window_auto ? 3 : (sub_wave ? 1 : 2));  // 4 and 5 were tried above
     if (variant == 3 && !window_ok) variant = sub_wave ? 1 : 2;
