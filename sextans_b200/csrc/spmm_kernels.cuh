@@ -911,7 +911,9 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
     // (a one-warp kernel between two SpMMs costs the chain ~1.1 us per step: its completion gates the next wait).
     if (npub > 0 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 32) {
         const uint32_t t = *reinterpret_cast<volatile uint32_t *>(pub_pushes);
-        for (int p = 0; p < npub; ++p) st_relaxed_sys(pub.ready[p], t + 1u);
+#pragma unroll
+        for (int p = 0; p < 15; ++p)  // constant indices: a by-value list indexed by a variable is copied to local memory at kernel entry
+            if (p < npub) st_relaxed_sys(pub.ready[p], t + 1u);
         *reinterpret_cast<volatile uint32_t *>(pub_pushes) = t + 1u;
     }
     // ---- multi-GPU: one thread polls.  No system-scope FENCE anywhere in this kernel: on sm_100a
@@ -952,7 +954,9 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
         const int64_t lo = push_n16 * blockIdx.x / gridDim.x, hi = push_n16 * (blockIdx.x + 1) / gridDim.x;
         for (int64_t i = lo + threadIdx.x; i < hi; i += THREADS) {
             const int4 v = __ldg(src + i);
-            for (int p = 0; p < npush; ++p) push.dst[p][i] = v;
+#pragma unroll
+            for (int p = 0; p < 15; ++p)
+                if (p < npush) push.dst[p][i] = v;
         }
     }
     // a lane group takes rows rl, rl + ROWS, ... of the block; C_in of the next one is fetched while this one is computed

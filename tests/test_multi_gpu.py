@@ -18,11 +18,14 @@ def _gpus():
 
 
 @pytest.mark.timeout(600)
-def test_row_blocks_over_nccl_match_oracle_bitwise():
-    if _gpus() < 2:
-        pytest.skip("needs 2 GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "multi_gpu_worker.py")]
+@pytest.mark.parametrize("nproc", [2, 4])
+def test_row_blocks_over_nccl_match_oracle_bitwise(nproc):
+    """2 ranks: holder -> receiver.  4 ranks: the push tree has a rank that receives AND forwards
+    (profiles/r02_multi_gpu_worker_4gpu.txt is the kept output of the 4-GPU run)."""
+    if _gpus() < nproc:
+        pytest.skip(f"needs {nproc} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29515 + nproc), os.path.join(ROOT, "tests", "multi_gpu_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=560)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("OK ") == 7, r.stdout
