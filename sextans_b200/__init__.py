@@ -439,16 +439,21 @@ class Engine:
         ``tapa::invoke`` returns in the reference (src/sextans-host.cpp:237); with
         ``want_ns=False`` the C call gets ``kernel_ns = NULL`` and returns ``None``."""
         suf, ct, _ = _suffix(self.dtype)
-        B = np.ascontiguousarray(B, dtype=self.dtype)
+        if B.dtype != self.dtype or not B.flags.c_contiguous:
+            B = np.ascontiguousarray(B, dtype=self.dtype)
         if C_inout.dtype != self.dtype or not C_inout.flags.c_contiguous:
             raise ValueError("C must be a contiguous array of the matrix dtype")
         if B.size != self.K * N or C_inout.size != self.M * N:
             raise ValueError("B must hold K*N and C must hold M*N elements")
+        fn = self._L.sx_spmm_f64 if suf == "f64" else self._L.sx_spmm_f32
+        if not want_ns:   # the short way through: nothing to allocate, nothing to read back
+            status = fn(self._ctx, N, ct(alpha), B.ctypes.data, ct(beta), C_inout.ctypes.data, rp_time, None)
+            if status != 0:
+                _check(status)
+            return None
         ns = C.c_double()
-        _check(getattr(self._L, f"sx_spmm_{suf}")(self._ctx, N, ct(alpha), _host_ptr(B), ct(beta),
-                                                  _host_ptr(C_inout), rp_time,
-                                                  C.byref(ns) if want_ns else None))
-        return ns.value if want_ns else None
+        _check(fn(self._ctx, N, ct(alpha), _host_ptr(B), ct(beta), _host_ptr(C_inout), rp_time, C.byref(ns)))
+        return ns.value
 
     def spmm_staged_B(self, N, alpha, beta, C_inout):
         """One blocking SpMM on the B image the context already holds (stage_B, a peer's push, a
