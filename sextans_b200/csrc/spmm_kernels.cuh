@@ -822,8 +822,12 @@ template <int G> struct EdgeShape {
     static constexpr int THREADS = G >= 16 ? 512 : 256;
     static constexpr int ROWS = THREADS / G;
 };
+// blocks per SM the register allocation of the edge-list kernel is held to (build-time knob for A/B runs)
+#ifndef SX_EDGE_MINBLOCKS
+#define SX_EDGE_MINBLOCKS 2
+#endif
 template <typename T, int G, bool STRICT, bool HOSTC = false>
-__global__ void __launch_bounds__(EdgeShape<G>::THREADS, 2)
+__global__ void __launch_bounds__(EdgeShape<G>::THREADS, SX_EDGE_MINBLOCKS)
 spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ cols, const int *__restrict__ rowptr,
                      const uint16_t *__restrict__ lcol, const T *__restrict__ val, const T *__restrict__ B0,
                      const uint32_t ldbv, const T *Cin0, T *Cout0, const uint32_t ldcv, const T alpha, const T beta,
