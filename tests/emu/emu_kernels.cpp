@@ -619,14 +619,22 @@ void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, u
     plist.dst[1] = reinterpret_cast<int4 *>(peer1.p);
     plist.ready[0] = pflags.p + 3;
     plist.ready[1] = pflags.p + 4;
+    // deferred publication of an EARLIER push (another image's counter at 11): this launch stores 12 into that push's two ready flags
+    Aligned<uint32_t> dflags(8);
+    dflags.p[0] = 11;
+    sx::PubList publist = {};
+    publist.ready[0] = dflags.p + 1;
+    publist.ready[1] = dflags.p + 2;
     sx_emu::launch((unsigned)nb, THREADS, (size_t)std::max(max_smem, 16), [&] {
         sx::spmm_edgelist_kernel<T, G, true>(reinterpret_cast<const int4 *>(dblocks.p), dcols.p,
                                              rp.p, dlcol.p, val.p, B.p, ldv, Cin.p, Cout.p, ldv, alpha, beta, nvec,
                                              sx::SX_EDGE_PREFETCH, with_flags ? flags.p : nullptr, flags.p + 1, flags.p + 2,
                                              flags.p + 4, with_flags ? 2 : 0, plist, (int64_t)((size_t)K * ld * sizeof(T) / 16),
-                                             pflags.p, pflags.p + 2, nullptr, 0, N, 0u, 0, 0, 0, sx::PubList{}, 0, nullptr);
+                                             pflags.p, pflags.p + 2, nullptr, 0, N, 0u, 0, 0, 0, publist, with_flags ? 2 : 0, dflags.p);
     });
     bool ok = true;
+    if (with_flags) ok = dflags.p[0] == 12u && dflags.p[1] == 12u && dflags.p[2] == 12u && dflags.p[3] == 0u;
+    else ok = dflags.p[0] == 11u && dflags.p[1] == 0u;
     for (int i = 0; i < M && ok; ++i) ok = same_bits(Cout.p + (int64_t)i * ld, Ref.p + (int64_t)i * ld, (size_t)N);
     // the last block advanced the epoch, acknowledged to the pusher and reset the block counter; no time-out
     if (with_flags) ok = ok && flags.p[1] == 41u && flags.p[2] == 41u && flags.p[6] == 0u && flags.p[5] == 0u;
