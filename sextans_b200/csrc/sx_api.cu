@@ -191,6 +191,7 @@ struct sx_ctx {
     uint32_t *host_flag = nullptr, *host_flag_dev = nullptr;
     struct Occ { const void *kern; size_t smem; int per_sm; };
     std::vector<Occ> host_occ;
+    int edge_balance = 0;  // experiment knob (env SX_EDGE_BALANCE=1): edge-list grids sized to whole waves of the SMs
     int host_coop = 1;   // experiment knob (env SX_HOST_COOP=0): launch the one-kernel call without the cooperative attribute
     int host_depth = 0;  // experiment knob (env SX_HOST_DEPTH): column groups requested ahead in the one-kernel call
     int host_groups = 0; // SX_OPT_HOST_GROUPS: column groups of the fused host-facing call (0 auto)
@@ -962,8 +963,21 @@ int get_edge_plan(sx_ctx *c, int row_bytes, int elem_bytes, int rows, const Edge
     // one block per SM -- the planner can: max_rows, nnz_target -- was measured and lost on nasa4704,
     // 4.30 against 3.58 us per step: blocks of many short rows need several sweeps, and a sweep of
     // short rows costs its latency, not its nonzeros.)
-    const int expect = (c->M + rows - 1) / rows;
-    const int max_rows = rows;
+    // (Sizing the grid to a whole number of waves -- 219 blocks of 64 rows leave half of the 148 SMs with two blocks and
+    // the other half with one on pcrystk02 N=16; 293 blocks of 48 rows give every SM two -- was measured and lost as
+    // well: N=8 7.53 against 7.03 us, N=16 7.49 against 6.76 (profiles/r02_edge_balance.txt): shorter blocks stage more
+    // B rows in total (129103 against 108777) and a block's time is its staging and its longest row, not its row count.
+    // Kept behind SX_EDGE_BALANCE=1 for A/B runs.)
+    int max_rows = rows;
+    {
+        const int64_t nb0 = ((int64_t)c->M + rows - 1) / rows;
+        const int64_t waves = (nb0 + c->sm_count - 1) / c->sm_count;
+        if (c->edge_balance && waves <= 8) {
+            const int r = (int)(((int64_t)c->M + waves * c->sm_count - 1) / (waves * c->sm_count));
+            if (r >= (rows + 1) / 2) max_rows = std::min(rows, r);
+        }
+    }
+    const int expect = (c->M + max_rows - 1) / max_rows;
     const int64_t nnz_target = 0;
     // as many blocks per SM as leave every block uncut (6, 4, 3, 2 or 1); if even one block per SM
     // needs cuts, that plan is taken with its cuts
@@ -1802,6 +1816,7 @@ int sx_create(int device, sx_ctx **out) {
     c->sm_count = prop.multiProcessorCount;
     if (const char *e = std::getenv("SX_HOST_DEPTH")) c->host_depth = std::atoi(e);
     if (const char *e = std::getenv("SX_HOST_COOP")) c->host_coop = std::atoi(e);
+    if (const char *e = std::getenv("SX_EDGE_BALANCE")) c->edge_balance = std::atoi(e);
     cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
