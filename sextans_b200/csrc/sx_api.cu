@@ -676,8 +676,9 @@ int autotune(sx_ctx *c, int N, T alpha, const T *dB, int64_t ldb, T beta, const 
     return SX_OK;
 }
 
-// Automatic pass width (columns), see spmm_device.  Measured on C4 (uniform, M = K = 1e6, 20 nonzeros per row,
-// N = 128 fp32: B = 512 MB, every B row used 20 times): TODO
+// Automatic pass width (columns), see spmm_device: one pass.  Measured on C4 (uniform, M = K = 1e6, 20 nonzeros per
+// row, N = 128 fp32: B = 512 MB, every B row used 20 times): 64 / 32 / 16 columns per pass 1.51 / 2.68 / 4.27 ms against
+// 1.46 ms in one pass; C5 in two passes 2.98 against 1.59 ms (profiles/r02_n_passes.txt) -- a pass costs its nonzeros.
 template <typename T>
 int auto_panel_cols(const sx_ctx *c, int N, int64_t ldb) {
     (void)c; (void)N; (void)ldb;
