@@ -84,7 +84,7 @@ struct Plan {
 struct EdgePlan {
     int row_bytes = 0, rows = 0;  // key: bytes of a B row, rows per block
     bool usable = false;  // planned, and staging a block's distinct B rows beats gathering per nonzero
-    int nblocks = 0, max_smem = 0;
+    int nblocks = 0, max_smem = 0, max_rows = 0;  // max_rows: most rows a block holds (the HOSTC tiles are sized by it)
     int64_t total_cols = 0;
     DevBuf blocks, cols, lcol;
     void release() { blocks.release(); cols.release(); lcol.release(); }
@@ -252,7 +252,7 @@ int launch_edge(sx_ctx *c, const EdgePlan *ep, int N, T alpha, const T *dB, int6
     constexpr int E = sx::VecOf<T>::E;
     const int nvec = (N * (int)sizeof(T) + 15) / 16;
     auto kern = sx::spmm_edgelist_kernel<T, G, STRICT, HOSTC>;
-    const int tile_ld = sx::EdgeShape<G>::ROWS + 1;
+    const int tile_ld = std::max(sx::EdgeShape<G>::ROWS, ep->max_rows) + 1;
     const size_t tile_off = ((size_t)std::max(ep->max_smem, 16) + 15) & ~(size_t)15;
     const size_t smem = HOSTC ? tile_off + (size_t)N * tile_ld * sizeof(T) : (size_t)std::max(ep->max_smem, 16);
     if (smem > 48 * 1024 &&
@@ -968,16 +968,23 @@ int get_edge_plan(sx_ctx *c, int row_bytes, int elem_bytes, int rows, const Edge
     // the other half with one on pcrystk02 N=16; 293 blocks of 48 rows give every SM two -- was measured and lost as
     // well: N=8 7.53 against 7.03 us, N=16 7.49 against 6.76 (profiles/r02_edge_balance.txt): shorter blocks stage more
     // B rows in total (129103 against 108777) and a block's time is its staging and its longest row, not its row count.
-    // Kept behind SX_EDGE_BALANCE=1 for A/B runs.)
+    // Fatter blocks lose too: two sweeps of the lane groups so that pcrystk02 N=16 is one wave of 150 blocks 8.97 us, always
+    // 2 x ROWS rows per block 11.3 us (nasa4704 4.22 against 3.51).  One sweep of exactly ROWS rows it is; the alternatives
+    // stay behind SX_EDGE_BALANCE=1/2/3 for A/B runs.)
     int max_rows = rows;
     {
         const int64_t nb0 = ((int64_t)c->M + rows - 1) / rows;
         const int64_t waves = (nb0 + c->sm_count - 1) / c->sm_count;
-        if (c->edge_balance && waves <= 8) {
+        if (c->edge_balance == 1 && waves <= 8) {
             const int r = (int)(((int64_t)c->M + waves * c->sm_count - 1) / (waves * c->sm_count));
             if (r >= (rows + 1) / 2) max_rows = std::min(rows, r);
         }
+        // SX_EDGE_BALANCE=2 (A/B): fatter blocks, up to two sweeps of the lane groups, the grid one wave where that is enough
+        if (c->edge_balance == 2 && nb0 > c->sm_count && nb0 <= 2 * (int64_t)c->sm_count)
+            max_rows = std::min(2 * rows, (int)(((int64_t)c->M + c->sm_count - 1) / c->sm_count));
+        if (c->edge_balance == 3) max_rows = 2 * rows;
     }
+    p->max_rows = max_rows;
     const int expect = (c->M + max_rows - 1) / max_rows;
     const int64_t nnz_target = 0;
     // as many blocks per SM as leave every block uncut (6, 4, 3, 2 or 1); if even one block per SM
@@ -1469,7 +1476,7 @@ int launch_edge_host(sx_ctx *c, const EdgePlan *ep, int N, T alpha, const T *Bh,
     constexpr int E = sx::VecOf<T>::E, THREADS = sx::EdgeShape<G>::THREADS;
     *done = false;
     auto kern = sx::spmm_edgelist_host_kernel<T, G, STRICT>;
-    const int tile_ld = sx::EdgeShape<G>::ROWS + 1;
+    const int tile_ld = std::max(sx::EdgeShape<G>::ROWS, ep->max_rows) + 1;
     const int share_ld = ((c->K + ep->nblocks - 1) / ep->nblocks) | 1;
     const size_t tile_off = ((size_t)std::max(ep->max_smem, 16) + 15) & ~(size_t)15;
     const size_t share_off = tile_off + (((size_t)N * tile_ld * sizeof(T) + 15) & ~(size_t)15);
