@@ -246,6 +246,15 @@ int sx_spmm_f32(sx_ctx *ctx, int N, float alpha, const float *B, float beta, flo
 int sx_spmm_f64(sx_ctx *ctx, int N, double alpha, const double *B, double beta, double *C,
                 int rp_time, double *kernel_ns);
 
+/* The same call without its final host synchronisation (rp_time = 1, no kernel time): it returns once
+ * the work is enqueued on the context's stream; B and C must stay valid and untouched until
+ * sx_synchronize(ctx) returns, which also reports a failed call.  For callers that keep several
+ * calls in flight -- two contexts on two streams with double-buffered page-locked operands: one
+ * call's results leave over PCIe while the next call's operands arrive (the link is full duplex).
+ * Pageable operands make the call blocking (cudaMemcpyAsync from/to pageable memory is). */
+int sx_spmm_enqueue_f32(sx_ctx *ctx, int N, float alpha, const float *B, float beta, float *C);
+int sx_spmm_enqueue_f64(sx_ctx *ctx, int N, double alpha, const double *B, double beta, double *C);
+
 /* ---- the same call in stages (what sx_spmm_* does internally) ------------- */
 int sx_stage_B_f32(sx_ctx *ctx, int N, const float *B_colmajor);
 int sx_stage_B_f64(sx_ctx *ctx, int N, const double *B_colmajor);

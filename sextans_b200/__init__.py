@@ -83,6 +83,8 @@ def lib():
         "sx_spmm_f64": ([vp, i, C.c_double, vp, C.c_double, vp, i, _PD], i),
         "sx_stage_B_f32": ([vp, i, vp], i), "sx_stage_B_f64": ([vp, i, vp], i),
         "sx_stage_C_f32": ([vp, i, vp], i), "sx_stage_C_f64": ([vp, i, vp], i),
+        "sx_spmm_enqueue_f32": ([vp, i, C.c_float, vp, C.c_float, vp], i),
+        "sx_spmm_enqueue_f64": ([vp, i, C.c_double, vp, C.c_double, vp], i),
         "sx_spmm_staged_B_f32": ([vp, i, C.c_float, C.c_float, vp], i),
         "sx_spmm_staged_B_f64": ([vp, i, C.c_double, C.c_double, vp], i),
         "sx_launch_f32": ([vp, C.c_float, C.c_float, i, _PD], i),
@@ -454,6 +456,19 @@ class Engine:
         ns = C.c_double()
         _check(fn(self._ctx, N, ct(alpha), _host_ptr(B), ct(beta), _host_ptr(C_inout), rp_time, C.byref(ns)))
         return ns.value
+
+    def spmm_enqueue(self, N, alpha, B, beta, C_inout):
+        """The host-facing call without its final host sync (sx_spmm_enqueue_*): B and C_inout (page-locked,
+        of the matrix dtype) must stay valid and untouched until ``synchronize()``."""
+        suf, ct, _ = _suffix(self.dtype)
+        if B.dtype != self.dtype or C_inout.dtype != self.dtype or not B.flags.c_contiguous or not C_inout.flags.c_contiguous:
+            raise ValueError("B and C must be contiguous arrays of the matrix dtype")
+        if B.size != self.K * N or C_inout.size != self.M * N:
+            raise ValueError("B must hold K*N and C must hold M*N elements")
+        fn = self._L.sx_spmm_enqueue_f64 if suf == "f64" else self._L.sx_spmm_enqueue_f32
+        status = fn(self._ctx, N, ct(alpha), B.ctypes.data, ct(beta), C_inout.ctypes.data)
+        if status != 0:
+            _check(status)
 
     def spmm_staged_B(self, N, alpha, beta, C_inout):
         """One blocking SpMM on the B image the context already holds (stage_B, a peer's push, a

@@ -192,6 +192,7 @@ struct sx_ctx {
     struct Occ { const void *kern; size_t smem; int per_sm; };
     std::vector<Occ> host_occ;
     int edge_balance = 0;  // experiment knob (env SX_EDGE_BALANCE=1): edge-list grids sized to whole waves of the SMs
+    bool defer_sync = false;  // inside sx_spmm_enqueue_*: the host-facing call returns without its final host sync
     int host_coop = 1;   // experiment knob (env SX_HOST_COOP=0): launch the one-kernel call without the cooperative attribute
     int host_depth = 0;  // experiment knob (env SX_HOST_DEPTH): column groups requested ahead in the one-kernel call
     int host_groups = 0; // SX_OPT_HOST_GROUPS: column groups of the fused host-facing call (0 auto)
@@ -1415,7 +1416,19 @@ int enqueue_launch(sx_ctx *c, T alpha, T beta, int rp_time) {
 }
 
 // wait for everything enqueued so far, then read the kernel time
+// a block of the one-kernel host call gave up waiting for the others (flag in page-locked host memory, raised by the kernel)
+int check_host_flag(sx_ctx *c) {
+    if (c->host_flag && *c->host_flag) {
+        *c->host_flag = 0;
+        c->host_counters.release();
+        c->exchange_timeouts_host++;
+        return fail(SX_ERR_STATE, "the one-kernel host call timed out waiting for its own blocks (is another kernel holding the GPU?)");
+    }
+    return SX_OK;
+}
+
 int finish_stream(sx_ctx *c, double *kernel_ns) {
+    if (c->defer_sync && !kernel_ns) return SX_OK;  // sx_spmm_enqueue_*: the caller synchronises (sx_synchronize)
     SX_CUDA(cudaStreamSynchronize(c->stream));
     if (kernel_ns) {
         float ms = 0.f;
@@ -1712,13 +1725,7 @@ int spmm_host(sx_ctx *c, int N, T alpha, const T *B, T beta, T *C, int rp_time, 
             if (done) {
                 c->last_path = c->last_kernel / 10000 == 10 ? 3 : 2;
                 if ((rc = finish_stream(c, nullptr))) return rc;
-                if (c->host_flag && *c->host_flag) {  // a block of the one-kernel call gave up waiting for the others
-                    *c->host_flag = 0;
-                    c->host_counters.release();
-                    c->exchange_timeouts_host++;
-                    return fail(SX_ERR_STATE, "the one-kernel host call timed out waiting for its own blocks (is another kernel holding the GPU?)");
-                }
-                return SX_OK;
+                return c->defer_sync ? SX_OK : check_host_flag(c);
             }
         }
         if ((rc = set_columns(c, N))) return rc;
@@ -1764,6 +1771,18 @@ int spmm_host(sx_ctx *c, int N, T alpha, const T *B, T beta, T *C, int rp_time, 
     if (out_bytes) SX_CUDA(cudaMemcpyAsync(C, c->stage.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
     c->last_path = 0;
     return finish_stream(c, kernel_ns);
+}
+
+// The host-facing call without its final host synchronisation: B and C must stay valid and untouched until
+// sx_synchronize returns.  What a caller that keeps several calls in flight (two contexts on two streams, double-buffered
+// page-locked operands) uses: one call's results leave over PCIe while the next call's operands arrive.
+template <typename T>
+int spmm_enqueue(sx_ctx *c, int N, T alpha, const T *B, T beta, T *C) {
+    if (!c) return fail(SX_ERR_INVALID, "null context");
+    c->defer_sync = true;
+    const int rc = spmm_host<T>(c, N, alpha, B, beta, C, 1, nullptr);
+    c->defer_sync = false;
+    return rc;
 }
 
 }  // namespace
@@ -1994,8 +2013,11 @@ int sx_synchronize(sx_ctx *c) {
     int rc = bind(c);
     if (rc) return rc;
     SX_CUDA(cudaStreamSynchronize(c->stream));
-    return SX_OK;
+    return check_host_flag(c);
 }
+
+int sx_spmm_enqueue_f32(sx_ctx *c, int N, float alpha, const float *B, float beta, float *C) { return spmm_enqueue<float>(c, N, alpha, B, beta, C); }
+int sx_spmm_enqueue_f64(sx_ctx *c, int N, double alpha, const double *B, double beta, double *C) { return spmm_enqueue<double>(c, N, alpha, B, beta, C); }
 
 int sx_upload_csr_f32(sx_ctx *c, int M, int K, int64_t nnz, const int32_t *rowptr, const int32_t *colidx, const float *val) {
     return upload_csr<float>(c, M, K, nnz, rowptr, colidx, val);

@@ -325,3 +325,36 @@ def test_spmm_on_the_staged_B_image_with_host_C(eng, dtype, pinned, M, K, N):
             assert eng.info(sx.INFO_HOST_PATH) == 2 and eng.info(sx.INFO_LAST_KERNEL) // 10000 == 9
         if not pinned:
             assert eng.info(sx.INFO_HOST_PATH) == 0
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_calls_in_flight_on_two_contexts(dtype):
+    """sx_spmm_enqueue_*: the host-facing call without its final host sync.  Two contexts (two streams) with
+    double-buffered page-locked operands keep two calls in flight -- one call's results leave over PCIe
+    while the next call's operands arrive; sx_synchronize hands a buffer back.  Every step bitwise the oracle."""
+    M, K, N = 4704, 4704, 16
+    rp, ci, v = banded_csr(M, K, 150, 20, 11, dtype)
+    engs = [sx.Engine(0), sx.Engine(0)]
+    try:
+        for e in engs:
+            e.upload_csr(M, K, rp, ci, v)
+        hB = [sx.pinned_empty(K * N, dtype) for _ in range(2)]
+        hC = [sx.pinned_empty(M * N, dtype) for _ in range(2)]
+        refs = [None, None]
+        for step in range(9):
+            j = step % 2
+            if step >= 2:
+                engs[j].synchronize()                                   # the call that used buffer j two steps ago is complete
+                assert engs[j].info(sx.INFO_HOST_PATH) == 3
+                assert np.array_equal(bits(np.asarray(hC[j])), bits(refs[j])), step - 2
+            B, Cin = random_dense(M, K, N, 300 + step, dtype)
+            hB[j][:] = B
+            hC[j][:] = Cin
+            refs[j] = oracle.spmm_csr(M, N, K, rp, ci, v, dtype(0.85), B, dtype(-2.06), Cin.copy())
+            engs[j].spmm_enqueue(N, dtype(0.85), hB[j], dtype(-2.06), hC[j])
+        for j in range(2):
+            engs[j].synchronize()
+            assert np.array_equal(bits(np.asarray(hC[j])), bits(refs[j]))
+    finally:
+        for e in engs:
+            e.close()
