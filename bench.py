@@ -67,7 +67,8 @@ CONFIGS_NGPU = [("uniform_c4", "uniform", 128), ("powerlaw_c5", "powerlaw", 16)]
 ALPHA, BETA = float(np.float32(0.85)), float(np.float32(-2.06))   # host.cpp:29-30
 L2_BYTES = 126 * 1024 * 1024
 KERNEL_NAMES = {1: "spmm_rows_kernel", 2: "spmm_staged_kernel", 3: "spmm_window_kernel", 4: "spmm_panels_dmma_kernel",
-                5: "spmm_staged_kernel<WIN>", 7: "spmm_slide_kernel", 8: "spmm_edgelist_kernel", 9: "spmm_edgelist_kernel<HOSTC>"}
+                5: "spmm_staged_kernel<WIN>", 7: "spmm_slide_kernel", 8: "spmm_edgelist_kernel", 9: "spmm_edgelist_kernel<HOSTC>",
+                10: "spmm_edgelist_host_kernel", 11: "spmm_edgelist_batch_kernel"}
 
 
 def parse():
@@ -592,7 +593,8 @@ def run_batched(w, args, dev, stream, peak, nb):
     return {"nb": nb, "ms_per_spmm": round(ms, 6), "gflops": round(2.0 * nnz * N / (ms * 1e-3) / 1e9, 1),
             "frac": round(alg / (ms * 1e-3) / 1e9 / peak, 4), "launches_per_batch": int(launches),
             "kernel_family": int(kernel // 10000), "triples": T, "bit_exact_every_triple": bit_exact,
-            "note": f"{nb} distinct (B, C_in, C_out) triples per launch, same A (grid.y = nb); cold: {T} triples = {T * per / 1e6:.0f} MB rotate; "
+            "kernel": KERNEL_NAMES.get(int(kernel // 10000), "?"),
+            "note": f"{nb} distinct (B, C_in, C_out) triples per launch, same A; cold: {T} triples = {T * per / 1e6:.0f} MB rotate; "
                     "frac counts A once per batch"}
 
 
