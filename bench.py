@@ -68,7 +68,7 @@ ALPHA, BETA = float(np.float32(0.85)), float(np.float32(-2.06))   # host.cpp:29-
 L2_BYTES = 126 * 1024 * 1024
 KERNEL_NAMES = {1: "spmm_rows_kernel", 2: "spmm_staged_kernel", 3: "spmm_window_kernel", 4: "spmm_panels_dmma_kernel",
                 5: "spmm_staged_kernel<WIN>", 7: "spmm_slide_kernel", 8: "spmm_edgelist_kernel", 9: "spmm_edgelist_kernel<HOSTC>",
-                10: "spmm_edgelist_host_kernel", 11: "spmm_edgelist_batch_kernel"}
+                10: "spmm_edgelist_host_kernel"}
 
 
 def parse():

@@ -1021,91 +1021,12 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
     // kernel: the kernel boundary is the fence, and this kernel's tail stays free of system-scope fences)
 }
 
-// ---- several B's in one launch, PERSISTENT form (sx_spmm_device_batch_*) ----
-// spmm_edgelist_kernel with grid.y = nb gives every (row block, operand) pair a thread block of its own: each one pays
-// the whole chain prologue -> window staging -> rows -> store (~4 us), three of them per SM at a time, and a batch of 20
-// SpMMs of nasa4704 N=16 fp64 costs 1.48 us per SpMM (ncu: L1/shared memory 58 % busy, occupancy 33 %).  Here a block
-// owns its row block for a SLICE of the operands (blockIdx.y, stepping by gridDim.y; the grid is sized so that all of
-// it is resident): the A side is staged ONCE, and the window of operand k+1 is copied into a second buffer (cp.async,
-// one commit group) while the rows of operand k are walked -- the staging latency leaves the chain.  Same
-// edge_row_walk, same order of operations: bit-identical to nb single launches.
-//   shared memory: window 0 | window 1 | values | local columns | column list | row pointers
-template <typename T, int G, bool STRICT>
-__global__ void __launch_bounds__(EdgeShape<G>::THREADS, 2)
-spmm_edgelist_batch_kernel(const int4 *__restrict__ blocks, const int *__restrict__ cols, const int *__restrict__ rowptr,
-                           const uint16_t *__restrict__ lcol, const T *__restrict__ val, const T *__restrict__ B0,
-                           const uint32_t ldbv, const T *Cin0, T *Cout0, const uint32_t ldcv, const T alpha, const T beta,
-                           const int nvec, const int nbatch, const int64_t strideB, const int64_t strideC) {
-    using V = typename VecOf<T>::type;
-    constexpr int THREADS = EdgeShape<G>::THREADS, ROWS = EdgeShape<G>::ROWS;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t bar;
-    const int lg = threadIdx.x & (G - 1);
-    const int rl = threadIdx.x / G;
-    const int4 b0 = __ldg(blocks + 2 * blockIdx.x), b1 = __ldg(blocks + 2 * blockIdx.x + 1);
-    const int row0 = b0.x, nrows = b0.y, jb = b0.z, je = b0.w;
-    const int ncols = b1.y;
-    const uint32_t rowbytes = ldbv * 16u;
-    const uint32_t wbytes = (uint32_t)ncols * (G * 16u);
-    const int jal = jb & ~7;
-    const bool has = je > jb;
-    const uint32_t na = has ? (uint32_t)((je - jal + 7) & ~7) : 0u;
-    const uint32_t ncp = (uint32_t)(ncols + 3) & ~3u;
-    unsigned char *abase = smem_raw + 2 * (size_t)wbytes;
-    const T *sval = reinterpret_cast<const T *>(abase);
-    const uint16_t *scol = reinterpret_cast<const uint16_t *>(abase + (size_t)na * sizeof(T));
-    const int *scols = reinterpret_cast<const int *>(abase + (size_t)na * (sizeof(T) + 2));
-    int *srp = const_cast<int *>(scols) + ncp;
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && has) {  // the A side by TMA, once for every operand of the slice
-        const uint64_t pol_a = policy_evict_last();  // the other blocks of this row block (other slices) read it too
-        mbar_expect_tx(&bar, na * (uint32_t)(sizeof(T) + 2) + ncp * 4u);
-        tma_bulk_g2s(const_cast<int *>(scols), cols + b1.x, ncp * 4u, &bar, pol_a);
-        tma_bulk_g2s(const_cast<T *>(sval), val + jal, na * (uint32_t)sizeof(T), &bar, pol_a);
-        tma_bulk_g2s(const_cast<uint16_t *>(scol), lcol + jal, na * 2u, &bar, pol_a);
-    }
-    for (int i = threadIdx.x; i <= nrows; i += THREADS) srp[i] = __ldg(rowptr + row0 + i);
-    if (has) mbar_wait(&bar, 0);
-    __syncthreads();  // srp
-    const bool lane_on = lg < nvec;
-    auto stage = [&](const int b, const int buf) {  // the window of operand b into buffer buf: one commit group
-        const unsigned char *Bb = reinterpret_cast<const unsigned char *>(B0 + (size_t)b * strideB) + lg * 16;
-        unsigned char *win = smem_raw + (size_t)buf * wbytes;
-        if (lane_on)
-            for (int lr = rl; lr < ncols; lr += ROWS)
-                cp_async_16(win + ((size_t)lr * G + lg) * 16, Bb + (size_t)(uint32_t)scols[lr] * rowbytes);
-        cp_async_commit();
-    };
-    const T *sv = sval - jal;
-    const uint16_t *sc = scol - jal;
-    int b = blockIdx.y;
-    if (b < nbatch) stage(b, 0);
-    for (int k = 0; b < nbatch; b += gridDim.y, ++k) {
-        const int bn = b + gridDim.y;
-        if (bn < nbatch) stage(bn, (k + 1) & 1);  // (its buffer was released by the barrier that ended operand k-1)
-        else cp_async_commit();                   // an empty group keeps the count uniform
-        const V *Cv = reinterpret_cast<const V *>(Cin0 + (size_t)b * strideC) + (size_t)row0 * ldcv + lg;
-        V *Ov = reinterpret_cast<V *>(Cout0 + (size_t)b * strideC) + (size_t)row0 * ldcv + lg;
-        V cin_next;
-        vzero(cin_next);
-        if (lane_on && rl < nrows) cin_next = Cv[(size_t)rl * ldcv];
-        cp_async_wait_pending(1);  // everything but the group just committed: this operand's window has landed
-        __syncthreads();
-        const V *w = reinterpret_cast<const V *>(smem_raw + (size_t)(k & 1) * wbytes) + lg;
-        if (lane_on)
-            for (int rr = rl; rr < nrows; rr += ROWS) {
-                const V cin = cin_next;
-                if (rr + ROWS < nrows) cin_next = Cv[(size_t)(rr + ROWS) * ldcv];
-                const V acc = edge_row_walk<T, G, STRICT>(sc, sv, w, srp[rr], srp[rr + 1]);
-                Ov[(size_t)rr * ldcv] = vaxpby<STRICT>(alpha, acc, beta, cin);
-            }
-        __syncthreads();  // every lane group is done with this buffer before the operand after next is copied into it
-    }
-}
+// (A PERSISTENT form of the batched launch -- a block keeps its row block for a slice of the operands, the A side staged
+// once, the window of operand k+1 copied by cp.async while the rows of operand k are walked -- was built, emulated and run:
+// bit-exact, and no faster than grid.y = nb blocks of spmm_edgelist_kernel on nasa4704 (1.49 us per SpMM either way) and
+// slower on pcrystk02 (N=16: 5.79 against 3.78 us; its second window buffer costs a resident block per SM).  What bounds a
+// batch is the walk itself -- shared-memory instructions of three co-resident blocks, ncu: L1 58 % busy -- not the
+// staging latency.  Removed; commit d557125 holds it, profiles/r02_batch_persistent.txt the numbers.)
 
 // ---- the host-facing call as ONE kernel (sx_spmm_* with small page-locked operands, kernel_ns == NULL) ----
 // The pieces of the call were measured on the host's clock (scripts/micro/pcie_floor.cu, profiles/r02_pcie_floor.txt):

@@ -84,7 +84,7 @@ struct Plan {
 struct EdgePlan {
     int row_bytes = 0, rows = 0;  // key: bytes of a B row, rows per block
     bool usable = false;  // planned, and staging a block's distinct B rows beats gathering per nonzero
-    int nblocks = 0, max_smem = 0, max_smem_batch = 0, max_rows = 0;  // max_smem_batch: with a second window buffer (batch kernel)  // max_rows: most rows a block holds (the HOSTC tiles are sized by it)
+    int nblocks = 0, max_smem = 0, max_rows = 0;  // max_rows: most rows a block holds (the HOSTC tiles are sized by it)  // max_rows: most rows a block holds (the HOSTC tiles are sized by it)
     int64_t total_cols = 0;
     DevBuf blocks, cols, lcol;
     void release() { blocks.release(); cols.release(); lcol.release(); }
@@ -193,7 +193,6 @@ struct sx_ctx {
     std::vector<Occ> host_occ;
     int edge_balance = 0;  // experiment knob (env SX_EDGE_BALANCE=1): edge-list grids sized to whole waves of the SMs
     bool defer_sync = false;  // inside sx_spmm_enqueue_*: the host-facing call returns without its final host sync
-    int batch_persistent = 1;  // experiment knob (env SX_BATCH_PERSISTENT=0): a batch as grid.y = nb launches of spmm_edgelist_kernel
     int host_coop = 1;   // experiment knob (env SX_HOST_COOP=0): launch the one-kernel call without the cooperative attribute
     int host_depth = 0;  // experiment knob (env SX_HOST_DEPTH): column groups requested ahead in the one-kernel call
     int host_groups = 0; // SX_OPT_HOST_GROUPS: column groups of the fused host-facing call (0 auto)
@@ -268,34 +267,6 @@ int launch_edge(sx_ctx *c, const EdgePlan *ep, int N, T alpha, const T *dB, int6
     cudaLaunchConfig_t cfg = {};
     const int nbatch = HOSTC ? 1 : c->batch;
     if (nbatch > 1 && (c->x_ready || c->p_npeers)) return fail(SX_ERR_STATE, "a batched SpMM cannot carry the multi-GPU exchange");
-    if constexpr (!HOSTC) {
-        // a batch: the persistent form (a block keeps its row block for a slice of the operands, A staged once, the next
-        // operand's window copied while this one's rows are walked), its grid sized to be resident at once
-        const size_t bsmem = (size_t)std::max(ep->max_smem_batch, 16);
-        if (nbatch > 1 && c->batch_persistent && bsmem <= 227 * 1024 - 1024 && c->win_col0 == 0) {
-            auto bk = sx::spmm_edgelist_batch_kernel<T, G, STRICT>;
-            int per_sm = -1;
-            for (const auto &o : c->host_occ)
-                if (o.kern == (const void *)bk && o.smem == bsmem) per_sm = o.per_sm;
-            if (per_sm < 0) {
-                if (bsmem > 48 * 1024) SX_CUDA(cudaFuncSetAttribute(bk, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-                SX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk, sx::EdgeShape<G>::THREADS, bsmem));
-                c->host_occ.push_back({(const void *)bk, bsmem, per_sm});
-            }
-            const int64_t resident = (int64_t)per_sm * c->sm_count;
-            const int slices = (int)std::max<int64_t>(1, std::min<int64_t>(nbatch, resident / std::max(1, ep->nblocks)));
-            bk<<<dim3((unsigned)ep->nblocks, (unsigned)slices), sx::EdgeShape<G>::THREADS, bsmem, c->stream>>>(
-                (const int4 *)ep->blocks.p, (const int *)ep->cols.p, (const int *)c->rowptr.p, (const uint16_t *)ep->lcol.p,
-                (const T *)c->val.p, dB, (uint32_t)(ldb / E), dCin, dCout, (uint32_t)(ldc / E), alpha, beta, nvec, nbatch,
-                c->batch_sB, c->batch_sC);
-            SX_CUDA(cudaGetLastError());
-            c->batch_taken = true;
-            c->launches++;
-            c->last_edge_plan = ep;
-            c->last_kernel = 110000 + G * 100 + 10 + (STRICT ? 0 : 1);
-            return SX_OK;
-        }
-    }
     cfg.gridDim = dim3((unsigned)ep->nblocks, (unsigned)nbatch);
     cfg.blockDim = dim3(sx::EdgeShape<G>::THREADS);
     cfg.dynamicSmemBytes = smem;
@@ -1050,9 +1021,6 @@ int get_edge_plan(sx_ctx *c, int row_bytes, int elem_bytes, int rows, const Edge
         if (!rc) {
             p->nblocks = nb;
             p->max_smem = max_smem;
-            p->max_smem_batch = 0;
-            for (int bI = 0; bI < nb; ++bI)  // block record: {row_begin, nrows, nnz_begin, nnz_end, col_begin, ncols, 0, smem_bytes}
-                p->max_smem_batch = std::max(p->max_smem_batch, blocks[(size_t)bI * 8 + 7] + blocks[(size_t)bI * 8 + 5] * (row_bytes));
             p->total_cols = total;
             p->usable = true;
         }
@@ -1875,7 +1843,6 @@ int sx_create(int device, sx_ctx **out) {
     c->sm_count = prop.multiProcessorCount;
     if (const char *e = std::getenv("SX_HOST_DEPTH")) c->host_depth = std::atoi(e);
     if (const char *e = std::getenv("SX_HOST_COOP")) c->host_coop = std::atoi(e);
-    if (const char *e = std::getenv("SX_BATCH_PERSISTENT")) c->batch_persistent = std::atoi(e);
     if (const char *e = std::getenv("SX_EDGE_BALANCE")) c->edge_balance = std::atoi(e);
     cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);

@@ -667,39 +667,6 @@ void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, u
         std::printf("%-34s %s M=%d K=%d N=%d G=%d: %s\n", "edge lists HOSTC (C in the caller's array)", tname, M, K, N, G, okh ? "bit-exact" : "MISMATCH");
         if (!okh) ++failures;
     }
-    {   // several B's in one launch, persistent form: 3 operands over 2 slices (the second slice gets one operand),
-        // the operands at strides with slack between them; every one bit-exact, the slack untouched
-        const int nbat = 3;
-        const int64_t sB = (int64_t)K * ld + 8 * E, sC = (int64_t)M * ld + 4 * E;
-        Aligned<T> Bs((size_t)nbat * sB), Cis((size_t)nbat * sC), Cos((size_t)nbat * sC);
-        std::vector<std::vector<T>> refs;
-        for (int b = 0; b < nbat; ++b) {
-            for (int64_t i = 0; i < (int64_t)K * ld; ++i) Bs.p[b * sB + i] = (i % ld) < N ? (T)U(rng) : (T)0;
-            for (int64_t i = 0; i < (int64_t)M * ld; ++i) Cis.p[b * sC + i] = (i % ld) < N ? (T)U(rng) : (T)0;
-            std::vector<T> r((size_t)M * ld);
-            reference<T>(a, hval, N, Bs.p + b * sB, ld, alpha, beta, Cis.p + b * sC, r.data(), ld);
-            refs.push_back(r);
-        }
-        std::fill(Cos.p, Cos.p + (int64_t)nbat * sC, (T)777);
-        int bsmem = 16;
-        for (int b = 0; b < nb; ++b) bsmem = std::max(bsmem, blocks[(size_t)b * 8 + 7] + blocks[(size_t)b * 8 + 5] * G * 16);
-        for (unsigned slice = 0; slice < 2; ++slice) {   // the emulator runs a 1-D grid: one pass per value of blockIdx.y
-            sx_emu::launch((unsigned)nb, THREADS, (size_t)bsmem, [&] {
-                blockIdx.y = slice;
-                gridDim.y = 2;
-                sx::spmm_edgelist_batch_kernel<T, G, true>(reinterpret_cast<const int4 *>(dblocks.p), dcols.p, rp.p, dlcol.p, val.p,
-                                                           Bs.p, ldv, Cis.p, Cos.p, ldv, alpha, beta, nvec, nbat, sB, sC);
-            });
-        }
-        gridDim.y = 1;
-        bool okb = true;
-        for (int b = 0; b < nbat && okb; ++b) {
-            for (int i = 0; i < M && okb; ++i) okb = same_bits(Cos.p + b * sC + (int64_t)i * ld, refs[b].data() + (int64_t)i * ld, (size_t)N);
-            for (int64_t i = (int64_t)M * ld; i < sC && okb; ++i) okb = Cos.p[b * sC + i] == (T)777;
-        }
-        std::printf("%-34s %s M=%d K=%d N=%d G=%d: %s\n", "edge lists BATCH (persistent)", tname, M, K, N, G, okb ? "bit-exact" : "MISMATCH");
-        if (!okb) ++failures;
-    }
     if (max_rows == ROWS) {
         // the host-facing call as ONE kernel: B and C column-major in the caller's arrays, the B image built by the blocks
         // themselves.  Blocks run one after the other here, so the grid-wide wait cannot be emulated: pass 1 (on a scratch

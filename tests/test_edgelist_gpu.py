@@ -248,8 +248,7 @@ def test_batched_call_matches_one_call_per_operand(eng, dtype, kernel, M, K, N, 
     eng.spmm_device_batch(N, nb, dtype(0.85), dB, ld, sB, dtype(-2.06), dCin, dCout, ld, sC)
     torch.cuda.synchronize()
     if kernel == 0 and N * np.dtype(dtype).itemsize <= 256:
-        # family 11: the persistent batch kernel (a block keeps its row block for a slice of the operands)
-        assert eng.info(sx.INFO_LAST_KERNEL) // 10000 == 11 and eng.info(sx.INFO_LAUNCHES) - l0 == 1
+        assert eng.info(sx.INFO_LAST_KERNEL) // 10000 == 8 and eng.info(sx.INFO_LAUNCHES) - l0 == 1
     out = dCout.cpu().numpy()
     for b in range(nb):
         got = out[b * sC: b * sC + M * ld].reshape(M, ld)[:, :N].T.ravel()
