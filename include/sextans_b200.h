@@ -406,17 +406,24 @@ int sx_plan_slide(int M, const int32_t *rowptr, const int32_t *colidx, int nchai
  *   nnz_target   nonzeros per block to aim for (0: blocks of max_rows rows)
  *   smem_budget  shared memory one block may use (window + its slices of values and local
  *                columns + its column list + its row pointers)
- *   blocks  8 ints per block: {row_begin, nrows, nnz_begin, nnz_end, col_begin, ncols, 0, smem_bytes}
+ * The streams of A are ROW-ALIGNED: row r's entries start at prow[r], a multiple of 8 entries, and
+ * are padded to a multiple of 8, so that the kernel fetches 8 (local column, value) pairs with whole
+ * 16-byte shared-memory loads; the pad entries' additions are predicated off (the reference pads its
+ * PE lists with bubbles, src/sparse_helper.h:345-403).
+ *   blocks  8 ints per block: {row_begin, nrows, pnz_begin, pnz_end, col_begin, ncols, 0, smem_bytes}
+ *           with pnz_* in padded coordinates (prow[row_begin], prow[row_begin + nrows])
  *   cols    *ncols ints: the blocks' column lists back to back, each starting at a multiple of 4
  *           entries; pad entries repeat the block's last column
- *   lcol    one uint16 per nonzero, parallel to colidx
+ *   prow    M + 1 ints: padded row starts
+ *   lcol    prow[M] uint16: entry k of row r at prow[r] + k, pad entries 0
  *   total_cols  sum of ncols over the blocks (B rows staged per SpMM)
  *   max_smem    largest smem_bytes
  * *nblocks = 0 (and SX_OK) if some single row does not fit the budget.  Arrays are malloc'ed;
  * release each with sx_free. */
 int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colidx, int row_bytes, int elem_bytes,
                        int max_rows, int64_t nnz_target, int smem_budget, int *nblocks, int32_t **blocks,
-                       int64_t *ncols, int32_t **cols, uint16_t **lcol, int64_t *total_cols, int *max_smem);
+                       int64_t *ncols, int32_t **cols, uint16_t **lcol, int64_t *total_cols, int *max_smem,
+                       int32_t **prow);
 int sx_split_col_windows(int M, int K, const int32_t *rowptr, const int32_t *colidx, int window_rows,
                          int *nwin, int32_t **win_rowptr, int64_t **win_base, int32_t **order,
                          int *ascending);

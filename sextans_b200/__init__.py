@@ -121,7 +121,8 @@ def lib():
         "sx_plan_slide": ([i, _PI32, _PI32, i, C.POINTER(i), C.POINTER(_PI32), C.POINTER(i), C.POINTER(_PI32),
                            C.POINTER(i), C.POINTER(i)], i),
         "sx_plan_edge_lists": ([i, i, _PI32, _PI32, i, i, i, i64, i, C.POINTER(i), C.POINTER(_PI32), C.POINTER(i64),
-                                C.POINTER(_PI32), C.POINTER(C.POINTER(C.c_uint16)), C.POINTER(i64), C.POINTER(i)], i),
+                                C.POINTER(_PI32), C.POINTER(C.POINTER(C.c_uint16)), C.POINTER(i64), C.POINTER(i),
+                                C.POINTER(_PI32)], i),
         "sx_free": ([vp], None),
         "sx_sextans_invoke": ([vp, _PI32, _A8, _F4, _F8, _F8, i, i, i, i, i, i, i, _PD], i),
         "sx_sextans_last_kernel_ns": ([], C.c_double),
@@ -214,26 +215,29 @@ def plan_slide(M, rowptr, colidx, nchains):
 
 def plan_edge_lists(M, K, rowptr, colidx, row_bytes, elem_bytes, smem_budget, max_rows=32, nnz_target=0):
     """Plan of the edge-list kernel (sx_plan_edge_lists) ->
-    (blocks [nblocks, 8], cols [ncols] int32, lcol [nnz] uint16, total_cols, max_smem); nblocks == 0 if some
-    row does not fit ``smem_budget``."""
+    (blocks [nblocks, 8], cols [ncols] int32, lcol [prow[M]] uint16, total_cols, max_smem, prow [M+1] int32);
+    the streams are row-aligned (row r's entries at prow[r] + k, rows padded to multiples of 8 entries, pad
+    entries 0; blocks[:, 2:4] in padded coordinates); nblocks == 0 if some row does not fit ``smem_budget``."""
     rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
     colidx = np.ascontiguousarray(colidx, dtype=np.int32)
     nb, ms, tot, nc = C.c_int(), C.c_int(), C.c_int64(), C.c_int64()
-    bl, co, lc = _PI32(), _PI32(), C.POINTER(C.c_uint16)()
+    bl, co, lc, pr = _PI32(), _PI32(), C.POINTER(C.c_uint16)(), _PI32()
     L = lib()
     _check(L.sx_plan_edge_lists(M, K, rowptr.ctypes.data_as(_PI32), colidx.ctypes.data_as(_PI32), row_bytes, elem_bytes,
                                 max_rows, nnz_target, smem_budget, C.byref(nb), C.byref(bl), C.byref(nc), C.byref(co),
-                                C.byref(lc), C.byref(tot), C.byref(ms)))
+                                C.byref(lc), C.byref(tot), C.byref(ms), C.byref(pr)))
     if nb.value == 0:
-        return np.zeros((0, 8), np.int32), np.zeros(0, np.int32), np.zeros(0, np.uint16), 0, 0
+        L.sx_free(pr)
+        return np.zeros((0, 8), np.int32), np.zeros(0, np.int32), np.zeros(0, np.uint16), 0, 0, np.zeros(M + 1, np.int32)
     try:
-        n = int(rowptr[M])
+        prow = np.ctypeslib.as_array(pr, shape=(M + 1,)).copy()
+        n = int(prow[M])
         blocks = np.ctypeslib.as_array(bl, shape=(nb.value * 8,)).reshape(-1, 8).copy()
         cols = np.ctypeslib.as_array(co, shape=(max(nc.value, 1),))[:nc.value].copy()
         lcol = np.ctypeslib.as_array(lc, shape=(max(n, 1),))[:n].copy()
     finally:
-        L.sx_free(bl), L.sx_free(co), L.sx_free(lc)
-    return blocks, cols, lcol, tot.value, ms.value
+        L.sx_free(bl), L.sx_free(co), L.sx_free(lc), L.sx_free(pr)
+    return blocks, cols, lcol, tot.value, ms.value, prow
 
 
 def split_col_windows(M, K, rowptr, colidx, window_rows):

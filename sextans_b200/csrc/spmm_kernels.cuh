@@ -693,7 +693,7 @@ spmm_window_kernel(const int M, const int4 *__restrict__ blocks, const int *__re
 // pcrystk02: 317 against 918): a third of the bytes through L2 and of the shared memory, so 4-6
 // blocks share an SM instead of 1-2, and the index stream of A shrinks from 4 to 2 bytes per nonzero.
 //   block record (two int4): {row_begin, nrows, nnz_begin, nnz_end} {col_begin, ncols, -, smem}
-//   shared memory:           window ncols x (G x 16 bytes) | values | local columns | column list | row pointers
+//   shared memory:           window ncols x (G x 16 bytes) | values | local columns | column list | row starts | row ends
 //                            (A slice from the 8-entry boundary at or below nnz_begin: whole 16-byte units)
 // One lane group per row, stored order, so strict mode is bit-identical to cpu_spmm_CSR.
 // (Round 2 also built "super-rows": the 2-3 consecutive rows of a FEM node share their column
@@ -766,12 +766,23 @@ __device__ __forceinline__ unsigned long long sx_now() {
 #else
 #define SX_TRACE_MARK(i) do { } while (0)
 #endif
-// One row of the edge-list kernels out of shared memory: sc[j] / sv[j] = local column / value of nonzero j,
-// w[local column * G] = this lane's 16-byte piece of that B row.  Stored order, chunks of 8 nonzeros,
-// software-pipelined: the (column, value) pairs of chunk k+1 and the eight B-row pieces of chunk k are in
-// flight while the ordered chain of additions of chunk k runs.
+// One row of the edge-list kernels out of shared memory: sc[j] / sv[j] = local column / value of entry j of the
+// ROW-ALIGNED streams (the row starts at `begin`, a multiple of 8, holds end - begin entries and is padded to a multiple
+// of 8 in storage), w[local column * G] = this lane's 16-byte piece of that B row.  A chunk of 8 (column, value) pairs is
+// ONE 16-byte load of columns and 8 * sizeof(T) / 16 loads of values -- against 8 + 8 scalar loads when rows start
+// anywhere -- next to its 8 loads of B pieces.  Stored order; the columns of chunk k+1 (the critical path: the B pieces'
+// addresses) are fetched while chunk k is added up, the B pieces and values four at a time; the additions of pad entries
+// are predicated off (never an explicit +0, which would turn a -0 sum into +0).
+// Measured on a B200 (profiles/r02_aligned_walk.txt) against the walk over rows that start anywhere (8 + 8 + 8 scalar and
+// vector loads per chunk, 71 registers): nasa4704 N=16 fp64 3.51 -> 3.36 us, pcrystk02 N=8/16/32 7.03/6.75/9.13 ->
+// 5.94/6.50/8.45 us.  Eight B pieces in flight with a look-ahead of columns AND values took 104 registers (two resident
+// blocks instead of three: pcrystk02 N=32 12.1 us, a batch of 20 SpMMs 2.06 instead of 1.49 us each); with a look-ahead
+// of columns only 85-87 registers (3.52 us, N=32 12.0); held to 80 registers 3.71 us.
+// The walk with scalar loads of the pairs (it does not need the rows aligned, only contiguous): kept for 16-lane groups,
+// whose 512-thread blocks are held to 64 registers -- there the eight B pieces in flight it affords beat the vector
+// loads' fewer instructions (pcrystk02 N=64 fp32: 18.3 against 19.6 us).
 template <typename T, int G, bool STRICT>
-__device__ __forceinline__ typename VecOf<T>::type edge_row_walk(const uint16_t *sc, const T *sv, const typename VecOf<T>::type *w,
+__device__ __forceinline__ typename VecOf<T>::type edge_row_walk_scalar(const uint16_t *sc, const T *sv, const typename VecOf<T>::type *w,
                                                                  const int begin, const int end) {
     using V = typename VecOf<T>::type;
     V acc;
@@ -818,6 +829,46 @@ __device__ __forceinline__ typename VecOf<T>::type edge_row_walk(const uint16_t 
     }
     return acc;
 }
+// eight 16-bit local columns in four registers; col8(q, u) = column u
+__device__ __forceinline__ uint4 lds_cols8(const uint16_t *p) { return *reinterpret_cast<const uint4 *>(p); }
+__device__ __forceinline__ uint32_t col8(const uint4 &q, const int u) {
+    const uint32_t wd = (u >> 1) == 0 ? q.x : (u >> 1) == 1 ? q.y : (u >> 1) == 2 ? q.z : q.w;
+    return (u & 1) ? wd >> 16 : wd & 0xffffu;
+}
+template <typename T, int G, bool STRICT>
+__device__ __forceinline__ typename VecOf<T>::type edge_row_walk(const uint16_t *sc, const T *sv, const typename VecOf<T>::type *w,
+                                                                 const int begin, const int end) {
+    using V = typename VecOf<T>::type;
+    if constexpr (G >= 16) return edge_row_walk_scalar<T, G, STRICT>(sc, sv, w, begin, end);
+    V acc;
+    vzero(acc);
+    constexpr int UC = 8;
+    int j = begin;
+    if (j >= end) return acc;
+    uint4 c = lds_cols8(sc + j);
+    for (;;) {
+        const int jn = j + UC;
+        const bool more = jn < end;
+        const uint4 c2 = lds_cols8(sc + (more ? jn : j));  // unconditional load (this chunk again when there is no next one)
+#pragma unroll
+        for (int h = 0; h < UC; h += 4) {
+            if (j + h < end) {
+                T a[4];
+                V b[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) b[u] = w[col8(c, h + u) * G];
+                lds_vec<4>(sv + j + h, a);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (j + h + u < end) vmac<STRICT>(acc, a[u], b[u]);
+            }
+        }
+        if (!more) break;
+        j = jn;
+        c = c2;
+    }
+    return acc;
+}
 template <int G> struct EdgeShape {
     static constexpr int THREADS = G >= 16 ? 512 : 256;
     static constexpr int ROWS = THREADS / G;
@@ -829,7 +880,7 @@ template <int G> struct EdgeShape {
 template <typename T, int G, bool STRICT, bool HOSTC = false>
 __global__ void __launch_bounds__(EdgeShape<G>::THREADS, SX_EDGE_MINBLOCKS)
 spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ cols, const int *__restrict__ rowptr,
-                     const uint16_t *__restrict__ lcol, const T *__restrict__ val, const T *__restrict__ B0,
+                     const int *__restrict__ prow, const uint16_t *__restrict__ lcol, const T *__restrict__ val, const T *__restrict__ B0,
                      const uint32_t ldbv, const T *Cin0, T *Cout0, const uint32_t ldcv, const T alpha, const T beta,
                      const int nvec, const int flags, const uint32_t *ready, uint32_t *epoch, uint32_t *done_remote,
                      unsigned int *sync_words, const int npush, const PushList push, const int64_t push_n16,
@@ -866,15 +917,16 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
     const int ncols = b1.y;
     const uint32_t rowbytes = ldbv * 16u;                     // a row of the B image in global memory
     const uint32_t wbytes = (uint32_t)ncols * (G * 16u);      // a staged row: G vectors, whatever the image's leading dimension
-    const int jal = jb & ~7;
+    const int jal = jb;  // the block's slice of the row-aligned streams: [jb, je) in padded coordinates, multiples of 8
     const bool has = je > jb;
-    const uint32_t na = has ? (uint32_t)((je - jal + 7) & ~7) : 0u;
+    const uint32_t na = (uint32_t)(je - jb);
     const uint32_t ncp = (uint32_t)(ncols + 3) & ~3u;
     unsigned char *win = smem_raw;
     const T *sval = reinterpret_cast<const T *>(smem_raw + wbytes);
     const uint16_t *scol = reinterpret_cast<const uint16_t *>(smem_raw + wbytes + (size_t)na * sizeof(T));
     const int *scols = reinterpret_cast<const int *>(smem_raw + wbytes + (size_t)na * (sizeof(T) + 2));
-    int *srp = const_cast<int *>(scols) + ncp;  // row pointers of the block's rows, nrows + 1 of them
+    int *srp = const_cast<int *>(scols) + ncp;  // padded starts of the block's rows ...
+    int *send = srp + ((nrows + 4) & ~3);       // ... and where their entries end (start + length)
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -888,7 +940,11 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
         tma_bulk_g2s(const_cast<T *>(sval), val + jal, na * (uint32_t)sizeof(T), &bar, pol_a);
         tma_bulk_g2s(const_cast<uint16_t *>(scol), lcol + jal, na * 2u, &bar, pol_a);
     }
-    for (int i = threadIdx.x; i <= nrows; i += THREADS) srp[i] = __ldg(rowptr + row0 + i);
+    for (int i = threadIdx.x; i < nrows; i += THREADS) {
+        const int ps = __ldg(prow + row0 + i);
+        srp[i] = ps;
+        send[i] = ps + (__ldg(rowptr + row0 + i + 1) - __ldg(rowptr + row0 + i));
+    }
     T *tile = reinterpret_cast<T *>(smem_raw + tile_off);  // HOSTC: tile[column * tile_ld + row of the block]
     if (HOSTC) {
         // the caller's C_in, straight from its page-locked column-major array over PCIe: a warp per
@@ -978,7 +1034,7 @@ spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ co
     const V *w = reinterpret_cast<const V *>(win) + lg;  // w[local column * G] = this lane's piece of that B row
     if (lane_on)
         for (int rr = rl; rr < nrows; rr += ROWS) {
-            const int begin = srp[rr], end = srp[rr + 1];
+            const int begin = srp[rr], end = send[rr];
             V cin = cin_next;
             if (HOSTC) {
                 T *cp = reinterpret_cast<T *>(&cin);
@@ -1056,7 +1112,7 @@ constexpr int SX_HOST_MAX_GROUPS = 8;
 template <typename T, int G, bool STRICT>
 __global__ void __launch_bounds__(EdgeShape<G>::THREADS, 2)
 spmm_edgelist_host_kernel(const int4 *__restrict__ blocks, const int *__restrict__ cols, const int *__restrict__ rowptr,
-                          const uint16_t *__restrict__ lcol, const T *__restrict__ val, const T *Bh, T *Bimg,
+                          const int *__restrict__ prow, const uint16_t *__restrict__ lcol, const T *__restrict__ val, const T *Bh, T *Bimg,
                           const uint32_t ldbv, T *Ch, const int64_t M, const int64_t K, const int N, const T alpha,
                           const T beta, const int gw, uint32_t *counters, const uint32_t target, uint32_t *timeout_flag,
                           const uint32_t tile_off, const int tile_ld, const uint32_t share_off, const int share_ld, const int depth) {
@@ -1071,15 +1127,16 @@ spmm_edgelist_host_kernel(const int4 *__restrict__ blocks, const int *__restrict
     const int row0 = b0.x, nrows = b0.y, jb = b0.z, je = b0.w;
     const int ncols = b1.y;
     const uint32_t wbytes = (uint32_t)ncols * (G * 16u);
-    const int jal = jb & ~7;
+    const int jal = jb;
     const bool has = je > jb;
-    const uint32_t na = has ? (uint32_t)((je - jal + 7) & ~7) : 0u;
+    const uint32_t na = (uint32_t)(je - jb);
     const uint32_t ncp = (uint32_t)(ncols + 3) & ~3u;
     V *win = reinterpret_cast<V *>(smem_raw);
     const T *sval = reinterpret_cast<const T *>(smem_raw + wbytes);
     const uint16_t *scol = reinterpret_cast<const uint16_t *>(smem_raw + wbytes + (size_t)na * sizeof(T));
     const int *scols = reinterpret_cast<const int *>(smem_raw + wbytes + (size_t)na * (sizeof(T) + 2));
     int *srp = const_cast<int *>(scols) + ncp;
+    int *send = srp + ((nrows + 4) & ~3);
     T *tile = reinterpret_cast<T *>(smem_raw + tile_off);    // tile[column * tile_ld + row of the block]
     T *share = reinterpret_cast<T *>(smem_raw + share_off);  // share[column * share_ld + row of the share]
     if (threadIdx.x == 0) {
@@ -1109,7 +1166,11 @@ spmm_edgelist_host_kernel(const int4 *__restrict__ blocks, const int *__restrict
         cp_async_commit();
     };
     for (int g = 0; g < min(depth, ngroups); ++g) fetch_group(g);
-    for (int i = threadIdx.x; i <= nrows; i += THREADS) srp[i] = __ldg(rowptr + row0 + i);
+    for (int i = threadIdx.x; i < nrows; i += THREADS) {
+        const int ps = __ldg(prow + row0 + i);
+        srp[i] = ps;
+        send[i] = ps + (__ldg(rowptr + row0 + i + 1) - __ldg(rowptr + row0 + i));
+    }
     if (has) mbar_wait(&bar, 0);
     const T *sv = sval - jal;
     const uint16_t *sc = scol - jal;
@@ -1154,7 +1215,7 @@ spmm_edgelist_host_kernel(const int4 *__restrict__ blocks, const int *__restrict
                 T *cp = reinterpret_cast<T *>(&cin);
 #pragma unroll
                 for (int e = 0; e < E; ++e) cp[e] = (lg * E + e < N) ? tile[(lg * E + e) * tile_ld + rr] : T(0);
-                const V acc = edge_row_walk<T, G, STRICT>(sc, sv, win + lg, srp[rr], srp[rr + 1]);
+                const V acc = edge_row_walk<T, G, STRICT>(sc, sv, win + lg, srp[rr], send[rr]);
                 const V out = vaxpby<STRICT>(alpha, acc, beta, cin);
                 const T *op = reinterpret_cast<const T *>(&out);
 #pragma unroll

@@ -86,8 +86,8 @@ struct EdgePlan {
     bool usable = false;  // planned, and staging a block's distinct B rows beats gathering per nonzero
     int nblocks = 0, max_smem = 0, max_rows = 0;  // max_rows: most rows a block holds (the HOSTC tiles are sized by it)  // max_rows: most rows a block holds (the HOSTC tiles are sized by it)
     int64_t total_cols = 0;
-    DevBuf blocks, cols, lcol;
-    void release() { blocks.release(); cols.release(); lcol.release(); }
+    DevBuf blocks, cols, lcol, pval, prow;  // lcol / pval: the row-aligned (padded) streams of local columns and values; prow: padded row starts
+    void release() { blocks.release(); cols.release(); lcol.release(); pval.release(); prow.release(); }
 };
 
 struct sx_ctx {
@@ -286,7 +286,7 @@ int launch_edge(sx_ctx *c, const EdgePlan *ep, int N, T alpha, const T *dB, int6
     if (npub && (rc = ensure_sync_words(c))) return rc;
     const int64_t push_n16 = (int64_t)((size_t)c->K * (size_t)ldb * sizeof(T) / 16);
     SX_CUDA(cudaLaunchKernelEx(&cfg, kern, (const int4 *)ep->blocks.p, (const int *)ep->cols.p, (const int *)c->rowptr.p,
-                               (const uint16_t *)ep->lcol.p, (const T *)c->val.p, dB, (uint32_t)(ldb / E), dCin, dCout,
+                               (const int *)ep->prow.p, (const uint16_t *)ep->lcol.p, (const T *)ep->pval.p, dB, (uint32_t)(ldb / E), dCin, dCout,
                                (uint32_t)(ldc / E), alpha, beta, nvec, pf ? sx::SX_EDGE_PREFETCH : 0, c->x_ready, c->x_epoch,
                                c->x_done, (unsigned int *)c->sync_words.p, npush, c->p_list, push_n16, c->p_done, c->p_pushes,
                                Ch, (int64_t)c->M, N, (uint32_t)tile_off, tile_ld, nbatch > 1 ? c->batch_sB : (int64_t)0,
@@ -959,7 +959,9 @@ int get_edge_plan(sx_ctx *c, int row_bytes, int elem_bytes, int rows, const Edge
         }
     }
     std::vector<int32_t> ci((size_t)c->nnz);
+    std::vector<unsigned char> hv((size_t)c->nnz * (size_t)elem_bytes);  // the values, to lay them out row-aligned
     SX_CUDA(cudaMemcpyAsync(ci.data(), c->colidx.p, (size_t)c->nnz * 4, cudaMemcpyDeviceToHost, c->stream));
+    SX_CUDA(cudaMemcpyAsync(hv.data(), c->val.p, hv.size(), cudaMemcpyDeviceToHost, c->stream));
     SX_CUDA(cudaStreamSynchronize(c->stream));
     // Blocks of `rows` rows, one sweep of the lane groups.  (Cutting a small matrix by NONZEROS into
     // one block per SM -- the planner can: max_rows, nnz_target -- was measured and lost on nasa4704,
@@ -991,16 +993,16 @@ int get_edge_plan(sx_ctx *c, int row_bytes, int elem_bytes, int rows, const Edge
     // as many blocks per SM as leave every block uncut (6, 4, 3, 2 or 1); if even one block per SM
     // needs cuts, that plan is taken with its cuts
     int nb = 0, max_smem = 0, rc = SX_OK;
-    int32_t *blocks = nullptr, *cols = nullptr;
+    int32_t *blocks = nullptr, *cols = nullptr, *prow = nullptr;
     uint16_t *lcol = nullptr;
     int64_t total = 0, ncols = 0;
     int k_used = 1;
     for (int k : {6, 4, 3, 2, 1}) {
-        sx_free(blocks); sx_free(cols); sx_free(lcol);
-        blocks = cols = nullptr;
+        sx_free(blocks); sx_free(cols); sx_free(lcol); sx_free(prow);
+        blocks = cols = prow = nullptr;
         lcol = nullptr;
         rc = sx_plan_edge_lists(c->M, c->K, c->h_rowptr.data(), ci.data(), row_bytes, elem_bytes, max_rows, nnz_target,
-                                edge_budget(k), &nb, &blocks, &ncols, &cols, &lcol, &total, &max_smem);
+                                edge_budget(k), &nb, &blocks, &ncols, &cols, &lcol, &total, &max_smem, &prow);
         if (rc) return rc;
         k_used = k;
         if (nb == expect) break;
@@ -1010,11 +1012,21 @@ int get_edge_plan(sx_ctx *c, int row_bytes, int elem_bytes, int rows, const Edge
     // within +-2000 nodes, M = 1e6, 97 KB windows: 3.75 ms against 0.89 ms for the staged kernel).
     const bool fits = k_used >= 4 || (int64_t)nb <= (int64_t)4 * c->sm_count * k_used;
     if (nb > 0 && (c->kernel == 5 || (total * 2 <= c->nnz && fits))) {
+        // the values in the row-aligned layout of the plan: entry k of row r at prow[r] + k, pad entries 0
+        const size_t pnz = (size_t)prow[c->M];
+        std::vector<unsigned char> pv(std::max<size_t>(pnz, 8) * (size_t)elem_bytes, 0);
+        for (int r = 0; r < c->M; ++r) {
+            const size_t n = (size_t)(c->h_rowptr[r + 1] - c->h_rowptr[r]);
+            if (n) std::memcpy(pv.data() + (size_t)prow[r] * elem_bytes, hv.data() + (size_t)c->h_rowptr[r] * elem_bytes, n * elem_bytes);
+        }
         if (!(rc = p->blocks.ensure((size_t)nb * 32)) && !(rc = p->cols.ensure(std::max<size_t>((size_t)ncols * 4, 16))) &&
-            !(rc = p->lcol.ensure((size_t)c->nnz * 2 + 64))) {
+            !(rc = p->lcol.ensure(pnz * 2 + 64)) && !(rc = p->pval.ensure(pnz * elem_bytes + 64)) &&
+            !(rc = p->prow.ensure(((size_t)c->M + 1) * 4))) {
             if (cudaMemcpyAsync(p->blocks.p, blocks, (size_t)nb * 32, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
                 (ncols > 0 && cudaMemcpyAsync(p->cols.p, cols, (size_t)ncols * 4, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) ||
-                cudaMemcpyAsync(p->lcol.p, lcol, (size_t)c->nnz * 2, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+                (pnz > 0 && cudaMemcpyAsync(p->lcol.p, lcol, pnz * 2, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) ||
+                (pnz > 0 && cudaMemcpyAsync(p->pval.p, pv.data(), pnz * elem_bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) ||
+                cudaMemcpyAsync(p->prow.p, prow, ((size_t)c->M + 1) * 4, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
                 cudaStreamSynchronize(c->stream) != cudaSuccess)
                 rc = fail(SX_ERR_CUDA, "edge-list plan upload failed");
         }
@@ -1028,6 +1040,7 @@ int get_edge_plan(sx_ctx *c, int row_bytes, int elem_bytes, int rows, const Edge
     sx_free(blocks);
     sx_free(cols);
     sx_free(lcol);
+    sx_free(prow);
     return rc;
 }
 
@@ -1533,7 +1546,7 @@ int launch_edge_host(sx_ctx *c, const EdgePlan *ep, int N, T alpha, const T *Bh,
     cfg.attrs = at;
     cfg.numAttrs = c->host_coop != 0 ? 1 : 0;
     SX_CUDA(cudaLaunchKernelEx(&cfg, kern, (const int4 *)ep->blocks.p, (const int *)ep->cols.p, (const int *)c->rowptr.p,
-                               (const uint16_t *)ep->lcol.p, (const T *)c->val.p, Bh, (T *)c->B.p, (uint32_t)(c->ld / E), Ch,
+                               (const int *)ep->prow.p, (const uint16_t *)ep->lcol.p, (const T *)ep->pval.p, Bh, (T *)c->B.p, (uint32_t)(c->ld / E), Ch,
                                (int64_t)c->M, (int64_t)c->K, N, alpha, beta, gw, (uint32_t *)c->host_counters.p, target,
                                c->host_flag_dev, (uint32_t)tile_off, tile_ld, (uint32_t)share_off, share_ld,
                                c->host_depth > 0 ? std::min(c->host_depth, sx::SX_HOST_MAX_GROUPS) : 1));

@@ -638,10 +638,18 @@ int sx_plan_slide(int M, const int32_t *rowptr, const int32_t *colidx, int nchai
 // into that compacted window; blocks are cut so that they hold about the same number of
 // nonzeros.  On FEM-type matrices the compacted window is a third of the contiguous column span
 // (nasa4704: 142 distinct columns per 32 rows against a span of 456; pcrystk02: 317 against 918).
-//   blocks  8 ints per block: {row_begin, nrows, nnz_begin, nnz_end, col_begin, ncols, 0, smem_bytes}
+// The streams of A are ROW-ALIGNED: row r's entries start at prow[r], a multiple of 8 entries, and are padded to a
+// multiple of 8 (prow[r+1] - prow[r] = its length rounded up), so that the kernel fetches a chunk of 8 (local column,
+// value) pairs with whole 16-byte shared-memory loads -- 1 + 4 loads instead of 8 + 8 for fp64 -- next to the 8 loads
+// of B pieces; the additions of the pad entries are predicated off (the reference's bubbles, src/sparse_helper.h:345-403,
+// without their arithmetic).
+//   blocks  8 ints per block: {row_begin, nrows, pnz_begin, pnz_end, col_begin, ncols, 0, smem_bytes}, pnz in PADDED
+//           coordinates: prow[row_begin], prow[row_begin + nrows]
 //   cols    the blocks' column lists, back to back, each starting at a multiple of 4 entries
 //           (16 bytes: the list travels to shared memory by TMA); pad entries repeat the last column
-//   lcol    nnz 16-bit local column indices, parallel to colidx
+//   prow    M + 1 padded row starts
+//   lcol    prow[M] 16-bit local column indices: entry k of row r at prow[r] + k, pad entries 0 (a valid local
+//           column whenever the row has entries)
 // A block is closed when it holds max_rows rows, when its nonzeros reach nnz_target (0: no such
 // limit; compared at the row that brings it closest), or when the next row would not fit the
 // shared-memory budget; a single row that does not fit makes the matrix unplannable (*nblocks =
@@ -649,14 +657,14 @@ int sx_plan_slide(int M, const int32_t *rowptr, const int32_t *colidx, int nchai
 int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colidx, int row_bytes, int elem_bytes,
                        int max_rows, int64_t nnz_target, int smem_budget, int *nblocks_out, int32_t **blocks_out,
                        int64_t *ncols_out, int32_t **cols_out, uint16_t **lcol_out, int64_t *total_cols_out,
-                       int *max_smem_out) {
-    if (!nblocks_out || !blocks_out || !ncols_out || !cols_out || !lcol_out || !total_cols_out || !max_smem_out) {
+                       int *max_smem_out, int32_t **prow_out) {
+    if (!nblocks_out || !blocks_out || !ncols_out || !cols_out || !lcol_out || !total_cols_out || !max_smem_out || !prow_out) {
         sx_internal_set_error("sx_plan_edge_lists: null output pointer");
         return SX_ERR_INVALID;
     }
     *nblocks_out = *max_smem_out = 0;
     *ncols_out = *total_cols_out = 0;
-    *blocks_out = *cols_out = nullptr;
+    *blocks_out = *cols_out = *prow_out = nullptr;
     *lcol_out = nullptr;
     if (M < 0 || K < 0 || !rowptr || (M > 0 && rowptr[M] > 0 && !colidx) || row_bytes < 16 || row_bytes % 16 ||
         (elem_bytes != 4 && elem_bytes != 8) || smem_budget < 1024 || max_rows < 1 || max_rows > 4096 || nnz_target < 0) {
@@ -667,17 +675,30 @@ int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colid
     constexpr int SG = 4096;  // rows per super-group: cuts restart here
     const int64_t nnz = rowptr[M];
     const int ngroups = (M + SG - 1) / SG;
-    // shared memory of a block: window | values | local columns | column list | row pointers (the A
-    // slice starts at the 8-entry boundary at or below nnz_begin: both streams are whole 16-byte units)
-    auto smem_of = [&](int ncols, int nrows, int jb, int je) -> int64_t {
-        const int64_t na = je > jb ? (int64_t)((je - (jb & ~7) + 7) & ~7) : 0;
-        return (int64_t)ncols * row_bytes + na * elem_bytes + na * 2 + (int64_t)((ncols + 3) & ~3) * 4 + (int64_t)((nrows + 4) & ~3) * 4;
+    // padded row starts
+    int32_t *prow = (int32_t *)std::malloc(((size_t)M + 1) * sizeof(int32_t));
+    if (!prow) { sx_internal_set_error("sx_plan_edge_lists: out of host memory"); return SX_ERR_NOMEM; }
+    {
+        int64_t at = 0;
+        for (int r = 0; r < M; ++r) {
+            prow[r] = (int32_t)at;
+            at += ((int64_t)(rowptr[r + 1] - rowptr[r]) + 7) & ~(int64_t)7;
+            if (at > INT32_MAX - 8) { std::free(prow); return SX_OK; }  // not plannable: the caller keeps its other kernels
+        }
+        prow[M] = (int32_t)at;
+    }
+    const int64_t pnz = prow[M];
+    // shared memory of a block: window | values | local columns | column list | padded row starts | row ends
+    // (pb, pe in padded coordinates: both streams are whole 16-byte units)
+    auto smem_of = [&](int ncols, int nrows, int pb, int pe) -> int64_t {
+        const int64_t na = pe - pb;
+        return (int64_t)ncols * row_bytes + na * elem_bytes + na * 2 + (int64_t)((ncols + 3) & ~3) * 4 + 2 * (int64_t)((nrows + 4) & ~3) * 4;
     };
     struct Part { std::vector<int32_t> blocks, cols; int64_t total = 0; int max_smem = 0; bool ok = true; };
     const unsigned nt = (unsigned)std::min<int64_t>(nnz < (1 << 18) ? 1 : std::min(sxhost::host_threads(), 16u), ngroups);  // 6 bytes x K of scratch per thread
     std::vector<Part> parts(nt);
-    uint16_t *lcol = (uint16_t *)std::malloc(std::max<size_t>((size_t)nnz, 8) * sizeof(uint16_t));
-    if (!lcol) { sx_internal_set_error("sx_plan_edge_lists: out of host memory"); return SX_ERR_NOMEM; }
+    uint16_t *lcol = (uint16_t *)std::calloc(std::max<size_t>((size_t)pnz, 8), sizeof(uint16_t));  // pad entries: 0
+    if (!lcol) { std::free(prow); sx_internal_set_error("sx_plan_edge_lists: out of host memory"); return SX_ERR_NOMEM; }
     sxhost::parallel_for(nt, [&](unsigned t) {
         Part &P = parts[t];
         std::vector<int32_t> stamp((size_t)K, -1), cols;
@@ -700,7 +721,7 @@ int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colid
                     int fresh = 0;
                     for (int32_t j = rowptr[r]; j < rowptr[r + 1]; ++j)
                         if (stamp[colidx[j]] != tag) { stamp[colidx[j]] = tag; cols.push_back(colidx[j]); ++fresh; }
-                    if (smem_of(ncols + fresh, r - rb + 1, jb, rowptr[r + 1]) > smem_budget || ncols + fresh > 65535) {
+                    if (smem_of(ncols + fresh, r - rb + 1, prow[rb], prow[r + 1]) > smem_budget || ncols + fresh > 65535) {
                         if (r == rb) { P.ok = false; break; }  // one row alone does not fit
                         for (int k = 0; k < fresh; ++k) { stamp[cols.back()] = -1; cols.pop_back(); }
                         break;
@@ -709,12 +730,12 @@ int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colid
                     ++r;
                 }
                 if (!P.ok) break;
-                const int je = rowptr[r];
                 std::sort(cols.begin(), cols.end());
                 for (int i = 0; i < ncols; ++i) local[cols[i]] = (uint16_t)i;
-                for (int32_t j = jb; j < je; ++j) lcol[j] = local[colidx[j]];
-                const int sm = (int)smem_of(ncols, r - rb, jb, je);
-                P.blocks.insert(P.blocks.end(), {rb, r - rb, jb, je, (int32_t)P.cols.size(), ncols, 0, sm});
+                for (int rr = rb; rr < r; ++rr)
+                    for (int32_t j = rowptr[rr]; j < rowptr[rr + 1]; ++j) lcol[prow[rr] + (j - rowptr[rr])] = local[colidx[j]];
+                const int sm = (int)smem_of(ncols, r - rb, prow[rb], prow[r]);
+                P.blocks.insert(P.blocks.end(), {rb, r - rb, prow[rb], prow[r], (int32_t)P.cols.size(), ncols, 0, sm});
                 P.cols.insert(P.cols.end(), cols.begin(), cols.end());
                 while (P.cols.size() % 4) P.cols.push_back(ncols ? cols.back() : 0);
                 P.total += ncols;
@@ -727,12 +748,13 @@ int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colid
     for (const Part &P : parts) { ok = ok && P.ok; nb += P.blocks.size() / 8; nc += P.cols.size(); }
     if (!ok || nb > (size_t)INT32_MAX || nc > (size_t)INT32_MAX) {
         std::free(lcol);
+        std::free(prow);
         return SX_OK;  // not plannable with this budget: the caller keeps its other kernels
     }
     int32_t *blocks = (int32_t *)std::malloc(std::max<size_t>(nb, 1) * 8 * sizeof(int32_t));
     int32_t *cols = (int32_t *)std::malloc(std::max<size_t>(nc, 4) * sizeof(int32_t));
     if (!blocks || !cols) {
-        std::free(blocks); std::free(cols); std::free(lcol);
+        std::free(blocks); std::free(cols); std::free(lcol); std::free(prow);
         sx_internal_set_error("sx_plan_edge_lists: out of host memory");
         return SX_ERR_NOMEM;
     }
@@ -755,6 +777,7 @@ int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colid
     *ncols_out = (int64_t)nc;
     *cols_out = cols;
     *lcol_out = lcol;
+    *prow_out = prow;
     *total_cols_out = total;
     *max_smem_out = max_smem;
     return SX_OK;

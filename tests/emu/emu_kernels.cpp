@@ -24,7 +24,7 @@ int sx_plan_slide(int M, const int32_t *rowptr, const int32_t *colidx, int nchai
                   int *nchains, int32_t **chains, int *ring_rows, int *max_step_entries);
 int sx_plan_edge_lists(int M, int K, const int32_t *rowptr, const int32_t *colidx, int row_bytes, int elem_bytes,
                        int max_rows, int64_t nnz_target, int smem_budget, int *nblocks, int32_t **blocks, int64_t *ncols,
-                       int32_t **cols, uint16_t **lcol, int64_t *total_cols, int *max_smem);
+                       int32_t **cols, uint16_t **lcol, int64_t *total_cols, int *max_smem, int32_t **prow);
 void sx_free(void *);
 }
 
@@ -567,12 +567,13 @@ void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, u
     int nb = 0, max_smem = 0;
     int32_t *blocks = nullptr, *cols = nullptr;
     uint16_t *lcol = nullptr;
+    int32_t *prow = nullptr;
     int64_t total = 0, ncols = 0;
     // every other case cuts by nonzeros with up to 4 sweeps of the lane groups (what sx_api.cu does for small matrices)
     const int max_rows = (seed & 1) ? 4 * ROWS : ROWS;
     const int64_t nnz_target = (seed & 1) ? std::max(8, a.rp[M] / 5) : 0;
     if (sx_plan_edge_lists(M, K, a.rp.data(), a.ci.data(), G * 16, (int)sizeof(T), max_rows, nnz_target, budget, &nb, &blocks,
-                           &ncols, &cols, &lcol, &total, &max_smem) != 0) {
+                           &ncols, &cols, &lcol, &total, &max_smem, &prow) != 0) {
         std::printf("edge lists: plan FAILED\n");
         ++failures;
         return;
@@ -581,24 +582,37 @@ void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, u
     std::snprintf(what, sizeof what, "edge lists (variant 5)%s%s", shuffle_rows ? " unsorted" : "", with_flags ? " +flags" : "");
     if (nb == 0) {
         std::printf("%-34s %s M=%d K=%d N=%d G=%d budget=%d: not plannable (a row exceeds the budget)\n", what, tname, M, K, N, G, budget);
+        sx_free(prow);
         return;
     }
     // device copies at exactly the product's sizes and pads (sx_api.cu: get_edge_plan, upload_csr)
     Aligned<int> dblocks((size_t)nb * 8), dcols((size_t)std::max<int64_t>(ncols, 4));
-    Aligned<uint16_t> dlcol((size_t)nnz, 64);
+    // the row-aligned streams: entry k of row r at prow[r] + k, rows padded to multiples of 8 entries (pad: column 0, value 0)
+    const int pnz = prow[M];
+    Aligned<uint16_t> dlcol((size_t)pnz, 64);
+    Aligned<T> pval((size_t)pnz, 64);
+    Aligned<int> dprow((size_t)M + 1);
     std::copy(blocks, blocks + (size_t)nb * 8, dblocks.p);
     std::copy(cols, cols + ncols, dcols.p);
-    std::copy(lcol, lcol + nnz, dlcol.p);
+    std::copy(lcol, lcol + pnz, dlcol.p);
+    std::copy(prow, prow + M + 1, dprow.p);
+    for (int r = 0; r < M; ++r)
+        for (int k = 0; k < a.rp[r + 1] - a.rp[r]; ++k) pval.p[prow[r] + k] = hval[a.rp[r] + k];
     // plan invariants: blocks tile the rows in order, every nonzero's local column names its column
     bool plan_ok = true;
     int next_row = 0;
     for (int b = 0; b < nb && plan_ok; ++b) {
         const int32_t *r = blocks + (size_t)b * 8;
-        plan_ok = r[0] == next_row && r[1] >= 1 && r[1] <= max_rows && r[2] == a.rp[r[0]] && r[3] == a.rp[r[0] + r[1]] &&
-                  r[4] % 4 == 0 && r[7] <= budget && r[7] <= max_smem;
+        plan_ok = r[0] == next_row && r[1] >= 1 && r[1] <= max_rows && r[2] == prow[r[0]] && r[3] == prow[r[0] + r[1]] &&
+                  r[2] % 8 == 0 && r[3] % 8 == 0 && r[4] % 4 == 0 && r[7] <= budget && r[7] <= max_smem;
         next_row = r[0] + r[1];
         for (int i = 1; i < r[5] && plan_ok; ++i) plan_ok = cols[r[4] + i] > cols[r[4] + i - 1];
-        for (int j = r[2]; j < r[3] && plan_ok; ++j) plan_ok = lcol[j] < r[5] && cols[r[4] + lcol[j]] == a.ci[j];
+        for (int rr = r[0]; rr < r[0] + r[1] && plan_ok; ++rr) {
+            const int n = a.rp[rr + 1] - a.rp[rr];
+            plan_ok = prow[rr + 1] - prow[rr] == ((n + 7) & ~7);
+            for (int k = 0; k < n && plan_ok; ++k) plan_ok = lcol[prow[rr] + k] < r[5] && cols[r[4] + lcol[prow[rr] + k]] == a.ci[a.rp[rr] + k];
+            for (int k = n; k < prow[rr + 1] - prow[rr] && plan_ok; ++k) plan_ok = lcol[prow[rr] + k] == 0;
+        }
     }
     plan_ok = plan_ok && next_row == M;
     if (!plan_ok) { std::printf("%-34s %s M=%d N=%d: PLAN INVARIANT MISMATCH\n", what, tname, M, N); ++failures; }
@@ -627,7 +641,7 @@ void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, u
     publist.ready[1] = dflags.p + 2;
     sx_emu::launch((unsigned)nb, THREADS, (size_t)std::max(max_smem, 16), [&] {
         sx::spmm_edgelist_kernel<T, G, true>(reinterpret_cast<const int4 *>(dblocks.p), dcols.p,
-                                             rp.p, dlcol.p, val.p, B.p, ldv, Cin.p, Cout.p, ldv, alpha, beta, nvec,
+                                             rp.p, dprow.p, dlcol.p, pval.p, B.p, ldv, Cin.p, Cout.p, ldv, alpha, beta, nvec,
                                              sx::SX_EDGE_PREFETCH, with_flags ? flags.p : nullptr, flags.p + 1, flags.p + 2,
                                              flags.p + 4, with_flags ? 2 : 0, plist, (int64_t)((size_t)K * ld * sizeof(T) / 16),
                                              pflags.p, pflags.p + 2, nullptr, 0, N, 0u, 0, 0, 0, publist, with_flags ? 2 : 0, dflags.p);
@@ -655,7 +669,7 @@ void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, u
         const int tile_ld = max_rows + 1;
         const size_t tile_off = ((size_t)std::max(max_smem, 16) + 15) & ~(size_t)15;
         sx_emu::launch((unsigned)nb, THREADS, tile_off + (size_t)N * tile_ld * sizeof(T), [&] {
-            sx::spmm_edgelist_kernel<T, G, true, true>(reinterpret_cast<const int4 *>(dblocks.p), dcols.p, rp.p, dlcol.p, val.p,
+            sx::spmm_edgelist_kernel<T, G, true, true>(reinterpret_cast<const int4 *>(dblocks.p), dcols.p, rp.p, dprow.p, dlcol.p, pval.p,
                                                        B.p, ldv, nullptr, nullptr, ldv, alpha, beta, nvec, sx::SX_EDGE_PREFETCH,
                                                        nullptr, nullptr, nullptr, flags.p + 4, 0, plist, 0, nullptr, nullptr,
                                                        Ch.p, (int64_t)M, N, (uint32_t)tile_off, tile_ld, 0, 0, sx::PubList{}, 0, nullptr);
@@ -687,7 +701,7 @@ void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, u
                 for (int n = 0; n < N; ++n) Ch.p[(size_t)M * n + i] = Cin.p[(int64_t)i * ld + n];
             if (pass == 0) std::fill(Bimg.p, Bimg.p + (int64_t)K * ld, (T)777);
             sx_emu::launch((unsigned)nb, THREADS, smem, [&] {
-                sx::spmm_edgelist_host_kernel<T, G, true>(reinterpret_cast<const int4 *>(dblocks.p), dcols.p, rp.p, dlcol.p, val.p,
+                sx::spmm_edgelist_host_kernel<T, G, true>(reinterpret_cast<const int4 *>(dblocks.p), dcols.p, rp.p, dprow.p, dlcol.p, pval.p,
                                                           Bh.p, Bimg.p, ldv, Ch.p, (int64_t)M, (int64_t)K, N, alpha, beta, gw,
                                                           counters.p, 0u, tflag.p, (uint32_t)tile_off, tile_ld, (uint32_t)share_off, share_ld, 1 + (int)(seed % 3));
             });
@@ -704,6 +718,7 @@ void edge_case(const char *tname, Csr a, int N, int budget, bool shuffle_rows, u
     sx_free(blocks);
     sx_free(cols);
     sx_free(lcol);
+    sx_free(prow);
 }
 
 template <typename T>
