@@ -878,7 +878,7 @@ template <int G> struct EdgeShape {
 #define SX_EDGE_MINBLOCKS 2
 #endif
 template <typename T, int G, bool STRICT, bool HOSTC = false>
-__global__ void __launch_bounds__(EdgeShape<G>::THREADS, SX_EDGE_MINBLOCKS)
+__global__ void __launch_bounds__(EdgeShape<G>::THREADS, (G >= 16 ? 2 : SX_EDGE_MINBLOCKS))
 spmm_edgelist_kernel(const int4 *__restrict__ blocks, const int *__restrict__ cols, const int *__restrict__ rowptr,
                      const int *__restrict__ prow, const uint16_t *__restrict__ lcol, const T *__restrict__ val, const T *__restrict__ B0,
                      const uint32_t ldbv, const T *Cin0, T *Cout0, const uint32_t ldcv, const T alpha, const T beta,
