@@ -702,7 +702,7 @@ spmm_window_kernel(const int M, const int4 *__restrict__ blocks, const int *__re
 // nasa4704 4.40 against 3.68 us, pcrystk02 N=16 9.4 against 7.0 us -- a third of the lane groups
 // doing three times the work lengthens the dependent chains more than the saved LDS traffic buys.
 // Reverted; the planner and kernel are in the history.)
-// 256 threads per block (512 for 16-lane groups), i.e. ROWS = 128 / 64 / 32 / 32 lane groups for G = 2 / 4 / 8 / 16;
+// 256 threads per block (128 for 2-lane, 512 for 16-lane groups), i.e. ROWS = 64 / 64 / 32 / 32 lane groups for G = 2 / 4 / 8 / 16;
 // a lane group takes rows rl, rl + ROWS, ... of its block (blocks are cut by nonzeros, not by rows: a
 // small matrix becomes one block per SM with equal work, the reference's equal-length PE lists).
 //
@@ -870,7 +870,9 @@ __device__ __forceinline__ typename VecOf<T>::type edge_row_walk(const uint16_t 
     return acc;
 }
 template <int G> struct EdgeShape {
-    static constexpr int THREADS = G >= 16 ? 512 : 256;
+    // 2-lane groups (32-byte dense rows) in 128-thread blocks: 64 rows per block instead of 128 -- twice the blocks for the
+    // same matrix (nasa4704 N=4 fp64 3.54 -> 3.12 us, N=8 fp32 3.49 -> 3.28; pcrystk02 N=8 unchanged at 6.0 us)
+    static constexpr int THREADS = G >= 16 ? 512 : (G == 2 ? 128 : 256);
     static constexpr int ROWS = THREADS / G;
 };
 // blocks per SM the register allocation of the edge-list kernel is held to (build-time knob for A/B runs)

@@ -1575,7 +1575,7 @@ int spmm_host_fused(sx_ctx *c, int N, T alpha, const void *dB, T beta, void *dC,
     if (!pick_shape(nvec, &s) || s.G > 16 || s.VPL != 1) return SX_OK;
     int rc;
     if ((rc = set_columns(c, N))) return rc;
-    const int rows = s.G >= 16 ? 32 : 256 / s.G;  // sx::EdgeShape<G>::ROWS
+    const int rows = s.G >= 16 ? 32 : (s.G == 2 ? sx::EdgeShape<2>::ROWS : 256 / s.G);  // sx::EdgeShape<G>::ROWS
     const EdgePlan *ep = nullptr;
     if ((rc = get_edge_plan(c, s.G * 16, (int)sizeof(T), rows, &ep))) return rc;
     if (!ep || !ep->usable) return SX_OK;
@@ -1678,7 +1678,7 @@ int spmm_host_deviceB(sx_ctx *c, int N, T alpha, T beta, T *C) {
     Shape s;
     if (c->host_fused != 0 && c->tile_steps == 0 && c->wins.empty() && c->M > 0 && (c->kernel == 0 || c->kernel == 5) &&
         bytes <= (size_t)c->zerocopy_bytes && pick_shape(nvec, &s) && s.G <= 16 && s.VPL == 1 && (dC = mapped_alias(C))) {
-        const int rows = s.G >= 16 ? 32 : 256 / s.G;
+        const int rows = s.G >= 16 ? 32 : (s.G == 2 ? sx::EdgeShape<2>::ROWS : 256 / s.G);
         const EdgePlan *ep = nullptr;
         if ((rc = get_edge_plan(c, s.G * 16, (int)sizeof(T), rows, &ep))) return rc;
         if (ep && ep->usable) {
